@@ -1,0 +1,222 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/* by running the UNMODIFIED reference on the CPU.
+
+Run in the build container only (needs /root/reference):
+    python -m oracle.gen_golden
+Everything written is small (< 200 KB total) and committed. The inputs are
+regenerated from seeds by the tests (vpd_b200/synth.py), so only reference
+OUTPUTS (and hashes of large ones) are stored.
+"""
+import hashlib
+import json
+import os
+import random
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim                      # noqa: E402
+from vpd_b200 import synth                       # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def sha(t):
+    if isinstance(t, torch.Tensor):
+        t = t.detach().contiguous().numpy()
+    return hashlib.sha256(np.ascontiguousarray(t).tobytes()).hexdigest()
+
+
+def sd_hash(sd):
+    h = hashlib.sha256()
+    for k, v in sd.items():
+        h.update(k.encode())
+        h.update(np.ascontiguousarray(v.detach().numpy()).tobytes())
+    return h.hexdigest()
+
+
+def write_crop_dir(root, video, rgb, flow, flow_name='flow'):
+    import cv2
+    d = os.path.join(root, video)
+    os.makedirs(d, exist_ok=True)
+    for i in range(rgb.shape[0]):
+        cv2.imwrite(os.path.join(d, '{}.png'.format(i)),
+                    cv2.cvtColor(rgb[i].numpy(), cv2.COLOR_RGB2BGR))
+        cv2.imwrite(os.path.join(d, '{}.{}.png'.format(i, flow_name)), flow[i].numpy())
+
+
+def gen_assembly(ref):
+    """A1-A4: FrameDataset / GenericDataset on PNGs of synthetic crops."""
+    out = {}
+    tmp = tempfile.mkdtemp()
+    try:
+        # -- per-dataset LUTs through the real _load_image/_load_flow ------
+        ramp = torch.arange(256, dtype=torch.uint8).view(16, 16, 1).repeat(1, 1, 3)
+        write_crop_dir(tmp, 'ramp', ramp[None], ramp[None])
+        luts = {}
+        for name, ms in ref.RGB_MEAN_STD.items():
+            ds = ref.FrameDataset([(0, 0, os.path.join(tmp, 'ramp', '0'))], 16, ms,
+                                  flow_img_name='flow')
+            img = ds[0]['img'][0].numpy()                 # [5,16,16]
+            luts[name] = img.reshape(5, 256)
+        out['lut_names'] = np.array(sorted(luts))
+        out['luts'] = np.stack([luts[k] for k in sorted(luts)])
+
+        # -- apply path, 32x32, flip on / off ------------------------------
+        rgb, flow = synth.crops(4, seed=11, height=32, width=32)
+        write_crop_dir(tmp, 'v32', rgb, flow)
+        ms = ref.RGB_MEAN_STD['fs']
+        tasks = [(0, i, os.path.join(tmp, 'v32', str(i))) for i in range(4)]
+        ds = ref.FrameDataset(tasks, 32, ms, augment_flip=True, flow_img_name='flow')
+        out['apply_flip'] = torch.stack([ds[i]['img'] for i in range(4)]).numpy()
+        ds = ref.FrameDataset(tasks, 32, ms, augment_flip=False, flow_img_name='flow')
+        out['apply_noflip'] = torch.stack([ds[i]['img'] for i in range(4)]).numpy()
+        ds = ref.FrameDataset(tasks, 32, ms, augment_flip=True, flow_img_name=None)
+        out['apply_flip_rgbonly'] = torch.stack([ds[i]['img'] for i in range(4)]).numpy()
+
+        # -- train path: GenericDataset.__getitem__ with the stochastic
+        #    augmentations neutralised (no jitter in the transform, identity
+        #    crop, no mask png) and the flip bit forced --------------------
+        teach = synth.teacher(4, seed=12, emb_dim=8, motion=True).numpy()
+        data = [('v32', i, teach[i], {}) for i in range(4)]
+        gd = ref.GenericDataset(data, tmp, 32, ms, 4, augment=False,
+                                flow_img_name='flow')
+        gd.augment = True                      # enables the flip branch only:
+        gd._random_crop = lambda im: im        # transform was built w/o jitter
+        flips = [0, 1, 1, 0]
+        imgs, embs = [], []
+        sf = ref.single_frame
+        orig_choice, orig_bits = random.choice, random.getrandbits
+        try:
+            for i in range(4):
+                random.choice = lambda seq, i=i: seq[i]
+                random.getrandbits = lambda k, i=i: flips[i]
+                item = gd[0]
+                imgs.append(item['img'])
+                embs.append(item['emb'])
+        finally:
+            random.choice, random.getrandbits = orig_choice, orig_bits
+        out['train_flips'] = np.array(flips, dtype=np.uint8)
+        out['train_img'] = torch.stack(imgs).numpy()
+        out['train_emb'] = torch.stack(embs).numpy()
+
+        # -- one full-size frame, hash only ---------------------------------
+        rgb, flow = synth.crops(1, seed=13)
+        write_crop_dir(tmp, 'v128', rgb, flow)
+        ds = ref.FrameDataset([(0, 0, os.path.join(tmp, 'v128', '0'))], 128, ms,
+                              augment_flip=True, flow_img_name='flow')
+        out['apply128_sha256'] = np.array(sha(ds[0]['img']))
+    finally:
+        shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(GOLD, 'assembly.npz'), **out)
+    print('assembly.npz written')
+
+
+def gen_student(ref):
+    """A5-A10: constructor, embed, train steps, loss curve."""
+    meta = {}
+    D = 32
+    torch.manual_seed(0)
+    enc = ref.RGBF_EmbeddingModel('resnet34', D, True, 'cpu')
+    trainer = ref.ModelTrainer(enc, True)
+    meta['init_seed'] = 0
+    meta['encoder_init_sha256'] = sd_hash(enc.state_dict())
+    meta['decoder_init_sha256'] = sd_hash(trainer.fcn_time.state_dict())
+    torch.manual_seed(5)
+    enc18 = ref.RGBF_EmbeddingModel('resnet18', 26, False, 'cpu')
+    meta['resnet18_rgb_D26_seed5_sha256'] = sd_hash(enc18.state_dict())
+
+    # eval-mode embed with non-trivial BN buffers
+    from oracle.student_ref import randomize_bn_state
+    sd = randomize_bn_state(enc.state_dict(), seed=21)
+    enc.load_state_dict(sd)
+    rgb, flow = synth.crops(4, seed=22)
+    from oracle import assemble_ref
+    x = assemble_ref.apply_batch(rgb.numpy(), flow.numpy(), *synth.FS_MEAN_STD,
+                                 flip=True).view(-1, 5, 128, 128)
+    emb = enc.embed(x)
+    arrays = {'embed_out': emb}
+
+    # two training steps through ModelTrainer.epoch (B=8), losses + checksums
+    torch.manual_seed(0)
+    enc = ref.RGBF_EmbeddingModel('resnet34', D, True, 'cpu')
+    trainer = ref.ModelTrainer(enc, True)
+    opt, scaler = trainer.get_optimizer(5e-4)
+    assert scaler is None
+    B, steps = 8, 200
+    rgb, flow = synth.crops(64, seed=1)
+    teach = synth.teacher(64, seed=3, emb_dim=D, motion=True)
+    fl = synth.flips(steps * B, seed=2)
+    idx_g = torch.Generator().manual_seed(4)
+    idx = torch.randint(0, 64, (steps * B,), generator=idx_g)
+    losses = []
+    for s in range(steps):
+        sel = idx[s * B:(s + 1) * B]
+        f = fl[s * B:(s + 1) * B]
+        img, tgt = assemble_ref.train_batch(
+            rgb[sel].numpy(), flow[sel].numpy(), teach[sel].numpy(), f.numpy(),
+            *synth.FS_MEAN_STD)
+        if s == 0:
+            # gradients of the very first step, before the optimizer touches anything
+            enc.train(); trainer.fcn_time.train()
+            import copy
+            enc2 = copy.deepcopy(enc); dec2 = copy.deepcopy(trainer.fcn_time)
+            out = dec2(enc2(img))
+            l0 = torch.nn.functional.mse_loss(out, tgt, reduction='sum')
+            l0.backward()
+            names = [n for n, _ in enc2.named_parameters()] + \
+                    ['decoder.' + n for n, _ in dec2.named_parameters()]
+            params = list(enc2.parameters()) + list(dec2.parameters())
+            arrays['step0_out'] = out.detach().numpy()
+            arrays['step0_grad_norms'] = np.array(
+                [p.grad.norm().item() for p in params], dtype=np.float64)
+            arrays['step0_grad_fc'] = enc2.resnet.fc.weight.grad.numpy()
+            arrays['step0_grad_conv1'] = enc2.resnet.conv1.weight.grad.numpy()
+            arrays['step0_grad_l4'] = enc2.resnet.layer4[2].conv2.weight.grad[:8, :8].numpy()
+            meta['param_names'] = names
+        loss = trainer.epoch([{'img': img, 'emb': tgt}], optimizer=opt, scaler=scaler)
+        losses.append(loss)
+        if s in (0, 1):
+            meta['step{}_state_sha256'.format(s)] = sd_hash(enc.state_dict())
+            arrays['step{}_fc_weight'.format(s)] = enc.resnet.fc.weight.detach().numpy().copy()
+            arrays['step{}_bn1_running_var'.format(s)] = enc.resnet.bn1.running_var.numpy().copy()
+        if s % 20 == 0:
+            print('step', s, 'loss/frame', loss, flush=True)
+    arrays['loss_curve'] = np.array(losses, dtype=np.float64)
+    meta['loss_curve'] = {'batch': B, 'steps': steps, 'lr': 5e-4, 'pool': 64,
+                          'seeds': {'crops': 1, 'flips': 2, 'teacher': 3, 'index': 4}}
+    # eval-mode loss on a fixed batch after training (exercises running stats)
+    sel = torch.arange(8)
+    img, tgt = assemble_ref.train_batch(rgb[sel].numpy(), flow[sel].numpy(),
+                                        teach[sel].numpy(), np.zeros(8, np.uint8),
+                                        *synth.FS_MEAN_STD)
+    meta['final_eval_loss'] = trainer.epoch([{'img': img, 'emb': tgt}])
+    np.savez_compressed(os.path.join(GOLD, 'student.npz'), **arrays)
+    with open(os.path.join(GOLD, 'student.json'), 'w') as fp:
+        json.dump(meta, fp, indent=1)
+    print('student.npz / student.json written')
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    ref = ref_shim.load()
+    torch.set_num_threads(os.cpu_count())
+    which = sys.argv[1:] or ['assembly', 'student']
+    if 'assembly' in which:
+        gen_assembly(ref)
+    if 'student' in which:
+        gen_student(ref)
+    with open(os.path.join(GOLD, 'README.md'), 'w') as fp:
+        fp.write('Golden vectors produced by `python -m oracle.gen_golden` from the unmodified\n'
+                 'reference at /root/reference (torch {}, CPU fp32). Inputs are regenerated\n'
+                 'from seeds by vpd_b200/synth.py; see oracle/gen_golden.py.\n'.format(
+                     torch.__version__))
+
+
+if __name__ == '__main__':
+    main()
