@@ -1,0 +1,100 @@
+/* vpd_b200 - C ABI of the B200-native VPD student hot path.
+ *
+ * The reference (jhong93/vpd) is pure Python/PyTorch and has no FFI layer; its
+ * boundary for this path is the Python object API of models/rgb.py:46-86
+ * (RGBF_EmbeddingModel), train_vpd_model.py:53-112 (ModelTrainer) and
+ * apply_vpd_model.py:152-178. `vpd_b200/` mirrors that API in Python and binds
+ * the functions below with ctypes (vpd_b200/_lib.py); INTEGRATION.md shows the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a raw CUDA device pointer unless marked "host";
+ *   - `stream` is a cudaStream_t passed as void*; no function synchronises it;
+ *   - return value 0 = ok, non-zero = error, message via vpd_last_error()
+ *     (thread-local, valid until the next failing call on that thread);
+ *   - nothing here allocates device memory: callers own every buffer
+ *     (vpd_net_workspace_bytes tells how much scratch a network needs);
+ *   - activations inside the network are NHWC bf16, parameters and gradients
+ *     are fp32 in the reference's own state_dict layout (OIHW conv weights).
+ */
+#ifndef VPD_B200_H_
+#define VPD_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define VPD_API __attribute__((visibility("default")))
+#else
+#define VPD_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+VPD_API const char* vpd_last_error(void);
+VPD_API int vpd_abi_version(void);
+
+/* ---- K1: frame-batch assembly ------------------------------------------------
+ * Replaces vpd_dataset/common.py:52-69 (_load_image/_load_flow arithmetic),
+ * vpd_dataset/single_frame.py:168-206 (GenericDataset.__getitem__, deterministic
+ * part: teacher-row select by flip bit, RGB+flow stack, horizontal flip with
+ * flow-x negation) and :373-400 (FrameDataset.__getitem__, [orig, flipped]).
+ *   rgb      uint8 [pool][H][W][3]  (RGB order, i.e. after cv2 BGR2RGB)
+ *   flow     uint8 [pool][H][W][flow_channels] or NULL (RGB-only model)
+ *   index    int32 [B] pool index per output frame, or NULL (frame b = pool b)
+ *   flip     uint8 [B] flip bit per frame, or NULL (k == 1 only)
+ *   teacher  fp32  [pool][teacher_rows][tdim] or NULL; row = flip bit
+ *   mean,std host fp32 [3]
+ *   k        1: one image per frame (flipped iff flip[b]); 2: [orig, flipped]
+ * vpd_assemble_nchw writes the reference layout fp32 [B][k][C][H][W] (bit-exact);
+ * vpd_assemble_stem writes the network's own input layout, bf16
+ * [B*k][H+6][W+8][8], for the fused device-resident pipeline.
+ */
+VPD_API int vpd_assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
+                      const int32_t* index, const uint8_t* flip, const float* teacher,
+                      int teacher_rows, int tdim, const float* mean, const float* std,
+                      float* out_img, float* out_tgt, int B, int H, int W, int k, void* stream);
+VPD_API int vpd_assemble_stem(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
+                      const int32_t* index, const uint8_t* flip, const float* teacher,
+                      int teacher_rows, int tdim, const float* mean, const float* std,
+                      void* out_stem_bf16, float* out_tgt, int B, int H, int W, int k,
+                      void* stream);
+/* fp32 NCHW batch (the reference's batch['img']) -> network input layout */
+VPD_API int vpd_nchw_to_stem(const float* x, void* out_stem_bf16, int B, int C, int H, int W,
+                     void* stream);
+
+/* ---- K5: fused AdamW ------------------------------------------------------------
+ * Replaces torch.optim.AdamW.step over all tensors (train_vpd_model.py:100-105,
+ * models/util.py:50-58). Flat fp32 arenas of n elements; `step` is 1-based. */
+VPD_API int vpd_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+              double lr, double beta1, double beta2, double eps, double weight_decay, int step,
+              float grad_scale, void* stream);
+
+/* ---- K2: single convolution ops (NHWC bf16), used by the tests and the network ---
+ * Replace ATen conv2d forward / backward as called by torchvision BasicBlock
+ * (models/rgb.py:68-70). Weights: vpd_pack_conv_weight turns fp32 OIHW master
+ * weights into bf16 [k*k][Cout][Cin] (forward) and [k*k][Cin][Cout] (dgrad). */
+VPD_API int vpd_pack_conv_weight(const float* w_oihw, void* w_tap_bf16, void* wT_tap_bf16, int Cout,
+                         int Cin, int k, void* stream);
+VPD_API int vpd_pack_stem_weight(const float* w_oihw, void* w_stem_bf16, int Cimg, void* stream);
+/* y = conv(x); optional epilogue: y*scale[c]+shift[c], + residual, ReLU; optional
+ * fp64 per-channel (sum, sumsq) accumulation into stats[2][Cout] (training BN). */
+VPD_API int vpd_conv2d_fwd(const void* x, const void* w_tap, void* y, int N, int H, int W, int Cin,
+                   int Cout, int k, int stride, int pad, const float* scale, const float* shift,
+                   const void* residual, int relu, double* stats, void* stream);
+/* 7x7/2 pad-3 stem on the padded input layout written by vpd_assemble_stem */
+VPD_API int vpd_stem_conv_fwd(const void* x_stem, const void* w_stem, void* y, int N, int H, int W,
+                      const float* scale, const float* shift, int relu, double* stats,
+                      void* stream);
+/* dx = conv_transpose(dy) (+ residual); for stride 2 the optional 1x1/2
+ * downsample branch (dy_ds, wT_ds) is accumulated in the same pass. */
+VPD_API int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N, int H, int W, int Cin,
+                     int Cout, int k, int stride, int pad, const void* residual,
+                     const void* dy_ds, const void* wT_ds, int cout_ds, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPD_B200_H_ */

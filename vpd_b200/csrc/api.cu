@@ -1,0 +1,96 @@
+// extern "C" surface declared in include/vpd_b200.h
+#include "../../include/vpd_b200.h"
+
+#include "conv.h"
+#include "ops.h"
+
+using namespace vpd;
+typedef __nv_bfloat16 bf16;
+
+extern "C" {
+
+const char* vpd_last_error(void) { return get_error(); }
+int vpd_abi_version(void) { return 1; }
+
+int vpd_assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
+                      const int32_t* index, const uint8_t* flip, const float* teacher,
+                      int teacher_rows, int tdim, const float* mean, const float* std,
+                      float* out_img, float* out_tgt, int B, int H, int W, int k, void* stream) {
+  return assemble_nchw(rgb, flow, flow_channels, index, flip, teacher, teacher_rows, tdim, mean,
+                       std, out_img, out_tgt, B, H, W, k, (cudaStream_t)stream);
+}
+
+int vpd_assemble_stem(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
+                      const int32_t* index, const uint8_t* flip, const float* teacher,
+                      int teacher_rows, int tdim, const float* mean, const float* std,
+                      void* out_stem_bf16, float* out_tgt, int B, int H, int W, int k,
+                      void* stream) {
+  return assemble_pad8(rgb, flow, flow_channels, index, flip, teacher, teacher_rows, tdim, mean,
+                       std, (bf16*)out_stem_bf16, out_tgt, B, H, W, k, (cudaStream_t)stream);
+}
+
+int vpd_nchw_to_stem(const float* x, void* out_stem_bf16, int B, int C, int H, int W,
+                     void* stream) {
+  return nchw_to_pad8(x, (bf16*)out_stem_bf16, B, C, H, W, (cudaStream_t)stream);
+}
+
+int vpd_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+              double lr, double beta1, double beta2, double eps, double weight_decay, int step,
+              float grad_scale, void* stream) {
+  return adamw_step(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                    step, grad_scale, (cudaStream_t)stream);
+}
+
+int vpd_pack_conv_weight(const float* w_oihw, void* w_tap_bf16, void* wT_tap_bf16, int Cout,
+                         int Cin, int k, void* stream) {
+  return pack_conv_weight(w_oihw, (bf16*)w_tap_bf16, (bf16*)wT_tap_bf16, Cout, Cin, k,
+                          (cudaStream_t)stream);
+}
+
+int vpd_pack_stem_weight(const float* w_oihw, void* w_stem_bf16, int Cimg, void* stream) {
+  return pack_stem_weight(w_oihw, (bf16*)w_stem_bf16, Cimg, (cudaStream_t)stream);
+}
+
+int vpd_conv2d_fwd(const void* x, const void* w_tap, void* y, int N, int H, int W, int Cin,
+                   int Cout, int k, int stride, int pad, const float* scale, const float* shift,
+                   const void* residual, int relu, double* stats, void* stream) {
+  ConvGeom g{N, H, W, Cin, Cout, k, stride, pad};
+  ConvEpilogue e;
+  e.scale = scale;
+  e.shift = shift;
+  e.residual = (const bf16*)residual;
+  e.relu = relu;
+  e.stats = stats;
+  ConvLaunch L;
+  if (plan_conv_fwd(&L, g, (const bf16*)x, (const bf16*)w_tap, (bf16*)y, e)) return -1;
+  return launch_conv(L, (cudaStream_t)stream);
+}
+
+int vpd_stem_conv_fwd(const void* x_stem, const void* w_stem, void* y, int N, int H, int W,
+                      const float* scale, const float* shift, int relu, double* stats,
+                      void* stream) {
+  ConvEpilogue e;
+  e.scale = scale;
+  e.shift = shift;
+  e.relu = relu;
+  e.stats = stats;
+  ConvLaunch L;
+  if (plan_stem_fwd(&L, N, H, W, (const bf16*)x_stem, (const bf16*)w_stem, (bf16*)y, e)) return -1;
+  return launch_conv(L, (cudaStream_t)stream);
+}
+
+int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N, int H, int W, int Cin,
+                     int Cout, int k, int stride, int pad, const void* residual,
+                     const void* dy_ds, const void* wT_ds, int cout_ds, void* stream) {
+  ConvGeom g{N, H, W, Cin, Cout, k, stride, pad};
+  ConvLaunch L[4];
+  int count = 0;
+  if (plan_conv_dgrad(L, &count, g, (const bf16*)dy, (const bf16*)wT_tap, (bf16*)dx,
+                      (const bf16*)residual, (const bf16*)dy_ds, (const bf16*)wT_ds, cout_ds))
+    return -1;
+  for (int i = 0; i < count; ++i)
+    if (launch_conv(L[i], (cudaStream_t)stream)) return -1;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,294 @@
+// K1: frame-batch assembly.
+//
+// Reference arithmetic (vpd_dataset/common.py:52-69, single_frame.py:168-206,
+// :373-400) per pixel:
+//     rgb : ((float(u) / 255.f) - mean_c) / std_c        fp32, three roundings
+//     flow: float32(double(u) / 255.0 - 0.5)             fp64 then one rounding
+//     flip: out[c,h,w] = in[c,h,W-1-w]; flow-x negated
+// Each value depends only on (channel, byte), so every CTA builds the five
+// 256-entry tables in shared memory with exactly those IEEE operations
+// (division and subtraction are correctly rounded on both CPU and GPU, so the
+// tables - and therefore the outputs - are bit-identical to the reference) and
+// the per-pixel work becomes a table lookup. The kernels are HBM-bound:
+// 16-byte loads of the packed uint8 rows into shared memory, float4 / uint4
+// stores of the planes.
+#include "common.cuh"
+#include "tma_host.h"
+
+namespace vpd {
+
+constexpr int kAsmThreads = 256;
+
+__device__ __forceinline__ void build_lut(float* lut, const float* mean, const float* stdv,
+                                          int cimg) {
+  // lut[c*256 + u]; c < 3 rgb (or fewer), c = 3,4 flow
+  for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) {
+    const int c = i >> 8, u = i & 255;
+    float v;
+    if (c < 3) {
+      const float x = __fdiv_rn(static_cast<float>(u), 255.f);
+      v = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);
+    } else {
+      v = static_cast<float>(__dsub_rn(__ddiv_rn(static_cast<double>(u), 255.0), 0.5));
+    }
+    lut[i] = v;
+  }
+  (void)cimg;
+}
+
+// Stage `rows` image rows of packed uint8 pixels (pc bytes per pixel) into smem.
+__device__ __forceinline__ void stage_rows(uint8_t* dst, const uint8_t* src, int nbytes) {
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (nbytes & 15) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int i = threadIdx.x; i < nbytes / 16; i += blockDim.x) d4[i] = ldg_nc_v4(s4 + i);
+  } else {
+    for (int i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+struct AsmParams {
+  const uint8_t* rgb;     // [pool][H][W][3]
+  const uint8_t* flow;    // [pool][H][W][fc] or null
+  const int* index;       // [B] pool index per output frame, or null (identity)
+  const uint8_t* flip;    // [B] or null
+  const float* teacher;   // [pool][rows][tdim] or null
+  float mean[3], stdv[3];
+  int B, H, W, fc, rows_per_cta;
+  int teacher_rows, tdim;
+  int k;                  // apply variants: 1 = as is (flip bit per frame), 2 = [orig, flipped]
+  float* out_img;         // [B][k][C][H][W] fp32, C = 3 or 5
+  float* out_tgt;         // [B][tdim]
+  __nv_bfloat16* out_pad; // [B*k][H+6][W+8][8] bf16 (stem layout), or null
+};
+
+// Reference layout: fp32 NCHW planes.
+__global__ void __launch_bounds__(kAsmThreads)
+assemble_nchw_kernel(const AsmParams p) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  float* lut = reinterpret_cast<float*>(sm);
+  uint8_t* s_rgb = sm + 5 * 256 * 4;
+  const int R = p.rows_per_cta;
+  uint8_t* s_flow = s_rgb + ((R * p.W * 3 + 15) & ~15);
+  const int chunks = (p.H + R - 1) / R;
+  const int b = blockIdx.x / chunks;
+  const int h0 = (blockIdx.x % chunks) * R;
+  const int rows = min(R, p.H - h0);
+  const int src = p.index ? p.index[b] : b;
+  const int C = p.flow ? 5 : 3;
+
+  build_lut(lut, p.mean, p.stdv, 3);
+  stage_rows(s_rgb, p.rgb + ((size_t)src * p.H + h0) * p.W * 3, rows * p.W * 3);
+  if (p.flow) stage_rows(s_flow, p.flow + ((size_t)src * p.H + h0) * p.W * p.fc, rows * p.W * p.fc);
+  __syncthreads();
+
+  if (h0 == 0 && p.teacher && p.out_tgt) {
+    const int row = (p.teacher_rows > 1 && p.flip && p.flip[b]) ? 1 : 0;
+    const float* t = p.teacher + ((size_t)src * p.teacher_rows + row) * p.tdim;
+    for (int i = threadIdx.x; i < p.tdim; i += blockDim.x) p.out_tgt[(size_t)b * p.tdim + i] = t[i];
+  }
+
+  const int W4 = p.W / 4;  // host guarantees W % 4 == 0
+  for (int v = 0; v < p.k; ++v) {
+    const bool fl = (p.k == 2) ? (v == 1) : (p.flip && p.flip[b]);
+    float* obase = p.out_img + ((size_t)b * p.k + v) * C * p.H * p.W;
+    for (int i = threadIdx.x; i < C * rows * W4; i += blockDim.x) {
+      const int w4 = i % W4;
+      const int r = (i / W4) % rows;
+      const int c = i / (W4 * rows);
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int w = w4 * 4 + j;
+        const int ws = fl ? (p.W - 1 - w) : w;
+        if (c < 3) {
+          o[j] = lut[c * 256 + s_rgb[(r * p.W + ws) * 3 + c]];
+        } else {
+          const float f = lut[c * 256 + s_flow[(r * p.W + ws) * p.fc + (c - 3)]];
+          o[j] = (fl && c == 3) ? -f : f;
+        }
+      }
+      float4* op = reinterpret_cast<float4*>(obase + ((size_t)c * p.H + h0 + r) * p.W) + w4;
+      __stcs(op, make_float4(o[0], o[1], o[2], o[3]));
+    }
+  }
+}
+
+// Stem layout: bf16 [frame][H+6][W+8][8] (3 zero rows/cols of conv padding on
+// the top/left, channels 5..7 zero). One 16-byte store per pixel. The border
+// is written here too, so the buffer needs no separate clearing.
+__global__ void __launch_bounds__(kAsmThreads)
+assemble_pad8_kernel(const AsmParams p) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  float* lut = reinterpret_cast<float*>(sm);
+  uint8_t* s_rgb = sm + 5 * 256 * 4;
+  const int R = p.rows_per_cta;
+  uint8_t* s_flow = s_rgb + ((R * p.W * 3 + 15) & ~15);
+  const int Hp = p.H + 6, Wp = p.W + 8;
+  const int chunks = (Hp + R - 1) / R;
+  const int b = blockIdx.x / chunks;
+  const int hp0 = (blockIdx.x % chunks) * R;  // padded row range [hp0, hp0+rows)
+  const int rows = min(R, Hp - hp0);
+  const int src = p.index ? p.index[b] : b;
+  // image rows covered: hp-3 in [0,H)
+  const int h_lo = max(hp0 - 3, 0), h_hi = min(hp0 + rows - 3, p.H);
+  const int nimg = max(h_hi - h_lo, 0);
+
+  build_lut(lut, p.mean, p.stdv, 3);
+  if (nimg > 0) {
+    stage_rows(s_rgb, p.rgb + ((size_t)src * p.H + h_lo) * p.W * 3, nimg * p.W * 3);
+    if (p.flow)
+      stage_rows(s_flow, p.flow + ((size_t)src * p.H + h_lo) * p.W * p.fc, nimg * p.W * p.fc);
+  }
+  __syncthreads();
+
+  if (hp0 == 0 && p.teacher && p.out_tgt) {
+    const int row = (p.teacher_rows > 1 && p.flip && p.flip[b]) ? 1 : 0;
+    const float* t = p.teacher + ((size_t)src * p.teacher_rows + row) * p.tdim;
+    for (int i = threadIdx.x; i < p.tdim; i += blockDim.x) p.out_tgt[(size_t)b * p.tdim + i] = t[i];
+  }
+
+  for (int v = 0; v < p.k; ++v) {
+    const bool fl = (p.k == 2) ? (v == 1) : (p.flip && p.flip[b]);
+    __nv_bfloat16* obase = p.out_pad + ((size_t)b * p.k + v) * Hp * Wp * 8;
+    for (int i = threadIdx.x; i < rows * Wp; i += blockDim.x) {
+      const int wp = i % Wp, hp = hp0 + i / Wp;
+      const int h = hp - 3, w = wp - 3;
+      uint4 o = make_uint4(0, 0, 0, 0);
+      if (h >= 0 && h < p.H && w >= 0 && w < p.W) {
+        const int ws = fl ? (p.W - 1 - w) : w;
+        const int r = h - h_lo;
+        const uint8_t* px = s_rgb + (r * p.W + ws) * 3;
+        const float c0 = lut[px[0]], c1 = lut[256 + px[1]], c2 = lut[512 + px[2]];
+        float c3 = 0.f, c4 = 0.f;
+        if (p.flow) {
+          const uint8_t* pf = s_flow + (r * p.W + ws) * p.fc;
+          c3 = lut[768 + pf[0]];
+          c4 = lut[1024 + pf[1]];
+          if (fl) c3 = -c3;
+        }
+        o.x = pack_bf16x2(c0, c1);
+        o.y = pack_bf16x2(c2, c3);
+        o.z = pack_bf16x2(c4, 0.f);
+      }
+      stg_v4(reinterpret_cast<uint4*>(obase + ((size_t)hp * Wp + wp) * 8), o);
+    }
+  }
+}
+
+// fp32 NCHW (the reference's batch['img']) -> stem layout
+__global__ void __launch_bounds__(256)
+nchw_to_pad8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C,
+                    int H, int W) {
+  const int Hp = H + 6, Wp = W + 8;
+  const long long total = (long long)B * Hp * Wp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int wp = (int)(i % Wp);
+    const int hp = (int)((i / Wp) % Hp);
+    const int b = (int)(i / ((long long)Wp * Hp));
+    const int h = hp - 3, w = wp - 3;
+    float c[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const float* px = x + ((size_t)b * C * H + h) * W + w;
+      for (int k = 0; k < C; ++k) c[k] = __ldg(px + (size_t)k * H * W);
+    }
+    stg_v4(reinterpret_cast<uint4*>(out + i * 8),
+           make_uint4(pack_bf16x2(c[0], c[1]), pack_bf16x2(c[2], c[3]), pack_bf16x2(c[4], c[5]),
+                      pack_bf16x2(c[6], c[7])));
+  }
+}
+
+static int fill_params(AsmParams* p, const uint8_t* rgb, const uint8_t* flow, int flow_channels,
+                       const int* index, const uint8_t* flip, const float* teacher,
+                       int teacher_rows, int tdim, const float* mean, const float* stdv, int B,
+                       int H, int W, int k) {
+  VPD_REQUIRE(rgb != nullptr, "assemble: rgb is null");
+  VPD_REQUIRE(W % 4 == 0, "assemble: W must be a multiple of 4 (got %d)", W);
+  VPD_REQUIRE(k == 1 || k == 2, "assemble: k must be 1 or 2");
+  VPD_REQUIRE(flow == nullptr || flow_channels >= 2, "assemble: flow needs >= 2 channels");
+  p->rgb = rgb;
+  p->flow = flow;
+  p->index = index;
+  p->flip = flip;
+  p->teacher = teacher;
+  for (int i = 0; i < 3; ++i) {
+    p->mean[i] = mean[i];
+    p->stdv[i] = stdv[i];
+  }
+  p->B = B;
+  p->H = H;
+  p->W = W;
+  p->fc = flow_channels;
+  p->teacher_rows = teacher_rows;
+  p->tdim = tdim;
+  p->k = k;
+  p->out_img = nullptr;
+  p->out_tgt = nullptr;
+  p->out_pad = nullptr;
+  return 0;
+}
+
+static int smem_for(const AsmParams& p, int R) {
+  return 5 * 256 * 4 + ((R * p.W * 3 + 15) & ~15) + ((R * p.W * (p.flow ? p.fc : 0) + 15) & ~15) + 16;
+}
+
+int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, const int* index,
+                  const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
+                  const float* mean, const float* stdv, float* out_img, float* out_tgt, int B,
+                  int H, int W, int k, cudaStream_t stream) {
+  AsmParams p;
+  if (fill_params(&p, rgb, flow, flow_channels, index, flip, teacher, teacher_rows, tdim, mean,
+                  stdv, B, H, W, k))
+    return -1;
+  if (B == 0) return 0;
+  p.out_img = out_img;
+  p.out_tgt = out_tgt;
+  p.rows_per_cta = H < 8 ? H : 8;
+  const int smem = smem_for(p, p.rows_per_cta);
+  VPD_REQUIRE(smem <= 200 * 1024, "assemble: image too wide (W=%d)", W);
+  if (smem > 48 * 1024)
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_nchw_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int chunks = (H + p.rows_per_cta - 1) / p.rows_per_cta;
+  assemble_nchw_kernel<<<B * chunks, kAsmThreads, smem, stream>>>(p);
+  VPD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, const int* index,
+                  const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
+                  const float* mean, const float* stdv, __nv_bfloat16* out_pad, float* out_tgt,
+                  int B, int H, int W, int k, cudaStream_t stream) {
+  AsmParams p;
+  if (fill_params(&p, rgb, flow, flow_channels, index, flip, teacher, teacher_rows, tdim, mean,
+                  stdv, B, H, W, k))
+    return -1;
+  if (B == 0) return 0;
+  p.out_pad = out_pad;
+  p.out_tgt = out_tgt;
+  p.rows_per_cta = 8;
+  const int smem = smem_for(p, p.rows_per_cta);
+  VPD_REQUIRE(smem <= 200 * 1024, "assemble: image too wide (W=%d)", W);
+  if (smem > 48 * 1024)
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_kernel,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int chunks = (H + 6 + p.rows_per_cta - 1) / p.rows_per_cta;
+  assemble_pad8_kernel<<<B * chunks, kAsmThreads, smem, stream>>>(p);
+  VPD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int nchw_to_pad8(const float* x, __nv_bfloat16* out, int B, int C, int H, int W,
+                 cudaStream_t stream) {
+  VPD_REQUIRE(C >= 1 && C <= 8, "nchw_to_pad8: C=%d unsupported", C);
+  if (B == 0) return 0;
+  const long long total = (long long)B * (H + 6) * (W + 8);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  nchw_to_pad8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, out, B, C, H, W);
+  VPD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vpd

@@ -1,0 +1,343 @@
+#include "conv.h"
+
+#include <string.h>
+
+namespace vpd {
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+static int floor_pow2(int v) {
+  int p = 1;
+  while (p * 2 <= v) p *= 2;
+  return p;
+}
+
+// 128 output pixels per tile as tw x th x tn
+static void tile_geometry(int Ho, int Wo, int N, ConvParams* p) {
+  int tw = floor_pow2(Wo < 128 ? Wo : 128);
+  int th = floor_pow2(Ho);
+  if (th > 128 / tw) th = 128 / tw;
+  int tn = 128 / (tw * th);
+  p->tw = tw;
+  p->th = th;
+  p->tn = tn;
+  p->tiles_w = (Wo + tw - 1) / tw;
+  p->tiles_h = (Ho + th - 1) / th;
+  p->tiles_b = (N + tn - 1) / tn;
+  p->batch = N;
+  p->out_h = Ho;
+  p->out_w = Wo;
+}
+
+static int pick_block_n(int cout) {
+  if (cout % 128 != 0) return 64;
+  return 128;
+}
+
+static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+static int mod2(int v) { return ((v % 2) + 2) % 2; }
+
+static void finish_launch(ConvLaunch* L, int cout, bool stats) {
+  L->block_n = pick_block_n(cout);
+  L->p.n_tiles = cout / L->block_n;
+  L->p.cout = cout;
+  const int total = L->p.tiles_w * L->p.tiles_h * L->p.tiles_b * L->p.n_tiles;
+  int grid = device_sm_count();
+  if (grid > total) grid = total;
+  if (stats && grid >= L->p.n_tiles) grid -= grid % L->p.n_tiles;  // channel block fixed per CTA
+  L->grid = grid;
+}
+
+// weights [taps][rows][kdim] bf16 -> 3-D map, box {64, block_n, 1}
+static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int taps, int rows, int kdim,
+                      int block_n) {
+  uint64_t dims[3] = {(uint64_t)kdim, (uint64_t)rows, (uint64_t)taps};
+  uint64_t str[3] = {2, (uint64_t)kdim * 2, (uint64_t)rows * kdim * 2};
+  uint32_t box[3] = {64, (uint32_t)block_n, 1};
+  return encode_tmap_bf16(m, w, 3, dims, str, box, true);
+}
+
+// NHWC activation [N][H][W][C] viewed for a conv of the given stride
+static int act_map(CUtensorMap* m, const __nv_bfloat16* x, int N, int H, int W, int C, int stride,
+                   const ConvParams& p) {
+  uint32_t box[5] = {64, (uint32_t)p.tw, 1, (uint32_t)p.th, (uint32_t)p.tn};
+  if (stride == 1) {
+    uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, 1, (uint64_t)H, (uint64_t)N};
+    uint64_t str[5] = {2, (uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)W * C * 2,
+                       (uint64_t)H * W * C * 2};
+    return encode_tmap_bf16(m, x, 5, dims, str, box, true);
+  }
+  // stride 2: even/odd columns fold into the channel axis, even/odd rows get
+  // their own axis, so every tap is a dense box
+  uint64_t dims[5] = {(uint64_t)2 * C, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)N};
+  uint64_t str[5] = {2, (uint64_t)2 * C * 2, (uint64_t)W * C * 2, (uint64_t)2 * W * C * 2,
+                     (uint64_t)H * W * C * 2};
+  return encode_tmap_bf16(m, x, 5, dims, str, box, true);
+}
+
+static void set_epilogue(ConvParams* p, const ConvEpilogue& e) {
+  p->scale = e.scale;
+  p->shift = e.shift;
+  p->residual = e.residual;
+  p->relu = e.relu;
+  p->stats = e.stats;
+}
+
+int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
+                  const __nv_bfloat16* w_tap, __nv_bfloat16* y, const ConvEpilogue& e) {
+  memset(L, 0, sizeof(*L));
+  VPD_REQUIRE(g.Cin % 64 == 0 && g.Cout % 64 == 0, "conv: Cin/Cout must be multiples of 64 (%d,%d)",
+              g.Cin, g.Cout);
+  VPD_REQUIRE(g.stride == 1 || g.stride == 2, "conv: stride %d unsupported", g.stride);
+  VPD_REQUIRE(g.k * g.k <= kMaxTaps, "conv: kernel %d too large", g.k);
+  if (g.stride == 2) VPD_REQUIRE(g.H % 2 == 0 && g.W % 2 == 0, "conv: stride 2 needs even H, W");
+  const int Ho = g.Ho(), Wo = g.Wo();
+  ConvParams& p = L->p;
+  tile_geometry(Ho, Wo, g.N, &p);
+  p.num_taps = g.k * g.k;
+  for (int kh = 0; kh < g.k; ++kh)
+    for (int kw = 0; kw < g.k; ++kw) {
+      ConvTap& t = p.taps[kh * g.k + kw];
+      const int u = kw - g.pad, v = kh - g.pad;
+      if (g.stride == 1) {
+        t.c0 = 0;
+        t.d1 = u;
+        t.d2 = 0;
+        t.d3 = v;
+      } else {
+        t.c0 = mod2(u) * g.Cin;
+        t.d1 = floordiv2(u);
+        t.d2 = mod2(v);
+        t.d3 = floordiv2(v);
+      }
+      t.src = 0;
+      t.btap = kh * g.k + kw;
+      t.kchunks = g.Cin / 64;
+    }
+  p.out = y;
+  p.out_sn = (long long)Ho * Wo * g.Cout;
+  p.out_sh = (long long)Wo * g.Cout;
+  p.out_sw = g.Cout;
+  set_epilogue(&p, e);
+  finish_launch(L, g.Cout, e.stats != nullptr);
+  if (act_map(&L->a0, x, g.N, g.H, g.W, g.Cin, g.stride, p)) return -1;
+  if (weight_map(&L->b0, w_tap, g.k * g.k, g.Cout, g.Cin, L->block_n)) return -1;
+  L->a1 = L->a0;
+  L->b1 = L->b0;
+  return 0;
+}
+
+int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
+                  const __nv_bfloat16* w_stem, __nv_bfloat16* y, const ConvEpilogue& e) {
+  memset(L, 0, sizeof(*L));
+  VPD_REQUIRE(H % 2 == 0 && W % 8 == 0, "stem: H must be even and W a multiple of 8 (%d,%d)", H, W);
+  const int Ho = H / 2, Wo = W / 2, Hp = H + 6, Wp = W + 8;
+  ConvParams& p = L->p;
+  tile_geometry(Ho, Wo, N, &p);
+  p.num_taps = 7;
+  for (int kh = 0; kh < 7; ++kh) {
+    ConvTap& t = p.taps[kh];
+    t.c0 = 0;
+    t.d1 = 0;
+    t.d2 = kh % 2;
+    t.d3 = kh / 2;
+    t.src = 0;
+    t.btap = kh;
+    t.kchunks = 1;
+  }
+  p.out = y;
+  p.out_sn = (long long)Ho * Wo * 64;
+  p.out_sh = (long long)Wo * 64;
+  p.out_sw = 64;
+  set_epilogue(&p, e);
+  finish_launch(L, 64, e.stats != nullptr);
+  // overlapping 8-pixel windows: output column wo reads padded columns
+  // 2wo .. 2wo+7 (64 contiguous bf16), output row ho / tap kh reads padded
+  // row 2ho+kh = 2*(ho + kh/2) + kh%2
+  const uint64_t pitch = (uint64_t)Wp * 8 * 2;
+  uint64_t dims[5] = {64, (uint64_t)Wo, 2, (uint64_t)Hp / 2, (uint64_t)N};
+  uint64_t str[5] = {2, 2 * 8 * 2, pitch, 2 * pitch, (uint64_t)Hp * pitch};
+  uint32_t box[5] = {64, (uint32_t)p.tw, 1, (uint32_t)p.th, (uint32_t)p.tn};
+  if (encode_tmap_bf16(&L->a0, x_pad, 5, dims, str, box, true)) return -1;
+  if (weight_map(&L->b0, w_stem, 7, 64, 64, L->block_n)) return -1;
+  L->a1 = L->a0;
+  L->b1 = L->b0;
+  return 0;
+}
+
+int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bfloat16* dy,
+                    const __nv_bfloat16* wT_tap, __nv_bfloat16* dx,
+                    const __nv_bfloat16* residual, const __nv_bfloat16* dy_ds,
+                    const __nv_bfloat16* wT_ds, int cout_ds) {
+  VPD_REQUIRE(g.Cin % 64 == 0 && g.Cout % 64 == 0, "dgrad: channels must be multiples of 64");
+  const int Ho = g.Ho(), Wo = g.Wo();
+  *count = 0;
+  if (g.stride == 1) {
+    VPD_REQUIRE(g.k == 2 * g.pad + 1, "dgrad: stride-1 conv must be 'same' padded");
+    ConvLaunch* L = &Ls[0];
+    memset(L, 0, sizeof(*L));
+    ConvParams& p = L->p;
+    tile_geometry(g.H, g.W, g.N, &p);
+    p.num_taps = g.k * g.k;
+    for (int kh = 0; kh < g.k; ++kh)
+      for (int kw = 0; kw < g.k; ++kw) {
+        ConvTap& t = p.taps[kh * g.k + kw];
+        t.c0 = 0;
+        t.d1 = g.pad - kw;
+        t.d2 = 0;
+        t.d3 = g.pad - kh;
+        t.src = 0;
+        t.btap = kh * g.k + kw;
+        t.kchunks = g.Cout / 64;
+      }
+    p.out = dx;
+    p.residual = residual;
+    p.out_sn = (long long)g.H * g.W * g.Cin;
+    p.out_sh = (long long)g.W * g.Cin;
+    p.out_sw = g.Cin;
+    finish_launch(L, g.Cin, false);
+    if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
+    if (weight_map(&L->b0, wT_tap, g.k * g.k, g.Cin, g.Cout, L->block_n)) return -1;
+    L->a1 = L->a0;
+    L->b1 = L->b0;
+    *count = 1;
+    return 0;
+  }
+  VPD_REQUIRE(g.stride == 2 && g.k == 3 && g.pad == 1, "dgrad: only 3x3/2 pad 1 strided convs");
+  VPD_REQUIRE(g.H == 2 * Ho && g.W == 2 * Wo, "dgrad: stride 2 needs even input dims");
+  // dx[2i+a, 2j+b] = sum over kh = a+1 (mod 2), kw = b+1 (mod 2) of
+  //                  dy[i + (a+1-kh)/2, j + (b+1-kw)/2] * w[kh,kw]
+  for (int a = 0; a < 2; ++a)
+    for (int b = 0; b < 2; ++b) {
+      ConvLaunch* L = &Ls[*count];
+      memset(L, 0, sizeof(*L));
+      ConvParams& p = L->p;
+      tile_geometry(Ho, Wo, g.N, &p);
+      int nt = 0;
+      for (int kh = 0; kh < 3; ++kh) {
+        if ((a + 1 - kh) % 2 != 0) continue;
+        for (int kw = 0; kw < 3; ++kw) {
+          if ((b + 1 - kw) % 2 != 0) continue;
+          ConvTap& t = p.taps[nt++];
+          t.c0 = 0;
+          t.d1 = (b + 1 - kw) / 2;
+          t.d2 = 0;
+          t.d3 = (a + 1 - kh) / 2;
+          t.src = 0;
+          t.btap = kh * 3 + kw;
+          t.kchunks = g.Cout / 64;
+        }
+      }
+      const bool fuse_ds = (a == 0 && b == 0 && dy_ds != nullptr);
+      if (fuse_ds) {
+        ConvTap& t = p.taps[nt++];
+        t.c0 = 0;
+        t.d1 = 0;
+        t.d2 = 0;
+        t.d3 = 0;
+        t.src = 1;
+        t.btap = 0;
+        t.kchunks = cout_ds / 64;
+      }
+      p.num_taps = nt;
+      const long long base = ((long long)a * g.W + b) * g.Cin;
+      p.out = dx + base;
+      p.residual = residual ? residual + base : nullptr;
+      p.out_sn = (long long)g.H * g.W * g.Cin;
+      p.out_sh = (long long)2 * g.W * g.Cin;
+      p.out_sw = (long long)2 * g.Cin;
+      finish_launch(L, g.Cin, false);
+      if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
+      if (weight_map(&L->b0, wT_tap, 9, g.Cin, g.Cout, L->block_n)) return -1;
+      if (fuse_ds) {
+        if (act_map(&L->a1, dy_ds, g.N, Ho, Wo, cout_ds, 1, p)) return -1;
+        if (weight_map(&L->b1, wT_ds, 1, g.Cin, cout_ds, L->block_n)) return -1;
+      } else {
+        L->a1 = L->a0;
+        L->b1 = L->b0;
+      }
+      ++*count;
+    }
+  return 0;
+}
+
+template <int BN>
+static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        ConvCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  conv_igemm_kernel<BN><<<L.grid, kConvThreads, ConvCfg<BN>::kSmemBytes, stream>>>(
+      L.a0, L.a1, L.b0, L.b1, L.p);
+  VPD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_conv(const ConvLaunch& L, cudaStream_t stream) {
+  if (L.grid <= 0) return 0;
+  switch (L.block_n) {
+    case 64: return launch_bn<64>(L, stream);
+    case 128: return launch_bn<128>(L, stream);
+    case 256: return launch_bn<256>(L, stream);
+  }
+  set_error("launch_conv: bad block_n %d", L.block_n);
+  return -1;
+}
+
+// ---------------------------------------------------------------- weight packing
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_tap,
+                                        __nv_bfloat16* __restrict__ wT_tap, int Cout, int Cin,
+                                        int kk) {
+  // one thread per (co, ci): reads kk contiguous floats, scatters to both layouts
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * Cin) return;
+  const int ci = (int)(i % Cin), co = (int)(i / Cin);
+  const float* src = w + i * kk;
+  for (int t = 0; t < kk; ++t) {
+    const __nv_bfloat16 v = __float2bfloat16_rn(src[t]);
+    if (w_tap) w_tap[((long long)t * Cout + co) * Cin + ci] = v;
+    if (wT_tap) wT_tap[((long long)t * Cin + ci) * Cout + co] = v;
+  }
+}
+
+int pack_conv_weight(const float* w_oihw, __nv_bfloat16* w_tap, __nv_bfloat16* wT_tap, int Cout,
+                     int Cin, int k, cudaStream_t stream) {
+  const long long n = (long long)Cout * Cin;
+  pack_conv_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w_oihw, w_tap, wT_tap,
+                                                                          Cout, Cin, k * k);
+  VPD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+__global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws,
+                                        int Cimg) {
+  // ws[kh][co][kw*8 + c], zero for kw == 7 or c >= Cimg
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 7 * 64 * 64) return;
+  const int e = i % 64, co = (i / 64) % 64, kh = i / 4096;
+  const int kw = e / 8, c = e % 8;
+  float v = 0.f;
+  if (kw < 7 && c < Cimg) v = w[((co * Cimg + c) * 7 + kh) * 7 + kw];
+  ws[i] = __float2bfloat16_rn(v);
+}
+
+int pack_stem_weight(const float* w_oihw, __nv_bfloat16* w_stem, int Cimg, cudaStream_t stream) {
+  VPD_REQUIRE(Cimg >= 1 && Cimg <= 8, "stem: %d input channels unsupported", Cimg);
+  pack_stem_weight_kernel<<<(7 * 64 * 64 + 255) / 256, 256, 0, stream>>>(w_oihw, w_stem, Cimg);
+  VPD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vpd

@@ -1,0 +1,58 @@
+// Host-side planning for the implicit-GEMM convolution kernels (K2/K2b/K2c).
+#pragma once
+#include "conv_igemm.cuh"
+#include "tma_host.h"
+
+namespace vpd {
+
+struct ConvLaunch {
+  CUtensorMap a0, a1, b0, b1;
+  ConvParams p;
+  int block_n;
+  int grid;
+};
+
+struct ConvGeom {
+  int N, H, W;     // input batch / height / width (of x; for dgrad: of dx)
+  int Cin, Cout;
+  int k, stride, pad;
+  int Ho() const { return (H + 2 * pad - k) / stride + 1; }
+  int Wo() const { return (W + 2 * pad - k) / stride + 1; }
+};
+
+struct ConvEpilogue {
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  const __nv_bfloat16* residual = nullptr;
+  int relu = 0;
+  double* stats = nullptr;
+};
+
+int device_sm_count();
+
+// y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) ; w_tap = bf16 [k*k][Cout][Cin]
+int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
+                  const __nv_bfloat16* w_tap, __nv_bfloat16* y, const ConvEpilogue& e);
+
+// 7x7/2 pad 3 stem on the padded NHWC8 input [N][H+6][W+8][8];
+// w_stem = bf16 [7][64][64] (kw*8+c, zero padded)
+int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
+                  const __nv_bfloat16* w_stem, __nv_bfloat16* y, const ConvEpilogue& e);
+
+// dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w) (+ residual)
+// wT_tap = bf16 [k*k][Cin][Cout]. For stride 2 this produces 4 launches (one
+// per output-pixel parity class); the 1x1/2 downsample branch (dy_ds, wT_ds
+// = bf16 [1][Cin][Cout_ds]) is fused into class (0,0).
+int plan_conv_dgrad(ConvLaunch* L, int* count, const ConvGeom& g, const __nv_bfloat16* dy,
+                    const __nv_bfloat16* wT_tap, __nv_bfloat16* dx,
+                    const __nv_bfloat16* residual, const __nv_bfloat16* dy_ds,
+                    const __nv_bfloat16* wT_ds, int cout_ds);
+
+int launch_conv(const ConvLaunch& L, cudaStream_t stream);
+
+// fp32 OIHW master weights -> bf16 tap-major copies used by the kernels
+int pack_conv_weight(const float* w_oihw, __nv_bfloat16* w_tap, __nv_bfloat16* wT_tap, int Cout,
+                     int Cin, int k, cudaStream_t stream);
+int pack_stem_weight(const float* w_oihw, __nv_bfloat16* w_stem, int Cimg, cudaStream_t stream);
+
+}  // namespace vpd

@@ -1,0 +1,328 @@
+// K2: implicit-GEMM convolution on tcgen05 tensor cores (sm_100a).
+//
+// One persistent, warp-specialised kernel serves the forward convolutions
+// (torchvision BasicBlock convs called from models/rgb.py:68-70)
+// and their data gradients (A9). GEMM view, per output tile:
+//     D[128 pixels, BLOCK_N channels] = sum over taps t, 64-channel chunks kc of
+//         A_t,kc[128 pixels, 64]  x  B_t,kc[BLOCK_N, 64]^T
+//   * activations live in HBM as NHWC bf16; the A tile of tap t is ONE 5-D TMA
+//     box {64 ch, tw, 1, th, tn} fetched at the tap's spatial offset from a
+//     tensor-map *view* of the same buffer (stride-1: (C,W,1,H,N); stride-2:
+//     (2C,W/2,2,H/2,N) so that even/odd pixels become separate coordinates; the
+//     7x7 stem uses overlapping 8-pixel windows). Out-of-range coordinates
+//     are zero-filled by TMA, which implements the conv padding.
+//   * weights are bf16 [tap][Cout][Cin] (K-major), box {64, BLOCK_N, 1}.
+//   * both land in shared memory 128B-swizzled, K-major; a single thread
+//     issues tcgen05.mma (M=128, N=BLOCK_N, K=16) accumulating in TMEM
+//     (fp32). Two TMEM accumulator stages let the epilogue of tile i overlap
+//     the MMAs of tile i+1.
+//   * epilogue warps read TMEM (tcgen05.ld), optionally apply a per-channel
+//     affine (folded eval-mode BN) + residual + ReLU, write bf16 NHWC, and in
+//     training mode accumulate the per-channel sum / sum-of-squares that
+//     BatchNorm needs (warp transpose-reduce -> smem -> fp64 global atomics).
+#pragma once
+#include "common.cuh"
+
+namespace vpd {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kMaxTaps = 12;
+constexpr int kConvThreads = 192;
+
+struct ConvTap {
+  int c0;       // offset added to the innermost (channel) coordinate
+  int d1, d2, d3;  // offsets for the w, parity and h coordinates
+  int src;      // which (A,B) tensor-map pair (0/1)
+  int btap;     // index on the tap axis of the weight tensor
+  int kchunks;  // number of 64-wide K chunks for this tap
+  int pad_;
+};
+
+struct ConvParams {
+  int tw, th, tn;  // tile = tw x th pixels x tn images, tw*th*tn == 128
+  int tiles_w, tiles_h, tiles_b;
+  int n_tiles;     // Cout / BLOCK_N
+  int num_taps;
+  ConvTap taps[kMaxTaps];
+  int batch, out_h, out_w;  // valid extents of the (n, h, w) tile coordinates
+  int cout;
+  __nv_bfloat16* out;
+  const __nv_bfloat16* residual;      // same addressing as out, or null
+  long long out_sn, out_sh, out_sw;   // element strides of out/residual
+  const float* scale;                 // [cout] or null
+  const float* shift;                 // [cout] or null
+  int relu;
+  double* stats;                      // [2][cout] (sum, sumsq) or null
+};
+
+template <int BLOCK_N>
+struct ConvCfg {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N == 64 ? 6 : (BLOCK_N == 128 ? 5 : 4);
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 2 * BLOCK_N * 4 + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+                  const __grid_constant__ ConvParams p) {
+  using Cfg = ConvCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_sum = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes);
+  float* s_sq = s_sum + BLOCK_N;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB0);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kConvThreads) s_sum[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int total_tiles = m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * p.tw;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * p.th;
+        const int b0 = (mt / p.tiles_h) * p.tn;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const ConvTap tap = p.taps[t];
+          const CUtensorMap* ma = tap.src ? &tmA1 : &tmA0;
+          const CUtensorMap* mb = tap.src ? &tmB1 : &tmB0;
+          for (int kc = 0; kc < tap.kchunks; ++kc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            uint8_t* sb = sa + Cfg::kABytes;
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_5d(sa, ma, &full_bar[stage], tap.c0 + kc * kBlockK, w0 + tap.d1, tap.d2,
+                        h0 + tap.d3, b0);
+            tma_load_3d(sb, mb, &full_bar[stage], kc * kBlockK, n_tile * BLOCK_N, tap.btap);
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int total_kb = 0;
+      for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].kchunks;
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t adesc = make_smem_desc(sa, 16, 1024);
+          const uint64_t bdesc = make_smem_desc(sb, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advance 32 B (16 bf16) along K inside the 128 B swizzled row
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int q = warp & 3;       // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;  // row of the 128-row tile
+    int as = 0;
+    uint32_t aphase = 0;
+    int cur_ntile = -1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      int mt = tile / p.n_tiles;
+      const int w0 = (mt % p.tiles_w) * p.tw;
+      mt /= p.tiles_w;
+      const int h0 = (mt % p.tiles_h) * p.th;
+      const int b0 = (mt / p.tiles_h) * p.tn;
+      const int w = w0 + r % p.tw;
+      const int h = h0 + (r / p.tw) % p.th;
+      const int n = b0 + r / (p.tw * p.th);
+      const bool valid = (n < p.batch) && (h < p.out_h) && (w < p.out_w);
+      const long long off = n * p.out_sn + h * p.out_sh + w * p.out_sw + n_tile * BLOCK_N;
+
+      if (p.stats != nullptr && cur_ntile != n_tile) {
+        // flush per-CTA channel statistics when the channel block changes
+        // (named barrier over the 4 epilogue warps only)
+        if (cur_ntile >= 0) {
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+            atomicAdd(&p.stats[cur_ntile * BLOCK_N + i], static_cast<double>(s_sum[i]));
+            atomicAdd(&p.stats[p.cout + cur_ntile * BLOCK_N + i], static_cast<double>(s_sq[i]));
+            s_sum[i] = 0.f;
+            s_sq[i] = 0.f;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        cur_ntile = n_tile;
+      }
+
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        const int ch0 = n_tile * BLOCK_N + c * 32;
+        if (p.scale != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + j));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch0 + j));
+            f[j + 0] = fmaf(f[j + 0], sc.x, sh.x);
+            f[j + 1] = fmaf(f[j + 1], sc.y, sh.y);
+            f[j + 2] = fmaf(f[j + 2], sc.z, sh.z);
+            f[j + 3] = fmaf(f[j + 3], sc.w, sh.w);
+          }
+        }
+        if (p.residual != nullptr && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 rv = __ldg(rp + j);
+            f[8 * j + 0] += bf16_lo(rv.x);
+            f[8 * j + 1] += bf16_hi(rv.x);
+            f[8 * j + 2] += bf16_lo(rv.y);
+            f[8 * j + 3] += bf16_hi(rv.y);
+            f[8 * j + 4] += bf16_lo(rv.z);
+            f[8 * j + 5] += bf16_hi(rv.z);
+            f[8 * j + 6] += bf16_lo(rv.w);
+            f[8 * j + 7] += bf16_hi(rv.w);
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+        if (valid) {
+          uint4* op = reinterpret_cast<uint4*>(p.out + off + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            stg_v4(op + j, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+        }
+        if (p.stats != nullptr) {
+          // statistics of the values as stored (bf16-rounded); invalid rows = 0
+          float s[32], s2[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float a = valid ? bf16_lo(pk[j]) : 0.f;
+            const float b = valid ? bf16_hi(pk[j]) : 0.f;
+            s[2 * j] = a;
+            s[2 * j + 1] = b;
+            s2[2 * j] = a * a;
+            s2[2 * j + 1] = b * b;
+          }
+          // warp transpose-reduce: after the 5 steps lane j holds column j's
+          // total over the warp's 32 rows (31 shuffles per quantity)
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const bool up = (lane & o) != 0;
+#pragma unroll
+            for (int i = 0; i < o; ++i) {
+              const float keep = up ? s[i + o] : s[i];
+              const float send = up ? s[i] : s[i + o];
+              s[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+              const float keep2 = up ? s2[i + o] : s2[i];
+              const float send2 = up ? s2[i] : s2[i + o];
+              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, o);
+            }
+          }
+          atomicAdd(&s_sum[c * 32 + lane], s[0]);
+          atomicAdd(&s_sq[c * 32 + lane], s2[0]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+    if (p.stats != nullptr && cur_ntile >= 0) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+        atomicAdd(&p.stats[cur_ntile * BLOCK_N + i], static_cast<double>(s_sum[i]));
+        atomicAdd(&p.stats[p.cout + cur_ntile * BLOCK_N + i], static_cast<double>(s_sq[i]));
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+}  // namespace vpd

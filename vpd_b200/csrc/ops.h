@@ -1,0 +1,23 @@
+// Internal (C++) declarations of the op launchers implemented across csrc/*.cu
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vpd {
+
+int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, const int* index,
+                  const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
+                  const float* mean, const float* stdv, float* out_img, float* out_tgt, int B,
+                  int H, int W, int k, cudaStream_t stream);
+int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, const int* index,
+                  const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
+                  const float* mean, const float* stdv, __nv_bfloat16* out_pad, float* out_tgt,
+                  int B, int H, int W, int k, cudaStream_t stream);
+int nchw_to_pad8(const float* x, __nv_bfloat16* out, int B, int C, int H, int W,
+                 cudaStream_t stream);
+int adamw_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1,
+               double b2, double eps, double wd, int step, float grad_scale,
+               cudaStream_t stream);
+
+}  // namespace vpd

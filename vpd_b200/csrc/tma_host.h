@@ -1,0 +1,38 @@
+// Host-side CUtensorMap construction. libcuda is not linked at build time (the
+// build box has no driver); cuTensorMapEncodeTiled is resolved at run time
+// through cudaGetDriverEntryPoint.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vpd {
+
+// Encodes a bf16 tiled tensor map with 128-byte swizzle (or none).
+// dims/strides are innermost-first; strides_bytes[0] is implied (2 bytes) and
+// ignored. Returns 0 on success, else sets the library error string.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define VPD_CHECK_CUDA(expr)                                                        \
+  do {                                                                              \
+    cudaError_t _e = (expr);                                                        \
+    if (_e != cudaSuccess) {                                                        \
+      ::vpd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                       __FILE__, __LINE__);                                         \
+      return -1;                                                                    \
+    }                                                                               \
+  } while (0)
+
+#define VPD_REQUIRE(cond, ...)          \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::vpd::set_error(__VA_ARGS__);    \
+      return -1;                        \
+    }                                   \
+  } while (0)
+
+}  // namespace vpd
