@@ -94,6 +94,14 @@ VPD_API int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N
                      int Cout, int k, int stride, int pad, const void* residual,
                      const void* dy_ds, const void* wT_ds, int cout_ds, void* stream);
 
+/* dw[k*k][Cout][Cin] (fp32, tap-major: the gradient arena's native conv layout)
+ * += sum over pixels dy (x) x. ACCUMULATES into dw (zero it first). */
+VPD_API int vpd_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
+                     int Cout, int k, int stride, int pad, void* stream);
+/* stem weight gradient, dw[7][64][64] fp32 in the packed stem layout (kh, cout, kw*8+c) */
+VPD_API int vpd_stem_conv_wgrad(const void* x_stem, const void* dy, float* dw, int N, int H, int W,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -307,3 +307,58 @@ def test_conv2d_dgrad_matches_autograd(case, extras):
     msg = report('dgrad{}{}'.format(case, extras), got, ref)
     assert torch.isfinite(got).all(), msg
     assert rel_err(got, ref) < 6e-3, msg
+
+
+WGRAD_CASES = [
+    (2, 32, 32, 64, 64, 3, 1, 1),
+    (16, 32, 32, 64, 64, 3, 1, 1),
+    (3, 16, 16, 128, 128, 3, 1, 1),
+    (4, 8, 8, 256, 256, 3, 1, 1),
+    (9, 4, 4, 512, 512, 3, 1, 1),
+    (2, 32, 32, 64, 128, 3, 2, 1),
+    (2, 32, 32, 64, 128, 1, 2, 0),
+    (3, 16, 16, 128, 256, 3, 2, 1),
+    (5, 8, 8, 256, 512, 1, 2, 0),
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES)
+def test_conv2d_wgrad_matches_autograd(case):
+    N, H, W, Cin, Cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(13)
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    x = nhwc_bf16(torch.randn((N, Cin, H, W), generator=g)).to(dev())
+    dy = nhwc_bf16(torch.randn((N, Cout, Ho, Wo), generator=g)).to(dev())
+    dw = torch.zeros((k * k, Cout, Cin), device=dev(), dtype=torch.float32)
+    lib().call('vpd_conv2d_wgrad', x, dy, dw, N, H, W, Cin, Cout, k, stride, pad, stream_ptr())
+    ref = torch.nn.grad.conv2d_weight(nchw_f32(x), (Cout, Cin, k, k), nchw_f32(dy),
+                                      stride=stride, padding=pad)
+    got = dw.view(k, k, Cout, Cin).permute(2, 3, 0, 1).contiguous()
+    msg = report('wgrad{}'.format(case), got, ref, tol=2e-3)
+    assert torch.isfinite(got).all(), msg
+    assert rel_err(got, ref) < 2e-3, msg
+    # accumulation semantics: a second call doubles the result
+    lib().call('vpd_conv2d_wgrad', x, dy, dw, N, H, W, Cin, Cout, k, stride, pad, stream_ptr())
+    got2 = dw.view(k, k, Cout, Cin).permute(2, 3, 0, 1)
+    assert rel_err(got2, 2 * ref) < 2e-3
+
+
+@pytest.mark.parametrize('N,H,W,Cimg', [(2, 128, 128, 5), (5, 32, 32, 3)])
+def test_stem_conv_wgrad(N, H, W, Cimg):
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn((N, Cimg, H, W), generator=g)
+    xs = torch.empty((N, H + 6, W + 8, 8), device=dev(), dtype=torch.bfloat16)
+    lib().call('vpd_nchw_to_stem', x.to(dev()), xs, N, Cimg, H, W, stream_ptr())
+    dy = nhwc_bf16(torch.randn((N, 64, H // 2, W // 2), generator=g)).to(dev())
+    dw = torch.zeros((7, 64, 64), device=dev(), dtype=torch.float32)
+    lib().call('vpd_stem_conv_wgrad', xs, dy, dw, N, H, W, stream_ptr())
+    ref = torch.nn.grad.conv2d_weight(x.to(torch.bfloat16).float().to(dev()), (64, Cimg, 7, 7),
+                                      nchw_f32(dy), stride=2, padding=3)
+    # dw[kh][co][kw*8+c] -> [co][c][kh][kw]
+    full = dw.view(7, 64, 8, 8)                       # kh, co, kw, c
+    got = full[:, :, :7, :Cimg].permute(1, 3, 0, 2).contiguous()
+    msg = report('stem_wgrad', got, ref, tol=2e-3)
+    assert rel_err(got, ref) < 2e-3, msg
+    assert full[:, :, 7, :].abs().max().item() == 0.0          # kw == 7 pad never written
+    assert full[:, :, :7, Cimg:].abs().max().item() == 0.0      # zero input channels

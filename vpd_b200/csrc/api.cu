@@ -93,4 +93,19 @@ int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N, int H,
   return 0;
 }
 
+int vpd_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
+                     int Cout, int k, int stride, int pad, void* stream) {
+  ConvGeom g{N, H, W, Cin, Cout, k, stride, pad};
+  WgradLaunch L;
+  if (plan_conv_wgrad(&L, g, (const bf16*)x, (const bf16*)dy, dw)) return -1;
+  return launch_wgrad(L, (cudaStream_t)stream);
+}
+
+int vpd_stem_conv_wgrad(const void* x_stem, const void* dy, float* dw, int N, int H, int W,
+                        void* stream) {
+  WgradLaunch L;
+  if (plan_stem_wgrad(&L, N, H, W, (const bf16*)x_stem, (const bf16*)dy, dw)) return -1;
+  return launch_wgrad(L, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -238,10 +238,12 @@ int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
                   const float* mean, const float* stdv, float* out_img, float* out_tgt, int B,
                   int H, int W, int k, cudaStream_t stream) {
   AsmParams p;
+  VPD_REQUIRE(B >= 0, "assemble: negative batch");
+  VPD_REQUIRE(W % 4 == 0, "assemble: W must be a multiple of 4 (got %d)", W);
+  if (B == 0) return 0;
   if (fill_params(&p, rgb, flow, flow_channels, index, flip, teacher, teacher_rows, tdim, mean,
                   stdv, B, H, W, k))
     return -1;
-  if (B == 0) return 0;
   p.out_img = out_img;
   p.out_tgt = out_tgt;
   p.rows_per_cta = H < 8 ? H : 8;
@@ -261,10 +263,12 @@ int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
                   const float* mean, const float* stdv, __nv_bfloat16* out_pad, float* out_tgt,
                   int B, int H, int W, int k, cudaStream_t stream) {
   AsmParams p;
+  VPD_REQUIRE(B >= 0, "assemble: negative batch");
+  VPD_REQUIRE(W % 4 == 0, "assemble: W must be a multiple of 4 (got %d)", W);
+  if (B == 0) return 0;
   if (fill_params(&p, rgb, flow, flow_channels, index, flip, teacher, teacher_rows, tdim, mean,
                   stdv, B, H, W, k))
     return -1;
-  if (B == 0) return 0;
   p.out_pad = out_pad;
   p.out_tgt = out_tgt;
   p.rows_per_cta = 8;

@@ -296,6 +296,92 @@ int launch_conv(const ConvLaunch& L, cudaStream_t stream) {
   return -1;
 }
 
+// ------------------------------------------------------------------------ wgrad
+static void finish_wgrad(WgradLaunch* L, int cin, int cout, int num_taps, int kchunks,
+                         int row_limit, float* dw) {
+  WgradParams& p = L->p;
+  L->block_n = cout % 128 == 0 ? 128 : 64;
+  p.n_tiles = cout / L->block_n;
+  p.kchunks = kchunks;
+  p.num_taps = num_taps;
+  p.num_units = num_taps * kchunks;
+  p.num_pairs = (p.num_units + 1) / 2;
+  p.cin = cin;
+  p.cout = cout;
+  p.row_limit = row_limit;
+  p.dw = dw;
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  int splits = device_sm_count() / (p.num_pairs * p.n_tiles);
+  if (splits < 1) splits = 1;
+  if (splits > pix_tiles) splits = pix_tiles;
+  // no empty splits: per_split = ceil(pix/splits) must leave the last one non-empty
+  while (splits > 1 && (splits - 1) * ((pix_tiles + splits - 1) / splits) >= pix_tiles) --splits;
+  p.splits = splits;
+  const int items = p.num_pairs * p.n_tiles * splits;
+  L->grid = items < device_sm_count() ? items : device_sm_count();
+}
+
+static void copy_geometry(WgradParams* w, const ConvParams& c) {
+  w->tw = c.tw;
+  w->th = c.th;
+  w->tn = c.tn;
+  w->tiles_w = c.tiles_w;
+  w->tiles_h = c.tiles_h;
+  w->tiles_b = c.tiles_b;
+  for (int i = 0; i < kMaxTaps; ++i) w->taps[i] = c.taps[i];
+}
+
+int plan_conv_wgrad(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
+                    const __nv_bfloat16* dy, float* dw) {
+  memset(L, 0, sizeof(*L));
+  // reuse the forward plan for tile geometry, taps and the X tensor-map view
+  ConvLaunch f;
+  ConvEpilogue e;
+  if (plan_conv_fwd(&f, g, x, reinterpret_cast<const __nv_bfloat16*>(dw),
+                    const_cast<__nv_bfloat16*>(dy), e))
+    return -1;
+  copy_geometry(&L->p, f.p);
+  L->x = f.a0;
+  if (act_map(&L->dy, dy, g.N, g.Ho(), g.Wo(), g.Cout, 1, f.p)) return -1;
+  finish_wgrad(L, g.Cin, g.Cout, g.k * g.k, g.Cin / 64, 64, dw);
+  return 0;
+}
+
+int plan_stem_wgrad(WgradLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
+                    const __nv_bfloat16* dy, float* dw) {
+  memset(L, 0, sizeof(*L));
+  ConvLaunch f;
+  ConvEpilogue e;
+  if (plan_stem_fwd(&f, N, H, W, x_pad, reinterpret_cast<const __nv_bfloat16*>(dw),
+                    const_cast<__nv_bfloat16*>(dy), e))
+    return -1;
+  copy_geometry(&L->p, f.p);
+  L->x = f.a0;
+  if (act_map(&L->dy, dy, N, H / 2, W / 2, 64, 1, f.p)) return -1;
+  finish_wgrad(L, 64, 64, 7, 1, 56, dw);
+  return 0;
+}
+
+template <int BN>
+static int launch_wgrad_bn(const WgradLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel<BN>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        WgradCfg<BN>::kSmemBytes));
+    attr_set = true;
+  }
+  conv_wgrad_kernel<BN><<<L.grid, kConvThreads, WgradCfg<BN>::kSmemBytes, stream>>>(L.x, L.dy, L.p);
+  VPD_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_wgrad(const WgradLaunch& L, cudaStream_t stream) {
+  if (L.grid <= 0) return 0;
+  if (L.block_n == 64) return launch_wgrad_bn<64>(L, stream);
+  return launch_wgrad_bn<128>(L, stream);
+}
+
 // ---------------------------------------------------------------- weight packing
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_tap,
                                         __nv_bfloat16* __restrict__ wT_tap, int Cout, int Cin,

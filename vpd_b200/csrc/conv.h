@@ -50,6 +50,20 @@ int plan_conv_dgrad(ConvLaunch* L, int* count, const ConvGeom& g, const __nv_bfl
 
 int launch_conv(const ConvLaunch& L, cudaStream_t stream);
 
+struct WgradLaunch {
+  CUtensorMap x, dy;
+  WgradParams p;
+  int block_n;
+  int grid;
+};
+// dw[k*k][Cout][Cin] (fp32, tap-major) += sum over pixels dy * x  (accumulates!)
+int plan_conv_wgrad(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
+                    const __nv_bfloat16* dy, float* dw);
+// stem: dw[7][64][64] (kw*8+c, entries with kw == 7 are left untouched)
+int plan_stem_wgrad(WgradLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
+                    const __nv_bfloat16* dy, float* dw);
+int launch_wgrad(const WgradLaunch& L, cudaStream_t stream);
+
 // fp32 OIHW master weights -> bf16 tap-major copies used by the kernels
 int pack_conv_weight(const float* w_oihw, __nv_bfloat16* w_tap, __nv_bfloat16* wT_tap, int Cout,
                      int Cin, int k, cudaStream_t stream);

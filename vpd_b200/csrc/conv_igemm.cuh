@@ -325,4 +325,212 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+
+// ===========================================================================
+// K2c: weight gradient, dW[tap][co][ci] += sum over pixels dY[p][co] * X[p+tap][ci]
+//
+// GEMM view: the reduction runs over PIXELS, which is the slow axis of both NHWC
+// operands, so both are fed to the tensor core MN-major straight from the same
+// TMA boxes the forward uses (no transposed copies):
+//     D[128 = two (tap, 64-channel) units of X][BLOCK_N couts] +=
+//         A[128 pixels, 128]^T  x  B[128 pixels, BLOCK_N]
+// A work item is (unit pair, cout tile, pixel split); it walks its share of the
+// pixel tiles accumulating in TMEM and finally adds its partial result into the
+// fp32 gradient arena (tap-major [tap][Cout][Cin], the arena's native layout)
+// with coalesced red.global.add.f32.
+// ===========================================================================
+struct WgradParams {
+  int tw, th, tn;
+  int tiles_w, tiles_h, tiles_b;
+  int n_tiles;          // Cout / BLOCK_N
+  int num_units;        // taps * (Cin / 64)
+  int num_pairs;        // ceil(num_units / 2)
+  int splits;           // pixel-range splits per (pair, n_tile)
+  int kchunks;          // Cin / 64
+  int num_taps;
+  ConvTap taps[kMaxTaps];
+  int cin, cout;
+  int row_limit;        // rows (ci within unit) >= row_limit are not written (stem pad)
+  float* dw;            // [taps][cout][cin] fp32, accumulated
+};
+
+template <int BLOCK_N>
+struct WgradCfg {
+  static constexpr int kABytes = 2 * kBlockM * 64 * 2;        // two unit boxes
+  static constexpr int kBBytes = (BLOCK_N / 64) * kBlockM * 64 * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N == 64 ? 4 : 3;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                  const __grid_constant__ WgradParams p) {
+  using Cfg = WgradCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 4);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int per_split = (pix_tiles + p.splits - 1) / p.splits;
+  const int total_items = p.num_pairs * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int n_tile = (item / p.splits) % p.n_tiles;
+        const int pair = item / (p.splits * p.n_tiles);
+        int u[2] = {2 * pair, 2 * pair + 1};
+        if (u[1] >= p.num_units) u[1] = u[0];  // dummy second unit (result discarded)
+        const int pt_end = min(pix_tiles, (split + 1) * per_split);
+        for (int pt = split * per_split; pt < pt_end; ++pt) {
+          int mt = pt;
+          const int w0 = (mt % p.tiles_w) * p.tw;
+          mt /= p.tiles_w;
+          const int h0 = (mt % p.tiles_h) * p.th;
+          const int b0 = (mt / p.tiles_h) * p.tn;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const ConvTap tap = p.taps[u[j] / p.kchunks];
+            const int kc = u[j] % p.kchunks;
+            tma_load_5d(sa + j * (kBlockM * 128), &tmX, &full_bar[stage], tap.c0 + kc * 64,
+                        w0 + tap.d1, tap.d2, h0 + tap.d3, b0);
+          }
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_5d(sb + j * (kBlockM * 128), &tmDY, &full_bar[stage],
+                        n_tile * BLOCK_N + j * 64, w0, 0, h0, b0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int pt_beg = split * per_split;
+        const int pt_end = min(pix_tiles, (split + 1) * per_split);
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int pt = pt_beg; pt < pt_end; ++pt) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          // MN-major: LBO = bytes between 64-wide M/N blocks (one TMA box),
+          // SBO = bytes between 8-pixel groups along K
+          const uint64_t adesc = make_smem_desc(sa, kBlockM * 128, 1024);
+          const uint64_t bdesc = make_smem_desc(sb, kBlockM * 128, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockM / kUmmaK; ++k) {
+            // 16 pixels (rows of 128 B) per MMA -> 2048 B -> +128 in the address field
+            umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, idesc,
+                      (pt != pt_beg || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int split = item % p.splits;
+      const int n_tile = (item / p.splits) % p.n_tiles;
+      const int pair = item / (p.splits * p.n_tiles);
+      const int unit = 2 * pair + (r >> 6);
+      const int rl = r & 63;
+      const bool has_work = split * per_split < pix_tiles;
+      const bool valid = has_work && unit < p.num_units && rl < p.row_limit;
+      const int tap_i = valid ? unit / p.kchunks : 0;
+      const int kc = valid ? unit % p.kchunks : 0;
+      float* dst = p.dw + ((size_t)p.taps[tap_i].btap * p.cout + n_tile * BLOCK_N) * p.cin +
+                   kc * 64 + rl;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            atomicAdd(dst + (size_t)(c * 32 + j) * p.cin, __uint_as_float(v[j]));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
 }  // namespace vpd
