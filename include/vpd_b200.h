@@ -102,6 +102,55 @@ VPD_API int vpd_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, in
 VPD_API int vpd_stem_conv_wgrad(const void* x_stem, const void* dy, float* dw, int N, int H, int W,
                         void* stream);
 
+/* ---- the student network ---------------------------------------------------------
+ * Replaces RGBF_EmbeddingModel.forward/embed (models/rgb.py:68-86), the body of
+ * ModelTrainer.epoch (train_vpd_model.py:67-98: forward, FCNet decoder,
+ * F.mse_loss(reduction='sum')) and loss.backward() (models/util.py:50-58).
+ *
+ * A vpd_net is a host-side execution plan (TMA descriptors, launch parameters);
+ * it owns no device memory. The caller binds:
+ *   params / grads   fp32 [vpd_net_param_count]   (grads may be NULL: inference only)
+ *   buffers          fp32 [vpd_net_buffer_count]  BN running means then variances
+ *   nbt              int64 [vpd_net_num_bn]       BN num_batches_tracked
+ *   workspace        bytes [vpd_net_workspace_bytes]
+ * vpd_net_tensor_info maps every reference state_dict entry ("resnet.*", plus
+ * "decoder.layers.*" for the FCNet) to (arena, offset, layout):
+ *   arena  0 params/grads, 1 buffers, 2 nbt
+ *   layout 0 plain row-major in the reference shape
+ *          1 conv weight stored tap-major [kh*kw][Cout][Cin]
+ *          2 stem conv stored [7 kh][64 cout][kw*8 + c] (kw == 7 / c >= Cin zero)
+ * Inputs: either x_nchw (fp32 [B][C][H][W], the reference's batch['img']) or
+ * x_stem (the layout vpd_assemble_stem writes; may be vpd_net_stem_input itself).
+ */
+typedef struct vpd_net vpd_net;
+VPD_API vpd_net* vpd_net_create(const char* arch, int emb_dim, int in_channels, int H, int W,
+                        int max_batch, int motion);
+VPD_API void vpd_net_destroy(vpd_net* net);
+VPD_API int64_t vpd_net_param_count(vpd_net* net);
+VPD_API int64_t vpd_net_conv_param_count(vpd_net* net);
+VPD_API int64_t vpd_net_buffer_count(vpd_net* net);
+VPD_API int vpd_net_num_bn(vpd_net* net);
+VPD_API int64_t vpd_net_workspace_bytes(vpd_net* net);
+VPD_API int vpd_net_num_tensors(vpd_net* net);
+VPD_API int vpd_net_tensor_info(vpd_net* net, int i, char* name, int name_cap, int* arena,
+                        int64_t* offset, int* layout, int* ndim, int64_t* shape4);
+VPD_API int vpd_net_bind(vpd_net* net, float* params, float* grads, float* buffers, int64_t* nbt,
+                 void* workspace, int64_t workspace_bytes);
+/* call after writing the parameter arena from outside (load_state_dict, optimizer) */
+VPD_API int vpd_net_params_changed(vpd_net* net);
+VPD_API void* vpd_net_stem_input(vpd_net* net);
+/* eval-mode encoder: emb_out fp32 [B][emb_dim] */
+VPD_API int vpd_net_forward(vpd_net* net, const float* x_nchw, const void* x_stem, int B,
+                    float* emb_out, void* stream);
+/* eval-mode forward + decoder + sum-squared-error; *loss_sum (device fp64) += loss;
+ * out (optional) fp32 [B][target_dim] */
+VPD_API int vpd_net_eval_loss(vpd_net* net, const float* x_nchw, const void* x_stem,
+                      const float* target, int B, double* loss_sum, float* out, void* stream);
+/* train-mode forward (batch-stat BN, running stats updated) + loss + backward;
+ * gradients of every parameter are written to the grads arena */
+VPD_API int vpd_net_train_step(vpd_net* net, const float* x_nchw, const void* x_stem,
+                       const float* target, int B, double* loss_sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,252 @@
+"""GPU parity of the whole student path (through the Python mirror -> C ABI) against
+the oracle and the golden vectors the unmodified reference produced.
+
+Stated tolerances (bf16 tensor-core operands and bf16 activation storage, fp32
+accumulation / statistics / master weights, vs the reference's fp32 CPU path):
+  * embeddings: per-frame cosine >= 0.999 (north_star), max-abs error reported and
+    bounded by 3% of the embedding's max magnitude;
+  * first-step gradients: per-tensor cosine >= 0.98 for weight tensors, loss within 1%;
+  * 200-step loss curve from identical init: every 20-step window mean within 5%,
+    overall mean within 2%.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import assemble_ref, student_ref
+from vpd_b200 import synth
+from gpu_util import dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a = a.double().flatten(); b = b.double().flatten()
+    return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+
+@pytest.fixture(scope='module')
+def gold(golden_dir):
+    with open(os.path.join(golden_dir, 'student.json')) as fp:
+        meta = json.load(fp)
+    return np.load(os.path.join(golden_dir, 'student.npz')), meta
+
+
+def _model(seed=0, arch='resnet34', D=32, use_flow=True):
+    from vpd_b200 import RGBF_EmbeddingModel
+    torch.manual_seed(seed)
+    return RGBF_EmbeddingModel(arch, D, use_flow, 'cuda')
+
+
+def test_constructor_state_dict_equals_reference_init():
+    m = _model(0)
+    torch.manual_seed(0)
+    ref = student_ref.init_encoder_state('resnet34', 32, True)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys()) and len(sd) == 218
+    for k in ref:
+        assert sd[k].dtype == ref[k].dtype and tuple(sd[k].shape) == tuple(ref[k].shape), k
+        assert torch.equal(sd[k].cpu(), ref[k]), k
+    assert m.device == 'cuda' and m.emb_dim == 32 and m.use_flow is True
+
+
+def test_state_dict_roundtrip_and_checkpoint_files(tmp_path):
+    from vpd_b200 import ModelTrainer
+    m = _model(3)
+    tr = ModelTrainer(m, True)
+    torch.manual_seed(9)
+    sd = student_ref.randomize_bn_state(student_ref.init_encoder_state('resnet34', 32, True), 4)
+    sd['resnet.bn1.num_batches_tracked'] = torch.tensor(17)
+    m.load_state_dict(sd)
+    back = m.state_dict()
+    for k in sd:
+        assert torch.equal(back[k].cpu(), sd[k]), k
+    tr.save_model(str(tmp_path), 'best_epoch')
+    enc = torch.load(os.path.join(str(tmp_path), 'best_epoch.encoder.pt'))
+    dec = torch.load(os.path.join(str(tmp_path), 'best_epoch.decoder.pt'))
+    assert list(enc.keys()) == list(sd.keys())
+    assert list(dec.keys()) == student_ref.DECODER_PARAM_NAMES
+    assert dec['layers.5.weight'].shape == (64, 128)
+    # the files load into the oracle's fp32 model unchanged
+    out = student_ref.embed(enc, torch.zeros(1, 5, 128, 128))
+    assert out.shape == (1, 32)
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({'resnet.conv1.weight': sd['resnet.conv1.weight']})
+
+
+def test_embed_matches_reference_golden(gold):
+    arrays, meta = gold
+    m = _model(0)
+    torch.manual_seed(0)
+    sd = student_ref.randomize_bn_state(student_ref.init_encoder_state('resnet34', 32, True), 21)
+    m.load_state_dict(sd)
+    rgb, flow = synth.crops(4, seed=22)
+    x = assemble_ref.apply_batch(rgb.numpy(), flow.numpy(), *synth.FS_MEAN_STD,
+                                 flip=True).view(-1, 5, 128, 128)
+    got = m.embed(x.numpy())
+    ref = arrays['embed_out']            # from the unmodified reference's embed()
+    assert got.shape == ref.shape and got.dtype == np.float32
+    cos = [_cos(torch.from_numpy(got[i]), torch.from_numpy(ref[i])) for i in range(len(ref))]
+    max_abs = np.abs(got - ref).max()
+    print('embed cos min {:.6f} max_abs {:.4e} ref_max {:.3f}'.format(min(cos), max_abs,
+                                                                      np.abs(ref).max()))
+    assert min(cos) >= 0.999, cos
+    assert max_abs <= 0.03 * np.abs(ref).max()
+    # single [C,H,W] frame and the channel assertion (models/rgb.py:76-82)
+    one = m.embed(x[0].numpy())
+    assert one.shape == (1, 32)
+    with pytest.raises(AssertionError):
+        m.embed(np.zeros((1, 3, 128, 128), np.float32))
+
+
+def test_embed_other_arch_and_size():
+    m = _model(5, arch='resnet18', D=26, use_flow=False)
+    torch.manual_seed(5)
+    sd = student_ref.randomize_bn_state(student_ref.init_encoder_state('resnet18', 26, False), 6)
+    m.load_state_dict(sd)
+    x = torch.randn((3, 3, 64, 96), generator=torch.Generator().manual_seed(1))
+    got = m.embed(x)
+    ref = student_ref.embed(sd, x, arch='resnet18')
+    cos = [_cos(torch.from_numpy(got[i]), torch.from_numpy(ref[i])) for i in range(3)]
+    assert min(cos) >= 0.999, cos
+
+
+def _curve_data(meta):
+    lc = meta['loss_curve']
+    B, steps = lc['batch'], lc['steps']
+    rgb, flow = synth.crops(lc['pool'], seed=lc['seeds']['crops'])
+    teach = synth.teacher(lc['pool'], seed=lc['seeds']['teacher'], emb_dim=32, motion=True)
+    fl = synth.flips(steps * B, seed=lc['seeds']['flips'])
+    idx = torch.randint(0, lc['pool'], (steps * B,),
+                        generator=torch.Generator().manual_seed(lc['seeds']['index']))
+    return B, steps, rgb, flow, teach, fl, idx
+
+
+def test_first_step_gradients_match_oracle(gold):
+    from vpd_b200 import ModelTrainer
+    arrays, meta = gold
+    B, steps, rgb, flow, teach, fl, idx = _curve_data(meta)
+    sel, f = idx[:B], fl[:B]
+    img, tgt = assemble_ref.train_batch(rgb[sel].numpy(), flow[sel].numpy(), teach[sel].numpy(),
+                                        f.numpy(), *synth.FS_MEAN_STD)
+    m = _model(0)
+    tr = ModelTrainer(m, True)
+    m._ensure_grads()
+    m.train()
+    tr._loss.zero_()
+    tr._run(img.to(dev()), tgt.to(dev()), B, True)
+    torch.cuda.synchronize()
+    loss = tr._loss.item()
+    ref_loss = arrays['loss_curve'][0] * B
+    print('step0 loss {:.4f} ref {:.4f}'.format(loss, ref_loss))
+    assert abs(loss - ref_loss) <= 0.01 * ref_loss
+    # gradients in reference layout
+    views = m._views()
+    names = meta['param_names']
+    grads = {}
+    params, m._params = m._params, m._grads          # read the grad arena with the same views
+    try:
+        gsd = m._read_state(lambda k: True)
+    finally:
+        m._params = params
+    norms = arrays['step0_grad_norms']
+    worst = 1.0
+    for i, name in enumerate(names):
+        g = gsd[name].cpu()
+        rel = abs(g.norm().item() - norms[i]) / (norms[i] + 1e-12)
+        if name.endswith('.weight') and g.dim() > 1:
+            assert rel < 0.08, (name, g.norm().item(), norms[i])
+    for key, name in (('step0_grad_fc', 'resnet.fc.weight'), ('step0_grad_conv1', 'resnet.conv1.weight')):
+        c = _cos(gsd[name].cpu(), torch.from_numpy(arrays[key]))
+        print(name, 'grad cos', c)
+        worst = min(worst, c)
+        assert c >= 0.98, (name, c)
+    c = _cos(gsd['resnet.layer4.2.conv2.weight'].cpu()[:8, :8], torch.from_numpy(arrays['step0_grad_l4']))
+    assert c >= 0.98, c
+    # every tensor against the oracle's autograd on the same batch
+    torch.manual_seed(0)
+    osd = student_ref.init_encoder_state('resnet34', 32, True)
+    odsd = student_ref.init_decoder_state(32)
+    otr = student_ref.OracleTrainer(osd, odsd)
+    _, ograds, _ = otr.loss_and_grads(img, tgt, train=True)
+    bad = []
+    for name, og in zip(names, ograds):
+        c = _cos(gsd[name].cpu(), og)
+        if c < (0.98 if og.dim() > 1 else 0.95):
+            bad.append((name, round(c, 4)))
+    assert not bad, bad
+    # BN running statistics after one train-mode forward
+    sd = m.state_dict()
+    np.testing.assert_allclose(sd['resnet.bn1.running_var'].cpu().numpy(),
+                               arrays['step0_bn1_running_var'], rtol=2e-2)
+    assert int(sd['resnet.bn1.num_batches_tracked']) == 1
+
+
+def test_loss_curve_200_steps_vs_reference(gold):
+    from vpd_b200 import ModelTrainer
+    arrays, meta = gold
+    B, steps, rgb, flow, teach, fl, idx = _curve_data(meta)
+    m = _model(0)
+    tr = ModelTrainer(m, True)
+    opt, scaler = tr.get_optimizer(meta['loss_curve']['lr'])
+    assert scaler is None
+    losses = []
+    for s in range(steps):
+        sel, f = idx[s * B:(s + 1) * B], fl[s * B:(s + 1) * B]
+        img, tgt = assemble_ref.train_batch(rgb[sel].numpy(), flow[sel].numpy(),
+                                            teach[sel].numpy(), f.numpy(), *synth.FS_MEAN_STD)
+        losses.append(tr.epoch([{'img': img, 'emb': tgt}], optimizer=opt, scaler=scaler))
+    got = np.array(losses)
+    ref = arrays['loss_curve']
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    os.makedirs(out, exist_ok=True)
+    np.savetxt(os.path.join(out, 'loss_curve.txt'), np.stack([ref, got], 1), header='reference ours')
+    win = 20
+    gw = got.reshape(-1, win).mean(1)
+    rw = ref.reshape(-1, win).mean(1)
+    print('window rel dev', np.round(np.abs(gw - rw) / rw, 4).tolist())
+    assert np.all(np.abs(gw - rw) / rw <= 0.05)
+    assert abs(got.mean() - ref.mean()) / ref.mean() <= 0.02
+    assert abs(got[0] - ref[0]) / ref[0] <= 0.01
+    # eval-mode epoch on a fixed batch (running statistics path)
+    sel = torch.arange(8)
+    img, tgt = assemble_ref.train_batch(rgb[sel].numpy(), flow[sel].numpy(), teach[sel].numpy(),
+                                        np.zeros(8, np.uint8), *synth.FS_MEAN_STD)
+    seen = []
+    ev = tr.epoch([{'img': img, 'emb': tgt}], progress_cb=seen.append)
+    assert seen == [8]
+    print('final eval loss {:.4f} ref {:.4f}'.format(ev, meta['final_eval_loss']))
+    assert abs(ev - meta['final_eval_loss']) / meta['final_eval_loss'] <= 0.15
+
+
+def test_fused_stem_path_equals_fp32_batch_path():
+    """K1 -> network layout directly == reference-layout fp32 batch through epoch()."""
+    from vpd_b200 import ModelTrainer
+    from vpd_b200.assemble import assemble_stem, assemble_batch
+    B = 16
+    rgb, flow = synth.crops(B, seed=41)
+    teach = synth.teacher(B, seed=42)
+    fl = synth.flips(B, seed=43)
+    res = []
+    for fused in (False, True):
+        m = _model(1)
+        tr = ModelTrainer(m, True)
+        opt, _ = tr.get_optimizer(5e-4)
+        if fused:
+            tgt = torch.empty((B, 64), device=dev())
+            ptr = tr.stem_buffer(B, 128, 128)
+            assemble_stem(ptr, rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD,
+                          flip=fl.to(dev()), teacher=teach.to(dev()), tgt=tgt)
+            tr._loss.zero_()
+            tr.train_step_stem(ptr, tgt, B, 128, 128, opt)
+            loss = tr._loss.item() / B
+        else:
+            batch = assemble_batch(rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD,
+                                   flip=fl.to(dev()), teacher=teach.to(dev()))
+            loss = tr.epoch([batch], optimizer=opt)
+        res.append((loss, m.state_dict()['resnet.fc.weight'].cpu()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-3 * abs(res[0][0])
+    assert torch.allclose(res[0][1], res[1][1], atol=1e-4)

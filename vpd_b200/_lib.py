@@ -27,7 +27,12 @@ def parse_header(path=HEADER):
     protos = {}
     for m in re.finditer(r'VPD_API\s+([\w\s\*]+?)\s*\b(vpd_\w+)\s*\(([^;]*?)\)\s*;', text, flags=re.S):
         ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
-        restype = ctypes.c_char_p if '*' in ret else _SCALARS[ret]
+        if '*' in ret:
+            restype = ctypes.c_char_p if 'char' in ret else ctypes.c_void_p
+        elif ret == 'void':
+            restype = None
+        else:
+            restype = _SCALARS[ret]
         argl = []
         if args and args != 'void':
             for a in args.split(','):
@@ -40,6 +45,10 @@ def parse_header(path=HEADER):
                     argl.append((an, _SCALARS[ty]))
         protos[name] = (restype, argl)
     return protos
+
+
+# int-returning entry points whose result is a value, not a status code
+_VALUE_INT = {'vpd_abi_version', 'vpd_net_num_bn', 'vpd_net_num_tensors'}
 
 
 class VpdError(RuntimeError):
@@ -73,15 +82,17 @@ class _Lib:
                     conv.append(None)
                 elif hasattr(a, 'data_ptr'):
                     conv.append(a.data_ptr())
+                elif isinstance(a, (bytes, int)):
+                    conv.append(a)
                 else:
-                    conv.append(int(a))
+                    conv.append(a)          # ctypes byref()/pointer/array
             else:
                 conv.append(a)
         if len(conv) != len(self.protos[name][1]):
             raise TypeError('{} expects {} arguments, got {}'.format(
                 name, len(self.protos[name][1]), len(conv)))
         rc = fn(*conv)
-        if self.protos[name][0] is ctypes.c_int and rc != 0:
+        if self.protos[name][0] is ctypes.c_int and name not in _VALUE_INT and rc != 0:
             raise VpdError('{} failed: {}'.format(name, self.last_error()))
         return rc
 

@@ -1,0 +1,68 @@
+"""Python face of K1 (frame-batch assembly) - see include/vpd_b200.h.
+
+`assemble_batch` / `assemble_apply` reproduce what the reference's Dataset
+`__getitem__` + DataLoader collation produce for the deterministic part of
+vpd_dataset/single_frame.py:168-206 and :373-400, from uint8 crops already on
+the device."""
+import torch
+
+from ._lib import lib, stream_ptr
+
+
+def _mean_std(rgb_mean_std):
+    mean = torch.tensor([float(v) for v in rgb_mean_std[0]], dtype=torch.float32)
+    std = torch.tensor([float(v) for v in rgb_mean_std[1]], dtype=torch.float32)
+    return mean, std
+
+
+def assemble_batch(rgb, flow, rgb_mean_std, flip=None, teacher=None, index=None):
+    """-> {'img': fp32 [B,C,H,W], 'emb': fp32 [B,E] (if teacher given)} on the device.
+
+    rgb uint8 [P,H,W,3]; flow uint8 [P,H,W,>=2] or None; flip uint8 [B] or None;
+    teacher fp32 [P,2,E] (rows unflipped/flipped) or [P,E]; index int32 [B] or None."""
+    mean, std = _mean_std(rgb_mean_std)
+    P, H, W, _ = rgb.shape
+    B = P if index is None else index.numel()
+    C = 5 if flow is not None else 3
+    img = torch.empty((B, 1, C, H, W), device=rgb.device, dtype=torch.float32)
+    emb = None
+    rows = tdim = 0
+    if teacher is not None:
+        teacher = teacher.contiguous()
+        rows = teacher.shape[1] if teacher.dim() == 3 else 1
+        tdim = teacher.shape[-1]
+        emb = torch.empty((B, tdim), device=rgb.device, dtype=torch.float32)
+    lib().call('vpd_assemble_nchw', rgb, flow, 0 if flow is None else flow.shape[-1], index, flip,
+               teacher, rows, tdim, mean, std, img, emb, B, H, W, 1, stream_ptr(rgb.device))
+    out = {'img': img[:, 0]}
+    if emb is not None:
+        out['emb'] = emb
+    return out
+
+
+def assemble_apply(rgb, flow, rgb_mean_std, flip=True):
+    """FrameDataset batch: fp32 [B,k,C,H,W], k = 2 ([orig, flipped]) or 1."""
+    mean, std = _mean_std(rgb_mean_std)
+    B, H, W, _ = rgb.shape
+    k = 2 if flip else 1
+    C = 5 if flow is not None else 3
+    img = torch.empty((B, k, C, H, W), device=rgb.device, dtype=torch.float32)
+    lib().call('vpd_assemble_nchw', rgb, flow, 0 if flow is None else flow.shape[-1], None, None,
+               None, 0, 0, mean, std, img, None, B, H, W, k, stream_ptr(rgb.device))
+    return img
+
+
+def assemble_stem(out, rgb, flow, rgb_mean_std, flip=None, teacher=None, index=None, k=1,
+                  tgt=None):
+    """Fused device pipeline: write the network's own bf16 input layout
+    [B*k, H+6, W+8, 8] straight into `out` (tensor or raw pointer)."""
+    mean, std = _mean_std(rgb_mean_std)
+    P, H, W, _ = rgb.shape
+    B = P if index is None else index.numel()
+    rows = tdim = 0
+    if teacher is not None:
+        rows = teacher.shape[1] if teacher.dim() == 3 else 1
+        tdim = teacher.shape[-1]
+    lib().call('vpd_assemble_stem', rgb, flow, 0 if flow is None else flow.shape[-1], index, flip,
+               teacher, rows, tdim, mean, std, out, tgt, B, H, W, k, stream_ptr(rgb.device))
+    return B * k

@@ -2,6 +2,7 @@
 #include "../../include/vpd_b200.h"
 
 #include "conv.h"
+#include "net.h"
 #include "ops.h"
 
 using namespace vpd;
@@ -106,6 +107,44 @@ int vpd_stem_conv_wgrad(const void* x_stem, const void* dy, float* dw, int N, in
   WgradLaunch L;
   if (plan_stem_wgrad(&L, N, H, W, (const bf16*)x_stem, (const bf16*)dy, dw)) return -1;
   return launch_wgrad(L, (cudaStream_t)stream);
+}
+
+vpd_net* vpd_net_create(const char* arch, int emb_dim, int in_channels, int H, int W,
+                        int max_batch, int motion) {
+  return (vpd_net*)net_create(arch, emb_dim, in_channels, H, W, max_batch, motion);
+}
+void vpd_net_destroy(vpd_net* net) { net_destroy((Net*)net); }
+int64_t vpd_net_param_count(vpd_net* net) { return net_param_count((Net*)net); }
+int64_t vpd_net_conv_param_count(vpd_net* net) { return net_conv_section_len((Net*)net); }
+int64_t vpd_net_buffer_count(vpd_net* net) { return net_buffer_count((Net*)net); }
+int vpd_net_num_bn(vpd_net* net) { return net_num_bn((Net*)net); }
+int64_t vpd_net_workspace_bytes(vpd_net* net) { return net_workspace_bytes((Net*)net); }
+int vpd_net_num_tensors(vpd_net* net) { return net_num_tensors((Net*)net); }
+int vpd_net_tensor_info(vpd_net* net, int i, char* name, int name_cap, int* arena,
+                        int64_t* offset, int* layout, int* ndim, int64_t* shape4) {
+  return net_tensor_info((Net*)net, i, name, name_cap, arena, (long long*)offset, layout, ndim,
+                         (long long*)shape4);
+}
+int vpd_net_bind(vpd_net* net, float* params, float* grads, float* buffers, int64_t* nbt,
+                 void* workspace, int64_t workspace_bytes) {
+  return net_bind((Net*)net, params, grads, buffers, (long long*)nbt, workspace, workspace_bytes);
+}
+int vpd_net_params_changed(vpd_net* net) {
+  net_params_changed((Net*)net);
+  return 0;
+}
+void* vpd_net_stem_input(vpd_net* net) { return net_stem_input((Net*)net); }
+int vpd_net_forward(vpd_net* net, const float* x_nchw, const void* x_stem, int B,
+                    float* emb_out, void* stream) {
+  return net_forward((Net*)net, x_nchw, x_stem, B, emb_out, (cudaStream_t)stream);
+}
+int vpd_net_eval_loss(vpd_net* net, const float* x_nchw, const void* x_stem,
+                      const float* target, int B, double* loss_sum, float* out, void* stream) {
+  return net_eval_loss((Net*)net, x_nchw, x_stem, target, B, loss_sum, out, (cudaStream_t)stream);
+}
+int vpd_net_train_step(vpd_net* net, const float* x_nchw, const void* x_stem,
+                       const float* target, int B, double* loss_sum, void* stream) {
+  return net_train_step((Net*)net, x_nchw, x_stem, target, B, loss_sum, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -247,7 +247,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 rv = __ldg(rp + j);
+            const uint4 rv = rp[j];  // plain load: residual may alias out
             f[8 * j + 0] += bf16_lo(rv.x);
             f[8 * j + 1] += bf16_hi(rv.x);
             f[8 * j + 2] += bf16_lo(rv.y);

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_kernel(const BnBwdParams p)
   for (long long row = beg + r0; row < end; row += rstep) {
     const size_t off = (size_t)row * p.C + g * 8;
     float gr[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(p.dz + off)), gr);
+    unpack8(*reinterpret_cast<const uint4*>(p.dz + off), gr);  // may alias dmask/dy
     if (p.z != nullptr) {
       float zz[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(p.z + off)), zz);

@@ -1,0 +1,794 @@
+// The student network as a native execution plan:
+// ResNet-18/34 BasicBlock encoder + fc head (+ FCNet decoder), forward in
+// eval and train mode, loss, and the full backward pass producing gradients
+// in a flat fp32 arena. The host object owns NO device memory: parameters,
+// gradients, BN buffers and one scratch workspace are bound by the caller.
+//
+// Arena layout (fp32, every tensor padded to a multiple of 4 floats):
+//   [A] conv weights, tap-major: stem [7][64][64] (kh, cout, kw*8+c), then
+//       per block conv1, conv2, (downsample) as [k*k][Cout][Cin]
+//   [B] all BN gammas, then all BN betas (concatenated over layers)
+//   [C] fc weight [D][F], fc bias [D]
+//   [D] decoder layers.{0,2,5} weight/bias (motion models)
+// BN running statistics live in a second arena: all means, then all variances.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv.h"
+#include "elementwise.cuh"
+#include "head.h"
+#include "net.h"
+#include "ops.h"
+
+namespace vpd {
+
+typedef __nv_bfloat16 bf16;
+
+static long long pad4(long long n) { return (n + 3) & ~3LL; }
+
+struct BnDesc {
+  int C;
+  long long ch_off;  // offset into the concatenated channel axis of section [B]
+  int idx;
+};
+struct ConvDesc {
+  int Cin, Cout, k, stride, pad;
+  long long w_off;   // into section [A] (floats; same offsets in the bf16 mirrors)
+  int Hin, Win;      // input spatial dims
+};
+struct BlockDesc {
+  std::string prefix;
+  ConvDesc c1, c2, ds;
+  BnDesc b1, b2, bds;
+  bool has_ds;
+  // workspace activations (bf16 NHWC)
+  bf16 *y1, *z1, *y2, *yds, *zout;
+};
+
+struct TensorInfo {
+  std::string name;
+  int arena;  // 0 params, 1 buffers (fp32), 2 num_batches_tracked (int64)
+  long long offset;
+  int layout;  // 0 plain, 1 conv tap-major [k*k][Cout][Cin], 2 stem packed [7][64][64]
+  int ndim;
+  long long shape[4];
+};
+
+struct Plan {  // everything that depends on the batch size
+  int B;
+  ConvLaunch stem_train, stem_eval;
+  std::vector<ConvLaunch> c1_train, c2_train, ds_train, c1_eval, c2_eval, ds_eval;
+  std::vector<ConvLaunch> dgrad2;                // conv2 data grad per block
+  std::vector<std::vector<ConvLaunch>> dgrad1;   // conv1 (+ds) data grad per block
+  std::vector<WgradLaunch> wg1, wg2, wgds;
+  WgradLaunch wg_stem;
+};
+
+struct Net {
+  // configuration
+  std::string arch;
+  int D, Cimg, H, W, maxB, motion, T, Hd, F;
+  std::vector<BlockDesc> blocks;
+  ConvDesc stem;
+  BnDesc stem_bn;
+  int num_bn;
+  long long total_ch;
+  // arena offsets (floats)
+  long long secA, secA_len, gamma_off, beta_off, fc_w_off, fc_b_off, dec_off[6], n_params;
+  long long n_buffers;
+  std::vector<TensorInfo> tensors;
+  // bound memory
+  float *params = nullptr, *grads = nullptr, *buffers = nullptr;
+  long long* nbt = nullptr;
+  uint8_t* ws = nullptr;
+  long long ws_bytes = 0;
+  bool params_dirty = true;
+  // workspace carve
+  long long ws_need = 0;
+  bf16 *w_tap, *wT_tap;            // bf16 mirrors of section [A]
+  double* stats;                   // [2][total_ch] forward sum/sumsq   (zeroed per step)
+  double* bwd_sums;                // [2][total_ch] backward sums        (zeroed per step)
+  double* loss_dev;                // scalar
+  float *save_mean, *save_rstd;    // [total_ch]
+  float *ev_scale, *ev_shift;      // [total_ch]
+  bf16 *x_stem, *y_stem, *z_pool;
+  uint8_t* argmax;
+  bf16 *gA, *gA2, *gB, *gC, *gD, *gStem;
+  float* head_ws;
+  int* tr_table_dev;               // transpose table for the dgrad weight mirrors
+  int tr_blocks;
+  bool tr_uploaded = false;
+  std::vector<int> tr_table_host;
+  std::map<int, Plan*> plans;
+};
+
+// ------------------------------------------------------------------ construction
+static int arch_layers(const std::string& arch, int out[4]) {
+  if (arch == "resnet18") {
+    out[0] = out[1] = out[2] = out[3] = 2;
+    return 0;
+  }
+  if (arch == "resnet34") {
+    out[0] = 3; out[1] = 4; out[2] = 6; out[3] = 3;
+    return 0;
+  }
+  set_error("arch '%s' not supported by the CUDA path (BasicBlock ResNets: resnet18, resnet34)",
+            arch.c_str());
+  return -1;
+}
+
+static void add_tensor(Net* n, const std::string& name, int arena, long long off, int layout,
+                       std::initializer_list<long long> shape) {
+  TensorInfo t;
+  t.name = name;
+  t.arena = arena;
+  t.offset = off;
+  t.layout = layout;
+  t.ndim = (int)shape.size();
+  int i = 0;
+  for (long long s : shape) t.shape[i++] = s;
+  for (; i < 4; ++i) t.shape[i] = 1;
+  n->tensors.push_back(t);
+}
+
+static void add_bn_tensors(Net* n, const std::string& prefix, const BnDesc& b) {
+  add_tensor(n, prefix + ".weight", 0, n->gamma_off + b.ch_off, 0, {b.C});
+  add_tensor(n, prefix + ".bias", 0, n->beta_off + b.ch_off, 0, {b.C});
+  add_tensor(n, prefix + ".running_mean", 1, b.ch_off, 0, {b.C});
+  add_tensor(n, prefix + ".running_var", 1, n->total_ch + b.ch_off, 0, {b.C});
+  add_tensor(n, prefix + ".num_batches_tracked", 2, b.idx, 0, {});
+}
+
+Net* net_create(const char* arch, int emb_dim, int in_channels, int H, int W, int max_batch,
+                int motion) {
+  int layers[4];
+  if (arch_layers(arch, layers)) return nullptr;
+  if (in_channels < 1 || in_channels > 8 || H % 32 != 0 || W % 32 != 0 || H < 32 || W < 32) {
+    set_error("net: unsupported input %dx%dx%d (channels 1..8, H and W multiples of 32)",
+              in_channels, H, W);
+    return nullptr;
+  }
+  if (emb_dim < 1 || emb_dim > 256 || max_batch < 1) {
+    set_error("net: bad emb_dim %d / max_batch %d", emb_dim, max_batch);
+    return nullptr;
+  }
+  Net* n = new Net();
+  n->arch = arch;
+  n->D = emb_dim;
+  n->Cimg = in_channels;
+  n->H = H;
+  n->W = W;
+  n->maxB = max_batch;
+  n->motion = motion ? 1 : 0;
+  n->T = motion ? 2 * emb_dim : emb_dim;
+  n->Hd = 128;
+  n->F = 512;
+
+  // ---- section [A]: conv weights
+  long long wo = 0, ch = 0;
+  int bn_idx = 0;
+  auto mk_bn = [&](int C) {
+    BnDesc b{C, ch, bn_idx++};
+    ch += C;
+    return b;
+  };
+  n->stem = ConvDesc{64, 64, 7, 2, 3, wo, H, W};
+  wo += 7 * 64 * 64;
+  n->stem_bn = mk_bn(64);
+  int inpl = 64, h = H / 4, w = W / 4;
+  const int planes[4] = {64, 128, 256, 512};
+  for (int s = 0; s < 4; ++s)
+    for (int b = 0; b < layers[s]; ++b) {
+      BlockDesc bd;
+      char buf[64];
+      snprintf(buf, sizeof(buf), "resnet.layer%d.%d", s + 1, b);
+      bd.prefix = buf;
+      const int stride = (b == 0 && s > 0) ? 2 : 1;
+      const int cout = planes[s];
+      bd.has_ds = (b == 0) && (stride != 1 || inpl != cout);
+      bd.c1 = ConvDesc{inpl, cout, 3, stride, 1, wo, h, w};
+      wo += 9LL * cout * inpl;
+      bd.b1 = mk_bn(cout);
+      const int ho = h / stride, wo2 = w / stride;
+      bd.c2 = ConvDesc{cout, cout, 3, 1, 1, wo, ho, wo2};
+      wo += 9LL * cout * cout;
+      bd.b2 = mk_bn(cout);
+      if (bd.has_ds) {
+        bd.ds = ConvDesc{inpl, cout, 1, stride, 0, wo, h, w};
+        wo += 1LL * cout * inpl;
+        bd.bds = mk_bn(cout);
+      }
+      n->blocks.push_back(bd);
+      inpl = cout;
+      h = ho;
+      w = wo2;
+    }
+  n->num_bn = bn_idx;
+  n->total_ch = ch;
+  n->secA = 0;
+  n->secA_len = wo;
+  long long off = pad4(wo);
+  n->gamma_off = off;
+  off += pad4(ch);
+  n->beta_off = off;
+  off += pad4(ch);
+  n->fc_w_off = off;
+  off += pad4((long long)n->D * n->F);
+  n->fc_b_off = off;
+  off += pad4(n->D);
+  if (n->motion) {
+    const long long sz[6] = {(long long)n->Hd * n->D, n->Hd, (long long)n->Hd * n->Hd, n->Hd,
+                             (long long)n->T * n->Hd, n->T};
+    for (int i = 0; i < 6; ++i) {
+      n->dec_off[i] = off;
+      off += pad4(sz[i]);
+    }
+  }
+  n->n_params = off;
+  n->n_buffers = 2 * n->total_ch;
+
+  // ---- tensor table in the reference's state_dict order
+  add_tensor(n, "resnet.conv1.weight", 0, n->stem.w_off, 2, {64, in_channels, 7, 7});
+  add_bn_tensors(n, "resnet.bn1", n->stem_bn);
+  for (auto& bd : n->blocks) {
+    add_tensor(n, bd.prefix + ".conv1.weight", 0, bd.c1.w_off, 1, {bd.c1.Cout, bd.c1.Cin, 3, 3});
+    add_bn_tensors(n, bd.prefix + ".bn1", bd.b1);
+    add_tensor(n, bd.prefix + ".conv2.weight", 0, bd.c2.w_off, 1, {bd.c2.Cout, bd.c2.Cin, 3, 3});
+    add_bn_tensors(n, bd.prefix + ".bn2", bd.b2);
+    if (bd.has_ds) {
+      add_tensor(n, bd.prefix + ".downsample.0.weight", 0, bd.ds.w_off, 1,
+                 {bd.ds.Cout, bd.ds.Cin, 1, 1});
+      add_bn_tensors(n, bd.prefix + ".downsample.1", bd.bds);
+    }
+  }
+  add_tensor(n, "resnet.fc.weight", 0, n->fc_w_off, 0, {n->D, n->F});
+  add_tensor(n, "resnet.fc.bias", 0, n->fc_b_off, 0, {n->D});
+  if (n->motion) {
+    add_tensor(n, "decoder.layers.0.weight", 0, n->dec_off[0], 0, {n->Hd, n->D});
+    add_tensor(n, "decoder.layers.0.bias", 0, n->dec_off[1], 0, {n->Hd});
+    add_tensor(n, "decoder.layers.2.weight", 0, n->dec_off[2], 0, {n->Hd, n->Hd});
+    add_tensor(n, "decoder.layers.2.bias", 0, n->dec_off[3], 0, {n->Hd});
+    add_tensor(n, "decoder.layers.5.weight", 0, n->dec_off[4], 0, {n->T, n->Hd});
+    add_tensor(n, "decoder.layers.5.bias", 0, n->dec_off[5], 0, {n->T});
+  }
+
+  // ---- workspace carve (offsets only; pointers are fixed up in bind)
+  // transposed-mirror table: one entry per 32x32 tile of every (conv, tap)
+  for (auto& bd : n->blocks) {
+    const ConvDesc* cs[3] = {&bd.c1, &bd.c2, bd.has_ds ? &bd.ds : nullptr};
+    for (const ConvDesc* c : cs) {
+      if (!c) continue;
+      for (int t = 0; t < c->k * c->k; ++t)
+        for (int r = 0; r < c->Cout / 32; ++r)
+          for (int q = 0; q < c->Cin / 32; ++q) {
+            // src offset of the (tap) matrix, rows, cols, tile row, tile col
+            n->tr_table_host.push_back((int)(c->w_off + (long long)t * c->Cout * c->Cin));
+            n->tr_table_host.push_back(c->Cout);
+            n->tr_table_host.push_back(c->Cin);
+            n->tr_table_host.push_back(r);
+            n->tr_table_host.push_back(q);
+          }
+    }
+  }
+  n->tr_blocks = (int)(n->tr_table_host.size() / 5);
+  return n;
+}
+
+void net_destroy(Net* n) {
+  if (!n) return;
+  for (auto& kv : n->plans) delete kv.second;
+  delete n;
+}
+
+// workspace carving ------------------------------------------------------------
+struct Carver {
+  uint8_t* base;
+  long long off = 0;
+  template <typename T>
+  T* take(long long count) {
+    off = (off + 1023) & ~1023LL;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * (long long)sizeof(T);
+    return p;
+  }
+};
+
+static long long carve(Net* n, uint8_t* base) {
+  Carver c{base};
+  const long long B = n->maxB;
+  n->w_tap = c.take<bf16>(n->secA_len);
+  n->wT_tap = c.take<bf16>(n->secA_len);
+  n->stats = c.take<double>(2 * n->total_ch);
+  n->bwd_sums = c.take<double>(2 * n->total_ch);
+  n->loss_dev = c.take<double>(8);
+  n->save_mean = c.take<float>(n->total_ch);
+  n->save_rstd = c.take<float>(n->total_ch);
+  n->ev_scale = c.take<float>(n->total_ch);
+  n->ev_shift = c.take<float>(n->total_ch);
+  n->tr_table_dev = c.take<int>((long long)n->tr_table_host.size());
+  n->x_stem = c.take<bf16>(B * (n->H + 6) * (n->W + 8) * 8);
+  const long long stem_out = B * (n->H / 2) * (n->W / 2) * 64;
+  n->y_stem = c.take<bf16>(stem_out);
+  const long long l1 = B * (n->H / 4) * (n->W / 4) * 64;
+  n->z_pool = c.take<bf16>(l1);
+  n->argmax = c.take<uint8_t>(l1);
+  for (auto& bd : n->blocks) {
+    const long long sz = B * (bd.c2.Hin) * (bd.c2.Win) * bd.c2.Cout;
+    bd.y1 = c.take<bf16>(sz);
+    bd.z1 = c.take<bf16>(sz);
+    bd.y2 = c.take<bf16>(sz);
+    bd.yds = bd.has_ds ? c.take<bf16>(sz) : nullptr;
+    bd.zout = c.take<bf16>(sz);
+  }
+  n->gA = c.take<bf16>(l1);
+  n->gA2 = c.take<bf16>(l1);
+  n->gB = c.take<bf16>(l1);
+  n->gC = c.take<bf16>(l1);
+  n->gD = c.take<bf16>(l1);
+  n->gStem = c.take<bf16>(stem_out);
+  n->head_ws = c.take<float>(B * head_ws_stride(n->F, n->D, n->Hd, n->T));
+  return c.off + 1024;
+}
+
+long long net_workspace_bytes(Net* n) {
+  if (n->ws_need == 0) {
+    Net tmp = *n;  // carve on a copy so unbound pointers stay null
+    tmp.plans.clear();
+    n->ws_need = carve(&tmp, nullptr);
+  }
+  return n->ws_need;
+}
+
+int net_bind(Net* n, float* params, float* grads, float* buffers, long long* nbt, void* ws,
+             long long ws_bytes) {
+  VPD_REQUIRE(params && buffers && nbt && ws, "net_bind: null arena");
+  VPD_REQUIRE(ws_bytes >= net_workspace_bytes(n), "net_bind: workspace too small (%lld < %lld)",
+              ws_bytes, net_workspace_bytes(n));
+  VPD_REQUIRE(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)buffers | (uintptr_t)ws) % 16 == 0,
+              "net_bind: arenas must be 16-byte aligned");
+  n->params = params;
+  n->grads = grads;
+  n->buffers = buffers;
+  n->nbt = nbt;
+  n->ws = (uint8_t*)(((uintptr_t)ws + 1023) & ~(uintptr_t)1023);
+  n->ws_bytes = ws_bytes;
+  carve(n, n->ws);
+  for (auto& kv : n->plans) delete kv.second;
+  n->plans.clear();
+  n->params_dirty = true;
+  n->tr_uploaded = false;
+  return 0;
+}
+
+// ------------------------------------------------------------------ weight mirrors
+__global__ void cast_weights_kernel(const float* __restrict__ w, bf16* __restrict__ o, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(w + i);
+    uint2 r;
+    r.x = pack_bf16x2(v.x, v.y);
+    r.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(o + i) = r;
+  } else {
+    for (long long j = i; j < n; ++j) o[j] = __float2bfloat16_rn(w[j]);
+  }
+}
+
+// wT[tap][ci][co] = bf16(w[tap][co][ci]); one 32x32 tile per block, table-driven
+__global__ void __launch_bounds__(256)
+transpose_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wT,
+                         const int* __restrict__ table) {
+  __shared__ float tile[32][33];
+  const int* e = table + blockIdx.x * 5;
+  const long long base = e[0];
+  const int rows = e[1], cols = e[2], tr = e[3] * 32, tc = e[4] * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = w[base + (long long)(tr + r) * cols + tc + tx];
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8)
+    wT[base + (long long)(tc + r) * rows + tr + tx] = __float2bfloat16_rn(tile[tx][r]);
+}
+
+static int pack_weights(Net* n, cudaStream_t s) {
+  if (!n->tr_uploaded) {
+    VPD_CHECK_CUDA(cudaMemcpyAsync(n->tr_table_dev, n->tr_table_host.data(),
+                                   n->tr_table_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    n->tr_uploaded = true;
+  }
+  const long long n4 = (n->secA_len + 3) / 4;
+  cast_weights_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(n->params + n->secA, n->w_tap,
+                                                                  n->secA_len);
+  transpose_weights_kernel<<<n->tr_blocks, 256, 0, s>>>(n->params + n->secA, n->wT_tap,
+                                                        n->tr_table_dev);
+  VPD_CHECK_CUDA(cudaGetLastError());
+  n->params_dirty = false;
+  return 0;
+}
+
+// ----------------------------------------------------------------------- planning
+static BnLayer bn_layer(Net* n, const BnDesc& b, bool train, long long count) {
+  BnLayer L;
+  L.stats = train ? n->stats + 2 * b.ch_off : nullptr;  // [2][C] block per layer
+  L.gamma = n->params + n->gamma_off + b.ch_off;
+  L.beta = n->params + n->beta_off + b.ch_off;
+  L.running_mean = n->buffers + b.ch_off;
+  L.running_var = n->buffers + n->total_ch + b.ch_off;
+  L.num_batches = n->nbt + b.idx;
+  L.save_mean = n->save_mean + b.ch_off;
+  L.save_rstd = n->save_rstd + b.ch_off;
+  L.count = (float)count;
+  L.momentum = 0.1f;
+  L.eps = 1e-5f;
+  L.update_running = train ? 1 : 0;
+  return L;
+}
+
+static ConvGeom geom(const ConvDesc& c, int B) {
+  return ConvGeom{B, c.Hin, c.Win, c.Cin, c.Cout, c.k, c.stride, c.pad};
+}
+
+static Plan* get_plan(Net* n, int B) {
+  auto it = n->plans.find(B);
+  if (it != n->plans.end()) return it->second;
+  Plan* P = new Plan();
+  P->B = B;
+  const size_t nb = n->blocks.size();
+  P->c1_train.resize(nb); P->c2_train.resize(nb); P->ds_train.resize(nb);
+  P->c1_eval.resize(nb); P->c2_eval.resize(nb); P->ds_eval.resize(nb);
+  P->dgrad2.resize(nb); P->dgrad1.resize(nb);
+  P->wg1.resize(nb); P->wg2.resize(nb); P->wgds.resize(nb);
+  bool ok = true;
+  auto ev = [&](const BnDesc& b, const bf16* res, int relu) {
+    ConvEpilogue e;
+    e.scale = n->ev_scale + b.ch_off;
+    e.shift = n->ev_shift + b.ch_off;
+    e.residual = res;
+    e.relu = relu;
+    return e;
+  };
+  auto tr = [&](const BnDesc& b) {
+    ConvEpilogue e;
+    e.stats = n->stats + 2 * b.ch_off;
+    return e;
+  };
+  const bf16* wt = n->w_tap;
+  const bf16* wT = n->wT_tap;
+  ok &= !plan_stem_fwd(&P->stem_train, B, n->H, n->W, n->x_stem, wt + n->stem.w_off, n->y_stem,
+                       tr(n->stem_bn));
+  ok &= !plan_stem_fwd(&P->stem_eval, B, n->H, n->W, n->x_stem, wt + n->stem.w_off, n->y_stem,
+                       ev(n->stem_bn, nullptr, 1));
+  if (n->grads)
+    ok &= !plan_stem_wgrad(&P->wg_stem, B, n->H, n->W, n->x_stem, n->gStem,
+                           n->grads + n->stem.w_off);
+  const bf16* zin = n->z_pool;
+  bf16* gcur = n->gA;   // buffer holding dz_out of the block being processed (backward order!)
+  // backward walks blocks in reverse; the ping-pong assignment is resolved below
+  std::vector<bf16*> g_out(nb), g_in(nb);
+  {
+    bf16* cur = n->gA;
+    bf16* other = n->gA2;
+    for (int i = (int)nb - 1; i >= 0; --i) {
+      g_out[i] = cur;                       // dz_out lives here
+      if (n->blocks[i].has_ds) {            // dz_in has another shape -> other buffer
+        g_in[i] = other;
+        std::swap(cur, other);
+      } else {
+        g_in[i] = cur;                      // in place (identity residual)
+      }
+    }
+  }
+  (void)gcur;
+  for (size_t i = 0; i < nb && ok; ++i) {
+    BlockDesc& bd = n->blocks[i];
+    const ConvGeom g1 = geom(bd.c1, B), g2 = geom(bd.c2, B);
+    ok &= !plan_conv_fwd(&P->c1_train[i], g1, zin, wt + bd.c1.w_off, bd.y1, tr(bd.b1));
+    ok &= !plan_conv_fwd(&P->c2_train[i], g2, bd.z1, wt + bd.c2.w_off, bd.y2, tr(bd.b2));
+    ok &= !plan_conv_fwd(&P->c1_eval[i], g1, zin, wt + bd.c1.w_off, bd.z1, ev(bd.b1, nullptr, 1));
+    const bf16* res = zin;
+    if (bd.has_ds) {
+      const ConvGeom gd = geom(bd.ds, B);
+      ok &= !plan_conv_fwd(&P->ds_train[i], gd, zin, wt + bd.ds.w_off, bd.yds, tr(bd.bds));
+      ok &= !plan_conv_fwd(&P->ds_eval[i], gd, zin, wt + bd.ds.w_off, bd.yds, ev(bd.bds, nullptr, 0));
+      res = bd.yds;
+    }
+    ok &= !plan_conv_fwd(&P->c2_eval[i], g2, bd.z1, wt + bd.c2.w_off, bd.zout, ev(bd.b2, res, 1));
+    if (n->grads) {
+      // backward: dy2 in gB, dz1/dy1 in gC, dy_ds in gD
+      int cnt = 0;
+      ConvLaunch tmp[4];
+      ok &= !plan_conv_dgrad(tmp, &cnt, g2, n->gB, wT + bd.c2.w_off, n->gC, nullptr, nullptr,
+                             nullptr, 0);
+      P->dgrad2[i] = tmp[0];
+      ok &= !plan_conv_wgrad(&P->wg2[i], g2, bd.z1, n->gB, n->grads + bd.c2.w_off);
+      ok &= !plan_conv_wgrad(&P->wg1[i], g1, zin, n->gC, n->grads + bd.c1.w_off);
+      if (bd.has_ds) {
+        ok &= !plan_conv_wgrad(&P->wgds[i], geom(bd.ds, B), zin, n->gD, n->grads + bd.ds.w_off);
+        if (bd.c1.stride == 2) {
+          ok &= !plan_conv_dgrad(tmp, &cnt, g1, n->gC, wT + bd.c1.w_off, g_in[i], nullptr, n->gD,
+                                 wT + bd.ds.w_off, bd.ds.Cout);
+        } else {
+          set_error("net: stride-1 downsample blocks are not supported");
+          ok = false;
+        }
+      } else {
+        ok &= !plan_conv_dgrad(tmp, &cnt, g1, n->gC, wT + bd.c1.w_off, g_in[i], g_out[i], nullptr,
+                               nullptr, 0);
+      }
+      P->dgrad1[i].assign(tmp, tmp + cnt);
+    }
+    zin = bd.zout;
+  }
+  if (!ok) {
+    delete P;
+    return nullptr;
+  }
+  n->plans[B] = P;
+  return P;
+}
+
+// ------------------------------------------------------------------------ running
+static int prepare_input(Net* n, const float* x_nchw, const void* x_stem, int B, cudaStream_t s) {
+  VPD_REQUIRE(n->params != nullptr, "net: arenas not bound");
+  VPD_REQUIRE(B >= 1 && B <= n->maxB, "net: batch %d outside [1, %d]", B, n->maxB);
+  if (x_nchw != nullptr) return nchw_to_pad8(x_nchw, n->x_stem, B, n->Cimg, n->H, n->W, s);
+  VPD_REQUIRE(x_stem != nullptr, "net: no input given");
+  if (x_stem != n->x_stem) {
+    VPD_CHECK_CUDA(cudaMemcpyAsync(n->x_stem, x_stem,
+                                   (size_t)B * (n->H + 6) * (n->W + 8) * 8 * sizeof(bf16),
+                                   cudaMemcpyDeviceToDevice, s));
+  }
+  return 0;
+}
+
+static HeadParams head_params(Net* n, const bf16* z, int B) {
+  HeadParams h;
+  memset(&h, 0, sizeof(h));
+  h.z = z;
+  h.B = B;
+  h.HW = (n->H / 32) * (n->W / 32);
+  h.F = n->F;
+  h.D = n->D;
+  h.T = n->T;
+  h.Hd = n->Hd;
+  h.motion = n->motion;
+  h.fc_w = n->params + n->fc_w_off;
+  h.fc_b = n->params + n->fc_b_off;
+  if (n->motion) {
+    h.w0 = n->params + n->dec_off[0];
+    h.b0 = n->params + n->dec_off[1];
+    h.w2 = n->params + n->dec_off[2];
+    h.b2 = n->params + n->dec_off[3];
+    h.w5 = n->params + n->dec_off[4];
+    h.b5 = n->params + n->dec_off[5];
+  }
+  return h;
+}
+
+static int forward_eval_body(Net* n, Plan* P, int B, cudaStream_t s) {
+  if (n->params_dirty && pack_weights(n, s)) return -1;
+  if (launch_bn_fold(n->params + n->gamma_off, n->params + n->beta_off, n->buffers,
+                     n->buffers + n->total_ch, 1e-5f, n->ev_scale, n->ev_shift, (int)n->total_ch, s))
+    return -1;
+  if (launch_conv(P->stem_eval, s)) return -1;
+  if (launch_maxpool(n->y_stem, n->z_pool, B, n->H / 2, n->W / 2, 64, s)) return -1;
+  for (size_t i = 0; i < n->blocks.size(); ++i) {
+    if (launch_conv(P->c1_eval[i], s)) return -1;
+    if (n->blocks[i].has_ds && launch_conv(P->ds_eval[i], s)) return -1;
+    if (launch_conv(P->c2_eval[i], s)) return -1;
+  }
+  return 0;
+}
+
+int net_forward(Net* n, const float* x_nchw, const void* x_stem, int B, float* emb_out,
+                cudaStream_t s) {
+  if (prepare_input(n, x_nchw, x_stem, B, s)) return -1;
+  Plan* P = get_plan(n, B);
+  if (!P) return -1;
+  if (forward_eval_body(n, P, B, s)) return -1;
+  HeadParams h = head_params(n, n->blocks.back().zout, B);
+  h.emb_out = emb_out;
+  h.motion = 0;  // the decoder is not part of the embedding (apply_vpd_model.py:141-162)
+  h.T = h.D;
+  return launch_head(h, nullptr, s);
+}
+
+int net_eval_loss(Net* n, const float* x_nchw, const void* x_stem, const float* target, int B,
+                  double* loss_sum, float* out, cudaStream_t s) {
+  if (prepare_input(n, x_nchw, x_stem, B, s)) return -1;
+  Plan* P = get_plan(n, B);
+  if (!P) return -1;
+  if (forward_eval_body(n, P, B, s)) return -1;
+  HeadParams h = head_params(n, n->blocks.back().zout, B);
+  h.target = target;
+  h.loss = loss_sum;
+  h.out = out;
+  return launch_head(h, nullptr, s);
+}
+
+int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float* target, int B,
+                   double* loss_sum, cudaStream_t s) {
+  VPD_REQUIRE(n->grads != nullptr, "net: gradient arena not bound");
+  VPD_REQUIRE(target != nullptr && loss_sum != nullptr, "net_train_step: null target/loss");
+  if (prepare_input(n, x_nchw, x_stem, B, s)) return -1;
+  Plan* P = get_plan(n, B);
+  if (!P) return -1;
+  // zero: BN statistics (fwd + bwd, contiguous) and the conv-weight gradients
+  VPD_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, (size_t)((uint8_t*)n->loss_dev - (uint8_t*)n->stats), s));
+  VPD_CHECK_CUDA(cudaMemsetAsync(n->grads + n->secA, 0, (size_t)n->secA_len * sizeof(float), s));
+  if (pack_weights(n, s)) return -1;
+
+  // ------------------------------------------------------------------ forward
+  if (launch_conv(P->stem_train, s)) return -1;
+  {
+    PoolParams pp;
+    pp.y = n->y_stem;
+    pp.z = n->z_pool;
+    pp.argmax = n->argmax;
+    pp.N = B;
+    pp.H = n->H / 2;
+    pp.W = n->W / 2;
+    pp.C = 64;
+    pp.bn = bn_layer(n, n->stem_bn, true, (long long)B * pp.H * pp.W);
+    if (launch_bn_pool(pp, s)) return -1;
+  }
+  const bf16* zin = n->z_pool;
+  for (size_t i = 0; i < n->blocks.size(); ++i) {
+    BlockDesc& bd = n->blocks[i];
+    const long long M = (long long)B * bd.c2.Hin * bd.c2.Win;
+    if (launch_conv(P->c1_train[i], s)) return -1;
+    BnApplyParams a;
+    memset(&a, 0, sizeof(a));
+    a.y = bd.y1;
+    a.z = bd.z1;
+    a.M = M;
+    a.C = bd.c1.Cout;
+    a.relu = 1;
+    a.bn = bn_layer(n, bd.b1, true, M);
+    if (launch_bn_apply(a, s)) return -1;
+    if (launch_conv(P->c2_train[i], s)) return -1;
+    if (bd.has_ds && launch_conv(P->ds_train[i], s)) return -1;
+    memset(&a, 0, sizeof(a));
+    a.y = bd.y2;
+    a.z = bd.zout;
+    a.M = M;
+    a.C = bd.c2.Cout;
+    a.relu = 1;
+    a.bn = bn_layer(n, bd.b2, true, M);
+    if (bd.has_ds) {
+      a.res = bd.yds;
+      a.has_res_bn = 1;
+      a.res_bn = bn_layer(n, bd.bds, true, M);
+    } else {
+      a.res = zin;
+    }
+    if (launch_bn_apply(a, s)) return -1;
+    zin = bd.zout;
+  }
+
+  // ------------------------------------------------------- head: loss + gradient
+  const size_t nb = n->blocks.size();
+  {
+    HeadParams h = head_params(n, n->blocks.back().zout, B);
+    h.target = target;
+    h.loss = loss_sum;
+    h.dz = n->gA;
+    h.ws = n->head_ws;
+    HeadGrads hg;
+    memset(&hg, 0, sizeof(hg));
+    hg.fc_w = n->grads + n->fc_w_off;
+    hg.fc_b = n->grads + n->fc_b_off;
+    if (n->motion) {
+      hg.w0 = n->grads + n->dec_off[0];
+      hg.b0 = n->grads + n->dec_off[1];
+      hg.w2 = n->grads + n->dec_off[2];
+      hg.b2 = n->grads + n->dec_off[3];
+      hg.w5 = n->grads + n->dec_off[4];
+      hg.b5 = n->grads + n->dec_off[5];
+    }
+    if (launch_head(h, &hg, s)) return -1;
+  }
+
+  // ----------------------------------------------------------------- backward
+  bf16* cur = n->gA;
+  bf16* other = n->gA2;
+  for (int i = (int)nb - 1; i >= 0; --i) {
+    BlockDesc& bd = n->blocks[i];
+    const long long M = (long long)B * bd.c2.Hin * bd.c2.Win;
+    BnBwdParams q;
+    memset(&q, 0, sizeof(q));
+    q.dz = cur;
+    q.z = bd.zout;
+    q.dmask = bd.has_ds ? nullptr : cur;  // identity gradient, reused as dgrad residual
+    q.M = M;
+    q.C = bd.c2.Cout;
+    q.nbranch = bd.has_ds ? 2 : 1;
+    const BnDesc* bs[2] = {&bd.b2, &bd.bds};
+    const bf16* ys[2] = {bd.y2, bd.yds};
+    bf16* dys[2] = {n->gB, n->gD};
+    for (int b = 0; b < q.nbranch; ++b) {
+      q.y[b] = ys[b];
+      q.dy[b] = dys[b];
+      q.gamma[b] = n->params + n->gamma_off + bs[b]->ch_off;
+      q.save_mean[b] = n->save_mean + bs[b]->ch_off;
+      q.save_rstd[b] = n->save_rstd + bs[b]->ch_off;
+      q.sums[b] = n->bwd_sums + 2 * bs[b]->ch_off;
+      q.dgamma[b] = n->grads + n->gamma_off + bs[b]->ch_off;
+      q.dbeta[b] = n->grads + n->beta_off + bs[b]->ch_off;
+    }
+    if (launch_bn_bwd(q, s)) return -1;
+    if (launch_wgrad(P->wg2[i], s)) return -1;
+    if (launch_conv(P->dgrad2[i], s)) return -1;  // gB -> gC
+    memset(&q, 0, sizeof(q));
+    q.dz = n->gC;
+    q.z = bd.z1;
+    q.M = M;
+    q.C = bd.c1.Cout;
+    q.nbranch = 1;
+    q.y[0] = bd.y1;
+    q.dy[0] = n->gC;  // in place
+    q.gamma[0] = n->params + n->gamma_off + bd.b1.ch_off;
+    q.save_mean[0] = n->save_mean + bd.b1.ch_off;
+    q.save_rstd[0] = n->save_rstd + bd.b1.ch_off;
+    q.sums[0] = n->bwd_sums + 2 * bd.b1.ch_off;
+    q.dgamma[0] = n->grads + n->gamma_off + bd.b1.ch_off;
+    q.dbeta[0] = n->grads + n->beta_off + bd.b1.ch_off;
+    if (launch_bn_bwd(q, s)) return -1;
+    if (launch_wgrad(P->wg1[i], s)) return -1;
+    if (bd.has_ds && launch_wgrad(P->wgds[i], s)) return -1;
+    for (auto& L : P->dgrad1[i])
+      if (launch_conv(L, s)) return -1;
+    if (bd.has_ds) std::swap(cur, other);
+  }
+  // stem: maxpool + ReLU + BN backward, then the stem weight gradient
+  {
+    StemBwdParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.dpool = cur;
+    sp.argmax = n->argmax;
+    sp.y = n->y_stem;
+    sp.dy = n->gStem;
+    sp.N = B;
+    sp.H = n->H / 2;
+    sp.W = n->W / 2;
+    sp.C = 64;
+    sp.gamma = n->params + n->gamma_off + n->stem_bn.ch_off;
+    sp.beta = n->params + n->beta_off + n->stem_bn.ch_off;
+    sp.save_mean = n->save_mean + n->stem_bn.ch_off;
+    sp.save_rstd = n->save_rstd + n->stem_bn.ch_off;
+    sp.sums = n->bwd_sums + 2 * n->stem_bn.ch_off;
+    sp.dgamma = n->grads + n->gamma_off + n->stem_bn.ch_off;
+    sp.dbeta = n->grads + n->beta_off + n->stem_bn.ch_off;
+    if (launch_stem_bwd(sp, s)) return -1;
+    if (launch_wgrad(P->wg_stem, s)) return -1;
+  }
+  n->params_dirty = true;  // the caller is about to update the parameters
+  return 0;
+}
+
+long long net_param_count(Net* n) { return n->n_params; }
+long long net_buffer_count(Net* n) { return n->n_buffers; }
+int net_num_bn(Net* n) { return n->num_bn; }
+int net_num_tensors(Net* n) { return (int)n->tensors.size(); }
+long long net_conv_section_len(Net* n) { return n->secA_len; }
+void net_params_changed(Net* n) { n->params_dirty = true; }
+void* net_stem_input(Net* n) { return n->x_stem; }
+
+int net_tensor_info(Net* n, int i, char* name, int name_cap, int* arena, long long* offset,
+                    int* layout, int* ndim, long long* shape4) {
+  VPD_REQUIRE(i >= 0 && i < (int)n->tensors.size(), "tensor index %d out of range", i);
+  const TensorInfo& t = n->tensors[i];
+  snprintf(name, name_cap, "%s", t.name.c_str());
+  *arena = t.arena;
+  *offset = t.offset;
+  *layout = t.layout;
+  *ndim = t.ndim;
+  for (int k = 0; k < 4; ++k) shape4[k] = t.shape[k];
+  return 0;
+}
+
+}  // namespace vpd

@@ -1,0 +1,185 @@
+"""`ModelTrainer` - drop-in for train_vpd_model.py:53-112, running the native
+train step (forward, sum-MSE distillation loss, backward, fused AdamW) and, when
+torch.distributed is initialised, summing gradients across ranks with NCCL.
+
+Differences a caller can observe, all deliberate:
+  * `get_optimizer` returns `(FusedAdamW, None)`: no GradScaler is needed because
+    the kernels keep fp32 master weights / accumulators (the reference only uses
+    a scaler for its fp16 autocast path, train_vpd_model.py:100-105);
+  * the loss is accumulated on the device and read back once per epoch instead of
+    `loss.item()` every step (train_vpd_model.py:93); the returned value is the
+    same quantity, sum of losses / number of frames.
+"""
+import os
+
+import torch
+
+from ._lib import lib, stream_ptr, VpdError
+
+
+class FusedAdamW:
+    """torch.optim.AdamW defaults (betas .9/.999, eps 1e-8, weight_decay .01) as one
+    kernel launch over the flat parameter arena (K5)."""
+
+    def __init__(self, encoder, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01):
+        self.encoder = encoder
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.step_count = 0
+        self._m = self._v = None
+
+    def _state(self):
+        p = self.encoder._params
+        if self._m is None or self._m.numel() != p.numel():
+            self._m = torch.zeros_like(p)
+            self._v = torch.zeros_like(p)
+        return self._m, self._v
+
+    def step(self):
+        enc = self.encoder
+        m, v = self._state()
+        self.step_count += 1
+        with torch.cuda.device(enc._dev):
+            lib().call('vpd_adamw', enc._params, enc._grads, m, v, enc._params.numel(), self.lr,
+                       self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                       self.step_count, 1.0, stream_ptr(enc._dev))
+            if enc._net is not None:
+                lib().call('vpd_net_params_changed', enc._net.handle)
+
+    def zero_grad(self, set_to_none=False):
+        pass    # every train step overwrites the whole gradient arena
+
+    def state_dict(self):
+        m, v = self._state()
+        return {'step': self.step_count, 'exp_avg': m.clone(), 'exp_avg_sq': v.clone(),
+                'lr': self.lr, 'betas': self.betas, 'eps': self.eps,
+                'weight_decay': self.weight_decay}
+
+    def load_state_dict(self, sd):
+        m, v = self._state()
+        m.copy_(sd['exp_avg'])
+        v.copy_(sd['exp_avg_sq'])
+        self.step_count = sd['step']
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+class ModelTrainer:
+    """Class for training the encoder. Discarded after training"""
+
+    def __init__(self, encoder, motion):
+        self.encoder = encoder.to(encoder.device)
+        self.motion = bool(motion)
+        if motion:
+            encoder._attach_decoder()
+        dev = encoder._dev
+        self._loss = torch.zeros(1, device=dev, dtype=torch.float64)
+        self._copy_stream = torch.cuda.Stream(device=dev)
+
+    # ------------------------------------------------------------- one batch
+    def _run(self, img, tgt, n, train):
+        enc = self.encoder
+        H, W = img.shape[-2:]
+        with torch.cuda.device(enc._dev):
+            if train:
+                enc._ensure_grads()
+            net = enc._native(H, W, n)
+            fn = 'vpd_net_train_step' if train else 'vpd_net_eval_loss'
+            args = [net.handle, img, None, tgt, n, self._loss]
+            if not train:
+                args.append(None)
+            lib().call(fn, *args, stream_ptr(enc._dev))
+
+    def train_step_stem(self, stem, tgt, n, height, width, optimizer):
+        """Device-resident fast path: input already in the network layout (K1
+        `assemble_stem`), target fp32 [n, T] on the device."""
+        enc = self.encoder
+        with torch.cuda.device(enc._dev):
+            enc._ensure_grads()
+            net = enc._native(height, width, n)
+            lib().call('vpd_net_train_step', net.handle, None, stem, tgt, n, self._loss,
+                       stream_ptr(enc._dev))
+            self._sync_grads()
+            optimizer.step()
+
+    def stem_buffer(self, n, height, width):
+        """Raw device pointer of the bound net's own input buffer (so assembly can
+        write into it without an extra copy)."""
+        enc = self.encoder
+        with torch.cuda.device(enc._dev):
+            enc._ensure_grads()
+            net = enc._native(height, width, n)
+            return lib().call('vpd_net_stem_input', net.handle)
+
+    def _sync_grads(self):
+        dist = _dist()
+        if dist is not None:
+            # reduction='sum' loss => gradients add across ranks (SUM, not mean)
+            dist.all_reduce(self.encoder._grads, op=dist.ReduceOp.SUM)
+
+    def _stage(self, batch):
+        """Start the host->device copies of a batch on the copy stream."""
+        if batch is None:
+            return None
+        dev = self.encoder._dev
+        with torch.cuda.stream(self._copy_stream):
+            img = batch['img'].to(dev, dtype=torch.float32, non_blocking=True)
+            emb = batch['emb'].to(dev, dtype=torch.float32, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        return img, emb, ev
+
+    def epoch(self, data_loader, optimizer=None, scaler=None, progress_cb=None):
+        enc = self.encoder
+        train = optimizer is not None
+        enc.eval() if optimizer is None else enc.train()
+        if self.motion:
+            assert enc.use_flow in (True, False)
+        self._loss.zero_()
+        epoch_n = 0
+        it = iter(data_loader)
+        nxt = self._stage(next(it, None))
+        cur_stream = torch.cuda.current_stream(enc._dev)
+        while nxt is not None:
+            img, emb, ev = nxt
+            nxt = self._stage(next(it, None))        # overlap the next copy with this step
+            cur_stream.wait_event(ev)
+            img = img.contiguous()
+            emb = emb.contiguous()
+            n = img.shape[0]
+            enc._check_channels(img)
+            expect = 2 * enc.emb_dim if self.motion else enc.emb_dim
+            if emb.shape[1] != expect:
+                raise ValueError('target dim {} != {}'.format(emb.shape[1], expect))
+            self._run(img, emb, n, train)
+            img.record_stream(cur_stream)
+            emb.record_stream(cur_stream)
+            if train:
+                self._sync_grads()
+                optimizer.step()
+                optimizer.zero_grad()
+            epoch_n += n
+            if progress_cb is not None:
+                progress_cb(n)
+        total = self._loss.clone()
+        dist = _dist()
+        if dist is not None and train:
+            cnt = torch.tensor([float(epoch_n)], device=enc._dev, dtype=torch.float64)
+            dist.all_reduce(total, op=dist.ReduceOp.SUM)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+            return total.item() / cnt.item()
+        return total.item() / epoch_n
+
+    def get_optimizer(self, learning_rate):
+        return FusedAdamW(self.encoder, learning_rate), None
+
+    def save_model(self, save_dir, name):
+        sd = {k: v.cpu() for k, v in self.encoder.state_dict().items()}
+        torch.save(sd, os.path.join(save_dir, '{}.encoder.pt'.format(name)))
+        if self.motion:
+            dsd = {k: v.cpu() for k, v in self.encoder.decoder_state_dict().items()}
+            torch.save(dsd, os.path.join(save_dir, '{}.decoder.pt'.format(name)))
