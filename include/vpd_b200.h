@@ -151,6 +151,23 @@ VPD_API int vpd_net_eval_loss(vpd_net* net, const float* x_nchw, const void* x_s
 VPD_API int vpd_net_train_step(vpd_net* net, const float* x_nchw, const void* x_stem,
                        const float* target, int B, double* loss_sum, void* stream);
 
+/* Test/debug access to the bf16 NHWC activation buffers left by the last step:
+ * block -1 = stem (which 0: conv1 output, 4: pooled), block >= 0 = BasicBlock index
+ * (which 0 conv1 out, 1 post-bn1-relu, 2 conv2 out, 3 downsample conv out, 4 block out) */
+VPD_API int vpd_net_activation(vpd_net* net, int block, int which, int B, void** ptr,
+                       int64_t* numel);
+/* device-to-device copy on `stream` (lets tests snapshot the buffers above) */
+VPD_API int vpd_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream);
+/* Per-launch timing of vpd_net_train_step (CUDA events around every kernel),
+ * summed into ms[8 kinds][8 stages] / counts[8][8]; kinds: 0 conv fwd, 1 BN/ReLU/pool
+ * fwd, 2 conv dgrad, 3 conv wgrad, 4 BN/ReLU/pool bwd, 5 head+loss, 6 pack/convert,
+ * 7 other; stages: 0 stem, 1..4 residual stages, 5 head/global. Synchronise the
+ * stream before reading. Used by bench.py's roofline pass. */
+VPD_API int vpd_net_profile_enable(vpd_net* net, int on);
+VPD_API int vpd_net_profile_read(vpd_net* net, float* ms_host, int* counts_host);
+/* number of kernel launches issued by this library since it was loaded */
+VPD_API int64_t vpd_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,7 +88,7 @@ int adamw_step(float* p, const float* g, float* m, float* v, long long n, double
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   adamw_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, m, v, n, s);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 

@@ -147,4 +147,21 @@ int vpd_net_train_step(vpd_net* net, const float* x_nchw, const void* x_stem,
   return net_train_step((Net*)net, x_nchw, x_stem, target, B, loss_sum, (cudaStream_t)stream);
 }
 
+int vpd_net_activation(vpd_net* net, int block, int which, int B, void** ptr, int64_t* numel) {
+  return net_activation((Net*)net, block, which, B, ptr, (long long*)numel);
+}
+int vpd_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream) {
+  VPD_CHECK_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice,
+                                 (cudaStream_t)stream));
+  return 0;
+}
+int vpd_net_profile_enable(vpd_net* net, int on) {
+  net_profile_enable((Net*)net, on);
+  return 0;
+}
+int vpd_net_profile_read(vpd_net* net, float* ms_host, int* counts_host) {
+  return net_profile_read((Net*)net, ms_host, counts_host);
+}
+int64_t vpd_launch_count(void) { return launch_count(); }
+
 }  // extern "C"

@@ -254,7 +254,7 @@ int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int chunks = (H + p.rows_per_cta - 1) / p.rows_per_cta;
   assemble_nchw_kernel<<<B * chunks, kAsmThreads, smem, stream>>>(p);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 
@@ -279,7 +279,7 @@ int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int chunks = (H + 6 + p.rows_per_cta - 1) / p.rows_per_cta;
   assemble_pad8_kernel<<<B * chunks, kAsmThreads, smem, stream>>>(p);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 
@@ -291,7 +291,7 @@ int nchw_to_pad8(const float* x, __nv_bfloat16* out, int B, int C, int H, int W,
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   nchw_to_pad8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, out, B, C, H, W);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 

@@ -281,7 +281,7 @@ static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
   }
   conv_igemm_kernel<BN><<<L.grid, kConvThreads, ConvCfg<BN>::kSmemBytes, stream>>>(
       L.a0, L.a1, L.b0, L.b1, L.p);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 
@@ -372,7 +372,7 @@ static int launch_wgrad_bn(const WgradLaunch& L, cudaStream_t stream) {
     attr_set = true;
   }
   conv_wgrad_kernel<BN><<<L.grid, kConvThreads, WgradCfg<BN>::kSmemBytes, stream>>>(L.x, L.dy, L.p);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 
@@ -403,7 +403,7 @@ int pack_conv_weight(const float* w_oihw, __nv_bfloat16* w_tap, __nv_bfloat16* w
   const long long n = (long long)Cout * Cin;
   pack_conv_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w_oihw, w_tap, wT_tap,
                                                                           Cout, Cin, k * k);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 
@@ -422,7 +422,7 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat
 int pack_stem_weight(const float* w_oihw, __nv_bfloat16* w_stem, int Cimg, cudaStream_t stream) {
   VPD_REQUIRE(Cimg >= 1 && Cimg <= 8, "stem: %d input channels unsupported", Cimg);
   pack_stem_weight_kernel<<<(7 * 64 * 64 + 255) / 256, 256, 0, stream>>>(w_oihw, w_stem, Cimg);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 

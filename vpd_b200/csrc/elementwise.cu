@@ -122,7 +122,7 @@ int launch_bn_apply(const BnApplyParams& p, cudaStream_t s) {
               "bn_apply: unsupported channel count %d", p.C);
   if (p.M == 0) return 0;
   bn_apply_kernel<<<ew_grid(p.M * (p.C / 8)), kEwThreads, 0, s>>>(p);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 
@@ -197,7 +197,7 @@ int launch_bn_pool(const PoolParams& p, cudaStream_t s) {
   long long blocks = (total + kEwThreads - 1) / kEwThreads;
   if (blocks > 148 * 16) blocks = 148 * 16;
   bn_pool_kernel<<<(int)blocks, kEwThreads, 0, s>>>(p);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 
@@ -244,7 +244,7 @@ int launch_maxpool(const __nv_bfloat16* x, __nv_bfloat16* z, int N, int H, int W
   long long blocks = (total + kEwThreads - 1) / kEwThreads;
   if (blocks > 148 * 16) blocks = 148 * 16;
   maxpool_kernel<<<(int)blocks, kEwThreads, 0, s>>>(x, z, N, H, W, C);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 
@@ -259,7 +259,7 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 int launch_bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv,
                    float eps, float* scale, float* shift, int C, cudaStream_t s) {
   bn_fold_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, rm, rv, eps, scale, shift, C);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 
@@ -371,7 +371,7 @@ int launch_bn_bwd(const BnBwdParams& p, cudaStream_t s) {
   const int grid = ew_grid(p.M * (p.C / 8));
   bn_bwd_kernel<false><<<grid, kEwThreads, 0, s>>>(p);
   bn_bwd_kernel<true><<<grid, kEwThreads, 0, s>>>(p);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(2);
   return 0;
 }
 
@@ -484,7 +484,7 @@ int launch_stem_bwd(const StemBwdParams& p, cudaStream_t s) {
   if (blocks < 1) blocks = 1;
   stem_bwd_kernel<false><<<(int)blocks, kEwThreads, 0, s>>>(p);
   stem_bwd_kernel<true><<<(int)blocks, kEwThreads, 0, s>>>(p);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(2);
   return 0;
 }
 

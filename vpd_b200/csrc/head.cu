@@ -185,7 +185,7 @@ int launch_head(const HeadParams& p, const HeadGrads* grads, cudaStream_t stream
   if (p.B == 0) return 0;
   const int smem = (p.F + 2 * p.D + 4 * p.Hd + p.T) * sizeof(float);
   head_kernel<<<p.B, kHeadThreads, smem, stream>>>(p);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   if (grads == nullptr || p.dz == nullptr) return 0;
   // workspace layout per frame: pooled[F] e[D] de[D] h1[Hd] h2[Hd] dh1[Hd] dh2[Hd] dO[T]
   OuterParams op;
@@ -210,7 +210,7 @@ int launch_head(const HeadParams& p, const HeadGrads* grads, cudaStream_t stream
   op.nseg = n;
   for (int i = 0; i < n; ++i) total += op.seg[i].O * (op.seg[i].I + 1);
   head_wgrad_kernel<<<(total + 255) / 256, 256, 0, stream>>>(op);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(1);
   return 0;
 }
 

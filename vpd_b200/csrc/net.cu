@@ -43,6 +43,7 @@ struct ConvDesc {
 };
 struct BlockDesc {
   std::string prefix;
+  int stage;  // 1..4
   ConvDesc c1, c2, ds;
   BnDesc b1, b2, bds;
   bool has_ds;
@@ -69,7 +70,36 @@ struct Plan {  // everything that depends on the batch size
   WgradLaunch wg_stem;
 };
 
+// Optional per-launch timing (CUDA events around every kernel of a step),
+// bucketed by kind x stage; used by bench.py's roofline pass only.
+enum ProfKind { kConvFwd = 0, kEwFwd, kConvDgrad, kConvWgrad, kEwBwd, kHead, kPack, kOther, kNumKinds };
+constexpr int kNumStages = 8;  // 0 stem, 1..4 layers, 5 head/other
+struct Profiler {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<int> cat;  // per record: kind * kNumStages + stage
+  size_t used = 0;
+  void begin(int kind, int stage, cudaStream_t s) {
+    if (!on) return;
+    if (used + 2 > pool.size()) {
+      for (int i = 0; i < 64; ++i) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        pool.push_back(e);
+      }
+    }
+    cat.push_back(kind * kNumStages + stage);
+    cudaEventRecord(pool[used], s);
+  }
+  void end(cudaStream_t s) {
+    if (!on) return;
+    cudaEventRecord(pool[used + 1], s);
+    used += 2;
+  }
+};
+
 struct Net {
+  Profiler prof;
   // configuration
   std::string arch;
   int D, Cimg, H, W, maxB, motion, T, Hd, F;
@@ -188,6 +218,7 @@ Net* net_create(const char* arch, int emb_dim, int in_channels, int H, int W, in
       char buf[64];
       snprintf(buf, sizeof(buf), "resnet.layer%d.%d", s + 1, b);
       bd.prefix = buf;
+      bd.stage = s + 1;
       const int stride = (b == 0 && s > 0) ? 2 : 1;
       const int cout = planes[s];
       bd.has_ds = (b == 0) && (stride != 1 || inpl != cout);
@@ -405,7 +436,7 @@ static int pack_weights(Net* n, cudaStream_t s) {
                                                                   n->secA_len);
   transpose_weights_kernel<<<n->tr_blocks, 256, 0, s>>>(n->params + n->secA, n->wT_tap,
                                                         n->tr_table_dev);
-  VPD_CHECK_CUDA(cudaGetLastError());
+  VPD_LAUNCHED(2);
   n->params_dirty = false;
   return 0;
 }
@@ -610,20 +641,30 @@ int net_eval_loss(Net* n, const float* x_nchw, const void* x_stem, const float* 
   return launch_head(h, nullptr, s);
 }
 
+#define PROF(kind, stage, expr)        \
+  do {                                 \
+    n->prof.begin(kind, stage, s);     \
+    const int _rc = (expr);            \
+    n->prof.end(s);                    \
+    if (_rc) return -1;                \
+  } while (0)
+
 int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float* target, int B,
                    double* loss_sum, cudaStream_t s) {
   VPD_REQUIRE(n->grads != nullptr, "net: gradient arena not bound");
   VPD_REQUIRE(target != nullptr && loss_sum != nullptr, "net_train_step: null target/loss");
-  if (prepare_input(n, x_nchw, x_stem, B, s)) return -1;
+  PROF(kPack, 0, prepare_input(n, x_nchw, x_stem, B, s));
   Plan* P = get_plan(n, B);
   if (!P) return -1;
   // zero: BN statistics (fwd + bwd, contiguous) and the conv-weight gradients
+  n->prof.begin(kPack, 5, s);
   VPD_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, (size_t)((uint8_t*)n->loss_dev - (uint8_t*)n->stats), s));
   VPD_CHECK_CUDA(cudaMemsetAsync(n->grads + n->secA, 0, (size_t)n->secA_len * sizeof(float), s));
   if (pack_weights(n, s)) return -1;
+  n->prof.end(s);
 
   // ------------------------------------------------------------------ forward
-  if (launch_conv(P->stem_train, s)) return -1;
+  PROF(kConvFwd, 0, launch_conv(P->stem_train, s));
   {
     PoolParams pp;
     pp.y = n->y_stem;
@@ -634,13 +675,13 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     pp.W = n->W / 2;
     pp.C = 64;
     pp.bn = bn_layer(n, n->stem_bn, true, (long long)B * pp.H * pp.W);
-    if (launch_bn_pool(pp, s)) return -1;
+    PROF(kEwFwd, 0, launch_bn_pool(pp, s));
   }
   const bf16* zin = n->z_pool;
   for (size_t i = 0; i < n->blocks.size(); ++i) {
     BlockDesc& bd = n->blocks[i];
     const long long M = (long long)B * bd.c2.Hin * bd.c2.Win;
-    if (launch_conv(P->c1_train[i], s)) return -1;
+    PROF(kConvFwd, bd.stage, launch_conv(P->c1_train[i], s));
     BnApplyParams a;
     memset(&a, 0, sizeof(a));
     a.y = bd.y1;
@@ -649,9 +690,9 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     a.C = bd.c1.Cout;
     a.relu = 1;
     a.bn = bn_layer(n, bd.b1, true, M);
-    if (launch_bn_apply(a, s)) return -1;
-    if (launch_conv(P->c2_train[i], s)) return -1;
-    if (bd.has_ds && launch_conv(P->ds_train[i], s)) return -1;
+    PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
+    PROF(kConvFwd, bd.stage, launch_conv(P->c2_train[i], s));
+    if (bd.has_ds) PROF(kConvFwd, bd.stage, launch_conv(P->ds_train[i], s));
     memset(&a, 0, sizeof(a));
     a.y = bd.y2;
     a.z = bd.zout;
@@ -666,7 +707,7 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     } else {
       a.res = zin;
     }
-    if (launch_bn_apply(a, s)) return -1;
+    PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
     zin = bd.zout;
   }
 
@@ -690,7 +731,7 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
       hg.w5 = n->grads + n->dec_off[4];
       hg.b5 = n->grads + n->dec_off[5];
     }
-    if (launch_head(h, &hg, s)) return -1;
+    PROF(kHead, 5, launch_head(h, &hg, s));
   }
 
   // ----------------------------------------------------------------- backward
@@ -720,9 +761,9 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
       q.dgamma[b] = n->grads + n->gamma_off + bs[b]->ch_off;
       q.dbeta[b] = n->grads + n->beta_off + bs[b]->ch_off;
     }
-    if (launch_bn_bwd(q, s)) return -1;
-    if (launch_wgrad(P->wg2[i], s)) return -1;
-    if (launch_conv(P->dgrad2[i], s)) return -1;  // gB -> gC
+    PROF(kEwBwd, bd.stage, launch_bn_bwd(q, s));
+    PROF(kConvWgrad, bd.stage, launch_wgrad(P->wg2[i], s));
+    PROF(kConvDgrad, bd.stage, launch_conv(P->dgrad2[i], s));  // gB -> gC
     memset(&q, 0, sizeof(q));
     q.dz = n->gC;
     q.z = bd.z1;
@@ -737,11 +778,11 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     q.sums[0] = n->bwd_sums + 2 * bd.b1.ch_off;
     q.dgamma[0] = n->grads + n->gamma_off + bd.b1.ch_off;
     q.dbeta[0] = n->grads + n->beta_off + bd.b1.ch_off;
-    if (launch_bn_bwd(q, s)) return -1;
-    if (launch_wgrad(P->wg1[i], s)) return -1;
-    if (bd.has_ds && launch_wgrad(P->wgds[i], s)) return -1;
+    PROF(kEwBwd, bd.stage, launch_bn_bwd(q, s));
+    PROF(kConvWgrad, bd.stage, launch_wgrad(P->wg1[i], s));
+    if (bd.has_ds) PROF(kConvWgrad, bd.stage, launch_wgrad(P->wgds[i], s));
     for (auto& L : P->dgrad1[i])
-      if (launch_conv(L, s)) return -1;
+      PROF(kConvDgrad, bd.stage, launch_conv(L, s));
     if (bd.has_ds) std::swap(cur, other);
   }
   // stem: maxpool + ReLU + BN backward, then the stem weight gradient
@@ -763,10 +804,52 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     sp.sums = n->bwd_sums + 2 * n->stem_bn.ch_off;
     sp.dgamma = n->grads + n->gamma_off + n->stem_bn.ch_off;
     sp.dbeta = n->grads + n->beta_off + n->stem_bn.ch_off;
-    if (launch_stem_bwd(sp, s)) return -1;
-    if (launch_wgrad(P->wg_stem, s)) return -1;
+    PROF(kEwBwd, 0, launch_stem_bwd(sp, s));
+    PROF(kConvWgrad, 0, launch_wgrad(P->wg_stem, s));
   }
   n->params_dirty = true;  // the caller is about to update the parameters
+  return 0;
+}
+
+// Debug/test access to the activation buffers of the last step.
+// block = -1: stem (which 0 = conv output y, 4 = pooled z); block >= 0: which
+// 0 y1, 1 z1, 2 y2, 3 y_ds, 4 z_out.
+int net_activation(Net* n, int block, int which, int B, void** ptr, long long* numel) {
+  VPD_REQUIRE(n->ws != nullptr, "net_activation: not bound");
+  if (block < 0) {
+    *ptr = which == 0 ? (void*)n->y_stem : (void*)n->z_pool;
+    *numel = which == 0 ? (long long)B * (n->H / 2) * (n->W / 2) * 64
+                        : (long long)B * (n->H / 4) * (n->W / 4) * 64;
+    return 0;
+  }
+  VPD_REQUIRE(block < (int)n->blocks.size() && which >= 0 && which <= 4, "net_activation: range");
+  BlockDesc& bd = n->blocks[block];
+  bf16* ps[5] = {bd.y1, bd.z1, bd.y2, bd.yds, bd.zout};
+  *ptr = ps[which];
+  *numel = (long long)B * bd.c2.Hin * bd.c2.Win * bd.c2.Cout;
+  return 0;
+}
+
+void net_profile_enable(Net* n, int on) {
+  n->prof.on = on != 0;
+  n->prof.used = 0;
+  n->prof.cat.clear();
+}
+
+// Sums the recorded intervals (the stream must be synchronised by the caller).
+int net_profile_read(Net* n, float* ms, int* counts) {
+  for (int i = 0; i < kNumKinds * kNumStages; ++i) {
+    ms[i] = 0.f;
+    counts[i] = 0;
+  }
+  for (size_t r = 0; r < n->prof.cat.size(); ++r) {
+    float t = 0.f;
+    VPD_CHECK_CUDA(cudaEventElapsedTime(&t, n->prof.pool[2 * r], n->prof.pool[2 * r + 1]));
+    ms[n->prof.cat[r]] += t;
+    counts[n->prof.cat[r]] += 1;
+  }
+  n->prof.used = 0;
+  n->prof.cat.clear();
   return 0;
 }
 

@@ -29,5 +29,8 @@ int net_tensor_info(Net* n, int i, char* name, int name_cap, int* arena, long lo
 void net_params_changed(Net* n);
 void* net_stem_input(Net* n);
 long long net_conv_section_len(Net* n);
+int net_activation(Net* n, int block, int which, int B, void** ptr, long long* numel);
+void net_profile_enable(Net* n, int on);
+int net_profile_read(Net* n, float* ms, int* counts);
 
 }  // namespace vpd

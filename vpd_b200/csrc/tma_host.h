@@ -15,6 +15,8 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);
+long long launch_count();
 const char* get_error();
 
 #define VPD_CHECK_CUDA(expr)                                                        \
@@ -25,6 +27,13 @@ const char* get_error();
                        __FILE__, __LINE__);                                         \
       return -1;                                                                    \
     }                                                                               \
+  } while (0)
+
+// after a <<<>>> launch: bump the launch counter and check for launch errors
+#define VPD_LAUNCHED(n)                       \
+  do {                                        \
+    ::vpd::count_launches(n);                 \
+    VPD_CHECK_CUDA(cudaGetLastError());       \
   } while (0)
 
 #define VPD_REQUIRE(cond, ...)          \
