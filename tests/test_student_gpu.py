@@ -262,4 +262,8 @@ def test_fused_stem_path_equals_fp32_batch_path():
             loss = tr.epoch([batch], optimizer=opt)
         res.append((loss, m.state_dict()['resnet.fc.weight'].cpu()))
     assert abs(res[0][0] - res[1][0]) <= 1e-3 * abs(res[0][0])
-    assert torch.allclose(res[0][1], res[1][1], atol=1e-4)
+    # identical inputs, but fp32 atomics make the gradients differ in the last bits and
+    # the first AdamW step is ~lr*sign(g): a few near-zero gradients may flip sign
+    diff = (res[0][1] - res[1][1]).abs()
+    assert (diff > 1e-4).float().mean().item() < 0.01
+    assert diff.max().item() <= 2.1 * 5e-4
