@@ -1,0 +1,73 @@
+"""CPU: host logic of the apply driver - video sharding (incl. a 2-rank gloo run) and the
+pickle format of apply_vpd_model.py:163-178."""
+import os
+import pickle
+import subprocess
+import sys
+
+import numpy as np
+
+from vpd_b200 import apply as vapply
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_videos_partitions_and_balances():
+    counts = [4200, 10, 3900, 4100, 0, 2500, 2600, 700]
+    for world in (1, 2, 3, 8):
+        parts = [vapply.shard_videos(counts, world, r) for r in range(world)]
+        flat = sorted(i for p in parts for i in p)
+        assert flat == list(range(len(counts)))
+        loads = [sum(counts[i] for i in p) for p in parts]
+        if world == 2:
+            assert max(loads) - min(loads) <= max(counts)
+    assert vapply.shard_videos([], 4, 1) == []
+
+
+def test_pickle_format_matches_reference(tmp_path):
+    embs = np.arange(3 * 2 * 4, dtype=np.float32).reshape(3, 2, 4)
+    out = vapply.format_video_embs([7, 2, 5], embs, flip=True)
+    assert [t[0] for t in out] == [2, 5, 7]
+    assert all(isinstance(t[0], int) and t[1].dtype == np.float32 and t[1].shape == (2, 4)
+               and t[2] == {} for t in out)
+    assert np.array_equal(out[0][1], embs[1])
+    single = vapply.format_video_embs([1, 0], embs[:2], flip=False)
+    assert single[0][1].shape == (4,) and np.array_equal(single[0][1], embs[1, 0])
+    path = os.path.join(str(tmp_path), 'v.emb.pkl')
+    vapply.store_pickle(path, out)
+    with open(path, 'rb') as fp:
+        back = pickle.load(fp)
+    assert back[2][0] == 7 and np.array_equal(back[2][1], embs[0])
+
+
+GLOO_SCRIPT = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from vpd_b200 import apply as vapply
+dist.init_process_group('gloo')
+rank, world = dist.get_rank(), dist.get_world_size()
+counts = [50, 7, 31, 44, 12, 9]
+mine = vapply.shard_videos(counts, world, rank)
+# gradient-sum semantics used by the trainer: all_reduce(SUM) of a flat arena
+g = torch.full((5,), float(rank + 1))
+dist.all_reduce(g, op=dist.ReduceOp.SUM)
+assert g.tolist() == [3.0] * 5
+gathered = [None] * world
+dist.all_gather_object(gathered, mine)
+if rank == 0:
+    flat = sorted(i for p in gathered for i in p)
+    assert flat == list(range(len(counts))), gathered
+    print('OK', gathered)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    script = os.path.join(str(tmp_path), 'gloo_shard.py')
+    with open(script, 'w') as fp:
+        fp.write(GLOO_SCRIPT)
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', '29611', script, ROOT]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert 'OK' in res.stdout

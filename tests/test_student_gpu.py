@@ -267,3 +267,36 @@ def test_fused_stem_path_equals_fp32_batch_path():
     diff = (res[0][1] - res[1][1]).abs()
     assert (diff > 1e-4).float().mean().item() < 0.01
     assert diff.max().item() <= 2.1 * 5e-4
+
+
+def test_apply_corpus_extraction_pickles(tmp_path):
+    """apply_vpd_model.py:152-178: per-video sorted (frame, float32 [2,D], {}) pickles whose
+    embeddings match the oracle run on the reference-layout batches."""
+    import pickle
+    from vpd_b200 import apply as vapply
+    m = _model(2)
+    torch.manual_seed(2)
+    sd = student_ref.randomize_bn_state(student_ref.init_encoder_state('resnet34', 32, True), 3)
+    m.load_state_dict(sd)
+    videos = []
+    for v, n in enumerate((5, 0, 3)):
+        rgb, flow = synth.crops(n, seed=50 + v)
+        frames = list(range(10 + n, 10, -1))          # unsorted on purpose
+        videos.append(('vid{}'.format(v), frames, rgb, flow))
+    names = vapply.extract_corpus(m, videos, str(tmp_path), synth.FS_MEAN_STD, flip=True,
+                                  batch_size=4)
+    assert names == ['vid0', 'vid2']
+    with open(os.path.join(str(tmp_path), 'vid0.emb.pkl'), 'rb') as fp:
+        embs = pickle.load(fp)
+    assert [e[0] for e in embs] == sorted(videos[0][1])
+    assert all(e[1].shape == (2, 32) and e[1].dtype == np.float32 and e[2] == {} for e in embs)
+    x = assemble_ref.apply_batch(videos[0][2].numpy(), videos[0][3].numpy(), *synth.FS_MEAN_STD)
+    ref = student_ref.embed(sd, x.view(-1, 5, 128, 128)).reshape(5, 2, 32)
+    by_frame = {f: ref[i] for i, f in enumerate(videos[0][1])}
+    for f, e, _ in embs:
+        for k in range(2):
+            assert _cos(torch.from_numpy(e[k]), torch.from_numpy(by_frame[f][k])) >= 0.999
+    # two-rank sharding writes disjoint files
+    a = vapply.shard_videos([5, 0, 3], 2, 0)
+    b = vapply.shard_videos([5, 0, 3], 2, 1)
+    assert sorted(a + b) == [0, 1, 2]
