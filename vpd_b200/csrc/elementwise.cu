@@ -18,20 +18,22 @@ VPD_DEVINL uint4 pack8(const float (&f)[8]) {
 }
 
 // Batch (train) or running (eval) statistics -> fp32 mean / rstd of channel c.
+// Only fp64 multiplies/FMAs (full rate) - the mean-square subtraction is the one
+// place that needs the extra bits; the reciprocal square root is fp32.
 VPD_DEVINL void bn_mean_rstd(const BnLayer& bn, int c, int C, float& mean, float& rstd,
                              float& var_biased) {
   if (bn.stats != nullptr) {
-    const double inv = 1.0 / static_cast<double>(bn.count);
-    const double m = bn.stats[c] * inv;
-    double v = bn.stats[C + c] * inv - m * m;
+    const double inv = bn.inv_count;
+    const double m = __ldg(bn.stats + c) * inv;
+    double v = fma(__ldg(bn.stats + C + c), inv, -m * m);
     if (v < 0.0) v = 0.0;
     mean = static_cast<float>(m);
     var_biased = static_cast<float>(v);
-    rstd = static_cast<float>(1.0 / sqrt(v + static_cast<double>(bn.eps)));
+    rstd = rsqrtf(var_biased + bn.eps);
   } else {
     mean = bn.running_mean[c];
     var_biased = bn.running_var[c];
-    rstd = 1.0f / sqrtf(var_biased + bn.eps);
+    rstd = rsqrtf(var_biased + bn.eps);
   }
 }
 // The affine every kernel (forward and backward) derives from (mean, rstd).
@@ -82,23 +84,39 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParam
   const long long chunk = (p.M + gridDim.x - 1) / gridDim.x;
   const long long beg = (long long)blockIdx.x * chunk;
   const long long end = beg + chunk < p.M ? beg + chunk : p.M;
-  for (long long row = beg + r0; row < end; row += rstep) {
-    const size_t off = (size_t)row * p.C + g * 8;
-    float f[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(p.y + off)), f);
+  constexpr int U = 4;  // independent rows in flight per thread
+  for (long long row = beg + r0; row < end; row += (long long)rstep * U) {
+    uint4 vy[U], vr[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-    if (p.res != nullptr) {
-      float r[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.res + off)), r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += fmaf(r[j], rsc[j], rsh[j]);
+    for (int u = 0; u < U; ++u) {
+      const long long r = row + (long long)u * rstep;
+      if (r < end) {
+        const size_t off = (size_t)r * p.C + g * 8;
+        vy[u] = ldg_nc_v4(p.y + off);
+        if (p.res != nullptr) vr[u] = ldg_nc_v4(p.res + off);
+      }
     }
-    if (p.relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    for (int u = 0; u < U; ++u) {
+      const long long r = row + (long long)u * rstep;
+      if (r >= end) break;
+      const size_t off = (size_t)r * p.C + g * 8;
+      float f[8];
+      unpack8(vy[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (p.res != nullptr) {
+        float rr[8];
+        unpack8(vr[u], rr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += fmaf(rr[j], rsc[j], rsh[j]);
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      stg_v4(p.z + off, pack8(f));
     }
-    stg_v4(p.z + off, pack8(f));
   }
   // every block has consumed the statistics above before block 0 may touch
   // the running buffers it also reads in eval mode; in train mode the inputs
@@ -109,9 +127,10 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParam
   }
 }
 
-static int ew_grid(long long vectors) {
-  long long blocks = (vectors + kEwThreads * 8 - 1) / (kEwThreads * 8);
-  const long long cap = 148 * 8;
+// `per_thread` vectors per thread at most `cap_per_sm` resident blocks' worth of CTAs
+static int ew_grid(long long vectors, int per_thread = 4, int cap_per_sm = 8) {
+  long long blocks = (vectors + (long long)kEwThreads * per_thread - 1) / (kEwThreads * per_thread);
+  const long long cap = 148LL * cap_per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -121,7 +140,7 @@ int launch_bn_apply(const BnApplyParams& p, cudaStream_t s) {
   VPD_REQUIRE(p.C % 64 == 0 && p.C <= 2048 && kEwThreads % (p.C / 8) == 0,
               "bn_apply: unsupported channel count %d", p.C);
   if (p.M == 0) return 0;
-  bn_apply_kernel<<<ew_grid(p.M * (p.C / 8)), kEwThreads, 0, s>>>(p);
+  bn_apply_kernel<<<ew_grid(p.M * (p.C / 8), 4, 8), kEwThreads, 0, s>>>(p);
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -155,25 +174,31 @@ __global__ void __launch_bounds__(kEwThreads) bn_pool_kernel(const PoolParams p)
       best[j] = -INFINITY;
       idx[j] = 0;
     }
+    uint4 win[9];
+    bool ok[9];
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int h = 2 * ho - 1 + kh;
-      if (h < 0 || h >= p.H) continue;
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
         const int w = 2 * wo - 1 + kw;
-        if (w < 0 || w >= p.W) continue;
-        float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(
-                    p.y + (((size_t)n * p.H + h) * p.W + w) * p.C + g * 8)),
-                f);
+        ok[kh * 3 + kw] = h >= 0 && h < p.H && w >= 0 && w < p.W;
+        if (ok[kh * 3 + kw])
+          win[kh * 3 + kw] = __ldg(reinterpret_cast<const uint4*>(
+              p.y + (((size_t)n * p.H + h) * p.W + w) * p.C + g * 8));
+      }
+    }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float v = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-          if (v > best[j]) {
-            best[j] = v;
-            idx[j] = kh * 3 + kw;
-          }
+    for (int k = 0; k < 9; ++k) {
+      if (!ok[k]) continue;
+      float f[8];
+      unpack8(win[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+        if (v > best[j]) {
+          best[j] = v;
+          idx[j] = k;
         }
       }
     }
@@ -264,99 +289,126 @@ int launch_bn_fold(const float* gamma, const float* beta, const float* rm, const
 }
 
 // --------------------------------------------------------------- BN backward
-// pass 1: per-channel sum(g), sum(g * xhat_b);  pass 2: dy_b, dgamma, dbeta.
-template <bool kApply>
+// pass 1 (kApply = false): per-channel sum(g), sum(g * xhat_b), g = dz * 1[z > 0]
+// pass 2 (kApply = true) : dy_b = A_b*g + B_b*y_b + C_b  (the usual
+//          gamma*rstd*(g - mean(g) - xhat*mean(g*xhat)) with the constants folded),
+//          masked gradient written back for the identity branch, dgamma/dbeta.
+// Four rows per thread are loaded before any is used (memory-level parallelism).
+template <bool kApply, int NB>
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_kernel(const BnBwdParams p) {
   __shared__ float s_g[512];
-  __shared__ float s_gx[2][512];
+  __shared__ float s_gx[NB][512];
   const int groups = p.C >> 3;
   const int g = threadIdx.x % groups;
   const int r0 = threadIdx.x / groups;
   const int rstep = kEwThreads / groups;
-  float mean[2][8], rstd[2][8], k0[2][8], k1[2][8], k2[2][8];
+  // reduce: c0 = mean, c1 = rstd.  apply: dy = c0*g + c1*y + c2
+  float c0[NB][8], c1[NB][8], c2[NB][8];
 #pragma unroll
-  for (int b = 0; b < 2; ++b) {
-    if (b >= p.nbranch) break;
+  for (int b = 0; b < NB; ++b) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = g * 8 + j;
-      mean[b][j] = p.save_mean[b][c];
-      rstd[b][j] = p.save_rstd[b][c];
+      const float mean = __ldg(p.save_mean[b] + c), rstd = __ldg(p.save_rstd[b] + c);
       if (kApply) {
         const float invM = 1.0f / static_cast<float>(p.M);
-        const float sg = static_cast<float>(p.sums[b][c]);
-        const float sgx = static_cast<float>(p.sums[b][p.C + c]);
-        k0[b][j] = p.gamma[b][c] * rstd[b][j];  // dy = k0 * (g - k1 - xhat * k2)
-        k1[b][j] = sg * invM;
-        k2[b][j] = sgx * invM;
+        const float k0 = __ldg(p.gamma[b] + c) * rstd;
+        const float k1 = static_cast<float>(p.sums[b][c]) * invM;
+        const float k2 = static_cast<float>(p.sums[b][p.C + c]) * invM;
+        c0[b][j] = k0;
+        c1[b][j] = -k0 * k2 * rstd;
+        c2[b][j] = -k0 * k1 + k0 * k2 * rstd * mean;
+      } else {
+        c0[b][j] = mean;
+        c1[b][j] = rstd;
+        c2[b][j] = 0.f;
       }
     }
   }
-  float acc_g[8], acc_gx[2][8];
+  float acc_g[8], acc_gx[NB][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc_g[j] = acc_gx[0][j] = acc_gx[1][j] = 0.f;
+  for (int j = 0; j < 8; ++j) {
+    acc_g[j] = 0.f;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) acc_gx[b][j] = 0.f;
+  }
 
   const long long chunk = (p.M + gridDim.x - 1) / gridDim.x;
   const long long beg = (long long)blockIdx.x * chunk;
   const long long end = beg + chunk < p.M ? beg + chunk : p.M;
-  for (long long row = beg + r0; row < end; row += rstep) {
-    const size_t off = (size_t)row * p.C + g * 8;
-    float gr[8];
-    unpack8(*reinterpret_cast<const uint4*>(p.dz + off), gr);  // may alias dmask/dy
-    if (p.z != nullptr) {
-      float zz[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.z + off)), zz);
+  constexpr int U = NB == 1 ? 4 : 2;
+  for (long long row = beg + r0; row < end; row += (long long)rstep * U) {
+    uint4 vd[U], vz[U], vy[NB][U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) gr[j] = zz[j] > 0.f ? gr[j] : 0.f;
-    }
+    for (int u = 0; u < U; ++u) {
+      const long long r = row + (long long)u * rstep;
+      if (r < end) {
+        const size_t off = (size_t)r * p.C + g * 8;
+        vd[u] = *reinterpret_cast<const uint4*>(p.dz + off);  // may alias dmask / dy
+        if (p.z != nullptr) vz[u] = ldg_nc_v4(p.z + off);
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      if (b >= p.nbranch) break;
-      float yy[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(p.y[b] + off)), yy);
-      if (kApply) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (yy[j] - mean[b][j]) * rstd[b][j];
-          o[j] = k0[b][j] * (gr[j] - k1[b][j] - xh * k2[b][j]);
-        }
-        stg_v4(p.dy[b] + off, pack8(o));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = (yy[j] - mean[b][j]) * rstd[b][j];
-          acc_gx[b][j] += gr[j] * xh;
-        }
+        for (int b = 0; b < NB; ++b) vy[b][u] = ldg_nc_v4(p.y[b] + off);
       }
     }
-    if (kApply) {
-      if (p.dmask != nullptr) stg_v4(p.dmask + off, pack8(gr));
-    } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc_g[j] += gr[j];
+    for (int u = 0; u < U; ++u) {
+      const long long r = row + (long long)u * rstep;
+      if (r >= end) break;
+      const size_t off = (size_t)r * p.C + g * 8;
+      float gr[8];
+      unpack8(vd[u], gr);
+      if (p.z != nullptr) {
+        float zz[8];
+        unpack8(vz[u], zz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gr[j] = zz[j] > 0.f ? gr[j] : 0.f;
+      }
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float yy[8];
+        unpack8(vy[b][u], yy);
+        if (kApply) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = fmaf(c0[b][j], gr[j], fmaf(c1[b][j], yy[j], c2[b][j]));
+          stg_v4(p.dy[b] + off, pack8(o));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            acc_gx[b][j] = fmaf(gr[j], (yy[j] - c0[b][j]) * c1[b][j], acc_gx[b][j]);
+        }
+      }
+      if (kApply) {
+        if (p.dmask != nullptr) stg_v4(p.dmask + off, pack8(gr));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc_g[j] += gr[j];
+      }
     }
   }
   if (kApply) {
     if (blockIdx.x == 0) {
       for (int c = threadIdx.x; c < p.C; c += kEwThreads)
-        for (int b = 0; b < p.nbranch; ++b) {
+        for (int b = 0; b < NB; ++b) {
           p.dbeta[b][c] = static_cast<float>(p.sums[b][c]);
           p.dgamma[b][c] = static_cast<float>(p.sums[b][p.C + c]);
         }
     }
   } else {
-    for (int c = threadIdx.x; c < p.C; c += kEwThreads) s_g[c] = s_gx[0][c] = s_gx[1][c] = 0.f;
+    for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
+      s_g[c] = 0.f;
+      for (int b = 0; b < NB; ++b) s_gx[b][c] = 0.f;
+    }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       atomicAdd(&s_g[g * 8 + j], acc_g[j]);
-      atomicAdd(&s_gx[0][g * 8 + j], acc_gx[0][j]);
-      if (p.nbranch > 1) atomicAdd(&s_gx[1][g * 8 + j], acc_gx[1][j]);
+#pragma unroll
+      for (int b = 0; b < NB; ++b) atomicAdd(&s_gx[b][g * 8 + j], acc_gx[b][j]);
     }
     __syncthreads();
     for (int c = threadIdx.x; c < p.C; c += kEwThreads)
-      for (int b = 0; b < p.nbranch; ++b) {
+      for (int b = 0; b < NB; ++b) {
         atomicAdd(&p.sums[b][c], static_cast<double>(s_g[c]));
         atomicAdd(&p.sums[b][p.C + c], static_cast<double>(s_gx[b][c]));
       }
@@ -368,41 +420,124 @@ int launch_bn_bwd(const BnBwdParams& p, cudaStream_t s) {
               "bn_bwd: unsupported channel count %d", p.C);
   VPD_REQUIRE(p.nbranch == 1 || p.nbranch == 2, "bn_bwd: nbranch");
   if (p.M == 0) return 0;
-  const int grid = ew_grid(p.M * (p.C / 8));
-  bn_bwd_kernel<false><<<grid, kEwThreads, 0, s>>>(p);
-  bn_bwd_kernel<true><<<grid, kEwThreads, 0, s>>>(p);
+  const long long vectors = p.M * (p.C / 8);
+  const int grid_r = ew_grid(vectors, 4, 4);   // fewer blocks: every block ends in atomics
+  const int grid_a = ew_grid(vectors, 4, 8);
+  if (p.nbranch == 1) {
+    bn_bwd_kernel<false, 1><<<grid_r, kEwThreads, 0, s>>>(p);
+    bn_bwd_kernel<true, 1><<<grid_a, kEwThreads, 0, s>>>(p);
+  } else {
+    bn_bwd_kernel<false, 2><<<grid_r, kEwThreads, 0, s>>>(p);
+    bn_bwd_kernel<true, 2><<<grid_a, kEwThreads, 0, s>>>(p);
+  }
   VPD_LAUNCHED(2);
   return 0;
 }
 
 // ------------------------------------------- stem backward (pool + ReLU + BN)
-template <bool kApply>
-__global__ void __launch_bounds__(kEwThreads) stem_bwd_kernel(const StemBwdParams p) {
+// pass 1 runs at POOLED resolution: the gradient of the pre-pool activation is
+// non-zero only at each window's argmax, so sum(g) and sum(g*xhat) are sums over
+// pooled elements of dpool * 1[relu'(y_argmax)] (* xhat(y_argmax)).
+__global__ void __launch_bounds__(kEwThreads) stem_bwd_reduce_kernel(const StemBwdParams p) {
   __shared__ float s_g[512];
   __shared__ float s_gx[512];
   const int groups = p.C >> 3;
   const int g = threadIdx.x % groups;
   const int Ho = p.H / 2, Wo = p.W / 2;
-  const long long M = (long long)p.N * p.H * p.W;
-  float mean[8], rstd[8], sc[8], sh[8], k0[8], k1[8], k2[8];
+  float mean[8], rstd[8], sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = g * 8 + j;
-    mean[j] = p.save_mean[c];
-    rstd[j] = p.save_rstd[c];
-    bn_affine(p.gamma[c], p.beta[c], mean[j], rstd[j], sc[j], sh[j]);
-    if (kApply) {
-      const float invM = 1.0f / static_cast<float>(M);
-      k0[j] = p.gamma[c] * rstd[j];
-      k1[j] = static_cast<float>(p.sums[c]) * invM;
-      k2[j] = static_cast<float>(p.sums[p.C + c]) * invM;
-    }
+    mean[j] = __ldg(p.save_mean + c);
+    rstd[j] = __ldg(p.save_rstd + c);
+    bn_affine(__ldg(p.gamma + c), __ldg(p.beta + c), mean[j], rstd[j], sc[j], sh[j]);
   }
   float acc_g[8], acc_gx[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc_g[j] = acc_gx[j] = 0.f;
-  const long long total = M * groups;
+  const long long total = (long long)p.N * Ho * Wo * groups;
   const long long stride = (long long)gridDim.x * kEwThreads;  // multiple of groups
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += stride) {
+    long long pix = i / groups;
+    const int wo = (int)(pix % Wo);
+    pix /= Wo;
+    const int ho = (int)(pix % Ho);
+    const int n = (int)(pix / Ho);
+    const size_t po = (((size_t)n * Ho + ho) * Wo + wo) * p.C + g * 8;
+    const uint2 am = __ldg(reinterpret_cast<const uint2*>(p.argmax + po));
+    float dp[8], ysel[8];
+    unpack8(ldg_nc_v4(p.dpool + po), dp);
+    uint4 win[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = 2 * ho - 1 + kh;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = 2 * wo - 1 + kw;
+        if (h >= 0 && h < p.H && w >= 0 && w < p.W)
+          win[kh * 3 + kw] = __ldg(reinterpret_cast<const uint4*>(
+              p.y + (((size_t)n * p.H + h) * p.W + w) * p.C + g * 8));
+        else
+          win[kh * 3 + kw] = make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ysel[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      float f[8];
+      unpack8(win[k], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t word = j < 4 ? am.x : am.y;
+        const int a = (word >> (8 * (j & 3))) & 0xFF;
+        if (a == k) ysel[j] = f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gq = fmaf(ysel[j], sc[j], sh[j]) > 0.f ? dp[j] : 0.f;
+      acc_g[j] += gq;
+      acc_gx[j] = fmaf(gq, (ysel[j] - mean[j]) * rstd[j], acc_gx[j]);
+    }
+  }
+  for (int c = threadIdx.x; c < p.C; c += kEwThreads) s_g[c] = s_gx[c] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_g[g * 8 + j], acc_g[j]);
+    atomicAdd(&s_gx[g * 8 + j], acc_gx[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
+    atomicAdd(&p.sums[c], static_cast<double>(s_g[c]));
+    atomicAdd(&p.sums[p.C + c], static_cast<double>(s_gx[c]));
+  }
+}
+
+// pass 2 at input resolution: gather the <= 4 windows covering each pixel.
+__global__ void __launch_bounds__(kEwThreads) stem_bwd_apply_kernel(const StemBwdParams p) {
+  const int groups = p.C >> 3;
+  const int g = threadIdx.x % groups;
+  const int Ho = p.H / 2, Wo = p.W / 2;
+  const long long M = (long long)p.N * p.H * p.W;
+  float sc[8], sh[8], a0[8], a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    const float mean = __ldg(p.save_mean + c), rstd = __ldg(p.save_rstd + c);
+    const float gamma = __ldg(p.gamma + c);
+    bn_affine(gamma, __ldg(p.beta + c), mean, rstd, sc[j], sh[j]);
+    const float invM = 1.0f / static_cast<float>(M);
+    const float k0 = gamma * rstd;
+    const float k1 = static_cast<float>(p.sums[c]) * invM;
+    const float k2 = static_cast<float>(p.sums[p.C + c]) * invM;
+    a0[j] = k0;
+    a1[j] = -k0 * k2 * rstd;
+    a2[j] = -k0 * k1 + k0 * k2 * rstd * mean;
+  }
+  const long long total = M * groups;
+  const long long stride = (long long)gridDim.x * kEwThreads;
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += stride) {
     long long pix = i / groups;
     const int w = (int)(pix % p.W);
@@ -410,80 +545,65 @@ __global__ void __launch_bounds__(kEwThreads) stem_bwd_kernel(const StemBwdParam
     const int h = (int)(pix % p.H);
     const int n = (int)(pix / p.H);
     const size_t off = (((size_t)n * p.H + h) * p.W + w) * p.C + g * 8;
-    float yy[8], gr[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(p.y + off)), yy);
+    // pooled windows (pi, pj) containing (h, w): rows 2pi-1 .. 2pi+1
+    const int i_lo = h >> 1, i_hi = min((h + 1) >> 1, Ho - 1);
+    const int j_lo = w >> 1, j_hi = min((w + 1) >> 1, Wo - 1);
+    const uint4 vy = ldg_nc_v4(p.y + off);
+    uint4 vdp[4];
+    uint2 vam[4];
+    int kidx[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gr[j] = 0.f;
-    // pooled windows (i, j) that contain (h, w): rows 2i-1 .. 2i+1
-    const int i_lo = h >> 1, i_hi = (h + 1) >> 1;  // i_lo == i_hi when h is even
-    const int j_lo = w >> 1, j_hi = (w + 1) >> 1;
-    for (int pi = i_lo; pi <= i_hi; ++pi) {
-      if (pi >= Ho) continue;
-      for (int pj = j_lo; pj <= j_hi; ++pj) {
-        if (pj >= Wo) continue;
-        const int kidx = (h - (2 * pi - 1)) * 3 + (w - (2 * pj - 1));
-        const size_t po = (((size_t)n * Ho + pi) * Wo + pj) * p.C + g * 8;
-        const uint2 am = __ldg(reinterpret_cast<const uint2*>(p.argmax + po));
-        float dp[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.dpool + po)), dp);
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t word = j < 4 ? am.x : am.y;
-          const int a = (word >> (8 * (j & 3))) & 0xFF;
-          if (a == kidx) gr[j] += dp[j];
+      for (int b = 0; b < 2; ++b) {
+        const int pi = i_lo + a, pj = j_lo + b;
+        const int q = a * 2 + b;
+        if (pi <= i_hi && pj <= j_hi) {
+          const size_t po = (((size_t)n * Ho + pi) * Wo + pj) * p.C + g * 8;
+          vam[q] = __ldg(reinterpret_cast<const uint2*>(p.argmax + po));
+          vdp[q] = __ldg(reinterpret_cast<const uint4*>(p.dpool + po));
+          kidx[q] = (h - (2 * pi - 1)) * 3 + (w - (2 * pj - 1));
+        } else {
+          kidx[q] = -1;
         }
       }
-    }
+    float yy[8], gr[8];
+    unpack8(vy, yy);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gr[j] = fmaf(yy[j], sc[j], sh[j]) > 0.f ? gr[j] : 0.f;
-    if (kApply) {
-      float o[8];
+    for (int j = 0; j < 8; ++j) gr[j] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xh = (yy[j] - mean[j]) * rstd[j];
-        o[j] = k0[j] * (gr[j] - k1[j] - xh * k2[j]);
-      }
-      stg_v4(p.dy + off, pack8(o));
-    } else {
+    for (int q = 0; q < 4; ++q) {
+      if (kidx[q] < 0) continue;
+      float dp[8];
+      unpack8(vdp[q], dp);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float xh = (yy[j] - mean[j]) * rstd[j];
-        acc_g[j] += gr[j];
-        acc_gx[j] += gr[j] * xh;
+        const uint32_t word = j < 4 ? vam[q].x : vam[q].y;
+        const int a = (word >> (8 * (j & 3))) & 0xFF;
+        if (a == kidx[q]) gr[j] += dp[j];
       }
     }
-  }
-  if (kApply) {
-    if (blockIdx.x == 0)
-      for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
-        p.dbeta[c] = static_cast<float>(p.sums[c]);
-        p.dgamma[c] = static_cast<float>(p.sums[p.C + c]);
-      }
-  } else {
-    for (int c = threadIdx.x; c < p.C; c += kEwThreads) s_g[c] = s_gx[c] = 0.f;
-    __syncthreads();
+    float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_g[g * 8 + j], acc_g[j]);
-      atomicAdd(&s_gx[g * 8 + j], acc_gx[j]);
+      const float gq = fmaf(yy[j], sc[j], sh[j]) > 0.f ? gr[j] : 0.f;
+      o[j] = fmaf(a0[j], gq, fmaf(a1[j], yy[j], a2[j]));
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
-      atomicAdd(&p.sums[c], static_cast<double>(s_g[c]));
-      atomicAdd(&p.sums[p.C + c], static_cast<double>(s_gx[c]));
-    }
+    stg_cs_v4(p.dy + off, pack8(o));
   }
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
+      p.dbeta[c] = static_cast<float>(p.sums[c]);
+      p.dgamma[c] = static_cast<float>(p.sums[p.C + c]);
+    }
 }
 
 int launch_stem_bwd(const StemBwdParams& p, cudaStream_t s) {
   VPD_REQUIRE(p.C % 64 == 0 && p.C <= 512 && kEwThreads % (p.C / 8) == 0, "stem_bwd: C=%d", p.C);
   if (p.N == 0) return 0;
-  const long long total = (long long)p.N * p.H * p.W * (p.C / 8);
-  long long blocks = (total + kEwThreads * 4 - 1) / (kEwThreads * 4);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  stem_bwd_kernel<false><<<(int)blocks, kEwThreads, 0, s>>>(p);
-  stem_bwd_kernel<true><<<(int)blocks, kEwThreads, 0, s>>>(p);
+  const long long pooled = (long long)p.N * (p.H / 2) * (p.W / 2) * (p.C / 8);
+  stem_bwd_reduce_kernel<<<ew_grid(pooled, 2, 4), kEwThreads, 0, s>>>(p);
+  stem_bwd_apply_kernel<<<ew_grid(pooled * 4, 2, 8), kEwThreads, 0, s>>>(p);
   VPD_LAUNCHED(2);
   return 0;
 }

@@ -22,6 +22,7 @@ struct BnLayer {
   float* save_mean;        // [C] out (train) - batch mean
   float* save_rstd;        // [C] out (train) - 1/sqrt(var+eps)
   float count;             // N*H*W
+  double inv_count;        // 1 / count
   float momentum, eps;
   int update_running;      // train: block 0 updates running stats
 };

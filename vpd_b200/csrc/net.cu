@@ -453,6 +453,7 @@ static BnLayer bn_layer(Net* n, const BnDesc& b, bool train, long long count) {
   L.save_mean = n->save_mean + b.ch_off;
   L.save_rstd = n->save_rstd + b.ch_off;
   L.count = (float)count;
+  L.inv_count = 1.0 / (double)count;
   L.momentum = 0.1f;
   L.eps = 1e-5f;
   L.update_running = train ? 1 : 0;
