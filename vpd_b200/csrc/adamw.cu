@@ -45,6 +45,8 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
              float* __restrict__ v, long long n, const AdamScalars s) {
+  pdl_trigger();
+  pdl_wait();
   const long long n4 = n >> 2;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -87,7 +89,7 @@ int adamw_step(float* p, const float* g, float* m, float* v, long long n, double
   const long long cap = (long long)148 * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  adamw_kernel<<<(unsigned)blocks, 256, 0, stream>>>(p, g, m, v, n, s);
+  VPD_CHECK_CUDA(launch_kernel(adamw_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, p, g, m, v, n, s));
   VPD_LAUNCHED(1);
   return 0;
 }

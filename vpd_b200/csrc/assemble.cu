@@ -65,6 +65,8 @@ struct AsmParams {
 // Reference layout: fp32 NCHW planes.
 __global__ void __launch_bounds__(kAsmThreads)
 assemble_nchw_kernel(const AsmParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t sm[];
   float* lut = reinterpret_cast<float*>(sm);
   uint8_t* s_rgb = sm + 5 * 256 * 4;
@@ -119,6 +121,8 @@ assemble_nchw_kernel(const AsmParams p) {
 // is written here too, so the buffer needs no separate clearing.
 __global__ void __launch_bounds__(kAsmThreads)
 assemble_pad8_kernel(const AsmParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t sm[];
   float* lut = reinterpret_cast<float*>(sm);
   uint8_t* s_rgb = sm + 5 * 256 * 4;
@@ -180,6 +184,8 @@ assemble_pad8_kernel(const AsmParams p) {
 __global__ void __launch_bounds__(256)
 nchw_to_pad8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C,
                     int H, int W) {
+  pdl_trigger();
+  pdl_wait();
   const int Hp = H + 6, Wp = W + 8;
   const long long total = (long long)B * Hp * Wp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -253,7 +259,7 @@ int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
     VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_nchw_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int chunks = (H + p.rows_per_cta - 1) / p.rows_per_cta;
-  assemble_nchw_kernel<<<B * chunks, kAsmThreads, smem, stream>>>(p);
+  VPD_CHECK_CUDA(launch_kernel(assemble_nchw_kernel, dim3(B * chunks), dim3(kAsmThreads), smem, stream, p));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -278,7 +284,7 @@ int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
     VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int chunks = (H + 6 + p.rows_per_cta - 1) / p.rows_per_cta;
-  assemble_pad8_kernel<<<B * chunks, kAsmThreads, smem, stream>>>(p);
+  VPD_CHECK_CUDA(launch_kernel(assemble_pad8_kernel, dim3(B * chunks), dim3(kAsmThreads), smem, stream, p));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -290,7 +296,7 @@ int nchw_to_pad8(const float* x, __nv_bfloat16* out, int B, int C, int H, int W,
   const long long total = (long long)B * (H + 6) * (W + 8);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  nchw_to_pad8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(x, out, B, C, H, W);
+  VPD_CHECK_CUDA(launch_kernel(nchw_to_pad8_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, out, B, C, H, W));
   VPD_LAUNCHED(1);
   return 0;
 }

@@ -12,6 +12,14 @@
 
 namespace vpd {
 
+// ------------------------------------------- programmatic dependent launch (PDL)
+// Every kernel triggers its dependents at entry (the next kernel in the stream may
+// be scheduled as soon as all CTAs of this one have started, hiding its launch
+// latency and prologue) and waits for the previous kernel's completion + memory
+// flush before it touches any global data.
+VPD_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+VPD_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- addresses
 VPD_DEVINL uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

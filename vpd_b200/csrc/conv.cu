@@ -279,8 +279,8 @@ static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
                                         ConvCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  conv_igemm_kernel<BN><<<L.grid, kConvThreads, ConvCfg<BN>::kSmemBytes, stream>>>(
-      L.a0, L.a1, L.b0, L.b1, L.p);
+  VPD_CHECK_CUDA(launch_kernel(conv_igemm_kernel<BN>, dim3(L.grid), dim3(kConvThreads), ConvCfg<BN>::kSmemBytes, stream, 
+      L.a0, L.a1, L.b0, L.b1, L.p));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -371,7 +371,7 @@ static int launch_wgrad_bn(const WgradLaunch& L, cudaStream_t stream) {
                                         WgradCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  conv_wgrad_kernel<BN><<<L.grid, kConvThreads, WgradCfg<BN>::kSmemBytes, stream>>>(L.x, L.dy, L.p);
+  VPD_CHECK_CUDA(launch_kernel(conv_wgrad_kernel<BN>, dim3(L.grid), dim3(kConvThreads), WgradCfg<BN>::kSmemBytes, stream, L.x, L.dy, L.p));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -386,6 +386,8 @@ int launch_wgrad(const WgradLaunch& L, cudaStream_t stream) {
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ w_tap,
                                         __nv_bfloat16* __restrict__ wT_tap, int Cout, int Cin,
                                         int kk) {
+  pdl_trigger();
+  pdl_wait();
   // one thread per (co, ci): reads kk contiguous floats, scatters to both layouts
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Cout * Cin) return;
@@ -401,14 +403,16 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
 int pack_conv_weight(const float* w_oihw, __nv_bfloat16* w_tap, __nv_bfloat16* wT_tap, int Cout,
                      int Cin, int k, cudaStream_t stream) {
   const long long n = (long long)Cout * Cin;
-  pack_conv_weight_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w_oihw, w_tap, wT_tap,
-                                                                          Cout, Cin, k * k);
+  VPD_CHECK_CUDA(launch_kernel(pack_conv_weight_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, w_oihw, w_tap, wT_tap,
+                                                                          Cout, Cin, k * k));
   VPD_LAUNCHED(1);
   return 0;
 }
 
 __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws,
                                         int Cimg) {
+  pdl_trigger();
+  pdl_wait();
   // ws[kh][co][kw*8 + c], zero for kw == 7 or c >= Cimg
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 7 * 64 * 64) return;
@@ -421,7 +425,7 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat
 
 int pack_stem_weight(const float* w_oihw, __nv_bfloat16* w_stem, int Cimg, cudaStream_t stream) {
   VPD_REQUIRE(Cimg >= 1 && Cimg <= 8, "stem: %d input channels unsupported", Cimg);
-  pack_stem_weight_kernel<<<(7 * 64 * 64 + 255) / 256, 256, 0, stream>>>(w_oihw, w_stem, Cimg);
+  VPD_CHECK_CUDA(launch_kernel(pack_stem_weight_kernel, dim3((7 * 64 * 64 + 255) / 256), dim3(256), 0, stream, w_oihw, w_stem, Cimg));
   VPD_LAUNCHED(1);
   return 0;
 }

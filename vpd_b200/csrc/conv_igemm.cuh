@@ -74,6 +74,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                   const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
                   const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -110,6 +111,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel's tail
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   const int total_tiles = m_tiles * p.n_tiles;
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const __grid_constant__ WgradParams p) {
   using Cfg = WgradCfg<BLOCK_N>;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
@@ -402,6 +405,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel's tail
 
   const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   const int per_split = (pix_tiles + p.splits - 1) / p.splits;

@@ -63,6 +63,8 @@ VPD_DEVINL void bn_side_effects(const BnLayer& bn, int C) {
 
 // ------------------------------------------------------------------ BN apply
 __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int groups = p.C >> 3;
   const int g = threadIdx.x % groups;
   const int r0 = threadIdx.x / groups;
@@ -140,13 +142,15 @@ int launch_bn_apply(const BnApplyParams& p, cudaStream_t s) {
   VPD_REQUIRE(p.C % 64 == 0 && p.C <= 2048 && kEwThreads % (p.C / 8) == 0,
               "bn_apply: unsupported channel count %d", p.C);
   if (p.M == 0) return 0;
-  bn_apply_kernel<<<ew_grid(p.M * (p.C / 8), 4, 8), kEwThreads, 0, s>>>(p);
+  VPD_CHECK_CUDA(launch_kernel(bn_apply_kernel, dim3(ew_grid(p.M * (p.C / 8), 4, 8)), dim3(kEwThreads), 0, s, p));
   VPD_LAUNCHED(1);
   return 0;
 }
 
 // ---------------------------------------------- stem: BN + ReLU + maxpool 3x3/2
 __global__ void __launch_bounds__(kEwThreads) bn_pool_kernel(const PoolParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int groups = p.C >> 3;
   const int Ho = p.H / 2, Wo = p.W / 2;
   const long long total = (long long)p.N * Ho * Wo * groups;
@@ -221,7 +225,7 @@ int launch_bn_pool(const PoolParams& p, cudaStream_t s) {
   const long long total = (long long)p.N * (p.H / 2) * (p.W / 2) * (p.C / 8);
   long long blocks = (total + kEwThreads - 1) / kEwThreads;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  bn_pool_kernel<<<(int)blocks, kEwThreads, 0, s>>>(p);
+  VPD_CHECK_CUDA(launch_kernel(bn_pool_kernel, dim3((int)blocks), dim3(kEwThreads), 0, s, p));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -230,6 +234,8 @@ int launch_bn_pool(const PoolParams& p, cudaStream_t s) {
 __global__ void __launch_bounds__(kEwThreads)
 maxpool_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ z, int N, int H,
                int W, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int groups = C >> 3;
   const int Ho = H / 2, Wo = W / 2;
   const long long total = (long long)N * Ho * Wo * groups;
@@ -268,13 +274,15 @@ int launch_maxpool(const __nv_bfloat16* x, __nv_bfloat16* z, int N, int H, int W
   const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
   long long blocks = (total + kEwThreads - 1) / kEwThreads;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  maxpool_kernel<<<(int)blocks, kEwThreads, 0, s>>>(x, z, N, H, W, C);
+  VPD_CHECK_CUDA(launch_kernel(maxpool_kernel, dim3((int)blocks), dim3(kEwThreads), 0, s, x, z, N, H, W, C));
   VPD_LAUNCHED(1);
   return 0;
 }
 
 __global__ void bn_fold_kernel(const float* gamma, const float* beta, const float* rm,
                                const float* rv, float eps, float* scale, float* shift, int C) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float rstd = 1.0f / sqrtf(rv[c] + eps);
@@ -283,7 +291,7 @@ __global__ void bn_fold_kernel(const float* gamma, const float* beta, const floa
 
 int launch_bn_fold(const float* gamma, const float* beta, const float* rm, const float* rv,
                    float eps, float* scale, float* shift, int C, cudaStream_t s) {
-  bn_fold_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, rm, rv, eps, scale, shift, C);
+  VPD_CHECK_CUDA(launch_kernel(bn_fold_kernel, dim3((C + 127) / 128), dim3(128), 0, s, gamma, beta, rm, rv, eps, scale, shift, C));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -296,6 +304,8 @@ int launch_bn_fold(const float* gamma, const float* beta, const float* rm, const
 // Four rows per thread are loaded before any is used (memory-level parallelism).
 template <bool kApply, int NB>
 __global__ void __launch_bounds__(kEwThreads) bn_bwd_kernel(const BnBwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_g[512];
   __shared__ float s_gx[NB][512];
   const int groups = p.C >> 3;
@@ -424,11 +434,11 @@ int launch_bn_bwd(const BnBwdParams& p, cudaStream_t s) {
   const int grid_r = ew_grid(vectors, 4, 4);   // fewer blocks: every block ends in atomics
   const int grid_a = ew_grid(vectors, 4, 8);
   if (p.nbranch == 1) {
-    bn_bwd_kernel<false, 1><<<grid_r, kEwThreads, 0, s>>>(p);
-    bn_bwd_kernel<true, 1><<<grid_a, kEwThreads, 0, s>>>(p);
+    VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<false, 1>, dim3(grid_r), dim3(kEwThreads), 0, s, p));
+    VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<true, 1>, dim3(grid_a), dim3(kEwThreads), 0, s, p));
   } else {
-    bn_bwd_kernel<false, 2><<<grid_r, kEwThreads, 0, s>>>(p);
-    bn_bwd_kernel<true, 2><<<grid_a, kEwThreads, 0, s>>>(p);
+    VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<false, 2>, dim3(grid_r), dim3(kEwThreads), 0, s, p));
+    VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<true, 2>, dim3(grid_a), dim3(kEwThreads), 0, s, p));
   }
   VPD_LAUNCHED(2);
   return 0;
@@ -439,6 +449,8 @@ int launch_bn_bwd(const BnBwdParams& p, cudaStream_t s) {
 // non-zero only at each window's argmax, so sum(g) and sum(g*xhat) are sums over
 // pooled elements of dpool * 1[relu'(y_argmax)] (* xhat(y_argmax)).
 __global__ void __launch_bounds__(kEwThreads) stem_bwd_reduce_kernel(const StemBwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float s_g[512];
   __shared__ float s_gx[512];
   const int groups = p.C >> 3;
@@ -517,6 +529,8 @@ __global__ void __launch_bounds__(kEwThreads) stem_bwd_reduce_kernel(const StemB
 
 // pass 2 at input resolution: gather the <= 4 windows covering each pixel.
 __global__ void __launch_bounds__(kEwThreads) stem_bwd_apply_kernel(const StemBwdParams p) {
+  pdl_trigger();
+  pdl_wait();
   const int groups = p.C >> 3;
   const int g = threadIdx.x % groups;
   const int Ho = p.H / 2, Wo = p.W / 2;
@@ -602,8 +616,8 @@ int launch_stem_bwd(const StemBwdParams& p, cudaStream_t s) {
   VPD_REQUIRE(p.C % 64 == 0 && p.C <= 512 && kEwThreads % (p.C / 8) == 0, "stem_bwd: C=%d", p.C);
   if (p.N == 0) return 0;
   const long long pooled = (long long)p.N * (p.H / 2) * (p.W / 2) * (p.C / 8);
-  stem_bwd_reduce_kernel<<<ew_grid(pooled, 2, 4), kEwThreads, 0, s>>>(p);
-  stem_bwd_apply_kernel<<<ew_grid(pooled * 4, 2, 8), kEwThreads, 0, s>>>(p);
+  VPD_CHECK_CUDA(launch_kernel(stem_bwd_reduce_kernel, dim3(ew_grid(pooled, 2, 4)), dim3(kEwThreads), 0, s, p));
+  VPD_CHECK_CUDA(launch_kernel(stem_bwd_apply_kernel, dim3(ew_grid(pooled * 4, 2, 8)), dim3(kEwThreads), 0, s, p));
   VPD_LAUNCHED(2);
   return 0;
 }

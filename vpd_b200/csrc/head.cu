@@ -15,6 +15,8 @@ namespace vpd {
 constexpr int kHeadThreads = 128;
 
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sh[];
   float* pooled = sh;                 // F
   float* e = pooled + p.F;            // D
@@ -158,6 +160,8 @@ struct OuterParams {
 };
 
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const OuterParams p) {
+  pdl_trigger();
+  pdl_wait();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   for (int s = 0; s < p.nseg; ++s) {
     const OuterSeg& g = p.seg[s];
@@ -184,7 +188,7 @@ int launch_head(const HeadParams& p, const HeadGrads* grads, cudaStream_t stream
   VPD_REQUIRE(p.motion || p.T == p.D, "head: target dim must equal emb_dim without decoder");
   if (p.B == 0) return 0;
   const int smem = (p.F + 2 * p.D + 4 * p.Hd + p.T) * sizeof(float);
-  head_kernel<<<p.B, kHeadThreads, smem, stream>>>(p);
+  VPD_CHECK_CUDA(launch_kernel(head_kernel, dim3(p.B), dim3(kHeadThreads), smem, stream, p));
   VPD_LAUNCHED(1);
   if (grads == nullptr || p.dz == nullptr) return 0;
   // workspace layout per frame: pooled[F] e[D] de[D] h1[Hd] h2[Hd] dh1[Hd] dh2[Hd] dO[T]
@@ -209,7 +213,7 @@ int launch_head(const HeadParams& p, const HeadGrads* grads, cudaStream_t stream
   }
   op.nseg = n;
   for (int i = 0; i < n; ++i) total += op.seg[i].O * (op.seg[i].I + 1);
-  head_wgrad_kernel<<<(total + 255) / 256, 256, 0, stream>>>(op);
+  VPD_CHECK_CUDA(launch_kernel(head_wgrad_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, op));
   VPD_LAUNCHED(1);
   return 0;
 }

@@ -398,6 +398,8 @@ int net_bind(Net* n, float* params, float* grads, float* buffers, long long* nbt
 
 // ------------------------------------------------------------------ weight mirrors
 __global__ void cast_weights_kernel(const float* __restrict__ w, bf16* __restrict__ o, long long n) {
+  pdl_trigger();
+  pdl_wait();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(w + i);
@@ -414,6 +416,8 @@ __global__ void cast_weights_kernel(const float* __restrict__ w, bf16* __restric
 __global__ void __launch_bounds__(256)
 transpose_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wT,
                          const int* __restrict__ table) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int* e = table + blockIdx.x * 5;
   const long long base = e[0];
@@ -432,10 +436,10 @@ static int pack_weights(Net* n, cudaStream_t s) {
     n->tr_uploaded = true;
   }
   const long long n4 = (n->secA_len + 3) / 4;
-  cast_weights_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, s>>>(n->params + n->secA, n->w_tap,
-                                                                  n->secA_len);
-  transpose_weights_kernel<<<n->tr_blocks, 256, 0, s>>>(n->params + n->secA, n->wT_tap,
-                                                        n->tr_table_dev);
+  VPD_CHECK_CUDA(launch_kernel(cast_weights_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, n->params + n->secA, n->w_tap,
+                                                                  n->secA_len));
+  VPD_CHECK_CUDA(launch_kernel(transpose_weights_kernel, dim3(n->tr_blocks), dim3(256), 0, s, n->params + n->secA, n->wT_tap,
+                                                        n->tr_table_dev));
   VPD_LAUNCHED(2);
   n->params_dirty = false;
   return 0;

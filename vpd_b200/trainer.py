@@ -121,33 +121,48 @@ class ModelTrainer:
             # reduction='sum' loss => gradients add across ranks (SUM, not mean)
             dist.all_reduce(self.encoder._grads, op=dist.ReduceOp.SUM)
 
-    def _stage(self, batch):
-        """Start the host->device copies of a batch on the copy stream."""
+    def _stage(self, batch, slot):
+        """Start the host->device copies of a batch on the copy stream, into one of
+        two persistent device staging buffers (no per-step allocation)."""
         if batch is None:
             return None
         dev = self.encoder._dev
+        img_h, emb_h = batch['img'], batch['emb']
+        key = (tuple(img_h.shape), tuple(emb_h.shape))
+        ring = getattr(self, '_ring', None)
+        if ring is None or ring['key'] != key:
+            ring = {'key': key,
+                    'img': [torch.empty(img_h.shape, device=dev, dtype=torch.float32) for _ in range(2)],
+                    'emb': [torch.empty(emb_h.shape, device=dev, dtype=torch.float32) for _ in range(2)],
+                    'free': [None, None]}
+            self._ring = ring
+        if img_h.device == dev and emb_h.device == dev and img_h.dtype == torch.float32:
+            return img_h, emb_h, None, None            # already resident
         with torch.cuda.stream(self._copy_stream):
-            img = batch['img'].to(dev, dtype=torch.float32, non_blocking=True)
-            emb = batch['emb'].to(dev, dtype=torch.float32, non_blocking=True)
+            if ring['free'][slot] is not None:         # previous consumer of this slot done?
+                self._copy_stream.wait_event(ring['free'][slot])
+            ring['img'][slot].copy_(img_h, non_blocking=True)
+            ring['emb'][slot].copy_(emb_h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        return img, emb, ev
+        return ring['img'][slot], ring['emb'][slot], ev, slot
 
     def epoch(self, data_loader, optimizer=None, scaler=None, progress_cb=None):
         enc = self.encoder
         train = optimizer is not None
         enc.eval() if optimizer is None else enc.train()
-        if self.motion:
-            assert enc.use_flow in (True, False)
         self._loss.zero_()
         epoch_n = 0
         it = iter(data_loader)
-        nxt = self._stage(next(it, None))
+        step_i = 0
+        nxt = self._stage(next(it, None), 0)
         cur_stream = torch.cuda.current_stream(enc._dev)
         while nxt is not None:
-            img, emb, ev = nxt
-            nxt = self._stage(next(it, None))        # overlap the next copy with this step
-            cur_stream.wait_event(ev)
+            img, emb, ev, slot = nxt
+            step_i += 1
+            nxt = self._stage(next(it, None), step_i % 2)   # overlap next copy with this step
+            if ev is not None:
+                cur_stream.wait_event(ev)
             img = img.contiguous()
             emb = emb.contiguous()
             n = img.shape[0]
@@ -156,8 +171,10 @@ class ModelTrainer:
             if emb.shape[1] != expect:
                 raise ValueError('target dim {} != {}'.format(emb.shape[1], expect))
             self._run(img, emb, n, train)
-            img.record_stream(cur_stream)
-            emb.record_stream(cur_stream)
+            if slot is not None:
+                done = torch.cuda.Event()
+                done.record(cur_stream)
+                self._ring['free'][slot] = done
             if train:
                 self._sync_grads()
                 optimizer.step()
@@ -165,6 +182,8 @@ class ModelTrainer:
             epoch_n += n
             if progress_cb is not None:
                 progress_cb(n)
+        if epoch_n == 0:
+            return float('nan')
         total = self._loss.clone()
         dist = _dist()
         if dist is not None and train:
