@@ -165,6 +165,12 @@ VPD_API int vpd_copy_d2d(void* dst, const void* src, int64_t bytes, void* stream
  * stream before reading. Used by bench.py's roofline pass. */
 VPD_API int vpd_net_profile_enable(vpd_net* net, int on);
 VPD_API int vpd_net_profile_read(vpd_net* net, float* ms_host, int* counts_host);
+/* Test-only hardware probe: D[128][64] = A x I where A is a K-major SWIZZLE_128B UMMA
+ * operand whose descriptor starts at row `row_start` of a swizzled [rows][64] bf16 patch
+ * in shared memory, 8-row groups `sbo_bytes` apart; base_offset_mode 1 sets the
+ * descriptor's base-offset field to (start_addr >> 7) & 7. */
+VPD_API int vpd_umma_probe(const void* src_bf16, int rows, int row_start, int sbo_bytes,
+                   int base_offset_mode, float* out, void* stream);
 /* number of kernel launches issued by this library since it was loaded */
 VPD_API int64_t vpd_launch_count(void);
 

@@ -81,6 +81,29 @@ VPD_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// multicast variant: the box lands at the same CTA-relative smem offset of every CTA
+// in `cta_mask`, and each destination's mbarrier (same offset) gets the complete_tx
+VPD_DEVINL void tma_load_3d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0,
+                                  int c1, int c2, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+      "h"(cta_mask)
+      : "memory");
+}
+
+// ------------------------------------------------------------------ clusters
+VPD_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+VPD_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ------------------------------------------------------------ tcgen05 / TMEM
 VPD_DEVINL void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -116,6 +139,14 @@ VPD_DEVINL void umma_commit(uint64_t* bar) {
   asm volatile(
       "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
           smem_u32(bar))
+      : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `cta_mask`
+VPD_DEVINL void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
       : "memory");
 }
 // 32 lanes x 32 columns of fp32: thread i of the warp gets lane (base_lane+i).

@@ -1,5 +1,6 @@
 #include "conv.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 namespace vpd {
@@ -38,8 +39,18 @@ static void tile_geometry(int Ho, int Wo, int N, ConvParams* p) {
   p->out_w = Wo;
 }
 
-static int pick_block_n(int cout) {
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+// Channel-block width. The kernels are bound by L2->SM operand traffic
+// (~42 B/cycle/SM), so wider tiles are better as long as enough tiles remain to
+// fill the SMs.
+static int pick_block_n(int cout, int m_tiles) {
   if (cout % 128 != 0) return 64;
+  static const int allow256 = env_int("VPD_BN256", 1);
+  if (allow256 && cout % 256 == 0 && (long long)m_tiles * (cout / 256) >= 96) return 256;
   return 128;
 }
 
@@ -47,22 +58,27 @@ static int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 static int mod2(int v) { return ((v % 2) + 2) % 2; }
 
 static void finish_launch(ConvLaunch* L, int cout, bool stats) {
-  L->block_n = pick_block_n(cout);
+  const int m_tiles = L->p.tiles_w * L->p.tiles_h * L->p.tiles_b;
+  L->block_n = pick_block_n(cout, m_tiles);
   L->p.n_tiles = cout / L->block_n;
   L->p.cout = cout;
-  const int total = L->p.tiles_w * L->p.tiles_h * L->p.tiles_b * L->p.n_tiles;
-  int grid = device_sm_count();
-  if (grid > total) grid = total;
-  if (stats && grid >= L->p.n_tiles) grid -= grid % L->p.n_tiles;  // channel block fixed per CTA
-  L->grid = grid;
+  static const int want_cluster = env_int("VPD_CLUSTER", 2);
+  L->cluster = (want_cluster >= 2 && m_tiles >= 2) ? 2 : 1;
+  const int cs = L->cluster;
+  const int items = ((m_tiles + cs - 1) / cs) * L->p.n_tiles;  // cluster-level work items
+  int clusters = device_sm_count() / cs;
+  if (clusters > items) clusters = items;
+  // keep the channel block fixed per CTA so BN statistics stay in shared memory
+  if (stats && clusters >= L->p.n_tiles) clusters -= clusters % L->p.n_tiles;
+  L->grid = clusters * cs;
 }
 
 // weights [taps][rows][kdim] bf16 -> 3-D map, box {64, block_n, 1}
 static int weight_map(CUtensorMap* m, const __nv_bfloat16* w, int taps, int rows, int kdim,
-                      int block_n) {
+                      int box_rows) {
   uint64_t dims[3] = {(uint64_t)kdim, (uint64_t)rows, (uint64_t)taps};
   uint64_t str[3] = {2, (uint64_t)kdim * 2, (uint64_t)rows * kdim * 2};
-  uint32_t box[3] = {64, (uint32_t)block_n, 1};
+  uint32_t box[3] = {64, (uint32_t)box_rows, 1};
   return encode_tmap_bf16(m, w, 3, dims, str, box, true);
 }
 
@@ -130,7 +146,7 @@ int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
   set_epilogue(&p, e);
   finish_launch(L, g.Cout, e.stats != nullptr);
   if (act_map(&L->a0, x, g.N, g.H, g.W, g.Cin, g.stride, p)) return -1;
-  if (weight_map(&L->b0, w_tap, g.k * g.k, g.Cout, g.Cin, L->block_n)) return -1;
+  if (weight_map(&L->b0, w_tap, g.k * g.k, g.Cout, g.Cin, L->block_n / L->cluster)) return -1;
   L->a1 = L->a0;
   L->b1 = L->b0;
   return 0;
@@ -168,7 +184,7 @@ int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad
   uint64_t str[5] = {2, 2 * 8 * 2, pitch, 2 * pitch, (uint64_t)Hp * pitch};
   uint32_t box[5] = {64, (uint32_t)p.tw, 1, (uint32_t)p.th, (uint32_t)p.tn};
   if (encode_tmap_bf16(&L->a0, x_pad, 5, dims, str, box, true)) return -1;
-  if (weight_map(&L->b0, w_stem, 7, 64, 64, L->block_n)) return -1;
+  if (weight_map(&L->b0, w_stem, 7, 64, 64, L->block_n / L->cluster)) return -1;
   L->a1 = L->a0;
   L->b1 = L->b0;
   return 0;
@@ -206,7 +222,7 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
     p.out_sw = g.Cin;
     finish_launch(L, g.Cin, false);
     if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
-    if (weight_map(&L->b0, wT_tap, g.k * g.k, g.Cin, g.Cout, L->block_n)) return -1;
+    if (weight_map(&L->b0, wT_tap, g.k * g.k, g.Cin, g.Cout, L->block_n / L->cluster)) return -1;
     L->a1 = L->a0;
     L->b1 = L->b0;
     *count = 1;
@@ -257,10 +273,10 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
       p.out_sw = (long long)2 * g.Cin;
       finish_launch(L, g.Cin, false);
       if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
-      if (weight_map(&L->b0, wT_tap, 9, g.Cin, g.Cout, L->block_n)) return -1;
+      if (weight_map(&L->b0, wT_tap, 9, g.Cin, g.Cout, L->block_n / L->cluster)) return -1;
       if (fuse_ds) {
         if (act_map(&L->a1, dy_ds, g.N, Ho, Wo, cout_ds, 1, p)) return -1;
-        if (weight_map(&L->b1, wT_ds, 1, g.Cin, cout_ds, L->block_n)) return -1;
+        if (weight_map(&L->b1, wT_ds, 1, g.Cin, cout_ds, L->block_n / L->cluster)) return -1;
       } else {
         L->a1 = L->a0;
         L->b1 = L->b0;
@@ -270,27 +286,36 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
   return 0;
 }
 
-template <int BN>
+template <int BN, int CS>
 static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN>,
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, CS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         ConvCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  VPD_CHECK_CUDA(launch_kernel(conv_igemm_kernel<BN>, dim3(L.grid), dim3(kConvThreads), ConvCfg<BN>::kSmemBytes, stream, 
-      L.a0, L.a1, L.b0, L.b1, L.p));
+  VPD_CHECK_CUDA(launch_kernel_cluster(CS, conv_igemm_kernel<BN, CS>, dim3(L.grid),
+                                       dim3(kConvThreads), ConvCfg<BN>::kSmemBytes, stream, L.a0,
+                                       L.a1, L.b0, L.b1, L.p));
   VPD_LAUNCHED(1);
   return 0;
 }
 
 int launch_conv(const ConvLaunch& L, cudaStream_t stream) {
   if (L.grid <= 0) return 0;
-  switch (L.block_n) {
-    case 64: return launch_bn<64>(L, stream);
-    case 128: return launch_bn<128>(L, stream);
-    case 256: return launch_bn<256>(L, stream);
+  if (L.cluster == 2) {
+    switch (L.block_n) {
+      case 64: return launch_bn<64, 2>(L, stream);
+      case 128: return launch_bn<128, 2>(L, stream);
+      case 256: return launch_bn<256, 2>(L, stream);
+    }
+  } else {
+    switch (L.block_n) {
+      case 64: return launch_bn<64, 1>(L, stream);
+      case 128: return launch_bn<128, 1>(L, stream);
+      case 256: return launch_bn<256, 1>(L, stream);
+    }
   }
   set_error("launch_conv: bad block_n %d", L.block_n);
   return -1;

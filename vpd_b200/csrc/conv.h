@@ -9,6 +9,7 @@ struct ConvLaunch {
   CUtensorMap a0, a1, b0, b1;
   ConvParams p;
   int block_n;
+  int cluster;  // CTAs per cluster along M (weight multicast)
   int grid;
 };
 

@@ -68,7 +68,10 @@ struct ConvCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 2 * BLOCK_N * 4 + 1024;
 };
 
-template <int BLOCK_N>
+// CS = cluster size along M: the CS CTAs of a cluster work on CS adjacent pixel
+// tiles of the SAME channel block in lockstep; each loads 1/CS of the weight tile
+// and multicasts it to all of them, cutting the L2->SM weight traffic by CS.
+template <int BLOCK_N, int CS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
@@ -92,7 +95,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CS);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
@@ -109,21 +112,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kConvThreads) s_sum[i] = 0.f;
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_wait();  // everything above overlapped the previous kernel's tail
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-  const int total_tiles = m_tiles * p.n_tiles;
+  // work items are (group of CS pixel tiles, channel block); a CTA takes the pixel
+  // tile `group*CS + rank` (possibly past the end: loads zero-fill, stores masked)
+  const int rank = CS > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int total_tiles = ((m_tiles + CS - 1) / CS) * p.n_tiles;
+  const int first_item = blockIdx.x / CS;
+  const int item_stride = gridDim.x / CS;
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_item; tile < total_tiles; tile += item_stride) {
         const int n_tile = tile % p.n_tiles;
-        int mt = tile / p.n_tiles;
+        int mt = (tile / p.n_tiles) * CS + rank;
         const int w0 = (mt % p.tiles_w) * p.tw;
         mt /= p.tiles_w;
         const int h0 = (mt % p.tiles_h) * p.th;
@@ -139,7 +148,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             tma_load_5d(sa, ma, &full_bar[stage], tap.c0 + kc * kBlockK, w0 + tap.d1, tap.d2,
                         h0 + tap.d3, b0);
-            tma_load_3d(sb, mb, &full_bar[stage], kc * kBlockK, n_tile * BLOCK_N, tap.btap);
+            if (CS == 1) {
+              tma_load_3d(sb, mb, &full_bar[stage], kc * kBlockK, n_tile * BLOCK_N, tap.btap);
+            } else {
+              tma_load_3d_mcast(sb + rank * (Cfg::kBBytes / CS), mb, &full_bar[stage],
+                                kc * kBlockK, n_tile * BLOCK_N + rank * (BLOCK_N / CS), tap.btap,
+                                static_cast<uint16_t>((1u << CS) - 1));
+            }
             if (++stage == Cfg::kStages) {
               stage = 0;
               phase ^= 1;
@@ -158,7 +173,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_item; tile < total_tiles; tile += item_stride) {
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -174,7 +189,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             // advance 32 B (16 bf16) along K inside the 128 B swizzled row
             umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);
+          if (CS == 1) umma_commit(&empty_bar[stage]);
+          else umma_commit_mcast(&empty_bar[stage], static_cast<uint16_t>((1u << CS) - 1));
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -194,9 +210,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     int as = 0;
     uint32_t aphase = 0;
     int cur_ntile = -1;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = first_item; tile < total_tiles; tile += item_stride) {
       const int n_tile = tile % p.n_tiles;
-      int mt = tile / p.n_tiles;
+      int mt = (tile / p.n_tiles) * CS + rank;
       const int w0 = (mt % p.tiles_w) * p.tw;
       mt /= p.tiles_w;
       const int h0 = (mt % p.tiles_h) * p.th;
@@ -323,6 +339,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   tc_fence_before();
   __syncthreads();
+  if (CS > 1) cluster_sync_all();  // no CTA exits while a peer may still signal / multicast to it
   tc_fence_after();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }

@@ -38,21 +38,39 @@ const char* get_error();
 
 bool pdl_enabled();
 
-// Kernel launch with the programmatic-stream-serialization attribute (PDL).
+// Kernel launch with the programmatic-stream-serialization attribute (PDL) and an
+// optional thread-block cluster of `cluster` CTAs along x.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                                 cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_kernel_cluster(int cluster, void (*kernel)(KArgs...), dim3 grid,
+                                         dim3 block, size_t smem, cudaStream_t stream,
+                                         Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+  return launch_kernel_cluster(1, kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
 }
 
 #define VPD_REQUIRE(cond, ...)          \
