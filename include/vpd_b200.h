@@ -94,6 +94,14 @@ VPD_API int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N
                      int Cout, int k, int stride, int pad, const void* residual,
                      const void* dy_ds, const void* wT_ds, int cout_ds, void* stream);
 
+/* Same as vpd_conv2d_dgrad (stride 1 or 2, no downsample branch) with the BatchNorm-
+ * backward reduction of the consuming ReLU->BN stage folded into the epilogue: dx is
+ * stored already masked, g = dx * 1[z > 0], and sums[0..Cin) += sum g,
+ * sums[Cin..2Cin) += sum g * (y - mean) * rstd  (fp64, accumulated). */
+VPD_API int vpd_conv2d_dgrad_bnfused(const void* dy, const void* wT_tap, void* dx, int N, int H, int W,
+                             int Cin, int Cout, int k, int stride, int pad, const void* residual,
+                             const void* z, const void* y, const float* mean, const float* rstd,
+                             double* sums, void* stream);
 /* dw[k*k][Cout][Cin] (fp32, tap-major: the gradient arena's native conv layout)
  * += sum over pixels dy (x) x. ACCUMULATES into dw (zero it first). */
 VPD_API int vpd_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,

@@ -362,3 +362,37 @@ def test_stem_conv_wgrad(N, H, W, Cimg):
     assert rel_err(got, ref) < 2e-3, msg
     assert full[:, :, 7, :].abs().max().item() == 0.0          # kw == 7 pad never written
     assert full[:, :, :7, Cimg:].abs().max().item() == 0.0      # zero input channels
+
+
+@pytest.mark.parametrize('case', [(4, 32, 32, 64, 64, 3, 1, 1), (3, 16, 16, 128, 128, 3, 1, 1),
+                                  (5, 8, 8, 256, 256, 3, 1, 1), (2, 32, 32, 64, 128, 3, 2, 1),
+                                  (9, 4, 4, 512, 512, 3, 1, 1)])
+def test_conv2d_dgrad_with_fused_bn_backward_reduction(case):
+    N, H, W, Cin, Cout, k, stride, pad = case
+    g = torch.Generator().manual_seed(19)
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    w = torch.randn((Cout, Cin, k, k), generator=g) / (Cout * k * k) ** 0.5
+    dy = nhwc_bf16(torch.randn((N, Cout, Ho, Wo), generator=g)).to(dev())
+    wT_tap = torch.empty((k * k, Cin, Cout), device=dev(), dtype=torch.bfloat16)
+    lib().call('vpd_pack_conv_weight', w.to(dev()), None, wT_tap, Cout, Cin, k, stream_ptr())
+    res = nhwc_bf16(torch.randn((N, Cin, H, W), generator=g)).to(dev())
+    z = nhwc_bf16(torch.randn((N, Cin, H, W), generator=g).relu()).to(dev())
+    y = nhwc_bf16(torch.randn((N, Cin, H, W), generator=g) * 2 + 0.5).to(dev())
+    mean = (torch.randn(Cin, generator=g) * 0.3).to(dev())
+    rstd = (torch.rand(Cin, generator=g) + 0.5).to(dev())
+    sums = torch.zeros((2, Cin), device=dev(), dtype=torch.float64)
+    dx = torch.full((N, H, W, Cin), float('nan'), device=dev(), dtype=torch.bfloat16)
+    lib().call('vpd_conv2d_dgrad_bnfused', dy, wT_tap, dx, N, H, W, Cin, Cout, k, stride, pad, res,
+               z, y, mean, rstd, sums, stream_ptr())
+    ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w.to(torch.bfloat16).float().to(dev()),
+                                     nchw_f32(dy), stride=stride, padding=pad) + nchw_f32(res)
+    ref = ref * (nchw_f32(z) > 0)
+    got = nchw_f32(dx)
+    assert rel_err(got, ref) < 6e-3, report('dgrad_fused{}'.format(case), got, ref)
+    assert ((got == 0) | (nchw_f32(z) > 0)).all()
+    xhat = (nchw_f32(y) - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1)
+    s0 = got.double().sum((0, 2, 3))
+    s1 = (got.double() * xhat.double()).sum((0, 2, 3))
+    assert torch.allclose(sums[0], s0, rtol=1e-4, atol=1e-2)
+    assert torch.allclose(sums[1], s1, rtol=1e-4, atol=1e-2)

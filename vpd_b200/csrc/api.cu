@@ -94,6 +94,28 @@ int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N, int H,
   return 0;
 }
 
+int vpd_conv2d_dgrad_bnfused(const void* dy, const void* wT_tap, void* dx, int N, int H, int W,
+                             int Cin, int Cout, int k, int stride, int pad, const void* residual,
+                             const void* z, const void* y, const float* mean, const float* rstd,
+                             double* sums, void* stream) {
+  ConvGeom g{N, H, W, Cin, Cout, k, stride, pad};
+  ConvBwdFuse f;
+  f.nb = 1;
+  f.z = (const bf16*)z;
+  f.y[0] = (const bf16*)y;
+  f.mean[0] = mean;
+  f.rstd[0] = rstd;
+  f.sums[0] = sums;
+  ConvLaunch L[4];
+  int count = 0;
+  if (plan_conv_dgrad(L, &count, g, (const bf16*)dy, (const bf16*)wT_tap, (bf16*)dx,
+                      (const bf16*)residual, nullptr, nullptr, 0, &f))
+    return -1;
+  for (int i = 0; i < count; ++i)
+    if (launch_conv(L[i], (cudaStream_t)stream)) return -1;
+  return 0;
+}
+
 int vpd_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
                      int Cout, int k, int stride, int pad, void* stream) {
   ConvGeom g{N, H, W, Cin, Cout, k, stride, pad};

@@ -193,8 +193,22 @@ int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad
 int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bfloat16* dy,
                     const __nv_bfloat16* wT_tap, __nv_bfloat16* dx,
                     const __nv_bfloat16* residual, const __nv_bfloat16* dy_ds,
-                    const __nv_bfloat16* wT_ds, int cout_ds) {
+                    const __nv_bfloat16* wT_ds, int cout_ds, const ConvBwdFuse* fuse) {
   VPD_REQUIRE(g.Cin % 64 == 0 && g.Cout % 64 == 0, "dgrad: channels must be multiples of 64");
+  // attach the fused BN-backward reduction; `base` = element offset of this launch's
+  // first output pixel (stride-2 parity classes)
+  auto set_fuse = [&](ConvParams* p, long long base) {
+    p->bnb = 0;
+    if (fuse == nullptr || fuse->nb == 0) return;
+    p->bnb = fuse->nb;
+    p->bz = fuse->z + base;
+    for (int b = 0; b < fuse->nb; ++b) {
+      p->by[b] = fuse->y[b] + base;
+      p->bmean[b] = fuse->mean[b];
+      p->brstd[b] = fuse->rstd[b];
+      p->bsums[b] = fuse->sums[b];
+    }
+  };
   const int Ho = g.Ho(), Wo = g.Wo();
   *count = 0;
   if (g.stride == 1) {
@@ -220,7 +234,8 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
     p.out_sn = (long long)g.H * g.W * g.Cin;
     p.out_sh = (long long)g.W * g.Cin;
     p.out_sw = g.Cin;
-    finish_launch(L, g.Cin, false);
+    set_fuse(&p, 0);
+    finish_launch(L, g.Cin, p.bnb > 0);
     if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
     if (weight_map(&L->b0, wT_tap, g.k * g.k, g.Cin, g.Cout, L->block_n / L->cluster)) return -1;
     L->a1 = L->a0;
@@ -271,7 +286,8 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
       p.out_sn = (long long)g.H * g.W * g.Cin;
       p.out_sh = (long long)2 * g.W * g.Cin;
       p.out_sw = (long long)2 * g.Cin;
-      finish_launch(L, g.Cin, false);
+      set_fuse(&p, base);
+      finish_launch(L, g.Cin, p.bnb > 0);
       if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
       if (weight_map(&L->b0, wT_tap, 9, g.Cin, g.Cout, L->block_n / L->cluster)) return -1;
       if (fuse_ds) {

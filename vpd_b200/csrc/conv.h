@@ -29,6 +29,16 @@ struct ConvEpilogue {
   double* stats = nullptr;
 };
 
+// Fused BN-backward reduction for a dgrad launch (see ConvParams::bnb)
+struct ConvBwdFuse {
+  int nb = 0;
+  const __nv_bfloat16* z = nullptr;
+  const __nv_bfloat16* y[2] = {nullptr, nullptr};
+  const float* mean[2] = {nullptr, nullptr};
+  const float* rstd[2] = {nullptr, nullptr};
+  double* sums[2] = {nullptr, nullptr};
+};
+
 int device_sm_count();
 
 // y[N,Ho,Wo,Cout] = conv(x[N,H,W,Cin], w) ; w_tap = bf16 [k*k][Cout][Cin]
@@ -47,7 +57,7 @@ int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad
 int plan_conv_dgrad(ConvLaunch* L, int* count, const ConvGeom& g, const __nv_bfloat16* dy,
                     const __nv_bfloat16* wT_tap, __nv_bfloat16* dx,
                     const __nv_bfloat16* residual, const __nv_bfloat16* dy_ds,
-                    const __nv_bfloat16* wT_ds, int cout_ds);
+                    const __nv_bfloat16* wT_ds, int cout_ds, const ConvBwdFuse* fuse = nullptr);
 
 int launch_conv(const ConvLaunch& L, cudaStream_t stream);
 

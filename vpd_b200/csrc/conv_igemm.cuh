@@ -55,7 +55,41 @@ struct ConvParams {
   const float* shift;                 // [cout] or null
   int relu;
   double* stats;                      // [2][cout] (sum, sumsq) or null
+  // Fused BatchNorm-backward reduction (dgrad launches): the tile just computed is
+  // dz of a ReLU->BN stage; mask it with 1[z > 0] before it is stored (so `out`
+  // holds g) and accumulate sum(g), sum(g * xhat_b) for up to two BN branches.
+  int bnb;                            // 0 = off, else number of branches (1 or 2)
+  const __nv_bfloat16* bz;            // post-ReLU output of that stage (same addressing as out)
+  const __nv_bfloat16* by[2];         // its pre-BN conv outputs
+  const float* bmean[2];              // [cout] saved batch mean
+  const float* brstd[2];              // [cout] saved 1/sqrt(var+eps)
+  double* bsums[2];                   // [2][cout]: sum g, sum g*xhat
 };
+
+// called by the 128 epilogue threads (threadIdx.x in [64,192))
+template <int BLOCK_N>
+VPD_DEVINL void flush_channel_sums(const ConvParams& p, int ntile, float* s_sum, float* s_sq,
+                                   float* s_x2, bool clear) {
+  for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+    const int c = ntile * BLOCK_N + i;
+    if (p.stats != nullptr) {
+      atomicAdd(&p.stats[c], static_cast<double>(s_sum[i]));
+      atomicAdd(&p.stats[p.cout + c], static_cast<double>(s_sq[i]));
+    } else {
+      atomicAdd(&p.bsums[0][c], static_cast<double>(s_sum[i]));
+      atomicAdd(&p.bsums[0][p.cout + c], static_cast<double>(s_sq[i]));
+      if (p.bnb > 1) {
+        atomicAdd(&p.bsums[1][c], static_cast<double>(s_sum[i]));
+        atomicAdd(&p.bsums[1][p.cout + c], static_cast<double>(s_x2[i]));
+      }
+    }
+    if (clear) {
+      s_sum[i] = 0.f;
+      s_sq[i] = 0.f;
+      s_x2[i] = 0.f;
+    }
+  }
+}
 
 template <int BLOCK_N>
 struct ConvCfg {
@@ -65,8 +99,43 @@ struct ConvCfg {
   static constexpr int kStages = BLOCK_N == 64 ? 6 : (BLOCK_N == 128 ? 5 : 4);
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 2 * BLOCK_N * 4 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 3 * BLOCK_N * 4 + 1024;
 };
+
+// Warp transpose-reduce of two 32-wide per-lane vectors: afterwards lane j holds in
+// a[0] / b[0] the totals of column j over the warp's 32 rows (31 shuffles each).
+VPD_DEVINL void warp_colsum2(float (&a)[32], float (&b)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float ka = up ? a[i + o] : a[i];
+      const float sa = up ? a[i] : a[i + o];
+      a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, o);
+      const float kb = up ? b[i + o] : b[i];
+      const float sb = up ? b[i] : b[i + o];
+      b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+  }
+}
+struct ConvParams;
+template <int BLOCK_N>
+VPD_DEVINL void flush_channel_sums(const ConvParams& p, int ntile, float* s_sum, float* s_sq,
+                                   float* s_x2, bool clear);
+
+VPD_DEVINL void warp_colsum1(float (&a)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float ka = up ? a[i + o] : a[i];
+      const float sa = up ? a[i] : a[i + o];
+      a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, o);
+    }
+  }
+}
 
 // CS = cluster size along M: the CS CTAs of a cluster work on CS adjacent pixel
 // tiles of the SAME channel block in lockstep; each loads 1/CS of the weight tile
@@ -88,6 +157,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_sum = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes);
   float* s_sq = s_sum + BLOCK_N;
+  float* s_x2 = s_sq + BLOCK_N;  // second BN branch (fused backward reduction)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,7 +179,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kConvThreads) s_sum[i] = 0.f;
+  for (int i = threadIdx.x; i < 3 * BLOCK_N; i += kConvThreads) s_sum[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive
@@ -223,17 +293,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const bool valid = (n < p.batch) && (h < p.out_h) && (w < p.out_w);
       const long long off = n * p.out_sn + h * p.out_sh + w * p.out_sw + n_tile * BLOCK_N;
 
-      if (p.stats != nullptr && cur_ntile != n_tile) {
-        // flush per-CTA channel statistics when the channel block changes
+      if ((p.stats != nullptr || p.bnb > 0) && cur_ntile != n_tile) {
+        // flush per-CTA channel sums when the channel block changes
         // (named barrier over the 4 epilogue warps only)
         if (cur_ntile >= 0) {
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
-            atomicAdd(&p.stats[cur_ntile * BLOCK_N + i], static_cast<double>(s_sum[i]));
-            atomicAdd(&p.stats[p.cout + cur_ntile * BLOCK_N + i], static_cast<double>(s_sq[i]));
-            s_sum[i] = 0.f;
-            s_sq[i] = 0.f;
-          }
+          flush_channel_sums<BLOCK_N>(p, cur_ntile, s_sum, s_sq, s_x2, true);
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         cur_ntile = n_tile;
@@ -280,6 +345,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
+        if (p.bnb > 0) {  // g = dz * 1[z > 0]
+          if (valid) {
+            const uint4* zp = reinterpret_cast<const uint4*>(p.bz + off + c * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 zv = __ldg(zp + j);
+              f[8 * j + 0] = bf16_lo(zv.x) > 0.f ? f[8 * j + 0] : 0.f;
+              f[8 * j + 1] = bf16_hi(zv.x) > 0.f ? f[8 * j + 1] : 0.f;
+              f[8 * j + 2] = bf16_lo(zv.y) > 0.f ? f[8 * j + 2] : 0.f;
+              f[8 * j + 3] = bf16_hi(zv.y) > 0.f ? f[8 * j + 3] : 0.f;
+              f[8 * j + 4] = bf16_lo(zv.z) > 0.f ? f[8 * j + 4] : 0.f;
+              f[8 * j + 5] = bf16_hi(zv.z) > 0.f ? f[8 * j + 5] : 0.f;
+              f[8 * j + 6] = bf16_lo(zv.w) > 0.f ? f[8 * j + 6] : 0.f;
+              f[8 * j + 7] = bf16_hi(zv.w) > 0.f ? f[8 * j + 7] : 0.f;
+            }
+          }
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
@@ -301,23 +383,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             s2[2 * j] = a * a;
             s2[2 * j + 1] = b * b;
           }
-          // warp transpose-reduce: after the 5 steps lane j holds column j's
-          // total over the warp's 32 rows (31 shuffles per quantity)
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const bool up = (lane & o) != 0;
-#pragma unroll
-            for (int i = 0; i < o; ++i) {
-              const float keep = up ? s[i + o] : s[i];
-              const float send = up ? s[i] : s[i + o];
-              s[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-              const float keep2 = up ? s2[i + o] : s2[i];
-              const float send2 = up ? s2[i] : s2[i + o];
-              s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, o);
-            }
-          }
+          warp_colsum2(s, s2, lane);
           atomicAdd(&s_sum[c * 32 + lane], s[0]);
           atomicAdd(&s_sq[c * 32 + lane], s2[0]);
+        }
+        if (p.bnb > 0) {
+          // sum g and sum g*xhat of the stored (bf16-rounded) masked gradient
+          float g[32], gx[32];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            g[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
+            g[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
+          }
+#pragma unroll 1
+          for (int b = 0; b < p.bnb; ++b) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) gx[j] = 0.f;
+            if (valid) {
+              const uint4* yp = reinterpret_cast<const uint4*>(p.by[b] + off + c * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 yv = __ldg(yp + j);
+                const float4 m0 = __ldg(reinterpret_cast<const float4*>(p.bmean[b] + ch0 + 8 * j));
+                const float4 m1 = __ldg(reinterpret_cast<const float4*>(p.bmean[b] + ch0 + 8 * j + 4));
+                const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.brstd[b] + ch0 + 8 * j));
+                const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.brstd[b] + ch0 + 8 * j + 4));
+                gx[8 * j + 0] = g[8 * j + 0] * ((bf16_lo(yv.x) - m0.x) * r0.x);
+                gx[8 * j + 1] = g[8 * j + 1] * ((bf16_hi(yv.x) - m0.y) * r0.y);
+                gx[8 * j + 2] = g[8 * j + 2] * ((bf16_lo(yv.y) - m0.z) * r0.z);
+                gx[8 * j + 3] = g[8 * j + 3] * ((bf16_hi(yv.y) - m0.w) * r0.w);
+                gx[8 * j + 4] = g[8 * j + 4] * ((bf16_lo(yv.z) - m1.x) * r1.x);
+                gx[8 * j + 5] = g[8 * j + 5] * ((bf16_hi(yv.z) - m1.y) * r1.y);
+                gx[8 * j + 6] = g[8 * j + 6] * ((bf16_lo(yv.w) - m1.z) * r1.z);
+                gx[8 * j + 7] = g[8 * j + 7] * ((bf16_hi(yv.w) - m1.w) * r1.w);
+              }
+            }
+            if (b == 0) {
+              warp_colsum2(g, gx, lane);   // g is consumed here (b == 0 only)
+              atomicAdd(&s_sum[c * 32 + lane], g[0]);
+              atomicAdd(&s_sq[c * 32 + lane], gx[0]);
+            } else {
+              warp_colsum1(gx, lane);
+              atomicAdd(&s_x2[c * 32 + lane], gx[0]);
+            }
+            if (b == 0 && p.bnb > 1) {   // restore g for the second branch
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                g[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
+                g[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
+              }
+            }
+          }
         }
       }
       tc_fence_before();
@@ -328,12 +444,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         aphase ^= 1;
       }
     }
-    if (p.stats != nullptr && cur_ntile >= 0) {
+    if ((p.stats != nullptr || p.bnb > 0) && cur_ntile >= 0) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
-        atomicAdd(&p.stats[cur_ntile * BLOCK_N + i], static_cast<double>(s_sum[i]));
-        atomicAdd(&p.stats[p.cout + cur_ntile * BLOCK_N + i], static_cast<double>(s_sq[i]));
-      }
+      flush_channel_sums<BLOCK_N>(p, cur_ntile, s_sum, s_sq, s_x2, false);
     }
   }
 

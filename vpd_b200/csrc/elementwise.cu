@@ -434,13 +434,15 @@ int launch_bn_bwd(const BnBwdParams& p, cudaStream_t s) {
   const int grid_r = ew_grid(vectors, 4, 4);   // fewer blocks: every block ends in atomics
   const int grid_a = ew_grid(vectors, 4, 8);
   if (p.nbranch == 1) {
-    VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<false, 1>, dim3(grid_r), dim3(kEwThreads), 0, s, p));
+    if (!p.sums_ready)
+      VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<false, 1>, dim3(grid_r), dim3(kEwThreads), 0, s, p));
     VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<true, 1>, dim3(grid_a), dim3(kEwThreads), 0, s, p));
   } else {
-    VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<false, 2>, dim3(grid_r), dim3(kEwThreads), 0, s, p));
+    if (!p.sums_ready)
+      VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<false, 2>, dim3(grid_r), dim3(kEwThreads), 0, s, p));
     VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<true, 2>, dim3(grid_a), dim3(kEwThreads), 0, s, p));
   }
-  VPD_LAUNCHED(2);
+  VPD_LAUNCHED(p.sums_ready ? 1 : 2);
   return 0;
 }
 

@@ -54,6 +54,7 @@ struct BnBwdParams {
   long long M;
   int C;
   int nbranch;               // 1 or 2 BN branches fed by the same g
+  int sums_ready;            // 1: sums were accumulated by the producer (fused dgrad epilogue)
   const __nv_bfloat16* y[2]; // pre-BN conv outputs
   __nv_bfloat16* dy[2];      // out: gradient wrt conv outputs
   const float* gamma[2];

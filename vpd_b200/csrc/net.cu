@@ -13,6 +13,7 @@
 // BN running statistics live in a second arena: all means, then all variances.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -68,6 +69,7 @@ struct Plan {  // everything that depends on the batch size
   std::vector<std::vector<ConvLaunch>> dgrad1;   // conv1 (+ds) data grad per block
   std::vector<WgradLaunch> wg1, wg2, wgds;
   WgradLaunch wg_stem;
+  bool fused = false;  // BN-backward reductions folded into the dgrad epilogues
 };
 
 // Optional per-launch timing (CUDA events around every kernel of a step),
@@ -535,27 +537,53 @@ static Plan* get_plan(Net* n, int B) {
     ok &= !plan_conv_fwd(&P->c2_eval[i], g2, bd.z1, wt + bd.c2.w_off, bd.zout, ev(bd.b2, res, 1));
     if (n->grads) {
       // backward: dy2 in gB, dz1/dy1 in gC, dy_ds in gD
+      static const bool fuse_on = getenv("VPD_FUSE_BNBWD") == nullptr ||
+                                  getenv("VPD_FUSE_BNBWD")[0] != '0';
+      auto bn_fuse = [&](ConvBwdFuse* f, int slot, const BnDesc& b, const bf16* y) {
+        f->y[slot] = y;
+        f->mean[slot] = n->save_mean + b.ch_off;
+        f->rstd[slot] = n->save_rstd + b.ch_off;
+        f->sums[slot] = n->bwd_sums + 2 * b.ch_off;
+      };
       int cnt = 0;
       ConvLaunch tmp[4];
+      // conv2's data gradient is dz of the bn1+ReLU stage of this block
+      ConvBwdFuse f2;
+      if (fuse_on) {
+        f2.nb = 1;
+        f2.z = bd.z1;
+        bn_fuse(&f2, 0, bd.b1, bd.y1);
+      }
       ok &= !plan_conv_dgrad(tmp, &cnt, g2, n->gB, wT + bd.c2.w_off, n->gC, nullptr, nullptr,
-                             nullptr, 0);
+                             nullptr, 0, &f2);
       P->dgrad2[i] = tmp[0];
       ok &= !plan_conv_wgrad(&P->wg2[i], g2, bd.z1, n->gB, n->grads + bd.c2.w_off);
       ok &= !plan_conv_wgrad(&P->wg1[i], g1, zin, n->gC, n->grads + bd.c1.w_off);
+      // conv1's data gradient (+ identity / downsample branch) is dz of the previous
+      // block's output stage (bn2 [+ downsample bn] + ReLU)
+      ConvBwdFuse f1;
+      if (fuse_on && i > 0) {
+        BlockDesc& pb = n->blocks[i - 1];
+        f1.nb = pb.has_ds ? 2 : 1;
+        f1.z = pb.zout;
+        bn_fuse(&f1, 0, pb.b2, pb.y2);
+        if (pb.has_ds) bn_fuse(&f1, 1, pb.bds, pb.yds);
+      }
       if (bd.has_ds) {
         ok &= !plan_conv_wgrad(&P->wgds[i], geom(bd.ds, B), zin, n->gD, n->grads + bd.ds.w_off);
         if (bd.c1.stride == 2) {
           ok &= !plan_conv_dgrad(tmp, &cnt, g1, n->gC, wT + bd.c1.w_off, g_in[i], nullptr, n->gD,
-                                 wT + bd.ds.w_off, bd.ds.Cout);
+                                 wT + bd.ds.w_off, bd.ds.Cout, &f1);
         } else {
           set_error("net: stride-1 downsample blocks are not supported");
           ok = false;
         }
       } else {
         ok &= !plan_conv_dgrad(tmp, &cnt, g1, n->gC, wT + bd.c1.w_off, g_in[i], g_out[i], nullptr,
-                               nullptr, 0);
+                               nullptr, 0, &f1);
       }
       P->dgrad1[i].assign(tmp, tmp + cnt);
+      P->fused = fuse_on;
     }
     zin = bd.zout;
   }
@@ -747,9 +775,11 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     const long long M = (long long)B * bd.c2.Hin * bd.c2.Win;
     BnBwdParams q;
     memset(&q, 0, sizeof(q));
+    const bool pre2 = P->fused && i + 1 < (int)nb;  // dz already masked + reduced by dgrad1[i+1]
     q.dz = cur;
-    q.z = bd.zout;
-    q.dmask = bd.has_ds ? nullptr : cur;  // identity gradient, reused as dgrad residual
+    q.z = pre2 ? nullptr : bd.zout;
+    q.dmask = (bd.has_ds || pre2) ? nullptr : cur;  // identity gradient, reused as dgrad residual
+    q.sums_ready = pre2 ? 1 : 0;
     q.M = M;
     q.C = bd.c2.Cout;
     q.nbranch = bd.has_ds ? 2 : 1;
@@ -771,7 +801,8 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     PROF(kConvDgrad, bd.stage, launch_conv(P->dgrad2[i], s));  // gB -> gC
     memset(&q, 0, sizeof(q));
     q.dz = n->gC;
-    q.z = bd.z1;
+    q.z = P->fused ? nullptr : bd.z1;   // fused: dgrad2 already masked + reduced
+    q.sums_ready = P->fused ? 1 : 0;
     q.M = M;
     q.C = bd.c1.Cout;
     q.nbranch = 1;
