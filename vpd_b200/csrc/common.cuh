@@ -218,6 +218,34 @@ VPD_DEVINL void stg_cs_v4(void* p, uint4 v) {  // streaming store (evict-first)
                : "memory");
 }
 
+// Explicit shared-space accesses. Pointers carved out of the dynamic smem buffer via
+// integer arithmetic are GENERIC to the compiler: plain loads/stores become LD.E/ST.E
+// and atomicAdd becomes a CAS loop; these wrappers emit LDS/STS/RED.shared instead.
+VPD_DEVINL void sts_v4(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+VPD_DEVINL uint4 lds_v4(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "r"(saddr)
+               : "memory");
+  return r;
+}
+VPD_DEVINL float4 __uint4_as_float4(uint4 v) {
+  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+VPD_DEVINL float lds_f32(uint32_t saddr) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(saddr) : "memory");
+  return r;
+}
+VPD_DEVINL void red_shared_add(uint32_t saddr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
+
 VPD_DEVINL float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

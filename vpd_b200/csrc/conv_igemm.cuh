@@ -99,7 +99,7 @@ struct ConvCfg {
   static constexpr int kStages = BLOCK_N == 64 ? 6 : (BLOCK_N == 128 ? 5 : 4);
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 3 * BLOCK_N * 4 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 7 * BLOCK_N * 4 + 1024;
 };
 
 // Warp transpose-reduce of two 32-wide per-lane vectors: afterwards lane j holds in
@@ -158,6 +158,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   float* s_sum = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes);
   float* s_sq = s_sum + BLOCK_N;
   float* s_x2 = s_sq + BLOCK_N;  // second BN branch (fused backward reduction)
+  float* s_bn = s_x2 + BLOCK_N;  // [mean0 | rstd0 | mean1 | rstd1] of the current channel block
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -302,6 +303,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           asm volatile("bar.sync 1, 128;" ::: "memory");
         }
         cur_ntile = n_tile;
+        if (p.bnb > 0) {
+          for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+            const int ch = n_tile * BLOCK_N + i;
+            s_bn[i] = __ldg(p.bmean[0] + ch);
+            s_bn[BLOCK_N + i] = __ldg(p.brstd[0] + ch);
+            if (p.bnb > 1) {
+              s_bn[2 * BLOCK_N + i] = __ldg(p.bmean[1] + ch);
+              s_bn[3 * BLOCK_N + i] = __ldg(p.brstd[1] + ch);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
       }
 
       mbar_wait(&tfull_bar[as], aphase);
@@ -310,6 +323,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
+        // issue every global load of this chunk before waiting on anything, so the
+        // TMEM read and the (up to four) 64-byte row segments are all in flight together
+        const bool do_res = p.residual != nullptr && valid;
+        const bool do_bn = p.bnb > 0 && valid;
+        uint4 rres[4], rz[4], ry0[4], ry1[4];
+        if (do_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rres[j] = rp[j];  // plain load: residual may alias out
+        }
+        if (do_bn) {
+          const uint4* zp = reinterpret_cast<const uint4*>(p.bz + off + c * 32);
+          const uint4* yp = reinterpret_cast<const uint4*>(p.by[0] + off + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rz[j] = __ldg(zp + j);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ry0[j] = __ldg(yp + j);
+          if (p.bnb > 1) {
+            const uint4* y1p = reinterpret_cast<const uint4*>(p.by[1] + off + c * 32);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ry1[j] = __ldg(y1p + j);
+          }
+        }
         tmem_ld_wait();
         float f[32];
 #pragma unroll
@@ -326,40 +362,34 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             f[j + 3] = fmaf(f[j + 3], sc.w, sh.w);
           }
         }
-        if (p.residual != nullptr && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
+        if (do_res) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 rv = rp[j];  // plain load: residual may alias out
-            f[8 * j + 0] += bf16_lo(rv.x);
-            f[8 * j + 1] += bf16_hi(rv.x);
-            f[8 * j + 2] += bf16_lo(rv.y);
-            f[8 * j + 3] += bf16_hi(rv.y);
-            f[8 * j + 4] += bf16_lo(rv.z);
-            f[8 * j + 5] += bf16_hi(rv.z);
-            f[8 * j + 6] += bf16_lo(rv.w);
-            f[8 * j + 7] += bf16_hi(rv.w);
+            f[8 * j + 0] += bf16_lo(rres[j].x);
+            f[8 * j + 1] += bf16_hi(rres[j].x);
+            f[8 * j + 2] += bf16_lo(rres[j].y);
+            f[8 * j + 3] += bf16_hi(rres[j].y);
+            f[8 * j + 4] += bf16_lo(rres[j].z);
+            f[8 * j + 5] += bf16_hi(rres[j].z);
+            f[8 * j + 6] += bf16_lo(rres[j].w);
+            f[8 * j + 7] += bf16_hi(rres[j].w);
           }
         }
         if (p.relu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        if (p.bnb > 0) {  // g = dz * 1[z > 0]
-          if (valid) {
-            const uint4* zp = reinterpret_cast<const uint4*>(p.bz + off + c * 32);
+        if (do_bn) {  // g = dz * 1[z > 0]
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 zv = __ldg(zp + j);
-              f[8 * j + 0] = bf16_lo(zv.x) > 0.f ? f[8 * j + 0] : 0.f;
-              f[8 * j + 1] = bf16_hi(zv.x) > 0.f ? f[8 * j + 1] : 0.f;
-              f[8 * j + 2] = bf16_lo(zv.y) > 0.f ? f[8 * j + 2] : 0.f;
-              f[8 * j + 3] = bf16_hi(zv.y) > 0.f ? f[8 * j + 3] : 0.f;
-              f[8 * j + 4] = bf16_lo(zv.z) > 0.f ? f[8 * j + 4] : 0.f;
-              f[8 * j + 5] = bf16_hi(zv.z) > 0.f ? f[8 * j + 5] : 0.f;
-              f[8 * j + 6] = bf16_lo(zv.w) > 0.f ? f[8 * j + 6] : 0.f;
-              f[8 * j + 7] = bf16_hi(zv.w) > 0.f ? f[8 * j + 7] : 0.f;
-            }
+          for (int j = 0; j < 4; ++j) {
+            f[8 * j + 0] = bf16_lo(rz[j].x) > 0.f ? f[8 * j + 0] : 0.f;
+            f[8 * j + 1] = bf16_hi(rz[j].x) > 0.f ? f[8 * j + 1] : 0.f;
+            f[8 * j + 2] = bf16_lo(rz[j].y) > 0.f ? f[8 * j + 2] : 0.f;
+            f[8 * j + 3] = bf16_hi(rz[j].y) > 0.f ? f[8 * j + 3] : 0.f;
+            f[8 * j + 4] = bf16_lo(rz[j].z) > 0.f ? f[8 * j + 4] : 0.f;
+            f[8 * j + 5] = bf16_hi(rz[j].z) > 0.f ? f[8 * j + 5] : 0.f;
+            f[8 * j + 6] = bf16_lo(rz[j].w) > 0.f ? f[8 * j + 6] : 0.f;
+            f[8 * j + 7] = bf16_hi(rz[j].w) > 0.f ? f[8 * j + 7] : 0.f;
           }
         }
         uint32_t pk[16];
@@ -384,8 +414,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             s2[2 * j + 1] = b * b;
           }
           warp_colsum2(s, s2, lane);
-          atomicAdd(&s_sum[c * 32 + lane], s[0]);
-          atomicAdd(&s_sq[c * 32 + lane], s2[0]);
+          red_shared_add(smem_u32(s_sum + c * 32 + lane), s[0]);
+          red_shared_add(smem_u32(s_sq + c * 32 + lane), s2[0]);
         }
         if (p.bnb > 0) {
           // sum g and sum g*xhat of the stored (bf16-rounded) masked gradient
@@ -395,45 +425,45 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             g[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
             g[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
           }
-#pragma unroll 1
-          for (int b = 0; b < p.bnb; ++b) {
+          const uint32_t sbn = smem_u32(s_bn + c * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) gx[j] = 0.f;
-            if (valid) {
-              const uint4* yp = reinterpret_cast<const uint4*>(p.by[b] + off + c * 32);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 yv = __ldg(yp + j);
-                const float4 m0 = __ldg(reinterpret_cast<const float4*>(p.bmean[b] + ch0 + 8 * j));
-                const float4 m1 = __ldg(reinterpret_cast<const float4*>(p.bmean[b] + ch0 + 8 * j + 4));
-                const float4 r0 = __ldg(reinterpret_cast<const float4*>(p.brstd[b] + ch0 + 8 * j));
-                const float4 r1 = __ldg(reinterpret_cast<const float4*>(p.brstd[b] + ch0 + 8 * j + 4));
-                gx[8 * j + 0] = g[8 * j + 0] * ((bf16_lo(yv.x) - m0.x) * r0.x);
-                gx[8 * j + 1] = g[8 * j + 1] * ((bf16_hi(yv.x) - m0.y) * r0.y);
-                gx[8 * j + 2] = g[8 * j + 2] * ((bf16_lo(yv.y) - m0.z) * r0.z);
-                gx[8 * j + 3] = g[8 * j + 3] * ((bf16_hi(yv.y) - m0.w) * r0.w);
-                gx[8 * j + 4] = g[8 * j + 4] * ((bf16_lo(yv.z) - m1.x) * r1.x);
-                gx[8 * j + 5] = g[8 * j + 5] * ((bf16_hi(yv.z) - m1.y) * r1.y);
-                gx[8 * j + 6] = g[8 * j + 6] * ((bf16_lo(yv.w) - m1.z) * r1.z);
-                gx[8 * j + 7] = g[8 * j + 7] * ((bf16_hi(yv.w) - m1.w) * r1.w);
-              }
-            }
-            if (b == 0) {
-              warp_colsum2(g, gx, lane);   // g is consumed here (b == 0 only)
-              atomicAdd(&s_sum[c * 32 + lane], g[0]);
-              atomicAdd(&s_sq[c * 32 + lane], gx[0]);
-            } else {
-              warp_colsum1(gx, lane);
-              atomicAdd(&s_x2[c * 32 + lane], gx[0]);
-            }
-            if (b == 0 && p.bnb > 1) {   // restore g for the second branch
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                g[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
-                g[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
-              }
-            }
+          for (int j = 0; j < 4; ++j) {
+            const float4 m0 = __uint4_as_float4(lds_v4(sbn + 32 * j));
+            const float4 m1 = __uint4_as_float4(lds_v4(sbn + 32 * j + 16));
+            const float4 r0 = __uint4_as_float4(lds_v4(sbn + 4 * BLOCK_N + 32 * j));
+            const float4 r1 = __uint4_as_float4(lds_v4(sbn + 4 * BLOCK_N + 32 * j + 16));
+            gx[8 * j + 0] = do_bn ? g[8 * j + 0] * ((bf16_lo(ry0[j].x) - m0.x) * r0.x) : 0.f;
+            gx[8 * j + 1] = do_bn ? g[8 * j + 1] * ((bf16_hi(ry0[j].x) - m0.y) * r0.y) : 0.f;
+            gx[8 * j + 2] = do_bn ? g[8 * j + 2] * ((bf16_lo(ry0[j].y) - m0.z) * r0.z) : 0.f;
+            gx[8 * j + 3] = do_bn ? g[8 * j + 3] * ((bf16_hi(ry0[j].y) - m0.w) * r0.w) : 0.f;
+            gx[8 * j + 4] = do_bn ? g[8 * j + 4] * ((bf16_lo(ry0[j].z) - m1.x) * r1.x) : 0.f;
+            gx[8 * j + 5] = do_bn ? g[8 * j + 5] * ((bf16_hi(ry0[j].z) - m1.y) * r1.y) : 0.f;
+            gx[8 * j + 6] = do_bn ? g[8 * j + 6] * ((bf16_lo(ry0[j].w) - m1.z) * r1.z) : 0.f;
+            gx[8 * j + 7] = do_bn ? g[8 * j + 7] * ((bf16_hi(ry0[j].w) - m1.w) * r1.w) : 0.f;
           }
+          if (p.bnb > 1) {
+            float gx1[32];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 m0 = __uint4_as_float4(lds_v4(sbn + 8 * BLOCK_N + 32 * j));
+              const float4 m1 = __uint4_as_float4(lds_v4(sbn + 8 * BLOCK_N + 32 * j + 16));
+              const float4 r0 = __uint4_as_float4(lds_v4(sbn + 12 * BLOCK_N + 32 * j));
+              const float4 r1 = __uint4_as_float4(lds_v4(sbn + 12 * BLOCK_N + 32 * j + 16));
+              gx1[8 * j + 0] = do_bn ? g[8 * j + 0] * ((bf16_lo(ry1[j].x) - m0.x) * r0.x) : 0.f;
+              gx1[8 * j + 1] = do_bn ? g[8 * j + 1] * ((bf16_hi(ry1[j].x) - m0.y) * r0.y) : 0.f;
+              gx1[8 * j + 2] = do_bn ? g[8 * j + 2] * ((bf16_lo(ry1[j].y) - m0.z) * r0.z) : 0.f;
+              gx1[8 * j + 3] = do_bn ? g[8 * j + 3] * ((bf16_hi(ry1[j].y) - m0.w) * r0.w) : 0.f;
+              gx1[8 * j + 4] = do_bn ? g[8 * j + 4] * ((bf16_lo(ry1[j].z) - m1.x) * r1.x) : 0.f;
+              gx1[8 * j + 5] = do_bn ? g[8 * j + 5] * ((bf16_hi(ry1[j].z) - m1.y) * r1.y) : 0.f;
+              gx1[8 * j + 6] = do_bn ? g[8 * j + 6] * ((bf16_lo(ry1[j].w) - m1.z) * r1.z) : 0.f;
+              gx1[8 * j + 7] = do_bn ? g[8 * j + 7] * ((bf16_hi(ry1[j].w) - m1.w) * r1.w) : 0.f;
+            }
+            warp_colsum1(gx1, lane);
+            red_shared_add(smem_u32(s_x2 + c * 32 + lane), gx1[0]);
+          }
+          warp_colsum2(g, gx, lane);
+          red_shared_add(smem_u32(s_sum + c * 32 + lane), g[0]);
+          red_shared_add(smem_u32(s_sq + c * 32 + lane), gx[0]);
         }
       }
       tc_fence_before();
