@@ -62,7 +62,9 @@ static void finish_launch(ConvLaunch* L, int cout, bool stats) {
   L->block_n = pick_block_n(cout, m_tiles);
   L->p.n_tiles = cout / L->block_n;
   L->p.cout = cout;
-  static const int want_cluster = env_int("VPD_CLUSTER", 2);
+  // weight multicast over a 2-CTA cluster is implemented and tested, but measured no
+  // gain on B200 (L2 de-duplicates only for clusters >= 8), so it is opt-in
+  static const int want_cluster = env_int("VPD_CLUSTER", 1);
   L->cluster = (want_cluster >= 2 && m_tiles >= 2) ? 2 : 1;
   const int cs = L->cluster;
   const int items = ((m_tiles + cs - 1) / cs) * L->p.n_tiles;  // cluster-level work items
@@ -98,6 +100,55 @@ static int act_map(CUtensorMap* m, const __nv_bfloat16* x, int N, int H, int W, 
   uint64_t str[5] = {2, (uint64_t)2 * C * 2, (uint64_t)W * C * 2, (uint64_t)2 * W * C * 2,
                      (uint64_t)H * W * C * 2};
   return encode_tmap_bf16(m, x, 5, dims, str, box, true);
+}
+
+// Re-plan a stride-1 3x3 'same' convolution (forward or dgrad) for the halo-reuse
+// kernel: 8x16 pixel tiles, 64-wide channel blocks with resident weights.
+// `x`: the tensor the taps read ([N][H][W][Cin_k]); `wt`: its tap-major weights
+// [9][Cout_k][Cin_k]. Returns false when the shape does not qualify.
+static thread_local bool g_plan_no_halo = false;  // set while planning wgrad helpers
+
+static bool try_halo(ConvLaunch* L, const __nv_bfloat16* x, const __nv_bfloat16* wt, int N, int H,
+                     int W, int cin_k, int cout_k, bool stats) {
+  static const int enable = env_int("VPD_HALO", 1);
+  if (g_plan_no_halo) return false;
+  const int chunks = cin_k / 64;
+  if (!enable || (chunks != 1 && chunks != 2) || cin_k % 64 != 0 || cout_k % 64 != 0) return false;
+  if (H % 16 != 0 || W % 8 != 0) return false;
+  // 128-channel layers: resident weights force 64-wide channel blocks, which measured
+  // no faster than the generic 128-wide tiles -> opt-in
+  if (chunks == 2 && !env_int("VPD_HALO2", 0)) return false;
+  ConvParams& p = L->p;
+  p.tw = 8;
+  p.th = 16;
+  p.tn = 1;
+  p.tiles_w = W / 8;
+  p.tiles_h = H / 16;
+  p.tiles_b = N;
+  p.batch = N;
+  p.out_h = H;
+  p.out_w = W;
+  L->block_n = 64;
+  L->cluster = 1;
+  L->halo = chunks;
+  p.n_tiles = cout_k / 64;
+  p.cout = cout_k;
+  const int total = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
+  int grid = device_sm_count();
+  if (grid > total) grid = total;
+  grid -= grid % p.n_tiles;  // fixed channel block per CTA (resident weights)
+  if (grid <= 0) return false;
+  L->grid = grid;
+  (void)stats;
+  uint64_t dims[5] = {(uint64_t)cin_k, (uint64_t)W, 1, (uint64_t)H, (uint64_t)N};
+  uint64_t str[5] = {2, (uint64_t)cin_k * 2, (uint64_t)W * cin_k * 2, (uint64_t)W * cin_k * 2,
+                     (uint64_t)H * W * cin_k * 2};
+  uint32_t box[5] = {64, 10, 1, 18, 1};
+  if (encode_tmap_bf16(&L->a0, x, 5, dims, str, box, true)) return false;
+  if (weight_map(&L->b0, wt, 9, cout_k, cin_k, 64)) return false;
+  L->a1 = L->a0;
+  L->b1 = L->b0;
+  return true;
 }
 
 static void set_epilogue(ConvParams* p, const ConvEpilogue& e) {
@@ -144,6 +195,9 @@ int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
   p.out_sh = (long long)Wo * g.Cout;
   p.out_sw = g.Cout;
   set_epilogue(&p, e);
+  if (g.k == 3 && g.stride == 1 && g.pad == 1 &&
+      try_halo(L, x, w_tap, g.N, g.H, g.W, g.Cin, g.Cout, e.stats != nullptr))
+    return 0;
   finish_launch(L, g.Cout, e.stats != nullptr);
   if (act_map(&L->a0, x, g.N, g.H, g.W, g.Cin, g.stride, p)) return -1;
   if (weight_map(&L->b0, w_tap, g.k * g.k, g.Cout, g.Cin, L->block_n / L->cluster)) return -1;
@@ -235,6 +289,10 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
     p.out_sh = (long long)g.W * g.Cin;
     p.out_sw = g.Cin;
     set_fuse(&p, 0);
+    if (g.k == 3 && try_halo(L, dy, wT_tap, g.N, Ho, Wo, g.Cout, g.Cin, p.bnb > 0)) {
+      *count = 1;
+      return 0;
+    }
     finish_launch(L, g.Cin, p.bnb > 0);
     if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
     if (weight_map(&L->b0, wT_tap, g.k * g.k, g.Cin, g.Cout, L->block_n / L->cluster)) return -1;
@@ -318,8 +376,25 @@ static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
   return 0;
 }
 
+template <int CHUNKS>
+static int launch_halo(const ConvLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<CHUNKS>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        HaloCfg<CHUNKS>::kSmemBytes));
+    attr_set = true;
+  }
+  VPD_CHECK_CUDA(launch_kernel(conv3x3_halo_kernel<CHUNKS>, dim3(L.grid), dim3(kConvThreads),
+                               HaloCfg<CHUNKS>::kSmemBytes, stream, L.a0, L.b0, L.p));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
 int launch_conv(const ConvLaunch& L, cudaStream_t stream) {
   if (L.grid <= 0) return 0;
+  if (L.halo == 1) return launch_halo<1>(L, stream);
+  if (L.halo == 2) return launch_halo<2>(L, stream);
   if (L.cluster == 2) {
     switch (L.block_n) {
       case 64: return launch_bn<64, 2>(L, stream);
@@ -378,9 +453,11 @@ int plan_conv_wgrad(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
   // reuse the forward plan for tile geometry, taps and the X tensor-map view
   ConvLaunch f;
   ConvEpilogue e;
-  if (plan_conv_fwd(&f, g, x, reinterpret_cast<const __nv_bfloat16*>(dw),
-                    const_cast<__nv_bfloat16*>(dy), e))
-    return -1;
+  g_plan_no_halo = true;
+  const int rc = plan_conv_fwd(&f, g, x, reinterpret_cast<const __nv_bfloat16*>(dw),
+                               const_cast<__nv_bfloat16*>(dy), e);
+  g_plan_no_halo = false;
+  if (rc) return -1;
   copy_geometry(&L->p, f.p);
   L->x = f.a0;
   if (act_map(&L->dy, dy, g.N, g.Ho(), g.Wo(), g.Cout, 1, f.p)) return -1;
@@ -412,7 +489,7 @@ static int launch_wgrad_bn(const WgradLaunch& L, cudaStream_t stream) {
                                         WgradCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  VPD_CHECK_CUDA(launch_kernel(conv_wgrad_kernel<BN>, dim3(L.grid), dim3(kConvThreads), WgradCfg<BN>::kSmemBytes, stream, L.x, L.dy, L.p));
+  VPD_CHECK_CUDA(launch_kernel(conv_wgrad_kernel<BN>, dim3(L.grid), dim3(kWgradThreads), WgradCfg<BN>::kSmemBytes, stream, L.x, L.dy, L.p));
   VPD_LAUNCHED(1);
   return 0;
 }

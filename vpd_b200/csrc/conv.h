@@ -10,6 +10,7 @@ struct ConvLaunch {
   ConvParams p;
   int block_n;
   int cluster;  // CTAs per cluster along M (weight multicast)
+  int halo;     // 0 = generic kernel, else number of 64-channel chunks (halo-reuse kernel)
   int grid;
 };
 

@@ -29,7 +29,10 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kMaxTaps = 12;
-constexpr int kConvThreads = 192;
+constexpr int kEpiWarps = 4;                       // epilogue warps (one per TMEM lane quarter; 8 was slower)
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kConvThreads = 64 + kEpiThreads;     // TMA warp + MMA warp + epilogue warps
+constexpr int kWgradThreads = 192;
 
 struct ConvTap {
   int c0;       // offset added to the innermost (channel) coordinate
@@ -70,7 +73,7 @@ struct ConvParams {
 template <int BLOCK_N>
 VPD_DEVINL void flush_channel_sums(const ConvParams& p, int ntile, float* s_sum, float* s_sq,
                                    float* s_x2, bool clear) {
-  for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
+  for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiThreads) {
     const int c = ntile * BLOCK_N + i;
     if (p.stats != nullptr) {
       atomicAdd(&p.stats[c], static_cast<double>(s_sum[i]));
@@ -137,6 +140,218 @@ VPD_DEVINL void warp_colsum1(float (&a)[32], int lane) {
   }
 }
 
+// Epilogue shared by the implicit-GEMM kernels: executed by warps 2..5 (threads
+// 64..191); drains the TMEM accumulator stages tile by tile.
+template <int BLOCK_N, int CS>
+VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
+                              uint64_t* tempty_bar, float* s_sum, float* s_sq, float* s_x2,
+                              float* s_bn, int rank, int first_item, int item_stride,
+                              int total_tiles, int warp, int lane) {
+  // ---------------------------------------------------------------- epilogue
+  const int q = warp & 3;       // TMEM lane quarter this warp may access
+  const int r = q * 32 + lane;  // row of the 128-row tile
+  int as = 0;
+  uint32_t aphase = 0;
+  int cur_ntile = -1;
+  for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+    const int n_tile = tile % p.n_tiles;
+    int mt = (tile / p.n_tiles) * CS + rank;
+    const int w0 = (mt % p.tiles_w) * p.tw;
+    mt /= p.tiles_w;
+    const int h0 = (mt % p.tiles_h) * p.th;
+    const int b0 = (mt / p.tiles_h) * p.tn;
+    const int w = w0 + r % p.tw;
+    const int h = h0 + (r / p.tw) % p.th;
+    const int n = b0 + r / (p.tw * p.th);
+    const bool valid = (n < p.batch) && (h < p.out_h) && (w < p.out_w);
+    const long long off = n * p.out_sn + h * p.out_sh + w * p.out_sw + n_tile * BLOCK_N;
+
+    if ((p.stats != nullptr || p.bnb > 0) && cur_ntile != n_tile) {
+      // flush per-CTA channel sums when the channel block changes
+      // (named barrier over the 4 epilogue warps only)
+      if (cur_ntile >= 0) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+        flush_channel_sums<BLOCK_N>(p, cur_ntile, s_sum, s_sq, s_x2, true);
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      }
+      cur_ntile = n_tile;
+      if (p.bnb > 0) {
+        for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiThreads) {
+          const int ch = n_tile * BLOCK_N + i;
+          s_bn[i] = __ldg(p.bmean[0] + ch);
+          s_bn[BLOCK_N + i] = __ldg(p.brstd[0] + ch);
+          if (p.bnb > 1) {
+            s_bn[2 * BLOCK_N + i] = __ldg(p.bmean[1] + ch);
+            s_bn[3 * BLOCK_N + i] = __ldg(p.brstd[1] + ch);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+      }
+    }
+
+    mbar_wait(&tfull_bar[as], aphase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
+      // issue every global load of this chunk before waiting on anything, so the
+      // TMEM read and the (up to four) 64-byte row segments are all in flight together
+      const bool do_res = p.residual != nullptr && valid;
+      const bool do_bn = p.bnb > 0 && valid;
+      uint4 rres[4], rz[4], ry0[4], ry1[4];
+      if (do_res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rres[j] = rp[j];  // plain load: residual may alias out
+      }
+      if (do_bn) {
+        const uint4* zp = reinterpret_cast<const uint4*>(p.bz + off + c * 32);
+        const uint4* yp = reinterpret_cast<const uint4*>(p.by[0] + off + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rz[j] = __ldg(zp + j);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ry0[j] = __ldg(yp + j);
+        if (p.bnb > 1) {
+          const uint4* y1p = reinterpret_cast<const uint4*>(p.by[1] + off + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) ry1[j] = __ldg(y1p + j);
+        }
+      }
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+      const int ch0 = n_tile * BLOCK_N + c * 32;
+      if (p.scale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + j));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch0 + j));
+          f[j + 0] = fmaf(f[j + 0], sc.x, sh.x);
+          f[j + 1] = fmaf(f[j + 1], sc.y, sh.y);
+          f[j + 2] = fmaf(f[j + 2], sc.z, sh.z);
+          f[j + 3] = fmaf(f[j + 3], sc.w, sh.w);
+        }
+      }
+      if (do_res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[8 * j + 0] += bf16_lo(rres[j].x);
+          f[8 * j + 1] += bf16_hi(rres[j].x);
+          f[8 * j + 2] += bf16_lo(rres[j].y);
+          f[8 * j + 3] += bf16_hi(rres[j].y);
+          f[8 * j + 4] += bf16_lo(rres[j].z);
+          f[8 * j + 5] += bf16_hi(rres[j].z);
+          f[8 * j + 6] += bf16_lo(rres[j].w);
+          f[8 * j + 7] += bf16_hi(rres[j].w);
+        }
+      }
+      if (p.relu) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (do_bn) {  // g = dz * 1[z > 0]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[8 * j + 0] = bf16_lo(rz[j].x) > 0.f ? f[8 * j + 0] : 0.f;
+          f[8 * j + 1] = bf16_hi(rz[j].x) > 0.f ? f[8 * j + 1] : 0.f;
+          f[8 * j + 2] = bf16_lo(rz[j].y) > 0.f ? f[8 * j + 2] : 0.f;
+          f[8 * j + 3] = bf16_hi(rz[j].y) > 0.f ? f[8 * j + 3] : 0.f;
+          f[8 * j + 4] = bf16_lo(rz[j].z) > 0.f ? f[8 * j + 4] : 0.f;
+          f[8 * j + 5] = bf16_hi(rz[j].z) > 0.f ? f[8 * j + 5] : 0.f;
+          f[8 * j + 6] = bf16_lo(rz[j].w) > 0.f ? f[8 * j + 6] : 0.f;
+          f[8 * j + 7] = bf16_hi(rz[j].w) > 0.f ? f[8 * j + 7] : 0.f;
+        }
+      }
+      uint32_t pk[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+      if (valid) {
+        uint4* op = reinterpret_cast<uint4*>(p.out + off + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          stg_v4(op + j, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
+      }
+      if (p.stats != nullptr) {
+        // statistics of the values as stored (bf16-rounded); invalid rows = 0
+        float s[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float a = valid ? bf16_lo(pk[j]) : 0.f;
+          const float b = valid ? bf16_hi(pk[j]) : 0.f;
+          s[2 * j] = a;
+          s[2 * j + 1] = b;
+          s2[2 * j] = a * a;
+          s2[2 * j + 1] = b * b;
+        }
+        warp_colsum2(s, s2, lane);
+        red_shared_add(smem_u32(s_sum + c * 32 + lane), s[0]);
+        red_shared_add(smem_u32(s_sq + c * 32 + lane), s2[0]);
+      }
+      if (p.bnb > 0) {
+        // sum g and sum g*xhat of the stored (bf16-rounded) masked gradient
+        float g[32], gx[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          g[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
+          g[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
+        }
+        const uint32_t sbn = smem_u32(s_bn + c * 32);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 m0 = __uint4_as_float4(lds_v4(sbn + 32 * j));
+          const float4 m1 = __uint4_as_float4(lds_v4(sbn + 32 * j + 16));
+          const float4 r0 = __uint4_as_float4(lds_v4(sbn + 4 * BLOCK_N + 32 * j));
+          const float4 r1 = __uint4_as_float4(lds_v4(sbn + 4 * BLOCK_N + 32 * j + 16));
+          gx[8 * j + 0] = do_bn ? g[8 * j + 0] * ((bf16_lo(ry0[j].x) - m0.x) * r0.x) : 0.f;
+          gx[8 * j + 1] = do_bn ? g[8 * j + 1] * ((bf16_hi(ry0[j].x) - m0.y) * r0.y) : 0.f;
+          gx[8 * j + 2] = do_bn ? g[8 * j + 2] * ((bf16_lo(ry0[j].y) - m0.z) * r0.z) : 0.f;
+          gx[8 * j + 3] = do_bn ? g[8 * j + 3] * ((bf16_hi(ry0[j].y) - m0.w) * r0.w) : 0.f;
+          gx[8 * j + 4] = do_bn ? g[8 * j + 4] * ((bf16_lo(ry0[j].z) - m1.x) * r1.x) : 0.f;
+          gx[8 * j + 5] = do_bn ? g[8 * j + 5] * ((bf16_hi(ry0[j].z) - m1.y) * r1.y) : 0.f;
+          gx[8 * j + 6] = do_bn ? g[8 * j + 6] * ((bf16_lo(ry0[j].w) - m1.z) * r1.z) : 0.f;
+          gx[8 * j + 7] = do_bn ? g[8 * j + 7] * ((bf16_hi(ry0[j].w) - m1.w) * r1.w) : 0.f;
+        }
+        if (p.bnb > 1) {
+          float gx1[32];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 m0 = __uint4_as_float4(lds_v4(sbn + 8 * BLOCK_N + 32 * j));
+            const float4 m1 = __uint4_as_float4(lds_v4(sbn + 8 * BLOCK_N + 32 * j + 16));
+            const float4 r0 = __uint4_as_float4(lds_v4(sbn + 12 * BLOCK_N + 32 * j));
+            const float4 r1 = __uint4_as_float4(lds_v4(sbn + 12 * BLOCK_N + 32 * j + 16));
+            gx1[8 * j + 0] = do_bn ? g[8 * j + 0] * ((bf16_lo(ry1[j].x) - m0.x) * r0.x) : 0.f;
+            gx1[8 * j + 1] = do_bn ? g[8 * j + 1] * ((bf16_hi(ry1[j].x) - m0.y) * r0.y) : 0.f;
+            gx1[8 * j + 2] = do_bn ? g[8 * j + 2] * ((bf16_lo(ry1[j].y) - m0.z) * r0.z) : 0.f;
+            gx1[8 * j + 3] = do_bn ? g[8 * j + 3] * ((bf16_hi(ry1[j].y) - m0.w) * r0.w) : 0.f;
+            gx1[8 * j + 4] = do_bn ? g[8 * j + 4] * ((bf16_lo(ry1[j].z) - m1.x) * r1.x) : 0.f;
+            gx1[8 * j + 5] = do_bn ? g[8 * j + 5] * ((bf16_hi(ry1[j].z) - m1.y) * r1.y) : 0.f;
+            gx1[8 * j + 6] = do_bn ? g[8 * j + 6] * ((bf16_lo(ry1[j].w) - m1.z) * r1.z) : 0.f;
+            gx1[8 * j + 7] = do_bn ? g[8 * j + 7] * ((bf16_hi(ry1[j].w) - m1.w) * r1.w) : 0.f;
+          }
+          warp_colsum1(gx1, lane);
+          red_shared_add(smem_u32(s_x2 + c * 32 + lane), gx1[0]);
+        }
+        warp_colsum2(g, gx, lane);
+        red_shared_add(smem_u32(s_sum + c * 32 + lane), g[0]);
+        red_shared_add(smem_u32(s_sq + c * 32 + lane), gx[0]);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    if (++as == 2) {
+      as = 0;
+      aphase ^= 1;
+    }
+  }
+  if ((p.stats != nullptr || p.bnb > 0) && cur_ntile >= 0) {
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+    flush_channel_sums<BLOCK_N>(p, cur_ntile, s_sum, s_sq, s_x2, false);
+  }
+}
+
 // CS = cluster size along M: the CS CTAs of a cluster work on CS adjacent pixel
 // tiles of the SAME channel block in lockstep; each loads 1/CS of the weight tile
 // and multicasts it to all of them, cutting the L2->SM weight traffic by CS.
@@ -170,7 +385,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], 4);
+      mbar_init(&tempty_bar[s], kEpiWarps);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
@@ -275,209 +490,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
   } else {
-    // ---------------------------------------------------------------- epilogue
-    const int q = warp & 3;       // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;  // row of the 128-row tile
-    int as = 0;
-    uint32_t aphase = 0;
-    int cur_ntile = -1;
-    for (int tile = first_item; tile < total_tiles; tile += item_stride) {
-      const int n_tile = tile % p.n_tiles;
-      int mt = (tile / p.n_tiles) * CS + rank;
-      const int w0 = (mt % p.tiles_w) * p.tw;
-      mt /= p.tiles_w;
-      const int h0 = (mt % p.tiles_h) * p.th;
-      const int b0 = (mt / p.tiles_h) * p.tn;
-      const int w = w0 + r % p.tw;
-      const int h = h0 + (r / p.tw) % p.th;
-      const int n = b0 + r / (p.tw * p.th);
-      const bool valid = (n < p.batch) && (h < p.out_h) && (w < p.out_w);
-      const long long off = n * p.out_sn + h * p.out_sh + w * p.out_sw + n_tile * BLOCK_N;
-
-      if ((p.stats != nullptr || p.bnb > 0) && cur_ntile != n_tile) {
-        // flush per-CTA channel sums when the channel block changes
-        // (named barrier over the 4 epilogue warps only)
-        if (cur_ntile >= 0) {
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          flush_channel_sums<BLOCK_N>(p, cur_ntile, s_sum, s_sq, s_x2, true);
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-        cur_ntile = n_tile;
-        if (p.bnb > 0) {
-          for (int i = threadIdx.x - 64; i < BLOCK_N; i += 128) {
-            const int ch = n_tile * BLOCK_N + i;
-            s_bn[i] = __ldg(p.bmean[0] + ch);
-            s_bn[BLOCK_N + i] = __ldg(p.brstd[0] + ch);
-            if (p.bnb > 1) {
-              s_bn[2 * BLOCK_N + i] = __ldg(p.bmean[1] + ch);
-              s_bn[3 * BLOCK_N + i] = __ldg(p.brstd[1] + ch);
-            }
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
-      }
-
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
-        // issue every global load of this chunk before waiting on anything, so the
-        // TMEM read and the (up to four) 64-byte row segments are all in flight together
-        const bool do_res = p.residual != nullptr && valid;
-        const bool do_bn = p.bnb > 0 && valid;
-        uint4 rres[4], rz[4], ry0[4], ry1[4];
-        if (do_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rres[j] = rp[j];  // plain load: residual may alias out
-        }
-        if (do_bn) {
-          const uint4* zp = reinterpret_cast<const uint4*>(p.bz + off + c * 32);
-          const uint4* yp = reinterpret_cast<const uint4*>(p.by[0] + off + c * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) rz[j] = __ldg(zp + j);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ry0[j] = __ldg(yp + j);
-          if (p.bnb > 1) {
-            const uint4* y1p = reinterpret_cast<const uint4*>(p.by[1] + off + c * 32);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ry1[j] = __ldg(y1p + j);
-          }
-        }
-        tmem_ld_wait();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        const int ch0 = n_tile * BLOCK_N + c * 32;
-        if (p.scale != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + j));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch0 + j));
-            f[j + 0] = fmaf(f[j + 0], sc.x, sh.x);
-            f[j + 1] = fmaf(f[j + 1], sc.y, sh.y);
-            f[j + 2] = fmaf(f[j + 2], sc.z, sh.z);
-            f[j + 3] = fmaf(f[j + 3], sc.w, sh.w);
-          }
-        }
-        if (do_res) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            f[8 * j + 0] += bf16_lo(rres[j].x);
-            f[8 * j + 1] += bf16_hi(rres[j].x);
-            f[8 * j + 2] += bf16_lo(rres[j].y);
-            f[8 * j + 3] += bf16_hi(rres[j].y);
-            f[8 * j + 4] += bf16_lo(rres[j].z);
-            f[8 * j + 5] += bf16_hi(rres[j].z);
-            f[8 * j + 6] += bf16_lo(rres[j].w);
-            f[8 * j + 7] += bf16_hi(rres[j].w);
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        if (do_bn) {  // g = dz * 1[z > 0]
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            f[8 * j + 0] = bf16_lo(rz[j].x) > 0.f ? f[8 * j + 0] : 0.f;
-            f[8 * j + 1] = bf16_hi(rz[j].x) > 0.f ? f[8 * j + 1] : 0.f;
-            f[8 * j + 2] = bf16_lo(rz[j].y) > 0.f ? f[8 * j + 2] : 0.f;
-            f[8 * j + 3] = bf16_hi(rz[j].y) > 0.f ? f[8 * j + 3] : 0.f;
-            f[8 * j + 4] = bf16_lo(rz[j].z) > 0.f ? f[8 * j + 4] : 0.f;
-            f[8 * j + 5] = bf16_hi(rz[j].z) > 0.f ? f[8 * j + 5] : 0.f;
-            f[8 * j + 6] = bf16_lo(rz[j].w) > 0.f ? f[8 * j + 6] : 0.f;
-            f[8 * j + 7] = bf16_hi(rz[j].w) > 0.f ? f[8 * j + 7] : 0.f;
-          }
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-        if (valid) {
-          uint4* op = reinterpret_cast<uint4*>(p.out + off + c * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            stg_v4(op + j, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
-        }
-        if (p.stats != nullptr) {
-          // statistics of the values as stored (bf16-rounded); invalid rows = 0
-          float s[32], s2[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = valid ? bf16_lo(pk[j]) : 0.f;
-            const float b = valid ? bf16_hi(pk[j]) : 0.f;
-            s[2 * j] = a;
-            s[2 * j + 1] = b;
-            s2[2 * j] = a * a;
-            s2[2 * j + 1] = b * b;
-          }
-          warp_colsum2(s, s2, lane);
-          red_shared_add(smem_u32(s_sum + c * 32 + lane), s[0]);
-          red_shared_add(smem_u32(s_sq + c * 32 + lane), s2[0]);
-        }
-        if (p.bnb > 0) {
-          // sum g and sum g*xhat of the stored (bf16-rounded) masked gradient
-          float g[32], gx[32];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            g[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
-            g[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
-          }
-          const uint32_t sbn = smem_u32(s_bn + c * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 m0 = __uint4_as_float4(lds_v4(sbn + 32 * j));
-            const float4 m1 = __uint4_as_float4(lds_v4(sbn + 32 * j + 16));
-            const float4 r0 = __uint4_as_float4(lds_v4(sbn + 4 * BLOCK_N + 32 * j));
-            const float4 r1 = __uint4_as_float4(lds_v4(sbn + 4 * BLOCK_N + 32 * j + 16));
-            gx[8 * j + 0] = do_bn ? g[8 * j + 0] * ((bf16_lo(ry0[j].x) - m0.x) * r0.x) : 0.f;
-            gx[8 * j + 1] = do_bn ? g[8 * j + 1] * ((bf16_hi(ry0[j].x) - m0.y) * r0.y) : 0.f;
-            gx[8 * j + 2] = do_bn ? g[8 * j + 2] * ((bf16_lo(ry0[j].y) - m0.z) * r0.z) : 0.f;
-            gx[8 * j + 3] = do_bn ? g[8 * j + 3] * ((bf16_hi(ry0[j].y) - m0.w) * r0.w) : 0.f;
-            gx[8 * j + 4] = do_bn ? g[8 * j + 4] * ((bf16_lo(ry0[j].z) - m1.x) * r1.x) : 0.f;
-            gx[8 * j + 5] = do_bn ? g[8 * j + 5] * ((bf16_hi(ry0[j].z) - m1.y) * r1.y) : 0.f;
-            gx[8 * j + 6] = do_bn ? g[8 * j + 6] * ((bf16_lo(ry0[j].w) - m1.z) * r1.z) : 0.f;
-            gx[8 * j + 7] = do_bn ? g[8 * j + 7] * ((bf16_hi(ry0[j].w) - m1.w) * r1.w) : 0.f;
-          }
-          if (p.bnb > 1) {
-            float gx1[32];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 m0 = __uint4_as_float4(lds_v4(sbn + 8 * BLOCK_N + 32 * j));
-              const float4 m1 = __uint4_as_float4(lds_v4(sbn + 8 * BLOCK_N + 32 * j + 16));
-              const float4 r0 = __uint4_as_float4(lds_v4(sbn + 12 * BLOCK_N + 32 * j));
-              const float4 r1 = __uint4_as_float4(lds_v4(sbn + 12 * BLOCK_N + 32 * j + 16));
-              gx1[8 * j + 0] = do_bn ? g[8 * j + 0] * ((bf16_lo(ry1[j].x) - m0.x) * r0.x) : 0.f;
-              gx1[8 * j + 1] = do_bn ? g[8 * j + 1] * ((bf16_hi(ry1[j].x) - m0.y) * r0.y) : 0.f;
-              gx1[8 * j + 2] = do_bn ? g[8 * j + 2] * ((bf16_lo(ry1[j].y) - m0.z) * r0.z) : 0.f;
-              gx1[8 * j + 3] = do_bn ? g[8 * j + 3] * ((bf16_hi(ry1[j].y) - m0.w) * r0.w) : 0.f;
-              gx1[8 * j + 4] = do_bn ? g[8 * j + 4] * ((bf16_lo(ry1[j].z) - m1.x) * r1.x) : 0.f;
-              gx1[8 * j + 5] = do_bn ? g[8 * j + 5] * ((bf16_hi(ry1[j].z) - m1.y) * r1.y) : 0.f;
-              gx1[8 * j + 6] = do_bn ? g[8 * j + 6] * ((bf16_lo(ry1[j].w) - m1.z) * r1.z) : 0.f;
-              gx1[8 * j + 7] = do_bn ? g[8 * j + 7] * ((bf16_hi(ry1[j].w) - m1.w) * r1.w) : 0.f;
-            }
-            warp_colsum1(gx1, lane);
-            red_shared_add(smem_u32(s_x2 + c * 32 + lane), gx1[0]);
-          }
-          warp_colsum2(g, gx, lane);
-          red_shared_add(smem_u32(s_sum + c * 32 + lane), g[0]);
-          red_shared_add(smem_u32(s_sq + c * 32 + lane), gx[0]);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) {
-        as = 0;
-        aphase ^= 1;
-      }
-    }
-    if ((p.stats != nullptr || p.bnb > 0) && cur_ntile >= 0) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      flush_channel_sums<BLOCK_N>(p, cur_ntile, s_sum, s_sq, s_x2, false);
-    }
+    conv_epilogue<BLOCK_N, CS>(p, tmem_base, tfull_bar, tempty_bar, s_sum, s_sq, s_x2, s_bn, rank,
+                               first_item, item_stride, total_tiles, warp, lane);
   }
 
   tc_fence_before();
@@ -487,6 +501,168 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+
+// ===========================================================================
+// K2h: 3x3 stride-1 convolution (forward or dgrad) with HALO REUSE.
+//
+// The generic kernel above fetches a separate 128-pixel A tile per tap, i.e. it pulls
+// every activation nine times through the L2->SM path, which is what bounds it
+// (~40 B/cycle/SM measured). Here a pixel tile is 8 wide x 16 high, and ONE TMA box
+// {64 ch, 10, 1, 18, 1} brings the tile plus its 1-pixel halo (180 rows of 128 B)
+// into shared memory. Each of the nine taps is then just a different UMMA
+// descriptor into that patch: start row (1+dy)*10 + (1+dx), 8-row groups 10 rows
+// (1280 B) apart - the tensor core's 128B-swizzle is a function of absolute
+// shared-memory address bits (probed in tests/diag_umma_probe.py), so any start
+// row / group stride that is a multiple of 128 B reads back exactly what TMA wrote.
+// The weights of the CTA's channel block (9 taps x CHUNKS x 64 x 64 bf16) are
+// loaded once and stay resident. L2->SM traffic per tile drops from
+// 9*CHUNKS*(16+8) KB to CHUNKS*22.5 KB.
+// ===========================================================================
+template <int CHUNKS>
+struct HaloCfg {
+  static constexpr int kBlockN = 64;
+  static constexpr int kPatchRows = 18 * 10;
+  static constexpr int kPatchBytes = kPatchRows * 128;               // 23040
+  static constexpr int kPatchSlot = (kPatchBytes + 1023) & ~1023;    // 23552
+  static constexpr int kWBytes = 9 * CHUNKS * kBlockN * 128;         // resident weights
+  static constexpr int kSlots = CHUNKS == 1 ? 5 : 3;                 // patch ring (per chunk)
+  static constexpr int kTmemCols = 2 * kBlockN;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = kWBytes + kSlots * kPatchSlot + kBarBytes + 7 * kBlockN * 4 + 1024;
+};
+
+template <int CHUNKS>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ ConvParams p) {
+  using Cfg = HaloCfg<CHUNKS>;
+  constexpr int BLOCK_N = Cfg::kBlockN;
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* s_w = smem;                         // [chunk][tap][64 cout][64 cin] bf16, swizzled
+  uint8_t* s_patch = smem + Cfg::kWBytes;      // kSlots x kPatchSlot
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_patch + Cfg::kSlots * Cfg::kPatchSlot);
+  uint64_t* empty_bar = full_bar + Cfg::kSlots;
+  uint64_t* tfull_bar = empty_bar + Cfg::kSlots;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* w_bar = tempty_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + Cfg::kBarBytes);
+  float* s_sq = s_sum + BLOCK_N;
+  float* s_x2 = s_sq + BLOCK_N;
+  float* s_bn = s_x2 + BLOCK_N;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kSlots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiWarps);
+    }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 3 * BLOCK_N; i += kConvThreads) s_sum[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int total_tiles = m_tiles * p.n_tiles;
+  // the channel block of a CTA is fixed (host: gridDim.x % n_tiles == 0)
+  const int my_ntile = blockIdx.x % p.n_tiles;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resident weights of this CTA's channel block: CHUNKS x 9 boxes {64 cin, 64 cout, 1}
+      mbar_expect_tx(w_bar, Cfg::kWBytes);
+      for (int kc = 0; kc < CHUNKS; ++kc)
+        for (int t = 0; t < 9; ++t)
+          tma_load_3d(s_w + (kc * 9 + t) * (BLOCK_N * 128), &tmB, w_bar, kc * 64,
+                      my_ntile * BLOCK_N, p.taps[t].btap);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt = tile / p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * p.tw;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * p.th;
+        const int b0 = mt / p.tiles_h;
+        for (int kc = 0; kc < CHUNKS; ++kc) {
+          mbar_wait(&empty_bar[slot], phase ^ 1);
+          mbar_expect_tx(&full_bar[slot], Cfg::kPatchBytes);
+          tma_load_5d(s_patch + slot * Cfg::kPatchSlot, &tmA, &full_bar[slot], kc * 64, w0 - 1, 0,
+                      h0 - 1, b0);
+          if (++slot == Cfg::kSlots) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      mbar_wait(w_bar, 0);
+      int slot = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kc = 0; kc < CHUNKS; ++kc) {
+          mbar_wait(&full_bar[slot], phase);
+          tc_fence_after();
+          const uint32_t patch = smem_u32(s_patch + slot * Cfg::kPatchSlot);
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            // tap (dy, dx): patch rows start at (1+dy)*10 + (1+dx); tile row h -> +10 rows
+            const int start_row = (1 + p.taps[t].d3) * 10 + (1 + p.taps[t].d1);
+            const uint64_t adesc = make_smem_desc(patch + start_row * 128, 16, 1280);
+            const uint64_t bdesc =
+                make_smem_desc(smem_u32(s_w + (kc * 9 + t) * (BLOCK_N * 128)), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | t | k) != 0);
+          }
+          umma_commit(&empty_bar[slot]);
+          if (++slot == Cfg::kSlots) {
+            slot = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, s_sum, s_sq, s_x2, s_bn, 0,
+                              blockIdx.x, gridDim.x, total_tiles, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
 
 // ===========================================================================
 // K2c: weight gradient, dW[tap][co][ci] += sum over pixels dY[p][co] * X[p+tap][ci]
@@ -528,7 +704,7 @@ struct WgradCfg {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const __grid_constant__ WgradParams p) {
   using Cfg = WgradCfg<BLOCK_N>;
