@@ -110,6 +110,48 @@ VPD_API int vpd_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, in
 VPD_API int vpd_stem_conv_wgrad(const void* x_stem, const void* dy, float* dw, int N, int H, int W,
                         void* stream);
 
+/* ---- BatchNorm / ReLU / pooling / head ops (NHWC bf16 activations) ----------------
+ * Replace torchvision BasicBlock's bn/relu/add, nn.MaxPool2d(3,2,1), the avgpool+fc
+ * head, FCNet and F.mse_loss(sum) with their autograd (models/rgb.py:68-70,
+ * models/module.py:133-156, train_vpd_model.py:87). Exposed for tests and reuse. */
+/* train-mode BN (+ optional residual, itself optionally batch-normalised) + ReLU.
+ * stats/res_stats: fp64 [2][C] per-channel (sum, sumsq) of y / res as produced by
+ * vpd_conv2d_fwd; running buffers are updated (momentum .1), save_* receive batch
+ * mean and 1/sqrt(var+eps). res_stats == NULL: residual added as is. */
+VPD_API int vpd_bn_act_fwd(const void* y, const void* res, void* z, int64_t M, int C, int relu,
+                   const double* stats, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, int64_t* num_batches,
+                   float* save_mean, float* save_rstd, const double* res_stats,
+                   const float* res_gamma, const float* res_beta, float* res_running_mean,
+                   float* res_running_var, int64_t* res_num_batches, float* res_save_mean,
+                   float* res_save_rstd, void* stream);
+/* gradient of the stage above: g = dz * 1[z > 0] (z may be NULL: no mask); dy = BN
+ * backward of g through (y, save_mean, save_rstd, gamma); optional second branch
+ * (y2...) fed by the same g; dmask (may alias dz) receives g; sums = fp64 [2][C]
+ * scratch per branch, zeroed by the caller. */
+VPD_API int vpd_bn_act_bwd(const void* dz, const void* z, void* dmask, int64_t M, int C,
+                   const void* y, void* dy, const float* gamma, const float* save_mean,
+                   const float* save_rstd, double* sums, float* dgamma, float* dbeta,
+                   const void* y2, void* dy2, const float* gamma2, const float* save_mean2,
+                   const float* save_rstd2, double* sums2, float* dgamma2, float* dbeta2,
+                   void* stream);
+/* stem: train-mode BN + ReLU + maxpool 3x3/2 pad 1 (argmax: uint8 window index) */
+VPD_API int vpd_stem_bn_pool_fwd(const void* y, void* z, uint8_t* argmax, int N, int H, int W, int C,
+                         const double* stats, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, int64_t* num_batches,
+                         float* save_mean, float* save_rstd, void* stream);
+VPD_API int vpd_stem_bn_pool_bwd(const void* dpool, const uint8_t* argmax, const void* y, void* dy,
+                         int N, int H, int W, int C, const float* gamma, const float* beta,
+                         const float* save_mean, const float* save_rstd, double* sums,
+                         float* dgamma, float* dbeta, void* stream);
+/* K4: avgpool -> fc -> [FCNet] -> sum-squared-error loss and backward. params/grads:
+ * fp32 arrays laid out [fc_w D*F][fc_b D][w0 Hd*D][b0 Hd][w2 Hd*Hd][b2 Hd][w5 T*Hd][b5 T]
+ * (decoder part only when motion != 0, Hd = 128). target NULL: forward only.
+ * ws: fp32 scratch of B*(F + 2D + 4*Hd + T). */
+VPD_API int vpd_head_fwd_bwd(const void* z, int B, int HW, int F, int D, int T, int motion,
+                     const float* params, const float* target, float* emb_out, float* out,
+                     double* loss_sum, void* dz, float* ws, float* grads, void* stream);
+
 /* ---- the student network ---------------------------------------------------------
  * Replaces RGBF_EmbeddingModel.forward/embed (models/rgb.py:68-86), the body of
  * ModelTrainer.epoch (train_vpd_model.py:67-98: forward, FCNet decoder,

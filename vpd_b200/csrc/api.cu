@@ -1,7 +1,11 @@
 // extern "C" surface declared in include/vpd_b200.h
 #include "../../include/vpd_b200.h"
 
+#include <string.h>
+
 #include "conv.h"
+#include "elementwise.cuh"
+#include "head.h"
 #include "net.h"
 #include "ops.h"
 
@@ -129,6 +133,132 @@ int vpd_stem_conv_wgrad(const void* x_stem, const void* dy, float* dw, int N, in
   WgradLaunch L;
   if (plan_stem_wgrad(&L, N, H, W, (const bf16*)x_stem, (const bf16*)dy, dw)) return -1;
   return launch_wgrad(L, (cudaStream_t)stream);
+}
+
+static BnLayer make_bn(const double* stats, const float* gamma, const float* beta, float* rm,
+                       float* rv, int64_t* nbt, float* sm, float* sr, long long count) {
+  BnLayer L;
+  L.stats = stats;
+  L.gamma = gamma;
+  L.beta = beta;
+  L.running_mean = rm;
+  L.running_var = rv;
+  L.num_batches = (long long*)nbt;
+  L.save_mean = sm;
+  L.save_rstd = sr;
+  L.count = (float)count;
+  L.inv_count = 1.0 / (double)count;
+  L.momentum = 0.1f;
+  L.eps = 1e-5f;
+  L.update_running = rm != nullptr ? 1 : 0;
+  return L;
+}
+
+int vpd_bn_act_fwd(const void* y, const void* res, void* z, int64_t M, int C, int relu,
+                   const double* stats, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, int64_t* num_batches,
+                   float* save_mean, float* save_rstd, const double* res_stats,
+                   const float* res_gamma, const float* res_beta, float* res_running_mean,
+                   float* res_running_var, int64_t* res_num_batches, float* res_save_mean,
+                   float* res_save_rstd, void* stream) {
+  BnApplyParams a;
+  memset(&a, 0, sizeof(a));
+  a.y = (const bf16*)y;
+  a.res = (const bf16*)res;
+  a.z = (bf16*)z;
+  a.M = M;
+  a.C = C;
+  a.relu = relu;
+  a.bn = make_bn(stats, gamma, beta, running_mean, running_var, num_batches, save_mean, save_rstd, M);
+  if (res_stats != nullptr) {
+    a.has_res_bn = 1;
+    a.res_bn = make_bn(res_stats, res_gamma, res_beta, res_running_mean, res_running_var,
+                       res_num_batches, res_save_mean, res_save_rstd, M);
+  }
+  return launch_bn_apply(a, (cudaStream_t)stream);
+}
+
+int vpd_bn_act_bwd(const void* dz, const void* z, void* dmask, int64_t M, int C,
+                   const void* y, void* dy, const float* gamma, const float* save_mean,
+                   const float* save_rstd, double* sums, float* dgamma, float* dbeta,
+                   const void* y2, void* dy2, const float* gamma2, const float* save_mean2,
+                   const float* save_rstd2, double* sums2, float* dgamma2, float* dbeta2,
+                   void* stream) {
+  BnBwdParams q;
+  memset(&q, 0, sizeof(q));
+  q.dz = (const bf16*)dz;
+  q.z = (const bf16*)z;
+  q.dmask = (bf16*)dmask;
+  q.M = M;
+  q.C = C;
+  q.nbranch = y2 != nullptr ? 2 : 1;
+  q.y[0] = (const bf16*)y; q.dy[0] = (bf16*)dy; q.gamma[0] = gamma; q.save_mean[0] = save_mean;
+  q.save_rstd[0] = save_rstd; q.sums[0] = sums; q.dgamma[0] = dgamma; q.dbeta[0] = dbeta;
+  q.y[1] = (const bf16*)y2; q.dy[1] = (bf16*)dy2; q.gamma[1] = gamma2; q.save_mean[1] = save_mean2;
+  q.save_rstd[1] = save_rstd2; q.sums[1] = sums2; q.dgamma[1] = dgamma2; q.dbeta[1] = dbeta2;
+  return launch_bn_bwd(q, (cudaStream_t)stream);
+}
+
+int vpd_stem_bn_pool_fwd(const void* y, void* z, uint8_t* argmax, int N, int H, int W, int C,
+                         const double* stats, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, int64_t* num_batches,
+                         float* save_mean, float* save_rstd, void* stream) {
+  PoolParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.y = (const bf16*)y;
+  pp.z = (bf16*)z;
+  pp.argmax = argmax;
+  pp.N = N; pp.H = H; pp.W = W; pp.C = C;
+  pp.bn = make_bn(stats, gamma, beta, running_mean, running_var, num_batches, save_mean, save_rstd,
+                  (long long)N * H * W);
+  return launch_bn_pool(pp, (cudaStream_t)stream);
+}
+
+int vpd_stem_bn_pool_bwd(const void* dpool, const uint8_t* argmax, const void* y, void* dy,
+                         int N, int H, int W, int C, const float* gamma, const float* beta,
+                         const float* save_mean, const float* save_rstd, double* sums,
+                         float* dgamma, float* dbeta, void* stream) {
+  StemBwdParams sp;
+  memset(&sp, 0, sizeof(sp));
+  sp.dpool = (const bf16*)dpool;
+  sp.argmax = argmax;
+  sp.y = (const bf16*)y;
+  sp.dy = (bf16*)dy;
+  sp.N = N; sp.H = H; sp.W = W; sp.C = C;
+  sp.gamma = gamma; sp.beta = beta; sp.save_mean = save_mean; sp.save_rstd = save_rstd;
+  sp.sums = sums; sp.dgamma = dgamma; sp.dbeta = dbeta;
+  return launch_stem_bwd(sp, (cudaStream_t)stream);
+}
+
+int vpd_head_fwd_bwd(const void* z, int B, int HW, int F, int D, int T, int motion,
+                     const float* params, const float* target, float* emb_out, float* out,
+                     double* loss_sum, void* dz, float* ws, float* grads, void* stream) {
+  const int Hd = 128;
+  HeadParams h;
+  memset(&h, 0, sizeof(h));
+  h.z = (const bf16*)z;
+  h.B = B; h.HW = HW; h.F = F; h.D = D; h.T = T; h.Hd = Hd; h.motion = motion;
+  const float* p = params;
+  float* g = grads;
+  HeadGrads hg;
+  memset(&hg, 0, sizeof(hg));
+  h.fc_w = p; p += (size_t)D * F; h.fc_b = p; p += D;
+  if (g) { hg.fc_w = g; g += (size_t)D * F; hg.fc_b = g; g += D; }
+  if (motion) {
+    h.w0 = p; p += Hd * D; h.b0 = p; p += Hd; h.w2 = p; p += Hd * Hd; h.b2 = p; p += Hd;
+    h.w5 = p; p += T * Hd; h.b5 = p;
+    if (g) {
+      hg.w0 = g; g += Hd * D; hg.b0 = g; g += Hd; hg.w2 = g; g += Hd * Hd; hg.b2 = g; g += Hd;
+      hg.w5 = g; g += T * Hd; hg.b5 = g;
+    }
+  }
+  h.target = target;
+  h.emb_out = emb_out;
+  h.out = out;
+  h.loss = loss_sum;
+  h.dz = (bf16*)dz;
+  h.ws = ws;
+  return launch_head(h, grads ? &hg : nullptr, (cudaStream_t)stream);
 }
 
 vpd_net* vpd_net_create(const char* arch, int emb_dim, int in_channels, int H, int W,
