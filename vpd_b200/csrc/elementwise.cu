@@ -62,7 +62,8 @@ VPD_DEVINL void bn_side_effects(const BnLayer& bn, int C) {
 }
 
 // ------------------------------------------------------------------ BN apply
-__global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParams p) {
+template <int RES>  // 0: no residual, 1: plain residual, 2: residual through its own BN
+__global__ void __launch_bounds__(kEwThreads, RES == 0 ? 4 : 3) bn_apply_kernel(const BnApplyParams p) {
   pdl_trigger();
   pdl_wait();
   const int groups = p.C >> 3;
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParam
     bn_affine(p.bn.gamma[c], p.bn.beta[c], mean, rstd, sc[j], sh[j]);
     rsc[j] = 1.f;
     rsh[j] = 0.f;
-    if (p.has_res_bn) {
+    if (RES == 2) {
       bn_mean_rstd(p.res_bn, c, p.C, mean, rstd, var);
       bn_affine(p.res_bn.gamma[c], p.res_bn.beta[c], mean, rstd, rsc[j], rsh[j]);
     }
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParam
       if (r < end) {
         const size_t off = (size_t)r * p.C + g * 8;
         vy[u] = ldg_nc_v4(p.y + off);
-        if (p.res != nullptr) vr[u] = ldg_nc_v4(p.res + off);
+        if (RES != 0) vr[u] = ldg_nc_v4(p.res + off);
       }
     }
 #pragma unroll
@@ -107,11 +108,11 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParam
       unpack8(vy[u], f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-      if (p.res != nullptr) {
+      if (RES != 0) {
         float rr[8];
         unpack8(vr[u], rr);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += fmaf(rr[j], rsc[j], rsh[j]);
+        for (int j = 0; j < 8; ++j) f[j] += RES == 2 ? fmaf(rr[j], rsc[j], rsh[j]) : rr[j];
       }
       if (p.relu) {
 #pragma unroll
@@ -125,14 +126,16 @@ __global__ void __launch_bounds__(kEwThreads) bn_apply_kernel(const BnApplyParam
   // (stats) are never modified here, so no ordering issue.
   if (blockIdx.x == 0) {
     bn_side_effects(p.bn, p.C);
-    if (p.has_res_bn) bn_side_effects(p.res_bn, p.C);
+    if (RES == 2) bn_side_effects(p.res_bn, p.C);
   }
 }
 
-// `per_thread` vectors per thread at most `cap_per_sm` resident blocks' worth of CTAs
-static int ew_grid(long long vectors, int per_thread = 4, int cap_per_sm = 8) {
+// One wave at most: `per_thread` vectors per thread, never more CTAs than
+// `blocks_per_sm` (the kernel's real residency) x SMs - these kernels are latency
+// bound on small tensors, so a second wave costs a full prologue + memory round trip.
+static int ew_grid(long long vectors, int per_thread, int blocks_per_sm) {
   long long blocks = (vectors + (long long)kEwThreads * per_thread - 1) / (kEwThreads * per_thread);
-  const long long cap = 148LL * cap_per_sm;
+  const long long cap = 148LL * blocks_per_sm;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -142,7 +145,13 @@ int launch_bn_apply(const BnApplyParams& p, cudaStream_t s) {
   VPD_REQUIRE(p.C % 64 == 0 && p.C <= 2048 && kEwThreads % (p.C / 8) == 0,
               "bn_apply: unsupported channel count %d", p.C);
   if (p.M == 0) return 0;
-  VPD_CHECK_CUDA(launch_kernel(bn_apply_kernel, dim3(ew_grid(p.M * (p.C / 8), 4, 8)), dim3(kEwThreads), 0, s, p));
+  const long long vectors = p.M * (p.C / 8);
+  if (p.res == nullptr)
+    VPD_CHECK_CUDA(launch_kernel(bn_apply_kernel<0>, dim3(ew_grid(vectors, 4, 4)), dim3(kEwThreads), 0, s, p));
+  else if (!p.has_res_bn)
+    VPD_CHECK_CUDA(launch_kernel(bn_apply_kernel<1>, dim3(ew_grid(vectors, 4, 3)), dim3(kEwThreads), 0, s, p));
+  else
+    VPD_CHECK_CUDA(launch_kernel(bn_apply_kernel<2>, dim3(ew_grid(vectors, 4, 3)), dim3(kEwThreads), 0, s, p));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -224,7 +233,7 @@ int launch_bn_pool(const PoolParams& p, cudaStream_t s) {
   if (p.N == 0) return 0;
   const long long total = (long long)p.N * (p.H / 2) * (p.W / 2) * (p.C / 8);
   long long blocks = (total + kEwThreads - 1) / kEwThreads;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 2) blocks = 148 * 2;  // one resident wave (97 registers/thread)
   VPD_CHECK_CUDA(launch_kernel(bn_pool_kernel, dim3((int)blocks), dim3(kEwThreads), 0, s, p));
   VPD_LAUNCHED(1);
   return 0;
@@ -303,7 +312,7 @@ int launch_bn_fold(const float* gamma, const float* beta, const float* rm, const
 //          masked gradient written back for the identity branch, dgamma/dbeta.
 // Four rows per thread are loaded before any is used (memory-level parallelism).
 template <bool kApply, int NB>
-__global__ void __launch_bounds__(kEwThreads) bn_bwd_kernel(const BnBwdParams p) {
+__global__ void __launch_bounds__(kEwThreads, NB == 1 ? 3 : 2) bn_bwd_kernel(const BnBwdParams p) {
   pdl_trigger();
   pdl_wait();
   __shared__ float s_g[512];
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_bwd_kernel(const BnBwdParams p)
   const long long chunk = (p.M + gridDim.x - 1) / gridDim.x;
   const long long beg = (long long)blockIdx.x * chunk;
   const long long end = beg + chunk < p.M ? beg + chunk : p.M;
-  constexpr int U = NB == 1 ? 4 : 2;
+  constexpr int U = 2;
   for (long long row = beg + r0; row < end; row += (long long)rstep * U) {
     uint4 vd[U], vz[U], vy[NB][U];
 #pragma unroll
@@ -431,8 +440,9 @@ int launch_bn_bwd(const BnBwdParams& p, cudaStream_t s) {
   VPD_REQUIRE(p.nbranch == 1 || p.nbranch == 2, "bn_bwd: nbranch");
   if (p.M == 0) return 0;
   const long long vectors = p.M * (p.C / 8);
-  const int grid_r = ew_grid(vectors, 4, 4);   // fewer blocks: every block ends in atomics
-  const int grid_a = ew_grid(vectors, 4, 8);
+  const int occ = p.nbranch == 1 ? 3 : 2;
+  const int grid_r = ew_grid(vectors, 2, occ);
+  const int grid_a = ew_grid(vectors, 2, occ);
   if (p.nbranch == 1) {
     if (!p.sums_ready)
       VPD_CHECK_CUDA(launch_kernel(bn_bwd_kernel<false, 1>, dim3(grid_r), dim3(kEwThreads), 0, s, p));
@@ -618,8 +628,8 @@ int launch_stem_bwd(const StemBwdParams& p, cudaStream_t s) {
   VPD_REQUIRE(p.C % 64 == 0 && p.C <= 512 && kEwThreads % (p.C / 8) == 0, "stem_bwd: C=%d", p.C);
   if (p.N == 0) return 0;
   const long long pooled = (long long)p.N * (p.H / 2) * (p.W / 2) * (p.C / 8);
-  VPD_CHECK_CUDA(launch_kernel(stem_bwd_reduce_kernel, dim3(ew_grid(pooled, 2, 4)), dim3(kEwThreads), 0, s, p));
-  VPD_CHECK_CUDA(launch_kernel(stem_bwd_apply_kernel, dim3(ew_grid(pooled * 4, 2, 8)), dim3(kEwThreads), 0, s, p));
+  VPD_CHECK_CUDA(launch_kernel(stem_bwd_reduce_kernel, dim3(ew_grid(pooled, 2, 2)), dim3(kEwThreads), 0, s, p));
+  VPD_CHECK_CUDA(launch_kernel(stem_bwd_apply_kernel, dim3(ew_grid(pooled * 4, 2, 2)), dim3(kEwThreads), 0, s, p));
   VPD_LAUNCHED(2);
   return 0;
 }
