@@ -252,7 +252,7 @@ int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
     return -1;
   p.out_img = out_img;
   p.out_tgt = out_tgt;
-  p.rows_per_cta = H < 8 ? H : 8;
+  p.rows_per_cta = H < 32 ? H : 32;
   const int smem = smem_for(p, p.rows_per_cta);
   VPD_REQUIRE(smem <= 200 * 1024, "assemble: image too wide (W=%d)", W);
   if (smem > 48 * 1024)
@@ -277,7 +277,7 @@ int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
     return -1;
   p.out_pad = out_pad;
   p.out_tgt = out_tgt;
-  p.rows_per_cta = 8;
+  p.rows_per_cta = 32;
   const int smem = smem_for(p, p.rows_per_cta);
   VPD_REQUIRE(smem <= 200 * 1024, "assemble: image too wide (W=%d)", W);
   if (smem > 48 * 1024)

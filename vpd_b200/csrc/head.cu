@@ -50,24 +50,27 @@ __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) 
   __syncthreads();
   if (p.emb_out != nullptr)
     for (int d = tid; d < p.D; d += kHeadThreads) p.emb_out[(size_t)b * p.D + d] = e[d];
-  // 3. decoder
+  // 3. decoder: one warp per output row, lanes stride the input (coalesced weight reads)
   if (p.motion) {
-    for (int j = tid; j < p.Hd; j += kHeadThreads) {
-      float s = p.b0[j];
-      for (int i = 0; i < p.D; ++i) s = fmaf(p.w0[j * p.D + i], e[i], s);
-      h1[j] = fmaxf(s, 0.f);
+    for (int j = warp; j < p.Hd; j += kHeadThreads / 32) {
+      float s = 0.f;
+      for (int i = lane; i < p.D; i += 32) s = fmaf(p.w0[j * p.D + i], e[i], s);
+      s = warp_sum(s);
+      if (lane == 0) h1[j] = fmaxf(s + p.b0[j], 0.f);
     }
     __syncthreads();
-    for (int j = tid; j < p.Hd; j += kHeadThreads) {
-      float s = p.b2[j];
-      for (int i = 0; i < p.Hd; ++i) s = fmaf(p.w2[j * p.Hd + i], h1[i], s);
-      h2[j] = fmaxf(s, 0.f);
+    for (int j = warp; j < p.Hd; j += kHeadThreads / 32) {
+      float s = 0.f;
+      for (int i = lane; i < p.Hd; i += 32) s = fmaf(p.w2[j * p.Hd + i], h1[i], s);
+      s = warp_sum(s);
+      if (lane == 0) h2[j] = fmaxf(s + p.b2[j], 0.f);
     }
     __syncthreads();
-    for (int t = tid; t < p.T; t += kHeadThreads) {
-      float s = p.b5[t];
-      for (int i = 0; i < p.Hd; ++i) s = fmaf(p.w5[t * p.Hd + i], h2[i], s);
-      o[t] = s;
+    for (int t = warp; t < p.T; t += kHeadThreads / 32) {
+      float s = 0.f;
+      for (int i = lane; i < p.Hd; i += 32) s = fmaf(p.w5[t * p.Hd + i], h2[i], s);
+      s = warp_sum(s);
+      if (lane == 0) o[t] = s + p.b5[t];
     }
   } else {
     for (int t = tid; t < p.T; t += kHeadThreads) o[t] = e[t];
@@ -159,27 +162,40 @@ struct OuterParams {
   int stride;  // floats between consecutive frames in the workspace
 };
 
+// 8 lanes per weight element, each summing every 8th frame, then a 3-step shuffle
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const OuterParams p) {
   pdl_trigger();
   pdl_wait();
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  int seg = -1, o = 0, i = 0;
   for (int s = 0; s < p.nseg; ++s) {
-    const OuterSeg& g = p.seg[s];
-    const int n = g.O * (g.I + 1);  // +1 column for the bias
+    const int n = p.seg[s].O * (p.seg[s].I + 1);  // +1 column for the bias
     if (idx < n) {
-      const int o = idx / (g.I + 1), i = idx % (g.I + 1);
-      float acc = 0.f;
-      if (i < g.I) {
-        for (int b = 0; b < p.B; ++b)
-          acc = fmaf(g.dout[(size_t)b * p.stride + o], g.in[(size_t)b * p.stride + i], acc);
-        g.dW[(size_t)o * g.I + i] = acc;
-      } else {
-        for (int b = 0; b < p.B; ++b) acc += g.dout[(size_t)b * p.stride + o];
-        g.db[o] = acc;
-      }
-      return;
+      seg = s;
+      o = idx / (p.seg[s].I + 1);
+      i = idx % (p.seg[s].I + 1);
+      break;
     }
     idx -= n;
+  }
+  float acc = 0.f;
+  if (seg >= 0) {
+    const OuterSeg& g = p.seg[seg];
+    if (i < g.I) {
+      for (int b = sub; b < p.B; b += 8)
+        acc = fmaf(g.dout[(size_t)b * p.stride + o], g.in[(size_t)b * p.stride + i], acc);
+    } else {
+      for (int b = sub; b < p.B; b += 8) acc += g.dout[(size_t)b * p.stride + o];
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);  // all 32 lanes take part
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (seg >= 0 && sub == 0) {
+    const OuterSeg& g = p.seg[seg];
+    if (i < g.I) g.dW[(size_t)o * g.I + i] = acc;
+    else g.db[o] = acc;
   }
 }
 
@@ -213,7 +229,7 @@ int launch_head(const HeadParams& p, const HeadGrads* grads, cudaStream_t stream
   }
   op.nseg = n;
   for (int i = 0; i < n; ++i) total += op.seg[i].O * (op.seg[i].I + 1);
-  VPD_CHECK_CUDA(launch_kernel(head_wgrad_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, op));
+  VPD_CHECK_CUDA(launch_kernel(head_wgrad_kernel, dim3((total * 8 + 255) / 256), dim3(256), 0, stream, op));
   VPD_LAUNCHED(1);
   return 0;
 }

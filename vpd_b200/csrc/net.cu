@@ -291,7 +291,17 @@ Net* net_create(const char* arch, int emb_dim, int in_channels, int H, int W, in
   }
 
   // ---- workspace carve (offsets only; pointers are fixed up in bind)
-  // transposed-mirror table: one entry per 32x32 tile of every (conv, tap)
+  // weight-mirror table: one entry per 32x32 tile of every (conv, tap); the stem's
+  // packed [7][64][64] weights are 7 "taps" of a 64x64 matrix
+  for (int t = 0; t < 7; ++t)
+    for (int r = 0; r < 2; ++r)
+      for (int q = 0; q < 2; ++q) {
+        n->tr_table_host.push_back((int)(n->stem.w_off + (long long)t * 64 * 64));
+        n->tr_table_host.push_back(64);
+        n->tr_table_host.push_back(64);
+        n->tr_table_host.push_back(r);
+        n->tr_table_host.push_back(q);
+      }
   for (auto& bd : n->blocks) {
     const ConvDesc* cs[3] = {&bd.c1, &bd.c2, bd.has_ds ? &bd.ds : nullptr};
     for (const ConvDesc* c : cs) {
@@ -414,10 +424,12 @@ __global__ void cast_weights_kernel(const float* __restrict__ w, bf16* __restric
   }
 }
 
-// wT[tap][ci][co] = bf16(w[tap][co][ci]); one 32x32 tile per block, table-driven
+// One pass over the fp32 master weights writes both bf16 mirrors: w_tap (same layout,
+// forward / wgrad-free operand) and wT[tap][ci][co] = w[tap][co][ci] (dgrad operand).
+// One 32x32 tile per block, table-driven.
 __global__ void __launch_bounds__(256)
-transpose_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wT,
-                         const int* __restrict__ table) {
+mirror_weights_kernel(const float* __restrict__ w, bf16* __restrict__ w_tap, bf16* __restrict__ wT,
+                      const int* __restrict__ table) {
   pdl_trigger();
   pdl_wait();
   __shared__ float tile[32][33];
@@ -425,7 +437,12 @@ transpose_weights_kernel(const float* __restrict__ w, bf16* __restrict__ wT,
   const long long base = e[0];
   const int rows = e[1], cols = e[2], tr = e[3] * 32, tc = e[4] * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) tile[r][tx] = w[base + (long long)(tr + r) * cols + tc + tx];
+  for (int r = ty; r < 32; r += 8) {
+    const long long idx = base + (long long)(tr + r) * cols + tc + tx;
+    const float v = w[idx];
+    tile[r][tx] = v;
+    w_tap[idx] = __float2bfloat16_rn(v);
+  }
   __syncthreads();
   for (int r = ty; r < 32; r += 8)
     wT[base + (long long)(tc + r) * rows + tr + tx] = __float2bfloat16_rn(tile[tx][r]);
@@ -437,12 +454,9 @@ static int pack_weights(Net* n, cudaStream_t s) {
                                    n->tr_table_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
     n->tr_uploaded = true;
   }
-  const long long n4 = (n->secA_len + 3) / 4;
-  VPD_CHECK_CUDA(launch_kernel(cast_weights_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, s, n->params + n->secA, n->w_tap,
-                                                                  n->secA_len));
-  VPD_CHECK_CUDA(launch_kernel(transpose_weights_kernel, dim3(n->tr_blocks), dim3(256), 0, s, n->params + n->secA, n->wT_tap,
-                                                        n->tr_table_dev));
-  VPD_LAUNCHED(2);
+  VPD_CHECK_CUDA(launch_kernel(mirror_weights_kernel, dim3(n->tr_blocks), dim3(256), 0, s,
+                               n->params + n->secA, n->w_tap, n->wT_tap, n->tr_table_dev));
+  VPD_LAUNCHED(1);
   n->params_dirty = false;
   return 0;
 }
