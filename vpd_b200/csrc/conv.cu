@@ -113,11 +113,13 @@ static bool try_halo(ConvLaunch* L, const __nv_bfloat16* x, const __nv_bfloat16*
   static const int enable = env_int("VPD_HALO", 1);
   if (g_plan_no_halo) return false;
   const int chunks = cin_k / 64;
-  if (!enable || (chunks != 1 && chunks != 2) || cin_k % 64 != 0 || cout_k % 64 != 0) return false;
+  if (!enable || cin_k % 64 != 0 || cout_k % 64 != 0) return false;
   if (H % 16 != 0 || W % 8 != 0) return false;
-  // 128-channel layers: resident weights force 64-wide channel blocks, which measured
-  // no faster than the generic 128-wide tiles -> opt-in
-  if (chunks == 2 && !env_int("VPD_HALO2", 0)) return false;
+  // 64 -> 64 layers keep their 72 KB of weights resident; wider layers stream the
+  // (chunk, tap) weight tiles through a TMA ring with 128-wide channel blocks
+  static const int stream_on = env_int("VPD_HALO_STREAM", 0);  // correct but measured neutral: opt-in
+  const bool resident = chunks == 1 && cout_k == 64;
+  if (!resident && !(stream_on && cout_k % 128 == 0 && chunks <= 8)) return false;
   ConvParams& p = L->p;
   p.tw = 8;
   p.th = 16;
@@ -128,11 +130,12 @@ static bool try_halo(ConvLaunch* L, const __nv_bfloat16* x, const __nv_bfloat16*
   p.batch = N;
   p.out_h = H;
   p.out_w = W;
-  L->block_n = 64;
+  L->block_n = resident ? 64 : 128;
   L->cluster = 1;
-  L->halo = chunks;
-  p.n_tiles = cout_k / 64;
+  L->halo = resident ? 1 : 3;   // 1: resident-weight kernel, 3: streamed weights
+  p.n_tiles = cout_k / L->block_n;
   p.cout = cout_k;
+  for (int t = 0; t < 9; ++t) p.taps[t].kchunks = chunks;
   const int total = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
   int grid = device_sm_count();
   if (grid > total) grid = total;
@@ -145,7 +148,7 @@ static bool try_halo(ConvLaunch* L, const __nv_bfloat16* x, const __nv_bfloat16*
                      (uint64_t)H * W * cin_k * 2};
   uint32_t box[5] = {64, 10, 1, 18, 1};
   if (encode_tmap_bf16(&L->a0, x, 5, dims, str, box, true)) return false;
-  if (weight_map(&L->b0, wt, 9, cout_k, cin_k, 64)) return false;
+  if (weight_map(&L->b0, wt, 9, cout_k, cin_k, L->block_n)) return false;
   L->a1 = L->a0;
   L->b1 = L->b0;
   return true;
@@ -394,7 +397,19 @@ static int launch_halo(const ConvLaunch& L, cudaStream_t stream) {
 int launch_conv(const ConvLaunch& L, cudaStream_t stream) {
   if (L.grid <= 0) return 0;
   if (L.halo == 1) return launch_halo<1>(L, stream);
-  if (L.halo == 2) return launch_halo<2>(L, stream);
+  if (L.halo == 3) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VPD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_stream_kernel<128>,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          HaloStreamCfg<128>::kSmemBytes));
+      attr_set = true;
+    }
+    VPD_CHECK_CUDA(launch_kernel(conv3x3_halo_stream_kernel<128>, dim3(L.grid), dim3(kConvThreads),
+                                 HaloStreamCfg<128>::kSmemBytes, stream, L.a0, L.b0, L.p));
+    VPD_LAUNCHED(1);
+    return 0;
+  }
   if (L.cluster == 2) {
     switch (L.block_n) {
       case 64: return launch_bn<64, 2>(L, stream);

@@ -664,6 +664,169 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+// ---------------------------------------------------------------------------
+// Halo-reuse variant with STREAMED weights (channel blocks too large to keep
+// resident, e.g. 128 -> 128): one patch per 64-channel chunk as above, and the
+// (chunk, tap) weight tiles [BLOCK_N][64] flow through their own TMA ring.
+// ---------------------------------------------------------------------------
+template <int BLOCK_N>
+struct HaloStreamCfg {
+  static constexpr int kPatchBytes = 18 * 10 * 128;
+  static constexpr int kPatchSlot = (kPatchBytes + 1023) & ~1023;
+  static constexpr int kSlots = 3;
+  static constexpr int kWTile = BLOCK_N * 128;
+  static constexpr int kWStages = 5;
+  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes =
+      kWStages * kWTile + kSlots * kPatchSlot + kBarBytes + 7 * BLOCK_N * 4 + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
+                           const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ ConvParams p) {
+  using Cfg = HaloStreamCfg<BLOCK_N>;
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* s_w = smem;                                   // kWStages x [BLOCK_N][64]
+  uint8_t* s_patch = smem + Cfg::kWStages * Cfg::kWTile;  // kSlots x kPatchSlot
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(s_patch + Cfg::kSlots * Cfg::kPatchSlot);
+  uint64_t* pempty = pfull + Cfg::kSlots;
+  uint64_t* wfull = pempty + Cfg::kSlots;
+  uint64_t* wempty = wfull + Cfg::kWStages;
+  uint64_t* tfull_bar = wempty + Cfg::kWStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(pfull) + Cfg::kBarBytes);
+  float* s_sq = s_sum + BLOCK_N;
+  float* s_x2 = s_sq + BLOCK_N;
+  float* s_bn = s_x2 + BLOCK_N;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kSlots; ++s) {
+      mbar_init(&pfull[s], 1);
+      mbar_init(&pempty[s], 1);
+    }
+    for (int s = 0; s < Cfg::kWStages; ++s) {
+      mbar_init(&wfull[s], 1);
+      mbar_init(&wempty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiWarps);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 3 * BLOCK_N; i += kConvThreads) s_sum[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int chunks = p.taps[0].kchunks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int slot = 0, ws = 0;
+      uint32_t pphase = 0, wphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int mt = tile / p.n_tiles;
+        const int w0 = (mt % p.tiles_w) * p.tw;
+        mt /= p.tiles_w;
+        const int h0 = (mt % p.tiles_h) * p.th;
+        const int b0 = mt / p.tiles_h;
+        for (int kc = 0; kc < chunks; ++kc) {
+          mbar_wait(&pempty[slot], pphase ^ 1);
+          mbar_expect_tx(&pfull[slot], Cfg::kPatchBytes);
+          tma_load_5d(s_patch + slot * Cfg::kPatchSlot, &tmA, &pfull[slot], kc * 64, w0 - 1, 0,
+                      h0 - 1, b0);
+          if (++slot == Cfg::kSlots) {
+            slot = 0;
+            pphase ^= 1;
+          }
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&wempty[ws], wphase ^ 1);
+            mbar_expect_tx(&wfull[ws], Cfg::kWTile);
+            tma_load_3d(s_w + ws * Cfg::kWTile, &tmB, &wfull[ws], kc * 64, n_tile * BLOCK_N,
+                        p.taps[t].btap);
+            if (++ws == Cfg::kWStages) {
+              ws = 0;
+              wphase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int slot = 0, ws = 0;
+      uint32_t pphase = 0, wphase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kc = 0; kc < chunks; ++kc) {
+          mbar_wait(&pfull[slot], pphase);
+          tc_fence_after();
+          const uint32_t patch = smem_u32(s_patch + slot * Cfg::kPatchSlot);
+#pragma unroll 1
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(&wfull[ws], wphase);
+            tc_fence_after();
+            const int start_row = (1 + p.taps[t].d3) * 10 + (1 + p.taps[t].d1);
+            const uint64_t adesc = make_smem_desc(patch + start_row * 128, 16, 1280);
+            const uint64_t bdesc = make_smem_desc(smem_u32(s_w + ws * Cfg::kWTile), 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k)
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | t | k) != 0);
+            umma_commit(&wempty[ws]);
+            if (++ws == Cfg::kWStages) {
+              ws = 0;
+              wphase ^= 1;
+            }
+          }
+          umma_commit(&pempty[slot]);
+          if (++slot == Cfg::kSlots) {
+            slot = 0;
+            pphase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, s_sum, s_sq, s_x2, s_bn, 0,
+                              blockIdx.x, gridDim.x, total_tiles, warp, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
 // ===========================================================================
 // K2c: weight gradient, dW[tap][co][ci] += sum over pixels dY[p][co] * X[p+tap][ci]
 //

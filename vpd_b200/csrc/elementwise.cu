@@ -305,6 +305,70 @@ int launch_bn_fold(const float* gamma, const float* beta, const float* rm, const
   return 0;
 }
 
+// ------------------------------------------------- standalone channel statistics
+// sum / sum-of-squares per channel of a [M][C] bf16 tensor (fp64 atomics at the end).
+// Used for the 64-channel layers, whose conv epilogue is the bottleneck: moving the
+// reduction out of it is cheaper than the extra (L2-resident) read.
+__global__ void __launch_bounds__(kEwThreads, 4)
+channel_stats_kernel(const __nv_bfloat16* __restrict__ y, long long M, int C, double* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float s_a[512];
+  __shared__ float s_b[512];
+  const int groups = C >> 3;
+  const int g = threadIdx.x % groups;
+  const int r0 = threadIdx.x / groups;
+  const int rstep = kEwThreads / groups;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  const long long chunk = (M + gridDim.x - 1) / gridDim.x;
+  const long long beg = (long long)blockIdx.x * chunk;
+  const long long end = beg + chunk < M ? beg + chunk : M;
+  constexpr int U = 4;
+  for (long long row = beg + r0; row < end; row += (long long)rstep * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = row + (long long)u * rstep;
+      if (r < end) v[u] = ldg_nc_v4(y + (size_t)r * C + g * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = row + (long long)u * rstep;
+      if (r >= end) break;
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] += f[j];
+        b[j] = fmaf(f[j], f[j], b[j]);
+      }
+    }
+  }
+  for (int c = threadIdx.x; c < C; c += kEwThreads) s_a[c] = s_b[c] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&s_a[g * 8 + j], a[j]);
+    atomicAdd(&s_b[g * 8 + j], b[j]);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kEwThreads) {
+    atomicAdd(&stats[c], static_cast<double>(s_a[c]));
+    atomicAdd(&stats[C + c], static_cast<double>(s_b[c]));
+  }
+}
+
+int launch_channel_stats(const __nv_bfloat16* y, long long M, int C, double* stats, cudaStream_t s) {
+  VPD_REQUIRE(C % 64 == 0 && C <= 512 && kEwThreads % (C / 8) == 0, "channel_stats: C=%d", C);
+  if (M == 0) return 0;
+  VPD_CHECK_CUDA(launch_kernel(channel_stats_kernel, dim3(ew_grid(M * (C / 8), 4, 4)),
+                               dim3(kEwThreads), 0, s, y, M, C, stats));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
 // --------------------------------------------------------------- BN backward
 // pass 1 (kApply = false): per-channel sum(g), sum(g * xhat_b), g = dz * 1[z > 0]
 // pass 2 (kApply = true) : dy_b = A_b*g + B_b*y_b + C_b  (the usual

@@ -81,6 +81,7 @@ struct StemBwdParams {       // maxpool + ReLU + BN backward of the stem
 };
 
 int launch_bn_apply(const BnApplyParams& p, cudaStream_t s);
+int launch_channel_stats(const __nv_bfloat16* y, long long M, int C, double* stats, cudaStream_t s);
 int launch_bn_pool(const PoolParams& p, cudaStream_t s);
 int launch_bn_bwd(const BnBwdParams& p, cudaStream_t s);    // reduce + apply
 int launch_stem_bwd(const StemBwdParams& p, cudaStream_t s);

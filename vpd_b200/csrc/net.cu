@@ -70,6 +70,7 @@ struct Plan {  // everything that depends on the batch size
   std::vector<WgradLaunch> wg1, wg2, wgds;
   WgradLaunch wg_stem;
   bool fused = false;  // BN-backward reductions folded into the dgrad epilogues
+  bool split_stats = false;  // 64-channel layers: BN statistics by a separate kernel
 };
 
 // Optional per-launch timing (CUDA events around every kernel of a step),
@@ -503,9 +504,15 @@ static Plan* get_plan(Net* n, int B) {
     e.relu = relu;
     return e;
   };
+  // 64-channel layers are epilogue-bound: their statistics come from a separate pass
+  // (measured: not a win - those epilogues are bound by their row-per-thread global
+  // accesses, not by the reduction - so this is opt-in)
+  static const bool split_stats = getenv("VPD_SPLIT_STATS") != nullptr &&
+                                  getenv("VPD_SPLIT_STATS")[0] == '1';
+  P->split_stats = split_stats;
   auto tr = [&](const BnDesc& b) {
     ConvEpilogue e;
-    e.stats = n->stats + 2 * b.ch_off;
+    if (!(split_stats && b.C == 64)) e.stats = n->stats + 2 * b.ch_off;
     return e;
   };
   const bf16* wt = n->w_tap;
@@ -712,6 +719,9 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
 
   // ------------------------------------------------------------------ forward
   PROF(kConvFwd, 0, launch_conv(P->stem_train, s));
+  if (P->split_stats)
+    PROF(kEwFwd, 0, launch_channel_stats(n->y_stem, (long long)B * (n->H / 2) * (n->W / 2), 64,
+                                         n->stats + 2 * n->stem_bn.ch_off, s));
   {
     PoolParams pp;
     pp.y = n->y_stem;
@@ -729,6 +739,9 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     BlockDesc& bd = n->blocks[i];
     const long long M = (long long)B * bd.c2.Hin * bd.c2.Win;
     PROF(kConvFwd, bd.stage, launch_conv(P->c1_train[i], s));
+    const bool split = P->split_stats && bd.c1.Cout == 64;
+    if (split)
+      PROF(kEwFwd, bd.stage, launch_channel_stats(bd.y1, M, 64, n->stats + 2 * bd.b1.ch_off, s));
     BnApplyParams a;
     memset(&a, 0, sizeof(a));
     a.y = bd.y1;
@@ -739,6 +752,8 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     a.bn = bn_layer(n, bd.b1, true, M);
     PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
     PROF(kConvFwd, bd.stage, launch_conv(P->c2_train[i], s));
+    if (split)
+      PROF(kEwFwd, bd.stage, launch_channel_stats(bd.y2, M, 64, n->stats + 2 * bd.b2.ch_off, s));
     if (bd.has_ds) PROF(kConvFwd, bd.stage, launch_conv(P->ds_train[i], s));
     memset(&a, 0, sizeof(a));
     a.y = bd.y2;
