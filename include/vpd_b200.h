@@ -189,6 +189,13 @@ VPD_API int vpd_net_bind(vpd_net* net, float* params, float* grads, float* buffe
 /* call after writing the parameter arena from outside (load_state_dict, optimizer) */
 VPD_API int vpd_net_params_changed(vpd_net* net);
 VPD_API void* vpd_net_stem_input(vpd_net* net);
+/* Data-parallel hook: during vpd_net_train_step, `fn(user, offset, count)` is called on
+ * the host each time a contiguous range of the gradient arena has been fully enqueued on
+ * `stream` (last layers first; the ranges partition the arena). The caller records an
+ * event and starts its all-reduce of that range on another stream, overlapping the rest
+ * of the backward pass. fn == NULL disables the hook. */
+typedef void (*vpd_bucket_fn)(void* user, int64_t offset, int64_t count);
+VPD_API int vpd_net_set_bucket_callback(vpd_net* net, vpd_bucket_fn fn, void* user);
 /* eval-mode encoder: emb_out fp32 [B][emb_dim] */
 VPD_API int vpd_net_forward(vpd_net* net, const float* x_nchw, const void* x_stem, int B,
                     float* emb_out, void* stream);

@@ -42,7 +42,8 @@ def parse_header(path=HEADER):
                 else:
                     ty, an = a.rsplit(' ', 1)
                     ty = ty.replace('const ', '').strip()
-                    argl.append((an, _SCALARS[ty]))
+                    # unknown names are opaque handles / function-pointer typedefs
+                    argl.append((an, _SCALARS.get(ty, ctypes.c_void_p)))
         protos[name] = (restype, argl)
     return protos
 

@@ -285,6 +285,10 @@ int vpd_net_params_changed(vpd_net* net) {
   net_params_changed((Net*)net);
   return 0;
 }
+int vpd_net_set_bucket_callback(vpd_net* net, vpd_bucket_fn fn, void* user) {
+  net_set_bucket_callback((Net*)net, (void (*)(void*, long long, long long))fn, user);
+  return 0;
+}
 void* vpd_net_stem_input(vpd_net* net) { return net_stem_input((Net*)net); }
 int vpd_net_forward(vpd_net* net, const float* x_nchw, const void* x_stem, int B,
                     float* emb_out, void* stream) {

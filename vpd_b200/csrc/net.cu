@@ -101,8 +101,12 @@ struct Profiler {
   }
 };
 
+typedef void (*BucketFn)(void* user, long long offset, long long count);
+
 struct Net {
   Profiler prof;
+  BucketFn bucket_fn = nullptr;   // called when grads[offset, offset+count) are final
+  void* bucket_user = nullptr;
   // configuration
   std::string arch;
   int D, Cimg, H, W, maxB, motion, T, Hd, F;
@@ -244,13 +248,14 @@ Net* net_create(const char* arch, int emb_dim, int in_channels, int H, int W, in
     }
   n->num_bn = bn_idx;
   n->total_ch = ch;
-  n->secA = 0;
+  // arena order: [BN gammas][BN betas][conv weights: stem, layer1..4][fc][decoder] - the
+  // tensors whose gradients are final first (decoder, fc, layer4, layer3, ...) sit at the
+  // END, so "everything from offset X on" is a contiguous all-reduce bucket
+  n->gamma_off = 0;
+  n->beta_off = pad4(ch);
+  n->secA = 2 * pad4(ch);
   n->secA_len = wo;
-  long long off = pad4(wo);
-  n->gamma_off = off;
-  off += pad4(ch);
-  n->beta_off = off;
-  off += pad4(ch);
+  long long off = n->secA + pad4(wo);
   n->fc_w_off = off;
   off += pad4((long long)n->D * n->F);
   n->fc_b_off = off;
@@ -267,15 +272,15 @@ Net* net_create(const char* arch, int emb_dim, int in_channels, int H, int W, in
   n->n_buffers = 2 * n->total_ch;
 
   // ---- tensor table in the reference's state_dict order
-  add_tensor(n, "resnet.conv1.weight", 0, n->stem.w_off, 2, {64, in_channels, 7, 7});
+  add_tensor(n, "resnet.conv1.weight", 0, n->secA + n->stem.w_off, 2, {64, in_channels, 7, 7});
   add_bn_tensors(n, "resnet.bn1", n->stem_bn);
   for (auto& bd : n->blocks) {
-    add_tensor(n, bd.prefix + ".conv1.weight", 0, bd.c1.w_off, 1, {bd.c1.Cout, bd.c1.Cin, 3, 3});
+    add_tensor(n, bd.prefix + ".conv1.weight", 0, n->secA + bd.c1.w_off, 1, {bd.c1.Cout, bd.c1.Cin, 3, 3});
     add_bn_tensors(n, bd.prefix + ".bn1", bd.b1);
-    add_tensor(n, bd.prefix + ".conv2.weight", 0, bd.c2.w_off, 1, {bd.c2.Cout, bd.c2.Cin, 3, 3});
+    add_tensor(n, bd.prefix + ".conv2.weight", 0, n->secA + bd.c2.w_off, 1, {bd.c2.Cout, bd.c2.Cin, 3, 3});
     add_bn_tensors(n, bd.prefix + ".bn2", bd.b2);
     if (bd.has_ds) {
-      add_tensor(n, bd.prefix + ".downsample.0.weight", 0, bd.ds.w_off, 1,
+      add_tensor(n, bd.prefix + ".downsample.0.weight", 0, n->secA + bd.ds.w_off, 1,
                  {bd.ds.Cout, bd.ds.Cin, 1, 1});
       add_bn_tensors(n, bd.prefix + ".downsample.1", bd.bds);
     }
@@ -523,7 +528,7 @@ static Plan* get_plan(Net* n, int B) {
                        ev(n->stem_bn, nullptr, 1));
   if (n->grads)
     ok &= !plan_stem_wgrad(&P->wg_stem, B, n->H, n->W, n->x_stem, n->gStem,
-                           n->grads + n->stem.w_off);
+                           n->grads + n->secA + n->stem.w_off);
   const bf16* zin = n->z_pool;
   bf16* gcur = n->gA;   // buffer holding dz_out of the block being processed (backward order!)
   // backward walks blocks in reverse; the ping-pong assignment is resolved below
@@ -578,8 +583,8 @@ static Plan* get_plan(Net* n, int B) {
       ok &= !plan_conv_dgrad(tmp, &cnt, g2, n->gB, wT + bd.c2.w_off, n->gC, nullptr, nullptr,
                              nullptr, 0, &f2);
       P->dgrad2[i] = tmp[0];
-      ok &= !plan_conv_wgrad(&P->wg2[i], g2, bd.z1, n->gB, n->grads + bd.c2.w_off);
-      ok &= !plan_conv_wgrad(&P->wg1[i], g1, zin, n->gC, n->grads + bd.c1.w_off);
+      ok &= !plan_conv_wgrad(&P->wg2[i], g2, bd.z1, n->gB, n->grads + n->secA + bd.c2.w_off);
+      ok &= !plan_conv_wgrad(&P->wg1[i], g1, zin, n->gC, n->grads + n->secA + bd.c1.w_off);
       // conv1's data gradient (+ identity / downsample branch) is dz of the previous
       // block's output stage (bn2 [+ downsample bn] + ReLU)
       ConvBwdFuse f1;
@@ -591,7 +596,7 @@ static Plan* get_plan(Net* n, int B) {
         if (pb.has_ds) bn_fuse(&f1, 1, pb.bds, pb.yds);
       }
       if (bd.has_ds) {
-        ok &= !plan_conv_wgrad(&P->wgds[i], geom(bd.ds, B), zin, n->gD, n->grads + bd.ds.w_off);
+        ok &= !plan_conv_wgrad(&P->wgds[i], geom(bd.ds, B), zin, n->gD, n->grads + n->secA + bd.ds.w_off);
         if (bd.c1.stride == 2) {
           ok &= !plan_conv_dgrad(tmp, &cnt, g1, n->gC, wT + bd.c1.w_off, g_in[i], nullptr, n->gD,
                                  wT + bd.ds.w_off, bd.ds.Cout, &f1);
@@ -797,6 +802,7 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
   }
 
   // ----------------------------------------------------------------- backward
+  long long bucket_hi = n->n_params;
   bf16* cur = n->gA;
   bf16* other = n->gA2;
   for (int i = (int)nb - 1; i >= 0; --i) {
@@ -849,6 +855,13 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     for (auto& L : P->dgrad1[i])
       PROF(kConvDgrad, bd.stage, launch_conv(L, s));
     if (bd.has_ds) std::swap(cur, other);
+    // gradient buckets for the data-parallel all-reduce: when stage 4 (then stage 3) is
+    // done, everything from its first conv weight to the end of the arena is final
+    if (n->bucket_fn != nullptr && i > 0 && n->blocks[i - 1].stage != bd.stage && bd.stage >= 3) {
+      const long long lo = n->secA + bd.c1.w_off;
+      n->bucket_fn(n->bucket_user, lo, bucket_hi - lo);
+      bucket_hi = lo;
+    }
   }
   // stem: maxpool + ReLU + BN backward, then the stem weight gradient
   {
@@ -872,6 +885,7 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     PROF(kEwBwd, 0, launch_stem_bwd(sp, s));
     PROF(kConvWgrad, 0, launch_wgrad(P->wg_stem, s));
   }
+  if (n->bucket_fn != nullptr) n->bucket_fn(n->bucket_user, 0, bucket_hi);
   n->params_dirty = true;  // the caller is about to update the parameters
   return 0;
 }
@@ -924,6 +938,10 @@ int net_num_bn(Net* n) { return n->num_bn; }
 int net_num_tensors(Net* n) { return (int)n->tensors.size(); }
 long long net_conv_section_len(Net* n) { return n->secA_len; }
 void net_params_changed(Net* n) { n->params_dirty = true; }
+void net_set_bucket_callback(Net* n, void (*fn)(void*, long long, long long), void* user) {
+  n->bucket_fn = fn;
+  n->bucket_user = user;
+}
 void* net_stem_input(Net* n) { return n->x_stem; }
 
 int net_tensor_info(Net* n, int i, char* name, int name_cap, int* arena, long long* offset,

@@ -27,6 +27,7 @@ int net_num_tensors(Net* n);
 int net_tensor_info(Net* n, int i, char* name, int name_cap, int* arena, long long* offset,
                     int* layout, int* ndim, long long* shape4);
 void net_params_changed(Net* n);
+void net_set_bucket_callback(Net* n, void (*fn)(void*, long long, long long), void* user);
 void* net_stem_input(Net* n);
 long long net_conv_section_len(Net* n);
 int net_activation(Net* n, int block, int which, int B, void** ptr, long long* numel);

@@ -10,11 +10,14 @@ Differences a caller can observe, all deliberate:
     `loss.item()` every step (train_vpd_model.py:93); the returned value is the
     same quantity, sum of losses / number of frames.
 """
+import ctypes
 import os
 
 import torch
 
 from ._lib import lib, stream_ptr, VpdError
+
+_BUCKET_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64)
 
 
 class FusedAdamW:
@@ -79,6 +82,39 @@ class ModelTrainer:
         dev = encoder._dev
         self._loss = torch.zeros(1, device=dev, dtype=torch.float64)
         self._copy_stream = torch.cuda.Stream(device=dev)
+        # data parallel: gradient buckets are all-reduced on their own stream while the
+        # rest of the backward pass is still running (hook: vpd_net_set_bucket_callback)
+        self._comm_stream = torch.cuda.Stream(device=dev)
+        self._bucket_cb = _BUCKET_FN(self._on_bucket)
+        self._hooked = None
+        self._pending = []
+        self.overlap_allreduce = os.environ.get('VPD_DP_OVERLAP', '1') != '0'
+
+    def _on_bucket(self, user, offset, count):
+        """Called by the native step when grads[offset:offset+count] are enqueued."""
+        dist = _dist()
+        if dist is None or count <= 0:
+            return
+        enc = self.encoder
+        cur = torch.cuda.current_stream(enc._dev)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        self._comm_stream.wait_event(ev)
+        with torch.cuda.stream(self._comm_stream):
+            # reduction='sum' loss => gradients add across ranks (SUM, not mean)
+            work = dist.all_reduce(enc._grads[offset:offset + count], op=dist.ReduceOp.SUM,
+                                   async_op=True)
+        self._pending.append(work)
+
+    def _hook(self, net):
+        """(Un)install the bucket callback on the bound native net."""
+        want = _dist() is not None and self.overlap_allreduce
+        key = (net.handle, want)
+        if self._hooked != key:
+            lib().call('vpd_net_set_bucket_callback', net.handle,
+                       ctypes.cast(self._bucket_cb, ctypes.c_void_p) if want else None, None)
+            self._hooked = key
+        return want
 
     # ------------------------------------------------------------- one batch
     def _run(self, img, tgt, n, train):
@@ -88,6 +124,7 @@ class ModelTrainer:
             if train:
                 enc._ensure_grads()
             net = enc._native(H, W, n)
+            self._overlapped = self._hook(net) if train else False
             fn = 'vpd_net_train_step' if train else 'vpd_net_eval_loss'
             args = [net.handle, img, None, tgt, n, self._loss]
             if not train:
@@ -101,6 +138,7 @@ class ModelTrainer:
         with torch.cuda.device(enc._dev):
             enc._ensure_grads()
             net = enc._native(height, width, n)
+            self._overlapped = self._hook(net)
             lib().call('vpd_net_train_step', net.handle, None, stem, tgt, n, self._loss,
                        stream_ptr(enc._dev))
             self._sync_grads()
@@ -117,7 +155,15 @@ class ModelTrainer:
 
     def _sync_grads(self):
         dist = _dist()
-        if dist is not None:
+        if dist is None:
+            return
+        if getattr(self, '_overlapped', False):
+            # buckets were launched from the callback; make the compute stream wait for them
+            for work in self._pending:
+                work.wait()
+            self._pending = []
+            torch.cuda.current_stream(self.encoder._dev).wait_stream(self._comm_stream)
+        else:
             # reduction='sum' loss => gradients add across ranks (SUM, not mean)
             dist.all_reduce(self.encoder._grads, op=dist.ReduceOp.SUM)
 
