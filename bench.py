@@ -286,6 +286,9 @@ def run_native(args, rank, world, local_rank):
     if rank == 0:
         net = enc._native(IMG, IMG, B)
         nprof = 3
+        # rank-0-only pass: no collectives may be issued from it
+        L.call('vpd_net_set_bucket_callback', net.handle, None, None)
+        trainer._hooked = None
         L.call('vpd_net_profile_enable', net.handle, 1)
         for i in range(nprof):
             # same body as step() but without the collective, so only kernels are timed
