@@ -228,6 +228,11 @@ VPD_API int vpd_net_profile_read(vpd_net* net, float* ms_host, int* counts_host)
  * descriptor's base-offset field to (start_addr >> 7) & 7. */
 VPD_API int vpd_umma_probe(const void* src_bf16, int rows, int row_start, int sbo_bytes,
                    int base_offset_mode, float* out, void* stream);
+/* Debug: while dev_i64 is non-null, every generic implicit-GEMM conv launch writes 8 int64
+ * per CTA into it (globaltimer at entry, then SM clock at entry / dependencies resolved /
+ * first operands landed / last MMA issued / first accumulator ready / epilogue done /
+ * exit). The buffer must hold 8 * 148 entries. */
+VPD_API int vpd_conv_trace(void* dev_i64);
 /* number of kernel launches issued by this library since it was loaded */
 VPD_API int64_t vpd_launch_count(void);
 

@@ -319,6 +319,10 @@ int vpd_net_profile_read(vpd_net* net, float* ms_host, int* counts_host) {
   return net_profile_read((Net*)net, ms_host, counts_host);
 }
 int64_t vpd_launch_count(void) { return launch_count(); }
+int vpd_conv_trace(void* dev_i64) {
+  set_conv_trace((long long*)dev_i64);
+  return 0;
+}
 int vpd_umma_probe(const void* src_bf16, int rows, int row_start, int sbo_bytes,
                    int base_offset_mode, float* out, void* stream) {
   return umma_probe((const bf16*)src_bf16, rows, row_start, sbo_bytes, base_offset_mode, out,

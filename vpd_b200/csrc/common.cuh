@@ -81,6 +81,14 @@ VPD_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (contiguous bytes, size % 16 == 0), completing on an mbarrier
+VPD_DEVINL void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes),
+      "r"(smem_u32(bar))
+      : "memory");
+}
 // multicast variant: the box lands at the same CTA-relative smem offset of every CTA
 // in `cta_mask`, and each destination's mbarrier (same offset) gets the complete_tx
 VPD_DEVINL void tma_load_3d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0,
@@ -93,7 +101,31 @@ VPD_DEVINL void tma_load_3d_mcast(void* smem_dst, const CUtensorMap* m, uint64_t
       : "memory");
 }
 
+// One lane of a converged warp. Unlike `lane == 0`, the compiler knows the guarded region
+// runs on a single thread, so uniform-datapath instructions (UTCHMMA, UTMALDG, UTCBAR)
+// issue directly instead of inside a per-active-lane broadcast loop.
+VPD_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ------------------------------------------------------------------ clusters
+// shared::cluster address of `local_smem_addr` in CTA `rank` of this cluster
+VPD_DEVINL uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+// arrive on an mbarrier that lives in another CTA of the cluster
+VPD_DEVINL void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
 VPD_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -118,6 +150,40 @@ VPD_DEVINL void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                : "memory");
 }
+// ---- cta_group::2: the two CTAs of a cluster pair act as one 256-row MMA unit
+VPD_DEVINL void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+}
+VPD_DEVINL void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+VPD_DEVINL void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// issued by the leader CTA only: D[256 x N] += A[256 x 16] * B[N x 16]^T, rows 0-127 of A/D
+// and the first N/2 rows of B in the leader's smem/TMEM, the rest in the peer's (same offsets)
+VPD_DEVINL void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (when the pair's MMAs retire) on the barrier at this offset in both CTAs
+VPD_DEVINL void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(static_cast<uint16_t>(3))
+      : "memory");
+}
+
 VPD_DEVINL void tc_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -189,6 +255,17 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn, i
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn) << 15) |
          (static_cast<uint32_t>(b_mn) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// Weight mirrors are stored PRE-TILED in the exact shared-memory image the tensor core
+// reads: per tap, per 64-wide K chunk, per 64-row block: [64 rows][64 k] bf16 with the
+// 16-byte chunks of a row XOR-swizzled by (row % 8). A [BLOCK_N rows x 64 k] operand tile
+// is then one contiguous run of BLOCK_N*128 bytes (a single bulk copy instead of BLOCK_N
+// strided 128-byte TMA rows). Offset (in elements) inside one tap's [rows][cols] block:
+__host__ __device__ inline long long wtile_offset(int row, int col, int rows) {
+  const int kc = col >> 6, cc = col & 63, rb = row >> 6, rr = row & 63;
+  const int chunk = (cc >> 3) ^ (rr & 7);
+  return ((long long)(kc * (rows >> 6) + rb) * 64 + rr) * 64 + chunk * 8 + (cc & 7);
 }
 
 // ------------------------------------------------------------- small helpers

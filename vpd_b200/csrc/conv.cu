@@ -62,10 +62,10 @@ static void finish_launch(ConvLaunch* L, int cout, bool stats) {
   L->block_n = pick_block_n(cout, m_tiles);
   L->p.n_tiles = cout / L->block_n;
   L->p.cout = cout;
-  // weight multicast over a 2-CTA cluster is implemented and tested, but measured no
-  // gain on B200 (L2 de-duplicates only for clusters >= 8), so it is opt-in
-  static const int want_cluster = env_int("VPD_CLUSTER", 1);
-  L->cluster = (want_cluster >= 2 && m_tiles >= 2) ? 2 : 1;
+  // pair mode (tcgen05 cta_group::2): two CTAs share one 256-row MMA and each stages only
+  // half of the weight tile, halving the shared-memory traffic per MAC
+  static const int want_pair = env_int("VPD_PAIR", 0);
+  L->cluster = (want_pair && L->block_n >= 128 && m_tiles >= 2) ? 2 : 1;
   const int cs = L->cluster;
   const int items = ((m_tiles + cs - 1) / cs) * L->p.n_tiles;  // cluster-level work items
   int clusters = device_sm_count() / cs;
@@ -100,6 +100,12 @@ static int act_map(CUtensorMap* m, const __nv_bfloat16* x, int N, int H, int W, 
   uint64_t str[5] = {2, (uint64_t)2 * C * 2, (uint64_t)W * C * 2, (uint64_t)2 * W * C * 2,
                      (uint64_t)H * W * C * 2};
   return encode_tmap_bf16(m, x, 5, dims, str, box, true);
+}
+
+static void set_weights(ConvParams* p, int src, const __nv_bfloat16* w, int rows, int kdim) {
+  p->w[src] = w;
+  p->w_kc[src] = kdim / 64;
+  p->w_rb[src] = rows / 64;
 }
 
 // Re-plan a stride-1 3x3 'same' convolution (forward or dgrad) for the halo-reuse
@@ -148,9 +154,11 @@ static bool try_halo(ConvLaunch* L, const __nv_bfloat16* x, const __nv_bfloat16*
                      (uint64_t)H * W * cin_k * 2};
   uint32_t box[5] = {64, 10, 1, 18, 1};
   if (encode_tmap_bf16(&L->a0, x, 5, dims, str, box, true)) return false;
-  if (weight_map(&L->b0, wt, 9, cout_k, cin_k, L->block_n)) return false;
+  set_weights(&p, 0, wt, cout_k, cin_k);
+  set_weights(&p, 1, wt, cout_k, cin_k);
   L->a1 = L->a0;
-  L->b1 = L->b0;
+  L->b0 = L->a0;
+  L->b1 = L->a0;
   return true;
 }
 
@@ -203,9 +211,11 @@ int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
     return 0;
   finish_launch(L, g.Cout, e.stats != nullptr);
   if (act_map(&L->a0, x, g.N, g.H, g.W, g.Cin, g.stride, p)) return -1;
-  if (weight_map(&L->b0, w_tap, g.k * g.k, g.Cout, g.Cin, L->block_n / L->cluster)) return -1;
+  set_weights(&p, 0, w_tap, g.Cout, g.Cin);
+  set_weights(&p, 1, w_tap, g.Cout, g.Cin);
   L->a1 = L->a0;
-  L->b1 = L->b0;
+  L->b0 = L->a0;
+  L->b1 = L->a0;
   return 0;
 }
 
@@ -241,9 +251,11 @@ int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad
   uint64_t str[5] = {2, 2 * 8 * 2, pitch, 2 * pitch, (uint64_t)Hp * pitch};
   uint32_t box[5] = {64, (uint32_t)p.tw, 1, (uint32_t)p.th, (uint32_t)p.tn};
   if (encode_tmap_bf16(&L->a0, x_pad, 5, dims, str, box, true)) return -1;
-  if (weight_map(&L->b0, w_stem, 7, 64, 64, L->block_n / L->cluster)) return -1;
+  set_weights(&p, 0, w_stem, 64, 64);
+  set_weights(&p, 1, w_stem, 64, 64);
   L->a1 = L->a0;
-  L->b1 = L->b0;
+  L->b0 = L->a0;
+  L->b1 = L->a0;
   return 0;
 }
 
@@ -298,9 +310,11 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
     }
     finish_launch(L, g.Cin, p.bnb > 0);
     if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
-    if (weight_map(&L->b0, wT_tap, g.k * g.k, g.Cin, g.Cout, L->block_n / L->cluster)) return -1;
+    set_weights(&p, 0, wT_tap, g.Cin, g.Cout);
+    set_weights(&p, 1, wT_tap, g.Cin, g.Cout);
     L->a1 = L->a0;
-    L->b1 = L->b0;
+    L->b0 = L->a0;
+    L->b1 = L->a0;
     *count = 1;
     return 0;
   }
@@ -350,13 +364,15 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
       set_fuse(&p, base);
       finish_launch(L, g.Cin, p.bnb > 0);
       if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
-      if (weight_map(&L->b0, wT_tap, 9, g.Cin, g.Cout, L->block_n / L->cluster)) return -1;
+      set_weights(&p, 0, wT_tap, g.Cin, g.Cout);
+      set_weights(&p, 1, wT_tap, g.Cin, g.Cout);
+      L->b0 = L->a0;
+      L->b1 = L->a0;
       if (fuse_ds) {
         if (act_map(&L->a1, dy_ds, g.N, Ho, Wo, cout_ds, 1, p)) return -1;
-        if (weight_map(&L->b1, wT_ds, 1, g.Cin, cout_ds, L->block_n / L->cluster)) return -1;
+        set_weights(&p, 1, wT_ds, g.Cin, cout_ds);
       } else {
         L->a1 = L->a0;
-        L->b1 = L->b0;
       }
       ++*count;
     }
@@ -394,8 +410,17 @@ static int launch_halo(const ConvLaunch& L, cudaStream_t stream) {
   return 0;
 }
 
-int launch_conv(const ConvLaunch& L, cudaStream_t stream) {
-  if (L.grid <= 0) return 0;
+static long long* g_conv_trace = nullptr;
+void set_conv_trace(long long* dev_buf) { g_conv_trace = dev_buf; }
+
+int launch_conv(const ConvLaunch& L0, cudaStream_t stream) {
+  if (L0.grid <= 0) return 0;
+  ConvLaunch traced;
+  if (g_conv_trace != nullptr) {
+    traced = L0;
+    traced.p.trace = g_conv_trace;
+  }
+  const ConvLaunch& L = g_conv_trace != nullptr ? traced : L0;
   if (L.halo == 1) return launch_halo<1>(L, stream);
   if (L.halo == 3) {
     static bool attr_set = false;
@@ -412,7 +437,6 @@ int launch_conv(const ConvLaunch& L, cudaStream_t stream) {
   }
   if (L.cluster == 2) {
     switch (L.block_n) {
-      case 64: return launch_bn<64, 2>(L, stream);
       case 128: return launch_bn<128, 2>(L, stream);
       case 256: return launch_bn<256, 2>(L, stream);
     }
@@ -528,8 +552,8 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat
   const float* src = w + i * kk;
   for (int t = 0; t < kk; ++t) {
     const __nv_bfloat16 v = __float2bfloat16_rn(src[t]);
-    if (w_tap) w_tap[((long long)t * Cout + co) * Cin + ci] = v;
-    if (wT_tap) wT_tap[((long long)t * Cin + ci) * Cout + co] = v;
+    if (w_tap) w_tap[(long long)t * Cout * Cin + wtile_offset(co, ci, Cout)] = v;
+    if (wT_tap) wT_tap[(long long)t * Cout * Cin + wtile_offset(ci, co, Cin)] = v;
   }
 }
 
@@ -553,7 +577,7 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat
   const int kw = e / 8, c = e % 8;
   float v = 0.f;
   if (kw < 7 && c < Cimg) v = w[((co * Cimg + c) * 7 + kh) * 7 + kw];
-  ws[i] = __float2bfloat16_rn(v);
+  ws[(long long)kh * 4096 + wtile_offset(co, e, 64)] = __float2bfloat16_rn(v);
 }
 
 int pack_stem_weight(const float* w_oihw, __nv_bfloat16* w_stem, int Cimg, cudaStream_t stream) {

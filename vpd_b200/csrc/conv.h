@@ -14,6 +14,9 @@ struct ConvLaunch {
   int grid;
 };
 
+// debug: generic-kernel launches record 8 int64 per CTA into dev_buf (null = off)
+void set_conv_trace(long long* dev_buf);
+
 struct ConvGeom {
   int N, H, W;     // input batch / height / width (of x; for dgrad: of dx)
   int Cin, Cout;

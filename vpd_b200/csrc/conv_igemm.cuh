@@ -58,6 +58,11 @@ struct ConvParams {
   const float* shift;                 // [cout] or null
   int relu;
   double* stats;                      // [2][cout] (sum, sumsq) or null
+  // pre-tiled bf16 weights (see wtile_offset) for tap.src 0 / 1: element offset of the
+  // [BLOCK_N x 64] tile (tap t, chunk kc, rows n0..) = ((t*w_kc + kc)*w_rb + n0/64) * 4096
+  const __nv_bfloat16* w[2];
+  int w_kc[2];                        // K chunks per tap
+  int w_rb[2];                        // 64-row blocks (N dimension / 64)
   // Fused BatchNorm-backward reduction (dgrad launches): the tile just computed is
   // dz of a ReLU->BN stage; mask it with 1[z > 0] before it is stored (so `out`
   // holds g) and accumulate sum(g), sum(g * xhat_b) for up to two BN branches.
@@ -67,7 +72,14 @@ struct ConvParams {
   const float* bmean[2];              // [cout] saved batch mean
   const float* brstd[2];              // [cout] saved 1/sqrt(var+eps)
   double* bsums[2];                   // [2][cout]: sum g, sum g*xhat
+  // debug (vpd_conv_trace): 8 int64 per CTA - globaltimer at entry, then clock64 at
+  // entry / after the dependency wait / first operands landed / last MMA issued /
+  // first accumulator ready / epilogue done / exit
+  long long* trace;
 };
+VPD_DEVINL void trace_mark(const ConvParams& p, int slot) {
+  if (p.trace != nullptr) p.trace[blockIdx.x * 8 + slot] = clock64();
+}
 
 // called by the 128 epilogue threads (threadIdx.x in [64,192))
 template <int BLOCK_N>
@@ -148,6 +160,10 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
                               float* s_bn, int rank, int first_item, int item_stride,
                               int total_tiles, int warp, int lane) {
   // ---------------------------------------------------------------- epilogue
+  // pair mode (CS == 2): the leader's MMA thread owns the accumulator hand-shake, so the
+  // peer's epilogue warps release the TMEM stage on the LEADER's barrier
+  const uint32_t tempty_remote0 =
+      (CS == 2 && rank == 1) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
   const int q = warp & 3;       // TMEM lane quarter this warp may access
   const int r = q * 32 + lane;  // row of the 128-row tile
   int as = 0;
@@ -190,6 +206,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
     }
 
     mbar_wait(&tfull_bar[as], aphase);
+    if (tile == first_item && threadIdx.x == 64) trace_mark(p, 5);
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N / 32; ++c) {
@@ -340,7 +357,10 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    if (lane == 0) {
+      if (CS == 2 && rank == 1) mbar_arrive_remote(tempty_remote0 + as * 8);
+      else mbar_arrive(&tempty_bar[as]);
+    }
     if (++as == 2) {
       as = 0;
       aphase ^= 1;
@@ -352,9 +372,14 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
   }
 }
 
-// CS = cluster size along M: the CS CTAs of a cluster work on CS adjacent pixel
-// tiles of the SAME channel block in lockstep; each loads 1/CS of the weight tile
-// and multicasts it to all of them, cutting the L2->SM weight traffic by CS.
+// CS = 2: PAIR mode (tcgen05 cta_group::2). The two CTAs of a cluster own two adjacent
+// pixel tiles of the same channel block and act as ONE 256 x BLOCK_N MMA unit: each loads
+// its own A tile and HALF of the weight tile; the leader issues the MMAs, which read A
+// from both CTAs' shared memory and the weight halves from both, and write each CTA's
+// 128 rows to its own TMEM. A 128x128 single-CTA tile needs 128 B/cycle of operand reads
+// plus as much TMA write traffic - twice the 128 B/cycle the shared memory can move -
+// which is what pins the single-CTA kernel near half of the tensor peak; in pair mode a
+// CTA reads/writes 3/4 (N=128) or 1/2 (N=256) as many bytes per MAC.
 template <int BLOCK_N, int CS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
@@ -369,7 +394,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* pfull_bar = tempty_bar + 2;  // leader only: "the peer's stage has landed"
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pfull_bar + Cfg::kStages);
   float* s_sum = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes);
   float* s_sq = s_sum + BLOCK_N;
   float* s_x2 = s_sq + BLOCK_N;  // second BN branch (fused backward reduction)
@@ -381,19 +407,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CS);
+      mbar_init(&empty_bar[s], 1);
+      if (CS == 2) mbar_init(&pfull_bar[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&tempty_bar[s], CS * kEpiWarps);  // pair mode: both CTAs' epilogue warps
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB0);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
-    tmem_relinquish();
+    if (CS == 2) {
+      tmem_alloc_pair(tmem_ptr, Cfg::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+      tmem_relinquish();
+    }
   }
   for (int i = threadIdx.x; i < 3 * BLOCK_N; i += kConvThreads) s_sum[i] = 0.f;
   tc_fence_before();
@@ -401,7 +433,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (CS > 1) cluster_sync_all();  // peers' barriers are initialised before any remote arrive
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (threadIdx.x == 0 && p.trace != nullptr) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.trace[blockIdx.x * 8] = static_cast<long long>(g);
+    trace_mark(p, 1);
+  }
   pdl_wait();  // everything above overlapped the previous kernel's tail
+  if (threadIdx.x == 0) trace_mark(p, 2);
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   // work items are (group of CS pixel tiles, channel block); a CTA takes the pixel
@@ -413,7 +452,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_item; tile < total_tiles; tile += item_stride) {
@@ -431,16 +470,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
-            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes / CS);
             tma_load_5d(sa, ma, &full_bar[stage], tap.c0 + kc * kBlockK, w0 + tap.d1, tap.d2,
                         h0 + tap.d3, b0);
-            if (CS == 1) {
-              tma_load_3d(sb, mb, &full_bar[stage], kc * kBlockK, n_tile * BLOCK_N, tap.btap);
-            } else {
-              tma_load_3d_mcast(sb + rank * (Cfg::kBBytes / CS), mb, &full_bar[stage],
-                                kc * kBlockK, n_tile * BLOCK_N + rank * (BLOCK_N / CS), tap.btap,
-                                static_cast<uint16_t>((1u << CS) - 1));
-            }
+            // this CTA's share of the weight tile: BLOCK_N / CS rows
+            bulk_load(sb,
+                      p.w[tap.src] + ((size_t)(tap.btap * p.w_kc[tap.src] + kc) * p.w_rb[tap.src] +
+                                      n_tile * (BLOCK_N / 64) + rank * (BLOCK_N / 64 / CS)) * 4096,
+                      Cfg::kBBytes / CS, &full_bar[stage]);
             if (++stage == Cfg::kStages) {
               stage = 0;
               phase ^= 1;
@@ -451,8 +488,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    const bool issuer = elect_one();  // executed by the whole (converged) warp
+    if (issuer && (CS == 1 || rank == 0)) {
+      constexpr uint32_t idesc = make_idesc_bf16(CS * kBlockM, BLOCK_N, 0, 0);
       int total_kb = 0;
       for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].kchunks;
       int stage = 0;
@@ -465,6 +503,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (CS == 2) mbar_wait(&pfull_bar[stage], phase);
+          if (kb == 0 && tile == first_item) trace_mark(p, 3);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
@@ -473,19 +513,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advance 32 B (16 bf16) along K inside the 128 B swizzled row
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (CS == 2) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
-          if (CS == 1) umma_commit(&empty_bar[stage]);
-          else umma_commit_mcast(&empty_bar[stage], static_cast<uint16_t>((1u << CS) - 1));
+          if (CS == 2) umma_commit_pair(&empty_bar[stage]);  // frees the stage in both CTAs
+          else umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[as]);
+        if (CS == 2) umma_commit_pair(&tfull_bar[as]);
+        else umma_commit(&tfull_bar[as]);
+        trace_mark(p, 4);
         if (++as == 2) {
           as = 0;
           aphase ^= 1;
+        }
+      }
+    } else if (issuer && CS == 2) {
+      // peer CTA: relay "my stage has landed" to the leader's MMA thread
+      const uint32_t pfull_remote0 = mapa_shared(smem_u32(&pfull_bar[0]), 0);
+      int total_kb = 0;
+      for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].kchunks;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+        for (int kb = 0; kb < total_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          mbar_arrive_remote(pfull_remote0 + stage * 8);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -494,11 +554,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                                first_item, item_stride, total_tiles, warp, lane);
   }
 
+  if (threadIdx.x == 64) trace_mark(p, 6);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace_mark(p, 7);
   if (CS > 1) cluster_sync_all();  // no CTA exits while a peer may still signal / multicast to it
   tc_fence_after();
-  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  if (warp == 1) {
+    if (CS == 2) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
 }
 
 
@@ -587,13 +652,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int my_ntile = blockIdx.x % p.n_tiles;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       // resident weights of this CTA's channel block: CHUNKS x 9 boxes {64 cin, 64 cout, 1}
       mbar_expect_tx(w_bar, Cfg::kWBytes);
       for (int kc = 0; kc < CHUNKS; ++kc)
         for (int t = 0; t < 9; ++t)
-          tma_load_3d(s_w + (kc * 9 + t) * (BLOCK_N * 128), &tmB, w_bar, kc * 64,
-                      my_ntile * BLOCK_N, p.taps[t].btap);
+          bulk_load(s_w + (kc * 9 + t) * (BLOCK_N * 128),
+                    p.w[0] + ((size_t)(p.taps[t].btap * p.w_kc[0] + kc) * p.w_rb[0] + my_ntile) * 4096,
+                    BLOCK_N * 128, w_bar);
       int slot = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -615,7 +681,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
       mbar_wait(w_bar, 0);
       int slot = 0;
@@ -741,7 +807,7 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
   const int chunks = p.taps[0].kchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int slot = 0, ws = 0;
       uint32_t pphase = 0, wphase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -763,8 +829,10 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
           for (int t = 0; t < 9; ++t) {
             mbar_wait(&wempty[ws], wphase ^ 1);
             mbar_expect_tx(&wfull[ws], Cfg::kWTile);
-            tma_load_3d(s_w + ws * Cfg::kWTile, &tmB, &wfull[ws], kc * 64, n_tile * BLOCK_N,
-                        p.taps[t].btap);
+            bulk_load(s_w + ws * Cfg::kWTile,
+                      p.w[0] + ((size_t)(p.taps[t].btap * p.w_kc[0] + kc) * p.w_rb[0] +
+                                n_tile * (BLOCK_N / 64)) * 4096,
+                      Cfg::kWTile, &wfull[ws]);
             if (++ws == Cfg::kWStages) {
               ws = 0;
               wphase ^= 1;
@@ -774,7 +842,7 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
       int slot = 0, ws = 0;
       uint32_t pphase = 0, wphase = 0;
@@ -911,7 +979,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   const int total_items = p.num_pairs * p.n_tiles * p.splits;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -950,7 +1018,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 1, 1);
       int stage = 0;
       uint32_t phase = 0;

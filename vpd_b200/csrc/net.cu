@@ -447,11 +447,11 @@ mirror_weights_kernel(const float* __restrict__ w, bf16* __restrict__ w_tap, bf1
     const long long idx = base + (long long)(tr + r) * cols + tc + tx;
     const float v = w[idx];
     tile[r][tx] = v;
-    w_tap[idx] = __float2bfloat16_rn(v);
+    w_tap[base + wtile_offset(tr + r, tc + tx, rows)] = __float2bfloat16_rn(v);
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8)
-    wT[base + (long long)(tc + r) * rows + tr + tx] = __float2bfloat16_rn(tile[tx][r]);
+  for (int r = ty; r < 32; r += 8)   // transposed operand: rows' = cols, k' = rows
+    wT[base + wtile_offset(tc + r, tr + tx, cols)] = __float2bfloat16_rn(tile[tx][r]);
 }
 
 static int pack_weights(Net* n, cudaStream_t s) {
