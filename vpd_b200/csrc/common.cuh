@@ -81,6 +81,23 @@ VPD_DEVINL void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
+// shared -> global tile store (bulk async-group completion); out-of-range box elements are
+// clipped by the hardware
+VPD_DEVINL void tma_store_5d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2,
+                             int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::
+          "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2),
+      "r"(c3), "r"(c4)
+      : "memory");
+}
+VPD_DEVINL void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING their shared-memory source
+VPD_DEVINL void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+VPD_DEVINL void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+// ... have completed (writes performed)
+VPD_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // 1-D bulk copy global -> shared (contiguous bytes, size % 16 == 0), completing on an mbarrier
 VPD_DEVINL void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile(
@@ -112,6 +129,16 @@ VPD_DEVINL bool elect_one() {
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// Per-warpgroup register re-allocation (all 4 warps of an aligned warpgroup must execute it)
+template <int N>
+VPD_DEVINL void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+VPD_DEVINL void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
 
 // ------------------------------------------------------------------ clusters
@@ -275,6 +302,11 @@ VPD_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
 }
 VPD_DEVINL float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 VPD_DEVINL float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+// 0xFFFF in each half whose bf16 value is > 0 (NaN -> 0), for masking a packed pair
+VPD_DEVINL uint32_t bf16x2_gt0_mask(uint32_t v) {
+  const __nv_bfloat162 z = *reinterpret_cast<const __nv_bfloat162*>(&v);
+  return __hgt2_mask(z, __floats2bfloat162_rn(0.f, 0.f));
+}
 VPD_DEVINL float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 VPD_DEVINL uint4 ldg_nc_v4(const void* p) {
@@ -282,6 +314,15 @@ VPD_DEVINL uint4 ldg_nc_v4(const void* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                : "l"(p));
+  return r;
+}
+// coherent 16-byte global load (data written earlier in this kernel by other warps of the CTA)
+VPD_DEVINL uint4 ldg_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
   return r;
 }
 VPD_DEVINL void stg_v4(void* p, uint4 v) {

@@ -102,6 +102,15 @@ static int act_map(CUtensorMap* m, const __nv_bfloat16* x, int N, int H, int W, 
   return encode_tmap_bf16(m, x, 5, dims, str, box, true);
 }
 
+// view of the output tensor [N][H][W][C] for the slab stores: same box as the A loads
+// (64 channels x the tile's pixels); `stride` 2 addresses one pixel-parity class
+static int out_map(ConvLaunch* L, const __nv_bfloat16* out, int N, int H, int W, int C, int stride,
+                   int c0, int d2) {
+  L->p.out_c0 = c0;
+  L->p.out_d2 = d2;
+  return act_map(&L->o, out, N, H, W, C, stride, L->p);
+}
+
 static void set_weights(ConvParams* p, int src, const __nv_bfloat16* w, int rows, int kdim) {
   p->w[src] = w;
   p->w_kc[src] = kdim / 64;
@@ -157,8 +166,6 @@ static bool try_halo(ConvLaunch* L, const __nv_bfloat16* x, const __nv_bfloat16*
   set_weights(&p, 0, wt, cout_k, cin_k);
   set_weights(&p, 1, wt, cout_k, cin_k);
   L->a1 = L->a0;
-  L->b0 = L->a0;
-  L->b1 = L->a0;
   return true;
 }
 
@@ -208,15 +215,13 @@ int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
   set_epilogue(&p, e);
   if (g.k == 3 && g.stride == 1 && g.pad == 1 &&
       try_halo(L, x, w_tap, g.N, g.H, g.W, g.Cin, g.Cout, e.stats != nullptr))
-    return 0;
+    return out_map(L, y, g.N, Ho, Wo, g.Cout, 1, 0, 0);
   finish_launch(L, g.Cout, e.stats != nullptr);
   if (act_map(&L->a0, x, g.N, g.H, g.W, g.Cin, g.stride, p)) return -1;
   set_weights(&p, 0, w_tap, g.Cout, g.Cin);
   set_weights(&p, 1, w_tap, g.Cout, g.Cin);
   L->a1 = L->a0;
-  L->b0 = L->a0;
-  L->b1 = L->a0;
-  return 0;
+  return out_map(L, y, g.N, Ho, Wo, g.Cout, 1, 0, 0);
 }
 
 int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
@@ -254,9 +259,7 @@ int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad
   set_weights(&p, 0, w_stem, 64, 64);
   set_weights(&p, 1, w_stem, 64, 64);
   L->a1 = L->a0;
-  L->b0 = L->a0;
-  L->b1 = L->a0;
-  return 0;
+  return out_map(L, y, N, Ho, Wo, 64, 1, 0, 0);
 }
 
 int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bfloat16* dy,
@@ -306,17 +309,15 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
     set_fuse(&p, 0);
     if (g.k == 3 && try_halo(L, dy, wT_tap, g.N, Ho, Wo, g.Cout, g.Cin, p.bnb > 0)) {
       *count = 1;
-      return 0;
+      return out_map(L, dx, g.N, g.H, g.W, g.Cin, 1, 0, 0);
     }
     finish_launch(L, g.Cin, p.bnb > 0);
     if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
     set_weights(&p, 0, wT_tap, g.Cin, g.Cout);
     set_weights(&p, 1, wT_tap, g.Cin, g.Cout);
     L->a1 = L->a0;
-    L->b0 = L->a0;
-    L->b1 = L->a0;
     *count = 1;
-    return 0;
+    return out_map(L, dx, g.N, g.H, g.W, g.Cin, 1, 0, 0);
   }
   VPD_REQUIRE(g.stride == 2 && g.k == 3 && g.pad == 1, "dgrad: only 3x3/2 pad 1 strided convs");
   VPD_REQUIRE(g.H == 2 * Ho && g.W == 2 * Wo, "dgrad: stride 2 needs even input dims");
@@ -366,8 +367,9 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
       if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
       set_weights(&p, 0, wT_tap, g.Cin, g.Cout);
       set_weights(&p, 1, wT_tap, g.Cin, g.Cout);
-      L->b0 = L->a0;
-      L->b1 = L->a0;
+      // parity class (a, b) of dx through the stride-2 view: channel coordinate b*Cin + c,
+      // parity coordinate a, tile coordinates in units of the half-resolution grid
+      if (out_map(L, dx, g.N, g.H, g.W, g.Cin, 2, b * g.Cin, a)) return -1;
       if (fuse_ds) {
         if (act_map(&L->a1, dy_ds, g.N, Ho, Wo, cout_ds, 1, p)) return -1;
         set_weights(&p, 1, wT_ds, g.Cin, cout_ds);
@@ -390,7 +392,7 @@ static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
   }
   VPD_CHECK_CUDA(launch_kernel_cluster(CS, conv_igemm_kernel<BN, CS>, dim3(L.grid),
                                        dim3(kConvThreads), ConvCfg<BN>::kSmemBytes, stream, L.a0,
-                                       L.a1, L.b0, L.b1, L.p));
+                                       L.a1, L.o, L.p));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -405,7 +407,7 @@ static int launch_halo(const ConvLaunch& L, cudaStream_t stream) {
     attr_set = true;
   }
   VPD_CHECK_CUDA(launch_kernel(conv3x3_halo_kernel<CHUNKS>, dim3(L.grid), dim3(kConvThreads),
-                               HaloCfg<CHUNKS>::kSmemBytes, stream, L.a0, L.b0, L.p));
+                               HaloCfg<CHUNKS>::kSmemBytes, stream, L.a0, L.o, L.p));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -420,7 +422,12 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t stream) {
     traced = L0;
     traced.p.trace = g_conv_trace;
   }
-  const ConvLaunch& L = g_conv_trace != nullptr ? traced : L0;
+  static const int dbg_skip = env_int("VPD_DBG_SKIP", 0);
+  if (dbg_skip != 0) {
+    if (g_conv_trace == nullptr) traced = L0;
+    traced.p.dbg = dbg_skip;
+  }
+  const ConvLaunch& L = (g_conv_trace != nullptr || dbg_skip != 0) ? traced : L0;
   if (L.halo == 1) return launch_halo<1>(L, stream);
   if (L.halo == 3) {
     static bool attr_set = false;
@@ -431,7 +438,7 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t stream) {
       attr_set = true;
     }
     VPD_CHECK_CUDA(launch_kernel(conv3x3_halo_stream_kernel<128>, dim3(L.grid), dim3(kConvThreads),
-                                 HaloStreamCfg<128>::kSmemBytes, stream, L.a0, L.b0, L.p));
+                                 HaloStreamCfg<128>::kSmemBytes, stream, L.a0, L.o, L.p));
     VPD_LAUNCHED(1);
     return 0;
   }

@@ -6,7 +6,8 @@
 namespace vpd {
 
 struct ConvLaunch {
-  CUtensorMap a0, a1, b0, b1;
+  CUtensorMap a0, a1;  // activation views read by the taps (tap.src 0 / 1)
+  CUtensorMap o;       // output view written by the TMA tile stores
   ConvParams p;
   int block_n;
   int cluster;  // CTAs per cluster along M (weight multicast)

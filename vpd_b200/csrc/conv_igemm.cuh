@@ -31,7 +31,17 @@ constexpr int kUmmaK = 16;
 constexpr int kMaxTaps = 12;
 constexpr int kEpiWarps = 4;                       // epilogue warps (one per TMEM lane quarter; 8 was slower)
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kConvThreads = 64 + kEpiThreads;     // TMA warp + MMA warp + epilogue warps
+constexpr int kStatWarps = 4;                      // reduction warps (one per 32 tile rows)
+constexpr int kStatThreads = kStatWarps * 32;
+// Three aligned warpgroups so that registers can be re-balanced with setmaxnreg:
+//   warps 0-3: TMA producer (0), MMA issuer (1), two idle warps; warps 4-7: epilogue;
+//   warps 8-11: statistics / store
+constexpr int kEpiWarp0 = 4;
+constexpr int kStatWarp0 = 8;
+constexpr int kEpiThread0 = kEpiWarp0 * 32;
+constexpr int kStatThread0 = kStatWarp0 * 32;
+constexpr int kConvThreads = kStatThread0 + kStatThreads;
+constexpr int kRegsCtl = 64, kRegsEpi = 152, kRegsStat = 232;
 constexpr int kWgradThreads = 192;
 
 struct ConvTap {
@@ -51,7 +61,8 @@ struct ConvParams {
   ConvTap taps[kMaxTaps];
   int batch, out_h, out_w;  // valid extents of the (n, h, w) tile coordinates
   int cout;
-  __nv_bfloat16* out;
+  __nv_bfloat16* out;                 // written through the output tensor map (TMA store)
+  int out_c0, out_d2;                 // channel / parity coordinate offsets of that map's view
   const __nv_bfloat16* residual;      // same addressing as out, or null
   long long out_sn, out_sh, out_sw;   // element strides of out/residual
   const float* scale;                 // [cout] or null
@@ -76,35 +87,24 @@ struct ConvParams {
   // entry / after the dependency wait / first operands landed / last MMA issued /
   // first accumulator ready / epilogue done / exit
   long long* trace;
+  int dbg;  // diagnostics (VPD_DBG_SKIP): bit0 skip the A loads, bit1 skip the B loads, bit2 skip the epilogue body
 };
 VPD_DEVINL void trace_mark(const ConvParams& p, int slot) {
-  if (p.trace != nullptr) p.trace[blockIdx.x * 8 + slot] = clock64();
+  if (p.trace != nullptr) p.trace[blockIdx.x * 16 + slot] = clock64();
 }
 
-// called by the 128 epilogue threads (threadIdx.x in [64,192))
+// Output staging: the epilogue warps write finished 128-pixel x 64-channel SLABS (bf16,
+// 128 B per pixel row, 16-byte chunks XOR-swizzled by row % 8 = the TMA SWIZZLE_128B image)
+// into a small shared-memory ring; the statistics warps reduce / mask them there and one
+// thread sends each slab to global memory with a single TMA tile store.
+constexpr int kSlabBytes = kBlockM * 128;
+constexpr int kStatScratchBytes = 2 * 4 * 3 * 64 * 4;  // conv_stats cross-warp scratch
 template <int BLOCK_N>
-VPD_DEVINL void flush_channel_sums(const ConvParams& p, int ntile, float* s_sum, float* s_sq,
-                                   float* s_x2, bool clear) {
-  for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiThreads) {
-    const int c = ntile * BLOCK_N + i;
-    if (p.stats != nullptr) {
-      atomicAdd(&p.stats[c], static_cast<double>(s_sum[i]));
-      atomicAdd(&p.stats[p.cout + c], static_cast<double>(s_sq[i]));
-    } else {
-      atomicAdd(&p.bsums[0][c], static_cast<double>(s_sum[i]));
-      atomicAdd(&p.bsums[0][p.cout + c], static_cast<double>(s_sq[i]));
-      if (p.bnb > 1) {
-        atomicAdd(&p.bsums[1][c], static_cast<double>(s_sum[i]));
-        atomicAdd(&p.bsums[1][p.cout + c], static_cast<double>(s_x2[i]));
-      }
-    }
-    if (clear) {
-      s_sum[i] = 0.f;
-      s_sq[i] = 0.f;
-      s_x2[i] = 0.f;
-    }
-  }
-}
+struct StageCfg {
+  static constexpr int kSlabs = BLOCK_N / 64;          // slabs per tile
+  static constexpr int kSlots = BLOCK_N == 256 ? 1 : 2;  // ring depth (shared-memory budget)
+  static constexpr int kBytes = kSlots * kSlabBytes;
+};
 
 template <int BLOCK_N>
 struct ConvCfg {
@@ -114,61 +114,32 @@ struct ConvCfg {
   static constexpr int kStages = BLOCK_N == 64 ? 6 : (BLOCK_N == 128 ? 5 : 4);
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 7 * BLOCK_N * 4 + 1024;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + StageCfg<BLOCK_N>::kBytes + kBarBytes + 3 * BLOCK_N * 4 +
+      kStatScratchBytes + 1024;
 };
 
-// Warp transpose-reduce of two 32-wide per-lane vectors: afterwards lane j holds in
-// a[0] / b[0] the totals of column j over the warp's 32 rows (31 shuffles each).
-VPD_DEVINL void warp_colsum2(float (&a)[32], float (&b)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const float ka = up ? a[i + o] : a[i];
-      const float sa = up ? a[i] : a[i + o];
-      a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, o);
-      const float kb = up ? b[i + o] : b[i];
-      const float sb = up ? b[i] : b[i + o];
-      b[i] = kb + __shfl_xor_sync(0xffffffffu, sb, o);
-    }
-  }
-}
-struct ConvParams;
-template <int BLOCK_N>
-VPD_DEVINL void flush_channel_sums(const ConvParams& p, int ntile, float* s_sum, float* s_sq,
-                                   float* s_x2, bool clear);
-
-VPD_DEVINL void warp_colsum1(float (&a)[32], int lane) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const bool up = (lane & o) != 0;
-#pragma unroll
-    for (int i = 0; i < o; ++i) {
-      const float ka = up ? a[i + o] : a[i];
-      const float sa = up ? a[i] : a[i + o];
-      a[i] = ka + __shfl_xor_sync(0xffffffffu, sa, o);
-    }
-  }
-}
-
-// Epilogue shared by the implicit-GEMM kernels: executed by warps 2..5 (threads
-// 64..191); drains the TMEM accumulator stages tile by tile.
+// Epilogue, warps 2..5 (threads 64..191): drains the TMEM accumulator stages tile by tile -
+// optional folded-BN affine, residual, ReLU - and writes bf16 slabs to the staging ring.
+// It performs no reductions and no global stores.
 template <int BLOCK_N, int CS>
 VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
-                              uint64_t* tempty_bar, float* s_sum, float* s_sq, float* s_x2,
-                              float* s_bn, int rank, int first_item, int item_stride,
+                              uint64_t* tempty_bar, uint8_t* slabs, uint64_t* sfull,
+                              uint64_t* sempty, int rank, int first_item, int item_stride,
                               int total_tiles, int warp, int lane) {
-  // ---------------------------------------------------------------- epilogue
+  using SC = StageCfg<BLOCK_N>;
   // pair mode (CS == 2): the leader's MMA thread owns the accumulator hand-shake, so the
   // peer's epilogue warps release the TMEM stage on the LEADER's barrier
   const uint32_t tempty_remote0 =
       (CS == 2 && rank == 1) ? mapa_shared(smem_u32(&tempty_bar[0]), 0) : 0u;
   const int q = warp & 3;       // TMEM lane quarter this warp may access
   const int r = q * 32 + lane;  // row of the 128-row tile
+  const uint32_t row_addr = smem_u32(slabs) + r * 128;
+  const uint32_t rsw = static_cast<uint32_t>(r & 7);
   int as = 0;
   uint32_t aphase = 0;
-  int cur_ntile = -1;
+  int slot = 0;
+  uint32_t sphase = 0;
   for (int tile = first_item; tile < total_tiles; tile += item_stride) {
     const int n_tile = tile % p.n_tiles;
     int mt = (tile / p.n_tiles) * CS + rank;
@@ -182,194 +153,357 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
     const bool valid = (n < p.batch) && (h < p.out_h) && (w < p.out_w);
     const long long off = n * p.out_sn + h * p.out_sh + w * p.out_sw + n_tile * BLOCK_N;
 
-    if ((p.stats != nullptr || p.bnb > 0) && cur_ntile != n_tile) {
-      // flush per-CTA channel sums when the channel block changes
-      // (named barrier over the 4 epilogue warps only)
-      if (cur_ntile >= 0) {
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-        flush_channel_sums<BLOCK_N>(p, cur_ntile, s_sum, s_sq, s_x2, true);
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      }
-      cur_ntile = n_tile;
-      if (p.bnb > 0) {
-        for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiThreads) {
-          const int ch = n_tile * BLOCK_N + i;
-          s_bn[i] = __ldg(p.bmean[0] + ch);
-          s_bn[BLOCK_N + i] = __ldg(p.brstd[0] + ch);
-          if (p.bnb > 1) {
-            s_bn[2 * BLOCK_N + i] = __ldg(p.bmean[1] + ch);
-            s_bn[3 * BLOCK_N + i] = __ldg(p.brstd[1] + ch);
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-      }
-    }
-
     mbar_wait(&tfull_bar[as], aphase);
-    if (tile == first_item && threadIdx.x == 64) trace_mark(p, 5);
+    if (tile == first_item && threadIdx.x == kEpiThread0) trace_mark(p, 5);
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N / 32; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
-      // issue every global load of this chunk before waiting on anything, so the
-      // TMEM read and the (up to four) 64-byte row segments are all in flight together
-      const bool do_res = p.residual != nullptr && valid;
-      const bool do_bn = p.bnb > 0 && valid;
-      uint4 rres[4], rz[4], ry0[4], ry1[4];
-      if (do_res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
+    for (int j = 0; j < SC::kSlabs; ++j) {
+      mbar_wait(&sempty[slot], sphase ^ 1);  // the slab's previous contents have been stored
+      const uint32_t dst = row_addr + slot * kSlabBytes;
+#pragma unroll 1
+      for (int cc = 0; cc < ((p.dbg & 4) ? 0 : 2); ++cc) {
+        const int c = 2 * j + cc;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
+        const bool do_res = p.residual != nullptr && valid;
+        uint4 rres[4];
+        if (do_res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) rres[j] = rp[j];  // plain load: residual may alias out
-      }
-      if (do_bn) {
-        const uint4* zp = reinterpret_cast<const uint4*>(p.bz + off + c * 32);
-        const uint4* yp = reinterpret_cast<const uint4*>(p.by[0] + off + c * 32);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) rz[j] = __ldg(zp + j);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) ry0[j] = __ldg(yp + j);
-        if (p.bnb > 1) {
-          const uint4* y1p = reinterpret_cast<const uint4*>(p.by[1] + off + c * 32);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ry1[j] = __ldg(y1p + j);
+          for (int k = 0; k < 4; ++k) rres[k] = rp[k];  // plain load: residual may alias out
         }
-      }
-      tmem_ld_wait();
-      float f[32];
+        tmem_ld_wait();
+        float f[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      const int ch0 = n_tile * BLOCK_N + c * 32;
-      if (p.scale != nullptr) {
+        for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
+        const int ch0 = n_tile * BLOCK_N + c * 32;
+        if (p.scale != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + j));
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch0 + j));
-          f[j + 0] = fmaf(f[j + 0], sc.x, sh.x);
-          f[j + 1] = fmaf(f[j + 1], sc.y, sh.y);
-          f[j + 2] = fmaf(f[j + 2], sc.z, sh.z);
-          f[j + 3] = fmaf(f[j + 3], sc.w, sh.w);
-        }
-      }
-      if (do_res) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          f[8 * j + 0] += bf16_lo(rres[j].x);
-          f[8 * j + 1] += bf16_hi(rres[j].x);
-          f[8 * j + 2] += bf16_lo(rres[j].y);
-          f[8 * j + 3] += bf16_hi(rres[j].y);
-          f[8 * j + 4] += bf16_lo(rres[j].z);
-          f[8 * j + 5] += bf16_hi(rres[j].z);
-          f[8 * j + 6] += bf16_lo(rres[j].w);
-          f[8 * j + 7] += bf16_hi(rres[j].w);
-        }
-      }
-      if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-      }
-      if (do_bn) {  // g = dz * 1[z > 0]
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          f[8 * j + 0] = bf16_lo(rz[j].x) > 0.f ? f[8 * j + 0] : 0.f;
-          f[8 * j + 1] = bf16_hi(rz[j].x) > 0.f ? f[8 * j + 1] : 0.f;
-          f[8 * j + 2] = bf16_lo(rz[j].y) > 0.f ? f[8 * j + 2] : 0.f;
-          f[8 * j + 3] = bf16_hi(rz[j].y) > 0.f ? f[8 * j + 3] : 0.f;
-          f[8 * j + 4] = bf16_lo(rz[j].z) > 0.f ? f[8 * j + 4] : 0.f;
-          f[8 * j + 5] = bf16_hi(rz[j].z) > 0.f ? f[8 * j + 5] : 0.f;
-          f[8 * j + 6] = bf16_lo(rz[j].w) > 0.f ? f[8 * j + 6] : 0.f;
-          f[8 * j + 7] = bf16_hi(rz[j].w) > 0.f ? f[8 * j + 7] : 0.f;
-        }
-      }
-      uint32_t pk[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-      if (valid) {
-        uint4* op = reinterpret_cast<uint4*>(p.out + off + c * 32);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          stg_v4(op + j, make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]));
-      }
-      if (p.stats != nullptr) {
-        // statistics of the values as stored (bf16-rounded); invalid rows = 0
-        float s[32], s2[32];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float a = valid ? bf16_lo(pk[j]) : 0.f;
-          const float b = valid ? bf16_hi(pk[j]) : 0.f;
-          s[2 * j] = a;
-          s[2 * j + 1] = b;
-          s2[2 * j] = a * a;
-          s2[2 * j + 1] = b * b;
-        }
-        warp_colsum2(s, s2, lane);
-        red_shared_add(smem_u32(s_sum + c * 32 + lane), s[0]);
-        red_shared_add(smem_u32(s_sq + c * 32 + lane), s2[0]);
-      }
-      if (p.bnb > 0) {
-        // sum g and sum g*xhat of the stored (bf16-rounded) masked gradient
-        float g[32], gx[32];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          g[2 * j] = valid ? bf16_lo(pk[j]) : 0.f;
-          g[2 * j + 1] = valid ? bf16_hi(pk[j]) : 0.f;
-        }
-        const uint32_t sbn = smem_u32(s_bn + c * 32);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float4 m0 = __uint4_as_float4(lds_v4(sbn + 32 * j));
-          const float4 m1 = __uint4_as_float4(lds_v4(sbn + 32 * j + 16));
-          const float4 r0 = __uint4_as_float4(lds_v4(sbn + 4 * BLOCK_N + 32 * j));
-          const float4 r1 = __uint4_as_float4(lds_v4(sbn + 4 * BLOCK_N + 32 * j + 16));
-          gx[8 * j + 0] = do_bn ? g[8 * j + 0] * ((bf16_lo(ry0[j].x) - m0.x) * r0.x) : 0.f;
-          gx[8 * j + 1] = do_bn ? g[8 * j + 1] * ((bf16_hi(ry0[j].x) - m0.y) * r0.y) : 0.f;
-          gx[8 * j + 2] = do_bn ? g[8 * j + 2] * ((bf16_lo(ry0[j].y) - m0.z) * r0.z) : 0.f;
-          gx[8 * j + 3] = do_bn ? g[8 * j + 3] * ((bf16_hi(ry0[j].y) - m0.w) * r0.w) : 0.f;
-          gx[8 * j + 4] = do_bn ? g[8 * j + 4] * ((bf16_lo(ry0[j].z) - m1.x) * r1.x) : 0.f;
-          gx[8 * j + 5] = do_bn ? g[8 * j + 5] * ((bf16_hi(ry0[j].z) - m1.y) * r1.y) : 0.f;
-          gx[8 * j + 6] = do_bn ? g[8 * j + 6] * ((bf16_lo(ry0[j].w) - m1.z) * r1.z) : 0.f;
-          gx[8 * j + 7] = do_bn ? g[8 * j + 7] * ((bf16_hi(ry0[j].w) - m1.w) * r1.w) : 0.f;
-        }
-        if (p.bnb > 1) {
-          float gx1[32];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 m0 = __uint4_as_float4(lds_v4(sbn + 8 * BLOCK_N + 32 * j));
-            const float4 m1 = __uint4_as_float4(lds_v4(sbn + 8 * BLOCK_N + 32 * j + 16));
-            const float4 r0 = __uint4_as_float4(lds_v4(sbn + 12 * BLOCK_N + 32 * j));
-            const float4 r1 = __uint4_as_float4(lds_v4(sbn + 12 * BLOCK_N + 32 * j + 16));
-            gx1[8 * j + 0] = do_bn ? g[8 * j + 0] * ((bf16_lo(ry1[j].x) - m0.x) * r0.x) : 0.f;
-            gx1[8 * j + 1] = do_bn ? g[8 * j + 1] * ((bf16_hi(ry1[j].x) - m0.y) * r0.y) : 0.f;
-            gx1[8 * j + 2] = do_bn ? g[8 * j + 2] * ((bf16_lo(ry1[j].y) - m0.z) * r0.z) : 0.f;
-            gx1[8 * j + 3] = do_bn ? g[8 * j + 3] * ((bf16_hi(ry1[j].y) - m0.w) * r0.w) : 0.f;
-            gx1[8 * j + 4] = do_bn ? g[8 * j + 4] * ((bf16_lo(ry1[j].z) - m1.x) * r1.x) : 0.f;
-            gx1[8 * j + 5] = do_bn ? g[8 * j + 5] * ((bf16_hi(ry1[j].z) - m1.y) * r1.y) : 0.f;
-            gx1[8 * j + 6] = do_bn ? g[8 * j + 6] * ((bf16_lo(ry1[j].w) - m1.z) * r1.z) : 0.f;
-            gx1[8 * j + 7] = do_bn ? g[8 * j + 7] * ((bf16_hi(ry1[j].w) - m1.w) * r1.w) : 0.f;
+          for (int k = 0; k < 32; k += 4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + k));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch0 + k));
+            f[k + 0] = fmaf(f[k + 0], sc.x, sh.x);
+            f[k + 1] = fmaf(f[k + 1], sc.y, sh.y);
+            f[k + 2] = fmaf(f[k + 2], sc.z, sh.z);
+            f[k + 3] = fmaf(f[k + 3], sc.w, sh.w);
           }
-          warp_colsum1(gx1, lane);
-          red_shared_add(smem_u32(s_x2 + c * 32 + lane), gx1[0]);
         }
-        warp_colsum2(g, gx, lane);
-        red_shared_add(smem_u32(s_sum + c * 32 + lane), g[0]);
-        red_shared_add(smem_u32(s_sq + c * 32 + lane), gx[0]);
+        if (do_res) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            f[8 * k + 0] += bf16_lo(rres[k].x);
+            f[8 * k + 1] += bf16_hi(rres[k].x);
+            f[8 * k + 2] += bf16_lo(rres[k].y);
+            f[8 * k + 3] += bf16_hi(rres[k].y);
+            f[8 * k + 4] += bf16_lo(rres[k].z);
+            f[8 * k + 5] += bf16_hi(rres[k].z);
+            f[8 * k + 6] += bf16_lo(rres[k].w);
+            f[8 * k + 7] += bf16_hi(rres[k].w);
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
+        }
+        if (!valid) {  // rows outside the tensor: clipped by the store, zero for the sums
+#pragma unroll
+          for (int k = 0; k < 32; ++k) f[k] = 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          sts_v4(dst + (((static_cast<uint32_t>(cc * 4 + k)) ^ rsw) << 4),
+                 make_uint4(pack_bf16x2(f[8 * k + 0], f[8 * k + 1]),
+                            pack_bf16x2(f[8 * k + 2], f[8 * k + 3]),
+                            pack_bf16x2(f[8 * k + 4], f[8 * k + 5]),
+                            pack_bf16x2(f[8 * k + 6], f[8 * k + 7])));
       }
-    }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-      if (CS == 2 && rank == 1) mbar_arrive_remote(tempty_remote0 + as * 8);
-      else mbar_arrive(&tempty_bar[as]);
+      if (j == SC::kSlabs - 1) {
+        // accumulator fully read: hand the TMEM stage back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (CS == 2 && rank == 1) mbar_arrive_remote(tempty_remote0 + as * 8);
+          else mbar_arrive(&tempty_bar[as]);
+        }
+      }
+      fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
+      mbar_arrive(&sfull[slot]);
+      if (++slot == SC::kSlots) {
+        slot = 0;
+        sphase ^= 1;
+      }
     }
     if (++as == 2) {
       as = 0;
       aphase ^= 1;
     }
   }
-  if ((p.stats != nullptr || p.bnb > 0) && cur_ntile >= 0) {
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-    flush_channel_sums<BLOCK_N>(p, cur_ntile, s_sum, s_sq, s_x2, false);
+}
+
+// Statistics / store warps (warps 6..9, threads 192..319). For every staged slab:
+//   forward train (p.stats):  sum y, sum y^2 per channel  -> BatchNorm batch statistics
+//   dgrad (p.bnb):  the slab holds dz of a ReLU->BN stage; mask it in place with 1[z > 0]
+//                   (so the stored tensor is g) and accumulate sum g and sum g*(y - mean)
+//                   for up to two BN branches               -> fused BN-backward reduction
+// always on the stored (bf16-rounded) values; then ONE thread issues the slab's TMA tile
+// store. A lane owns eight consecutive channels and the four row groups of a warp
+// instruction cover whole 128-byte rows, so every shared / global access is fully
+// coalesced; the z / y rows of the NEXT slab are requested before the current one is
+// reduced, so their latency hides behind a whole slab period. Cross-warp totals are
+// combined through a small double-buffered scratch with exclusive owners (no shared-memory
+// float atomics: those are CAS loops) and reach the fp64 global accumulators when the
+// channel block changes and at the end.
+template <int BLOCK_N, int CS>
+VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out, uint8_t* slabs,
+                           uint64_t* sfull, uint64_t* sempty, float* s_sum, float* s_sq,
+                           float* s_x2, float* s_scr, int rank, int first_item, int item_stride,
+                           int total_tiles, int sw, int lane) {
+  using SC = StageCfg<BLOCK_N>;
+  const int cg = lane & 7;     // 16-byte chunk (8 channels) of the 128-byte slab row
+  const int rsub = lane >> 3;  // row within the 4 rows one warp instruction covers
+  const int ltw = __ffs(p.tw) - 1, lth = __ffs(p.th) - 1;  // tile extents are powers of two
+  const int nbr = p.bnb;
+  const bool fwd_stats = p.stats != nullptr;
+  const bool sums = fwd_stats || nbr > 0;
+  const bool live = !(p.dbg & (4 | 16));
+  const int st = threadIdx.x - kStatThread0;  // 0..127
+  float a0[8], a1[8], a2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a0[k] = a1[k] = a2[k] = 0.f;
+
+  // this warp's register sums -> scratch[par][sw][q][64] (lanes 8 apart hold the same channels)
+  auto regs_to_scratch = [&](int par) {
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a0[k] += __shfl_xor_sync(0xffffffffu, a0[k], o);
+        a1[k] += __shfl_xor_sync(0xffffffffu, a1[k], o);
+        if (nbr > 1) a2[k] += __shfl_xor_sync(0xffffffffu, a2[k], o);
+      }
+    }
+    if (lane < 8) {
+      const uint32_t base = smem_u32(s_scr + ((par * kStatWarps + sw) * 3) * 64 + cg * 8);
+      sts_v4(base, make_uint4(__float_as_uint(a0[0]), __float_as_uint(a0[1]),
+                              __float_as_uint(a0[2]), __float_as_uint(a0[3])));
+      sts_v4(base + 16, make_uint4(__float_as_uint(a0[4]), __float_as_uint(a0[5]),
+                                   __float_as_uint(a0[6]), __float_as_uint(a0[7])));
+      sts_v4(base + 256, make_uint4(__float_as_uint(a1[0]), __float_as_uint(a1[1]),
+                                    __float_as_uint(a1[2]), __float_as_uint(a1[3])));
+      sts_v4(base + 256 + 16, make_uint4(__float_as_uint(a1[4]), __float_as_uint(a1[5]),
+                                         __float_as_uint(a1[6]), __float_as_uint(a1[7])));
+      if (nbr > 1) {
+        sts_v4(base + 512, make_uint4(__float_as_uint(a2[0]), __float_as_uint(a2[1]),
+                                      __float_as_uint(a2[2]), __float_as_uint(a2[3])));
+        sts_v4(base + 512 + 16, make_uint4(__float_as_uint(a2[4]), __float_as_uint(a2[5]),
+                                           __float_as_uint(a2[6]), __float_as_uint(a2[7])));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a0[k] = a1[k] = a2[k] = 0.f;
+  };
+  // after a barrier: scratch[par] of the four warps -> per-CTA sums of slab j. Thread st
+  // owns channel st % 64 of quantity 0 / 2 (st < 64) or 1 (st >= 64): plain read-modify-write
+  auto combine = [&](int j, int par) {
+    const int c = st & 63;
+    const float* scr = s_scr + par * kStatWarps * 3 * 64 + c;
+    if (st < 64) {
+      s_sum[j * 64 + c] += scr[0] + scr[3 * 64] + scr[6 * 64] + scr[9 * 64];
+      if (nbr > 1)
+        s_x2[j * 64 + c] += scr[2 * 64] + scr[5 * 64] + scr[8 * 64] + scr[11 * 64];
+    } else {
+      s_sq[j * 64 + c] += scr[64] + scr[4 * 64] + scr[7 * 64] + scr[10 * 64];
+    }
+  };
+  // per-CTA sums -> fp64 global accumulators (N == 64 keeps its sums in registers until here)
+  auto global_flush = [&](int ntile) {
+    if (BLOCK_N == 64) {
+      regs_to_scratch(0);
+      asm volatile("bar.sync 2, %0;" ::"n"(kStatThreads) : "memory");
+      combine(0, 0);
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(kStatThreads) : "memory");
+    for (int i = st; i < BLOCK_N; i += kStatThreads) {
+      const int c = ntile * BLOCK_N + i;
+      if (fwd_stats) {
+        atomicAdd(&p.stats[c], static_cast<double>(s_sum[i]));
+        atomicAdd(&p.stats[p.cout + c], static_cast<double>(s_sq[i]));
+      } else {
+        // sum g * xhat = rstd * sum g * (y - mean)
+        atomicAdd(&p.bsums[0][c], static_cast<double>(s_sum[i]));
+        atomicAdd(&p.bsums[0][p.cout + c],
+                  static_cast<double>(s_sq[i]) * static_cast<double>(__ldg(p.brstd[0] + c)));
+        if (nbr > 1) {
+          atomicAdd(&p.bsums[1][c], static_cast<double>(s_sum[i]));
+          atomicAdd(&p.bsums[1][p.cout + c],
+                    static_cast<double>(s_x2[i]) * static_cast<double>(__ldg(p.brstd[1] + c)));
+        }
+      }
+      s_sum[i] = 0.f;
+      s_sq[i] = 0.f;
+      s_x2[i] = 0.f;
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(kStatThreads) : "memory");
+  };
+
+  // ---- prefetched operands of the fused BN backward: this warp's 32 rows of z, y0 (, y1)
+  // element offset of row i of this lane inside a tile (tile-invariant)
+  int rel[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = sw * 32 + i * 4 + rsub;
+    rel[i] = static_cast<int>((r >> (ltw + lth)) * p.out_sn + ((r >> ltw) & (p.th - 1)) * p.out_sh +
+                              (r & (p.tw - 1)) * p.out_sw);
   }
+  uint4 zz[8], y0[8], y1[8];
+  float m0[8], m1[8];
+  auto issue_loads = [&](int n_tile, int w0, int h0, int b0, int j) {
+    const int ch = n_tile * BLOCK_N + j * 64 + cg * 8;
+    const long long base = b0 * p.out_sn + h0 * p.out_sh + w0 * p.out_sw + ch;
+    const bool full = (b0 + p.tn <= p.batch) && (h0 + p.th <= p.out_h) && (w0 + p.tw <= p.out_w);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      bool ok = full;
+      if (!full) {
+        const int r = sw * 32 + i * 4 + rsub;
+        ok = (b0 + (r >> (ltw + lth)) < p.batch) && (h0 + ((r >> ltw) & (p.th - 1)) < p.out_h) &&
+             (w0 + (r & (p.tw - 1)) < p.out_w);
+      }
+      // rows outside the tensor hold g = 0 in the slab: any finite operand will do
+      const long long off = ok ? base + rel[i] : static_cast<long long>(ch);
+      zz[i] = ldg_nc_v4(p.bz + off);
+      y0[i] = ldg_nc_v4(p.by[0] + off);
+      if (nbr > 1) y1[i] = ldg_nc_v4(p.by[1] + off);
+    }
+    const float4 ma = __ldg(reinterpret_cast<const float4*>(p.bmean[0] + ch));
+    const float4 mb = __ldg(reinterpret_cast<const float4*>(p.bmean[0] + ch + 4));
+    m0[0] = ma.x, m0[1] = ma.y, m0[2] = ma.z, m0[3] = ma.w;
+    m0[4] = mb.x, m0[5] = mb.y, m0[6] = mb.z, m0[7] = mb.w;
+    if (nbr > 1) {
+      const float4 mc = __ldg(reinterpret_cast<const float4*>(p.bmean[1] + ch));
+      const float4 md = __ldg(reinterpret_cast<const float4*>(p.bmean[1] + ch + 4));
+      m1[0] = mc.x, m1[1] = mc.y, m1[2] = mc.z, m1[3] = mc.w;
+      m1[4] = md.x, m1[5] = md.y, m1[6] = md.z, m1[7] = md.w;
+    }
+  };
+  auto tile_coords = [&](int tile, int& n_tile, int& w0, int& h0, int& b0) {
+    n_tile = tile % p.n_tiles;
+    int mt = (tile / p.n_tiles) * CS + rank;
+    w0 = (mt % p.tiles_w) * p.tw;
+    mt /= p.tiles_w;
+    h0 = (mt % p.tiles_h) * p.th;
+    b0 = (mt / p.tiles_h) * p.tn;
+  };
+  // shared-memory address of this lane's 16-byte chunk in row i (relative to the slab)
+  uint32_t srow[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = sw * 32 + i * 4 + rsub;
+    srow[i] = r * 128 + ((cg ^ (r & 7)) << 4);
+  }
+
+  int cur_ntile = -1;
+  int slot = 0, prev_slot = -1, par = 0;
+  uint32_t sphase = 0;
+  int tile = first_item, j = 0;
+  bool have = tile < total_tiles;
+  int n_tile = 0, w0 = 0, h0 = 0, b0 = 0;
+  if (have) {
+    tile_coords(tile, n_tile, w0, h0, b0);
+    if (nbr > 0 && live) issue_loads(n_tile, w0, h0, b0, 0);
+  }
+  while (have) {
+    if (sums && cur_ntile != n_tile) {
+      if (cur_ntile >= 0) global_flush(cur_ntile);
+      cur_ntile = n_tile;
+    }
+    mbar_wait(&sfull[slot], sphase);
+    const uint32_t slab = smem_u32(slabs) + slot * kSlabBytes;
+    if (fwd_stats && live) {
+      uint4 g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = lds_v4(slab + srow[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t gw[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float lo = bf16_lo(gw[k]), hi = bf16_hi(gw[k]);
+          a0[2 * k] += lo;
+          a0[2 * k + 1] += hi;
+          a1[2 * k] = fmaf(lo, lo, a1[2 * k]);
+          a1[2 * k + 1] = fmaf(hi, hi, a1[2 * k + 1]);
+        }
+      }
+    } else if (nbr > 0 && live) {
+      uint4 g[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g[i] = lds_v4(slab + srow[i]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint32_t gw[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
+        const uint32_t zw[4] = {zz[i].x, zz[i].y, zz[i].z, zz[i].w};
+        const uint32_t yw[4] = {y0[i].x, y0[i].y, y0[i].z, y0[i].w};
+        const uint32_t y1w[4] = {y1[i].x, y1[i].y, y1[i].z, y1[i].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          gw[k] &= bf16x2_gt0_mask(zw[k]);  // g = dz * 1[z > 0]
+          const float lo = bf16_lo(gw[k]), hi = bf16_hi(gw[k]);
+          a0[2 * k] += lo;
+          a0[2 * k + 1] += hi;
+          a1[2 * k] = fmaf(lo, bf16_lo(yw[k]) - m0[2 * k], a1[2 * k]);
+          a1[2 * k + 1] = fmaf(hi, bf16_hi(yw[k]) - m0[2 * k + 1], a1[2 * k + 1]);
+          if (nbr > 1) {
+            a2[2 * k] = fmaf(lo, bf16_lo(y1w[k]) - m1[2 * k], a2[2 * k]);
+            a2[2 * k + 1] = fmaf(hi, bf16_hi(y1w[k]) - m1[2 * k + 1], a2[2 * k + 1]);
+          }
+        }
+        g[i] = make_uint4(gw[0], gw[1], gw[2], gw[3]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sts_v4(slab + srow[i], g[i]);
+      fence_proxy_async();
+    }
+    // store coordinates of the slab just processed
+    const int st_c = p.out_c0 + n_tile * BLOCK_N + j * 64, st_w = w0, st_h = h0, st_b = b0;
+    const int cur_j = j;
+    // advance, and request the next slab's operands before anything else
+    if (++j == SC::kSlabs) {
+      j = 0;
+      tile += item_stride;
+      have = tile < total_tiles;
+      if (have) tile_coords(tile, n_tile, w0, h0, b0);
+    }
+    if (have && nbr > 0 && live) issue_loads(n_tile, w0, h0, b0, j);
+    if (sums && BLOCK_N > 64) regs_to_scratch(par);
+    // every statistics thread is done with the slab (and its masked rewrite is visible)
+    asm volatile("bar.sync 2, %0;" ::"n"(kStatThreads) : "memory");
+    if (sums && BLOCK_N > 64) {
+      combine(cur_j, par);
+      par ^= 1;
+    }
+    if (st == 0) {
+      if (!(p.dbg & (4 | 8)))
+        tma_store_5d(tm_out, slabs + slot * kSlabBytes, st_c, st_w, p.out_d2, st_h, st_b);
+      bulk_commit_group();
+      if (SC::kSlots > 1) {
+        // release the slot of the PREVIOUS slab: its store has finished reading shared memory
+        // once at most one group (the one just committed) is still pending
+        bulk_wait_read1();
+        if (prev_slot >= 0) mbar_arrive(&sempty[prev_slot]);
+        prev_slot = slot;
+      } else {
+        bulk_wait_read0();
+        mbar_arrive(&sempty[slot]);
+      }
+    }
+    if (++slot == SC::kSlots) {
+      slot = 0;
+      sphase ^= 1;
+    }
+  }
+  if (sums && cur_ntile >= 0) global_flush(cur_ntile);
+  if (st == 0) bulk_wait0();  // all tile stores performed before the CTA exits
 }
 
 // CS = 2: PAIR mode (tcgen05 cta_group::2). The two CTAs of a cluster own two adjacent
@@ -383,23 +517,25 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 template <int BLOCK_N, int CS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
-                  const __grid_constant__ ConvParams p) {
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* slabs = smem + Cfg::kStages * Cfg::kStageBytes;  // output staging ring
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + StageCfg<BLOCK_N>::kBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* pfull_bar = tempty_bar + 2;  // leader only: "the peer's stage has landed"
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pfull_bar + Cfg::kStages);
-  float* s_sum = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kBarBytes);
+  uint64_t* sfull_bar = pfull_bar + Cfg::kStages;  // epilogue -> statistics warps: slab staged
+  uint64_t* sempty_bar = sfull_bar + 2;            // slab stored, slot free
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sempty_bar + 2);
+  float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + Cfg::kBarBytes);
   float* s_sq = s_sum + BLOCK_N;
   float* s_x2 = s_sq + BLOCK_N;  // second BN branch (fused backward reduction)
-  float* s_bn = s_x2 + BLOCK_N;  // [mean0 | rstd0 | mean1 | rstd1] of the current channel block
+  float* s_scr = s_x2 + BLOCK_N;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -413,10 +549,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], CS * kEpiWarps);  // pair mode: both CTAs' epilogue warps
+      mbar_init(&sfull_bar[s], kEpiThreads);
+      mbar_init(&sempty_bar[s], 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmB0);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1) {
     if (CS == 2) {
@@ -436,7 +574,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (threadIdx.x == 0 && p.trace != nullptr) {
     unsigned long long g;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
-    p.trace[blockIdx.x * 8] = static_cast<long long>(g);
+    p.trace[blockIdx.x * 16] = static_cast<long long>(g);
     trace_mark(p, 1);
   }
   pdl_wait();  // everything above overlapped the previous kernel's tail
@@ -450,7 +588,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int first_item = blockIdx.x / CS;
   const int item_stride = gridDim.x / CS;
 
-  if (warp == 0) {
+  if (warp >= kStatWarp0) {
+    setmaxnreg_inc<kRegsStat>();
+    conv_stats<BLOCK_N, CS>(p, &tmOut, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, rank,
+                            first_item, item_stride, total_tiles, warp - kStatWarp0, lane);
+  } else if (warp >= kEpiWarp0) {
+    setmaxnreg_dec<kRegsEpi>();
+    conv_epilogue<BLOCK_N, CS>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
+                               rank, first_item, item_stride, total_tiles, warp, lane);
+  } else {
+   setmaxnreg_dec<kRegsCtl>();
+   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (elect_one()) {
       int stage = 0;
@@ -465,16 +613,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int t = 0; t < p.num_taps; ++t) {
           const ConvTap tap = p.taps[t];
           const CUtensorMap* ma = tap.src ? &tmA1 : &tmA0;
-          const CUtensorMap* mb = tap.src ? &tmB1 : &tmB0;
           for (int kc = 0; kc < tap.kchunks; ++kc) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * Cfg::kStageBytes;
             uint8_t* sb = sa + Cfg::kABytes;
-            mbar_expect_tx(&full_bar[stage], Cfg::kABytes + Cfg::kBBytes / CS);
-            tma_load_5d(sa, ma, &full_bar[stage], tap.c0 + kc * kBlockK, w0 + tap.d1, tap.d2,
-                        h0 + tap.d3, b0);
+            mbar_expect_tx(&full_bar[stage], ((p.dbg & 1) ? 0 : Cfg::kABytes) +
+                                                 ((p.dbg & 2) ? 0 : Cfg::kBBytes / CS));
+            if (!(p.dbg & 1))
+              tma_load_5d(sa, ma, &full_bar[stage], tap.c0 + kc * kBlockK, w0 + tap.d1, tap.d2,
+                          h0 + tap.d3, b0);
             // this CTA's share of the weight tile: BLOCK_N / CS rows
-            bulk_load(sb,
+            if (!(p.dbg & 2))
+              bulk_load(sb,
                       p.w[tap.src] + ((size_t)(tap.btap * p.w_kc[tap.src] + kc) * p.w_rb[tap.src] +
                                       n_tile * (BLOCK_N / 64) + rank * (BLOCK_N / 64 / CS)) * 4096,
                       Cfg::kBBytes / CS, &full_bar[stage]);
@@ -549,12 +699,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         }
       }
     }
-  } else {
-    conv_epilogue<BLOCK_N, CS>(p, tmem_base, tfull_bar, tempty_bar, s_sum, s_sq, s_x2, s_bn, rank,
-                               first_item, item_stride, total_tiles, warp, lane);
+   }
   }
 
-  if (threadIdx.x == 64) trace_mark(p, 6);
+  if (threadIdx.x == kEpiThread0) trace_mark(p, 6);
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) trace_mark(p, 7);
@@ -590,15 +738,17 @@ struct HaloCfg {
   static constexpr int kPatchBytes = kPatchRows * 128;               // 23040
   static constexpr int kPatchSlot = (kPatchBytes + 1023) & ~1023;    // 23552
   static constexpr int kWBytes = 9 * CHUNKS * kBlockN * 128;         // resident weights
-  static constexpr int kSlots = CHUNKS == 1 ? 5 : 3;                 // patch ring (per chunk)
+  static constexpr int kSlots = CHUNKS == 1 ? 4 : 3;                 // patch ring (per chunk)
   static constexpr int kTmemCols = 2 * kBlockN;
   static constexpr int kBarBytes = 1024;
-  static constexpr int kSmemBytes = kWBytes + kSlots * kPatchSlot + kBarBytes + 7 * kBlockN * 4 + 1024;
+  static constexpr int kSmemBytes =
+      kWBytes + kSlots * kPatchSlot + StageCfg<kBlockN>::kBytes + kBarBytes + 3 * kBlockN * 4 +
+      kStatScratchBytes + 1024;
 };
 
 template <int CHUNKS>
 __global__ void __launch_bounds__(kConvThreads, 1)
-conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ ConvParams p) {
   using Cfg = HaloCfg<CHUNKS>;
   constexpr int BLOCK_N = Cfg::kBlockN;
@@ -608,16 +758,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* s_w = smem;                         // [chunk][tap][64 cout][64 cin] bf16, swizzled
   uint8_t* s_patch = smem + Cfg::kWBytes;      // kSlots x kPatchSlot
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_patch + Cfg::kSlots * Cfg::kPatchSlot);
+  uint8_t* slabs = s_patch + Cfg::kSlots * Cfg::kPatchSlot;  // output staging ring
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + StageCfg<BLOCK_N>::kBytes);
   uint64_t* empty_bar = full_bar + Cfg::kSlots;
   uint64_t* tfull_bar = empty_bar + Cfg::kSlots;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* w_bar = tempty_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* sfull_bar = w_bar + 1;
+  uint64_t* sempty_bar = sfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sempty_bar + 2);
   float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + Cfg::kBarBytes);
   float* s_sq = s_sum + BLOCK_N;
   float* s_x2 = s_sq + BLOCK_N;
-  float* s_bn = s_x2 + BLOCK_N;
+  float* s_scr = s_x2 + BLOCK_N;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -629,11 +782,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&sfull_bar[s], kEpiThreads);
+      mbar_init(&sempty_bar[s], 1);
     }
     mbar_init(w_bar, 1);
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);
@@ -651,7 +806,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // the channel block of a CTA is fixed (host: gridDim.x % n_tiles == 0)
   const int my_ntile = blockIdx.x % p.n_tiles;
 
-  if (warp == 0) {
+  if (warp >= kStatWarp0) {
+    setmaxnreg_inc<kRegsStat>();
+    conv_stats<BLOCK_N, 1>(p, &tmOut, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
+                           blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
+  } else if (warp >= kEpiWarp0) {
+    setmaxnreg_dec<kRegsEpi>();
+    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar, 0,
+                              blockIdx.x, gridDim.x, total_tiles, warp, lane);
+  } else {
+   setmaxnreg_dec<kRegsCtl>();
+   if (warp == 0) {
     if (elect_one()) {
       // resident weights of this CTA's channel block: CHUNKS x 9 boxes {64 cin, 64 cout, 1}
       mbar_expect_tx(w_bar, Cfg::kWBytes);
@@ -720,9 +885,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
-  } else {
-    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, s_sum, s_sq, s_x2, s_bn, 0,
-                              blockIdx.x, gridDim.x, total_tiles, warp, lane);
+   }
   }
   tc_fence_before();
   __syncthreads();
@@ -745,13 +908,14 @@ struct HaloStreamCfg {
   static constexpr int kTmemCols = 2 * BLOCK_N;
   static constexpr int kBarBytes = 1024;
   static constexpr int kSmemBytes =
-      kWStages * kWTile + kSlots * kPatchSlot + kBarBytes + 7 * BLOCK_N * 4 + 1024;
+      kWStages * kWTile + kSlots * kPatchSlot + StageCfg<BLOCK_N>::kBytes + kBarBytes +
+      3 * BLOCK_N * 4 + kStatScratchBytes + 1024;
 };
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
-                           const __grid_constant__ CUtensorMap tmB,
+                           const __grid_constant__ CUtensorMap tmOut,
                            const __grid_constant__ ConvParams p) {
   using Cfg = HaloStreamCfg<BLOCK_N>;
   pdl_trigger();
@@ -760,17 +924,20 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
                                              ~static_cast<uintptr_t>(1023));
   uint8_t* s_w = smem;                                   // kWStages x [BLOCK_N][64]
   uint8_t* s_patch = smem + Cfg::kWStages * Cfg::kWTile;  // kSlots x kPatchSlot
-  uint64_t* pfull = reinterpret_cast<uint64_t*>(s_patch + Cfg::kSlots * Cfg::kPatchSlot);
+  uint8_t* slabs = s_patch + Cfg::kSlots * Cfg::kPatchSlot;  // output staging ring
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(slabs + StageCfg<BLOCK_N>::kBytes);
   uint64_t* pempty = pfull + Cfg::kSlots;
   uint64_t* wfull = pempty + Cfg::kSlots;
   uint64_t* wempty = wfull + Cfg::kWStages;
   uint64_t* tfull_bar = wempty + Cfg::kWStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* sfull_bar = tempty_bar + 2;
+  uint64_t* sempty_bar = sfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sempty_bar + 2);
   float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(pfull) + Cfg::kBarBytes);
   float* s_sq = s_sum + BLOCK_N;
   float* s_x2 = s_sq + BLOCK_N;
-  float* s_bn = s_x2 + BLOCK_N;
+  float* s_scr = s_x2 + BLOCK_N;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -786,10 +953,12 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
       mbar_init(&tempty_bar[s], kEpiWarps);
+      mbar_init(&sfull_bar[s], kEpiThreads);
+      mbar_init(&sempty_bar[s], 1);
     }
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);
@@ -806,7 +975,17 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
   const int total_tiles = m_tiles * p.n_tiles;
   const int chunks = p.taps[0].kchunks;
 
-  if (warp == 0) {
+  if (warp >= kStatWarp0) {
+    setmaxnreg_inc<kRegsStat>();
+    conv_stats<BLOCK_N, 1>(p, &tmOut, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
+                           blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
+  } else if (warp >= kEpiWarp0) {
+    setmaxnreg_dec<kRegsEpi>();
+    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar, 0,
+                              blockIdx.x, gridDim.x, total_tiles, warp, lane);
+  } else {
+   setmaxnreg_dec<kRegsCtl>();
+   if (warp == 0) {
     if (elect_one()) {
       int slot = 0, ws = 0;
       uint32_t pphase = 0, wphase = 0;
@@ -885,9 +1064,7 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
         }
       }
     }
-  } else {
-    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, s_sum, s_sq, s_x2, s_bn, 0,
-                              blockIdx.x, gridDim.x, total_tiles, warp, lane);
+   }
   }
   tc_fence_before();
   __syncthreads();
