@@ -38,6 +38,11 @@ def main():
         rstd = torch.ones(Cin, device=dev)
         bs = torch.zeros((2, Cin), device=dev, dtype=torch.float64)
         dgrad = os.environ.get('DIAG_MODE', 'fwd') == 'dgrad'
+        alias = os.environ.get('DIAG_ALIAS', '0')
+        if alias == '1':      # z and y share one tensor (half the unique bytes)
+            yf = z
+        elif alias == '2':    # both alias the conv input (already streamed by TMA)
+            z = yf = x
 
         def run():
             if dgrad:   # Cin == Cout in every case: x doubles as dy, y as dx

@@ -103,8 +103,61 @@ struct Profiler {
 
 typedef void (*BucketFn)(void* user, long long offset, long long count);
 
+// Side stream for the weight gradients. wgrad kernels are tensor-bound and nothing on the
+// backward critical path (BN backward -> dgrad -> BN backward ...) consumes their result, so
+// they run on a second, lower-priority stream and fill the SMs while the memory-bound BN
+// kernels of the main chain are in flight (VPD_WGRAD_STREAM=0 keeps everything in order).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> ev;
+  size_t used = 0;
+  bool enabled() {
+    static const bool on = getenv("VPD_WGRAD_STREAM") == nullptr || getenv("VPD_WGRAD_STREAM")[0] != '0';
+    return on;
+  }
+  int init() {
+    if (stream != nullptr) return 0;
+    int lo = 0, hi = 0;
+    VPD_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VPD_CHECK_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, lo));
+    return 0;
+  }
+  cudaEvent_t next() {
+    if (used == ev.size()) {
+      cudaEvent_t e;
+      cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+      ev.push_back(e);
+    }
+    return ev[used++];
+  }
+  // `to` waits for everything enqueued on `from` so far
+  int order(cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e = next();
+    VPD_CHECK_CUDA(cudaEventRecord(e, from));
+    VPD_CHECK_CUDA(cudaStreamWaitEvent(to, e, 0));
+    return 0;
+  }
+  // marks "everything enqueued on `from` so far"; wait() makes `to` wait for it later
+  int mark(cudaStream_t from, cudaEvent_t* e) {
+    *e = next();
+    VPD_CHECK_CUDA(cudaEventRecord(*e, from));
+    return 0;
+  }
+  int wait(cudaStream_t to, cudaEvent_t* e) {
+    if (*e == nullptr) return 0;
+    VPD_CHECK_CUDA(cudaStreamWaitEvent(to, *e, 0));
+    *e = nullptr;
+    return 0;
+  }
+  ~SideStream() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
 struct Net {
   Profiler prof;
+  SideStream side;
   BucketFn bucket_fn = nullptr;   // called when grads[offset, offset+count) are final
   void* bucket_user = nullptr;
   // configuration
@@ -802,6 +855,17 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
   }
 
   // ----------------------------------------------------------------- backward
+  // weight gradients go to the side stream (not while profiling: per-launch timing wants
+  // one in-order stream). Hazards: wg2[i] reads gB and wg1[i] / wgds[i] read gC / gD, which
+  // the NEXT block's BN backward / dgrad2 overwrite, so the main stream waits for them there.
+  const bool use_side = n->side.enabled() && !n->prof.on;
+  cudaStream_t ws = s;
+  if (use_side) {
+    if (n->side.init()) return -1;
+    ws = n->side.stream;
+    n->side.used = 0;
+  }
+  cudaEvent_t e_wg2 = nullptr, e_wg1 = nullptr;  // side-stream readers of gB / gC, gD outstanding
   long long bucket_hi = n->n_params;
   bf16* cur = n->gA;
   bf16* other = n->gA2;
@@ -831,8 +895,17 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
       q.dgamma[b] = n->grads + n->gamma_off + bs[b]->ch_off;
       q.dbeta[b] = n->grads + n->beta_off + bs[b]->ch_off;
     }
+    if (use_side) {   // gB (and gD) are about to be rewritten
+      if (n->side.wait(s, &e_wg2)) return -1;
+      if (bd.has_ds && n->side.wait(s, &e_wg1)) return -1;
+    }
     PROF(kEwBwd, bd.stage, launch_bn_bwd(q, s));
-    PROF(kConvWgrad, bd.stage, launch_wgrad(P->wg2[i], s));
+    if (use_side && n->side.order(s, ws)) return -1;
+    PROF(kConvWgrad, bd.stage, launch_wgrad(P->wg2[i], ws));
+    if (use_side) {
+      if (n->side.mark(ws, &e_wg2)) return -1;
+      if (n->side.wait(s, &e_wg1)) return -1;   // gC is about to be rewritten
+    }
     PROF(kConvDgrad, bd.stage, launch_conv(P->dgrad2[i], s));  // gB -> gC
     memset(&q, 0, sizeof(q));
     q.dz = n->gC;
@@ -850,8 +923,10 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     q.dgamma[0] = n->grads + n->gamma_off + bd.b1.ch_off;
     q.dbeta[0] = n->grads + n->beta_off + bd.b1.ch_off;
     PROF(kEwBwd, bd.stage, launch_bn_bwd(q, s));
-    PROF(kConvWgrad, bd.stage, launch_wgrad(P->wg1[i], s));
-    if (bd.has_ds) PROF(kConvWgrad, bd.stage, launch_wgrad(P->wgds[i], s));
+    if (use_side && n->side.order(s, ws)) return -1;
+    PROF(kConvWgrad, bd.stage, launch_wgrad(P->wg1[i], ws));
+    if (bd.has_ds) PROF(kConvWgrad, bd.stage, launch_wgrad(P->wgds[i], ws));
+    if (use_side && n->side.mark(ws, &e_wg1)) return -1;
     for (auto& L : P->dgrad1[i])
       PROF(kConvDgrad, bd.stage, launch_conv(L, s));
     if (bd.has_ds) std::swap(cur, other);
@@ -859,6 +934,10 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     // done, everything from its first conv weight to the end of the arena is final
     if (n->bucket_fn != nullptr && i > 0 && n->blocks[i - 1].stage != bd.stage && bd.stage >= 3) {
       const long long lo = n->secA + bd.c1.w_off;
+      if (use_side) {
+        if (n->side.order(ws, s)) return -1;   // the bucket's weight gradients are final
+        e_wg2 = e_wg1 = nullptr;
+      }
       n->bucket_fn(n->bucket_user, lo, bucket_hi - lo);
       bucket_hi = lo;
     }
@@ -883,7 +962,9 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     sp.dgamma = n->grads + n->gamma_off + n->stem_bn.ch_off;
     sp.dbeta = n->grads + n->beta_off + n->stem_bn.ch_off;
     PROF(kEwBwd, 0, launch_stem_bwd(sp, s));
-    PROF(kConvWgrad, 0, launch_wgrad(P->wg_stem, s));
+    if (use_side && n->side.order(s, ws)) return -1;
+    PROF(kConvWgrad, 0, launch_wgrad(P->wg_stem, ws));
+    if (use_side && n->side.order(ws, s)) return -1;   // join: every gradient is final
   }
   if (n->bucket_fn != nullptr) n->bucket_fn(n->bucket_user, 0, bucket_hi);
   n->params_dirty = true;  // the caller is about to update the parameters
