@@ -85,6 +85,16 @@ def main():
         print('  last issue -> first accum seen     ', fmt(d(4, 5)), '(multi-tile CTAs: negative)')
         print('  epilogue (first accum -> done)     ', fmt(d(5, 6)))
         print('  total entry -> exit                ', fmt(d(1, 7)))
+        span = (t[:, 8].max() - t[:, 0].min()).item() / 1e3
+        first_exit = (t[:, 8].min() - t[:, 0].min()).item() / 1e3
+        late = t[t[:, 0] > t[:, 0].min() + 2000]   # CTAs that entered after the previous kernel drained
+        print('  kernel span first entry -> last exit: %.1f us (first exit at %.1f us); '
+              'exit spread %.1f us' % (span, first_exit, (t[:, 8].max() - t[:, 8].min()).item() / 1e3))
+        if late.shape[0]:
+            print('  late CTAs (%d): entry at +%.1f..%.1f us, entry -> exit %.1f us median'
+                  % (late.shape[0], (late[:, 0].min() - t[:, 0].min()).item() / 1e3,
+                     (late[:, 0].max() - t[:, 0].min()).item() / 1e3,
+                     (late[:, 8] - late[:, 0]).float().median().item() / 1e3))
 
 
 if __name__ == '__main__':

@@ -706,6 +706,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) trace_mark(p, 7);
+  if (threadIdx.x == 0 && p.trace != nullptr) {
+    unsigned long long g;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g));
+    p.trace[blockIdx.x * 16 + 8] = static_cast<long long>(g);
+  }
   if (CS > 1) cluster_sync_all();  // no CTA exits while a peer may still signal / multicast to it
   tc_fence_after();
   if (warp == 1) {

@@ -603,8 +603,11 @@ __global__ void __launch_bounds__(kEwThreads) stem_bwd_reduce_kernel(const StemB
   }
 }
 
-// pass 2 at input resolution: gather the <= 4 windows covering each pixel.
-__global__ void __launch_bounds__(kEwThreads) stem_bwd_apply_kernel(const StemBwdParams p) {
+// pass 2 at input resolution. A thread owns a 2x2 pixel quad (rows 2a, 2a+1; columns 2b,
+// 2b+1) of one 8-channel group: the only pooling windows that contain any of its pixels are
+// (a | a+1, b | b+1), so four dpool / argmax vectors serve four outputs (a per-pixel
+// gather needs up to four per output).
+__global__ void __launch_bounds__(kEwThreads, 2) stem_bwd_apply_kernel(const StemBwdParams p) {
   pdl_trigger();
   pdl_wait();
   const int groups = p.C >> 3;
@@ -626,60 +629,77 @@ __global__ void __launch_bounds__(kEwThreads) stem_bwd_apply_kernel(const StemBw
     a1[j] = -k0 * k2 * rstd;
     a2[j] = -k0 * k1 + k0 * k2 * rstd * mean;
   }
-  const long long total = M * groups;
+  const long long total = (long long)p.N * Ho * Wo * groups;   // quads x channel groups
   const long long stride = (long long)gridDim.x * kEwThreads;
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += stride) {
-    long long pix = i / groups;
-    const int w = (int)(pix % p.W);
-    pix /= p.W;
-    const int h = (int)(pix % p.H);
-    const int n = (int)(pix / p.H);
-    const size_t off = (((size_t)n * p.H + h) * p.W + w) * p.C + g * 8;
-    // pooled windows (pi, pj) containing (h, w): rows 2pi-1 .. 2pi+1
-    const int i_lo = h >> 1, i_hi = min((h + 1) >> 1, Ho - 1);
-    const int j_lo = w >> 1, j_hi = min((w + 1) >> 1, Wo - 1);
-    const uint4 vy = ldg_nc_v4(p.y + off);
+    long long q = i / groups;
+    const int b = (int)(q % Wo);
+    q /= Wo;
+    const int a = (int)(q % Ho);
+    const int n = (int)(q / Ho);
+    // the four windows (a + da, b + db); the second ones may fall off the edge
+    const bool has_a1 = a + 1 < Ho, has_b1 = b + 1 < Wo;
     uint4 vdp[4];
     uint2 vam[4];
-    int kidx[4];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int da = 0; da < 2; ++da)
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int pi = i_lo + a, pj = j_lo + b;
-        const int q = a * 2 + b;
-        if (pi <= i_hi && pj <= j_hi) {
-          const size_t po = (((size_t)n * Ho + pi) * Wo + pj) * p.C + g * 8;
-          vam[q] = __ldg(reinterpret_cast<const uint2*>(p.argmax + po));
-          vdp[q] = __ldg(reinterpret_cast<const uint4*>(p.dpool + po));
-          kidx[q] = (h - (2 * pi - 1)) * 3 + (w - (2 * pj - 1));
+      for (int db = 0; db < 2; ++db) {
+        const int k = da * 2 + db;
+        if ((da == 0 || has_a1) && (db == 0 || has_b1)) {
+          const size_t po = (((size_t)n * Ho + a + da) * Wo + b + db) * p.C + g * 8;
+          vam[k] = __ldg(reinterpret_cast<const uint2*>(p.argmax + po));
+          vdp[k] = ldg_nc_v4(p.dpool + po);
         } else {
-          kidx[q] = -1;
+          vam[k] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);   // matches no window position
+          vdp[k] = make_uint4(0, 0, 0, 0);
         }
       }
-    float yy[8], gr[8];
-    unpack8(vy, yy);
+    uint4 vy[4];
+    size_t off[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) gr[j] = 0.f;
+    for (int dh = 0; dh < 2; ++dh)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (kidx[q] < 0) continue;
-      float dp[8];
-      unpack8(vdp[q], dp);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t word = j < 4 ? vam[q].x : vam[q].y;
-        const int a = (word >> (8 * (j & 3))) & 0xFF;
-        if (a == kidx[q]) gr[j] += dp[j];
+      for (int dw = 0; dw < 2; ++dw) {
+        off[dh * 2 + dw] = (((size_t)n * p.H + 2 * a + dh) * p.W + 2 * b + dw) * p.C + g * 8;
+        vy[dh * 2 + dw] = ldg_nc_v4(p.y + off[dh * 2 + dw]);
       }
-    }
-    float o[8];
+    float dp[4][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float gq = fmaf(yy[j], sc[j], sh[j]) > 0.f ? gr[j] : 0.f;
-      o[j] = fmaf(a0[j], gq, fmaf(a1[j], yy[j], a2[j]));
-    }
-    stg_cs_v4(p.dy + off, pack8(o));
+    for (int k = 0; k < 4; ++k) unpack8(vdp[k], dp[k]);
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        // pixel (2a+dh, 2b+dw) sits at window position (kh, kw) = (2a+dh - (2(a+da)-1), ...)
+        //   = (dh + 1 - 2da, dw + 1 - 2db); valid when both are in 0..2
+        float yy[8], gr[8];
+        unpack8(vy[dh * 2 + dw], yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gr[j] = 0.f;
+#pragma unroll
+        for (int da = 0; da < 2; ++da)
+#pragma unroll
+          for (int db = 0; db < 2; ++db) {
+            const int kh = dh + 1 - 2 * da, kw = dw + 1 - 2 * db;
+            if (kh < 0 || kw < 0) continue;   // compile-time after unrolling
+            const int k = da * 2 + db;
+            const int kidx = kh * 3 + kw;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t word = j < 4 ? vam[k].x : vam[k].y;
+              const int am = (word >> (8 * (j & 3))) & 0xFF;
+              if (am == kidx) gr[j] += dp[k][j];
+            }
+          }
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float gq = fmaf(yy[j], sc[j], sh[j]) > 0.f ? gr[j] : 0.f;
+          o[j] = fmaf(a0[j], gq, fmaf(a1[j], yy[j], a2[j]));
+        }
+        stg_cs_v4(p.dy + off[dh * 2 + dw], pack8(o));
+      }
   }
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
@@ -693,7 +713,7 @@ int launch_stem_bwd(const StemBwdParams& p, cudaStream_t s) {
   if (p.N == 0) return 0;
   const long long pooled = (long long)p.N * (p.H / 2) * (p.W / 2) * (p.C / 8);
   VPD_CHECK_CUDA(launch_kernel(stem_bwd_reduce_kernel, dim3(ew_grid(pooled, 2, 2)), dim3(kEwThreads), 0, s, p));
-  VPD_CHECK_CUDA(launch_kernel(stem_bwd_apply_kernel, dim3(ew_grid(pooled * 4, 2, 2)), dim3(kEwThreads), 0, s, p));
+  VPD_CHECK_CUDA(launch_kernel(stem_bwd_apply_kernel, dim3(ew_grid(pooled, 2, 2)), dim3(kEwThreads), 0, s, p));
   VPD_LAUNCHED(2);
   return 0;
 }
