@@ -12,7 +12,7 @@
 
 namespace vpd {
 
-constexpr int kHeadThreads = 128;
+constexpr int kHeadThreads = 512;
 
 __global__ void __launch_bounds__(kHeadThreads) head_kernel(const HeadParams p) {
   pdl_trigger();
