@@ -542,6 +542,8 @@ static int launch_wgrad_bn(const WgradLaunch& L, cudaStream_t stream) {
 
 int launch_wgrad(const WgradLaunch& L, cudaStream_t stream) {
   if (L.grid <= 0) return 0;
+  static const int skip = env_int("VPD_DBG_SKIP_WGRAD", 0);  // timing experiments only
+  if (skip) return 0;
   if (L.block_n == 64) return launch_wgrad_bn<64>(L, stream);
   return launch_wgrad_bn<128>(L, stream);
 }

@@ -50,6 +50,9 @@ struct BlockDesc {
   bool has_ds;
   // workspace activations (bf16 NHWC)
   bf16 *y1, *z1, *y2, *yds, *zout;
+  // per-block gradients wrt the conv outputs (dy2, dy1, dy_ds): not shared between blocks, so
+  // the weight-gradient kernels may read them long after the backward chain has moved on
+  bf16 *gB, *gC, *gD;
 };
 
 struct TensorInfo {
@@ -188,7 +191,7 @@ struct Net {
   float *ev_scale, *ev_shift;      // [total_ch]
   bf16 *x_stem, *y_stem, *z_pool;
   uint8_t* argmax;
-  bf16 *gA, *gA2, *gB, *gC, *gD, *gStem;
+  bf16 *gA, *gA2, *gStem;
   float* head_ws;
   int* tr_table_dev;               // transpose table for the dgrad weight mirrors
   int tr_blocks;
@@ -426,12 +429,12 @@ static long long carve(Net* n, uint8_t* base) {
     bd.y2 = c.take<bf16>(sz);
     bd.yds = bd.has_ds ? c.take<bf16>(sz) : nullptr;
     bd.zout = c.take<bf16>(sz);
+    bd.gB = c.take<bf16>(sz);
+    bd.gC = c.take<bf16>(sz);
+    bd.gD = bd.has_ds ? c.take<bf16>(sz) : nullptr;
   }
   n->gA = c.take<bf16>(l1);
   n->gA2 = c.take<bf16>(l1);
-  n->gB = c.take<bf16>(l1);
-  n->gC = c.take<bf16>(l1);
-  n->gD = c.take<bf16>(l1);
   n->gStem = c.take<bf16>(stem_out);
   n->head_ws = c.take<float>(B * head_ws_stride(n->F, n->D, n->Hd, n->T));
   return c.off + 1024;
@@ -633,11 +636,11 @@ static Plan* get_plan(Net* n, int B) {
         f2.z = bd.z1;
         bn_fuse(&f2, 0, bd.b1, bd.y1);
       }
-      ok &= !plan_conv_dgrad(tmp, &cnt, g2, n->gB, wT + bd.c2.w_off, n->gC, nullptr, nullptr,
+      ok &= !plan_conv_dgrad(tmp, &cnt, g2, bd.gB, wT + bd.c2.w_off, bd.gC, nullptr, nullptr,
                              nullptr, 0, &f2);
       P->dgrad2[i] = tmp[0];
-      ok &= !plan_conv_wgrad(&P->wg2[i], g2, bd.z1, n->gB, n->grads + n->secA + bd.c2.w_off);
-      ok &= !plan_conv_wgrad(&P->wg1[i], g1, zin, n->gC, n->grads + n->secA + bd.c1.w_off);
+      ok &= !plan_conv_wgrad(&P->wg2[i], g2, bd.z1, bd.gB, n->grads + n->secA + bd.c2.w_off);
+      ok &= !plan_conv_wgrad(&P->wg1[i], g1, zin, bd.gC, n->grads + n->secA + bd.c1.w_off);
       // conv1's data gradient (+ identity / downsample branch) is dz of the previous
       // block's output stage (bn2 [+ downsample bn] + ReLU)
       ConvBwdFuse f1;
@@ -649,16 +652,16 @@ static Plan* get_plan(Net* n, int B) {
         if (pb.has_ds) bn_fuse(&f1, 1, pb.bds, pb.yds);
       }
       if (bd.has_ds) {
-        ok &= !plan_conv_wgrad(&P->wgds[i], geom(bd.ds, B), zin, n->gD, n->grads + n->secA + bd.ds.w_off);
+        ok &= !plan_conv_wgrad(&P->wgds[i], geom(bd.ds, B), zin, bd.gD, n->grads + n->secA + bd.ds.w_off);
         if (bd.c1.stride == 2) {
-          ok &= !plan_conv_dgrad(tmp, &cnt, g1, n->gC, wT + bd.c1.w_off, g_in[i], nullptr, n->gD,
+          ok &= !plan_conv_dgrad(tmp, &cnt, g1, bd.gC, wT + bd.c1.w_off, g_in[i], nullptr, bd.gD,
                                  wT + bd.ds.w_off, bd.ds.Cout, &f1);
         } else {
           set_error("net: stride-1 downsample blocks are not supported");
           ok = false;
         }
       } else {
-        ok &= !plan_conv_dgrad(tmp, &cnt, g1, n->gC, wT + bd.c1.w_off, g_in[i], g_out[i], nullptr,
+        ok &= !plan_conv_dgrad(tmp, &cnt, g1, bd.gC, wT + bd.c1.w_off, g_in[i], g_out[i], nullptr,
                                nullptr, 0, &f1);
       }
       P->dgrad1[i].assign(tmp, tmp + cnt);
@@ -856,8 +859,10 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
 
   // ----------------------------------------------------------------- backward
   // weight gradients go to the side stream (not while profiling: per-launch timing wants
-  // one in-order stream). Hazards: wg2[i] reads gB and wg1[i] / wgds[i] read gC / gD, which
-  // the NEXT block's BN backward / dgrad2 overwrite, so the main stream waits for them there.
+  // one in-order stream). Every block owns its dy buffers, so the only ordering needed is
+  // main -> side (dy ready); the main stream waits for the side stream only where gradients
+  // must be final (all-reduce buckets, end of the step) - cross-stream waits on the main
+  // chain would cost its programmatic-dependent-launch overlap.
   const bool use_side = n->side.enabled() && !n->prof.on;
   cudaStream_t ws = s;
   if (use_side) {
@@ -865,7 +870,6 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     ws = n->side.stream;
     n->side.used = 0;
   }
-  cudaEvent_t e_wg2 = nullptr, e_wg1 = nullptr;  // side-stream readers of gB / gC, gD outstanding
   long long bucket_hi = n->n_params;
   bf16* cur = n->gA;
   bf16* other = n->gA2;
@@ -884,7 +888,7 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     q.nbranch = bd.has_ds ? 2 : 1;
     const BnDesc* bs[2] = {&bd.b2, &bd.bds};
     const bf16* ys[2] = {bd.y2, bd.yds};
-    bf16* dys[2] = {n->gB, n->gD};
+    bf16* dys[2] = {bd.gB, bd.gD};
     for (int b = 0; b < q.nbranch; ++b) {
       q.y[b] = ys[b];
       q.dy[b] = dys[b];
@@ -895,27 +899,18 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
       q.dgamma[b] = n->grads + n->gamma_off + bs[b]->ch_off;
       q.dbeta[b] = n->grads + n->beta_off + bs[b]->ch_off;
     }
-    if (use_side) {   // gB (and gD) are about to be rewritten
-      if (n->side.wait(s, &e_wg2)) return -1;
-      if (bd.has_ds && n->side.wait(s, &e_wg1)) return -1;
-    }
     PROF(kEwBwd, bd.stage, launch_bn_bwd(q, s));
-    if (use_side && n->side.order(s, ws)) return -1;
-    PROF(kConvWgrad, bd.stage, launch_wgrad(P->wg2[i], ws));
-    if (use_side) {
-      if (n->side.mark(ws, &e_wg2)) return -1;
-      if (n->side.wait(s, &e_wg1)) return -1;   // gC is about to be rewritten
-    }
+    if (!use_side) PROF(kConvWgrad, bd.stage, launch_wgrad(P->wg2[i], s));
     PROF(kConvDgrad, bd.stage, launch_conv(P->dgrad2[i], s));  // gB -> gC
     memset(&q, 0, sizeof(q));
-    q.dz = n->gC;
+    q.dz = bd.gC;
     q.z = P->fused ? nullptr : bd.z1;   // fused: dgrad2 already masked + reduced
     q.sums_ready = P->fused ? 1 : 0;
     q.M = M;
     q.C = bd.c1.Cout;
     q.nbranch = 1;
     q.y[0] = bd.y1;
-    q.dy[0] = n->gC;  // in place
+    q.dy[0] = bd.gC;  // in place
     q.gamma[0] = n->params + n->gamma_off + bd.b1.ch_off;
     q.save_mean[0] = n->save_mean + bd.b1.ch_off;
     q.save_rstd[0] = n->save_rstd + bd.b1.ch_off;
@@ -923,10 +918,12 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     q.dgamma[0] = n->grads + n->gamma_off + bd.b1.ch_off;
     q.dbeta[0] = n->grads + n->beta_off + bd.b1.ch_off;
     PROF(kEwBwd, bd.stage, launch_bn_bwd(q, s));
-    if (use_side && n->side.order(s, ws)) return -1;
+    if (use_side) {   // dy2, dy1 (and dy_ds) of this block are final: its three wgrads may go
+      if (n->side.order(s, ws)) return -1;
+      if (launch_wgrad(P->wg2[i], ws)) return -1;
+    }
     PROF(kConvWgrad, bd.stage, launch_wgrad(P->wg1[i], ws));
     if (bd.has_ds) PROF(kConvWgrad, bd.stage, launch_wgrad(P->wgds[i], ws));
-    if (use_side && n->side.mark(ws, &e_wg1)) return -1;
     for (auto& L : P->dgrad1[i])
       PROF(kConvDgrad, bd.stage, launch_conv(L, s));
     if (bd.has_ds) std::swap(cur, other);
@@ -934,10 +931,7 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     // done, everything from its first conv weight to the end of the arena is final
     if (n->bucket_fn != nullptr && i > 0 && n->blocks[i - 1].stage != bd.stage && bd.stage >= 3) {
       const long long lo = n->secA + bd.c1.w_off;
-      if (use_side) {
-        if (n->side.order(ws, s)) return -1;   // the bucket's weight gradients are final
-        e_wg2 = e_wg1 = nullptr;
-      }
+      if (use_side && n->side.order(ws, s)) return -1;   // the bucket's weight gradients are final
       n->bucket_fn(n->bucket_user, lo, bucket_hi - lo);
       bucket_hi = lo;
     }
