@@ -325,10 +325,21 @@ def run_native(args, rank, world, local_rank):
         f_ig = flops[0] + flops[2]
         n_ig = per_kind_n[0] + per_kind_n[2]
         achieved = f_ig / (t_ig * 1e-3) / 1e12
+        # DRAM traffic per launch of the family's largest member, from the committed ncu
+        # --set full capture (profiles/): not measurable live without the profiler
+        traffic, traffic_of = None, None
+        tpath = os.path.join(ROOT, 'profiles', 'r01c_traffic.json')
+        if os.path.exists(tpath):
+            with open(tpath) as fp:
+                tj = json.load(fp)
+            traffic = tj['dram_bytes_per_launch']
+            traffic_of = {k: tj[k] for k in ('kernel', 'algorithmic_bytes_per_launch',
+                                             'tensor_pipe_active_pct', 'source')}
         roofline = {'kernel': 'conv_igemm_kernel + conv3x3_halo_kernel (forward and dgrad launches)',
                     'bound': 'tensor', 'achieved': round(achieved, 2), 'peak': pk['tflops'],
                     'unit': 'TFLOP/s', 'frac': round(achieved / pk['tflops'], 4),
-                    'traffic': None, 'peak_source': pk['source'] + ' bf16 sustained',
+                    'traffic': traffic, 'traffic_of': traffic_of,
+                    'peak_source': pk['source'] + ' bf16 sustained',
                     'launches_per_step': n_ig,
                     'avg_launch_ms': round(t_ig / max(1, n_ig), 5),
                     'algorithmic_flops_per_step': f_ig,

@@ -1117,7 +1117,7 @@ struct WgradCfg {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kWgradThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 3)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                   const __grid_constant__ WgradParams p) {
   using Cfg = WgradCfg<BLOCK_N>;

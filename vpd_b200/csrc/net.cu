@@ -122,7 +122,11 @@ struct SideStream {
     if (stream != nullptr) return 0;
     int lo = 0, hi = 0;
     VPD_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    VPD_CHECK_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, lo));
+    const char* e = getenv("VPD_WGRAD_PRIO");   // "lo" (default) | "hi" | "mid"
+    int prio = lo;
+    if (e != nullptr && e[0] == 'h') prio = hi;
+    if (e != nullptr && e[0] == 'm') prio = 0;
+    VPD_CHECK_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio));
     return 0;
   }
   cudaEvent_t next() {
