@@ -132,7 +132,7 @@ static bool try_halo(ConvLaunch* L, const __nv_bfloat16* x, const __nv_bfloat16*
   if (H % 16 != 0 || W % 8 != 0) return false;
   // 64 -> 64 layers keep their 72 KB of weights resident; wider layers stream the
   // (chunk, tap) weight tiles through a TMA ring with 128-wide channel blocks
-  static const int stream_on = env_int("VPD_HALO_STREAM", 0);  // correct but measured neutral: opt-in
+  static const int stream_on = env_int("VPD_HALO_STREAM", 1);  // 128-channel 16x16 layers: -0.04 ms/step
   const bool resident = chunks == 1 && cout_k == 64;
   if (!resident && !(stream_on && cout_k % 128 == 0 && chunks <= 8)) return false;
   ConvParams& p = L->p;
