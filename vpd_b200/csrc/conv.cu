@@ -221,7 +221,23 @@ int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
   set_weights(&p, 0, w_tap, g.Cout, g.Cin);
   set_weights(&p, 1, w_tap, g.Cout, g.Cin);
   L->a1 = L->a0;
-  return out_map(L, y, g.N, Ho, Wo, g.Cout, 1, 0, 0);
+  if (out_map(L, y, g.N, Ho, Wo, g.Cout, 1, 0, 0)) return -1;
+  L->o2 = L->o;
+  // BatchNorm apply behind a grid barrier: every CTA must hold its only tile's accumulator
+  // in TMEM across the barrier, and all CTAs must be co-resident (grid <= SMs, 1 CTA/SM)
+  const int items = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
+  static const int fuse_on = env_int("VPD_FUSE_BNFWD", 1);
+  if (fuse_on && e.fuse_bn && e.stats != nullptr && L->cluster == 1 && items == L->grid &&
+      L->grid <= device_sm_count()) {
+    p.fuse_bn = 1;
+    p.fbn = e.bn;
+    p.fres = e.fuse_res;
+    p.frelu = e.fuse_relu;
+    p.fbar = e.fuse_bar;
+    L->fused_bn = 1;
+    if (act_map(&L->o2, e.fuse_z, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
+  }
+  return 0;
 }
 
 int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
@@ -392,7 +408,7 @@ static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
   }
   VPD_CHECK_CUDA(launch_kernel_cluster(CS, conv_igemm_kernel<BN, CS>, dim3(L.grid),
                                        dim3(kConvThreads), ConvCfg<BN>::kSmemBytes, stream, L.a0,
-                                       L.a1, L.o, L.p));
+                                       L.a1, L.o, L.o2, L.p));
   VPD_LAUNCHED(1);
   return 0;
 }

@@ -22,6 +22,7 @@
 //     BatchNorm needs (warp transpose-reduce -> smem -> fp64 global atomics).
 #pragma once
 #include "common.cuh"
+#include "elementwise.cuh"
 
 namespace vpd {
 
@@ -87,6 +88,17 @@ struct ConvParams {
   // entry / after the dependency wait / first operands landed / last MMA issued /
   // first accumulator ready / epilogue done / exit
   long long* trace;
+  // Training-mode BatchNorm apply fused behind a GRID BARRIER (CTAs with exactly one tile,
+  // i.e. the small deep layers, where a separate elementwise kernel costs ~10 us of pipeline
+  // drain/fill for ~4 us of work): pass 1 stores y and accumulates the statistics as usual,
+  // all CTAs meet at `fbar`, every CTA derives scale/shift of its channel block and pass 2
+  // re-reads the accumulator still sitting in TMEM, rounds it exactly like the stored y and
+  // writes z = relu(y*scale + shift (+ residual)) through the second output map.
+  int fuse_bn;
+  BnLayer fbn;                   // fbn.stats == stats
+  const __nv_bfloat16* fres;     // residual (same addressing as out) or null
+  int frelu;
+  unsigned int* fbar;            // zeroed every step
   int dbg;  // diagnostics (VPD_DBG_SKIP): bit0 skip the A loads, bit1 skip the B loads, bit2 skip the epilogue body
 };
 VPD_DEVINL void trace_mark(const ConvParams& p, int slot) {
@@ -125,9 +137,11 @@ struct ConvCfg {
 template <int BLOCK_N, int CS>
 VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                               uint64_t* tempty_bar, uint8_t* slabs, uint64_t* sfull,
-                              uint64_t* sempty, int rank, int first_item, int item_stride,
+                              uint64_t* sempty, const float* s_scale, const float* s_shift,
+                              uint64_t* bnready, int rank, int first_item, int item_stride,
                               int total_tiles, int warp, int lane) {
   using SC = StageCfg<BLOCK_N>;
+  const int passes = p.fuse_bn ? 2 : 1;
   // pair mode (CS == 2): the leader's MMA thread owns the accumulator hand-shake, so the
   // peer's epilogue warps release the TMEM stage on the LEADER's barrier
   const uint32_t tempty_remote0 =
@@ -157,6 +171,9 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
     if (tile == first_item && threadIdx.x == kEpiThread0) trace_mark(p, 5);
     tc_fence_after();
 #pragma unroll 1
+    for (int pass = 0; pass < passes; ++pass) {
+    if (pass == 1) mbar_wait(bnready, 0);  // scale / shift of this channel block are in smem
+#pragma unroll 1
     for (int j = 0; j < SC::kSlabs; ++j) {
       mbar_wait(&sempty[slot], sphase ^ 1);  // the slab's previous contents have been stored
       const uint32_t dst = row_addr + slot * kSlabBytes;
@@ -165,10 +182,11 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
         const int c = 2 * j + cc;
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
-        const bool do_res = p.residual != nullptr && valid;
+        const __nv_bfloat16* resp = pass == 1 ? p.fres : p.residual;
+        const bool do_res = resp != nullptr && valid;
         uint4 rres[4];
         if (do_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + off + c * 32);
+          const uint4* rp = reinterpret_cast<const uint4*>(resp + off + c * 32);
 #pragma unroll
           for (int k = 0; k < 4; ++k) rres[k] = rp[k];  // plain load: residual may alias out
         }
@@ -177,7 +195,19 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 #pragma unroll
         for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
         const int ch0 = n_tile * BLOCK_N + c * 32;
-        if (p.scale != nullptr) {
+        if (pass == 1) {
+          // exactly what bn_apply_kernel does with the stored bf16 y
+          const uint32_t sc_a = smem_u32(s_scale + c * 32), sh_a = smem_u32(s_shift + c * 32);
+#pragma unroll
+          for (int k = 0; k < 32; k += 4) {
+            const float4 sc = __uint4_as_float4(lds_v4(sc_a + k * 4));
+            const float4 sh = __uint4_as_float4(lds_v4(sh_a + k * 4));
+            f[k + 0] = fmaf(bf16_round(f[k + 0]), sc.x, sh.x);
+            f[k + 1] = fmaf(bf16_round(f[k + 1]), sc.y, sh.y);
+            f[k + 2] = fmaf(bf16_round(f[k + 2]), sc.z, sh.z);
+            f[k + 3] = fmaf(bf16_round(f[k + 3]), sc.w, sh.w);
+          }
+        } else if (p.scale != nullptr) {
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
             const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + k));
@@ -201,7 +231,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
             f[8 * k + 7] += bf16_hi(rres[k].w);
           }
         }
-        if (p.relu) {
+        if (pass == 1 ? p.frelu : p.relu) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
         }
@@ -217,7 +247,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
                             pack_bf16x2(f[8 * k + 4], f[8 * k + 5]),
                             pack_bf16x2(f[8 * k + 6], f[8 * k + 7])));
       }
-      if (j == SC::kSlabs - 1) {
+      if (j == SC::kSlabs - 1 && pass == passes - 1) {
         // accumulator fully read: hand the TMEM stage back to the MMA warp
         tc_fence_before();
         __syncwarp();
@@ -232,6 +262,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
         slot = 0;
         sphase ^= 1;
       }
+    }
     }
     if (++as == 2) {
       as = 0;
@@ -254,7 +285,8 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 // float atomics: those are CAS loops) and reach the fp64 global accumulators when the
 // channel block changes and at the end.
 template <int BLOCK_N, int CS>
-VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out, uint8_t* slabs,
+VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
+                           const CUtensorMap* tm_out2, uint64_t* bnready, uint8_t* slabs,
                            uint64_t* sfull, uint64_t* sempty, float* s_sum, float* s_sq,
                            float* s_x2, float* s_scr, int rank, int first_item, int item_stride,
                            int total_tiles, int sw, int lane) {
@@ -503,6 +535,64 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out, uint8
     }
   }
   if (sums && cur_ntile >= 0) global_flush(cur_ntile);
+  if (p.fuse_bn && cur_ntile >= 0) {
+    // ---- grid barrier: every CTA's sums are in the global accumulators after this
+    if (st == 0) {
+      __threadfence();
+      atomicAdd(p.fbar, 1u);
+      unsigned int seen = 0, spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.fbar) : "memory");
+        if (seen >= gridDim.x) break;
+        __nanosleep(64);
+        if (++spins > (1u << 24)) __trap();  // a CTA of the grid never arrived: fail loudly
+      } while (true);
+      __threadfence();
+    }
+    asm volatile("bar.sync 2, %0;" ::"n"(kStatThreads) : "memory");
+    // scale / shift of this CTA's channel block (same arithmetic as the elementwise kernels);
+    // the CTA holding the first pixel tile of the block also persists the batch statistics
+    const bool owner = (first_item / p.n_tiles) == 0 && rank == 0;
+    for (int i = st; i < BLOCK_N; i += kStatThreads) {
+      const int c = cur_ntile * BLOCK_N + i;
+      float mean, rstd, var, sc, sh;
+      bn_mean_rstd<true>(p.fbn, c, p.cout, mean, rstd, var);
+      bn_affine(__ldg(p.fbn.gamma + c), __ldg(p.fbn.beta + c), mean, rstd, sc, sh);
+      s_sum[i] = sc;
+      s_sq[i] = sh;
+      if (owner) bn_channel_side_effects(p.fbn, c, mean, rstd, var);
+    }
+    if (first_item == 0 && rank == 0 && st == 0 && p.fbn.update_running && p.fbn.num_batches)
+      *p.fbn.num_batches += 1;
+    mbar_arrive(bnready);  // release: the epilogue warps may read scale / shift
+    // ---- pass 2: the epilogue warps stage z slabs; only the store thread has work
+    if (st == 0) {
+      const int n_tile0 = first_item % p.n_tiles;
+      int mt = (first_item / p.n_tiles) * CS + rank;
+      const int zw0 = (mt % p.tiles_w) * p.tw;
+      mt /= p.tiles_w;
+      const int zh0 = (mt % p.tiles_h) * p.th;
+      const int zb0 = (mt / p.tiles_h) * p.tn;
+      for (int jz = 0; jz < SC::kSlabs; ++jz) {
+        mbar_wait(&sfull[slot], sphase);
+        tma_store_5d(tm_out2, slabs + slot * kSlabBytes, p.out_c0 + n_tile0 * BLOCK_N + jz * 64,
+                     zw0, p.out_d2, zh0, zb0);
+        bulk_commit_group();
+        if (SC::kSlots > 1) {
+          bulk_wait_read1();
+          if (prev_slot >= 0) mbar_arrive(&sempty[prev_slot]);
+          prev_slot = slot;
+        } else {
+          bulk_wait_read0();
+          mbar_arrive(&sempty[slot]);
+        }
+        if (++slot == SC::kSlots) {
+          slot = 0;
+          sphase ^= 1;
+        }
+      }
+    }
+  }
   if (st == 0) bulk_wait0();  // all tile stores performed before the CTA exits
 }
 
@@ -517,7 +607,8 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out, uint8
 template <int BLOCK_N, int CS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
+                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                  const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -531,7 +622,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* pfull_bar = tempty_bar + 2;  // leader only: "the peer's stage has landed"
   uint64_t* sfull_bar = pfull_bar + Cfg::kStages;  // epilogue -> statistics warps: slab staged
   uint64_t* sempty_bar = sfull_bar + 2;            // slab stored, slot free
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sempty_bar + 2);
+  uint64_t* bnready_bar = sempty_bar + 2;          // fused BN: scale / shift ready
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bnready_bar + 1);
   float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + Cfg::kBarBytes);
   float* s_sq = s_sum + BLOCK_N;
   float* s_x2 = s_sq + BLOCK_N;  // second BN branch (fused backward reduction)
@@ -552,6 +644,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       mbar_init(&sfull_bar[s], kEpiThreads);
       mbar_init(&sempty_bar[s], 1);
     }
+    mbar_init(bnready_bar, kStatThreads);
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmOut);
@@ -590,12 +683,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, CS>(p, &tmOut, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, rank,
+    conv_stats<BLOCK_N, CS>(p, &tmOut, &tmOut2, bnready_bar, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, rank,
                             first_item, item_stride, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
     conv_epilogue<BLOCK_N, CS>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
-                               rank, first_item, item_stride, total_tiles, warp, lane);
+                               s_sum, s_sq, bnready_bar, rank, first_item, item_stride, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
    if (warp == 0) {
@@ -813,12 +906,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, 1>(p, &tmOut, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
+    conv_stats<BLOCK_N, 1>(p, &tmOut, &tmOut, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
                            blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar, 0,
-                              blockIdx.x, gridDim.x, total_tiles, warp, lane);
+    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
+                              s_sum, s_sq, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
    if (warp == 0) {
@@ -982,12 +1075,12 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, 1>(p, &tmOut, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
+    conv_stats<BLOCK_N, 1>(p, &tmOut, &tmOut, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
                            blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar, 0,
-                              blockIdx.x, gridDim.x, total_tiles, warp, lane);
+    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
+                              s_sum, s_sq, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
    if (warp == 0) {

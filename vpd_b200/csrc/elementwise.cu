@@ -17,32 +17,6 @@ VPD_DEVINL uint4 pack8(const float (&f)[8]) {
                     pack_bf16x2(f[6], f[7]));
 }
 
-// Batch (train) or running (eval) statistics -> fp32 mean / rstd of channel c.
-// Only fp64 multiplies/FMAs (full rate) - the mean-square subtraction is the one
-// place that needs the extra bits; the reciprocal square root is fp32.
-VPD_DEVINL void bn_mean_rstd(const BnLayer& bn, int c, int C, float& mean, float& rstd,
-                             float& var_biased) {
-  if (bn.stats != nullptr) {
-    const double inv = bn.inv_count;
-    const double m = __ldg(bn.stats + c) * inv;
-    double v = fma(__ldg(bn.stats + C + c), inv, -m * m);
-    if (v < 0.0) v = 0.0;
-    mean = static_cast<float>(m);
-    var_biased = static_cast<float>(v);
-    rstd = rsqrtf(var_biased + bn.eps);
-  } else {
-    mean = bn.running_mean[c];
-    var_biased = bn.running_var[c];
-    rstd = rsqrtf(var_biased + bn.eps);
-  }
-}
-// The affine every kernel (forward and backward) derives from (mean, rstd).
-VPD_DEVINL void bn_affine(float gamma, float beta, float mean, float rstd, float& scale,
-                          float& shift) {
-  scale = gamma * rstd;
-  shift = beta - mean * scale;
-}
-
 // Block 0: persist batch statistics and update the running buffers like
 // nn.BatchNorm2d (momentum 0.1, unbiased variance for the running estimate).
 VPD_DEVINL void bn_side_effects(const BnLayer& bn, int C) {
@@ -50,13 +24,7 @@ VPD_DEVINL void bn_side_effects(const BnLayer& bn, int C) {
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, rstd, var;
     bn_mean_rstd(bn, c, C, mean, rstd, var);
-    if (bn.save_mean) bn.save_mean[c] = mean;
-    if (bn.save_rstd) bn.save_rstd[c] = rstd;
-    if (bn.update_running) {
-      const float unbias = bn.count > 1.f ? bn.count / (bn.count - 1.f) : 1.f;
-      bn.running_mean[c] = (1.f - bn.momentum) * bn.running_mean[c] + bn.momentum * mean;
-      bn.running_var[c] = (1.f - bn.momentum) * bn.running_var[c] + bn.momentum * var * unbias;
-    }
+    bn_channel_side_effects(bn, c, mean, rstd, var);
   }
   if (bn.update_running && threadIdx.x == 0 && bn.num_batches) *bn.num_batches += 1;
 }

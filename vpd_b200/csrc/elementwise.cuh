@@ -27,6 +27,50 @@ struct BnLayer {
   int update_running;      // train: block 0 updates running stats
 };
 
+// Batch (train) or running (eval) statistics -> fp32 mean / rstd of channel c.
+// Only fp64 multiplies/FMAs (full rate) - the mean-square subtraction is the one
+// place that needs the extra bits; the reciprocal square root is fp32.
+// kCoherent: the sums were accumulated earlier in THIS kernel by other CTAs (conv kernels
+// with the BatchNorm apply fused behind a grid barrier): read them through L2, not the
+// non-coherent path.
+template <bool kCoherent = false>
+VPD_DEVINL void bn_mean_rstd(const BnLayer& bn, int c, int C, float& mean, float& rstd,
+                             float& var_biased) {
+  if (bn.stats != nullptr) {
+    const double inv = bn.inv_count;
+    const double s0 = kCoherent ? __ldcg(bn.stats + c) : __ldg(bn.stats + c);
+    const double s1 = kCoherent ? __ldcg(bn.stats + C + c) : __ldg(bn.stats + C + c);
+    const double m = s0 * inv;
+    double v = fma(s1, inv, -m * m);
+    if (v < 0.0) v = 0.0;
+    mean = static_cast<float>(m);
+    var_biased = static_cast<float>(v);
+    rstd = rsqrtf(var_biased + bn.eps);
+  } else {
+    mean = bn.running_mean[c];
+    var_biased = bn.running_var[c];
+    rstd = rsqrtf(var_biased + bn.eps);
+  }
+}
+// The affine every kernel (forward and backward) derives from (mean, rstd).
+VPD_DEVINL void bn_affine(float gamma, float beta, float mean, float rstd, float& scale,
+                          float& shift) {
+  scale = gamma * rstd;
+  shift = beta - mean * scale;
+}
+// Persist the batch statistics of channel c and update the running buffers like
+// nn.BatchNorm2d (momentum 0.1, unbiased variance for the running estimate).
+VPD_DEVINL void bn_channel_side_effects(const BnLayer& bn, int c, float mean, float rstd,
+                                        float var) {
+  if (bn.save_mean) bn.save_mean[c] = mean;
+  if (bn.save_rstd) bn.save_rstd[c] = rstd;
+  if (bn.update_running) {
+    const float unbias = bn.count > 1.f ? bn.count / (bn.count - 1.f) : 1.f;
+    bn.running_mean[c] = (1.f - bn.momentum) * bn.running_mean[c] + bn.momentum * mean;
+    bn.running_var[c] = (1.f - bn.momentum) * bn.running_var[c] + bn.momentum * var * unbias;
+  }
+}
+
 struct BnApplyParams {
   const __nv_bfloat16* y;    // [M][C] conv output (pre-BN)
   const __nv_bfloat16* res;  // [M][C] residual input or null

@@ -190,6 +190,7 @@ struct Net {
   bf16 *w_tap, *wT_tap;            // bf16 mirrors of section [A]
   double* stats;                   // [2][total_ch] forward sum/sumsq   (zeroed per step)
   double* bwd_sums;                // [2][total_ch] backward sums        (zeroed per step)
+  unsigned int* bn_bar;            // one grid-barrier counter per BN layer (fused BN apply)
   double* loss_dev;                // scalar
   float *save_mean, *save_rstd;    // [total_ch]
   float *ev_scale, *ev_shift;      // [total_ch]
@@ -414,6 +415,7 @@ static long long carve(Net* n, uint8_t* base) {
   n->wT_tap = c.take<bf16>(n->secA_len);
   n->stats = c.take<double>(2 * n->total_ch);
   n->bwd_sums = c.take<double>(2 * n->total_ch);
+  n->bn_bar = c.take<unsigned int>(n->num_bn + 8);   // grid-barrier counters (zeroed per step)
   n->loss_dev = c.take<double>(8);
   n->save_mean = c.take<float>(n->total_ch);
   n->save_rstd = c.take<float>(n->total_ch);
@@ -610,8 +612,27 @@ static Plan* get_plan(Net* n, int B) {
   for (size_t i = 0; i < nb && ok; ++i) {
     BlockDesc& bd = n->blocks[i];
     const ConvGeom g1 = geom(bd.c1, B), g2 = geom(bd.c2, B);
-    ok &= !plan_conv_fwd(&P->c1_train[i], g1, zin, wt + bd.c1.w_off, bd.y1, tr(bd.b1));
-    ok &= !plan_conv_fwd(&P->c2_train[i], g2, bd.z1, wt + bd.c2.w_off, bd.y2, tr(bd.b2));
+    // training convs: where every CTA gets a single tile (the deep, small layers) the
+    // BatchNorm apply rides in the same launch (ConvEpilogue::fuse_bn)
+    const long long Mout = (long long)B * bd.c2.Hin * bd.c2.Win;
+    ConvEpilogue e1 = tr(bd.b1), e2 = tr(bd.b2);
+    if (e1.stats != nullptr) {
+      e1.fuse_bn = true;
+      e1.bn = bn_layer(n, bd.b1, true, Mout);
+      e1.fuse_z = bd.z1;
+      e1.fuse_relu = 1;
+      e1.fuse_bar = n->bn_bar + bd.b1.idx;
+    }
+    if (e2.stats != nullptr && !bd.has_ds) {
+      e2.fuse_bn = true;
+      e2.bn = bn_layer(n, bd.b2, true, Mout);
+      e2.fuse_z = bd.zout;
+      e2.fuse_res = zin;
+      e2.fuse_relu = 1;
+      e2.fuse_bar = n->bn_bar + bd.b2.idx;
+    }
+    ok &= !plan_conv_fwd(&P->c1_train[i], g1, zin, wt + bd.c1.w_off, bd.y1, e1);
+    ok &= !plan_conv_fwd(&P->c2_train[i], g2, bd.z1, wt + bd.c2.w_off, bd.y2, e2);
     ok &= !plan_conv_fwd(&P->c1_eval[i], g1, zin, wt + bd.c1.w_off, bd.z1, ev(bd.b1, nullptr, 1));
     const bf16* res = zin;
     if (bd.has_ds) {
@@ -815,7 +836,7 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     a.C = bd.c1.Cout;
     a.relu = 1;
     a.bn = bn_layer(n, bd.b1, true, M);
-    PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
+    if (!P->c1_train[i].fused_bn) PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
     PROF(kConvFwd, bd.stage, launch_conv(P->c2_train[i], s));
     if (split)
       PROF(kEwFwd, bd.stage, launch_channel_stats(bd.y2, M, 64, n->stats + 2 * bd.b2.ch_off, s));
@@ -834,7 +855,7 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     } else {
       a.res = zin;
     }
-    PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
+    if (!P->c2_train[i].fused_bn) PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
     zin = bd.zout;
   }
 
