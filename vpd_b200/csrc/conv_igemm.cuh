@@ -134,14 +134,18 @@ struct ConvCfg {
 // Epilogue, warps 2..5 (threads 64..191): drains the TMEM accumulator stages tile by tile -
 // optional folded-BN affine, residual, ReLU - and writes bf16 slabs to the staging ring.
 // It performs no reductions and no global stores.
-template <int BLOCK_N, int CS>
+template <int BLOCK_N, int CS, bool FUSE>
 VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                               uint64_t* tempty_bar, uint8_t* slabs, uint64_t* sfull,
                               uint64_t* sempty, const float* s_scale, const float* s_shift,
-                              uint64_t* bnready, int rank, int first_item, int item_stride,
-                              int total_tiles, int warp, int lane) {
+                              uint64_t* bnready, uint8_t* ring, uint64_t* zfull, int rank,
+                              int first_item, int item_stride, int total_tiles, int warp,
+                              int lane) {
   using SC = StageCfg<BLOCK_N>;
-  const int passes = p.fuse_bn ? 2 : 1;
+  constexpr int passes = FUSE ? 2 : 1;
+  // fused-BN launches have one tile per CTA: once its accumulator is complete the operand
+  // ring is dead, so every slab of both passes gets its own 16 KB of it (no slot hand-shake)
+  constexpr bool direct = FUSE;
   // pair mode (CS == 2): the leader's MMA thread owns the accumulator hand-shake, so the
   // peer's epilogue warps release the TMEM stage on the LEADER's barrier
   const uint32_t tempty_remote0 =
@@ -172,17 +176,18 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
     tc_fence_after();
 #pragma unroll 1
     for (int pass = 0; pass < passes; ++pass) {
-    if (pass == 1) mbar_wait(bnready, 0);  // scale / shift of this channel block are in smem
+    if (FUSE && pass == 1) mbar_wait(bnready, 0);  // scale / shift of this channel block are in smem
 #pragma unroll 1
     for (int j = 0; j < SC::kSlabs; ++j) {
-      mbar_wait(&sempty[slot], sphase ^ 1);  // the slab's previous contents have been stored
-      const uint32_t dst = row_addr + slot * kSlabBytes;
+      if (!direct) mbar_wait(&sempty[slot], sphase ^ 1);  // the slab's previous contents have been stored
+      const uint32_t dst = direct ? smem_u32(ring) + (pass * SC::kSlabs + j) * kSlabBytes + r * 128
+                                  : row_addr + slot * kSlabBytes;
 #pragma unroll 1
       for (int cc = 0; cc < ((p.dbg & 4) ? 0 : 2); ++cc) {
         const int c = 2 * j + cc;
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
-        const __nv_bfloat16* resp = pass == 1 ? p.fres : p.residual;
+        const __nv_bfloat16* resp = (FUSE && pass == 1) ? p.fres : p.residual;
         const bool do_res = resp != nullptr && valid;
         uint4 rres[4];
         if (do_res) {
@@ -195,7 +200,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 #pragma unroll
         for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
         const int ch0 = n_tile * BLOCK_N + c * 32;
-        if (pass == 1) {
+        if (FUSE && pass == 1) {
           // exactly what bn_apply_kernel does with the stored bf16 y
           const uint32_t sc_a = smem_u32(s_scale + c * 32), sh_a = smem_u32(s_shift + c * 32);
 #pragma unroll
@@ -231,7 +236,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
             f[8 * k + 7] += bf16_hi(rres[k].w);
           }
         }
-        if (pass == 1 ? p.frelu : p.relu) {
+        if ((FUSE && pass == 1) ? p.frelu : p.relu) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
         }
@@ -257,10 +262,14 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
         }
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
-      mbar_arrive(&sfull[slot]);
-      if (++slot == SC::kSlots) {
-        slot = 0;
-        sphase ^= 1;
+      if (direct) {
+        mbar_arrive(&zfull[pass * SC::kSlabs + j]);
+      } else {
+        mbar_arrive(&sfull[slot]);
+        if (++slot == SC::kSlots) {
+          slot = 0;
+          sphase ^= 1;
+        }
       }
     }
     }
@@ -284,9 +293,10 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 // combined through a small double-buffered scratch with exclusive owners (no shared-memory
 // float atomics: those are CAS loops) and reach the fp64 global accumulators when the
 // channel block changes and at the end.
-template <int BLOCK_N, int CS>
+template <int BLOCK_N, int CS, bool FUSE>
 VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
-                           const CUtensorMap* tm_out2, uint64_t* bnready, uint8_t* slabs,
+                           const CUtensorMap* tm_out2, uint64_t* bnready, uint8_t* ring,
+                           uint64_t* zfull, uint8_t* slabs,
                            uint64_t* sfull, uint64_t* sempty, float* s_sum, float* s_sq,
                            float* s_x2, float* s_scr, int rank, int first_item, int item_stride,
                            int total_tiles, int sw, int lane) {
@@ -449,8 +459,11 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       if (cur_ntile >= 0) global_flush(cur_ntile);
       cur_ntile = n_tile;
     }
-    mbar_wait(&sfull[slot], sphase);
-    const uint32_t slab = smem_u32(slabs) + slot * kSlabBytes;
+    constexpr bool direct = FUSE;   // one tile per CTA: slab j lives in the dead operand ring
+    if (direct) mbar_wait(&zfull[j], 0);
+    else mbar_wait(&sfull[slot], sphase);
+    const uint8_t* slab_ptr = direct ? ring + j * kSlabBytes : slabs + slot * kSlabBytes;
+    const uint32_t slab = smem_u32(slab_ptr);
     if (fwd_stats && live) {
       uint4 g[8];
 #pragma unroll
@@ -514,7 +527,10 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       combine(cur_j, par);
       par ^= 1;
     }
-    if (st == 0) {
+    if (st == 0 && direct) {
+      tma_store_5d(tm_out, slab_ptr, st_c, st_w, p.out_d2, st_h, st_b);
+      bulk_commit_group();
+    } else if (st == 0) {
       if (!(p.dbg & (4 | 8)))
         tma_store_5d(tm_out, slabs + slot * kSlabBytes, st_c, st_w, p.out_d2, st_h, st_b);
       bulk_commit_group();
@@ -529,13 +545,13 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
         mbar_arrive(&sempty[slot]);
       }
     }
-    if (++slot == SC::kSlots) {
+    if (!direct && ++slot == SC::kSlots) {
       slot = 0;
       sphase ^= 1;
     }
   }
   if (sums && cur_ntile >= 0) global_flush(cur_ntile);
-  if (p.fuse_bn && cur_ntile >= 0) {
+  if (FUSE && cur_ntile >= 0) {
     // ---- grid barrier: every CTA's sums are in the global accumulators after this
     if (st == 0) {
       __threadfence();
@@ -574,22 +590,10 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       const int zh0 = (mt % p.tiles_h) * p.th;
       const int zb0 = (mt / p.tiles_h) * p.tn;
       for (int jz = 0; jz < SC::kSlabs; ++jz) {
-        mbar_wait(&sfull[slot], sphase);
-        tma_store_5d(tm_out2, slabs + slot * kSlabBytes, p.out_c0 + n_tile0 * BLOCK_N + jz * 64,
-                     zw0, p.out_d2, zh0, zb0);
+        mbar_wait(&zfull[SC::kSlabs + jz], 0);
+        tma_store_5d(tm_out2, ring + (SC::kSlabs + jz) * kSlabBytes,
+                     p.out_c0 + n_tile0 * BLOCK_N + jz * 64, zw0, p.out_d2, zh0, zb0);
         bulk_commit_group();
-        if (SC::kSlots > 1) {
-          bulk_wait_read1();
-          if (prev_slot >= 0) mbar_arrive(&sempty[prev_slot]);
-          prev_slot = slot;
-        } else {
-          bulk_wait_read0();
-          mbar_arrive(&sempty[slot]);
-        }
-        if (++slot == SC::kSlots) {
-          slot = 0;
-          sphase ^= 1;
-        }
       }
     }
   }
@@ -604,7 +608,7 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
 // plus as much TMA write traffic - twice the 128 B/cycle the shared memory can move -
 // which is what pins the single-CTA kernel near half of the tensor peak; in pair mode a
 // CTA reads/writes 3/4 (N=128) or 1/2 (N=256) as many bytes per MAC.
-template <int BLOCK_N, int CS>
+template <int BLOCK_N, int CS, bool FUSE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
@@ -623,7 +627,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* sfull_bar = pfull_bar + Cfg::kStages;  // epilogue -> statistics warps: slab staged
   uint64_t* sempty_bar = sfull_bar + 2;            // slab stored, slot free
   uint64_t* bnready_bar = sempty_bar + 2;          // fused BN: scale / shift ready
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bnready_bar + 1);
+  uint64_t* zfull_bar = bnready_bar + 1;           // fused BN: slab (pass, j) staged in the ring
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(zfull_bar + 8);
   float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + Cfg::kBarBytes);
   float* s_sq = s_sum + BLOCK_N;
   float* s_x2 = s_sq + BLOCK_N;  // second BN branch (fused backward reduction)
@@ -645,6 +650,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       mbar_init(&sempty_bar[s], 1);
     }
     mbar_init(bnready_bar, kStatThreads);
+    for (int s = 0; s < 8; ++s) mbar_init(&zfull_bar[s], kEpiThreads);
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmOut);
@@ -683,12 +689,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, CS>(p, &tmOut, &tmOut2, bnready_bar, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, rank,
-                            first_item, item_stride, total_tiles, warp - kStatWarp0, lane);
+    conv_stats<BLOCK_N, CS, FUSE>(p, &tmOut, &tmOut2, bnready_bar, smem, zfull_bar, slabs, sfull_bar,
+                                  sempty_bar, s_sum, s_sq, s_x2, s_scr, rank, first_item,
+                                  item_stride, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, CS>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
-                               s_sum, s_sq, bnready_bar, rank, first_item, item_stride, total_tiles, warp, lane);
+    conv_epilogue<BLOCK_N, CS, FUSE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar,
+                                     sempty_bar, s_sum, s_sq, bnready_bar, smem, zfull_bar, rank,
+                                     first_item, item_stride, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
    if (warp == 0) {
@@ -906,12 +914,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, 1>(p, &tmOut, &tmOut, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
+    conv_stats<BLOCK_N, 1, false>(p, &tmOut, &tmOut, nullptr, nullptr, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
                            blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
-                              s_sum, s_sq, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
+    conv_epilogue<BLOCK_N, 1, false>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
+                              s_sum, s_sq, nullptr, nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
    if (warp == 0) {
@@ -1075,12 +1083,12 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, 1>(p, &tmOut, &tmOut, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
+    conv_stats<BLOCK_N, 1, false>(p, &tmOut, &tmOut, nullptr, nullptr, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
                            blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, 1>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
-                              s_sum, s_sq, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
+    conv_epilogue<BLOCK_N, 1, false>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
+                              s_sum, s_sq, nullptr, nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
    if (warp == 0) {
