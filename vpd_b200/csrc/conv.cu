@@ -397,16 +397,20 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
   return 0;
 }
 
-template <int BN, int CS, bool FUSE>
+static int conv_mode(const ConvLaunch& L) {
+  return L.p.stats != nullptr ? 1 : (L.p.bnb == 1 ? 2 : (L.p.bnb == 2 ? 3 : 0));
+}
+
+template <int BN, int CS, bool FUSE, int MODE>
 static int launch_bn_impl(const ConvLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, CS, FUSE>,
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, CS, FUSE, MODE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         ConvCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  VPD_CHECK_CUDA(launch_kernel_cluster(CS, conv_igemm_kernel<BN, CS, FUSE>, dim3(L.grid),
+  VPD_CHECK_CUDA(launch_kernel_cluster(CS, conv_igemm_kernel<BN, CS, FUSE, MODE>, dim3(L.grid),
                                        dim3(kConvThreads), ConvCfg<BN>::kSmemBytes, stream, L.a0,
                                        L.a1, L.o, L.o2, L.p));
   VPD_LAUNCHED(1);
@@ -417,21 +421,51 @@ static int launch_bn_impl(const ConvLaunch& L, cudaStream_t stream) {
 // flavours in one kernel doubled its code and slowed every launch (instruction cache)
 template <int BN, int CS>
 static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
-  if (CS == 1 && L.fused_bn) return launch_bn_impl<BN, 1, true>(L, stream);
-  return launch_bn_impl<BN, CS, false>(L, stream);
+  if (CS == 1 && L.fused_bn) return launch_bn_impl<BN, 1, true, 1>(L, stream);
+  if (CS != 1) return launch_bn_impl<BN, CS, false, -1>(L, stream);   // opt-in pair mode: generic
+  switch (conv_mode(L)) {
+    case 1: return launch_bn_impl<BN, 1, false, 1>(L, stream);
+    case 2: return launch_bn_impl<BN, 1, false, 2>(L, stream);
+    case 3: return launch_bn_impl<BN, 1, false, 3>(L, stream);
+    default: return launch_bn_impl<BN, 1, false, 0>(L, stream);
+  }
 }
 
-template <int CHUNKS>
-static int launch_halo(const ConvLaunch& L, cudaStream_t stream) {
+template <int CHUNKS, int MODE>
+static int launch_halo_impl(const ConvLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<CHUNKS>,
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<CHUNKS, MODE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         HaloCfg<CHUNKS>::kSmemBytes));
     attr_set = true;
   }
-  VPD_CHECK_CUDA(launch_kernel(conv3x3_halo_kernel<CHUNKS>, dim3(L.grid), dim3(kConvThreads),
+  VPD_CHECK_CUDA(launch_kernel(conv3x3_halo_kernel<CHUNKS, MODE>, dim3(L.grid), dim3(kConvThreads),
                                HaloCfg<CHUNKS>::kSmemBytes, stream, L.a0, L.o, L.p));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+template <int CHUNKS>
+static int launch_halo(const ConvLaunch& L, cudaStream_t stream) {
+  switch (conv_mode(L)) {
+    case 1: return launch_halo_impl<CHUNKS, 1>(L, stream);
+    case 2: return launch_halo_impl<CHUNKS, 2>(L, stream);
+    case 3: return launch_halo_impl<CHUNKS, 3>(L, stream);
+    default: return launch_halo_impl<CHUNKS, 0>(L, stream);
+  }
+}
+template <int MODE>
+static int launch_halo_stream_impl(const ConvLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_stream_kernel<128, MODE>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        HaloStreamCfg<128>::kSmemBytes));
+    attr_set = true;
+  }
+  VPD_CHECK_CUDA(launch_kernel(conv3x3_halo_stream_kernel<128, MODE>, dim3(L.grid),
+                               dim3(kConvThreads), HaloStreamCfg<128>::kSmemBytes, stream, L.a0,
+                               L.o, L.p));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -454,17 +488,12 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t stream) {
   const ConvLaunch& L = (g_conv_trace != nullptr || dbg_skip != 0) ? traced : L0;
   if (L.halo == 1) return launch_halo<1>(L, stream);
   if (L.halo == 3) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      VPD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_stream_kernel<128>,
-                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          HaloStreamCfg<128>::kSmemBytes));
-      attr_set = true;
+    switch (conv_mode(L)) {
+      case 1: return launch_halo_stream_impl<1>(L, stream);
+      case 2: return launch_halo_stream_impl<2>(L, stream);
+      case 3: return launch_halo_stream_impl<3>(L, stream);
+      default: return launch_halo_stream_impl<0>(L, stream);
     }
-    VPD_CHECK_CUDA(launch_kernel(conv3x3_halo_stream_kernel<128>, dim3(L.grid), dim3(kConvThreads),
-                                 HaloStreamCfg<128>::kSmemBytes, stream, L.a0, L.o, L.p));
-    VPD_LAUNCHED(1);
-    return 0;
   }
   if (L.cluster == 2) {
     switch (L.block_n) {

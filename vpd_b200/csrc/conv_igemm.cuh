@@ -293,7 +293,11 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 // combined through a small double-buffered scratch with exclusive owners (no shared-memory
 // float atomics: those are CAS loops) and reach the fp64 global accumulators when the
 // channel block changes and at the end.
-template <int BLOCK_N, int CS, bool FUSE>
+// MODE: 0 store only (eval / plain dgrad), 1 BatchNorm statistics (training forward),
+// 2 / 3 fused BN-backward reduction with one / two BN branches (dgrad), -1 decided at run time. The specialised kernels
+// carry only their own reduction code: these kernels are large enough for instruction-cache
+// misses to show (keeping two epilogue flavours in one kernel cost ~10 % on the deep layers).
+template <int BLOCK_N, int CS, bool FUSE, int MODE>
 VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
                            const CUtensorMap* tm_out2, uint64_t* bnready, uint8_t* ring,
                            uint64_t* zfull, uint8_t* slabs,
@@ -304,8 +308,8 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
   const int cg = lane & 7;     // 16-byte chunk (8 channels) of the 128-byte slab row
   const int rsub = lane >> 3;  // row within the 4 rows one warp instruction covers
   const int ltw = __ffs(p.tw) - 1, lth = __ffs(p.th) - 1;  // tile extents are powers of two
-  const int nbr = p.bnb;
-  const bool fwd_stats = p.stats != nullptr;
+  const int nbr = MODE < 0 ? p.bnb : (MODE == 2 ? 1 : (MODE == 3 ? 2 : 0));
+  const bool fwd_stats = MODE < 0 ? (p.stats != nullptr) : (MODE == 1);
   const bool sums = fwd_stats || nbr > 0;
   const bool live = !(p.dbg & (4 | 16));
   const int st = threadIdx.x - kStatThread0;  // 0..127
@@ -608,7 +612,7 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
 // plus as much TMA write traffic - twice the 128 B/cycle the shared memory can move -
 // which is what pins the single-CTA kernel near half of the tensor peak; in pair mode a
 // CTA reads/writes 3/4 (N=128) or 1/2 (N=256) as many bytes per MAC.
-template <int BLOCK_N, int CS, bool FUSE>
+template <int BLOCK_N, int CS, bool FUSE, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
@@ -689,7 +693,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, CS, FUSE>(p, &tmOut, &tmOut2, bnready_bar, smem, zfull_bar, slabs, sfull_bar,
+    conv_stats<BLOCK_N, CS, FUSE, MODE>(p, &tmOut, &tmOut2, bnready_bar, smem, zfull_bar, slabs, sfull_bar,
                                   sempty_bar, s_sum, s_sq, s_x2, s_scr, rank, first_item,
                                   item_stride, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
@@ -852,7 +856,7 @@ struct HaloCfg {
       kStatScratchBytes + 1024;
 };
 
-template <int CHUNKS>
+template <int CHUNKS, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ ConvParams p) {
@@ -914,7 +918,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, 1, false>(p, &tmOut, &tmOut, nullptr, nullptr, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
+    conv_stats<BLOCK_N, 1, false, MODE>(p, &tmOut, &tmOut, nullptr, nullptr, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
                            blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
@@ -1018,7 +1022,7 @@ struct HaloStreamCfg {
       3 * BLOCK_N * 4 + kStatScratchBytes + 1024;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
                            const __grid_constant__ CUtensorMap tmOut,
@@ -1083,7 +1087,7 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, 1, false>(p, &tmOut, &tmOut, nullptr, nullptr, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
+    conv_stats<BLOCK_N, 1, false, MODE>(p, &tmOut, &tmOut, nullptr, nullptr, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
                            blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
