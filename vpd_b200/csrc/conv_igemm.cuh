@@ -134,7 +134,7 @@ struct ConvCfg {
 // Epilogue, warps 2..5 (threads 64..191): drains the TMEM accumulator stages tile by tile -
 // optional folded-BN affine, residual, ReLU - and writes bf16 slabs to the staging ring.
 // It performs no reductions and no global stores.
-template <int BLOCK_N, int CS, bool FUSE>
+template <int BLOCK_N, int CS, bool FUSE, int MODE>
 VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                               uint64_t* tempty_bar, uint8_t* slabs, uint64_t* sfull,
                               uint64_t* sempty, const float* s_scale, const float* s_shift,
@@ -187,7 +187,9 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
         const int c = 2 * j + cc;
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
-        const __nv_bfloat16* resp = (FUSE && pass == 1) ? p.fres : p.residual;
+        // training-forward kernels (MODE 1): the first pass is a plain conversion
+        const __nv_bfloat16* resp =
+            (FUSE && pass == 1) ? p.fres : (MODE == 1 ? nullptr : p.residual);
         const bool do_res = resp != nullptr && valid;
         uint4 rres[4];
         if (do_res) {
@@ -212,7 +214,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
             f[k + 2] = fmaf(bf16_round(f[k + 2]), sc.z, sh.z);
             f[k + 3] = fmaf(bf16_round(f[k + 3]), sc.w, sh.w);
           }
-        } else if (p.scale != nullptr) {
+        } else if (MODE != 1 && p.scale != nullptr) {
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
             const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + k));
@@ -236,7 +238,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
             f[8 * k + 7] += bf16_hi(rres[k].w);
           }
         }
-        if ((FUSE && pass == 1) ? p.frelu : p.relu) {
+        if ((FUSE && pass == 1) ? p.frelu : (MODE != 1 && p.relu)) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
         }
@@ -698,7 +700,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                                   item_stride, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, CS, FUSE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar,
+    conv_epilogue<BLOCK_N, CS, FUSE, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar,
                                      sempty_bar, s_sum, s_sq, bnready_bar, smem, zfull_bar, rank,
                                      first_item, item_stride, total_tiles, warp, lane);
   } else {
@@ -922,7 +924,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                            blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, 1, false>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
+    conv_epilogue<BLOCK_N, 1, false, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
                               s_sum, s_sq, nullptr, nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
@@ -1091,7 +1093,7 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
                            blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, 1, false>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
+    conv_epilogue<BLOCK_N, 1, false, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
                               s_sum, s_sq, nullptr, nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
