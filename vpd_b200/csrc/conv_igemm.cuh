@@ -458,7 +458,7 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
   int n_tile = 0, w0 = 0, h0 = 0, b0 = 0;
   if (have) {
     tile_coords(tile, n_tile, w0, h0, b0);
-    if (nbr > 0 && live) issue_loads(n_tile, w0, h0, b0, 0);
+    if (nbr > 0 && live && !(p.dbg & 32)) issue_loads(n_tile, w0, h0, b0, 0);
   }
   while (have) {
     if (sums && cur_ntile != n_tile) {
@@ -525,7 +525,7 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       have = tile < total_tiles;
       if (have) tile_coords(tile, n_tile, w0, h0, b0);
     }
-    if (have && nbr > 0 && live) issue_loads(n_tile, w0, h0, b0, j);
+    if (have && nbr > 0 && live && !(p.dbg & 32)) issue_loads(n_tile, w0, h0, b0, j);
     if (sums && BLOCK_N > 64) regs_to_scratch(par);
     // every statistics thread is done with the slab (and its masked rewrite is visible)
     asm volatile("bar.sync 2, %0;" ::"n"(kStatThreads) : "memory");
