@@ -67,7 +67,8 @@ static void finish_launch(ConvLaunch* L, int cout, bool stats) {
   static const int want_pair = env_int("VPD_PAIR", 0);
   L->cluster = (want_pair && L->block_n >= 128 && m_tiles >= 2) ? 2 : 1;
   const int cs = L->cluster;
-  const int items = ((m_tiles + cs - 1) / cs) * L->p.n_tiles;  // cluster-level work items
+  const int ncls = L->p.num_classes > 1 ? L->p.num_classes : 1;
+  const int items = ((m_tiles + cs - 1) / cs) * L->p.n_tiles * ncls;  // cluster-level work items
   int clusters = device_sm_count() / cs;
   if (clusters > items) clusters = items;
   // keep the channel block fixed per CTA so BN statistics stay in shared memory
@@ -106,9 +107,17 @@ static int act_map(CUtensorMap* m, const __nv_bfloat16* x, int N, int H, int W, 
 // (64 channels x the tile's pixels); `stride` 2 addresses one pixel-parity class
 static int out_map(ConvLaunch* L, const __nv_bfloat16* out, int N, int H, int W, int C, int stride,
                    int c0, int d2) {
-  L->p.out_c0 = c0;
-  L->p.out_d2 = d2;
-  return act_map(&L->o, out, N, H, W, C, stride, L->p);
+  if (L->p.num_classes <= 1) {   // ordinary convolution: one output class over all taps
+    L->p.num_classes = 1;
+    L->p.cls[0].tap0 = 0;
+    L->p.cls[0].ntaps = L->p.num_taps;
+    L->p.cls[0].out_c0 = c0;
+    L->p.cls[0].out_d2 = d2;
+    L->p.cls[0].base = 0;
+  }
+  if (act_map(&L->o, out, N, H, W, C, stride, L->p)) return -1;
+  L->o2 = L->o;
+  return 0;
 }
 
 static void set_weights(ConvParams* p, int src, const __nv_bfloat16* w, int rows, int kdim) {
@@ -339,13 +348,18 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
   VPD_REQUIRE(g.H == 2 * Ho && g.W == 2 * Wo, "dgrad: stride 2 needs even input dims");
   // dx[2i+a, 2j+b] = sum over kh = a+1 (mod 2), kw = b+1 (mod 2) of
   //                  dy[i + (a+1-kh)/2, j + (b+1-kw)/2] * w[kh,kw]
+  // The four output-parity classes (a, b) share everything but their tap subsets and their
+  // position in dx, so they are four OUTPUT CLASSES of a single launch (four separate
+  // launches of 1-4 taps each spent most of their time in launch/drain overhead).
+  ConvLaunch* L = &Ls[0];
+  memset(L, 0, sizeof(*L));
+  ConvParams& p = L->p;
+  tile_geometry(Ho, Wo, g.N, &p);
+  int nt = 0, nc = 0;
   for (int a = 0; a < 2; ++a)
     for (int b = 0; b < 2; ++b) {
-      ConvLaunch* L = &Ls[*count];
-      memset(L, 0, sizeof(*L));
-      ConvParams& p = L->p;
-      tile_geometry(Ho, Wo, g.N, &p);
-      int nt = 0;
+      ConvParams::OutClass& c = p.cls[nc++];
+      c.tap0 = nt;
       for (int kh = 0; kh < 3; ++kh) {
         if ((a + 1 - kh) % 2 != 0) continue;
         for (int kw = 0; kw < 3; ++kw) {
@@ -360,8 +374,7 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
           t.kchunks = g.Cout / 64;
         }
       }
-      const bool fuse_ds = (a == 0 && b == 0 && dy_ds != nullptr);
-      if (fuse_ds) {
+      if (a == 0 && b == 0 && dy_ds != nullptr) {   // 1x1/2 downsample branch: extra tap of (0,0)
         ConvTap& t = p.taps[nt++];
         t.c0 = 0;
         t.d1 = 0;
@@ -371,29 +384,35 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
         t.btap = 0;
         t.kchunks = cout_ds / 64;
       }
-      p.num_taps = nt;
-      const long long base = ((long long)a * g.W + b) * g.Cin;
-      p.out = dx + base;
-      p.residual = residual ? residual + base : nullptr;
-      p.out_sn = (long long)g.H * g.W * g.Cin;
-      p.out_sh = (long long)2 * g.W * g.Cin;
-      p.out_sw = (long long)2 * g.Cin;
-      set_fuse(&p, base);
-      finish_launch(L, g.Cin, p.bnb > 0);
-      if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
-      set_weights(&p, 0, wT_tap, g.Cin, g.Cout);
-      set_weights(&p, 1, wT_tap, g.Cin, g.Cout);
-      // parity class (a, b) of dx through the stride-2 view: channel coordinate b*Cin + c,
+      c.ntaps = nt - c.tap0;
+      // class (a, b) of dx through the stride-2 view: channel coordinate b*Cin + ch,
       // parity coordinate a, tile coordinates in units of the half-resolution grid
-      if (out_map(L, dx, g.N, g.H, g.W, g.Cin, 2, b * g.Cin, a)) return -1;
-      if (fuse_ds) {
-        if (act_map(&L->a1, dy_ds, g.N, Ho, Wo, cout_ds, 1, p)) return -1;
-        set_weights(&p, 1, wT_ds, g.Cin, cout_ds);
-      } else {
-        L->a1 = L->a0;
-      }
-      ++*count;
+      c.out_c0 = b * g.Cin;
+      c.out_d2 = a;
+      c.base = ((long long)a * g.W + b) * g.Cin;
     }
+  VPD_REQUIRE(nt <= kMaxTaps, "dgrad: too many taps (%d)", nt);
+  p.num_taps = nt;
+  p.num_classes = 4;
+  p.out = dx;
+  p.residual = residual;
+  p.out_sn = (long long)g.H * g.W * g.Cin;
+  p.out_sh = (long long)2 * g.W * g.Cin;
+  p.out_sw = (long long)2 * g.Cin;
+  set_fuse(&p, 0);
+  finish_launch(L, g.Cin, p.bnb > 0);
+  if (act_map(&L->a0, dy, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
+  set_weights(&p, 0, wT_tap, g.Cin, g.Cout);
+  set_weights(&p, 1, wT_tap, g.Cin, g.Cout);
+  if (dy_ds != nullptr) {
+    if (act_map(&L->a1, dy_ds, g.N, Ho, Wo, cout_ds, 1, p)) return -1;
+    set_weights(&p, 1, wT_ds, g.Cin, cout_ds);
+  } else {
+    L->a1 = L->a0;
+  }
+  if (out_map(L, dx, g.N, g.H, g.W, g.Cin, 2, 0, 0)) return -1;
+  L->o2 = L->o;
+  *count = 1;
   return 0;
 }
 

@@ -63,7 +63,16 @@ struct ConvParams {
   int batch, out_h, out_w;  // valid extents of the (n, h, w) tile coordinates
   int cout;
   __nv_bfloat16* out;                 // written through the output tensor map (TMA store)
-  int out_c0, out_d2;                 // channel / parity coordinate offsets of that map's view
+  // Output classes. Ordinary convolutions have one; the data gradient of a stride-2 conv has
+  // four (one per output-pixel parity), each with its own tap subset, its own coordinate
+  // offsets in the strided output view and its own base offset for `out`-addressed operands.
+  // They run as ONE launch: tile index = class * tiles_per_class + (pixel tile, channel block).
+  int num_classes;
+  struct OutClass {
+    int tap0, ntaps;       // taps[tap0 .. tap0 + ntaps)
+    int out_c0, out_d2;    // channel / parity coordinate offsets of the output view
+    long long base;        // element offset of the class's first output pixel
+  } cls[4];
   const __nv_bfloat16* residual;      // same addressing as out, or null
   long long out_sn, out_sh, out_sw;   // element strides of out/residual
   const float* scale;                 // [cout] or null
@@ -101,6 +110,25 @@ struct ConvParams {
   unsigned int* fbar;            // zeroed every step
   int dbg;  // diagnostics (VPD_DBG_SKIP): bit0 skip the A loads, bit1 skip the B loads, bit2 skip the epilogue body
 };
+struct TileCoord {
+  int cls, n_tile, w0, h0, b0;
+};
+// tile index -> (class, channel block, first pixel); CS = CTAs per cluster, rank = CTA in it
+template <int CS>
+VPD_DEVINL TileCoord decode_tile(const ConvParams& p, int tile, int rank) {
+  TileCoord t;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int per_class = ((m_tiles + CS - 1) / CS) * p.n_tiles;
+  t.cls = p.num_classes > 1 ? tile / per_class : 0;
+  const int inner = tile - t.cls * per_class;
+  t.n_tile = inner % p.n_tiles;
+  int mt = (inner / p.n_tiles) * CS + rank;
+  t.w0 = (mt % p.tiles_w) * p.tw;
+  mt /= p.tiles_w;
+  t.h0 = (mt % p.tiles_h) * p.th;
+  t.b0 = (mt / p.tiles_h) * p.tn;
+  return t;
+}
 VPD_DEVINL void trace_mark(const ConvParams& p, int slot) {
   if (p.trace != nullptr) p.trace[blockIdx.x * 16 + slot] = clock64();
 }
@@ -159,17 +187,14 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
   int slot = 0;
   uint32_t sphase = 0;
   for (int tile = first_item; tile < total_tiles; tile += item_stride) {
-    const int n_tile = tile % p.n_tiles;
-    int mt = (tile / p.n_tiles) * CS + rank;
-    const int w0 = (mt % p.tiles_w) * p.tw;
-    mt /= p.tiles_w;
-    const int h0 = (mt % p.tiles_h) * p.th;
-    const int b0 = (mt / p.tiles_h) * p.tn;
-    const int w = w0 + r % p.tw;
-    const int h = h0 + (r / p.tw) % p.th;
-    const int n = b0 + r / (p.tw * p.th);
+    const TileCoord tc = decode_tile<CS>(p, tile, rank);
+    const int n_tile = tc.n_tile;
+    const int w = tc.w0 + r % p.tw;
+    const int h = tc.h0 + (r / p.tw) % p.th;
+    const int n = tc.b0 + r / (p.tw * p.th);
     const bool valid = (n < p.batch) && (h < p.out_h) && (w < p.out_w);
-    const long long off = n * p.out_sn + h * p.out_sh + w * p.out_sw + n_tile * BLOCK_N;
+    const long long off =
+        p.cls[tc.cls].base + n * p.out_sn + h * p.out_sh + w * p.out_sw + n_tile * BLOCK_N;
 
     mbar_wait(&tfull_bar[as], aphase);
     if (tile == first_item && threadIdx.x == kEpiThread0) trace_mark(p, 5);
@@ -405,9 +430,10 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
   }
   uint4 zz[8], y0[8], y1[8];
   float m0[8], m1[8];
+  int cls = 0;  // output class of the tile the cursor is on
   auto issue_loads = [&](int n_tile, int w0, int h0, int b0, int j) {
     const int ch = n_tile * BLOCK_N + j * 64 + cg * 8;
-    const long long base = b0 * p.out_sn + h0 * p.out_sh + w0 * p.out_sw + ch;
+    const long long base = p.cls[cls].base + b0 * p.out_sn + h0 * p.out_sh + w0 * p.out_sw + ch;
     const bool full = (b0 + p.tn <= p.batch) && (h0 + p.th <= p.out_h) && (w0 + p.tw <= p.out_w);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -418,7 +444,7 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
              (w0 + (r & (p.tw - 1)) < p.out_w);
       }
       // rows outside the tensor hold g = 0 in the slab: any finite operand will do
-      const long long off = ok ? base + rel[i] : static_cast<long long>(ch);
+      const long long off = ok ? base + rel[i] : p.cls[cls].base + ch;
       zz[i] = ldg_nc_v4(p.bz + off);
       y0[i] = ldg_nc_v4(p.by[0] + off);
       if (nbr > 1) y1[i] = ldg_nc_v4(p.by[1] + off);
@@ -435,12 +461,12 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
     }
   };
   auto tile_coords = [&](int tile, int& n_tile, int& w0, int& h0, int& b0) {
-    n_tile = tile % p.n_tiles;
-    int mt = (tile / p.n_tiles) * CS + rank;
-    w0 = (mt % p.tiles_w) * p.tw;
-    mt /= p.tiles_w;
-    h0 = (mt % p.tiles_h) * p.th;
-    b0 = (mt / p.tiles_h) * p.tn;
+    const TileCoord tc = decode_tile<CS>(p, tile, rank);
+    cls = tc.cls;
+    n_tile = tc.n_tile;
+    w0 = tc.w0;
+    h0 = tc.h0;
+    b0 = tc.b0;
   };
   // shared-memory address of this lane's 16-byte chunk in row i (relative to the slab)
   uint32_t srow[8];
@@ -516,7 +542,8 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       fence_proxy_async();
     }
     // store coordinates of the slab just processed
-    const int st_c = p.out_c0 + n_tile * BLOCK_N + j * 64, st_w = w0, st_h = h0, st_b = b0;
+    const int st_c = p.cls[cls].out_c0 + n_tile * BLOCK_N + j * 64, st_w = w0, st_h = h0, st_b = b0;
+    const int st_d2 = p.cls[cls].out_d2;
     const int cur_j = j;
     // advance, and request the next slab's operands before anything else
     if (++j == SC::kSlabs) {
@@ -534,11 +561,11 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       par ^= 1;
     }
     if (st == 0 && direct) {
-      tma_store_5d(tm_out, slab_ptr, st_c, st_w, p.out_d2, st_h, st_b);
+      tma_store_5d(tm_out, slab_ptr, st_c, st_w, st_d2, st_h, st_b);
       bulk_commit_group();
     } else if (st == 0) {
       if (!(p.dbg & (4 | 8)))
-        tma_store_5d(tm_out, slabs + slot * kSlabBytes, st_c, st_w, p.out_d2, st_h, st_b);
+        tma_store_5d(tm_out, slabs + slot * kSlabBytes, st_c, st_w, st_d2, st_h, st_b);
       bulk_commit_group();
       if (SC::kSlots > 1) {
         // release the slot of the PREVIOUS slab: its store has finished reading shared memory
@@ -598,7 +625,7 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       for (int jz = 0; jz < SC::kSlabs; ++jz) {
         mbar_wait(&zfull[SC::kSlabs + jz], 0);
         tma_store_5d(tm_out2, ring + (SC::kSlabs + jz) * kSlabBytes,
-                     p.out_c0 + n_tile0 * BLOCK_N + jz * 64, zw0, p.out_d2, zh0, zb0);
+                     p.cls[0].out_c0 + n_tile0 * BLOCK_N + jz * 64, zw0, p.cls[0].out_d2, zh0, zb0);
         bulk_commit_group();
       }
     }
@@ -689,7 +716,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   // work items are (group of CS pixel tiles, channel block); a CTA takes the pixel
   // tile `group*CS + rank` (possibly past the end: loads zero-fill, stores masked)
   const int rank = CS > 1 ? static_cast<int>(cluster_ctarank()) : 0;
-  const int total_tiles = ((m_tiles + CS - 1) / CS) * p.n_tiles;
+  const int total_tiles = ((m_tiles + CS - 1) / CS) * p.n_tiles * p.num_classes;
   const int first_item = blockIdx.x / CS;
   const int item_stride = gridDim.x / CS;
 
@@ -711,13 +738,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_item; tile < total_tiles; tile += item_stride) {
-        const int n_tile = tile % p.n_tiles;
-        int mt = (tile / p.n_tiles) * CS + rank;
-        const int w0 = (mt % p.tiles_w) * p.tw;
-        mt /= p.tiles_w;
-        const int h0 = (mt % p.tiles_h) * p.th;
-        const int b0 = (mt / p.tiles_h) * p.tn;
-        for (int t = 0; t < p.num_taps; ++t) {
+        const TileCoord tc = decode_tile<CS>(p, tile, rank);
+        const int n_tile = tc.n_tile, w0 = tc.w0, h0 = tc.h0, b0 = tc.b0;
+        const int tap_end = p.cls[tc.cls].tap0 + p.cls[tc.cls].ntaps;
+        for (int t = p.cls[tc.cls].tap0; t < tap_end; ++t) {
           const ConvTap tap = p.taps[t];
           const CUtensorMap* ma = tap.src ? &tmA1 : &tmA0;
           for (int kc = 0; kc < tap.kchunks; ++kc) {
@@ -748,13 +772,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const bool issuer = elect_one();  // executed by the whole (converged) warp
     if (issuer && (CS == 1 || rank == 0)) {
       constexpr uint32_t idesc = make_idesc_bf16(CS * kBlockM, BLOCK_N, 0, 0);
-      int total_kb = 0;
-      for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].kchunks;
+      int kb_cls[4] = {0, 0, 0, 0};
+      for (int c = 0; c < p.num_classes; ++c)
+        for (int t = 0; t < p.cls[c].ntaps; ++t) kb_cls[c] += p.taps[p.cls[c].tap0 + t].kchunks;
+      const int per_class = total_tiles / p.num_classes;
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
       for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+        const int c_idx = p.num_classes > 1 ? tile / per_class : 0;
+        const int total_kb = c_idx == 0 ? kb_cls[0] : (c_idx == 1 ? kb_cls[1] : (c_idx == 2 ? kb_cls[2] : kb_cls[3]));
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -791,11 +819,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     } else if (issuer && CS == 2) {
       // peer CTA: relay "my stage has landed" to the leader's MMA thread
       const uint32_t pfull_remote0 = mapa_shared(smem_u32(&pfull_bar[0]), 0);
-      int total_kb = 0;
-      for (int t = 0; t < p.num_taps; ++t) total_kb += p.taps[t].kchunks;
+      int kb_cls[4] = {0, 0, 0, 0};
+      for (int c = 0; c < p.num_classes; ++c)
+        for (int t = 0; t < p.cls[c].ntaps; ++t) kb_cls[c] += p.taps[p.cls[c].tap0 + t].kchunks;
+      const int per_class = total_tiles / p.num_classes;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = first_item; tile < total_tiles; tile += item_stride) {
+        const int c_idx = p.num_classes > 1 ? tile / per_class : 0;
+        const int total_kb = c_idx == 0 ? kb_cls[0] : (c_idx == 1 ? kb_cls[1] : (c_idx == 2 ? kb_cls[2] : kb_cls[3]));
         for (int kb = 0; kb < total_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           mbar_arrive_remote(pfull_remote0 + stage * 8);
