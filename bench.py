@@ -148,7 +148,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.QUERY,
-                 '--format=csv,noheader,nounits', '-lms', '25'],
+                 '--format=csv,noheader,nounits', '-lms', '10'],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -328,7 +328,7 @@ def run_native(args, rank, world, local_rank):
         # DRAM traffic per launch of the family's largest member, from the committed ncu
         # --set full capture (profiles/): not measurable live without the profiler
         traffic, traffic_of = None, None
-        tpath = os.path.join(ROOT, 'profiles', 'r01c_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'r01d_traffic.json')
         if os.path.exists(tpath):
             with open(tpath) as fp:
                 tj = json.load(fp)
