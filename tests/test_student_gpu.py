@@ -305,3 +305,39 @@ def test_apply_corpus_extraction_pickles(tmp_path):
     a = vapply.shard_videos([5, 0, 3], 2, 0)
     b = vapply.shard_videos([5, 0, 3], 2, 1)
     assert sorted(a + b) == [0, 1, 2]
+
+
+def test_fused_bn_apply_matches_separate_kernels(monkeypatch):
+    """VPD_FUSE_BNFWD=1 (BatchNorm apply inside the single-tile conv launches, behind a grid
+    barrier) must give the same step as the separate bn_apply kernels: same loss, same
+    running statistics / num_batches_tracked, fewer launches."""
+    from vpd_b200 import ModelTrainer
+    from vpd_b200._lib import lib
+    from vpd_b200.assemble import assemble_batch
+    B = 32
+    rgb, flow = synth.crops(B, seed=51)
+    teach = synth.teacher(B, seed=52)
+    fl = synth.flips(B, seed=53)
+    res = []
+    for fused in ('0', '1'):
+        monkeypatch.setenv('VPD_FUSE_BNFWD', fused)
+        m = _model(2)
+        tr = ModelTrainer(m, True)
+        opt, _ = tr.get_optimizer(5e-4)
+        batch = assemble_batch(rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD,
+                               flip=fl.to(dev()), teacher=teach.to(dev()))
+        tr.epoch([batch], optimizer=opt)            # builds the plan under this setting
+        n0 = lib().call('vpd_launch_count')
+        loss = tr.epoch([batch], optimizer=opt)
+        torch.cuda.synchronize()
+        launches = lib().call('vpd_launch_count') - n0
+        sd = {k: v.float().cpu() for k, v in m.state_dict().items()}
+        res.append((loss, launches, sd))
+    (l0, n0, s0), (l1, n1, s1) = res
+    assert n1 < n0, (n0, n1)                        # the fused path really ran
+    assert abs(l0 - l1) <= 2e-3 * abs(l0), (l0, l1)
+    for k in s0:
+        if k.endswith('num_batches_tracked'):
+            assert torch.equal(s0[k], s1[k]), k
+        elif 'running_' in k:
+            assert torch.allclose(s0[k], s1[k], rtol=2e-2, atol=2e-3), k

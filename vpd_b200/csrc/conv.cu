@@ -235,7 +235,9 @@ int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
   // BatchNorm apply behind a grid barrier: every CTA must hold its only tile's accumulator
   // in TMEM across the barrier, and all CTAs must be co-resident (grid <= SMs, 1 CTA/SM)
   const int items = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
-  static const int fuse_on = env_int("VPD_FUSE_BNFWD", 0);  // correct, measured neutral (3.87-3.93 vs 3.89 ms/step): opt-in
+  // correct, measured neutral (3.87-3.93 vs 3.89 ms/step): opt-in; read at every planning so
+  // that a test can build one net with and one without it
+  const int fuse_on = env_int("VPD_FUSE_BNFWD", 0);
   if (fuse_on && e.fuse_bn && e.stats != nullptr && L->cluster == 1 && items == L->grid &&
       L->grid <= device_sm_count()) {
     p.fuse_bn = 1;
