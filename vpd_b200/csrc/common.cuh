@@ -98,6 +98,13 @@ VPD_DEVINL void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 
 // ... have completed (writes performed)
 VPD_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// asynchronous L2 prefetch of a contiguous global range (bytes % 16 == 0)
+VPD_DEVINL void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)),
+               "r"(bytes)
+               : "memory");
+}
+
 // 1-D bulk copy global -> shared (contiguous bytes, size % 16 == 0), completing on an mbarrier
 VPD_DEVINL void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile(

@@ -189,6 +189,8 @@ static void set_epilogue(ConvParams* p, const ConvEpilogue& e) {
 int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
                   const __nv_bfloat16* w_tap, __nv_bfloat16* y, const ConvEpilogue& e) {
   memset(L, 0, sizeof(*L));
+  L->w_ptr = w_tap;
+  L->w_bytes = (long long)g.k * g.k * g.Cout * g.Cin * 2;
   VPD_REQUIRE(g.Cin % 64 == 0 && g.Cout % 64 == 0, "conv: Cin/Cout must be multiples of 64 (%d,%d)",
               g.Cin, g.Cout);
   VPD_REQUIRE(g.stride == 1 || g.stride == 2, "conv: stride %d unsupported", g.stride);
@@ -254,6 +256,8 @@ int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
 int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
                   const __nv_bfloat16* w_stem, __nv_bfloat16* y, const ConvEpilogue& e) {
   memset(L, 0, sizeof(*L));
+  L->w_ptr = w_stem;
+  L->w_bytes = 7LL * 64 * 64 * 2;
   VPD_REQUIRE(H % 2 == 0 && W % 8 == 0, "stem: H must be even and W a multiple of 8 (%d,%d)", H, W);
   const int Ho = H / 2, Wo = W / 2, Hp = H + 6, Wp = W + 8;
   ConvParams& p = L->p;
@@ -314,6 +318,8 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
     VPD_REQUIRE(g.k == 2 * g.pad + 1, "dgrad: stride-1 conv must be 'same' padded");
     ConvLaunch* L = &Ls[0];
     memset(L, 0, sizeof(*L));
+    L->w_ptr = wT_tap;
+    L->w_bytes = (long long)g.k * g.k * g.Cout * g.Cin * 2;
     ConvParams& p = L->p;
     tile_geometry(g.H, g.W, g.N, &p);
     p.num_taps = g.k * g.k;
@@ -355,6 +361,8 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
   // launches of 1-4 taps each spent most of their time in launch/drain overhead).
   ConvLaunch* L = &Ls[0];
   memset(L, 0, sizeof(*L));
+  L->w_ptr = wT_tap;
+  L->w_bytes = (long long)g.k * g.k * g.Cout * g.Cin * 2;
   ConvParams& p = L->p;
   tile_geometry(Ho, Wo, g.N, &p);
   int nt = 0, nc = 0;

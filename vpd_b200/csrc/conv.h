@@ -10,6 +10,8 @@ struct ConvLaunch {
   CUtensorMap o;       // output view written by the TMA tile stores
   CUtensorMap o2;      // second output (z) of a conv with the BatchNorm apply fused in
   int fused_bn;        // 1: this launch also applies its BatchNorm (no bn_apply kernel needed)
+  const void* w_ptr;   // this launch's (main) weight block, for the previous launch's L2 prefetch
+  long long w_bytes;
   ConvParams p;
   int block_n;
   int cluster;  // CTAs per cluster along M (weight multicast)
@@ -75,6 +77,11 @@ int plan_conv_dgrad(ConvLaunch* L, int* count, const ConvGeom& g, const __nv_bfl
                     const __nv_bfloat16* wT_ds, int cout_ds, const ConvBwdFuse* fuse = nullptr);
 
 int launch_conv(const ConvLaunch& L, cudaStream_t stream);
+// `prev` pulls the weights of `next` into L2 while it runs
+inline void chain_weight_prefetch(ConvLaunch* prev, const ConvLaunch& next) {
+  prev->p.pf_ptr = static_cast<const __nv_bfloat16*>(next.w_ptr);
+  prev->p.pf_bytes = next.w_bytes;
+}
 
 struct WgradLaunch {
   CUtensorMap x, dy;

@@ -108,6 +108,10 @@ struct ConvParams {
   const __nv_bfloat16* fres;     // residual (same addressing as out) or null
   int frelu;
   unsigned int* fbar;            // zeroed every step
+  // weights of the NEXT convolution in the stream: every CTA pulls one slice into L2 while
+  // this kernel runs (they come from HBM once per step and nothing else would hide that)
+  const __nv_bfloat16* pf_ptr;
+  long long pf_bytes;
   int dbg;  // diagnostics (VPD_DBG_SKIP): bit0 skip the A loads, bit1 skip the B loads, bit2 skip the epilogue body
 };
 struct TileCoord {
@@ -128,6 +132,17 @@ VPD_DEVINL TileCoord decode_tile(const ConvParams& p, int tile, int rank) {
   t.h0 = (mt % p.tiles_h) * p.th;
   t.b0 = (mt / p.tiles_h) * p.tn;
   return t;
+}
+// one thread per CTA: this CTA's slice of the next convolution's weights -> L2
+VPD_DEVINL void conv_prefetch_next(const ConvParams& p) {
+  if (p.pf_ptr == nullptr) return;
+  const long long per = ((p.pf_bytes / gridDim.x) + 15) & ~15LL;
+  const long long beg = per * blockIdx.x;
+  long long n = p.pf_bytes - beg;
+  if (n > per) n = per;
+  if (n >= 16)
+    bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(p.pf_ptr) + beg,
+                     static_cast<uint32_t>(n & ~15LL));
 }
 VPD_DEVINL void trace_mark(const ConvParams& p, int slot) {
   if (p.trace != nullptr) p.trace[blockIdx.x * 16 + slot] = clock64();
@@ -687,6 +702,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmOut);
+    conv_prefetch_next(p);
   }
   if (warp == 1) {
     if (CS == 2) {
@@ -933,6 +949,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmOut);
+    conv_prefetch_next(p);
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);
@@ -1103,6 +1120,7 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
     fence_mbar_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmOut);
+    conv_prefetch_next(p);
   }
   if (warp == 1) {
     tmem_alloc(tmem_ptr, Cfg::kTmemCols);

@@ -698,6 +698,36 @@ static Plan* get_plan(Net* n, int B) {
     delete P;
     return nullptr;
   }
+  // chain the L2 weight prefetch along the execution order of the training step
+  {
+    static const bool pf_on = getenv("VPD_WEIGHT_PREFETCH") == nullptr ||
+                              getenv("VPD_WEIGHT_PREFETCH")[0] != '0';
+    std::vector<ConvLaunch*> order;
+    order.push_back(&P->stem_train);
+    for (size_t i = 0; i < nb; ++i) {
+      order.push_back(&P->c1_train[i]);
+      order.push_back(&P->c2_train[i]);
+      if (n->blocks[i].has_ds) order.push_back(&P->ds_train[i]);
+    }
+    if (n->grads)
+      for (int i = (int)nb - 1; i >= 0; --i) {
+        order.push_back(&P->dgrad2[i]);
+        for (auto& L : P->dgrad1[i]) order.push_back(&L);
+      }
+    if (pf_on)
+      for (size_t k = 0; k + 1 < order.size(); ++k) chain_weight_prefetch(order[k], *order[k + 1]);
+    // evaluation chain (apply path)
+    std::vector<ConvLaunch*> ev_order;
+    ev_order.push_back(&P->stem_eval);
+    for (size_t i = 0; i < nb; ++i) {
+      ev_order.push_back(&P->c1_eval[i]);
+      if (n->blocks[i].has_ds) ev_order.push_back(&P->ds_eval[i]);
+      ev_order.push_back(&P->c2_eval[i]);
+    }
+    if (pf_on)
+      for (size_t k = 0; k + 1 < ev_order.size(); ++k)
+        chain_weight_prefetch(ev_order[k], *ev_order[k + 1]);
+  }
   n->plans[B] = P;
   return P;
 }
