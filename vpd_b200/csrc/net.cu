@@ -162,9 +162,27 @@ struct SideStream {
   }
 };
 
+struct StepGraphKey {
+  int B;
+  const void *x_nchw, *x_stem, *target, *loss;
+  cudaStream_t stream;
+  bool operator==(const StepGraphKey& o) const {
+    return B == o.B && x_nchw == o.x_nchw && x_stem == o.x_stem && target == o.target &&
+           loss == o.loss && stream == o.stream;
+  }
+};
+struct StepGraph {
+  StepGraphKey key;
+  int seen;              // eager runs so far (< 0: capture failed, stay eager)
+  cudaGraphExec_t exec;
+  int launches = 0;      // kernels per replay (for vpd_launch_count)
+};
+
 struct Net {
   Profiler prof;
   SideStream side;
+  std::vector<StepGraph> graphs;
+  cudaStream_t cap_stream = nullptr;
   BucketFn bucket_fn = nullptr;   // called when grads[offset, offset+count) are final
   void* bucket_user = nullptr;
   // configuration
@@ -389,8 +407,16 @@ Net* net_create(const char* arch, int emb_dim, int in_channels, int H, int W, in
   return n;
 }
 
+static void drop_graphs(Net* n) {
+  for (auto& e : n->graphs)
+    if (e.exec) cudaGraphExecDestroy(e.exec);
+  n->graphs.clear();
+}
+
 void net_destroy(Net* n) {
   if (!n) return;
+  drop_graphs(n);
+  if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
   for (auto& kv : n->plans) delete kv.second;
   delete n;
 }
@@ -471,6 +497,7 @@ int net_bind(Net* n, float* params, float* grads, float* buffers, long long* nbt
   carve(n, n->ws);
   for (auto& kv : n->plans) delete kv.second;
   n->plans.clear();
+  drop_graphs(n);   // they hold the old pointers
   n->params_dirty = true;
   n->tr_uploaded = false;
   return 0;
@@ -819,10 +846,8 @@ int net_eval_loss(Net* n, const float* x_nchw, const void* x_stem, const float* 
     if (_rc) return -1;                \
   } while (0)
 
-int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float* target, int B,
-                   double* loss_sum, cudaStream_t s) {
-  VPD_REQUIRE(n->grads != nullptr, "net: gradient arena not bound");
-  VPD_REQUIRE(target != nullptr && loss_sum != nullptr, "net_train_step: null target/loss");
+static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, const float* target,
+                               int B, double* loss_sum, cudaStream_t s) {
   PROF(kPack, 0, prepare_input(n, x_nchw, x_stem, B, s));
   Plan* P = get_plan(n, B);
   if (!P) return -1;
@@ -1017,6 +1042,79 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
   }
   if (n->bucket_fn != nullptr) n->bucket_fn(n->bucket_user, 0, bucket_hi);
   n->params_dirty = true;  // the caller is about to update the parameters
+  return 0;
+}
+
+// The step is ~190 launches with static arguments per (batch size, input / target / loss
+// pointers): after two eager runs it is captured into a CUDA graph (the side stream and the
+// programmatic-dependent-launch edges are captured with it) and replayed, which takes the
+// per-launch driver work off the critical path. Eager when profiling, when an all-reduce
+// bucket callback is installed (host code inside the step) or with VPD_GRAPH=0.
+int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float* target, int B,
+                   double* loss_sum, cudaStream_t s) {
+  VPD_REQUIRE(n->grads != nullptr, "net: gradient arena not bound");
+  VPD_REQUIRE(target != nullptr && loss_sum != nullptr, "net_train_step: null target/loss");
+  static const bool graphs_on = getenv("VPD_GRAPH") == nullptr || getenv("VPD_GRAPH")[0] != '0';
+  if (!graphs_on || n->prof.on || n->bucket_fn != nullptr)
+    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
+  StepGraphKey key{B, x_nchw, x_stem, target, loss_sum, s};
+  StepGraph* g = nullptr;
+  for (auto& e : n->graphs)
+    if (e.key == key) g = &e;
+  if (g == nullptr) {
+    if (n->graphs.size() >= 16) {   // bounded cache: drop everything (pointers changed a lot)
+      for (auto& e : n->graphs)
+        if (e.exec) cudaGraphExecDestroy(e.exec);
+      n->graphs.clear();
+    }
+    n->graphs.push_back(StepGraph{key, 0, nullptr});
+    g = &n->graphs.back();
+  }
+  if (g->exec != nullptr) {
+    VPD_CHECK_CUDA(cudaGraphLaunch(g->exec, s));
+    count_launches(g->launches);
+    n->params_dirty = true;
+    return 0;
+  }
+  if (g->seen < 2) {   // warm-up: plans, function attributes, side stream, uploads
+    ++g->seen;
+    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
+  }
+  const long long l0 = launch_count();
+  cudaGraph_t graph = nullptr;
+  // captured on an internal stream (the caller's may be the legacy default stream, which
+  // cannot capture); the instantiated graph is then launched on the caller's stream
+  if (n->cap_stream == nullptr &&
+      cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    g->seen = -1000000;
+    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
+  }
+  if (cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    g->seen = -1000000;   // capture unavailable: stay eager
+    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
+  }
+  const int rc = net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, n->cap_stream);
+  const cudaError_t ce = cudaStreamEndCapture(n->cap_stream, &graph);
+  if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    g->seen = -1000000;
+    if (rc != 0) return rc;
+    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
+  }
+  g->launches = (int)(launch_count() - l0);
+  cudaGraphExec_t exec = nullptr;
+  if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    cudaGraphDestroy(graph);
+    g->seen = -1000000;
+    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
+  }
+  cudaGraphDestroy(graph);
+  g->exec = exec;
+  VPD_CHECK_CUDA(cudaGraphLaunch(g->exec, s));   // the captured step has not run yet
   return 0;
 }
 
