@@ -164,17 +164,20 @@ struct SideStream {
 
 struct StepGraphKey {
   int B;
-  const void *x_nchw, *x_stem, *target, *loss;
+  const void *x_nchw, *x_stem, *target, *loss, *hook;
   cudaStream_t stream;
   bool operator==(const StepGraphKey& o) const {
     return B == o.B && x_nchw == o.x_nchw && x_stem == o.x_stem && target == o.target &&
-           loss == o.loss && stream == o.stream;
+           loss == o.loss && hook == o.hook && stream == o.stream;
   }
 };
 struct StepGraph {
   StepGraphKey key;
   int seen;              // eager runs so far (< 0: capture failed, stay eager)
-  cudaGraphExec_t exec;
+  // one graph per segment; segment k is followed by the all-reduce bucket callback k (data
+  // parallel: host code between the segments; single GPU: one segment, no callback)
+  std::vector<cudaGraphExec_t> execs;
+  std::vector<std::pair<long long, long long>> buckets;
   int launches = 0;      // kernels per replay (for vpd_launch_count)
 };
 
@@ -183,6 +186,9 @@ struct Net {
   SideStream side;
   std::vector<StepGraph> graphs;
   cudaStream_t cap_stream = nullptr;
+  bool capturing = false;                                   // inside net_train_step's capture
+  std::vector<cudaGraph_t> cap_graphs;                      // finished segments
+  std::vector<std::pair<long long, long long>> cap_buckets; // callback after each segment
   BucketFn bucket_fn = nullptr;   // called when grads[offset, offset+count) are final
   void* bucket_user = nullptr;
   // configuration
@@ -409,8 +415,26 @@ Net* net_create(const char* arch, int emb_dim, int in_channels, int H, int W, in
 
 static void drop_graphs(Net* n) {
   for (auto& e : n->graphs)
-    if (e.exec) cudaGraphExecDestroy(e.exec);
+    for (cudaGraphExec_t x : e.execs) cudaGraphExecDestroy(x);
   n->graphs.clear();
+}
+
+// gradients [offset, offset+count) are final on stream s: hand them to the data-parallel
+// hook. While the step is being captured the hook is host code BETWEEN graph segments: close
+// the current segment, remember the bucket, open the next one.
+static int bucket_boundary(Net* n, cudaStream_t s, long long offset, long long count, bool last) {
+  if (n->bucket_fn == nullptr) return 0;
+  if (!n->capturing) {
+    n->bucket_fn(n->bucket_user, offset, count);
+    return 0;
+  }
+  n->cap_buckets.push_back({offset, count});
+  if (last) return 0;   // the wrapper ends the final segment
+  cudaGraph_t g = nullptr;
+  VPD_CHECK_CUDA(cudaStreamEndCapture(s, &g));
+  n->cap_graphs.push_back(g);
+  VPD_CHECK_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  return 0;
 }
 
 void net_destroy(Net* n) {
@@ -1012,7 +1036,7 @@ static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, 
     if (n->bucket_fn != nullptr && i > 0 && n->blocks[i - 1].stage != bd.stage && bd.stage >= 3) {
       const long long lo = n->secA + bd.c1.w_off;
       if (use_side && n->side.order(ws, s)) return -1;   // the bucket's weight gradients are final
-      n->bucket_fn(n->bucket_user, lo, bucket_hi - lo);
+      if (bucket_boundary(n, s, lo, bucket_hi - lo, false)) return -1;
       bucket_hi = lo;
     }
   }
@@ -1040,7 +1064,7 @@ static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, 
     PROF(kConvWgrad, 0, launch_wgrad(P->wg_stem, ws));
     if (use_side && n->side.order(ws, s)) return -1;   // join: every gradient is final
   }
-  if (n->bucket_fn != nullptr) n->bucket_fn(n->bucket_user, 0, bucket_hi);
+  if (bucket_boundary(n, s, 0, bucket_hi, true)) return -1;
   n->params_dirty = true;  // the caller is about to update the parameters
   return 0;
 }
@@ -1055,66 +1079,88 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
   VPD_REQUIRE(n->grads != nullptr, "net: gradient arena not bound");
   VPD_REQUIRE(target != nullptr && loss_sum != nullptr, "net_train_step: null target/loss");
   static const bool graphs_on = getenv("VPD_GRAPH") == nullptr || getenv("VPD_GRAPH")[0] != '0';
-  if (!graphs_on || n->prof.on || n->bucket_fn != nullptr)
+  if (!graphs_on || n->prof.on)
     return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
-  StepGraphKey key{B, x_nchw, x_stem, target, loss_sum, s};
+  StepGraphKey key{B, x_nchw, x_stem, target, loss_sum, (const void*)n->bucket_fn, s};
   StepGraph* g = nullptr;
   for (auto& e : n->graphs)
     if (e.key == key) g = &e;
   if (g == nullptr) {
-    if (n->graphs.size() >= 16) {   // bounded cache: drop everything (pointers changed a lot)
-      for (auto& e : n->graphs)
-        if (e.exec) cudaGraphExecDestroy(e.exec);
-      n->graphs.clear();
-    }
-    n->graphs.push_back(StepGraph{key, 0, nullptr});
+    if (n->graphs.size() >= 16) drop_graphs(n);   // bounded cache (pointers changed a lot)
+    n->graphs.emplace_back();
     g = &n->graphs.back();
+    g->key = key;
+    g->seen = 0;
   }
-  if (g->exec != nullptr) {
-    VPD_CHECK_CUDA(cudaGraphLaunch(g->exec, s));
+  if (!g->execs.empty()) {
+    for (size_t k = 0; k < g->execs.size(); ++k) {
+      VPD_CHECK_CUDA(cudaGraphLaunch(g->execs[k], s));
+      if (k < g->buckets.size() && n->bucket_fn != nullptr)
+        n->bucket_fn(n->bucket_user, g->buckets[k].first, g->buckets[k].second);
+    }
     count_launches(g->launches);
     n->params_dirty = true;
     return 0;
   }
   if (g->seen < 2) {   // warm-up: plans, function attributes, side stream, uploads
-    ++g->seen;
+    if (g->seen >= 0) ++g->seen;
     return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
   }
-  const long long l0 = launch_count();
-  cudaGraph_t graph = nullptr;
+  auto stay_eager = [&]() {
+    cudaGetLastError();
+    for (cudaGraph_t x : n->cap_graphs) cudaGraphDestroy(x);
+    n->cap_graphs.clear();
+    n->cap_buckets.clear();
+    n->capturing = false;
+    g->seen = -1;
+    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
+  };
   // captured on an internal stream (the caller's may be the legacy default stream, which
-  // cannot capture); the instantiated graph is then launched on the caller's stream
+  // cannot capture); the instantiated graphs are then launched on the caller's stream
   if (n->cap_stream == nullptr &&
-      cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
-    cudaGetLastError();
-    g->seen = -1000000;
-    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
-  }
-  if (cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-    cudaGetLastError();
-    g->seen = -1000000;   // capture unavailable: stay eager
-    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
-  }
+      cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+    return stay_eager();
+  if (cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    return stay_eager();
+  const long long l0 = launch_count();
+  n->capturing = true;
+  n->cap_graphs.clear();
+  n->cap_buckets.clear();
   const int rc = net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, n->cap_stream);
-  const cudaError_t ce = cudaStreamEndCapture(n->cap_stream, &graph);
-  if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
-    cudaGetLastError();
-    if (graph) cudaGraphDestroy(graph);
-    g->seen = -1000000;
-    if (rc != 0) return rc;
-    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
+  n->capturing = false;
+  cudaGraph_t last = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(n->cap_stream, &last);
+  if (last) n->cap_graphs.push_back(last);
+  if (rc != 0 || ce != cudaSuccess || last == nullptr) {
+    if (rc != 0) {
+      for (cudaGraph_t x : n->cap_graphs) cudaGraphDestroy(x);
+      n->cap_graphs.clear();
+      g->seen = -1;
+      return rc;
+    }
+    return stay_eager();
   }
   g->launches = (int)(launch_count() - l0);
-  cudaGraphExec_t exec = nullptr;
-  if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
-    cudaGetLastError();
-    cudaGraphDestroy(graph);
-    g->seen = -1000000;
-    return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
+  for (cudaGraph_t x : n->cap_graphs) {
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, x, 0) != cudaSuccess) {
+      for (cudaGraphExec_t e : g->execs) cudaGraphExecDestroy(e);
+      g->execs.clear();
+      return stay_eager();
+    }
+    g->execs.push_back(exec);
   }
-  cudaGraphDestroy(graph);
-  g->exec = exec;
-  VPD_CHECK_CUDA(cudaGraphLaunch(g->exec, s));   // the captured step has not run yet
+  for (cudaGraph_t x : n->cap_graphs) cudaGraphDestroy(x);
+  n->cap_graphs.clear();
+  g->buckets = n->cap_buckets;
+  n->cap_buckets.clear();
+  // the captured step has not run yet: replay it now
+  for (size_t k = 0; k < g->execs.size(); ++k) {
+    VPD_CHECK_CUDA(cudaGraphLaunch(g->execs[k], s));
+    if (k < g->buckets.size() && n->bucket_fn != nullptr)
+      n->bucket_fn(n->bucket_user, g->buckets[k].first, g->buckets[k].second);
+  }
+  n->params_dirty = true;
   return 0;
 }
 
