@@ -836,8 +836,8 @@ static int forward_eval_body(Net* n, Plan* P, int B, cudaStream_t s) {
   return 0;
 }
 
-int net_forward(Net* n, const float* x_nchw, const void* x_stem, int B, float* emb_out,
-                cudaStream_t s) {
+static int net_forward_body(Net* n, const float* x_nchw, const void* x_stem, int B, float* emb_out,
+                            cudaStream_t s) {
   if (prepare_input(n, x_nchw, x_stem, B, s)) return -1;
   Plan* P = get_plan(n, B);
   if (!P) return -1;
@@ -847,6 +847,67 @@ int net_forward(Net* n, const float* x_nchw, const void* x_stem, int B, float* e
   h.motion = 0;  // the decoder is not part of the embedding (apply_vpd_model.py:141-162)
   h.T = h.D;
   return launch_head(h, nullptr, s);
+}
+
+// Evaluation forward (apply path): same graph replay as the training step, keyed by the
+// batch size and the input / output pointers. The parameters may have changed since the
+// capture (their mirrors / folded BN are refreshed by kernels inside the graph when
+// params_dirty was set at capture time only), so a dirty net always runs eagerly once.
+int net_forward(Net* n, const float* x_nchw, const void* x_stem, int B, float* emb_out,
+                cudaStream_t s) {
+  static const bool graphs_on = getenv("VPD_GRAPH") == nullptr || getenv("VPD_GRAPH")[0] != '0';
+  if (!graphs_on || n->prof.on || n->params_dirty)
+    return net_forward_body(n, x_nchw, x_stem, B, emb_out, s);
+  StepGraphKey key{-B, x_nchw, x_stem, emb_out, nullptr, nullptr, s};   // B < 0: eval graphs
+  StepGraph* g = nullptr;
+  for (auto& e : n->graphs)
+    if (e.key == key) g = &e;
+  if (g == nullptr) {
+    if (n->graphs.size() >= 16) drop_graphs(n);
+    n->graphs.emplace_back();
+    g = &n->graphs.back();
+    g->key = key;
+    g->seen = 0;
+  }
+  if (!g->execs.empty()) {
+    VPD_CHECK_CUDA(cudaGraphLaunch(g->execs[0], s));
+    count_launches(g->launches);
+    return 0;
+  }
+  if (g->seen < 2) {
+    if (g->seen >= 0) ++g->seen;
+    return net_forward_body(n, x_nchw, x_stem, B, emb_out, s);
+  }
+  auto stay_eager = [&]() {
+    cudaGetLastError();
+    g->seen = -1;
+    return net_forward_body(n, x_nchw, x_stem, B, emb_out, s);
+  };
+  if (n->cap_stream == nullptr &&
+      cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking) != cudaSuccess)
+    return stay_eager();
+  if (cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+    return stay_eager();
+  const long long l0 = launch_count();
+  const int rc = net_forward_body(n, x_nchw, x_stem, B, emb_out, n->cap_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(n->cap_stream, &graph);
+  if (rc != 0 || ce != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != 0) {
+      g->seen = -1;
+      return rc;
+    }
+    return stay_eager();
+  }
+  g->launches = (int)(launch_count() - l0);
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ie != cudaSuccess) return stay_eager();
+  g->execs.push_back(exec);
+  VPD_CHECK_CUDA(cudaGraphLaunch(exec, s));
+  return 0;
 }
 
 int net_eval_loss(Net* n, const float* x_nchw, const void* x_stem, const float* target, int B,
