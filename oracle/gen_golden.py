@@ -202,15 +202,63 @@ def gen_student(ref):
     print('student.npz / student.json written')
 
 
+def write_teacher_pickles(root):
+    """Synthetic teacher output: 3 videos, [2, 8] embeddings, gaps in the frame numbers and
+    low-score frames so that every branch of load_default is exercised."""
+    import pickle
+    rng = np.random.RandomState(21)
+    for v, frames in (('vidA', [0, 1, 2, 3, 5, 6, 7, 9]), ('vidB', [10, 11, 12, 13, 14]),
+                      ('skip_me', [0, 1, 2])):
+        embs = []
+        for j, f in enumerate(frames):
+            meta = {'dp_score': 0.9} if j % 3 else {'kp_score': 0.3 if f in (2, 12) else 0.8}
+            embs.append((f, rng.randn(2, 8).astype(np.float32), meta))
+        with open(os.path.join(root, v + '.emb.pkl'), 'wb') as fp:
+            pickle.dump(embs, fp)
+    with open(os.path.join(root, 'notes.txt'), 'w') as fp:
+        fp.write('not a pickle')
+
+
+def gen_targets(ref):
+    """A13: GenericDataset.load_default on synthetic teacher pickles."""
+    tmp = tempfile.mkdtemp()
+    arrays, meta = {}, {}
+    real_listdir = os.listdir
+    os.listdir = lambda d: sorted(real_listdir(d))   # directory order is file-system dependent
+    try:
+        write_teacher_pickles(tmp)
+        for name, kw in (('motion', dict(embed_time=True)),
+                         ('plain_norm', dict(embed_time=False, normalize_target=True)),
+                         ('motion_norm_excl', dict(embed_time=True, normalize_target=True,
+                                                   min_pose_score=0.2,
+                                                   exclude_prefixes=('skip',)))):
+            np.random.seed(5)
+            tr, va, D = ref.GenericDataset.load_default(
+                tmp, tmp, 128, kw.pop('embed_time'), 100, ([0.5] * 3, [0.2] * 3), **kw)
+            for part, ds in (('train', tr), ('val', va)):
+                meta['{}_{}_keys'.format(name, part)] = [[d[0], int(d[1])] for d in ds.data]
+                arrays['{}_{}'.format(name, part)] = np.stack([d[2] for d in ds.data])
+            meta[name + '_emb_dim'] = int(D)
+    finally:
+        os.listdir = real_listdir
+        shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(GOLD, 'targets.npz'), **arrays)
+    with open(os.path.join(GOLD, 'targets.json'), 'w') as fp:
+        json.dump(meta, fp, indent=1)
+    print('targets.npz / targets.json written')
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_shim.load()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['assembly', 'student']
+    which = sys.argv[1:] or ['assembly', 'student', 'targets']
     if 'assembly' in which:
         gen_assembly(ref)
     if 'student' in which:
         gen_student(ref)
+    if 'targets' in which:
+        gen_targets(ref)
     with open(os.path.join(GOLD, 'README.md'), 'w') as fp:
         fp.write('Golden vectors produced by `python -m oracle.gen_golden` from the unmodified\n'
                  'reference at /root/reference (torch {}, CPU fp32). Inputs are regenerated\n'

@@ -341,3 +341,47 @@ def test_fused_bn_apply_matches_separate_kernels(monkeypatch):
             assert torch.equal(s0[k], s1[k]), k
         elif 'running_' in k:
             assert torch.allclose(s0[k], s1[k], rtol=2e-2, atol=2e-3), k
+
+
+def test_train_driver_targets_to_checkpoint_roundtrip(tmp_path):
+    """A13 -> PoolLoader (K1) -> fit() (train_vpd_model.main's loop) -> load_model_dir -> embed:
+    teacher pickles become targets, two short epochs lower the loss, the run directory has
+    the reference's files and the best checkpoint loads through the apply path."""
+    import pickle
+    from vpd_b200 import ModelTrainer, targets, train
+    from vpd_b200 import apply as vapply
+    D, n = 8, 24
+    rng = np.random.RandomState(3)
+    emb_dir = tmp_path / 'embs'
+    emb_dir.mkdir()
+    with open(emb_dir / 'clip.emb.pkl', 'wb') as fp:
+        pickle.dump([(f, (0.3 * rng.randn(2, D)).astype(np.float32), {'dp_score': 0.9})
+                     for f in range(n + 1)], fp)
+    data, emb_dim = targets.load_teacher_targets(str(emb_dir), embed_time=True)
+    assert emb_dim == D and len(data) == n          # frame 0 has no predecessor
+    teach = torch.from_numpy(targets.targets_array(data)).to(dev())      # [n, 2, 2D]
+    rgb, flow = synth.crops(n, seed=61)
+    torch.manual_seed(4)
+    from vpd_b200 import RGBF_EmbeddingModel
+    enc = RGBF_EmbeddingModel('resnet34', D, True, 'cuda')
+    tr = ModelTrainer(enc, True)
+    opt, scaler = tr.get_optimizer(5e-4)
+    mk = lambda seed, m: train.PoolLoader(rgb.to(dev()), flow.to(dev()), teach,   # noqa: E731
+                                          synth.FS_MEAN_STD, 16, m, seed=seed)
+    cfg = {'num_epochs': 3, 'batch_size': 16, 'learning_rate': 5e-4, 'img_dim': 128,
+           'use_flow': True, 'motion': True, 'emb_dim': D, 'encoder_arch': 'resnet34',
+           'rgb_mean_std': [list(map(float, synth.FS_MEAN_STD[0])),
+                            list(map(float, synth.FS_MEAN_STD[1]))]}
+    out = str(tmp_path / 'run')
+    hist = train.fit(tr, mk(1, 64), mk(2, 32), out, cfg, 3, optimizer=opt, scaler=scaler,
+                     model_select_window=1, checkpoint_frequency=None, log=lambda *a: None)
+    assert len(hist) == 3 and all(np.isfinite(h['train']) and np.isfinite(h['val']) for h in hist)
+    assert hist[-1]['train'] < hist[0]['train']
+    for f in ('config.json', 'loss.json', 'best_epoch.encoder.pt', 'best_epoch.decoder.pt',
+              'epoch0003.encoder.pt'):
+        assert os.path.exists(os.path.join(out, f)), f
+    model, cfg2 = vapply.load_model_dir(out)
+    assert cfg2['emb_dim'] == D and cfg2['motion'] is True
+    batch = next(iter(mk(5, 4)))
+    e = model.embed(batch['img'].cpu().numpy())
+    assert e.shape == (4, D) and e.dtype == np.float32 and np.isfinite(e).all()

@@ -5,6 +5,8 @@ Drop-in mirrors of the reference's Python API for this path:
     vpd_b200.ModelTrainer          <- train_vpd_model.py:53-112
     vpd_b200.apply                 <- apply_vpd_model.py:92-179 (corpus extraction)
     vpd_b200.assemble              <- vpd_dataset/{common,single_frame}.py deterministic part
+    vpd_b200.targets               <- GenericDataset.load_default's teacher-target construction
+    vpd_b200.train                 <- train_vpd_model.main's epoch loop (+ GPU-assembling loader)
 All compute runs in libvpd_b200.so (hand-written CUDA behind the C ABI of
 include/vpd_b200.h); importing the model classes without that library raises.
 """

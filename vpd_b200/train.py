@@ -1,0 +1,98 @@
+"""Training driver for the student path: the epoch loop of `train_vpd_model.main`
+(reference train_vpd_model.py:214-283) around `ModelTrainer`, plus a loader that assembles
+batches on the GPU from device-resident uint8 crop pools (K1) instead of PNG-decoding
+DataLoader workers.
+
+    fit(trainer, train_loader, val_loader, save_dir, config, num_epochs, ...)
+
+writes exactly what the reference writes: `config.json` (keys train_vpd_model.py:222-228),
+`loss.json` (one record per epoch, :251-262), `best_epoch.{encoder,decoder}.pt` whenever the
+`model_select_window`-epoch moving average of the validation loss improves (:257-269),
+`epochNNNN.*` every `checkpoint_frequency` epochs and for the last epoch (:270-280).
+`trainer` is anything with the ModelTrainer interface (epoch / save_model), so the loop is
+testable without a GPU.
+"""
+import json
+import os
+
+import numpy as np
+
+CONFIG_KEYS = ('num_epochs', 'batch_size', 'learning_rate', 'img_dim', 'use_flow', 'motion',
+               'emb_dim', 'encoder_arch', 'rgb_mean_std')
+
+
+def get_moving_avg_loss(losses, n, key):      # train_vpd_model.py:114-115
+    return np.mean([l[key] for l in losses[-n:]])
+
+
+def fit(trainer, train_loader, val_loader, save_dir, config, num_epochs, optimizer, scaler=None,
+        model_select_window=5, checkpoint_frequency=None, dataset='synthetic', log=print):
+    """Runs `num_epochs` epochs; returns the loss history (the content of loss.json)."""
+    missing = [k for k in CONFIG_KEYS if k not in config]
+    assert not missing, 'config lacks {}'.format(missing)
+    os.makedirs(save_dir)                      # like the reference: refuses to overwrite a run
+    with open(os.path.join(save_dir, 'config.json'), 'w') as fp:
+        json.dump({k: config[k] for k in CONFIG_KEYS}, fp, indent=2)
+    loss_file = os.path.join(save_dir, 'loss.json')
+    losses = []
+    best_val_loss = float('inf')
+    epoch = 0
+    for epoch in range(1, num_epochs + 1):
+        train_loss = trainer.epoch(train_loader, optimizer=optimizer, scaler=scaler)
+        val_loss = float('nan')
+        if val_loader is not None:
+            val_loss = trainer.epoch(val_loader)
+        losses.append({'epoch': epoch, 'train': train_loss, 'val': val_loss,
+                       'dataset_train': [(dataset, train_loss)],
+                       'dataset_val': [(dataset, val_loss)]})
+        moving_avg_val_loss = get_moving_avg_loss(losses, model_select_window, 'val')
+        log('Epoch {} - train loss: {:0.4f} [avg: {:0.4f}] val loss: {:0.4f} [avg: {:0.4f}]'.format(
+            epoch, train_loss, get_moving_avg_loss(losses, model_select_window, 'train'),
+            val_loss, moving_avg_val_loss))
+        with open(loss_file, 'w') as fp:
+            json.dump(losses, fp, indent=2)
+        if moving_avg_val_loss < best_val_loss:
+            log('New best epoch!')
+            trainer.save_model(save_dir, 'best_epoch')
+        if checkpoint_frequency is not None and epoch % checkpoint_frequency == 0:
+            log('Saving checkpoint: {}'.format(epoch))
+            trainer.save_model(save_dir, 'epoch{:04d}'.format(epoch))
+        best_val_loss = min(moving_avg_val_loss, best_val_loss)
+    if epoch > 0:
+        log('Saving last epoch: {}'.format(epoch))
+        trainer.save_model(save_dir, 'epoch{:04d}'.format(epoch))
+    return losses
+
+
+class PoolLoader:
+    """Epoch of `target_len` frames drawn WITH replacement (the reference's `_TrainDataset`:
+    `__len__` = target_len, `_get` = random.choice, vpd_dataset/common.py:104-108) from
+    device-resident uint8 pools; every batch is assembled by the K1 kernel (normalisation,
+    random horizontal flip with the flow-x sign change, teacher row = emb[int(flip)]).
+    Yields the reference's batch dict {'img': f32 [B,5,H,W], 'emb': f32 [B,Dt]} on the GPU.
+    The stochastic augmentations (ColorJitter, RandomResizedCrop, mask noise) are not applied
+    - they are unseeded in the reference and stay host-side."""
+
+    def __init__(self, rgb_u8, flow_u8, teacher, rgb_mean_std, batch_size, target_len, seed=0):
+        import torch
+        self.rgb, self.flow, self.teacher = rgb_u8, flow_u8, teacher
+        self.rgb_mean_std = rgb_mean_std
+        self.batch_size, self.target_len = batch_size, target_len
+        self.gen = torch.Generator().manual_seed(seed)
+
+    def __len__(self):
+        return (self.target_len + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        import torch
+        from .assemble import assemble_batch
+        dev = self.rgb.device
+        n = self.rgb.shape[0]
+        left = self.target_len
+        while left > 0:
+            b = min(self.batch_size, left)
+            left -= b
+            idx = torch.randint(0, n, (b,), generator=self.gen).int().to(dev)
+            flip = torch.randint(0, 2, (b,), generator=self.gen).to(torch.uint8).to(dev)
+            yield assemble_batch(self.rgb, self.flow, self.rgb_mean_std, flip=flip,
+                                 teacher=self.teacher, index=idx)
