@@ -71,3 +71,34 @@ def test_two_rank_gloo_sharding(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stderr[-2000:]
     assert 'OK' in res.stdout
+
+
+def test_downstream_reference_loader_reads_our_pickles(tmp_path):
+    """the reference's downstream loader (action_dataset/load.py:16-64, used by
+    recognize.py) must consume the `.emb.pkl` files this package writes. Runs only where the
+    reference checkout is present (the build container)."""
+    import sys
+    import pytest
+    from oracle import ref_shim
+    if not ref_shim.available():
+        pytest.skip('reference checkout not present')
+    sys.dont_write_bytecode = True
+    if ref_shim.REFERENCE_DIR not in sys.path:
+        sys.path.insert(0, ref_shim.REFERENCE_DIR)
+    from action_dataset.load import load_embs
+    rng = np.random.RandomState(0)
+    embs = rng.randn(4, 2, 32).astype(np.float32)
+    frames = [3, 0, 1, 6]                                 # gaps: the loader interpolates
+    vapply.store_pickle(os.path.join(str(tmp_path), 'clipA.emb.pkl'),
+                        vapply.format_video_embs(frames, embs, flip=True))
+    vapply.store_pickle(os.path.join(str(tmp_path), 'clipB.emb.pkl'),
+                        vapply.format_video_embs([0, 1], embs[:2], flip=True))
+    out = load_embs(str(tmp_path), norm=False)
+    assert sorted(out) == ['clipA', 'clipB']
+    dense, mask = out['clipA']
+    assert dense.shape == (7, 2, 32) and mask.tolist() == [True, True, False, True, False, False,
+                                                           True]
+    assert np.allclose(dense[3], embs[0]) and np.allclose(dense[6], embs[3])
+    assert np.allclose(dense[2], 0.5 * dense[1] + 0.5 * dense[3])   # its gap interpolation
+    normed = load_embs(str(tmp_path), norm=True)['clipB'][0]
+    assert np.allclose(np.linalg.norm(normed, axis=2), 1.0)

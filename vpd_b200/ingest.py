@@ -1,0 +1,92 @@
+"""On-disk ingest: the reference's crop directory
+`<crop_dir>/<video>/<frame>.png` (+ `<frame>.<flow_img>.png`; README.md:152-183, writer
+extract_square_crops.py:122-135, flow encoding raft/flow.py:80-93) packed once into flat
+uint8 shards that are memory-mapped and copied to the GPU as the pools K1 assembles from -
+PNG decoding (the reference's DataLoader workers) leaves the training loop entirely.
+
+    pack_crop_dir(crop_dir, out_prefix, flow_img='flow')   # -> <prefix>.rgb.npy, .flow.npy, .json
+    shard = load_shard(out_prefix)                         # memory-mapped arrays + index
+    pools = shard.to_device('cuda')                        # (rgb_u8, flow_u8) device tensors
+    idx = shard.rows_of(data)                              # (video, frame) keys -> pool rows
+
+The decoded bytes are exactly what `_BaseDataset._load_image/_load_flow`
+(vpd_dataset/common.py:52-69) see before their float conversion: BGR->RGB for the crop, the
+flow PNG's stored channels as is (K1 uses the first two).
+"""
+import json
+import os
+
+import numpy as np
+
+from .apply import read_crop_dir
+
+
+class Shard:
+    def __init__(self, rgb, flow, index):
+        self.rgb, self.flow, self.index = rgb, flow, index
+        self._row = {}
+        for v in index['videos']:
+            for j, f in enumerate(v['frames']):
+                self._row[(v['name'], int(f))] = v['first_row'] + j
+
+    def __len__(self):
+        return int(self.rgb.shape[0])
+
+    def rows_of(self, data):
+        """Pool rows of `(video, frame, ...)` tuples (e.g. vpd_b200.targets data lists);
+        raises KeyError for a frame that is not in the shard."""
+        return np.array([self._row[(d[0], int(d[1]))] for d in data], dtype=np.int64)
+
+    def to_device(self, device='cuda'):
+        import torch
+        rgb = torch.from_numpy(np.array(self.rgb)).to(device)
+        flow = None if self.flow is None else \
+            torch.from_numpy(np.array(self.flow)).to(device)
+        return rgb, flow
+
+    def videos(self):
+        """-> the `videos` list vpd_b200.apply.extract_corpus takes."""
+        import torch
+        out = []
+        for v in self.index['videos']:
+            lo, hi = v['first_row'], v['first_row'] + len(v['frames'])
+            out.append((v['name'], list(v['frames']),
+                        torch.from_numpy(np.array(self.rgb[lo:hi])),
+                        None if self.flow is None else
+                        torch.from_numpy(np.array(self.flow[lo:hi]))))
+        return out
+
+
+def pack_crop_dir(crop_dir, out_prefix, flow_img=None, img_dim=128):
+    """Decode every `<video>/<n>.png` (and flow PNG) once and write the shard files."""
+    videos = read_crop_dir(crop_dir, flow_img, img_dim)
+    n = sum(len(v[1]) for v in videos)
+    rgb = np.lib.format.open_memmap(out_prefix + '.rgb.npy', mode='w+', dtype=np.uint8,
+                                    shape=(n, img_dim, img_dim, 3))
+    flow = None
+    if flow_img:
+        flow = np.lib.format.open_memmap(out_prefix + '.flow.npy', mode='w+', dtype=np.uint8,
+                                         shape=(n, img_dim, img_dim, 3))
+    index = {'img_dim': img_dim, 'flow_img': flow_img, 'videos': []}
+    row = 0
+    for name, frames, vrgb, vflow in videos:
+        k = len(frames)
+        rgb[row:row + k] = vrgb.numpy()
+        if flow is not None:
+            flow[row:row + k] = vflow.numpy()
+        index['videos'].append({'name': name, 'frames': [int(f) for f in frames], 'first_row': row})
+        row += k
+    rgb.flush()
+    if flow is not None:
+        flow.flush()
+    with open(out_prefix + '.json', 'w') as fp:
+        json.dump(index, fp)
+    return index
+
+
+def load_shard(prefix):
+    with open(prefix + '.json') as fp:
+        index = json.load(fp)
+    rgb = np.load(prefix + '.rgb.npy', mmap_mode='r')
+    flow = np.load(prefix + '.flow.npy', mmap_mode='r') if index['flow_img'] else None
+    return Shard(rgb, flow, index)
