@@ -645,7 +645,9 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       }
     }
   }
-  if (st == 0) bulk_wait0();  // all tile stores performed before the CTA exits
+  // the last stores only need to have READ their slabs before the CTA (and its shared memory)
+  // goes away; grid completion makes the writes visible to the dependent kernel
+  if (st == 0) bulk_wait_read0();
 }
 
 // CS = 2: PAIR mode (tcgen05 cta_group::2). The two CTAs of a cluster own two adjacent
