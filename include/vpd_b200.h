@@ -61,6 +61,26 @@ VPD_API int vpd_assemble_stem(const uint8_t* rgb, const uint8_t* flow, int flow_
                       int teacher_rows, int tdim, const float* mean, const float* std,
                       void* out_stem_bf16, float* out_tgt, int B, int H, int W, int k,
                       void* stream);
+/* Training batch with the reference's masked-noise augmentation (single_frame.py:179-191:
+ * with probability 0.5 per frame, Gaussian noise of sd sqrt(0.05) is added to the normalised
+ * RGB planes at the pixels where `<n>.mask.png`'s first channel is NOT 0, before the flip).
+ *   mask      uint8 [pool][H][W]   first channel of the mask PNG
+ *   noise_on  uint8 [B]            the per-frame coin (host-drawn like `flip`), NULL = all
+ *   noise     fp32 [B][3][H][W]    explicit noise in source orientation (bit-exact parity
+ *                                  with a host generator), or NULL: counter-based Philox
+ *                                  normals from `seed` scaled by `noise_sd` */
+VPD_API int vpd_assemble_nchw_noise(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
+                            const int32_t* index, const uint8_t* flip, const float* teacher,
+                            int teacher_rows, int tdim, const float* mean, const float* std,
+                            float* out_img, float* out_tgt, int B, int H, int W,
+                            const uint8_t* mask, const uint8_t* noise_on, const float* noise,
+                            float noise_sd, uint64_t seed, void* stream);
+VPD_API int vpd_assemble_stem_noise(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
+                            const int32_t* index, const uint8_t* flip, const float* teacher,
+                            int teacher_rows, int tdim, const float* mean, const float* std,
+                            void* out_stem_bf16, float* out_tgt, int B, int H, int W,
+                            const uint8_t* mask, const uint8_t* noise_on, const float* noise,
+                            float noise_sd, uint64_t seed, void* stream);
 /* fp32 NCHW batch (the reference's batch['img']) -> network input layout */
 VPD_API int vpd_nchw_to_stem(const float* x, void* out_stem_bf16, int B, int C, int H, int W,
                      void* stream);

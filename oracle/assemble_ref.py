@@ -50,16 +50,25 @@ def lut(mean, std):
     return np.concatenate([rgb, fl], axis=0).astype(np.float32)               # [5,256]
 
 
-def train_item(rgb_u8, flow_u8, teacher, flip, mean, std):
-    """single_frame.py:168-206 without the stochastic augmentations.
+def train_item(rgb_u8, flow_u8, teacher, flip, mean, std, mask_u8=None, noise=None):
+    """single_frame.py:168-206 without the unseeded draws (ColorJitter, RandomResizedCrop).
     teacher: fp32 [2, E] (rows = unflipped / flipped) or [E]. Returns
-    (img fp32 [5,H,W] (or [3,H,W] if flow_u8 is None), emb fp32 [E])."""
+    (img fp32 [5,H,W] (or [3,H,W] if flow_u8 is None), emb fp32 [E]).
+    mask_u8 [H,W] (first channel of <n>.mask.png) with noise fp32 [3,H,W]: the masked noise
+    of single_frame.py:179-191 with the noise tensor given instead of drawn -
+    `mask = mask_png[:,:,0] == 0; noise[:, mask] = 0; img += noise`, before the flow is
+    stacked and before the flip."""
     emb = np.asarray(teacher, dtype=np.float32)
     if emb.ndim == 2:
         emb = emb[int(flip), :]
     else:
         flip = False
     img = load_image(rgb_u8, mean, std)
+    if mask_u8 is not None and noise is not None:
+        mask = torch.from_numpy(np.asarray(mask_u8) == 0)
+        nz = torch.as_tensor(noise, dtype=torch.float32).clone()
+        nz[:, mask] = 0
+        img += nz
     if flow_u8 is not None:
         img = torch.cat((img, load_flow(flow_u8)))
     if flip:
@@ -69,12 +78,16 @@ def train_item(rgb_u8, flow_u8, teacher, flip, mean, std):
     return img, torch.FloatTensor(emb)
 
 
-def train_batch(rgb_u8, flow_u8, teacher, flips, mean, std):
-    """Collated batch like the DataLoader does: img [B,5,H,W], emb [B,E]."""
+def train_batch(rgb_u8, flow_u8, teacher, flips, mean, std, mask_u8=None, noise=None,
+                noise_on=None):
+    """Collated batch like the DataLoader does: img [B,5,H,W], emb [B,E]. With mask_u8
+    [B,H,W] + noise [B,3,H,W] the frames with noise_on[i] (default all) get the masked noise."""
     imgs, embs = [], []
     for i in range(len(rgb_u8)):
+        on = mask_u8 is not None and noise is not None and (noise_on is None or noise_on[i])
         a, b = train_item(rgb_u8[i], None if flow_u8 is None else flow_u8[i],
-                          teacher[i], bool(flips[i]), mean, std)
+                          teacher[i], bool(flips[i]), mean, std,
+                          mask_u8[i] if on else None, noise[i] if on else None)
         imgs.append(a)
         embs.append(b)
     return torch.stack(imgs), torch.stack(embs)

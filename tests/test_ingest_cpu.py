@@ -43,5 +43,21 @@ def test_pack_without_flow_and_resize(tmp_path):
     prefix = str(tmp_path / 's')
     ingest.pack_crop_dir(crops, prefix, flow_img=None, img_dim=32)      # resized like the loader
     sh = ingest.load_shard(prefix)
-    assert sh.flow is None and sh.rgb.shape == (2, 32, 32, 3)
+    assert sh.flow is None and sh.mask is None and sh.rgb.shape == (2, 32, 32, 3)
     assert not os.path.exists(prefix + '.flow.npy')
+
+
+def test_pack_masks(tmp_path):
+    import cv2
+    crops = str(tmp_path / 'crops')
+    rgb, flow = synth.crops(3, seed=4, height=32, width=32)
+    write_crop_dir(crops, 'v', rgb, flow)
+    m = np.zeros((32, 32, 3), np.uint8)
+    m[4:9, :, :] = 255
+    cv2.imwrite(os.path.join(crops, 'v', '1.mask.png'), m)              # only frame 1 has a mask
+    prefix = str(tmp_path / 's')
+    ingest.pack_crop_dir(crops, prefix, flow_img='flow', img_dim=32, with_mask=True)
+    sh = ingest.load_shard(prefix)
+    assert sh.mask.shape == (3, 32, 32) and sh.mask.dtype == np.uint8
+    assert sh.mask[0].max() == 0 and sh.mask[2].max() == 0
+    assert np.array_equal(np.asarray(sh.mask[1]), m[:, :, 0])

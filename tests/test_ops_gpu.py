@@ -397,3 +397,58 @@ def test_conv2d_dgrad_with_fused_bn_backward_reduction(case):
     s1 = (got.double() * xhat.double()).sum((0, 2, 3))
     assert torch.allclose(sums[0], s0, rtol=1e-4, atol=1e-2)
     assert torch.allclose(sums[1], s1, rtol=1e-4, atol=1e-2)
+
+
+# --------------------------------------------------- K1 masked-noise augmentation
+def test_assemble_masked_noise_bit_exact_with_given_noise():
+    """single_frame.py:179-191 with the noise tensor supplied: img += noise where the mask
+    PNG byte is not 0, only on the frames whose coin says so, before the flip."""
+    from vpd_b200.assemble import assemble_batch
+    B, H, W = 6, 32, 32
+    g = torch.Generator().manual_seed(71)
+    rgb, flow = synth.crops(B, seed=72, height=H, width=W)
+    teach = synth.teacher(B, seed=73, emb_dim=8, motion=True)
+    flips = synth.flips(B, seed=74)
+    mask = (torch.rand((B, H, W), generator=g) < 0.4).to(torch.uint8) * 255   # 0 = background
+    noise = torch.randn((B, 3, H, W), generator=g) * (0.05 ** 0.5)
+    on = torch.tensor([1, 0, 1, 1, 0, 1], dtype=torch.uint8)
+    ref_img, ref_emb = assemble_ref.train_batch(rgb.numpy(), flow.numpy(), teach.numpy(),
+                                                flips.numpy(), *synth.FS_MEAN_STD,
+                                                mask_u8=mask.numpy(), noise=noise.numpy(),
+                                                noise_on=on.numpy())
+    out = assemble_batch(rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD, flip=flips.to(dev()),
+                         teacher=teach.to(dev()), mask=mask.to(dev()), noise_on=on.to(dev()),
+                         noise=noise.to(dev()))
+    assert torch.equal(out['img'].cpu(), ref_img)
+    assert torch.equal(out['emb'].cpu(), ref_emb)
+    # and it really changed something, only where it may
+    plain = assemble_batch(rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD, flip=flips.to(dev()))
+    d = (out['img'] - plain['img']).cpu()
+    assert d[1].abs().max() == 0 and d[4].abs().max() == 0 and d[:, 3:].abs().max() == 0
+    assert d[0, :3].abs().max() > 0
+
+
+def test_assemble_masked_noise_device_rng_statistics():
+    """Device Philox noise: zero on masked-out pixels / switched-off frames / flow planes,
+    N(0, sd^2) elsewhere, reproducible per seed, identical in both output layouts."""
+    from vpd_b200.assemble import assemble_batch, assemble_stem
+    B, H, W = 8, 64, 64
+    rgb, flow = synth.crops(B, seed=81, height=H, width=W)
+    mask = torch.zeros((B, H, W), dtype=torch.uint8)
+    mask[:, :, : W // 2] = 7                                     # left half = person pixels
+    args = dict(mask=mask.to(dev()), noise_sd=0.05 ** 0.5)
+    base = assemble_batch(rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD)['img']
+    a = assemble_batch(rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD, seed=5, **args)['img']
+    b = assemble_batch(rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD, seed=5, **args)['img']
+    c = assemble_batch(rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD, seed=6, **args)['img']
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    d = (a - base).cpu()
+    assert d[:, :3, :, W // 2:].abs().max() == 0 and d[:, 3:].abs().max() == 0
+    nz = d[:, :3, :, : W // 2].flatten().double()
+    assert abs(nz.mean().item()) < 4e-3 and abs(nz.std().item() - 0.05 ** 0.5) < 4e-3
+    assert abs((nz ** 4).mean().item() / nz.var().item() ** 2 - 3.0) < 0.15   # Gaussian kurtosis
+    # the network-layout kernel draws the same noise (then rounds to bf16)
+    stem = torch.zeros((B, H + 6, W + 8, 8), device=dev(), dtype=torch.bfloat16)
+    assemble_stem(stem, rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD, seed=5, **args)
+    got = stem[:, 3:3 + H, 3:3 + W, :5].permute(0, 3, 1, 2).float()
+    assert torch.equal(got, a.to(torch.bfloat16).float())

@@ -15,11 +15,27 @@ def _mean_std(rgb_mean_std):
     return mean, std
 
 
-def assemble_batch(rgb, flow, rgb_mean_std, flip=None, teacher=None, index=None):
+RANDOM_NOISE_SD = 0.05 ** 0.5        # vpd_dataset/single_frame.py:21
+RANDOM_MASK_PROB = 0.5               # :20
+
+
+def _noise_args(mask, noise_on, noise, noise_sd, seed):
+    if noise is None and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())    # torch's global RNG, like the loader
+    return (mask.contiguous(), noise_on, None if noise is None else noise.contiguous(),
+            float(noise_sd), int(seed or 0))
+
+
+def assemble_batch(rgb, flow, rgb_mean_std, flip=None, teacher=None, index=None, mask=None,
+                   noise_on=None, noise=None, noise_sd=RANDOM_NOISE_SD, seed=None):
     """-> {'img': fp32 [B,C,H,W], 'emb': fp32 [B,E] (if teacher given)} on the device.
 
     rgb uint8 [P,H,W,3]; flow uint8 [P,H,W,>=2] or None; flip uint8 [B] or None;
-    teacher fp32 [P,2,E] (rows unflipped/flipped) or [P,E]; index int32 [B] or None."""
+    teacher fp32 [P,2,E] (rows unflipped/flipped) or [P,E]; index int32 [B] or None.
+    mask uint8 [P,H,W] (first channel of `<n>.mask.png`) switches on the reference's noise
+    augmentation (single_frame.py:179-191) for the frames with noise_on[b] != 0: Gaussian
+    noise of sd `noise_sd` on the normalised RGB planes where the mask byte is not 0;
+    `noise` fp32 [B,3,H,W] supplies the noise explicitly (else device Philox from `seed`)."""
     mean, std = _mean_std(rgb_mean_std)
     P, H, W, _ = rgb.shape
     B = P if index is None else index.numel()
@@ -32,8 +48,14 @@ def assemble_batch(rgb, flow, rgb_mean_std, flip=None, teacher=None, index=None)
         rows = teacher.shape[1] if teacher.dim() == 3 else 1
         tdim = teacher.shape[-1]
         emb = torch.empty((B, tdim), device=rgb.device, dtype=torch.float32)
-    lib().call('vpd_assemble_nchw', rgb, flow, 0 if flow is None else flow.shape[-1], index, flip,
-               teacher, rows, tdim, mean, std, img, emb, B, H, W, 1, stream_ptr(rgb.device))
+    if mask is not None:
+        lib().call('vpd_assemble_nchw_noise', rgb, flow, 0 if flow is None else flow.shape[-1],
+                   index, flip, teacher, rows, tdim, mean, std, img, emb, B, H, W,
+                   *_noise_args(mask, noise_on, noise, noise_sd, seed), stream_ptr(rgb.device))
+    else:
+        lib().call('vpd_assemble_nchw', rgb, flow, 0 if flow is None else flow.shape[-1], index,
+                   flip, teacher, rows, tdim, mean, std, img, emb, B, H, W, 1,
+                   stream_ptr(rgb.device))
     out = {'img': img[:, 0]}
     if emb is not None:
         out['emb'] = emb
@@ -53,7 +75,8 @@ def assemble_apply(rgb, flow, rgb_mean_std, flip=True):
 
 
 def assemble_stem(out, rgb, flow, rgb_mean_std, flip=None, teacher=None, index=None, k=1,
-                  tgt=None):
+                  tgt=None, mask=None, noise_on=None, noise=None, noise_sd=RANDOM_NOISE_SD,
+                  seed=None):
     """Fused device pipeline: write the network's own bf16 input layout
     [B*k, H+6, W+8, 8] straight into `out` (tensor or raw pointer)."""
     mean, std = _mean_std(rgb_mean_std)
@@ -63,6 +86,12 @@ def assemble_stem(out, rgb, flow, rgb_mean_std, flip=None, teacher=None, index=N
     if teacher is not None:
         rows = teacher.shape[1] if teacher.dim() == 3 else 1
         tdim = teacher.shape[-1]
+    if mask is not None:
+        assert k == 1, 'the noise augmentation is a training-batch option'
+        lib().call('vpd_assemble_stem_noise', rgb, flow, 0 if flow is None else flow.shape[-1],
+                   index, flip, teacher, rows, tdim, mean, std, out, tgt, B, H, W,
+                   *_noise_args(mask, noise_on, noise, noise_sd, seed), stream_ptr(rgb.device))
+        return B
     lib().call('vpd_assemble_stem', rgb, flow, 0 if flow is None else flow.shape[-1], index, flip,
                teacher, rows, tdim, mean, std, out, tgt, B, H, W, k, stream_ptr(rgb.device))
     return B * k

@@ -13,6 +13,7 @@
 // 16-byte loads of the packed uint8 rows into shared memory, float4 / uint4
 // stores of the planes.
 #include "common.cuh"
+#include "ops.h"
 #include "tma_host.h"
 
 namespace vpd {
@@ -57,10 +58,49 @@ struct AsmParams {
   int B, H, W, fc, rows_per_cta;
   int teacher_rows, tdim;
   int k;                  // apply variants: 1 = as is (flip bit per frame), 2 = [orig, flipped]
+  // masked Gaussian noise on the normalised RGB planes (single_frame.py:179-191): applied to
+  // the frames with noise_on[b] != 0, at the pixels whose mask byte is NOT 0 (the reference
+  // zeroes the noise where `mask_png[:,:,0] == 0`), before the flip; k == 1 only
+  const uint8_t* mask;      // [pool][H][W] first channel of <n>.mask.png, or null (no noise)
+  const uint8_t* noise_on;  // [B] coin per frame (null: every frame)
+  const float* noise;       // [B][3][H][W] explicit noise (tests / host RNG), or null: Philox
+  float noise_sd;
+  unsigned long long seed;
   float* out_img;         // [B][k][C][H][W] fp32, C = 3 or 5
   float* out_tgt;         // [B][tdim]
   __nv_bfloat16* out_pad; // [B*k][H+6][W+8][8] bf16 (stem layout), or null
 };
+
+// Counter-based normal generator for the noise augmentation: Philox4x32-10 keyed by the
+// seed, counter = (element index, frame), Box-Muller on the first two words.
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned int idx,
+                                               unsigned int frame) {
+  unsigned int c0 = idx, c1 = frame, c2 = 0x1234u, c3 = 0u;
+  unsigned int k0 = static_cast<unsigned int>(seed), k1 = static_cast<unsigned int>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  const float u1 = (static_cast<float>(c0 >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1)
+  const float u2 = (static_cast<float>(c1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  return sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530718f * u2);
+}
+// noise added to RGB channel c of SOURCE pixel (h, ws) of output frame b (0 where masked out)
+__device__ __forceinline__ float pixel_noise(const AsmParams& p, int b, int src, int c, int h,
+                                             int ws) {
+  if (p.mask == nullptr || (p.noise_on != nullptr && p.noise_on[b] == 0)) return 0.f;
+  if (p.mask[((size_t)src * p.H + h) * p.W + ws] == 0) return 0.f;
+  const size_t e = ((size_t)c * p.H + h) * p.W + ws;
+  if (p.noise != nullptr) return p.noise[(size_t)b * 3 * p.H * p.W + e];
+  return p.noise_sd * philox_normal(p.seed, static_cast<unsigned int>(e), static_cast<unsigned int>(b));
+}
 
 // Reference layout: fp32 NCHW planes.
 __global__ void __launch_bounds__(kAsmThreads)
@@ -105,6 +145,7 @@ assemble_nchw_kernel(const AsmParams p) {
         const int ws = fl ? (p.W - 1 - w) : w;
         if (c < 3) {
           o[j] = lut[c * 256 + s_rgb[(r * p.W + ws) * 3 + c]];
+          if (p.mask != nullptr) o[j] += pixel_noise(p, b, src, c, h0 + r, ws);
         } else {
           const float f = lut[c * 256 + s_flow[(r * p.W + ws) * p.fc + (c - 3)]];
           o[j] = (fl && c == 3) ? -f : f;
@@ -163,7 +204,12 @@ assemble_pad8_kernel(const AsmParams p) {
         const int ws = fl ? (p.W - 1 - w) : w;
         const int r = h - h_lo;
         const uint8_t* px = s_rgb + (r * p.W + ws) * 3;
-        const float c0 = lut[px[0]], c1 = lut[256 + px[1]], c2 = lut[512 + px[2]];
+        float c0 = lut[px[0]], c1 = lut[256 + px[1]], c2 = lut[512 + px[2]];
+        if (p.mask != nullptr) {
+          c0 += pixel_noise(p, b, src, 0, h, ws);
+          c1 += pixel_noise(p, b, src, 1, h, ws);
+          c2 += pixel_noise(p, b, src, 2, h, ws);
+        }
         float c3 = 0.f, c4 = 0.f;
         if (p.flow) {
           const uint8_t* pf = s_flow + (r * p.W + ws) * p.fc;
@@ -232,6 +278,11 @@ static int fill_params(AsmParams* p, const uint8_t* rgb, const uint8_t* flow, in
   p->out_img = nullptr;
   p->out_tgt = nullptr;
   p->out_pad = nullptr;
+  p->mask = nullptr;
+  p->noise_on = nullptr;
+  p->noise = nullptr;
+  p->noise_sd = 0.f;
+  p->seed = 0;
   return 0;
 }
 
@@ -239,10 +290,22 @@ static int smem_for(const AsmParams& p, int R) {
   return 5 * 256 * 4 + ((R * p.W * 3 + 15) & ~15) + ((R * p.W * (p.flow ? p.fc : 0) + 15) & ~15) + 16;
 }
 
+static int set_noise(AsmParams* p, const AsmNoise* nz) {
+  if (nz == nullptr || nz->mask == nullptr) return 0;
+  VPD_REQUIRE(p->k == 1, "assemble: the noise augmentation is a training-batch option (k == 1)");
+  VPD_REQUIRE(nz->noise != nullptr || nz->noise_sd >= 0.f, "assemble: negative noise_sd");
+  p->mask = nz->mask;
+  p->noise_on = nz->noise_on;
+  p->noise = nz->noise;
+  p->noise_sd = nz->noise_sd;
+  p->seed = nz->seed;
+  return 0;
+}
+
 int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, const int* index,
                   const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
                   const float* mean, const float* stdv, float* out_img, float* out_tgt, int B,
-                  int H, int W, int k, cudaStream_t stream) {
+                  int H, int W, int k, cudaStream_t stream, const AsmNoise* nz) {
   AsmParams p;
   VPD_REQUIRE(B >= 0, "assemble: negative batch");
   VPD_REQUIRE(W % 4 == 0, "assemble: W must be a multiple of 4 (got %d)", W);
@@ -252,6 +315,7 @@ int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
     return -1;
   p.out_img = out_img;
   p.out_tgt = out_tgt;
+  if (set_noise(&p, nz)) return -1;
   p.rows_per_cta = H < 32 ? H : 32;
   const int smem = smem_for(p, p.rows_per_cta);
   VPD_REQUIRE(smem <= 200 * 1024, "assemble: image too wide (W=%d)", W);
@@ -267,7 +331,7 @@ int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
 int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, const int* index,
                   const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
                   const float* mean, const float* stdv, __nv_bfloat16* out_pad, float* out_tgt,
-                  int B, int H, int W, int k, cudaStream_t stream) {
+                  int B, int H, int W, int k, cudaStream_t stream, const AsmNoise* nz) {
   AsmParams p;
   VPD_REQUIRE(B >= 0, "assemble: negative batch");
   VPD_REQUIRE(W % 4 == 0, "assemble: W must be a multiple of 4 (got %d)", W);
@@ -277,6 +341,7 @@ int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
     return -1;
   p.out_pad = out_pad;
   p.out_tgt = out_tgt;
+  if (set_noise(&p, nz)) return -1;
   p.rows_per_cta = 32;
   const int smem = smem_for(p, p.rows_per_cta);
   VPD_REQUIRE(smem <= 200 * 1024, "assemble: image too wide (W=%d)", W);

@@ -6,14 +6,23 @@
 
 namespace vpd {
 
+// optional masked-noise augmentation of the assembled training batch (see assemble.cu)
+struct AsmNoise {
+  const uint8_t* mask = nullptr;      // [pool][H][W] first channel of <n>.mask.png
+  const uint8_t* noise_on = nullptr;  // [B] per-frame coin, or null (all frames)
+  const float* noise = nullptr;       // [B][3][H][W] explicit noise, or null (device Philox)
+  float noise_sd = 0.f;
+  unsigned long long seed = 0;
+};
+
 int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, const int* index,
                   const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
                   const float* mean, const float* stdv, float* out_img, float* out_tgt, int B,
-                  int H, int W, int k, cudaStream_t stream);
+                  int H, int W, int k, cudaStream_t stream, const AsmNoise* nz = nullptr);
 int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, const int* index,
                   const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
                   const float* mean, const float* stdv, __nv_bfloat16* out_pad, float* out_tgt,
-                  int B, int H, int W, int k, cudaStream_t stream);
+                  int B, int H, int W, int k, cudaStream_t stream, const AsmNoise* nz = nullptr);
 int nchw_to_pad8(const float* x, __nv_bfloat16* out, int B, int C, int H, int W,
                  cudaStream_t stream);
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1,

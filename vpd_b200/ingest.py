@@ -22,8 +22,8 @@ from .apply import read_crop_dir
 
 
 class Shard:
-    def __init__(self, rgb, flow, index):
-        self.rgb, self.flow, self.index = rgb, flow, index
+    def __init__(self, rgb, flow, index, mask=None):
+        self.rgb, self.flow, self.index, self.mask = rgb, flow, index, mask
         self._row = {}
         for v in index['videos']:
             for j, f in enumerate(v['frames']):
@@ -57,8 +57,28 @@ class Shard:
         return out
 
 
-def pack_crop_dir(crop_dir, out_prefix, flow_img=None, img_dim=128):
-    """Decode every `<video>/<n>.png` (and flow PNG) once and write the shard files."""
+def _read_masks(crop_dir, videos, img_dim):
+    """First channel of `<n>.mask.png` per frame ([n, H, W] uint8); frames without a mask file
+    get zeros, which the noise augmentation treats as "nothing to perturb" - the reference
+    skips the augmentation for them (single_frame.py:182)."""
+    import cv2
+    n = sum(len(v[1]) for v in videos)
+    out = np.zeros((n, img_dim, img_dim), np.uint8)
+    row = 0
+    for name, frames, _, _ in videos:
+        for f in frames:
+            path = os.path.join(crop_dir, name, '{}.mask.png'.format(f))
+            if os.path.exists(path):
+                m = cv2.imread(path)
+                if m.shape[:2] != (img_dim, img_dim):
+                    m = cv2.resize(m, (img_dim, img_dim))
+                out[row] = m[:, :, 0]
+            row += 1
+    return out
+
+
+def pack_crop_dir(crop_dir, out_prefix, flow_img=None, img_dim=128, with_mask=False):
+    """Decode every `<video>/<n>.png` (and flow / mask PNG) once and write the shard files."""
     videos = read_crop_dir(crop_dir, flow_img, img_dim)
     n = sum(len(v[1]) for v in videos)
     rgb = np.lib.format.open_memmap(out_prefix + '.rgb.npy', mode='w+', dtype=np.uint8,
@@ -67,7 +87,9 @@ def pack_crop_dir(crop_dir, out_prefix, flow_img=None, img_dim=128):
     if flow_img:
         flow = np.lib.format.open_memmap(out_prefix + '.flow.npy', mode='w+', dtype=np.uint8,
                                          shape=(n, img_dim, img_dim, 3))
-    index = {'img_dim': img_dim, 'flow_img': flow_img, 'videos': []}
+    index = {'img_dim': img_dim, 'flow_img': flow_img, 'with_mask': bool(with_mask), 'videos': []}
+    if with_mask:
+        np.save(out_prefix + '.mask.npy', _read_masks(crop_dir, videos, img_dim))
     row = 0
     for name, frames, vrgb, vflow in videos:
         k = len(frames)
@@ -89,4 +111,5 @@ def load_shard(prefix):
         index = json.load(fp)
     rgb = np.load(prefix + '.rgb.npy', mmap_mode='r')
     flow = np.load(prefix + '.flow.npy', mmap_mode='r') if index['flow_img'] else None
-    return Shard(rgb, flow, index)
+    mask = np.load(prefix + '.mask.npy', mmap_mode='r') if index.get('with_mask') else None
+    return Shard(rgb, flow, index, mask)

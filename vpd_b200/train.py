@@ -70,12 +70,16 @@ class PoolLoader:
     device-resident uint8 pools; every batch is assembled by the K1 kernel (normalisation,
     random horizontal flip with the flow-x sign change, teacher row = emb[int(flip)]).
     Yields the reference's batch dict {'img': f32 [B,5,H,W], 'emb': f32 [B,Dt]} on the GPU.
-    The stochastic augmentations (ColorJitter, RandomResizedCrop, mask noise) are not applied
-    - they are unseeded in the reference and stay host-side."""
+    With `mask_u8` [P,H,W] (first channel of `<n>.mask.png`, zeros where a frame has none) the
+    masked-noise augmentation of single_frame.py:179-191 is applied on the device with its
+    per-frame coin (p = 0.5). ColorJitter and RandomResizedCrop are not applied - they are
+    unseeded torchvision draws in the reference and stay host-side."""
 
-    def __init__(self, rgb_u8, flow_u8, teacher, rgb_mean_std, batch_size, target_len, seed=0):
+    def __init__(self, rgb_u8, flow_u8, teacher, rgb_mean_std, batch_size, target_len, seed=0,
+                 mask_u8=None):
         import torch
         self.rgb, self.flow, self.teacher = rgb_u8, flow_u8, teacher
+        self.mask = mask_u8
         self.rgb_mean_std = rgb_mean_std
         self.batch_size, self.target_len = batch_size, target_len
         self.gen = torch.Generator().manual_seed(seed)
@@ -94,5 +98,11 @@ class PoolLoader:
             left -= b
             idx = torch.randint(0, n, (b,), generator=self.gen).int().to(dev)
             flip = torch.randint(0, 2, (b,), generator=self.gen).to(torch.uint8).to(dev)
+            kw = {}
+            if self.mask is not None:
+                from .assemble import RANDOM_MASK_PROB
+                coin = (torch.rand((b,), generator=self.gen) <= RANDOM_MASK_PROB)
+                kw = dict(mask=self.mask, noise_on=coin.to(torch.uint8).to(dev),
+                          seed=int(torch.randint(0, 2 ** 62, (1,), generator=self.gen).item()))
             yield assemble_batch(self.rgb, self.flow, self.rgb_mean_std, flip=flip,
-                                 teacher=self.teacher, index=idx)
+                                 teacher=self.teacher, index=idx, **kw)
