@@ -91,6 +91,12 @@ VPD_API int vpd_nchw_to_stem(const float* x, void* out_stem_bf16, int B, int C, 
 VPD_API int vpd_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
               double lr, double beta1, double beta2, double eps, double weight_decay, int step,
               float grad_scale, void* stream);
+/* fused SGD: torch.optim.SGD over the same flat arenas (the reference trains with AdamW; this
+ * is the other optimiser BASELINE.json's north_star names). momentum_buf may be NULL when
+ * momentum == 0; first_step != 0 initialises the buffer with the gradient like torch does. */
+VPD_API int vpd_sgd(float* params, const float* grads, float* momentum_buf, int64_t n, double lr,
+            double momentum, double dampening, double weight_decay, int nesterov, int first_step,
+            float grad_scale, void* stream);
 
 /* ---- K2: single convolution ops (NHWC bf16), used by the tests and the network ---
  * Replace ATen conv2d forward / backward as called by torchvision BasicBlock

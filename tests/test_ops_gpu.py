@@ -452,3 +452,27 @@ def test_assemble_masked_noise_device_rng_statistics():
     assemble_stem(stem, rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD, seed=5, **args)
     got = stem[:, 3:3 + H, 3:3 + W, :5].permute(0, 3, 1, 2).float()
     assert torch.equal(got, a.to(torch.bfloat16).float())
+
+
+# ----------------------------------------------------------------- fused SGD
+@pytest.mark.parametrize('cfg', [dict(momentum=0.0, weight_decay=0.0),
+                                 dict(momentum=0.9, weight_decay=1e-4),
+                                 dict(momentum=0.9, weight_decay=5e-4, nesterov=True),
+                                 dict(momentum=0.8, dampening=0.1, weight_decay=0.0)])
+def test_sgd_matches_torch(cfg):
+    n = 4099
+    g = torch.Generator().manual_seed(91)
+    p0 = torch.randn(n, generator=g)
+    ref_p = torch.nn.Parameter(p0.clone().to(dev()))
+    opt = torch.optim.SGD([ref_p], lr=0.05, foreach=False, **cfg)
+    dp = p0.clone().to(dev())
+    buf = torch.zeros(n, device=dev()) if cfg.get('momentum', 0) else None
+    for t in range(1, 5):
+        grad = torch.randn(n, generator=g).to(dev())
+        ref_p.grad = grad.clone()
+        opt.step()
+        lib().call('vpd_sgd', dp, grad, buf, n, 0.05, cfg.get('momentum', 0.0),
+                   cfg.get('dampening', 0.0), cfg.get('weight_decay', 0.0),
+                   int(cfg.get('nesterov', False)), int(t == 1), 1.0, stream_ptr())
+        # same operations up to fma contraction: a few ulp at most
+        assert torch.allclose(dp, ref_p.detach(), rtol=2e-6, atol=2e-7), (cfg, t)

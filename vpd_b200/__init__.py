@@ -11,14 +11,14 @@ All compute runs in libvpd_b200.so (hand-written CUDA behind the C ABI of
 include/vpd_b200.h); importing the model classes without that library raises.
 """
 
-__all__ = ['RGBF_EmbeddingModel', 'ModelTrainer', 'FusedAdamW']
+__all__ = ['RGBF_EmbeddingModel', 'ModelTrainer', 'FusedAdamW', 'FusedSGD']
 
 
 def __getattr__(name):
     if name == 'RGBF_EmbeddingModel':
         from .rgb import RGBF_EmbeddingModel
         return RGBF_EmbeddingModel
-    if name in ('ModelTrainer', 'FusedAdamW'):
+    if name in ('ModelTrainer', 'FusedAdamW', 'FusedSGD'):
         from . import trainer
         return getattr(trainer, name)
     raise AttributeError(name)

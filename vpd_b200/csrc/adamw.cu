@@ -94,4 +94,66 @@ int adamw_step(float* p, const float* g, float* m, float* v, long long n, double
   return 0;
 }
 
+// ---------------------------------------------------------------- fused SGD
+// torch.optim.SGD (single-tensor path, torch/optim/sgd.py::_single_tensor_sgd) over the flat
+// arena, one launch:
+//     g1  = g + wd * p                       (weight_decay != 0)
+//     buf = g1                 (first step)  |  buf = momentum * buf + (1 - dampening) * g1
+//     g2  = nesterov ? g1 + momentum * buf : buf          (momentum != 0)
+//     p   = p - lr * g2
+// every `a + alpha * b` is one fma, which is what ATen's vectorised add(alpha) does.
+struct SgdScalars {
+  float lr, momentum, one_minus_damp, wd, gscale;
+  int nesterov, first;
+};
+
+__device__ __forceinline__ void sgd_one(float& p, float g, float* buf, const SgdScalars& s) {
+  if (s.gscale != 1.f) g = __fmul_rn(g, s.gscale);
+  if (s.wd != 0.f) g = __fmaf_rn(s.wd, p, g);
+  if (s.momentum != 0.f) {
+    float b;
+    if (s.first) b = g;
+    else b = __fmaf_rn(s.one_minus_damp, g, __fmul_rn(*buf, s.momentum));
+    *buf = b;
+    g = s.nesterov ? __fmaf_rn(s.momentum, b, g) : b;
+  }
+  p = __fmaf_rn(-s.lr, g, p);
+}
+
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
+           const SgdScalars s) {
+  pdl_trigger();
+  pdl_wait();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pp = p[i];
+    sgd_one(pp, __ldcs(g + i), buf ? buf + i : nullptr, s);
+    p[i] = pp;
+  }
+}
+
+int sgd_step(float* p, const float* g, float* buf, long long n, double lr, double momentum,
+             double dampening, double wd, int nesterov, int first_step, float grad_scale,
+             cudaStream_t stream) {
+  VPD_REQUIRE(momentum == 0.0 || buf != nullptr, "sgd: momentum needs a buffer");
+  VPD_REQUIRE(!nesterov || (momentum > 0.0 && dampening == 0.0),
+              "sgd: nesterov needs momentum > 0 and zero dampening");
+  if (n == 0) return 0;
+  SgdScalars s;
+  s.lr = (float)lr;
+  s.momentum = (float)momentum;
+  s.one_minus_damp = (float)(1.0 - dampening);
+  s.wd = (float)wd;
+  s.gscale = grad_scale;
+  s.nesterov = nesterov;
+  s.first = first_step;
+  long long blocks = (n + 255) / 256;
+  const long long cap = (long long)148 * 8;
+  if (blocks > cap) blocks = cap;
+  VPD_CHECK_CUDA(launch_kernel(sgd_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, p, g, buf, n, s));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
 }  // namespace vpd

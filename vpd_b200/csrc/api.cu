@@ -78,6 +78,13 @@ int vpd_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_
                     step, grad_scale, (cudaStream_t)stream);
 }
 
+int vpd_sgd(float* params, const float* grads, float* momentum_buf, int64_t n, double lr,
+            double momentum, double dampening, double weight_decay, int nesterov, int first_step,
+            float grad_scale, void* stream) {
+  return sgd_step(params, grads, momentum_buf, n, lr, momentum, dampening, weight_decay, nesterov,
+                  first_step, grad_scale, (cudaStream_t)stream);
+}
+
 int vpd_pack_conv_weight(const float* w_oihw, void* w_tap_bf16, void* wT_tap_bf16, int Cout,
                          int Cin, int k, void* stream) {
   return pack_conv_weight(w_oihw, (bf16*)w_tap_bf16, (bf16*)wT_tap_bf16, Cout, Cin, k,

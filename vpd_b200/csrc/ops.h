@@ -29,6 +29,10 @@ int adamw_step(float* p, const float* g, float* m, float* v, long long n, double
                double b2, double eps, double wd, int step, float grad_scale,
                cudaStream_t stream);
 
+int sgd_step(float* p, const float* g, float* buf, long long n, double lr, double momentum,
+             double dampening, double wd, int nesterov, int first_step, float grad_scale,
+             cudaStream_t stream);
+
 int umma_probe(const __nv_bfloat16* src, int rows, int row_start, int sbo_bytes,
                int base_offset_mode, float* out, cudaStream_t stream);
 

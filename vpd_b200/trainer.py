@@ -64,6 +64,35 @@ class FusedAdamW:
         self.step_count = sd['step']
 
 
+class FusedSGD:
+    """torch.optim.SGD (momentum / dampening / weight_decay / nesterov) as one kernel launch
+    over the flat parameter arena."""
+
+    def __init__(self, encoder, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False):
+        self.encoder = encoder
+        self.lr, self.momentum, self.dampening = lr, momentum, dampening
+        self.weight_decay, self.nesterov = weight_decay, nesterov
+        self.step_count = 0
+        self._buf = None
+
+    def step(self):
+        enc = self.encoder
+        p = enc._params
+        if self.momentum != 0 and (self._buf is None or self._buf.numel() != p.numel()):
+            self._buf = torch.zeros_like(p)
+            self.step_count = 0
+        self.step_count += 1
+        with torch.cuda.device(enc._dev):
+            lib().call('vpd_sgd', p, enc._grads, self._buf, p.numel(), self.lr, self.momentum,
+                       self.dampening, self.weight_decay, int(self.nesterov),
+                       int(self.step_count == 1), 1.0, stream_ptr(enc._dev))
+            if enc._net is not None:
+                lib().call('vpd_net_params_changed', enc._net.handle)
+
+    def zero_grad(self, set_to_none=False):
+        pass    # every train step overwrites the whole gradient arena
+
+
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
