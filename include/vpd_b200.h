@@ -81,6 +81,25 @@ VPD_API int vpd_assemble_stem_noise(const uint8_t* rgb, const uint8_t* flow, int
                             void* out_stem_bf16, float* out_tgt, int B, int H, int W,
                             const uint8_t* mask, const uint8_t* noise_on, const float* noise,
                             float noise_sd, uint64_t seed, void* stream);
+/* Training batch with the reference's full `augment=True` pipeline (single_frame.py:168-206):
+ * u8/255 -> transforms.ColorJitter (vpd_dataset/common.py:11-12,88-92) -> Normalize -> masked
+ * noise (:179-191) -> flow stacked -> horizontal flip (:199-203) -> transforms.RandomResizedCrop
+ * (common.py:49-50,79-80; antialiased bilinear resize of the crop back to H x W). The DRAWS are
+ * made by the caller in the reference's order (vpd_b200/augment.py); the pixel arithmetic
+ * follows torchvision / ATen rounding for rounding.
+ *   jitter_order  uint8 [B][4]  permutation of 0 brightness, 1 contrast, 2 saturation, 3 hue
+ *                               (a value > 3 skips that slot); NULL = no ColorJitter
+ *   jitter_factor fp32 [B][8]   {b, c, 1-c, s, 1-s, hue, 0, 0}, each rounded from the double
+ *   crop          int32 [B][4]  (i, j, h, w) inside the frame; NULL = no crop
+ *   mask / noise_on / noise / noise_sd / seed: as vpd_assemble_nchw_noise (mask NULL = none)
+ * Output fp32 [B][C][H][W]. One CTA per frame; H*W*12 bytes of shared memory (<= 227 KB). */
+VPD_API int vpd_assemble_nchw_aug(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
+                          const int32_t* index, const uint8_t* flip, const float* teacher,
+                          int teacher_rows, int tdim, const float* mean, const float* std,
+                          float* out_img, float* out_tgt, int B, int H, int W,
+                          const uint8_t* jitter_order, const float* jitter_factor,
+                          const int32_t* crop, const uint8_t* mask, const uint8_t* noise_on,
+                          const float* noise, float noise_sd, uint64_t seed, void* stream);
 /* fp32 NCHW batch (the reference's batch['img']) -> network input layout */
 VPD_API int vpd_nchw_to_stem(const float* x, void* out_stem_bf16, int B, int C, int H, int W,
                      void* stream);

@@ -248,17 +248,60 @@ def gen_targets(ref):
     print('targets.npz / targets.json written')
 
 
+def gen_augment(ref):
+    """A3 with augment=True: the real GenericDataset.__getitem__ (ColorJitter, masked noise,
+    flip, RandomResizedCrop) after `random.seed(s); torch.manual_seed(s)`. Only the outputs are
+    stored; tests re-draw the parameters with vpd_b200.augment.draw_batch from the same seeds."""
+    import cv2
+    from oracle import augment_ref
+    out = {}
+    tmp = tempfile.mkdtemp()
+    try:
+        ms = ref.RGB_MEAN_STD['fs']
+        for tag, n, dim, items, seed in (('s32', 6, 32, 12, 21), ('s128', 3, 128, 3, 22)):
+            rgb, flow, mask, has_mask = augment_ref.augment_inputs(n, seed, dim, dim)
+            video = 'aug' + tag
+            write_crop_dir(tmp, video, rgb, flow)
+            for i in range(n):
+                if bool(has_mask[i]):
+                    cv2.imwrite(os.path.join(tmp, video, '{}.mask.png'.format(i)),
+                                mask[i].numpy()[:, :, None].repeat(3, axis=2))
+            teach = synth.teacher(n, seed=seed + 1, emb_dim=8, motion=True).numpy()
+            data = [(video, i, teach[i], {}) for i in range(n)]
+            gd = ref.GenericDataset(data, tmp, dim, ms, items, augment=True, flow_img_name='flow')
+            random.seed(seed)
+            torch.manual_seed(seed)
+            imgs, embs = [], []
+            for k in range(items):
+                item = gd[k]
+                imgs.append(item['img'])
+                embs.append(item['emb'])
+            img = torch.stack(imgs).numpy()
+            out[tag + '_emb'] = torch.stack(embs).numpy()
+            out[tag + '_seed'] = np.array(seed)
+            if dim > 32:                       # keep the fixture small: every 4th pixel + a hash
+                out[tag + '_img_sub4'] = img[:, :, ::4, ::4].copy()
+            else:
+                out[tag + '_img'] = img
+    finally:
+        shutil.rmtree(tmp)
+    np.savez_compressed(os.path.join(GOLD, 'augment.npz'), **out)
+    print('augment.npz written')
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_shim.load()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['assembly', 'student', 'targets']
+    which = sys.argv[1:] or ['assembly', 'student', 'targets', 'augment']
     if 'assembly' in which:
         gen_assembly(ref)
     if 'student' in which:
         gen_student(ref)
     if 'targets' in which:
         gen_targets(ref)
+    if 'augment' in which:
+        gen_augment(ref)
     with open(os.path.join(GOLD, 'README.md'), 'w') as fp:
         fp.write('Golden vectors produced by `python -m oracle.gen_golden` from the unmodified\n'
                  'reference at /root/reference (torch {}, CPU fp32). Inputs are regenerated\n'

@@ -1,0 +1,135 @@
+"""CPU tests of the augmented training batch (stochastic half):
+the oracle restatement (oracle/augment_ref.py) against torchvision / ATen themselves and
+against the golden outputs of the unmodified reference dataset, and the host-side sampler
+(vpd_b200/augment.py) that re-draws the reference's random parameters from the same seeds.
+
+Tolerances: everything is bit-exact except what follows `adjust_contrast`, whose grayscale
+mean the reference takes with `torch.mean` (summation order depends on the CPU's vector
+width). The oracle uses the fp64 sum; the mean then differs by at most one fp32 ulp, which the
+remaining jitter ops, the normalisation (1/std ~ 5) and the resize carry to at most 2e-5 in
+the normalised image (measured <= 8e-6; asserted 2e-5)."""
+import itertools
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import augment_ref as A
+from vpd_b200 import augment, synth
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden', 'augment.npz')
+CONTRAST_TOL = 2e-5
+
+
+def _same(a, b):
+    return bool(np.array_equal(np.asarray(a), np.asarray(b)))   # value equality (-0 == +0)
+
+
+def test_color_jitter_bit_exact_vs_torchvision():
+    import torchvision.transforms.functional as F
+    torch.manual_seed(1)
+    for trial, perm in enumerate(itertools.permutations(range(4))):
+        u = torch.randint(0, 256, (24, 40, 3), dtype=torch.uint8)
+        if trial % 3 == 0:
+            u[:6] = u[:6, :, :1]                 # gray pixels: the maxc == minc branch
+            u[6, :20] = 0
+            u[6, 20:] = 255
+        x = torch.FloatTensor(u.numpy()).permute(2, 0, 1) / 255.
+        b = float(torch.empty(1).uniform_(0.8, 1.2))
+        c = float(torch.empty(1).uniform_(0.8, 1.2))
+        s = float(torch.empty(1).uniform_(0.95, 1.05))
+        h = float(torch.empty(1).uniform_(-0.05, 0.05))
+        y = x.clone()
+        mean = None
+        for fn in perm:
+            if fn == 0:
+                y = F.adjust_brightness(y, b)
+            elif fn == 1:
+                mean = torch.mean(F.rgb_to_grayscale(y), dim=(-3, -2, -1)).item()
+                y = F.adjust_contrast(y, c)
+            elif fn == 2:
+                y = F.adjust_saturation(y, s)
+            else:
+                y = F.adjust_hue(y, h)
+        exact = A.color_jitter(x.numpy(), perm, b, c, s, h, contrast_mean=mean)
+        assert _same(exact, y.numpy()), perm
+        own = A.color_jitter(x.numpy(), perm, b, c, s, h)
+        assert np.abs(own - y.numpy()).max() <= 4e-6, perm
+        # a skipped op (factor None) is skipped here too
+        y2 = F.adjust_hue(F.adjust_brightness(x, b), h)
+        assert _same(A.color_jitter(x.numpy(), (0, 1, 2, 3), b, None, None, h), y2.numpy())
+
+
+@pytest.mark.parametrize('box', [(3, 5, 100, 97), (0, 0, 128, 128), (10, 20, 91, 100),
+                                 (7, 9, 64, 70), (0, 1, 127, 113), (0, 0, 128, 120),
+                                 (31, 0, 97, 128)])
+def test_resized_crop_bit_exact_vs_aten(box):
+    import torchvision.transforms.functional as F
+    from torchvision.transforms import InterpolationMode
+    img = torch.randn(5, 128, 128, generator=torch.Generator().manual_seed(0))
+    i, j, h, w = box
+    ref = F.resized_crop(img, i, j, h, w, [128, 128], InterpolationMode.BILINEAR,
+                         antialias=True).numpy()
+    assert _same(A.resized_crop(img.numpy(), i, j, h, w, 128, 128), ref)
+
+
+def test_sampler_packs_what_the_kernel_reads():
+    random.seed(5)
+    torch.manual_seed(5)
+    has_mask = torch.tensor([True, False, True, True])
+    p = augment.draw_batch(16, 4, 128, 128, has_mask=has_mask, host_noise=False)
+    augment.check_params(p, 128, 128)
+    c = p.crop.numpy()
+    area = c[:, 2] * c[:, 3] / (128. * 128.)
+    assert (area > 0.45).all() and (area <= 1.0).all()
+    ratio = c[:, 3] / c[:, 2]
+    assert (ratio > 0.85).all() and (ratio < 1.16).all()
+    for b in range(16):
+        fn_idx, bf, cf, sf, hf = p.jitter[b]
+        assert sorted(fn_idx) == [0, 1, 2, 3] and p.jitter_order[b].tolist() == fn_idx
+        assert 0.8 <= bf <= 1.2 and 0.8 <= cf <= 1.2 and 0.95 <= sf <= 1.05 and -.05 <= hf <= .05
+        jf = p.jitter_factor[b].numpy()
+        assert jf[0] == np.float32(bf) and jf[2] == np.float32(1.0 - cf)
+        assert jf[4] == np.float32(1.0 - sf) and jf[5] == np.float32(hf)
+        if p.noise_on[b]:
+            assert bool(has_mask[int(p.index[b])])
+    assert 0 < int(p.noise_on.sum()) < 16 and 0 < int(p.flip.sum()) < 16
+    # jitter / crop can be switched off (the reference's augment=False datasets)
+    q = augment.draw_batch(3, 4, 32, 32, jitter=None, crop=False)
+    assert (q.jitter_order == 255).all() and q.crop.tolist() == [[0, 0, 32, 32]] * 3
+    with pytest.raises(AssertionError):
+        q.crop[0, 2] = 40
+        augment.check_params(q, 32, 32)
+
+
+@pytest.mark.parametrize('tag,n,dim,items', [('s32', 6, 32, 12), ('s128', 3, 128, 3)])
+def test_oracle_and_sampler_reproduce_the_reference_dataset(tag, n, dim, items):
+    """golden = the unmodified GenericDataset.__getitem__ (augment=True) after seeding both
+    generators; here the same seeds go through OUR sampler and the oracle's arithmetic."""
+    gold = np.load(GOLD)
+    seed = int(gold[tag + '_seed'])
+    rgb, flow, mask, has_mask = A.augment_inputs(n, seed, dim, dim)
+    teach = synth.teacher(n, seed=seed + 1, emb_dim=8, motion=True).numpy()
+    random.seed(seed)
+    torch.manual_seed(seed)
+    p = augment.draw_batch(items, n, dim, dim, has_mask=has_mask, host_noise=True)
+    ms = synth.FS_MEAN_STD
+    exact = 0
+    for k in range(items):
+        i = int(p.index[k])
+        on = bool(p.noise_on[k])
+        img, emb = A.augment_item(rgb[i].numpy(), flow[i].numpy(), teach[i], bool(p.flip[k]),
+                                  ms[0], ms[1], jitter=p.jitter[k],
+                                  crop=tuple(int(v) for v in p.crop[k]),
+                                  mask_u8=mask[i].numpy() if on else None,
+                                  noise=p.noise[k].numpy() if on else None)
+        assert _same(emb, gold[tag + '_emb'][k])
+        want = gold[tag + '_img'][k] if dim == 32 else gold[tag + '_img_sub4'][k]
+        got = img if dim == 32 else img[:, ::4, ::4]
+        assert np.abs(got - want).max() <= CONTRAST_TOL, (k, float(np.abs(got - want).max()))
+        assert _same(got[3:], want[3:])          # the flow planes never see the contrast mean
+        exact += _same(got, want)
+    assert exact >= items // 3                   # the mean usually rounds the same way
+    assert int(p.noise_on.sum()) > 0 or dim > 32

@@ -62,6 +62,44 @@ def assemble_batch(rgb, flow, rgb_mean_std, flip=None, teacher=None, index=None,
     return out
 
 
+def assemble_batch_aug(rgb, flow, rgb_mean_std, params, teacher=None, mask=None,
+                       noise_sd=RANDOM_NOISE_SD, seed=None):
+    """The reference's `augment=True` training batch (single_frame.py:168-206) on the device:
+    ColorJitter -> Normalize -> masked noise -> flow -> flip -> RandomResizedCrop, with the
+    draws in `params` (`vpd_b200.augment.draw_batch`, already on rgb's device).
+    -> {'img': fp32 [B,C,H,W], 'emb': fp32 [B,E] (if teacher given)}.
+    mask uint8 [P,H,W] enables the noise for the frames with params.noise_on; params.noise
+    (fp32 [B,3,H,W], host-drawn) makes it exact, else the device generator runs from `seed`."""
+    from .augment import check_params
+    mean, std = _mean_std(rgb_mean_std)
+    P, H, W, _ = rgb.shape
+    check_params(params, H, W)
+    B = params.index.numel()
+    C = 5 if flow is not None else 3
+    img = torch.empty((B, C, H, W), device=rgb.device, dtype=torch.float32)
+    emb = None
+    rows = tdim = 0
+    if teacher is not None:
+        teacher = teacher.contiguous()
+        rows = teacher.shape[1] if teacher.dim() == 3 else 1
+        tdim = teacher.shape[-1]
+        emb = torch.empty((B, tdim), device=rgb.device, dtype=torch.float32)
+    jo, jf = params.jitter_order, params.jitter_factor
+    if jo is not None and bool((jo > 3).all()):
+        jo = jf = None
+    nz = (None, None, None, 0.0, 0)
+    if mask is not None:
+        nz = _noise_args(mask, params.noise_on, params.noise, noise_sd, seed)
+    lib().call('vpd_assemble_nchw_aug', rgb, flow, 0 if flow is None else flow.shape[-1],
+               params.index, params.flip, teacher, rows,
+               tdim, mean, std, img, emb, B, H, W, jo, jf, params.crop, *nz,
+               stream_ptr(rgb.device))
+    out = {'img': img}
+    if emb is not None:
+        out['emb'] = emb
+    return out
+
+
 def assemble_apply(rgb, flow, rgb_mean_std, flip=True):
     """FrameDataset batch: fp32 [B,k,C,H,W], k = 2 ([orig, flipped]) or 1."""
     mean, std = _mean_std(rgb_mean_std)

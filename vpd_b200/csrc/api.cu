@@ -66,6 +66,24 @@ int vpd_assemble_stem_noise(const uint8_t* rgb, const uint8_t* flow, int flow_ch
                        std, (bf16*)out_stem_bf16, out_tgt, B, H, W, 1, (cudaStream_t)stream, &nz);
 }
 
+int vpd_assemble_nchw_aug(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
+                          const int32_t* index, const uint8_t* flip, const float* teacher,
+                          int teacher_rows, int tdim, const float* mean, const float* std,
+                          float* out_img, float* out_tgt, int B, int H, int W,
+                          const uint8_t* jitter_order, const float* jitter_factor,
+                          const int32_t* crop, const uint8_t* mask, const uint8_t* noise_on,
+                          const float* noise, float noise_sd, uint64_t seed, void* stream) {
+  AsmNoise nz;
+  nz.mask = mask;
+  nz.noise_on = noise_on;
+  nz.noise = noise;
+  nz.noise_sd = noise_sd;
+  nz.seed = seed;
+  return assemble_aug(rgb, flow, flow_channels, index, flip, teacher, teacher_rows, tdim, mean,
+                      std, out_img, out_tgt, B, H, W, jitter_order, jitter_factor, crop,
+                      (cudaStream_t)stream, &nz);
+}
+
 int vpd_nchw_to_stem(const float* x, void* out_stem_bf16, int B, int C, int H, int W,
                      void* stream) {
   return nchw_to_pad8(x, (bf16*)out_stem_bf16, B, C, H, W, (cudaStream_t)stream);

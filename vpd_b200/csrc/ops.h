@@ -23,6 +23,12 @@ int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
                   const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
                   const float* mean, const float* stdv, __nv_bfloat16* out_pad, float* out_tgt,
                   int B, int H, int W, int k, cudaStream_t stream, const AsmNoise* nz = nullptr);
+// training batch with ColorJitter + RandomResizedCrop (+ noise, flip) applied, fp32 NCHW
+int assemble_aug(const uint8_t* rgb, const uint8_t* flow, int flow_channels, const int* index,
+                 const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
+                 const float* mean, const float* stdv, float* out_img, float* out_tgt, int B,
+                 int H, int W, const uint8_t* jitter_order, const float* jitter_factor,
+                 const int* crop, cudaStream_t stream, const AsmNoise* nz = nullptr);
 int nchw_to_pad8(const float* x, __nv_bfloat16* out, int B, int C, int H, int W,
                  cudaStream_t stream);
 int adamw_step(float* p, const float* g, float* m, float* v, long long n, double lr, double b1,

@@ -72,14 +72,23 @@ class PoolLoader:
     Yields the reference's batch dict {'img': f32 [B,5,H,W], 'emb': f32 [B,Dt]} on the GPU.
     With `mask_u8` [P,H,W] (first channel of `<n>.mask.png`, zeros where a frame has none) the
     masked-noise augmentation of single_frame.py:179-191 is applied on the device with its
-    per-frame coin (p = 0.5). ColorJitter and RandomResizedCrop are not applied - they are
-    unseeded torchvision draws in the reference and stay host-side."""
+    per-frame coin (p = 0.5).
+    `augment=True` is the reference's `augment=True` dataset in full (single_frame.py:168-206):
+    ColorJitter, masked noise, flip and RandomResizedCrop, drawn per frame in the reference's
+    order from Python `random` and torch's global generator (vpd_b200/augment.py - seed THOSE
+    to reproduce a single-process reference loader; `seed` is not used then) and applied by
+    the K1a kernel; `has_mask` [P] says which frames have a mask PNG (default: all, if
+    `mask_u8` is given); `host_noise=True` also draws the noise on the host like the reference
+    (exact, but 3*H*W floats per noisy frame over PCIe) instead of the device generator."""
 
     def __init__(self, rgb_u8, flow_u8, teacher, rgb_mean_std, batch_size, target_len, seed=0,
-                 mask_u8=None):
+                 mask_u8=None, augment=False, has_mask=None, host_noise=False):
         import torch
         self.rgb, self.flow, self.teacher = rgb_u8, flow_u8, teacher
         self.mask = mask_u8
+        self.augment, self.has_mask, self.host_noise = augment, has_mask, host_noise
+        if augment and mask_u8 is not None and has_mask is None:
+            self.has_mask = torch.ones(rgb_u8.shape[0], dtype=torch.bool)
         self.rgb_mean_std = rgb_mean_std
         self.batch_size, self.target_len = batch_size, target_len
         self.gen = torch.Generator().manual_seed(seed)
@@ -96,6 +105,16 @@ class PoolLoader:
         while left > 0:
             b = min(self.batch_size, left)
             left -= b
+            if self.augment:
+                from .assemble import assemble_batch_aug
+                from .augment import draw_batch
+                two_rows = self.teacher is not None and self.teacher.dim() == 3
+                p = draw_batch(b, n, self.rgb.shape[1], self.rgb.shape[2], two_rows=two_rows,
+                               has_mask=self.has_mask, host_noise=self.host_noise,
+                               channels=5 if self.flow is not None else 3).to(dev)
+                yield assemble_batch_aug(self.rgb, self.flow, self.rgb_mean_std, p,
+                                         teacher=self.teacher, mask=self.mask)
+                continue
             idx = torch.randint(0, n, (b,), generator=self.gen).int().to(dev)
             flip = torch.randint(0, 2, (b,), generator=self.gen).to(torch.uint8).to(dev)
             kw = {}
