@@ -197,6 +197,27 @@ VPD_API int vpd_head_fwd_bwd(const void* z, int B, int HW, int F, int D, int T, 
                      const float* params, const float* target, float* emb_out, float* out,
                      double* loss_sum, void* dz, float* ws, float* grads, void* stream);
 
+/* ---- keypoint (VIPE*) teacher encoder: row-matrix helpers -----------------------------
+ * The teacher whose embeddings the student regresses is an MLP (models/module.py:159-204
+ * FcResidualBlock / FCResNet; eval forward models/keypoint.py:128-160 `_predict`,
+ * apply_vipe_model.py:165-204). Its hidden x hidden Linear layers run on vpd_conv2d_fwd as
+ * 1x1 convolutions over an [n][1][1][C] tensor (Linear bias + eval BatchNorm1d folded into
+ * the epilogue's scale/shift by vpd_bn_fold); these cover the rest:
+ *   vpd_rows_to_bf16    fp32 [M][C] -> bf16 [M][Cpad], zero padded (39 pose values -> 64)
+ *   vpd_axpby_bf16      out = alpha*a + beta*b over n bf16 values (b may be NULL): `x2 - x`
+ *   vpd_bn_fold         scale = gamma/sqrt(var+eps), shift = (bias-mean)*scale + beta
+ *                       (bias may be NULL)
+ *   vpd_linear_rows_f32 out fp32 [M][D] = x bf16 [M][K] . w fp32 [D][K]^T + bias; D <= 64,
+ *                       K % 64 == 0 (the last Linear: the embedding is never rounded to bf16) */
+VPD_API int vpd_rows_to_bf16(const float* x, void* out_bf16, int64_t M, int C, int Cpad, void* stream);
+VPD_API int vpd_axpby_bf16(const void* a, float alpha, const void* b, float beta, void* out, int64_t n,
+                   void* stream);
+VPD_API int vpd_bn_fold(const float* gamma, const float* beta, const float* running_mean,
+                const float* running_var, const float* bias, float eps, float* scale,
+                float* shift, int C, void* stream);
+VPD_API int vpd_linear_rows_f32(const void* x_bf16, const float* w, const float* bias, float* out,
+                        int64_t M, int K, int D, void* stream);
+
 /* ---- the student network ---------------------------------------------------------
  * Replaces RGBF_EmbeddingModel.forward/embed (models/rgb.py:68-86), the body of
  * ModelTrainer.epoch (train_vpd_model.py:67-98: forward, FCNet decoder,

@@ -289,11 +289,49 @@ def gen_augment(ref):
     print('augment.npz written')
 
 
+def gen_keypoint(ref):
+    """VIPE* teacher apply path: the reference's FCResNet + Keypoint_EmbeddingModel.embed and
+    apply_vipe_model.mean_embs_by_frame on seeded inputs."""
+    import types
+    from oracle import keypoint_ref
+    sys.modules.setdefault('matplotlib', types.ModuleType('matplotlib'))
+    from models.module import FCResNet
+    from models.keypoint import Keypoint_EmbeddingModel
+    import apply_vipe_model
+    out = {}
+    for tag, in_dim, joints, hidden, blocks, seed in (('d39', 39, 13, 1024, 2, 5),
+                                                     ('d75', 75, 25, 256, 1, 6)):
+        torch.manual_seed(seed)
+        enc = FCResNet(in_dim, 32, blocks, hidden, dropout=0.2)
+        out[tag + '_init_sha256'] = np.array(sd_hash(enc.state_dict()))
+        enc.load_state_dict(keypoint_ref.perturb_bn(enc.state_dict(), seed + 100))
+        model = Keypoint_EmbeddingModel(enc, {}, 'cpu')
+        poses = keypoint_ref.synth_poses(96, seed + 200, joints)
+        out[tag + '_emb'] = model.embed(poses)
+        out[tag + '_emb_one'] = model.embed(poses[3].numpy())           # [J,3] -> [1,D]
+        out[tag + '_seed'] = np.array(seed)
+    # mean_embs_by_frame: 2 detections in some frames, flipped twins
+    g = torch.Generator().manual_seed(9)
+    embs = []
+    for frame in (7, 3, 3, 11):
+        for fl in (False, True):
+            embs.append((frame, torch.randn(32, generator=g).numpy(),
+                         {'kp_score': float(torch.rand(1, generator=g)), 'is_mean': False,
+                          'is_flip': fl}))
+    res = apply_vipe_model.mean_embs_by_frame(embs, True)
+    out['mean_frames'] = np.array([r[0] for r in res])
+    out['mean_embs'] = np.stack([r[1] for r in res])
+    out['mean_scores'] = np.array([r[2]['kp_score'] for r in res])
+    out['mean_is_mean'] = np.array([r[2]['is_mean'] for r in res])
+    np.savez_compressed(os.path.join(GOLD, 'keypoint.npz'), **out)
+    print('keypoint.npz written')
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_shim.load()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['assembly', 'student', 'targets', 'augment']
+    which = sys.argv[1:] or ['assembly', 'student', 'targets', 'augment', 'keypoint']
     if 'assembly' in which:
         gen_assembly(ref)
     if 'student' in which:
@@ -302,6 +340,8 @@ def main():
         gen_targets(ref)
     if 'augment' in which:
         gen_augment(ref)
+    if 'keypoint' in which:
+        gen_keypoint(ref)
     with open(os.path.join(GOLD, 'README.md'), 'w') as fp:
         fp.write('Golden vectors produced by `python -m oracle.gen_golden` from the unmodified\n'
                  'reference at /root/reference (torch {}, CPU fp32). Inputs are regenerated\n'

@@ -84,6 +84,25 @@ int vpd_assemble_nchw_aug(const uint8_t* rgb, const uint8_t* flow, int flow_chan
                       (cudaStream_t)stream, &nz);
 }
 
+int vpd_rows_to_bf16(const float* x, void* out_bf16, int64_t M, int C, int Cpad, void* stream) {
+  return rows_to_bf16(x, (bf16*)out_bf16, M, C, Cpad, (cudaStream_t)stream);
+}
+int vpd_axpby_bf16(const void* a, float alpha, const void* b, float beta, void* out, int64_t n,
+                   void* stream) {
+  return axpby_bf16((const bf16*)a, alpha, (const bf16*)b, beta, (bf16*)out, n,
+                    (cudaStream_t)stream);
+}
+int vpd_bn_fold(const float* gamma, const float* beta, const float* running_mean,
+                const float* running_var, const float* bias, float eps, float* scale,
+                float* shift, int C, void* stream) {
+  return bn_fold(gamma, beta, running_mean, running_var, bias, eps, scale, shift, C,
+                 (cudaStream_t)stream);
+}
+int vpd_linear_rows_f32(const void* x_bf16, const float* w, const float* bias, float* out,
+                        int64_t M, int K, int D, void* stream) {
+  return linear_rows_f32((const bf16*)x_bf16, w, bias, out, M, K, D, (cudaStream_t)stream);
+}
+
 int vpd_nchw_to_stem(const float* x, void* out_stem_bf16, int B, int C, int H, int W,
                      void* stream) {
   return nchw_to_pad8(x, (bf16*)out_stem_bf16, B, C, H, W, (cudaStream_t)stream);

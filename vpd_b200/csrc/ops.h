@@ -39,6 +39,16 @@ int sgd_step(float* p, const float* g, float* buf, long long n, double lr, doubl
              double dampening, double wd, int nesterov, int first_step, float grad_scale,
              cudaStream_t stream);
 
+// row-matrix helpers of the keypoint (VIPE*) encoder, mlp.cu
+int rows_to_bf16(const float* x, __nv_bfloat16* out, long long M, int C, int Cpad,
+                 cudaStream_t stream);
+int axpby_bf16(const __nv_bfloat16* a, float alpha, const __nv_bfloat16* b, float beta,
+               __nv_bfloat16* out, long long n, cudaStream_t stream);
+int bn_fold(const float* gamma, const float* beta, const float* mean, const float* var,
+            const float* bias, float eps, float* scale, float* shift, int C, cudaStream_t stream);
+int linear_rows_f32(const __nv_bfloat16* x, const float* w, const float* bias, float* out,
+                    long long M, int K, int D, cudaStream_t stream);
+
 int umma_probe(const __nv_bfloat16* src, int rows, int row_start, int sbo_bytes,
                int base_offset_mode, float* out, cudaStream_t stream);
 

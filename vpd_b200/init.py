@@ -99,3 +99,24 @@ def decoder_state(emb_dim):
                         ('layers.5', (2 * emb_dim, 128))):
         sd[key + '.weight'], sd[key + '.bias'] = _draw_linear(o, i)
     return sd
+
+
+def fcresnet_state(in_dim, out_dim, num_blocks, hidden_dim):
+    """models/module.py:192-204 `FCResNet(in_dim, out_dim, num_blocks, hidden_dim)`: the
+    state_dict an nn.Module built in that order holds after construction (default nn.Linear /
+    nn.BatchNorm1d initialisation, same draws from the CPU generator). Keys:
+    layers.0 Linear(in, hidden); layers.{2+i}.block.{0,4} Linear(hidden, hidden) and
+    .block.{1,5} BatchNorm1d per FcResidualBlock (models/module.py:159-177); the last entry
+    Linear(hidden, out) unless out_dim is None."""
+    sd = OrderedDict()
+    sd['layers.0.weight'], sd['layers.0.bias'] = _draw_linear(hidden_dim, in_dim)
+    for i in range(num_blocks):
+        p = 'layers.{}.block'.format(2 + i)
+        for lin, bn in ((0, 1), (4, 5)):
+            w, b = _draw_linear(hidden_dim, hidden_dim)
+            sd['{}.{}.weight'.format(p, lin)], sd['{}.{}.bias'.format(p, lin)] = w, b
+            _bn(sd, '{}.{}'.format(p, bn), hidden_dim)
+    if out_dim is not None:
+        p = 'layers.{}'.format(2 + num_blocks)
+        sd[p + '.weight'], sd[p + '.bias'] = _draw_linear(out_dim, hidden_dim)
+    return sd

@@ -1,0 +1,283 @@
+"""The keypoint (VIPE*) teacher's APPLY path on the B200: `FCResNet` encoder and
+`Keypoint_EmbeddingModel.embed`, the producer of the `<video>.emb.pkl` teacher files that the
+student's target construction (`vpd_b200/targets.py`, reference single_frame.py:208-273) reads.
+
+Reference: models/module.py:159-204 (FcResidualBlock: Linear, BatchNorm1d, ReLU, Dropout,
+Linear, BatchNorm1d, ReLU, Dropout, then `x2 - x`; FCResNet: Linear + ReLU, the blocks, a last
+Linear), models/keypoint.py:14-35,128-160 (`_BaseModel`, `_predict`, `embed`),
+apply_vipe_model.py:37-69,133-204 (`mean_embs_by_frame`, `load_embedding_model`, the per-video
+loop). Same constructor arguments, same `state_dict()` keys / shapes / dtypes (checkpoints are
+interchangeable), same initialisation draw for draw (`vpd_b200/init.py::fcresnet_state`).
+
+Eval forward on the device, all through the C ABI (no torch arithmetic, no fallback):
+    poses fp32 [n, in_dim] --vpd_rows_to_bf16--> bf16 [n, 64 (128 with bones)]
+    Linear(in, hidden) + ReLU                vpd_conv2d_fwd (1x1 over [n,1,1,64]; bias = shift)
+    per block: Linear + BN1d(eval) + ReLU    vpd_conv2d_fwd, bias and BN folded by vpd_bn_fold
+               Linear + BN1d(eval) + ReLU    vpd_conv2d_fwd
+               x2 - x                        vpd_axpby_bf16
+    Linear(hidden, emb_dim)                  vpd_linear_rows_f32 (fp32 weights, fp32 output)
+Dropout is the identity in eval mode. Hidden activations are bf16 (tensor-core operands);
+the embedding is accumulated and returned in fp32.
+
+Training the teacher (`Keypoint_EmbeddingModel.epoch`: three weight-sharing encoder passes,
+hinge + MSE losses, models/keypoint.py:38-126) and the 3-D pose decoders are NOT built yet:
+those entry points raise NotImplementedError.
+"""
+import json
+import os
+import pickle
+from collections import OrderedDict, defaultdict
+
+import numpy as np
+import torch
+
+from . import init as _init
+from ._lib import lib, stream_ptr, VpdError
+
+NUM_COCO_KEYPOINTS = 13      # vipe_dataset/dataset_base.py (COCO keypoints used by VIPE)
+NUM_COCO_BONES = 12
+EMBED_BATCH_SIZE = 250       # apply_vipe_model.py:19 (the reference's chunk; we take any n)
+_MAX_ROWS = 1 << 16          # rows per launch group (bounds the activation buffers)
+_BN_EPS = 1e-5
+
+
+class FCResNet:
+    """models/module.py:192-204, eval forward on the GPU."""
+
+    def __init__(self, in_dim, out_dim, num_blocks, hidden_dim, dropout=0.3):
+        if out_dim is None:
+            raise NotImplementedError('FCResNet without the output Linear (the decoder trunk) '
+                                      'is not part of the CUDA path yet')
+        if hidden_dim % 64 != 0 or in_dim > 512 or out_dim > 64:
+            raise NotImplementedError(
+                'CUDA path: hidden_dim % 64 == 0, in_dim <= 512, out_dim <= 64 '
+                '(got in={}, hidden={}, out={})'.format(in_dim, hidden_dim, out_dim))
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self._cin = (in_dim + 63) // 64 * 64          # pose columns padded to whole channel chunks
+        self.num_blocks, self.hidden_dim, self.dropout = num_blocks, hidden_dim, dropout
+        self.training = True                          # nn.Module default
+        self._sd = _init.fcresnet_state(in_dim, out_dim, num_blocks, hidden_dim)
+        self._dev = None
+        self._prepared = None
+
+    # ---- nn.Module surface -------------------------------------------------------------
+    def to(self, device):
+        dev = torch.device('cuda' if str(device) == 'cuda' else device)
+        if dev.type != 'cuda':
+            raise VpdError("vpd_b200 needs a CUDA device; got '{}' (no CPU fallback)".format(device))
+        if dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        lib()
+        self._dev = dev
+        self._sd = OrderedDict((k, v.to(dev)) for k, v in self._sd.items())
+        self._prepared = None
+        return self
+
+    def train(self, mode=True):
+        self.training = bool(mode)
+        return self
+
+    def eval(self):
+        return self.train(False)
+
+    def state_dict(self):
+        return OrderedDict((k, v.detach().clone()) for k, v in self._sd.items())
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [k for k in self._sd if k not in sd]
+        unexpected = [k for k in sd if k not in self._sd]
+        if strict and (missing or unexpected):
+            raise RuntimeError('Error(s) in loading state_dict for FCResNet: missing {}, '
+                               'unexpected {}'.format(missing, unexpected))
+        for k, v in sd.items():
+            if k in self._sd:
+                if tuple(v.shape) != tuple(self._sd[k].shape):
+                    raise RuntimeError('size mismatch for {}: {} vs {}'.format(
+                        k, tuple(v.shape), tuple(self._sd[k].shape)))
+                self._sd[k] = v.detach().to(device=self._sd[k].device,
+                                            dtype=self._sd[k].dtype).clone()
+        self._prepared = None
+
+    def parameters(self):
+        return [v for k, v in self._sd.items()
+                if not k.endswith(('running_mean', 'running_var', 'num_batches_tracked'))]
+
+    # ---- device-side constants derived from the parameters -------------------------------
+    def _prepare(self):
+        if self._prepared is not None:
+            return self._prepared
+        if self._dev is None:
+            raise VpdError('FCResNet: call .to(cuda device) first (no CPU fallback)')
+        L, dev, H = lib(), self._dev, self.hidden_dim
+        st = stream_ptr(dev)
+        bf = lambda *s: torch.empty(s, device=dev, dtype=torch.bfloat16)
+        f32 = lambda *s: torch.empty(s, device=dev, dtype=torch.float32)
+        sd = self._sd
+        layers = []
+        # Linear(in, hidden): input columns zero-padded to a multiple of 64
+        cin = self._cin
+        w0 = torch.zeros((H, cin), device=dev, dtype=torch.float32)
+        w0[:, :self.in_dim] = sd['layers.0.weight']
+        wt = bf(H * cin)
+        L.call('vpd_pack_conv_weight', w0, wt, None, H, cin, 1, st)
+        layers.append((wt, torch.ones(H, device=dev), sd['layers.0.bias'].contiguous(), cin))
+        for i in range(self.num_blocks):
+            p = 'layers.{}.block'.format(2 + i)
+            for lin, bn in ((0, 1), (4, 5)):
+                wt = bf(H * H)
+                L.call('vpd_pack_conv_weight', sd['{}.{}.weight'.format(p, lin)].contiguous(), wt,
+                       None, H, H, 1, st)
+                scale, shift = f32(H), f32(H)
+                b = '{}.{}'.format(p, bn)
+                L.call('vpd_bn_fold', sd[b + '.weight'], sd[b + '.bias'], sd[b + '.running_mean'],
+                       sd[b + '.running_var'], sd['{}.{}.bias'.format(p, lin)], _BN_EPS, scale,
+                       shift, H, st)
+                layers.append((wt, scale, shift, H))
+        last = 'layers.{}'.format(2 + self.num_blocks)
+        self._prepared = (layers, sd[last + '.weight'].contiguous(), sd[last + '.bias'].contiguous())
+        return self._prepared
+
+    def forward(self, x):
+        """x fp32 [n, in_dim] (device or host) -> fp32 [n, out_dim] on the device. Eval mode
+        only: the training forward (batch statistics, dropout) belongs to the teacher's
+        training path, which is not built."""
+        if self.training:
+            raise NotImplementedError('FCResNet.forward in training mode (teacher training) is '
+                                      'not part of the CUDA path yet; call .eval()')
+        layers, w_out, b_out = self._prepare()
+        L, dev, H = lib(), self._dev, self.hidden_dim
+        x = x.to(device=dev, dtype=torch.float32).contiguous()
+        if x.dim() != 2 or x.shape[1] != self.in_dim:
+            raise ValueError('expected [n, {}] poses, got {}'.format(self.in_dim, tuple(x.shape)))
+        n = x.shape[0]
+        out = torch.empty((n, self.out_dim), device=dev, dtype=torch.float32)
+        st = stream_ptr(dev)
+        m = min(n, _MAX_ROWS)
+        xb = torch.empty((m, self._cin), device=dev, dtype=torch.bfloat16)
+        h, z1, z2 = (torch.empty((m, H), device=dev, dtype=torch.bfloat16) for _ in range(3))
+
+        def linear(src, dst, rows, layer):
+            wt, scale, shift, cin = layer
+            L.call('vpd_conv2d_fwd', src, wt, dst, rows, 1, 1, cin, H, 1, 1, 0, scale, shift,
+                   None, 1, None, st)
+
+        for r0 in range(0, n, _MAX_ROWS):
+            rows = min(_MAX_ROWS, n - r0)
+            L.call('vpd_rows_to_bf16', x[r0:r0 + rows], xb, rows, self.in_dim, self._cin, st)
+            linear(xb, h, rows, layers[0])
+            for i in range(self.num_blocks):
+                linear(h, z1, rows, layers[1 + 2 * i])
+                linear(z1, z2, rows, layers[2 + 2 * i])
+                L.call('vpd_axpby_bf16', z2, 1.0, h, -1.0, z1, rows * H, st)     # x2 - x
+                h, z1 = z1, h
+            L.call('vpd_linear_rows_f32', h, w_out, b_out, out[r0:r0 + rows], rows, H,
+                   self.out_dim, st)
+        return out
+
+    __call__ = forward
+
+
+class Keypoint_EmbeddingModel:
+    """models/keypoint.py:14-35,38-160 - the embedding side."""
+
+    def __init__(self, encoder, decoders, device):
+        self.encoder = encoder
+        self.decoders = decoders
+        self.device = device
+        self.encoder.to(device)
+        if decoders:
+            raise NotImplementedError('3-D pose decoders are not part of the CUDA path yet')
+
+    def epoch(self, data_loaders, optimizer=None, scaler=None, progress_cb=None, weight_3d=1):
+        raise NotImplementedError('training the keypoint teacher is not part of the CUDA path yet '
+                                  '(DESIGN.md section 8)')
+
+    def _predict(self, pose, get_emb, decoder_target=None):
+        assert get_emb or decoder_target is not None, 'Nothing to predict'
+        if decoder_target is not None:
+            raise NotImplementedError('3-D pose decoders are not part of the CUDA path yet')
+        if not isinstance(pose, torch.Tensor):
+            pose = torch.FloatTensor(np.asarray(pose))
+        if len(pose.shape) == 2:
+            pose = pose.unsqueeze(0)
+        self.encoder.eval()
+        n = pose.shape[0]
+        emb = self.encoder(pose.reshape(n, -1))
+        return emb.cpu().numpy(), None
+
+    def embed(self, pose):
+        return self._predict(pose, get_emb=True)[0]
+
+    def predict3d(self, pose, decoder_target):
+        return self._predict(pose, get_emb=False, decoder_target=decoder_target)[1]
+
+    def embed_and_predict3d(self, pose, decoder_target):
+        return self._predict(pose, get_emb=True, decoder_target=decoder_target)
+
+
+def load_embedding_model(model_dir, model_epoch=None, device='cuda'):
+    """apply_vipe_model.py:133-162: config.json + `<name>.encoder.pt` -> (model, embed_bones)"""
+    with open(os.path.join(model_dir, 'config.json')) as fp:
+        params = json.load(fp)
+    embed_bones = params['embed_bones']
+    name = 'best_epoch' if model_epoch is None else 'epoch{:04d}'.format(model_epoch)
+    encoder = FCResNet((NUM_COCO_KEYPOINTS + NUM_COCO_BONES if embed_bones
+                        else NUM_COCO_KEYPOINTS) * 3,
+                       params['embedding_dim'], *params['encoder_arch'])
+    encoder.load_state_dict(torch.load(os.path.join(model_dir, name + '.encoder.pt'),
+                                       map_location='cpu'))
+    return Keypoint_EmbeddingModel(encoder, {}, device), embed_bones
+
+
+def mean_embs_by_frame(pred_embs, flip):
+    """apply_vipe_model.py:37-69: one entry per frame; with flip, rows [unflipped, flipped]"""
+    grouped = defaultdict(list)
+    for frame_num, emb, meta in pred_embs:
+        grouped[frame_num].append((emb, meta))
+    expected_shape = emb.shape
+
+    def get_mean(emb_and_metas):
+        embs, metas = zip(*emb_and_metas)
+        if len(embs) == 1:
+            e, meta = embs[0], metas[0]
+        else:
+            e = np.mean(embs, axis=0)
+            meta = {'kp_score': min(m['kp_score'] for m in metas), 'is_mean': True}
+        assert e.shape == expected_shape
+        return e, meta
+
+    result = []
+    for frame_num, emb_and_metas in grouped.items():
+        if flip:
+            e, mean_meta = get_mean([x for x in emb_and_metas if not x[1]['is_flip']])
+            e_flip, _ = get_mean([x for x in emb_and_metas if x[1]['is_flip']])
+            mean_emb = np.stack((e, e_flip))
+        else:
+            mean_emb, mean_meta = get_mean(emb_and_metas)
+        result.append((frame_num, mean_emb, mean_meta))
+    result.sort(key=lambda x: x[0])
+    return result
+
+
+def embed_video(model, frames, scores, is_flip, poses, flip=True, allow_many_per_frame=False):
+    """The body of apply_vipe_model.main's loop (:181-201) for one video's arrays (what its
+    `VideoDataset` yields): -> the list stored in `<video>.emb.pkl`. The whole video is
+    embedded in one call instead of chunks of 250."""
+    frames, scores, is_flip = np.asarray(frames), np.asarray(scores), np.asarray(is_flip)
+    if len(frames) == 0:
+        return []
+    batch_embs = model.embed(poses)
+    embs = [(frames[j].item(), batch_embs[j, :],
+             {'kp_score': scores[j].item(), 'is_mean': False, 'is_flip': is_flip[j].item()})
+            for j in range(batch_embs.shape[0])]
+    if not allow_many_per_frame:
+        embs = mean_embs_by_frame(embs, flip)
+    return embs
+
+
+def write_embs(out_dir, video_name, embs):
+    """apply_vipe_model.py:171-178 + util/io.py:35-37 (store_pickle)"""
+    if embs and video_name is not None and out_dir is not None:
+        os.makedirs(out_dir, exist_ok=True)
+        with open(os.path.join(out_dir, '{}.emb.pkl'.format(video_name)), 'wb') as fp:
+            pickle.dump(embs, fp)
