@@ -93,11 +93,11 @@ class FusedSGD:
         pass    # every train step overwrites the whole gradient arena
 
 
+from . import dp
+
+
 def _dist():
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        return dist
-    return None
+    return dp.active()
 
 
 class ModelTrainer:
@@ -130,9 +130,7 @@ class ModelTrainer:
         ev.record(cur)
         self._comm_stream.wait_event(ev)
         with torch.cuda.stream(self._comm_stream):
-            # reduction='sum' loss => gradients add across ranks (SUM, not mean)
-            work = dist.all_reduce(enc._grads[offset:offset + count], op=dist.ReduceOp.SUM,
-                                   async_op=True)
+            work = dp.sum_bucket(enc._grads, offset, count, async_op=True)
         self._pending.append(work)
 
     def _hook(self, net):
@@ -193,8 +191,7 @@ class ModelTrainer:
             self._pending = []
             torch.cuda.current_stream(self.encoder._dev).wait_stream(self._comm_stream)
         else:
-            # reduction='sum' loss => gradients add across ranks (SUM, not mean)
-            dist.all_reduce(self.encoder._grads, op=dist.ReduceOp.SUM)
+            dp.sum_gradients(self.encoder._grads)
 
     def _stage(self, batch, slot):
         """Start the host->device copies of a batch on the copy stream, into one of
@@ -259,14 +256,9 @@ class ModelTrainer:
                 progress_cb(n)
         if epoch_n == 0:
             return float('nan')
-        total = self._loss.clone()
-        dist = _dist()
-        if dist is not None and train:
-            cnt = torch.tensor([float(epoch_n)], device=enc._dev, dtype=torch.float64)
-            dist.all_reduce(total, op=dist.ReduceOp.SUM)
-            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-            return total.item() / cnt.item()
-        return total.item() / epoch_n
+        if train:
+            return dp.epoch_loss(self._loss, epoch_n)
+        return self._loss.item() / epoch_n
 
     def get_optimizer(self, learning_rate):
         return FusedAdamW(self.encoder, learning_rate), None
