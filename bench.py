@@ -11,8 +11,10 @@ backward -> [NCCL all-reduce SUM of the gradient arena when N > 1] -> fused Adam
   value   device-timed frames/s over all ranks (CUDA events, max over ranks), inputs
           already in HBM;
   e2e     the same metric through the reference-facing call `ModelTrainer.epoch`
-          fed with HOST (pinned) fp32 batches, H2D copies and the loss read-back
-          inside the timed region;
+          fed with HOST (pinned) batches of raw uint8 crops (what the path's first stage,
+          K1, consumes), H2D copies, K1 and the loss read-back inside the timed region;
+          e2e.fp32_batches = the same with the fp32 {'img','emb'} batches the reference's
+          DataLoader yields (4x the bytes over PCIe);
   roofline  the dominant kernel family, measured live with CUDA events around every
           launch in a separate profiled pass of the same step;
   cpu_baseline  the oracle port of the reference's fp32 PyTorch path on the host cores
@@ -348,40 +350,64 @@ def run_native(args, rank, world, local_rank):
                     'how': 'CUDA events around every launch on the launching stream, '
                            '{} profiled steps after the timed region'.format(nprof)}
 
-    # ---- e2e through ModelTrainer.epoch with pinned host fp32 batches -----------------
+    # ---- e2e through ModelTrainer.epoch with pinned HOST batches ------------------------
+    # (a) raw uint8 crops + flip bits + both teacher rows: what the path's first stage (K1)
+    #     consumes; normalise / stack / flip / row select run on the device  -> `e2e`
+    # (b) the reference loader's own fp32 {'img', 'emb'} batches (4x the bytes) -> e2e.fp32_batches
     e2e = None
     if not args.no_e2e:
+        from vpd_b200.assemble import assemble_batch
         nb = 3
-        host = []
+        host_u8, host_f32 = [], []
         for j in range(nb):
+            idx = idx_all[j].long()
+            host_u8.append({'rgb_u8': rgb[idx].cpu().pin_memory(),
+                            'flow_u8': flow[idx].cpu().pin_memory(),
+                            'flip': flip_all[j].cpu().pin_memory(),
+                            'teacher': teach[idx].cpu().pin_memory(),
+                            'rgb_mean_std': synth.FS_MEAN_STD})
             b = {'img': torch.empty((B, 5, IMG, IMG), dtype=torch.float32).pin_memory(),
                  'emb': torch.empty((B, 2 * EMB), dtype=torch.float32).pin_memory()}
-            from vpd_b200.assemble import assemble_batch
             d = assemble_batch(rgb, flow, synth.FS_MEAN_STD, flip=flip_all[j], teacher=teach,
                                index=idx_all[j])
             b['img'].copy_(d['img'])
             b['emb'].copy_(d['emb'])
-            host.append(b)
+            host_f32.append(b)
         torch.cuda.synchronize()
         e2e_steps = max(4, min(args.steps, 20))
-        trainer.epoch([host[j % nb] for j in range(3)], optimizer=opt)      # warm-up
-        barrier()
-        t0 = time.perf_counter()
-        ev0.record()
-        loss = trainer.epoch([host[j % nb] for j in range(e2e_steps)], optimizer=opt)
-        ev1.record()
-        barrier()
-        wall = time.perf_counter() - t0
-        ms_e = max(ev0.elapsed_time(ev1), wall * 1e3)   # includes the loss read-back
-        if dist is not None:
-            t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e = t.item()
-        e2e = {'value': B * world * e2e_steps / (ms_e / 1e3), 'unit': UNIT,
-               'h2d_bytes_per_step': B * (5 * IMG * IMG + 2 * EMB) * 4,
+
+        def timed_epoch(host):
+            trainer.epoch([host[j % nb] for j in range(3)], optimizer=opt)      # warm-up
+            barrier()
+            t0 = time.perf_counter()
+            ev0.record()
+            loss = trainer.epoch([host[j % nb] for j in range(e2e_steps)], optimizer=opt)
+            ev1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+            ms_e = max(ev0.elapsed_time(ev1), wall * 1e3)   # includes the loss read-back
+            if dist is not None:
+                t = torch.tensor([ms_e], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_e = t.item()
+            return B * world * e2e_steps / (ms_e / 1e3), loss
+
+        fps_f32, loss_f32 = timed_epoch(host_f32)
+        fps_u8, loss_u8 = timed_epoch(host_u8)
+        u8_bytes = sum(v.numel() * v.element_size() for k, v in host_u8[0].items()
+                       if isinstance(v, torch.Tensor))
+        e2e = {'value': fps_u8, 'unit': UNIT, 'h2d_bytes_per_step': u8_bytes,
                'd2h_bytes_per_step': 8, 'steps': e2e_steps,
-               'api': 'ModelTrainer.epoch(loader of pinned host fp32 batches, optimizer)',
-               'loss_per_frame': loss}
+               'api': "ModelTrainer.epoch(loader of pinned host batches {'rgb_u8','flow_u8',"
+                      "'flip','teacher'}, optimizer): H2D copy, K1 assembly, train step, "
+                      "AdamW, loss read-back",
+               'loss_per_frame': loss_u8,
+               'fp32_batches': {'value': fps_f32, 'unit': UNIT,
+                                'h2d_bytes_per_step': B * (5 * IMG * IMG + 2 * EMB) * 4,
+                                'api': "ModelTrainer.epoch(loader of pinned host fp32 "
+                                       "{'img','emb'} batches as the reference's DataLoader "
+                                       "yields them, optimizer)",
+                                'loss_per_frame': loss_f32}}
 
     # ---- apply path (apply_vpd_model.py): K1 [orig, flipped] -> eval-mode encoder ----
     apply_res = None

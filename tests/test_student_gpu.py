@@ -274,6 +274,47 @@ def test_fused_stem_path_equals_fp32_batch_path():
     assert (diff > 1e-4).float().mean().item() < 0.15
 
 
+def test_epoch_accepts_raw_uint8_host_batches():
+    """ModelTrainer.epoch fed with pinned HOST batches of raw uint8 crops (H2D copy, K1 on the
+    device) == the same frames as the reference loader's fp32 {'img','emb'} batches."""
+    from vpd_b200 import ModelTrainer
+    from vpd_b200.assemble import assemble_batch
+    B = 16
+    rgb, flow = synth.crops(2 * B, seed=71)
+    teach = synth.teacher(2 * B, seed=72)
+    fl = synth.flips(2 * B, seed=73)
+    raw = [{'rgb_u8': rgb[i:i + B].pin_memory(), 'flow_u8': flow[i:i + B].pin_memory(),
+            'flip': fl[i:i + B].pin_memory(), 'teacher': teach[i:i + B].pin_memory(),
+            'rgb_mean_std': synth.FS_MEAN_STD} for i in (0, B)]
+    f32 = []
+    for i in (0, B):
+        d = assemble_batch(rgb[i:i + B].to(dev()), flow[i:i + B].to(dev()), synth.FS_MEAN_STD,
+                           flip=fl[i:i + B].to(dev()), teacher=teach[i:i + B].to(dev()))
+        f32.append({'img': d['img'].cpu().pin_memory(), 'emb': d['emb'].cpu().pin_memory()})
+    m = _model(1)
+    tr = ModelTrainer(m, True)
+    # eval mode (no optimizer): running statistics, deterministic -> same loss
+    a = tr.epoch(f32)
+    b = tr.epoch(raw)
+    assert abs(a - b) <= 1e-5 * abs(a), (a, b)
+    # 'emb' given instead of both teacher rows; trainer-level mean/std
+    tr.rgb_mean_std = synth.FS_MEAN_STD
+    raw2 = [{'rgb_u8': r['rgb_u8'], 'flow_u8': r['flow_u8'], 'flip': r['flip'], 'emb': f['emb']}
+            for r, f in zip(raw, f32)]
+    c = tr.epoch(raw2)
+    assert abs(a - c) <= 1e-5 * abs(a), (a, c)
+    # training through the same entry: finite loss close to the fp32-batch run's
+    opt, _ = tr.get_optimizer(5e-4)
+    lt = tr.epoch(raw, optimizer=opt)
+    m2 = _model(1)
+    tr2 = ModelTrainer(m2, True)
+    opt2, _ = tr2.get_optimizer(5e-4)
+    lt2 = tr2.epoch(f32, optimizer=opt2)
+    assert np.isfinite(lt) and abs(lt - lt2) <= 2e-2 * abs(lt2), (lt, lt2)
+    with pytest.raises(AssertionError):
+        tr.epoch([{'rgb_u8': raw[0]['rgb_u8'], 'flip': raw[0]['flip'], 'emb': f32[0]['emb']}])
+
+
 def test_apply_corpus_extraction_pickles(tmp_path):
     """apply_vpd_model.py:152-178: per-video sorted (frame, float32 [2,D], {}) pickles whose
     embeddings match the oracle run on the reference-layout batches."""

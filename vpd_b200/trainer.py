@@ -193,11 +193,81 @@ class ModelTrainer:
         else:
             dp.sum_gradients(self.encoder._grads)
 
+    def _run_u8(self, raw, tgt, train):
+        """One batch of raw uint8 crops (see `_stage`): K1 assembly straight into the bound
+        net's input buffer, then the native step."""
+        from .assemble import assemble_stem
+        enc = self.encoder
+        rgb, flow, flip, teacher = raw['rgb_u8'], raw.get('flow_u8'), raw.get('flip'), raw.get('teacher')
+        n, H, W, _ = rgb.shape
+        if (flow is not None) != bool(enc.use_flow):
+            raise AssertionError('Wrong number of channels for RGB' + (' + flow' if enc.use_flow else ''))
+        ms = raw.get('rgb_mean_std', getattr(self, 'rgb_mean_std', None))
+        if ms is None:
+            raise ValueError("uint8 batches need 'rgb_mean_std' (in the batch or on the trainer)")
+        expect = 2 * enc.emb_dim if self.motion else enc.emb_dim
+        with torch.cuda.device(enc._dev):
+            if train:
+                enc._ensure_grads()
+            net = enc._native(H, W, n)
+            stem = lib().call('vpd_net_stem_input', net.handle)
+            if teacher is not None:
+                if teacher.shape[-1] != expect:
+                    raise ValueError('target dim {} != {}'.format(teacher.shape[-1], expect))
+                if tgt is None or tuple(tgt.shape) != (n, expect):
+                    tgt = torch.empty((n, expect), device=enc._dev, dtype=torch.float32)
+                assemble_stem(stem, rgb, flow, ms, flip=flip, teacher=teacher, tgt=tgt)
+            else:
+                if tgt.shape[1] != expect:
+                    raise ValueError('target dim {} != {}'.format(tgt.shape[1], expect))
+                assemble_stem(stem, rgb, flow, ms, flip=flip)
+            self._overlapped = self._hook(net) if train else False
+            if train:
+                lib().call('vpd_net_train_step', net.handle, None, stem, tgt, n, self._loss,
+                           stream_ptr(enc._dev))
+            else:
+                lib().call('vpd_net_eval_loss', net.handle, None, stem, tgt, n, self._loss, None,
+                           stream_ptr(enc._dev))
+        return n
+
+    def _stage_u8(self, batch, slot):
+        """Raw batch {'rgb_u8': uint8 [B,H,W,3], 'flow_u8': uint8 [B,H,W,>=2] (flow models),
+        'flip': uint8 [B] (optional), and either 'emb': fp32 [B,T] (teacher row already chosen)
+        or 'teacher': fp32 [B,2,T] (row = flip bit, chosen on the device),
+        'rgb_mean_std': ((m,m,m),(s,s,s)) (or set `trainer.rgb_mean_std`)}: 4x fewer bytes over
+        PCIe than the fp32 batch; normalisation / stacking / flip run in the K1 kernel."""
+        dev = self.encoder._dev
+        names = [k for k in ('rgb_u8', 'flow_u8', 'flip', 'emb', 'teacher') if batch.get(k) is not None]
+        key = ('u8',) + tuple((k, tuple(batch[k].shape)) for k in names)
+        ring = getattr(self, '_ring', None)
+        if ring is None or ring['key'] != key:
+            ring = {'key': key, 'free': [None, None],
+                    'buf': [{k: torch.empty(batch[k].shape, device=dev, dtype=batch[k].dtype)
+                             for k in names} for _ in range(2)]}
+            self._ring = ring
+        extra = {k: batch[k] for k in ('rgb_mean_std',) if k in batch}
+        if all(batch[k].device == dev for k in names):
+            raw = {k: batch[k] for k in names}
+            raw.update(extra)
+            return raw, raw.get('emb'), None, None
+        with torch.cuda.stream(self._copy_stream):
+            if ring['free'][slot] is not None:
+                self._copy_stream.wait_event(ring['free'][slot])
+            for k in names:
+                ring['buf'][slot][k].copy_(batch[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        raw = dict(ring['buf'][slot])
+        raw.update(extra)
+        return raw, raw.get('emb'), ev, slot
+
     def _stage(self, batch, slot):
         """Start the host->device copies of a batch on the copy stream, into one of
         two persistent device staging buffers (no per-step allocation)."""
         if batch is None:
             return None
+        if 'rgb_u8' in batch:
+            return self._stage_u8(batch, slot)
         dev = self.encoder._dev
         img_h, emb_h = batch['img'], batch['emb']
         key = (tuple(img_h.shape), tuple(emb_h.shape))
@@ -235,14 +305,17 @@ class ModelTrainer:
             nxt = self._stage(next(it, None), step_i % 2)   # overlap next copy with this step
             if ev is not None:
                 cur_stream.wait_event(ev)
-            img = img.contiguous()
-            emb = emb.contiguous()
-            n = img.shape[0]
-            enc._check_channels(img)
-            expect = 2 * enc.emb_dim if self.motion else enc.emb_dim
-            if emb.shape[1] != expect:
-                raise ValueError('target dim {} != {}'.format(emb.shape[1], expect))
-            self._run(img, emb, n, train)
+            if isinstance(img, dict):                       # raw uint8 crops: K1 on the device
+                n = self._run_u8(img, emb, train)
+            else:
+                img = img.contiguous()
+                emb = emb.contiguous()
+                n = img.shape[0]
+                enc._check_channels(img)
+                expect = 2 * enc.emb_dim if self.motion else enc.emb_dim
+                if emb.shape[1] != expect:
+                    raise ValueError('target dim {} != {}'.format(emb.shape[1], expect))
+                self._run(img, emb, n, train)
             if slot is not None:
                 done = torch.cuda.Event()
                 done.record(cur_stream)
