@@ -218,6 +218,44 @@ VPD_API int vpd_bn_fold(const float* gamma, const float* beta, const float* runn
 VPD_API int vpd_linear_rows_f32(const void* x_bf16, const float* w, const float* bias, float* out,
                         int64_t M, int K, int D, void* stream);
 
+/* Training side of the same encoder (models/module.py:159-177 in train mode,
+ * models/keypoint.py:38-126). Rows are bf16 [M][C], C % 8 == 0, C <= 2048.
+ *   vpd_dropout_mask   keep[i] = 1 with probability 1 - p_drop (Philox4x32-10, keyed by seed
+ *                      and stream_id); n % 4 == 0
+ *   vpd_bn1d_fwd       out = keep * relu(BatchNorm1d_train(a)) / (1 - p_drop) [- res].
+ *                      `a` is the Linear output WITHOUT its bias (a bias in front of a batch-
+ *                      statistics BN cancels; lin_bias only enters running_mean); stats = fp64
+ *                      [2][C] column sums / sums of squares of `a` as vpd_conv2d_fwd
+ *                      accumulates them; running stats (momentum .1, unbiased variance) and
+ *                      num_batches are updated; save_mean / save_rstd for the backward
+ *   vpd_bn1d_bwd       da = BN backward of g = dz * keep / (1-p) * 1[bn(a) > 0];
+ *                      dgamma += sum g*xhat, dbeta += sum g (ACCUMULATED: the three encoder
+ *                      passes of a step share weights); sums = fp64 [2][C] scratch
+ *   vpd_relu_mask_bf16 out = d * 1[z > 0]
+ *   vpd_colsum_bf16    out[c] += sum_r x[r][c]   (Linear bias gradients)
+ *   vpd_vipe_loss      the loss head: contra = ||e1-e2|| + valid * max(0, 1 - ||e1-en||)
+ *                      (F.hinge_embedding_loss, targets +1 / -1), loss = contra + w3d *
+ *                      (SSE(pred1, true3d) + SSE(pred2, true3d)); sums[0] += contra,
+ *                      sums[1] += loss; gradients times gscale (1 / batch size): de* fp32
+ *                      [n][D], dpred* bf16 [n][Tpad] (pad columns zero). e2 / en / true3d /
+ *                      pred2 may be NULL (datasets without those entries). */
+VPD_API int vpd_dropout_mask(uint8_t* keep, int64_t n, float p_drop, uint64_t seed, int stream_id,
+                     void* stream);
+VPD_API int vpd_bn1d_fwd(const void* a, const double* stats, const float* gamma, const float* beta,
+                 const float* lin_bias, float* running_mean, float* running_var,
+                 int64_t* num_batches, float* save_mean, float* save_rstd, const uint8_t* keep,
+                 float p_drop, const void* res, void* out, int64_t M, int C, void* stream);
+VPD_API int vpd_bn1d_bwd(const void* dz, const void* a, const uint8_t* keep, float p_drop,
+                 const float* gamma, const float* beta, const float* save_mean,
+                 const float* save_rstd, double* sums, void* da, float* dgamma, float* dbeta,
+                 int64_t M, int C, void* stream);
+VPD_API int vpd_relu_mask_bf16(const void* d, const void* z, void* out, int64_t n, void* stream);
+VPD_API int vpd_colsum_bf16(const void* x, float* out, int64_t M, int C, void* stream);
+VPD_API int vpd_vipe_loss(const float* e1, const float* e2, const float* en, const float* valid,
+                  const void* pred1, const void* pred2, const float* true3d, float* de1,
+                  float* de2, float* den, void* dpred1, void* dpred2, double* sums, int64_t n,
+                  int D, int T, int Tpad, float w3d, float gscale, void* stream);
+
 /* ---- the student network ---------------------------------------------------------
  * Replaces RGBF_EmbeddingModel.forward/embed (models/rgb.py:68-86), the body of
  * ModelTrainer.epoch (train_vpd_model.py:67-98: forward, FCNet decoder,

@@ -327,11 +327,88 @@ def gen_keypoint(ref):
     print('keypoint.npz written')
 
 
+def gen_keypoint_train(ref):
+    """VIPE* teacher training: two optimizer steps of the reference's
+    Keypoint_EmbeddingModel.epoch (two datasets zipped: one with negatives + 3-D targets, one
+    with pose pairs only) - losses, first-step gradients, BatchNorm buffers, parameters after
+    the steps; the dropout masks the reference drew (replayed, checked through the oracle)."""
+    import types
+    from oracle import keypoint_train_ref as T
+    sys.modules.setdefault('matplotlib', types.ModuleType('matplotlib'))
+    from models.module import FCResNet, FCPoseDecoder
+    from models.keypoint import Keypoint_EmbeddingModel
+    H, blocks, n1, n2, p, lr = 128, 2, 136, 72, 0.2, 1e-3
+    torch.manual_seed(31)
+    enc = FCResNet(39, 32, blocks, H, dropout=p)
+    dec = FCPoseDecoder(32, [128, 128], [('h36m', 140)], dropout=0)
+    out = {'enc_init_sha256': np.array(sd_hash(enc.state_dict())),
+           'dec_init_sha256': np.array(sd_hash(dec.state_dict()))}
+    model = Keypoint_EmbeddingModel(enc, {'3d': dec}, 'cpu')
+    params = list(enc.parameters()) + list(dec.parameters())
+    names = (['enc.' + k for k, _ in enc.named_parameters()]
+             + ['dec.' + k for k, _ in dec.named_parameters()])
+    real = torch.optim.AdamW(params, lr=lr)
+    captured = []
+
+    class Opt:                                   # records the gradients the reference computed
+        def step(self):
+            captured.append({k: v.grad.clone() for k, v in zip(names, params)})
+            real.step()
+
+        def zero_grad(self):
+            real.zero_grad()
+
+    fcn_keys = ['fcn.layers.0', 'fcn.layers.2']
+    for step_i in range(2):
+        b1 = T.synth_batch(n1, 40 + step_i)
+        b2 = T.synth_batch(n2, 50 + step_i, with_neg=False, with_3d=False)
+        enc_sd0 = {k: v.clone() for k, v in enc.state_dict().items()}
+        dec_sd0 = {k: v.clone() for k, v in dec.state_dict().items()}
+        torch.manual_seed(60 + step_i)
+        contra, loss, per = model.epoch([('h36m', [b1]), ('pair', [b2])], optimizer=Opt(),
+                                        weight_3d=1)
+        # replay the masks the reference drew and check the restatement against it
+        torch.manual_seed(60 + step_i)
+        masks = [T.replay_masks(n1, H, blocks, 3, p), T.replay_masks(n2, H, blocks, 2, p)]
+        res, grads, bufs = T.zipped_step(enc_sd0, dec_sd0, fcn_keys, [('h36m', b1), ('pair', b2)],
+                                         masks, p, blocks)
+        tot = sum(v[1] for v in res.values()) / (n1 + n2)
+        assert abs(tot - loss) <= 1e-5 * abs(loss), (tot, loss)
+        for k, g in captured[step_i].items():
+            assert torch.allclose(g, grads[k], rtol=1e-4, atol=1e-7), k
+        for k, v in bufs.items():
+            assert torch.allclose(v.float(), enc.state_dict()[k].float(), rtol=1e-5, atol=1e-6), k
+        out['step{}_contra'.format(step_i)] = np.array(contra)
+        out['step{}_loss'.format(step_i)] = np.array(loss)
+        out['step{}_loss_h36m'.format(step_i)] = np.array(per['h36m'])
+        out['step{}_loss_pair'.format(step_i)] = np.array(per['pair'])
+        for di, m in enumerate(masks):
+            packed = np.packbits(np.stack([torch.stack(q).numpy() for q in m]).astype(np.uint8))
+            out['step{}_masks{}'.format(step_i, di)] = packed
+    for k in ('enc.layers.0.weight', 'enc.layers.0.bias', 'enc.layers.2.block.0.weight',
+              'enc.layers.2.block.1.weight', 'enc.layers.2.block.1.bias',
+              'enc.layers.3.block.4.weight', 'enc.layers.3.block.5.weight', 'enc.layers.4.weight',
+              'enc.layers.4.bias', 'dec.fcn.layers.0.weight', 'dec.fcn.layers.2.bias',
+              'dec.fc_h36m.weight', 'dec.fc_h36m.bias'):
+        out['grad0/' + k] = captured[0][k].numpy()
+    for k in ('layers.2.block.1.running_mean', 'layers.2.block.1.running_var',
+              'layers.3.block.5.running_mean', 'layers.3.block.5.running_var',
+              'layers.2.block.1.num_batches_tracked'):
+        out['final/' + k] = enc.state_dict()[k].numpy()
+    out['final/enc.layers.4.weight'] = enc.state_dict()['layers.4.weight'].numpy()
+    out['final/dec.fc_h36m.bias'] = dec.state_dict()['fc_h36m.bias'].numpy()
+    # evaluation epoch after the two steps (running statistics, no dropout)
+    contra, loss, per = model.epoch([('h36m', [T.synth_batch(n1, 70)])])
+    out['eval_contra'], out['eval_loss'] = np.array(contra), np.array(loss)
+    np.savez_compressed(os.path.join(GOLD, 'keypoint_train.npz'), **out)
+    print('keypoint_train.npz written')
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     ref = ref_shim.load()
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ['assembly', 'student', 'targets', 'augment', 'keypoint']
+    which = sys.argv[1:] or ['assembly', 'student', 'targets', 'augment', 'keypoint', 'keypoint_train']
     if 'assembly' in which:
         gen_assembly(ref)
     if 'student' in which:
@@ -342,6 +419,8 @@ def main():
         gen_augment(ref)
     if 'keypoint' in which:
         gen_keypoint(ref)
+    if 'keypoint_train' in which:
+        gen_keypoint_train(ref)
     with open(os.path.join(GOLD, 'README.md'), 'w') as fp:
         fp.write('Golden vectors produced by `python -m oracle.gen_golden` from the unmodified\n'
                  'reference at /root/reference (torch {}, CPU fp32). Inputs are regenerated\n'

@@ -103,6 +103,40 @@ int vpd_linear_rows_f32(const void* x_bf16, const float* w, const float* bias, f
   return linear_rows_f32((const bf16*)x_bf16, w, bias, out, M, K, D, (cudaStream_t)stream);
 }
 
+int vpd_dropout_mask(uint8_t* keep, int64_t n, float p_drop, uint64_t seed, int stream_id,
+                     void* stream) {
+  return dropout_mask(keep, n, p_drop, seed, (unsigned int)stream_id, (cudaStream_t)stream);
+}
+int vpd_bn1d_fwd(const void* a, const double* stats, const float* gamma, const float* beta,
+                 const float* lin_bias, float* running_mean, float* running_var,
+                 int64_t* num_batches, float* save_mean, float* save_rstd, const uint8_t* keep,
+                 float p_drop, const void* res, void* out, int64_t M, int C, void* stream) {
+  return bn1d_fwd((const bf16*)a, stats, gamma, beta, lin_bias, running_mean, running_var,
+                  (long long*)num_batches, save_mean, save_rstd, keep, p_drop, (const bf16*)res,
+                  (bf16*)out, M, C, (cudaStream_t)stream);
+}
+int vpd_bn1d_bwd(const void* dz, const void* a, const uint8_t* keep, float p_drop,
+                 const float* gamma, const float* beta, const float* save_mean,
+                 const float* save_rstd, double* sums, void* da, float* dgamma, float* dbeta,
+                 int64_t M, int C, void* stream) {
+  return bn1d_bwd((const bf16*)dz, (const bf16*)a, keep, p_drop, gamma, beta, save_mean, save_rstd,
+                  sums, (bf16*)da, dgamma, dbeta, M, C, (cudaStream_t)stream);
+}
+int vpd_relu_mask_bf16(const void* d, const void* z, void* out, int64_t n, void* stream) {
+  return relu_mask_bf16((const bf16*)d, (const bf16*)z, (bf16*)out, n, (cudaStream_t)stream);
+}
+int vpd_colsum_bf16(const void* x, float* out, int64_t M, int C, void* stream) {
+  return colsum_bf16((const bf16*)x, out, M, C, (cudaStream_t)stream);
+}
+int vpd_vipe_loss(const float* e1, const float* e2, const float* en, const float* valid,
+                  const void* pred1, const void* pred2, const float* true3d, float* de1,
+                  float* de2, float* den, void* dpred1, void* dpred2, double* sums, int64_t n,
+                  int D, int T, int Tpad, float w3d, float gscale, void* stream) {
+  return vipe_loss(e1, e2, en, valid, (const bf16*)pred1, (const bf16*)pred2, true3d, de1, de2,
+                   den, (bf16*)dpred1, (bf16*)dpred2, sums, n, D, T, Tpad, w3d, gscale,
+                   (cudaStream_t)stream);
+}
+
 int vpd_nchw_to_stem(const float* x, void* out_stem_bf16, int B, int C, int H, int W,
                      void* stream) {
   return nchw_to_pad8(x, (bf16*)out_stem_bf16, B, C, H, W, (cudaStream_t)stream);

@@ -122,6 +122,334 @@ linear_rows_f32_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Training-side pieces of the keypoint encoder (models/module.py:159-177 in train mode,
+// models/keypoint.py:38-126): BatchNorm1d with batch statistics + ReLU + Dropout (+ `x2 - x`)
+// forward and backward over bf16 rows [M][C], the ReLU mask, column sums (Linear bias
+// gradients) and the hinge + MSE loss head. C % 8 == 0; a thread owns 8 adjacent columns
+// (one 16-byte vector) of a set of rows.
+
+// keep[i] = 1 with probability 1 - p_drop (counter-based: Philox4x32-10 keyed by the seed,
+// one call per 4 elements)
+__global__ void __launch_bounds__(256)
+dropout_mask_kernel(uint8_t* __restrict__ keep, long long n4, float p_drop,
+                    unsigned long long seed, unsigned int stream_id) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+       i += (long long)gridDim.x * blockDim.x) {
+    unsigned int c0 = (unsigned int)i, c1 = (unsigned int)(i >> 32), c2 = stream_id, c3 = 0x5eedu;
+    unsigned int k0 = (unsigned int)seed, k1 = (unsigned int)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+      const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+      c0 = hi1 ^ c1 ^ k0;
+      c1 = lo1;
+      c2 = hi0 ^ c3 ^ k1;
+      c3 = lo0;
+      k0 += 0x9E3779B9u;
+      k1 += 0xBB67AE85u;
+    }
+    const unsigned int w[4] = {c0, c1, c2, c3};
+    unsigned int out = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float u = (static_cast<float>(w[j] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      out |= (u >= p_drop ? 1u : 0u) << (8 * j);
+    }
+    reinterpret_cast<unsigned int*>(keep)[i] = out;
+  }
+}
+
+struct Bn1dParams {
+  const __nv_bfloat16* a;      // [M][C] pre-BN Linear output WITHOUT its bias
+  const double* stats;         // [2][C] sum, sum of squares of `a` over the M rows
+  const float* gamma;
+  const float* beta;
+  const float* lin_bias;       // the Linear's bias: only shifts the batch mean (running_mean)
+  float* running_mean;
+  float* running_var;
+  long long* num_batches;
+  float* save_mean;            // [C] batch mean of `a` (bias excluded)
+  float* save_rstd;            // [C]
+  const uint8_t* keep;         // [M][C] dropout keep mask or null
+  float keep_scale;            // 1 / (1 - p)
+  const __nv_bfloat16* res;    // [M][C] subtracted from the result (`x2 - x`) or null
+  __nv_bfloat16* out;          // [M][C]
+  long long M;
+  int C;
+  float eps, momentum;
+};
+
+__global__ void __launch_bounds__(256)
+bn1d_fwd_kernel(const Bn1dParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int groups = p.C >> 3;                    // host: groups <= 256
+  const int rstep = 256 / groups;                 // rows per CTA pass; threads beyond are idle
+  const int gg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  if (rl < rstep) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = gg * 8 + j;
+      const double mean = p.stats[c] / static_cast<double>(p.M);
+      double var = p.stats[p.C + c] / static_cast<double>(p.M) - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+      sc[j] = p.gamma[c] * rstd;
+      sh[j] = p.beta[c] - static_cast<float>(mean) * sc[j];
+      if (blockIdx.x == 0 && rl == 0) {
+        p.save_mean[c] = static_cast<float>(mean);
+        p.save_rstd[c] = rstd;
+        const float bias = p.lin_bias ? p.lin_bias[c] : 0.f;
+        const double unbiased = p.M > 1 ? var * static_cast<double>(p.M) / static_cast<double>(p.M - 1) : var;
+        p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (static_cast<float>(mean) + bias);
+        p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * static_cast<float>(unbiased);
+      }
+    }
+    const long long r0 = (long long)blockIdx.x * rstep + rl;
+    for (long long r = r0; r < p.M; r += (long long)gridDim.x * rstep) {
+      const size_t off = (size_t)r * p.C + gg * 8;
+      const uint4 va = ldg_nc_v4(p.a + off);
+      float v[8] = {bf16_lo(va.x), bf16_hi(va.x), bf16_lo(va.y), bf16_hi(va.y),
+                    bf16_lo(va.z), bf16_hi(va.z), bf16_lo(va.w), bf16_hi(va.w)};
+      unsigned long long kp = 0x0101010101010101ull;
+      if (p.keep) kp = *reinterpret_cast<const unsigned long long*>(p.keep + off);
+      float rr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p.res) {
+        const uint4 vr = ldg_nc_v4(p.res + off);
+        rr[0] = bf16_lo(vr.x); rr[1] = bf16_hi(vr.x); rr[2] = bf16_lo(vr.y); rr[3] = bf16_hi(vr.y);
+        rr[4] = bf16_lo(vr.z); rr[5] = bf16_hi(vr.z); rr[6] = bf16_lo(vr.w); rr[7] = bf16_hi(vr.w);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float u = fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f);
+        u = ((kp >> (8 * j)) & 0xff) ? u * p.keep_scale : 0.f;
+        v[j] = u - rr[j];
+      }
+      stg_v4(p.out + off, make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                     pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && p.num_batches) *p.num_batches += 1;
+}
+
+struct Bn1dBwdParams {
+  const __nv_bfloat16* dz;     // [M][C] gradient of the block output path (before `- x`)
+  const __nv_bfloat16* a;      // [M][C] saved pre-BN values
+  const uint8_t* keep;         // or null
+  float keep_scale;
+  const float* gamma;
+  const float* beta;
+  const float* save_mean;
+  const float* save_rstd;
+  double* sums;                // [2][C] scratch: sum g, sum g * xhat (zeroed by the caller)
+  __nv_bfloat16* da;           // [M][C]
+  float* dgamma;               // += (weights are shared by the three encoder passes)
+  float* dbeta;                // +=
+  long long M;
+  int C;
+};
+
+// g = dz * keep * keep_scale * 1[gamma * xhat + beta > 0]
+template <bool kApply>
+__global__ void __launch_bounds__(256)
+bn1d_bwd_kernel(const Bn1dBwdParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int groups = p.C >> 3;
+  const int rstep = 256 / groups;
+  const int gg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  if (rl < rstep) {
+    float mean[8], rstd[8], ga[8], be[8], k1[8], k2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = gg * 8 + j;
+      mean[j] = p.save_mean[c];
+      rstd[j] = p.save_rstd[c];
+      ga[j] = p.gamma[c];
+      be[j] = p.beta[c];
+      k1[j] = kApply ? static_cast<float>(p.sums[c] / static_cast<double>(p.M)) : 0.f;
+      k2[j] = kApply ? static_cast<float>(p.sums[p.C + c] / static_cast<double>(p.M)) : 0.f;
+    }
+    float sg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sgx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long r0 = (long long)blockIdx.x * rstep + rl;
+    for (long long r = r0; r < p.M; r += (long long)gridDim.x * rstep) {
+      const size_t off = (size_t)r * p.C + gg * 8;
+      const uint4 vd = ldg_nc_v4(p.dz + off), va = ldg_nc_v4(p.a + off);
+      const float d[8] = {bf16_lo(vd.x), bf16_hi(vd.x), bf16_lo(vd.y), bf16_hi(vd.y),
+                          bf16_lo(vd.z), bf16_hi(vd.z), bf16_lo(vd.w), bf16_hi(vd.w)};
+      const float av[8] = {bf16_lo(va.x), bf16_hi(va.x), bf16_lo(va.y), bf16_hi(va.y),
+                           bf16_lo(va.z), bf16_hi(va.z), bf16_lo(va.w), bf16_hi(va.w)};
+      unsigned long long kp = 0x0101010101010101ull;
+      if (p.keep) kp = *reinterpret_cast<const unsigned long long*>(p.keep + off);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sc = ga[j] * rstd[j];
+        const float pre = fmaf(av[j], sc, be[j] - mean[j] * sc);   // same expression as forward
+        const float xh = (av[j] - mean[j]) * rstd[j];
+        float gr = (pre > 0.f && ((kp >> (8 * j)) & 0xff)) ? d[j] * p.keep_scale : 0.f;
+        if (kApply) {
+          o[j] = sc * (gr - k1[j] - xh * k2[j]);
+        } else {
+          sg[j] += gr;
+          sgx[j] = fmaf(gr, xh, sgx[j]);
+        }
+      }
+      if (kApply)
+        stg_v4(p.da + off, make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                      pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7])));
+    }
+    if (!kApply) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&p.sums[gg * 8 + j], static_cast<double>(sg[j]));
+        atomicAdd(&p.sums[p.C + gg * 8 + j], static_cast<double>(sgx[j]));
+      }
+    } else if (blockIdx.x == 0 && rl == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        p.dbeta[gg * 8 + j] += static_cast<float>(p.sums[gg * 8 + j]);
+        p.dgamma[gg * 8 + j] += static_cast<float>(p.sums[p.C + gg * 8 + j]);
+      }
+    }
+  }
+}
+
+// out = d * 1[z > 0]
+__global__ void __launch_bounds__(256)
+relu_mask_kernel(const __nv_bfloat16* __restrict__ d, const __nv_bfloat16* __restrict__ z,
+                 __nv_bfloat16* out, long long n8) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const uint4 vd = ldg_nc_v4(d + i * 8), vz = ldg_nc_v4(z + i * 8);
+    stg_v4(out + i * 8, make_uint4(vd.x & bf16x2_gt0_mask(vz.x), vd.y & bf16x2_gt0_mask(vz.y),
+                                   vd.z & bf16x2_gt0_mask(vz.z), vd.w & bf16x2_gt0_mask(vz.w)));
+  }
+}
+
+// out[c] += sum over rows of x[r][c]   (x bf16 [M][C], C % 8 == 0)
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* out, long long M, int C) {
+  pdl_trigger();
+  pdl_wait();
+  const int groups = C >> 3;
+  const int rstep = 256 / groups;
+  const int gg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  if (rl < rstep) {
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long r0 = (long long)blockIdx.x * rstep + rl;
+    for (long long r = r0; r < M; r += (long long)gridDim.x * rstep) {
+      const uint4 v = ldg_nc_v4(x + (size_t)r * C + gg * 8);
+      s[0] += bf16_lo(v.x); s[1] += bf16_hi(v.x); s[2] += bf16_lo(v.y); s[3] += bf16_hi(v.y);
+      s[4] += bf16_lo(v.z); s[5] += bf16_hi(v.z); s[6] += bf16_lo(v.w); s[7] += bf16_hi(v.w);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(out + gg * 8 + j, s[j]);
+  }
+}
+
+// Loss head of Keypoint_EmbeddingModel.epoch (models/keypoint.py:58-104), one warp per sample:
+//   contra  = ||e1 - e2||  (hinge_embedding_loss, target +1; only when e2 is given)
+//           + valid * max(0, 1 - ||e1 - en||)  (target -1, margin 1; only when en is given)
+//   loss    = contra + w3d * (sum (pred1 - true)^2 + sum (pred2 - true)^2)
+// and its gradient scaled by `gscale` (= 1 / batch_n: the reference divides the summed loss by
+// the number of samples before backward): de* fp32 [n][D], dpred* bf16 [n][Tpad].
+struct VipeLossParams {
+  const float* e1;
+  const float* e2;
+  const float* en;            // [n][D] (e2 / en may be null)
+  const float* valid;         // [n] or null (all valid)
+  const __nv_bfloat16* pred1;
+  const __nv_bfloat16* pred2; // [n][Tpad] or null
+  const float* true3d;        // [n][T] or null
+  float* de1;
+  float* de2;
+  float* den;                 // [n][D]
+  __nv_bfloat16* dpred1;
+  __nv_bfloat16* dpred2;      // [n][Tpad]
+  double* sums;               // [2]: contra, total (+=)
+  long long n;
+  int D, T, Tpad;
+  float w3d, gscale;
+};
+
+__global__ void __launch_bounds__(256)
+vipe_loss_kernel(const VipeLossParams p) {
+  pdl_trigger();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  double contra_acc = 0.0, total_acc = 0.0;
+  for (long long r = warp; r < p.n; r += nwarps) {
+    float contra = 0.f, mse = 0.f;
+    // embeddings: lane owns components lane, lane + 32
+    float a[2] = {0.f, 0.f}, d12[2] = {0.f, 0.f}, d1n[2] = {0.f, 0.f};
+    float s12 = 0.f, s1n = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = lane + 32 * j;
+      if (c < p.D) {
+        a[j] = p.e1[r * p.D + c];
+        if (p.e2) { d12[j] = a[j] - p.e2[r * p.D + c]; s12 = fmaf(d12[j], d12[j], s12); }
+        if (p.en) { d1n[j] = a[j] - p.en[r * p.D + c]; s1n = fmaf(d1n[j], d1n[j], s1n); }
+      }
+    }
+    s12 = warp_sum(s12);
+    s1n = warp_sum(s1n);
+    const float n12 = sqrtf(s12), n1n = sqrtf(s1n);
+    float c12 = 0.f, c1n = 0.f;                 // d loss / d (e1 - e2), d loss / d (e1 - en)
+    if (p.e2) {
+      contra += n12;
+      c12 = n12 > 0.f ? 1.f / n12 : 0.f;
+    }
+    if (p.en) {
+      const float v = p.valid ? p.valid[r] : 1.f;
+      const float h = 1.f - n1n;
+      if (h > 0.f) {
+        contra += v * h;
+        c1n = n1n > 0.f ? -v / n1n : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int c = lane + 32 * j;
+      if (c < p.D) {
+        const float g12 = c12 * d12[j] * p.gscale, g1n = c1n * d1n[j] * p.gscale;
+        p.de1[r * p.D + c] = g12 + g1n;
+        if (p.de2) p.de2[r * p.D + c] = -g12;
+        if (p.den) p.den[r * p.D + c] = -g1n;
+      }
+    }
+    if (p.true3d) {
+      for (int c = lane; c < p.Tpad; c += 32) {
+        const float t = c < p.T ? p.true3d[r * p.T + c] : 0.f;
+        const float e1 = c < p.T ? __bfloat162float(p.pred1[r * p.Tpad + c]) - t : 0.f;
+        mse = fmaf(e1, e1, mse);
+        p.dpred1[r * p.Tpad + c] = __float2bfloat16_rn(2.f * p.w3d * e1 * p.gscale);
+        if (p.pred2) {
+          const float e2 = c < p.T ? __bfloat162float(p.pred2[r * p.Tpad + c]) - t : 0.f;
+          mse = fmaf(e2, e2, mse);
+          p.dpred2[r * p.Tpad + c] = __float2bfloat16_rn(2.f * p.w3d * e2 * p.gscale);
+        }
+      }
+      mse = warp_sum(mse);
+    }
+    contra_acc += static_cast<double>(contra);
+    total_acc += static_cast<double>(contra) + static_cast<double>(p.w3d) * static_cast<double>(mse);
+  }
+  if (lane == 0 && (contra_acc != 0.0 || total_acc != 0.0)) {
+    atomicAdd(&p.sums[0], contra_acc);
+    atomicAdd(&p.sums[1], total_acc);
+  }
+}
+
 static unsigned grid_for(long long items, int threads) {
   long long blocks = (items + threads - 1) / threads;
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -167,6 +495,101 @@ int linear_rows_f32(const __nv_bfloat16* x, const float* w, const float* bias, f
   if (M <= 0) return 0;
   VPD_CHECK_CUDA(launch_kernel(linear_rows_f32_kernel, dim3((unsigned)((M + kLinRows - 1) / kLinRows)),
                                dim3(256), 0, stream, x, w, bias, out, M, K, D));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
+static unsigned rows_grid(long long M, int C) {
+  const int rstep = 256 / (C / 8);
+  long long blocks = (M + rstep - 1) / rstep;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+#define VPD_ROWS_OK(C) VPD_REQUIRE((C) >= 8 && (C) % 8 == 0 && (C) <= 2048, "row kernels: C %% 8 == 0, C <= 2048 (got %d)", (C))
+
+int dropout_mask(uint8_t* keep, long long n, float p_drop, unsigned long long seed,
+                 unsigned int stream_id, cudaStream_t stream) {
+  VPD_REQUIRE(n >= 0 && n % 4 == 0, "dropout_mask: element count must be a multiple of 4");
+  VPD_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "dropout_mask: p must be in [0, 1)");
+  if (n == 0) return 0;
+  VPD_CHECK_CUDA(launch_kernel(dropout_mask_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, stream,
+                               keep, n / 4, p_drop, seed, stream_id));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
+int bn1d_fwd(const __nv_bfloat16* a, const double* stats, const float* gamma, const float* beta,
+             const float* lin_bias, float* running_mean, float* running_var, long long* num_batches,
+             float* save_mean, float* save_rstd, const uint8_t* keep, float p_drop,
+             const __nv_bfloat16* res, __nv_bfloat16* out, long long M, int C, cudaStream_t stream) {
+  VPD_ROWS_OK(C);
+  VPD_REQUIRE(M >= 1, "bn1d_fwd: empty batch");
+  VPD_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "bn1d_fwd: p must be in [0, 1)");
+  Bn1dParams p;
+  p.a = a; p.stats = stats; p.gamma = gamma; p.beta = beta; p.lin_bias = lin_bias;
+  p.running_mean = running_mean; p.running_var = running_var; p.num_batches = num_batches;
+  p.save_mean = save_mean; p.save_rstd = save_rstd; p.keep = keep;
+  p.keep_scale = 1.f / (1.f - p_drop);
+  p.res = res; p.out = out; p.M = M; p.C = C; p.eps = 1e-5f; p.momentum = 0.1f;
+  VPD_CHECK_CUDA(launch_kernel(bn1d_fwd_kernel, dim3(rows_grid(M, C)), dim3(256), 0, stream, p));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
+int bn1d_bwd(const __nv_bfloat16* dz, const __nv_bfloat16* a, const uint8_t* keep, float p_drop,
+             const float* gamma, const float* beta, const float* save_mean, const float* save_rstd,
+             double* sums, __nv_bfloat16* da, float* dgamma, float* dbeta, long long M, int C,
+             cudaStream_t stream) {
+  VPD_ROWS_OK(C);
+  VPD_REQUIRE(M >= 1, "bn1d_bwd: empty batch");
+  Bn1dBwdParams p;
+  p.dz = dz; p.a = a; p.keep = keep; p.keep_scale = 1.f / (1.f - p_drop);
+  p.gamma = gamma; p.beta = beta; p.save_mean = save_mean; p.save_rstd = save_rstd;
+  p.sums = sums; p.da = da; p.dgamma = dgamma; p.dbeta = dbeta; p.M = M; p.C = C;
+  VPD_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
+  VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<false>, dim3(rows_grid(M, C)), dim3(256), 0, stream, p));
+  VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<true>, dim3(rows_grid(M, C)), dim3(256), 0, stream, p));
+  VPD_LAUNCHED(2);
+  return 0;
+}
+
+int relu_mask_bf16(const __nv_bfloat16* d, const __nv_bfloat16* z, __nv_bfloat16* out, long long n,
+                   cudaStream_t stream) {
+  VPD_REQUIRE(n >= 0 && n % 8 == 0, "relu_mask: element count must be a multiple of 8");
+  if (n == 0) return 0;
+  VPD_CHECK_CUDA(launch_kernel(relu_mask_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, stream, d, z,
+                               out, n / 8));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
+int colsum_bf16(const __nv_bfloat16* x, float* out, long long M, int C, cudaStream_t stream) {
+  VPD_ROWS_OK(C);
+  if (M <= 0) return 0;
+  VPD_CHECK_CUDA(launch_kernel(colsum_bf16_kernel, dim3(rows_grid(M, C)), dim3(256), 0, stream, x, out, M, C));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
+int vipe_loss(const float* e1, const float* e2, const float* en, const float* valid,
+              const __nv_bfloat16* pred1, const __nv_bfloat16* pred2, const float* true3d,
+              float* de1, float* de2, float* den, __nv_bfloat16* dpred1, __nv_bfloat16* dpred2,
+              double* sums, long long n, int D, int T, int Tpad, float w3d, float gscale,
+              cudaStream_t stream) {
+  VPD_REQUIRE(D >= 1 && D <= 64, "vipe_loss: 1 <= D <= 64 (got %d)", D);
+  VPD_REQUIRE(e1 != nullptr && de1 != nullptr && sums != nullptr, "vipe_loss: null e1 / de1 / sums");
+  VPD_REQUIRE((e2 == nullptr) == (de2 == nullptr) && (en == nullptr) == (den == nullptr),
+              "vipe_loss: every given embedding needs its gradient buffer");
+  VPD_REQUIRE(true3d == nullptr || (pred1 != nullptr && dpred1 != nullptr && T >= 1 && Tpad >= T),
+              "vipe_loss: 3-D targets need pred1 / dpred1 and 1 <= T <= Tpad");
+  VPD_REQUIRE((pred2 == nullptr) == (dpred2 == nullptr), "vipe_loss: pred2 and dpred2 come together");
+  if (n <= 0) return 0;
+  VipeLossParams p;
+  p.e1 = e1; p.e2 = e2; p.en = en; p.valid = valid; p.pred1 = pred1; p.pred2 = pred2;
+  p.true3d = true3d; p.de1 = de1; p.de2 = de2; p.den = den; p.dpred1 = dpred1; p.dpred2 = dpred2;
+  p.sums = sums; p.n = n; p.D = D; p.T = T; p.Tpad = Tpad; p.w3d = w3d; p.gscale = gscale;
+  VPD_CHECK_CUDA(launch_kernel(vipe_loss_kernel, dim3(grid_for(n * 32, 256)), dim3(256), 0, stream, p));
   VPD_LAUNCHED(1);
   return 0;
 }

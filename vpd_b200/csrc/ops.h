@@ -49,6 +49,25 @@ int bn_fold(const float* gamma, const float* beta, const float* mean, const floa
 int linear_rows_f32(const __nv_bfloat16* x, const float* w, const float* bias, float* out,
                     long long M, int K, int D, cudaStream_t stream);
 
+int dropout_mask(uint8_t* keep, long long n, float p_drop, unsigned long long seed,
+                 unsigned int stream_id, cudaStream_t stream);
+int bn1d_fwd(const __nv_bfloat16* a, const double* stats, const float* gamma, const float* beta,
+             const float* lin_bias, float* running_mean, float* running_var, long long* num_batches,
+             float* save_mean, float* save_rstd, const uint8_t* keep, float p_drop,
+             const __nv_bfloat16* res, __nv_bfloat16* out, long long M, int C, cudaStream_t stream);
+int bn1d_bwd(const __nv_bfloat16* dz, const __nv_bfloat16* a, const uint8_t* keep, float p_drop,
+             const float* gamma, const float* beta, const float* save_mean, const float* save_rstd,
+             double* sums, __nv_bfloat16* da, float* dgamma, float* dbeta, long long M, int C,
+             cudaStream_t stream);
+int relu_mask_bf16(const __nv_bfloat16* d, const __nv_bfloat16* z, __nv_bfloat16* out, long long n,
+                   cudaStream_t stream);
+int colsum_bf16(const __nv_bfloat16* x, float* out, long long M, int C, cudaStream_t stream);
+int vipe_loss(const float* e1, const float* e2, const float* en, const float* valid,
+              const __nv_bfloat16* pred1, const __nv_bfloat16* pred2, const float* true3d,
+              float* de1, float* de2, float* den, __nv_bfloat16* dpred1, __nv_bfloat16* dpred2,
+              double* sums, long long n, int D, int T, int Tpad, float w3d, float gscale,
+              cudaStream_t stream);
+
 int umma_probe(const __nv_bfloat16* src, int rows, int row_start, int sbo_bytes,
                int base_offset_mode, float* out, cudaStream_t stream);
 

@@ -20,8 +20,9 @@ Dropout is the identity in eval mode. Hidden activations are bf16 (tensor-core o
 the embedding is accumulated and returned in fp32.
 
 Training the teacher (`Keypoint_EmbeddingModel.epoch`: three weight-sharing encoder passes,
-hinge + MSE losses, models/keypoint.py:38-126) and the 3-D pose decoders are NOT built yet:
-those entry points raise NotImplementedError.
+hinge + MSE losses, models/keypoint.py:38-126) and the FC 3-D pose decoder live in
+`vpd_b200/keypoint_train.py`; `FCResNet.forward` itself stays eval-only (the training forward
+needs the saved activations the trainer keeps).
 """
 import json
 import os
@@ -94,8 +95,8 @@ class FCResNet:
                 if tuple(v.shape) != tuple(self._sd[k].shape):
                     raise RuntimeError('size mismatch for {}: {} vs {}'.format(
                         k, tuple(v.shape), tuple(self._sd[k].shape)))
-                self._sd[k] = v.detach().to(device=self._sd[k].device,
-                                            dtype=self._sd[k].dtype).clone()
+                # in place: during training the entries are views into the flat arena
+                self._sd[k].copy_(v.detach().to(device=self._sd[k].device, dtype=self._sd[k].dtype))
         self._prepared = None
 
     def parameters(self):
@@ -177,8 +178,45 @@ class FCResNet:
     __call__ = forward
 
 
+def batch_mulitplexer(data_loaders):
+    """models/util.py:5-23 - drain all loaders in a weighted way (evaluation)"""
+    import random
+    its = [{'name': a, 'n': len(b), 'it': iter(b)} for a, b in data_loaders]
+    while len(its) > 0:
+        i = random.choices(list(range(len(its))), k=1, weights=[x['n'] for x in its])[0]
+        sel = its[i]
+        try:
+            yield sel['name'], next(sel['it'])
+        except StopIteration:
+            raise Exception('Uh oh... something went horribly wrong! :(')
+        sel['n'] -= 1
+        if sel['n'] == 0:
+            its.pop(i)
+
+
+def batch_zipper(data_loaders):
+    """models/util.py:26-47 - drain all loaders simultaneously (training); loaders with fewer
+    batches skip randomly chosen rounds (numpy's global generator, like the reference)"""
+    its = [(a, len(b), iter(b)) for a, b in data_loaders]
+    num_batches = max(len(b) for a, b in data_loaders)
+    skip_idxs = {}
+    for a, b in data_loaders:
+        deficit = num_batches - len(b)
+        if deficit > 0:
+            skip_idxs[a] = set(np.random.choice(np.arange(num_batches), deficit,
+                                                replace=False).tolist())
+    for i in range(num_batches):
+        batch = []
+        for a, b, c in its:
+            if a in skip_idxs and i in skip_idxs[a]:
+                continue
+            batch.append((a, next(c)))
+        yield batch
+
+
 class Keypoint_EmbeddingModel:
-    """models/keypoint.py:14-35,38-160 - the embedding side."""
+    """models/keypoint.py:14-35,38-160. `decoders` = {} or {'3d': FCPoseDecoder}
+    (vpd_b200.keypoint_train.FCPoseDecoder; the FCResNet decoder variant is not built)."""
 
     def __init__(self, encoder, decoders, device):
         self.encoder = encoder
@@ -186,16 +224,81 @@ class Keypoint_EmbeddingModel:
         self.device = device
         self.encoder.to(device)
         if decoders:
-            raise NotImplementedError('3-D pose decoders are not part of the CUDA path yet')
+            from .keypoint_train import FCPoseDecoder
+            if set(decoders) != {'3d'} or not isinstance(decoders['3d'], FCPoseDecoder):
+                raise NotImplementedError("decoders must be {} or {'3d': FCPoseDecoder}")
+        self._core_obj = None
 
-    def epoch(self, data_loaders, optimizer=None, scaler=None, progress_cb=None, weight_3d=1):
-        raise NotImplementedError('training the keypoint teacher is not part of the CUDA path yet '
-                                  '(DESIGN.md section 8)')
+    def _core(self):
+        if self._core_obj is None:
+            from .keypoint_train import KeypointTrainCore
+            self._core_obj = KeypointTrainCore(self.encoder, self.decoders.get('3d'),
+                                               self.encoder._dev)
+        return self._core_obj
+
+    def get_optimizer(self, learning_rate):
+        """AdamW over encoder + decoder parameters (train_vipe_model.py:164-169,312-314) as one
+        fused launch over the flat arena. (The reference script builds torch.optim.AdamW over
+        `get_model_params(encoder, decoders)` itself; build this one instead.)"""
+        from .keypoint_train import KeypointAdamW
+        return KeypointAdamW(self._core(), learning_rate)
+
+    def _to_dev(self, batch):
+        dev = self.encoder._dev
+        out = {}
+        n = batch['pose1'].shape[0]
+        for k in ('pose1', 'pose2', 'pose_neg'):
+            if k in batch:
+                out[k] = torch.as_tensor(batch[k]).to(dev, torch.float32).reshape(n, -1).contiguous()
+        if 'pose_neg_is_valid' in batch:
+            out['pose_neg_is_valid'] = torch.as_tensor(batch['pose_neg_is_valid']).to(
+                dev, torch.float32).reshape(n).contiguous()
+        if 'kp_features' in batch:
+            out['kp_features'] = torch.as_tensor(batch['kp_features']).float().to(dev).reshape(
+                n, -1).contiguous()
+        return out
+
+    def epoch(self, data_loaders, optimizer=None, scaler=None, progress_cb=None, weight_3d=1,
+              dropout_masks=None):
+        """models/keypoint.py:38-126. data_loaders: [(dataset_name, loader of batch dicts)].
+        Returns (contrastive loss / n, loss / n, {dataset: loss / n}). `scaler` is ignored (fp32
+        master weights, bf16 range). dropout_masks: optional iterator yielding, per dataset
+        batch, the keep masks [pass][2 * num_blocks] uint8 [n, hidden] (tests)."""
+        from collections import Counter
+        train = optimizer is not None
+        self.encoder.train(train)
+        core = self._core()
+        core.weights_dirty = True
+        self.encoder._prepared = None
+        dataset_losses, dataset_contra_losses, dataset_counts = Counter(), Counter(), Counter()
+        batches = batch_zipper(data_loaders) if train else (
+            (x,) for x in batch_mulitplexer(data_loaders))
+        for zipped_batch in batches:
+            zipped_batch = [(name, self._to_dev(b)) for name, b in zipped_batch]
+            batch_n = sum(b['pose1'].shape[0] for _, b in zipped_batch)
+            for dataset_name, batch in zipped_batch:
+                core.loss_sums.zero_()
+                masks = next(dropout_masks) if dropout_masks is not None else None
+                n = core.dataset_step(batch, dataset_name, 1.0 / batch_n, weight_3d, masks=masks,
+                                      train=train)
+                contra_loss, loss = core.loss_sums.tolist()
+                if contra_loss > 0:
+                    dataset_contra_losses[dataset_name] += contra_loss
+                dataset_losses[dataset_name] += loss
+                dataset_counts[dataset_name] += n
+            if train:
+                optimizer.step()
+                optimizer.zero_grad()
+                self.encoder._prepared = None
+            if progress_cb is not None:
+                progress_cb(batch_n)
+        epoch_n = sum(dataset_counts.values())
+        return (sum(dataset_contra_losses.values()) / epoch_n,
+                sum(dataset_losses.values()) / epoch_n,
+                {k: v / dataset_counts[k] for k, v in dataset_losses.items()})
 
     def _predict(self, pose, get_emb, decoder_target=None):
         assert get_emb or decoder_target is not None, 'Nothing to predict'
-        if decoder_target is not None:
-            raise NotImplementedError('3-D pose decoders are not part of the CUDA path yet')
         if not isinstance(pose, torch.Tensor):
             pose = torch.FloatTensor(np.asarray(pose))
         if len(pose.shape) == 2:
@@ -203,7 +306,14 @@ class Keypoint_EmbeddingModel:
         self.encoder.eval()
         n = pose.shape[0]
         emb = self.encoder(pose.reshape(n, -1))
-        return emb.cpu().numpy(), None
+        if decoder_target is None:
+            return emb.cpu().numpy(), None
+        core = self._core()
+        core._refresh_mirrors()
+        pred, _ = core.decoder_forward(emb, decoder_target)
+        tdim = dict(self.decoders['3d'].target_dims)[decoder_target]
+        pred = pred[:, :tdim].float().cpu().numpy()
+        return (emb.cpu().numpy() if get_emb else None), pred
 
     def embed(self, pose):
         return self._predict(pose, get_emb=True)[0]
