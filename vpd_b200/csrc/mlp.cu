@@ -499,13 +499,15 @@ int linear_rows_f32(const __nv_bfloat16* x, const float* w, const float* bias, f
   return 0;
 }
 
-static unsigned rows_grid(long long M, int C) {
+static unsigned rows_grid(long long M, int C, long long cap = 148 * 4) {
   const int rstep = 256 / (C / 8);
   long long blocks = (M + rstep - 1) / rstep;
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
 }
+// reductions end in one atomic per thread and column: fewer, longer-running CTAs
+constexpr long long kReduceCtas = 74;
 #define VPD_ROWS_OK(C) VPD_REQUIRE((C) >= 8 && (C) % 8 == 0 && (C) <= 2048, "row kernels: C %% 8 == 0, C <= 2048 (got %d)", (C))
 
 int dropout_mask(uint8_t* keep, long long n, float p_drop, unsigned long long seed,
@@ -548,7 +550,7 @@ int bn1d_bwd(const __nv_bfloat16* dz, const __nv_bfloat16* a, const uint8_t* kee
   p.gamma = gamma; p.beta = beta; p.save_mean = save_mean; p.save_rstd = save_rstd;
   p.sums = sums; p.da = da; p.dgamma = dgamma; p.dbeta = dbeta; p.M = M; p.C = C;
   VPD_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
-  VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<false>, dim3(rows_grid(M, C)), dim3(256), 0, stream, p));
+  VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<false>, dim3(rows_grid(M, C, kReduceCtas)), dim3(256), 0, stream, p));
   VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<true>, dim3(rows_grid(M, C)), dim3(256), 0, stream, p));
   VPD_LAUNCHED(2);
   return 0;
@@ -567,7 +569,7 @@ int relu_mask_bf16(const __nv_bfloat16* d, const __nv_bfloat16* z, __nv_bfloat16
 int colsum_bf16(const __nv_bfloat16* x, float* out, long long M, int C, cudaStream_t stream) {
   VPD_ROWS_OK(C);
   if (M <= 0) return 0;
-  VPD_CHECK_CUDA(launch_kernel(colsum_bf16_kernel, dim3(rows_grid(M, C)), dim3(256), 0, stream, x, out, M, C));
+  VPD_CHECK_CUDA(launch_kernel(colsum_bf16_kernel, dim3(rows_grid(M, C, kReduceCtas)), dim3(256), 0, stream, x, out, M, C));
   VPD_LAUNCHED(1);
   return 0;
 }
