@@ -221,7 +221,9 @@ VPD_API int vpd_linear_rows_f32(const void* x_bf16, const float* w, const float*
 /* Training side of the same encoder (models/module.py:159-177 in train mode,
  * models/keypoint.py:38-126). Rows are bf16 [M][C], C % 8 == 0, C <= 2048.
  *   vpd_dropout_mask   keep[i] = 1 with probability 1 - p_drop (Philox4x32-10, keyed by seed
- *                      and stream_id); n % 4 == 0
+ *                      [+ *seed_add, a device-side step counter that lets a captured CUDA
+ *                      graph draw fresh masks on every replay; may be NULL] and stream_id);
+ *                      n % 4 == 0
  *   vpd_bn1d_fwd       out = keep * relu(BatchNorm1d_train(a)) / (1 - p_drop) [- res].
  *                      `a` is the Linear output WITHOUT its bias (a bias in front of a batch-
  *                      statistics BN cancels; lin_bias only enters running_mean); stats = fp64
@@ -239,8 +241,8 @@ VPD_API int vpd_linear_rows_f32(const void* x_bf16, const float* w, const float*
  *                      sums[1] += loss; gradients times gscale (1 / batch size): de* fp32
  *                      [n][D], dpred* bf16 [n][Tpad] (pad columns zero). e2 / en / true3d /
  *                      pred2 may be NULL (datasets without those entries). */
-VPD_API int vpd_dropout_mask(uint8_t* keep, int64_t n, float p_drop, uint64_t seed, int stream_id,
-                     void* stream);
+VPD_API int vpd_dropout_mask(uint8_t* keep, int64_t n, float p_drop, uint64_t seed,
+                     const uint64_t* seed_add, int stream_id, void* stream);
 VPD_API int vpd_bn1d_fwd(const void* a, const double* stats, const float* gamma, const float* beta,
                  const float* lin_bias, float* running_mean, float* running_var,
                  int64_t* num_batches, float* save_mean, float* save_rstd, const uint8_t* keep,

@@ -99,11 +99,14 @@ def test_small_ops_against_torch():
     L.call('vpd_relu_mask_bf16', x, z, o, x.numel(), st)
     assert torch.equal(o, torch.where(z > 0, x, torch.zeros_like(x)))
     keep = torch.empty(1 << 20, device=dev(), dtype=torch.uint8)
-    L.call('vpd_dropout_mask', keep, keep.numel(), 0.2, 1234, 7, st)
+    L.call('vpd_dropout_mask', keep, keep.numel(), 0.2, 1234, None, 7, st)
     assert set(keep.unique().tolist()) <= {0, 1} and abs(float(keep.float().mean()) - 0.8) < 0.003
     keep2 = torch.empty_like(keep)
-    L.call('vpd_dropout_mask', keep2, keep.numel(), 0.2, 1234, 8, st)
+    L.call('vpd_dropout_mask', keep2, keep.numel(), 0.2, 1234, None, 8, st)
     assert not torch.equal(keep, keep2)
+    add = torch.tensor([5], device=dev(), dtype=torch.int64)         # seed + device-side counter
+    L.call('vpd_dropout_mask', keep2, keep.numel(), 0.2, 1229, add, 7, st)
+    assert torch.equal(keep, keep2)
 
 
 @pytest.mark.parametrize('full', [True, False])
@@ -253,8 +256,10 @@ def test_two_training_steps_match_the_reference():
     assert emb.shape == (8, 32) and pred.shape == (8, 140) and np.isfinite(pred).all()
 
 
-def test_training_with_device_dropout_reduces_the_loss():
+@pytest.mark.parametrize('graphs', [False, True])
+def test_training_with_device_dropout_reduces_the_loss(graphs):
     model, enc, dec = _build()
+    model._core().use_graphs = graphs          # opt-in CUDA-graph replay of the step
     opt = model.get_optimizer(2e-3)
     data = [T.synth_batch(256, 80 + i) for i in range(4)]
     first = last = None
@@ -262,7 +267,7 @@ def test_training_with_device_dropout_reduces_the_loss():
         contra, loss, per = model.epoch([('h36m', data)], optimizer=opt)
         first = loss if first is None else first
         last = loss
-    _log('device-dropout training: loss {:.4f} -> {:.4f}'.format(first, last))
+    _log('device-dropout training (graphs={}): loss {:.4f} -> {:.4f}'.format(graphs, first, last))
     assert np.isfinite(last) and last < 0.9 * first
     sd = enc.state_dict()
     assert int(sd['layers.2.block.1.num_batches_tracked']) == 6 * 4 * 3

@@ -103,9 +103,10 @@ int vpd_linear_rows_f32(const void* x_bf16, const float* w, const float* bias, f
   return linear_rows_f32((const bf16*)x_bf16, w, bias, out, M, K, D, (cudaStream_t)stream);
 }
 
-int vpd_dropout_mask(uint8_t* keep, int64_t n, float p_drop, uint64_t seed, int stream_id,
-                     void* stream) {
-  return dropout_mask(keep, n, p_drop, seed, (unsigned int)stream_id, (cudaStream_t)stream);
+int vpd_dropout_mask(uint8_t* keep, int64_t n, float p_drop, uint64_t seed,
+                     const uint64_t* seed_add, int stream_id, void* stream) {
+  return dropout_mask(keep, n, p_drop, seed, (const unsigned long long*)seed_add,
+                      (unsigned int)stream_id, (cudaStream_t)stream);
 }
 int vpd_bn1d_fwd(const void* a, const double* stats, const float* gamma, const float* beta,
                  const float* lin_bias, float* running_mean, float* running_var,

@@ -133,9 +133,11 @@ linear_rows_f32_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
 // one call per 4 elements)
 __global__ void __launch_bounds__(256)
 dropout_mask_kernel(uint8_t* __restrict__ keep, long long n4, float p_drop,
-                    unsigned long long seed, unsigned int stream_id) {
+                    unsigned long long seed, const unsigned long long* __restrict__ seed_add,
+                    unsigned int stream_id) {
   pdl_trigger();
   pdl_wait();
+  if (seed_add != nullptr) seed += *seed_add;   // device-side step counter (CUDA-graph replays)
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
        i += (long long)gridDim.x * blockDim.x) {
     unsigned int c0 = (unsigned int)i, c1 = (unsigned int)(i >> 32), c2 = stream_id, c3 = 0x5eedu;
@@ -499,6 +501,13 @@ int linear_rows_f32(const __nv_bfloat16* x, const float* w, const float* bias, f
   return 0;
 }
 
+__global__ void __launch_bounds__(256) zero_f64_kernel(double* p, int n) {
+  pdl_trigger();
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+}
+
 static unsigned rows_grid(long long M, int C, long long cap = 148 * 4) {
   const int rstep = 256 / (C / 8);
   long long blocks = (M + rstep - 1) / rstep;
@@ -511,12 +520,12 @@ constexpr long long kReduceCtas = 74;
 #define VPD_ROWS_OK(C) VPD_REQUIRE((C) >= 8 && (C) % 8 == 0 && (C) <= 2048, "row kernels: C %% 8 == 0, C <= 2048 (got %d)", (C))
 
 int dropout_mask(uint8_t* keep, long long n, float p_drop, unsigned long long seed,
-                 unsigned int stream_id, cudaStream_t stream) {
+                 const unsigned long long* seed_add, unsigned int stream_id, cudaStream_t stream) {
   VPD_REQUIRE(n >= 0 && n % 4 == 0, "dropout_mask: element count must be a multiple of 4");
   VPD_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "dropout_mask: p must be in [0, 1)");
   if (n == 0) return 0;
   VPD_CHECK_CUDA(launch_kernel(dropout_mask_kernel, dim3(grid_for(n / 4, 256)), dim3(256), 0, stream,
-                               keep, n / 4, p_drop, seed, stream_id));
+                               keep, n / 4, p_drop, seed, seed_add, stream_id));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -549,10 +558,11 @@ int bn1d_bwd(const __nv_bfloat16* dz, const __nv_bfloat16* a, const uint8_t* kee
   p.dz = dz; p.a = a; p.keep = keep; p.keep_scale = 1.f / (1.f - p_drop);
   p.gamma = gamma; p.beta = beta; p.save_mean = save_mean; p.save_rstd = save_rstd;
   p.sums = sums; p.da = da; p.dgamma = dgamma; p.dbeta = dbeta; p.M = M; p.C = C;
-  VPD_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, stream));
+  // a kernel, not a memset node: the step is captured into a CUDA graph with programmatic edges
+  VPD_CHECK_CUDA(launch_kernel(zero_f64_kernel, dim3((2 * C + 255) / 256), dim3(256), 0, stream, sums, 2 * C));
   VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<false>, dim3(rows_grid(M, C, kReduceCtas)), dim3(256), 0, stream, p));
   VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<true>, dim3(rows_grid(M, C)), dim3(256), 0, stream, p));
-  VPD_LAUNCHED(2);
+  VPD_LAUNCHED(3);
   return 0;
 }
 

@@ -50,7 +50,7 @@ int linear_rows_f32(const __nv_bfloat16* x, const float* w, const float* bias, f
                     long long M, int K, int D, cudaStream_t stream);
 
 int dropout_mask(uint8_t* keep, long long n, float p_drop, unsigned long long seed,
-                 unsigned int stream_id, cudaStream_t stream);
+                 const unsigned long long* seed_add, unsigned int stream_id, cudaStream_t stream);
 int bn1d_fwd(const __nv_bfloat16* a, const double* stats, const float* gamma, const float* beta,
              const float* lin_bias, float* running_mean, float* running_var, long long* num_batches,
              float* save_mean, float* save_rstd, const uint8_t* keep, float p_drop,

@@ -139,6 +139,7 @@ class KeypointAdamW:
                    self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count, 1.0,
                    stream_ptr(self.core.dev))
         self.core.weights_dirty = True
+        self.core._refresh_mirrors()       # bf16 mirrors follow the masters right away
 
     def zero_grad(self, set_to_none=False):
         self.core.arena.grads.zero_()
@@ -195,6 +196,14 @@ class KeypointTrainCore:
         self.loss_sums = torch.zeros(2, device=dev, dtype=torch.float64)
         self.mask_seed = 0x5eed
         self.mask_calls = 0
+        # device-side step counter added to the dropout seed: a captured step draws fresh masks
+        # on every replay
+        self._seed_step = torch.zeros(1, device=dev, dtype=torch.int64)
+        self._graphs = {}
+        # measured on B200 (tests/diag_keypoint.py, n = 4096): 3.08 ms/step launched one by one,
+        # 3.26 ms replayed - the step is bound by the latency of ~160 small kernels, not by
+        # launching them; replay only frees the host thread, so it is opt-in
+        self.use_graphs = False
 
     # ---- helpers ---------------------------------------------------------------------------
     def _st(self):
@@ -252,7 +261,7 @@ class KeypointTrainCore:
         keep = torch.empty((n, self.H), device=self.dev, dtype=torch.uint8)
         self.mask_calls += 1
         lib().call('vpd_dropout_mask', keep, n * self.H, self.p_drop, self.mask_seed,
-                   self.mask_calls & 0x7fffffff, self._st())
+                   self._seed_step, self.mask_calls & 0x7fffffff, self._st())
         return keep
 
     # ---- encoder ---------------------------------------------------------------------------
@@ -363,9 +372,38 @@ class KeypointTrainCore:
     def dataset_step(self, batch, target, gscale, weight_3d=1.0, masks=None, train=True):
         """batch: dict of device fp32 tensors 'pose1' [n, in] (+ 'pose2', 'pose_neg',
         'pose_neg_is_valid' [n], 'kp_features' [n, T]); gscale = 1 / (samples in the zipped
-        batch). Adds (contra, loss) to self.loss_sums; returns n."""
-        L, st, D = lib(), self._st(), self.D
+        batch). Adds (contra, loss) to self.loss_sums; returns n.
+
+        With `use_graphs` (opt-in) a training step with device-generated dropout is captured,
+        per (dataset, shapes, scale), into a CUDA graph over static input buffers on its second
+        call and replayed afterwards (~160 launches -> one; fresh masks come from the
+        device-side seed counter)."""
         self._refresh_mirrors()
+        n = batch['pose1'].shape[0]
+        if not (train and masks is None and self.use_graphs):
+            return self._dataset_step(batch, target, gscale, weight_3d, masks, train)
+        self._seed_step.add_(1)
+        key = (target, float(gscale), float(weight_3d),
+               tuple((k, tuple(v.shape)) for k, v in sorted(batch.items())))
+        ent = self._graphs.get(key)
+        if ent is None:                       # first time: plain launches (also warms every kernel)
+            self._graphs[key] = {'calls': 1}
+            return self._dataset_step(batch, target, gscale, weight_3d, None, True)
+        if 'graph' not in ent:
+            ent['static'] = {k: v.clone() for k, v in batch.items()}
+            self.mask_calls = 0
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._dataset_step(ent['static'], target, gscale, weight_3d, None, True)
+            ent['graph'] = g
+        for k, v in batch.items():
+            ent['static'][k].copy_(v)
+        ent['graph'].replay()
+        return n
+
+    def _dataset_step(self, batch, target, gscale, weight_3d, masks, train):
+        L, st, D = lib(), self._st(), self.D
         n = batch['pose1'].shape[0]
         names = [k for k in ('pose1', 'pose2', 'pose_neg') if k in batch]
         embs, ctxs = {}, {}
