@@ -6,6 +6,7 @@ import hashlib
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import keypoint_train_ref as T
@@ -91,3 +92,63 @@ def test_arena_views_and_zipper():
     random.seed(0)
     seen = sorted(x for _, x in keypoint.batch_mulitplexer([('a', [1, 2, 3]), ('b', [10])]))
     assert seen == [1, 2, 3, 10]
+
+
+class _FakeState:
+    def __init__(self, v):
+        self.v = torch.tensor([float(v)])
+
+    def state_dict(self):
+        return {'v': self.v.clone()}
+
+    def load_state_dict(self, sd):
+        self.v = sd['v'].clone()
+
+
+class _FakeModel:
+    """epoch() returns scripted losses; the driver's file logic needs nothing else"""
+
+    def __init__(self, val_losses):
+        self.encoder, self.decoders = _FakeState(0), {'3d': _FakeState(0)}
+        self.val = list(val_losses)
+        self.calls = 0
+
+    def epoch(self, loaders, optimizer=None, weight_3d=1):
+        if optimizer is not None:
+            self.calls += 1
+            self.encoder.v += 1
+            return 0.5, 10.0 - self.calls, {'h36m': 10.0 - self.calls}
+        return 0.25, self.val[self.calls - 1], {'h36m': self.val[self.calls - 1]}
+
+
+def test_fit_driver_files_selection_and_resume(tmp_path):
+    import json
+    from vpd_b200 import keypoint_train as KT
+    cfg = {'datasets': [{'name': 'h36m', '3d_pose_shape': [20, 7], 'mean_kp_offset_norms': [1.0]}],
+           'num_epochs': 4, 'learning_rate': 1e-4, 'batch_size': 100, 'embedding_dim': 32,
+           'encoder_arch': [2, 1024], 'decoder_arch': [2, 512], 'embed_bones': False,
+           'augment_camera': True}
+    d = os.path.join(str(tmp_path), 'run')
+    model, opt = _FakeModel([5.0, 4.0, 4.5, 3.0]), _FakeState(7)
+    logs = []
+    hist = KT.fit(model, [], [], d, cfg, opt, num_epochs=4, checkpoint_frequency=2, log=logs.append)
+    assert [h['epoch'] for h in hist] == [1, 2, 3, 4] and hist[0]['dataset_train'][0] == ('contrast', 0.5)
+    assert sum('New best epoch' in l for l in logs) == 3                # epochs 1, 2, 4
+    files = sorted(os.listdir(d))
+    assert files == ['best_epoch.decoder-3d.pt', 'best_epoch.encoder.pt', 'best_epoch.optimizer.pt',
+                     'config.json', 'epoch0002.decoder-3d.pt', 'epoch0002.encoder.pt',
+                     'epoch0002.optimizer.pt', 'epoch0004.decoder-3d.pt', 'epoch0004.encoder.pt',
+                     'epoch0004.optimizer.pt', 'loss.json']
+    with open(os.path.join(d, 'config.json')) as fp:
+        assert json.load(fp) == json.loads(json.dumps(cfg))
+    assert KT.get_last_checkpoint(d) == 4
+    assert float(torch.load(os.path.join(d, 'best_epoch.encoder.pt'))['v']) == 4.0
+    # resume: state comes from epoch0004, history is kept, training continues at epoch 5
+    model2, opt2 = _FakeModel([9.0] * 6), _FakeState(0)
+    model2.calls = 4
+    hist2 = KT.fit(model2, [], [], d, cfg, opt2, num_epochs=6, checkpoint_frequency=2, resume=True,
+                   log=logs.append)
+    assert [h['epoch'] for h in hist2] == [1, 2, 3, 4, 5, 6] and float(opt2.v) == 7.0
+    assert float(model2.encoder.v) == 4.0 + 2
+    with pytest.raises(AssertionError):
+        KT.fit(model, [], [], os.path.join(str(tmp_path), 'x'), {'num_epochs': 1}, opt, num_epochs=1)

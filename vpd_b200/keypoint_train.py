@@ -144,6 +144,17 @@ class KeypointAdamW:
     def zero_grad(self, set_to_none=False):
         self.core.arena.grads.zero_()
 
+    def state_dict(self):
+        return {'step': self.step_count, 'exp_avg': self._m.cpu(), 'exp_avg_sq': self._v.cpu(),
+                'lr': self.lr, 'betas': self.betas, 'eps': self.eps,
+                'weight_decay': self.weight_decay,
+                'layout': [(k, v[0], list(v[1])) for k, v in self.core.arena.entries.items()]}
+
+    def load_state_dict(self, sd):
+        self._m.copy_(sd['exp_avg'])
+        self._v.copy_(sd['exp_avg_sq'])
+        self.step_count = sd['step']
+
 
 class KeypointTrainCore:
     """Owns the arena, the bf16 weight mirrors and the launch sequence of one training step."""
@@ -438,3 +449,100 @@ class KeypointTrainCore:
                 db = self.decoder_backward(dctx[k], dpred[k], db)
             self.encoder_backward(ctxs[k], db)
         return n
+
+
+# ---- the training driver: train_vipe_model.py:171-209,228-229,312-430 ---------------------------
+CONFIG_KEYS = ('datasets', 'num_epochs', 'learning_rate', 'batch_size', 'embedding_dim',
+               'encoder_arch', 'decoder_arch', 'embed_bones', 'augment_camera')
+
+
+def save_model(save_dir, name, encoder, decoders, optimizer):
+    """train_vipe_model.py:171-183: `<name>.encoder.pt`, `<name>.decoder-<k>.pt`,
+    `<name>.optimizer.pt` (the optimizer file holds the fused AdamW's flat moments, not
+    torch.optim.AdamW's per-tensor state)"""
+    import os
+    torch.save(OrderedDict((k, v.cpu()) for k, v in encoder.state_dict().items()),
+               os.path.join(save_dir, '{}.encoder.pt'.format(name)))
+    for k, v in decoders.items():
+        torch.save(OrderedDict((n, t.cpu()) for n, t in v.state_dict().items()),
+                   os.path.join(save_dir, '{}.decoder-{}.pt'.format(name, k)))
+    torch.save(optimizer.state_dict(), os.path.join(save_dir, '{}.optimizer.pt'.format(name)))
+
+
+def load_model(save_dir, name, encoder, decoders, optimizer, device='cuda'):
+    """train_vipe_model.py:186-199"""
+    import os
+    encoder.load_state_dict(torch.load(os.path.join(save_dir, '{}.encoder.pt'.format(name)),
+                                       map_location='cpu'))
+    for k, decoder in decoders.items():
+        decoder.load_state_dict(torch.load(
+            os.path.join(save_dir, '{}.decoder-{}.pt'.format(name, k)), map_location='cpu'))
+    optimizer.load_state_dict(torch.load(os.path.join(save_dir, '{}.optimizer.pt'.format(name)),
+                                         map_location='cpu'))
+
+
+def get_last_checkpoint(save_dir):
+    """train_vipe_model.py:202-209"""
+    import os
+    import re
+    last_epoch = -1
+    for fname in os.listdir(save_dir):
+        m = re.match(r'epoch(\d+).encoder.pt', fname)
+        if m:
+            last_epoch = max(int(m.group(1)), last_epoch)
+    return last_epoch
+
+
+def fit(model, train_loaders, val_loaders, save_dir, config, optimizer, num_epochs,
+        checkpoint_frequency=25, model_select_contrast=False, model_select_window=1,
+        resume=False, weight_3d=1, log=print):
+    """The epoch loop of train_vipe_model.main (:312-430) without the video previews: config.json
+    (same keys), loss.json (same records), `best_epoch.*` whenever the moving average of the
+    validation loss improves, `epochNNNN.*` every `checkpoint_frequency` epochs, resume from the
+    last checkpoint. `model` needs `.encoder`, `.decoders` and `.epoch` (Keypoint_EmbeddingModel).
+    Returns the loss history."""
+    import json
+    import os
+    import numpy as np
+    mv = lambda ls, n, key: float(np.mean([l[key] for l in ls[-n:]]))
+    loss_file = os.path.join(save_dir, 'loss.json')
+    if resume:
+        assert os.path.exists(save_dir)
+        last = get_last_checkpoint(save_dir)
+        load_model(save_dir, 'epoch{:04d}'.format(last), model.encoder, model.decoders, optimizer)
+        start_epoch = last + 1
+        with open(loss_file) as fp:
+            losses = [x for x in json.load(fp) if x['epoch'] < start_epoch]
+        best_val_loss = min([mv(losses[:i], model_select_window, 'val')
+                             for i in range(model_select_window, len(losses))] or [float('inf')])
+    else:
+        missing = [k for k in CONFIG_KEYS if k not in config]
+        assert not missing, 'config lacks {}'.format(missing)
+        start_epoch = 1
+        os.makedirs(save_dir)
+        with open(os.path.join(save_dir, 'config.json'), 'w') as fp:
+            json.dump({k: config[k] for k in CONFIG_KEYS}, fp, indent=2)
+        losses, best_val_loss = [], float('inf')
+    for epoch in range(start_epoch, num_epochs + 1):
+        tc, tl, dtl = model.epoch(train_loaders, optimizer=optimizer, weight_3d=weight_3d)
+        vc, vl, dvl = model.epoch(val_loaders, weight_3d=weight_3d)
+        losses.append({'epoch': epoch,
+                       'train': tc if model_select_contrast else tl,
+                       'val': vc if model_select_contrast else vl,
+                       'dataset_train': [('contrast', tc)] + list(dtl.items()),
+                       'dataset_val': [('contrast', vc)] + list(dvl.items())})
+        mv_avg_val_loss = mv(losses, model_select_window, 'val')
+        log('Epoch {} - train loss: {:0.5f}, contra: {:0.3f} [mv-avg: {:0.5f}]'.format(
+            epoch, tl, tc, mv(losses, model_select_window, 'train')))
+        log('Epoch {} - val loss: {:0.5f}, contra: {:0.3f} [mv-avg: {:0.5f}]'.format(
+            epoch, vl, vc, mv_avg_val_loss))
+        with open(loss_file, 'w') as fp:
+            json.dump(losses, fp, indent=2)
+        if mv_avg_val_loss < best_val_loss:
+            log('New best epoch!')
+            save_model(save_dir, 'best_epoch', model.encoder, model.decoders, optimizer)
+        if epoch % checkpoint_frequency == 0:
+            log('Saving checkpoint: {}'.format(epoch))
+            save_model(save_dir, 'epoch{:04d}'.format(epoch), model.encoder, model.decoders, optimizer)
+        best_val_loss = min(mv_avg_val_loss, best_val_loss)
+    return losses
