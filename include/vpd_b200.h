@@ -233,6 +233,11 @@ VPD_API int vpd_linear_rows_f32(const void* x_bf16, const float* w, const float*
  *   vpd_bn1d_bwd       da = BN backward of g = dz * keep / (1-p) * 1[bn(a) > 0];
  *                      dgamma += sum g*xhat, dbeta += sum g (ACCUMULATED: the three encoder
  *                      passes of a step share weights); sums = fp64 [2][C] scratch
+ *                      `groups`: the weight-sharing encoder passes of a step are stacked along
+ *                      the rows - `groups` consecutive blocks of M rows, each its own BatchNorm
+ *                      batch (stats / save_mean / save_rstd / sums are [groups][...]); running
+ *                      statistics are updated group after group like consecutive calls
+ *   vpd_colstats_bf16  stats[g] = column sums and sums of squares (fp64) of row group g
  *   vpd_relu_mask_bf16 out = d * 1[z > 0]
  *   vpd_colsum_bf16    out[c] += sum_r x[r][c]   (Linear bias gradients)
  *   vpd_vipe_loss      the loss head: contra = ||e1-e2|| + valid * max(0, 1 - ||e1-en||)
@@ -246,11 +251,13 @@ VPD_API int vpd_dropout_mask(uint8_t* keep, int64_t n, float p_drop, uint64_t se
 VPD_API int vpd_bn1d_fwd(const void* a, const double* stats, const float* gamma, const float* beta,
                  const float* lin_bias, float* running_mean, float* running_var,
                  int64_t* num_batches, float* save_mean, float* save_rstd, const uint8_t* keep,
-                 float p_drop, const void* res, void* out, int64_t M, int C, void* stream);
+                 float p_drop, const void* res, void* out, int64_t M, int C, int groups,
+                 void* stream);
 VPD_API int vpd_bn1d_bwd(const void* dz, const void* a, const uint8_t* keep, float p_drop,
                  const float* gamma, const float* beta, const float* save_mean,
                  const float* save_rstd, double* sums, void* da, float* dgamma, float* dbeta,
-                 int64_t M, int C, void* stream);
+                 int64_t M, int C, int groups, void* stream);
+VPD_API int vpd_colstats_bf16(const void* x, double* stats, int64_t M, int C, int groups, void* stream);
 VPD_API int vpd_relu_mask_bf16(const void* d, const void* z, void* out, int64_t n, void* stream);
 VPD_API int vpd_colsum_bf16(const void* x, float* out, int64_t M, int C, void* stream);
 VPD_API int vpd_vipe_loss(const float* e1, const float* e2, const float* en, const float* valid,

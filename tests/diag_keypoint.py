@@ -1,6 +1,6 @@
 """Timing of the keypoint (VIPE*) teacher on BASELINE config 4 (n = 4096 synthetic poses,
 encoder (2, 1024), decoder (2, 512), 20 x 7 3-D targets); not a test.
-    python tests/diag_keypoint.py [--cpu-steps K]  -> one JSON line (+ gpurun_out/keypoint_timing.json)
+    python tests/diag_keypoint.py [--cpu-steps K] [--graphs]  -> one JSON line (+ gpurun_out/keypoint_timing.json)
 train: Keypoint_EmbeddingModel.epoch over device-resident batches (3 encoder passes, decoder,
 hinge + MSE losses, backward, AdamW), device generator dropout; CUDA events around 20 steps.
 apply: embed() of 65536 poses. cpu: the oracle port of the same step (torch fp32, all host
@@ -33,6 +33,7 @@ def main():
     cpu_dec = {k: v.clone() for k, v in dec.state_dict().items()}
     model = keypoint.Keypoint_EmbeddingModel(enc, {'3d': dec}, 'cuda')
     opt = model.get_optimizer(1e-4)
+    model._core().use_graphs = '--graphs' in sys.argv
     batches = [{k: v.to(dev) for k, v in T.synth_batch(N, 100 + i).items()} for i in range(4)]
     model.epoch([('h36m', batches[:3])], optimizer=opt)                    # warm-up
     torch.cuda.synchronize()
@@ -49,7 +50,7 @@ def main():
     launches = (lib().call('vpd_launch_count') - l0) / steps
     res = {'train': {'ms_per_step': ms, 'samples_per_s': N / ms * 1e3,
                      'algorithmic_tflops': STEP_GFLOP / ms, 'launches_per_step': launches,
-                     'loss': loss, 'batch': N}}
+                     'loss': loss, 'batch': N, 'cuda_graph_replay': '--graphs' in sys.argv}}
     poses = T.synth_batch(65536, 7, with_neg=False, with_3d=False)['pose1'].to(dev)
     model.embed(poses[:4096])
     torch.cuda.synchronize()

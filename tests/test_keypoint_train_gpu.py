@@ -58,7 +58,7 @@ def test_bn1d_fwd_bwd_against_torch(M, C, drop, res):
     sm, sr = torch.empty(C, device=dev()), torch.empty(C, device=dev())
     out = torch.empty_like(a)
     L.call('vpd_bn1d_fwd', a, stats, gamma, beta, bias, rm, rv, nbt, sm, sr, keep, P if drop else 0.0,
-           r, out, M, C, st)
+           r, out, M, C, 1, st)
     # torch reference on the same bf16-rounded input
     x = af.clone().requires_grad_(True)
     gp, bp = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
@@ -78,13 +78,59 @@ def test_bn1d_fwd_bwd_against_torch(M, C, drop, res):
     dg, db = torch.ones(C, device=dev()), torch.ones(C, device=dev())     # += semantics
     sums = torch.empty(2 * C, device=dev(), dtype=torch.float64)
     L.call('vpd_bn1d_bwd', dz, a, keep, P if drop else 0.0, gamma, beta, sm, sr, sums, da, dg, db,
-           M, C, st)
+           M, C, 1, st)
     msg = 'bn1d M={} C={}: da cos {:.5f}, dgamma cos {:.5f}, dbeta cos {:.5f}'.format(
         M, C, _cos(da.float(), x.grad), _cos(dg - 1, gp.grad), _cos(db - 1, bp.grad))
     _log(msg)
     assert _cos(da.float(), x.grad) > 0.995, msg
     torch.testing.assert_close(dg - 1, gp.grad, rtol=2e-2, atol=2e-2 * float(gp.grad.abs().max()))
     torch.testing.assert_close(db - 1, bp.grad, rtol=2e-2, atol=2e-2 * float(bp.grad.abs().max()))
+
+
+def test_bn1d_row_groups_are_separate_batches():
+    """three stacked encoder passes: per-group batch statistics, running statistics updated
+    group after group, dgamma / dbeta summed over the groups"""
+    L, st = lib(), stream_ptr(dev())
+    G, M, C = 3, 136, 128
+    g = torch.Generator().manual_seed(77)
+    a = _bf(torch.randn((G * M, C), generator=g) * torch.tensor([1.0, 2.0, 0.5]).repeat_interleave(M)[:, None]
+            + torch.tensor([0.0, 1.0, -1.0]).repeat_interleave(M)[:, None])
+    gamma = (torch.rand(C, generator=g) + 0.5).to(dev())
+    beta = (torch.randn(C, generator=g) * 0.3).to(dev())
+    keep = (torch.rand((G * M, C), generator=g) < 0.8).to(torch.uint8).to(dev())
+    dz = _bf(torch.randn((G * M, C), generator=g))
+    stats = torch.empty(G * 2 * C, device=dev(), dtype=torch.float64)
+    L.call('vpd_colstats_bf16', a, stats, M, C, G, st)
+    af = a.float().view(G, M, C)
+    torch.testing.assert_close(stats.view(G, 2, C)[:, 0].float(), af.sum(1), rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(stats.view(G, 2, C)[:, 1].float(), (af ** 2).sum(1), rtol=1e-4, atol=1e-2)
+    rm, rv = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    nbt = torch.zeros((), device=dev(), dtype=torch.int64)
+    sm, sr = torch.empty(G * C, device=dev()), torch.empty(G * C, device=dev())
+    out = torch.empty_like(a)
+    L.call('vpd_bn1d_fwd', a, stats, gamma, beta, None, rm, rv, nbt, sm, sr, keep, P, None, out,
+           M, C, G, st)
+    x = a.float().clone().requires_grad_(True)
+    gp, bp = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    trm, trv = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    ys = []
+    for q in range(G):
+        y = torch.nn.functional.batch_norm(x[q * M:(q + 1) * M], trm, trv, gp, bp, training=True,
+                                           momentum=0.1)
+        ys.append(torch.relu(y) * keep[q * M:(q + 1) * M].float() / (1 - P))
+    y = torch.cat(ys)
+    torch.testing.assert_close(out.float(), y.detach(), rtol=1e-2, atol=2e-2)
+    torch.testing.assert_close(rm, trm, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(rv, trv, rtol=1e-3, atol=1e-4)
+    assert int(nbt) == G
+    y.backward(dz.float())
+    da = torch.empty_like(a)
+    dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+    sums = torch.empty(G * 2 * C, device=dev(), dtype=torch.float64)
+    L.call('vpd_bn1d_bwd', dz, a, keep, P, gamma, beta, sm, sr, sums, da, dg, db, M, C, G, st)
+    assert _cos(da.float(), x.grad) > 0.995
+    torch.testing.assert_close(dg, gp.grad, rtol=2e-2, atol=2e-2 * float(gp.grad.abs().max()))
+    torch.testing.assert_close(db, bp.grad, rtol=2e-2, atol=2e-2 * float(bp.grad.abs().max()))
 
 
 def test_small_ops_against_torch():

@@ -111,17 +111,21 @@ int vpd_dropout_mask(uint8_t* keep, int64_t n, float p_drop, uint64_t seed,
 int vpd_bn1d_fwd(const void* a, const double* stats, const float* gamma, const float* beta,
                  const float* lin_bias, float* running_mean, float* running_var,
                  int64_t* num_batches, float* save_mean, float* save_rstd, const uint8_t* keep,
-                 float p_drop, const void* res, void* out, int64_t M, int C, void* stream) {
+                 float p_drop, const void* res, void* out, int64_t M, int C, int groups,
+                 void* stream) {
   return bn1d_fwd((const bf16*)a, stats, gamma, beta, lin_bias, running_mean, running_var,
                   (long long*)num_batches, save_mean, save_rstd, keep, p_drop, (const bf16*)res,
-                  (bf16*)out, M, C, (cudaStream_t)stream);
+                  (bf16*)out, M, C, groups, (cudaStream_t)stream);
 }
 int vpd_bn1d_bwd(const void* dz, const void* a, const uint8_t* keep, float p_drop,
                  const float* gamma, const float* beta, const float* save_mean,
                  const float* save_rstd, double* sums, void* da, float* dgamma, float* dbeta,
-                 int64_t M, int C, void* stream) {
+                 int64_t M, int C, int groups, void* stream) {
   return bn1d_bwd((const bf16*)dz, (const bf16*)a, keep, p_drop, gamma, beta, save_mean, save_rstd,
-                  sums, (bf16*)da, dgamma, dbeta, M, C, (cudaStream_t)stream);
+                  sums, (bf16*)da, dgamma, dbeta, M, C, groups, (cudaStream_t)stream);
+}
+int vpd_colstats_bf16(const void* x, double* stats, int64_t M, int C, int groups, void* stream) {
+  return colstats_bf16((const bf16*)x, stats, M, C, groups, (cudaStream_t)stream);
 }
 int vpd_relu_mask_bf16(const void* d, const void* z, void* out, int64_t n, void* stream) {
   return relu_mask_bf16((const bf16*)d, (const bf16*)z, (bf16*)out, n, (cudaStream_t)stream);

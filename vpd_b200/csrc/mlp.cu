@@ -184,6 +184,10 @@ struct Bn1dParams {
   float eps, momentum;
 };
 
+// gridDim.y = number of row groups (the weight-sharing encoder passes of one step are stacked
+// along the rows; each group of p.M rows is its own BatchNorm batch): group g owns rows
+// [g*M, (g+1)*M), stats[g], save_mean[g], save_rstd[g]. Running statistics are updated group
+// after group, as the reference's consecutive encoder calls do.
 __global__ void __launch_bounds__(256)
 bn1d_fwd_kernel(const Bn1dParams p) {
   pdl_trigger();
@@ -191,29 +195,42 @@ bn1d_fwd_kernel(const Bn1dParams p) {
   const int groups = p.C >> 3;                    // host: groups <= 256
   const int rstep = 256 / groups;                 // rows per CTA pass; threads beyond are idle
   const int gg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  const int grp = blockIdx.y;
+  const double* stats = p.stats + (size_t)grp * 2 * p.C;
+  const size_t base = (size_t)grp * p.M * p.C;
   if (rl < rstep) {
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = gg * 8 + j;
-      const double mean = p.stats[c] / static_cast<double>(p.M);
-      double var = p.stats[p.C + c] / static_cast<double>(p.M) - mean * mean;
+      const double mean = stats[c] / static_cast<double>(p.M);
+      double var = stats[p.C + c] / static_cast<double>(p.M) - mean * mean;
       if (var < 0.0) var = 0.0;
       const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
       sc[j] = p.gamma[c] * rstd;
       sh[j] = p.beta[c] - static_cast<float>(mean) * sc[j];
       if (blockIdx.x == 0 && rl == 0) {
-        p.save_mean[c] = static_cast<float>(mean);
-        p.save_rstd[c] = rstd;
-        const float bias = p.lin_bias ? p.lin_bias[c] : 0.f;
-        const double unbiased = p.M > 1 ? var * static_cast<double>(p.M) / static_cast<double>(p.M - 1) : var;
-        p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * (static_cast<float>(mean) + bias);
-        p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * static_cast<float>(unbiased);
+        p.save_mean[(size_t)grp * p.C + c] = static_cast<float>(mean);
+        p.save_rstd[(size_t)grp * p.C + c] = rstd;
+        if (grp == 0) {
+          const float bias = p.lin_bias ? p.lin_bias[c] : 0.f;
+          float rm = p.running_mean[c], rv = p.running_var[c];
+          for (int q = 0; q < (int)gridDim.y; ++q) {
+            const double m = p.stats[(size_t)q * 2 * p.C + c] / static_cast<double>(p.M);
+            double v = p.stats[(size_t)q * 2 * p.C + p.C + c] / static_cast<double>(p.M) - m * m;
+            if (v < 0.0) v = 0.0;
+            const double unbiased = p.M > 1 ? v * static_cast<double>(p.M) / static_cast<double>(p.M - 1) : v;
+            rm = (1.f - p.momentum) * rm + p.momentum * (static_cast<float>(m) + bias);
+            rv = (1.f - p.momentum) * rv + p.momentum * static_cast<float>(unbiased);
+          }
+          p.running_mean[c] = rm;
+          p.running_var[c] = rv;
+        }
       }
     }
     const long long r0 = (long long)blockIdx.x * rstep + rl;
     for (long long r = r0; r < p.M; r += (long long)gridDim.x * rstep) {
-      const size_t off = (size_t)r * p.C + gg * 8;
+      const size_t off = base + (size_t)r * p.C + gg * 8;
       const uint4 va = ldg_nc_v4(p.a + off);
       float v[8] = {bf16_lo(va.x), bf16_hi(va.x), bf16_lo(va.y), bf16_hi(va.y),
                     bf16_lo(va.z), bf16_hi(va.z), bf16_lo(va.w), bf16_hi(va.w)};
@@ -235,7 +252,8 @@ bn1d_fwd_kernel(const Bn1dParams p) {
                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7])));
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0 && p.num_batches) *p.num_batches += 1;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && p.num_batches)
+    *p.num_batches += gridDim.y;
 }
 
 struct Bn1dBwdParams {
@@ -255,7 +273,7 @@ struct Bn1dBwdParams {
   int C;
 };
 
-// g = dz * keep * keep_scale * 1[gamma * xhat + beta > 0]
+// g = dz * keep * keep_scale * 1[gamma * xhat + beta > 0]; gridDim.y = row groups (see forward)
 template <bool kApply>
 __global__ void __launch_bounds__(256)
 bn1d_bwd_kernel(const Bn1dBwdParams p) {
@@ -264,22 +282,25 @@ bn1d_bwd_kernel(const Bn1dBwdParams p) {
   const int groups = p.C >> 3;
   const int rstep = 256 / groups;
   const int gg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  const int grp = blockIdx.y;
+  double* sums = p.sums + (size_t)grp * 2 * p.C;
+  const size_t base = (size_t)grp * p.M * p.C;
   if (rl < rstep) {
     float mean[8], rstd[8], ga[8], be[8], k1[8], k2[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = gg * 8 + j;
-      mean[j] = p.save_mean[c];
-      rstd[j] = p.save_rstd[c];
+      mean[j] = p.save_mean[(size_t)grp * p.C + c];
+      rstd[j] = p.save_rstd[(size_t)grp * p.C + c];
       ga[j] = p.gamma[c];
       be[j] = p.beta[c];
-      k1[j] = kApply ? static_cast<float>(p.sums[c] / static_cast<double>(p.M)) : 0.f;
-      k2[j] = kApply ? static_cast<float>(p.sums[p.C + c] / static_cast<double>(p.M)) : 0.f;
+      k1[j] = kApply ? static_cast<float>(sums[c] / static_cast<double>(p.M)) : 0.f;
+      k2[j] = kApply ? static_cast<float>(sums[p.C + c] / static_cast<double>(p.M)) : 0.f;
     }
     float sg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sgx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const long long r0 = (long long)blockIdx.x * rstep + rl;
     for (long long r = r0; r < p.M; r += (long long)gridDim.x * rstep) {
-      const size_t off = (size_t)r * p.C + gg * 8;
+      const size_t off = base + (size_t)r * p.C + gg * 8;
       const uint4 vd = ldg_nc_v4(p.dz + off), va = ldg_nc_v4(p.a + off);
       const float d[8] = {bf16_lo(vd.x), bf16_hi(vd.x), bf16_lo(vd.y), bf16_hi(vd.y),
                           bf16_lo(vd.z), bf16_hi(vd.z), bf16_lo(vd.w), bf16_hi(vd.w)};
@@ -308,15 +329,47 @@ bn1d_bwd_kernel(const Bn1dBwdParams p) {
     if (!kApply) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&p.sums[gg * 8 + j], static_cast<double>(sg[j]));
-        atomicAdd(&p.sums[p.C + gg * 8 + j], static_cast<double>(sgx[j]));
+        atomicAdd(&sums[gg * 8 + j], static_cast<double>(sg[j]));
+        atomicAdd(&sums[p.C + gg * 8 + j], static_cast<double>(sgx[j]));
       }
     } else if (blockIdx.x == 0 && rl == 0) {
+      // the groups (and earlier launches of the step) accumulate into the same dgamma / dbeta
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        p.dbeta[gg * 8 + j] += static_cast<float>(p.sums[gg * 8 + j]);
-        p.dgamma[gg * 8 + j] += static_cast<float>(p.sums[p.C + gg * 8 + j]);
+        atomicAdd(&p.dbeta[gg * 8 + j], static_cast<float>(sums[gg * 8 + j]));
+        atomicAdd(&p.dgamma[gg * 8 + j], static_cast<float>(sums[p.C + gg * 8 + j]));
       }
+    }
+  }
+}
+
+// stats[g][0][c] += sum_r x, stats[g][1][c] += sum_r x^2 over the rows of group g = blockIdx.y
+__global__ void __launch_bounds__(256)
+colstats_bf16_kernel(const __nv_bfloat16* __restrict__ x, double* stats, long long M, int C) {
+  pdl_trigger();
+  pdl_wait();
+  const int groups = C >> 3;
+  const int rstep = 256 / groups;
+  const int gg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  const int grp = blockIdx.y;
+  if (rl < rstep) {
+    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const long long r0 = (long long)blockIdx.x * rstep + rl;
+    for (long long r = r0; r < M; r += (long long)gridDim.x * rstep) {
+      const uint4 v = ldg_nc_v4(x + ((size_t)grp * M + r) * C + gg * 8);
+      const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                          bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] = fmaf(f[j], f[j], q[j]);
+      }
+    }
+    double* st = stats + (size_t)grp * 2 * C;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&st[gg * 8 + j], static_cast<double>(s[j]));
+      atomicAdd(&st[C + gg * 8 + j], static_cast<double>(q[j]));
     }
   }
 }
@@ -533,9 +586,10 @@ int dropout_mask(uint8_t* keep, long long n, float p_drop, unsigned long long se
 int bn1d_fwd(const __nv_bfloat16* a, const double* stats, const float* gamma, const float* beta,
              const float* lin_bias, float* running_mean, float* running_var, long long* num_batches,
              float* save_mean, float* save_rstd, const uint8_t* keep, float p_drop,
-             const __nv_bfloat16* res, __nv_bfloat16* out, long long M, int C, cudaStream_t stream) {
+             const __nv_bfloat16* res, __nv_bfloat16* out, long long M, int C, int groups,
+             cudaStream_t stream) {
   VPD_ROWS_OK(C);
-  VPD_REQUIRE(M >= 1, "bn1d_fwd: empty batch");
+  VPD_REQUIRE(M >= 1 && groups >= 1 && groups <= 64, "bn1d_fwd: empty batch / bad group count");
   VPD_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "bn1d_fwd: p must be in [0, 1)");
   Bn1dParams p;
   p.a = a; p.stats = stats; p.gamma = gamma; p.beta = beta; p.lin_bias = lin_bias;
@@ -543,7 +597,7 @@ int bn1d_fwd(const __nv_bfloat16* a, const double* stats, const float* gamma, co
   p.save_mean = save_mean; p.save_rstd = save_rstd; p.keep = keep;
   p.keep_scale = 1.f / (1.f - p_drop);
   p.res = res; p.out = out; p.M = M; p.C = C; p.eps = 1e-5f; p.momentum = 0.1f;
-  VPD_CHECK_CUDA(launch_kernel(bn1d_fwd_kernel, dim3(rows_grid(M, C)), dim3(256), 0, stream, p));
+  VPD_CHECK_CUDA(launch_kernel(bn1d_fwd_kernel, dim3(rows_grid(M, C, 148 * 4 / groups + 1), groups), dim3(256), 0, stream, p));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -551,18 +605,28 @@ int bn1d_fwd(const __nv_bfloat16* a, const double* stats, const float* gamma, co
 int bn1d_bwd(const __nv_bfloat16* dz, const __nv_bfloat16* a, const uint8_t* keep, float p_drop,
              const float* gamma, const float* beta, const float* save_mean, const float* save_rstd,
              double* sums, __nv_bfloat16* da, float* dgamma, float* dbeta, long long M, int C,
-             cudaStream_t stream) {
+             int groups, cudaStream_t stream) {
   VPD_ROWS_OK(C);
-  VPD_REQUIRE(M >= 1, "bn1d_bwd: empty batch");
+  VPD_REQUIRE(M >= 1 && groups >= 1 && groups <= 64, "bn1d_bwd: empty batch / bad group count");
   Bn1dBwdParams p;
   p.dz = dz; p.a = a; p.keep = keep; p.keep_scale = 1.f / (1.f - p_drop);
   p.gamma = gamma; p.beta = beta; p.save_mean = save_mean; p.save_rstd = save_rstd;
   p.sums = sums; p.da = da; p.dgamma = dgamma; p.dbeta = dbeta; p.M = M; p.C = C;
   // a kernel, not a memset node: the step is captured into a CUDA graph with programmatic edges
-  VPD_CHECK_CUDA(launch_kernel(zero_f64_kernel, dim3((2 * C + 255) / 256), dim3(256), 0, stream, sums, 2 * C));
-  VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<false>, dim3(rows_grid(M, C, kReduceCtas)), dim3(256), 0, stream, p));
-  VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<true>, dim3(rows_grid(M, C)), dim3(256), 0, stream, p));
+  VPD_CHECK_CUDA(launch_kernel(zero_f64_kernel, dim3((2 * C * groups + 255) / 256), dim3(256), 0, stream, sums, 2 * C * groups));
+  VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<false>, dim3(rows_grid(M, C, kReduceCtas / groups + 1), groups), dim3(256), 0, stream, p));
+  VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<true>, dim3(rows_grid(M, C, 148 * 4 / groups + 1), groups), dim3(256), 0, stream, p));
   VPD_LAUNCHED(3);
+  return 0;
+}
+
+int colstats_bf16(const __nv_bfloat16* x, double* stats, long long M, int C, int groups,
+                  cudaStream_t stream) {
+  VPD_ROWS_OK(C);
+  VPD_REQUIRE(M >= 1 && groups >= 1 && groups <= 64, "colstats: empty batch / bad group count");
+  VPD_CHECK_CUDA(launch_kernel(zero_f64_kernel, dim3((2 * C * groups + 255) / 256), dim3(256), 0, stream, stats, 2 * C * groups));
+  VPD_CHECK_CUDA(launch_kernel(colstats_bf16_kernel, dim3(rows_grid(M, C, kReduceCtas / groups + 1), groups), dim3(256), 0, stream, x, stats, M, C));
+  VPD_LAUNCHED(2);
   return 0;
 }
 

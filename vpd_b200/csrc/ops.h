@@ -54,11 +54,14 @@ int dropout_mask(uint8_t* keep, long long n, float p_drop, unsigned long long se
 int bn1d_fwd(const __nv_bfloat16* a, const double* stats, const float* gamma, const float* beta,
              const float* lin_bias, float* running_mean, float* running_var, long long* num_batches,
              float* save_mean, float* save_rstd, const uint8_t* keep, float p_drop,
-             const __nv_bfloat16* res, __nv_bfloat16* out, long long M, int C, cudaStream_t stream);
+             const __nv_bfloat16* res, __nv_bfloat16* out, long long M, int C, int groups,
+             cudaStream_t stream);
 int bn1d_bwd(const __nv_bfloat16* dz, const __nv_bfloat16* a, const uint8_t* keep, float p_drop,
              const float* gamma, const float* beta, const float* save_mean, const float* save_rstd,
              double* sums, __nv_bfloat16* da, float* dgamma, float* dbeta, long long M, int C,
-             cudaStream_t stream);
+             int groups, cudaStream_t stream);
+int colstats_bf16(const __nv_bfloat16* x, double* stats, long long M, int C, int groups,
+                  cudaStream_t stream);
 int relu_mask_bf16(const __nv_bfloat16* d, const __nv_bfloat16* z, __nv_bfloat16* out, long long n,
                    cudaStream_t stream);
 int colsum_bf16(const __nv_bfloat16* x, float* out, long long M, int C, cudaStream_t stream);

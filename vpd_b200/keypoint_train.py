@@ -276,15 +276,18 @@ class KeypointTrainCore:
         return keep
 
     # ---- encoder ---------------------------------------------------------------------------
-    def encoder_forward(self, pose, masks=None):
-        """train-mode pass: pose fp32 [n, in_dim] -> (emb fp32 [n, D], ctx for the backward).
-        masks: list of 2 * num_blocks uint8 [n, H] keep masks, or None (device generator)."""
+    def encoder_forward(self, pose, groups=1, masks=None):
+        """train-mode pass over `groups` stacked pose batches: pose fp32 [groups * n, in_dim]
+        (the weight-sharing passes pose1 / pose2 / pose_neg of one step share every launch;
+        each block of n rows is its own BatchNorm batch) -> (emb fp32 [groups * n, D], ctx).
+        masks: 2 * num_blocks uint8 [groups * n, H] keep masks, or None (device generator)."""
         L, st, H, enc = lib(), self._st(), self.H, self.enc
-        n = pose.shape[0]
-        ctx = {'n': n, 'blocks': []}
-        xb = self._bf(n, self.cin)
-        L.call('vpd_rows_to_bf16', pose.contiguous(), xb, n, enc.in_dim, self.cin, st)
-        h = self._bf(n, H)
+        N = pose.shape[0]
+        n = N // groups
+        ctx = {'n': n, 'N': N, 'groups': groups, 'blocks': []}
+        xb = self._bf(N, self.cin)
+        L.call('vpd_rows_to_bf16', pose.contiguous(), xb, N, enc.in_dim, self.cin, st)
+        h = self._bf(N, H)
         self._fwd(xb, 'enc.layers.0', h, relu=True)
         ctx['xb'], ctx['h0'] = xb, h
         sd = enc._sd
@@ -293,58 +296,59 @@ class KeypointTrainCore:
             blk = {'h_in': h, 'stage': []}
             z = h
             for j, (lin, bn) in enumerate(((0, 1), (4, 5))):
-                a = self._bf(n, H)
-                stats = torch.zeros(2 * H, device=self.dev, dtype=torch.float64)
-                self._fwd(z, 'enc.{}.{}'.format(p, lin), a, relu=False, stats=stats)
-                keep = self._mask(n, None if masks is None else masks[2 * i + j])
-                out = self._bf(n, H)
+                a = self._bf(N, H)
+                self._fwd(z, 'enc.{}.{}'.format(p, lin), a, relu=False, bias=False)
+                stats = torch.empty(groups * 2 * H, device=self.dev, dtype=torch.float64)
+                L.call('vpd_colstats_bf16', a, stats, n, H, groups, st)
+                keep = self._mask(N, None if masks is None else masks[2 * i + j])
+                out = self._bf(N, H)
                 b = '{}.{}'.format(p, bn)
-                save_mean = torch.empty(H, device=self.dev)
-                save_rstd = torch.empty(H, device=self.dev)
+                save_mean = torch.empty(groups * H, device=self.dev)
+                save_rstd = torch.empty(groups * H, device=self.dev)
                 L.call('vpd_bn1d_fwd', a, stats, sd[b + '.weight'], sd[b + '.bias'],
                        sd['{}.{}.bias'.format(p, lin)], sd[b + '.running_mean'],
                        sd[b + '.running_var'], sd[b + '.num_batches_tracked'], save_mean, save_rstd,
-                       keep, self.p_drop, h if j == 1 else None, out, n, H, st)
+                       keep, self.p_drop, h if j == 1 else None, out, n, H, groups, st)
                 blk['stage'].append({'x': z, 'a': a, 'keep': keep, 'mean': save_mean,
                                      'rstd': save_rstd, 'lin': 'enc.{}.{}'.format(p, lin),
                                      'bn': 'enc.' + b})
                 z = out
             h = z
             ctx['blocks'].append(blk)
-        emb = torch.empty((n, self.D), device=self.dev, dtype=torch.float32)
+        emb = torch.empty((N, self.D), device=self.dev, dtype=torch.float32)
         L.call('vpd_linear_rows_f32', h, self.arena.view(self.last + '.weight'),
-               self.arena.view(self.last + '.bias'), emb, n, H, self.D, st)
+               self.arena.view(self.last + '.bias'), emb, N, H, self.D, st)
         ctx['h_last'] = h
         return emb, ctx
 
     def encoder_backward(self, ctx, de_bf16):
-        """de_bf16: bf16 [n, 64] gradient of the embedding (columns >= D zero)"""
-        L, st, H, n = lib(), self._st(), self.H, ctx['n']
-        dh = self._bf(n, H)
+        """de_bf16: bf16 [groups * n, 64] gradient of the embeddings (columns >= D zero)"""
+        L, st, H, n, N, G = lib(), self._st(), self.H, ctx['n'], ctx['N'], ctx['groups']
+        dh = self._bf(N, H)
         self._bwd_linear(ctx['h_last'], de_bf16, self.last, dx=dh)
-        sums = torch.empty(2 * H, device=self.dev, dtype=torch.float64)
+        sums = torch.empty(G * 2 * H, device=self.dev, dtype=torch.float64)
         for blk in reversed(ctx['blocks']):
             s2, s1 = blk['stage'][1], blk['stage'][0]
-            da2 = self._bf(n, H)
-            self._bn_bwd(dh, s2, sums, da2)
-            dz1 = self._bf(n, H)
+            da2 = self._bf(N, H)
+            self._bn_bwd(dh, s2, sums, da2, n, G)
+            dz1 = self._bf(N, H)
             self._bwd_linear(s2['x'], da2, s2['lin'], dx=dz1, bias=False)
-            da1 = self._bf(n, H)
-            self._bn_bwd(dz1, s1, sums, da1)
-            neg = self._bf(n, H)
-            L.call('vpd_axpby_bf16', dh, -1.0, None, 0.0, neg, n * H, st)       # d(x2 - x)/dx
-            dh_in = self._bf(n, H)
+            da1 = self._bf(N, H)
+            self._bn_bwd(dz1, s1, sums, da1, n, G)
+            neg = self._bf(N, H)
+            L.call('vpd_axpby_bf16', dh, -1.0, None, 0.0, neg, N * H, st)       # d(x2 - x)/dx
+            dh_in = self._bf(N, H)
             self._bwd_linear(s1['x'], da1, s1['lin'], dx=dh_in, residual=neg, bias=False)
             dh = dh_in
-        dpre = self._bf(n, H)
-        L.call('vpd_relu_mask_bf16', dh, ctx['h0'], dpre, n * H, st)
+        dpre = self._bf(N, H)
+        L.call('vpd_relu_mask_bf16', dh, ctx['h0'], dpre, N * H, st)
         self._bwd_linear(ctx['xb'], dpre, 'enc.layers.0')
 
-    def _bn_bwd(self, dz, s, sums, da):
+    def _bn_bwd(self, dz, s, sums, da, n, groups):
         g = lambda k: self.arena.full(s['bn'] + k)
         lib().call('vpd_bn1d_bwd', dz, s['a'], s['keep'], self.p_drop, g('.weight'), g('.bias'),
                    s['mean'], s['rstd'], sums, da, self.arena.full(s['bn'] + '.weight', grad=True),
-                   self.arena.full(s['bn'] + '.bias', grad=True), dz.shape[0], self.H, self._st())
+                   self.arena.full(s['bn'] + '.bias', grad=True), n, self.H, groups, self._st())
 
     # ---- decoder ---------------------------------------------------------------------------
     def decoder_forward(self, emb, target):
@@ -364,8 +368,9 @@ class KeypointTrainCore:
         self._fwd(acts[-1], name, pred, relu=False)
         return pred, {'acts': acts, 'head': name, 'n': n}
 
-    def decoder_backward(self, ctx, dpred, de_contra_bf16):
-        """-> bf16 [n, 64]: decoder gradient of the embedding + de_contra"""
+    def decoder_backward(self, ctx, dpred, de_contra_bf16, out=None):
+        """-> bf16 [n, 64] (written into `out` if given): decoder gradient of the embedding +
+        de_contra"""
         L, st, n = lib(), self._st(), ctx['n']
         acts = ctx['acts']
         d = self._bf(n, acts[-1].shape[1])
@@ -373,7 +378,7 @@ class KeypointTrainCore:
         for i in range(len(self.dec.fcn_keys) - 1, -1, -1):
             dm = self._bf(*d.shape)
             L.call('vpd_relu_mask_bf16', d, acts[i + 1], dm, dm.numel(), st)
-            dx = self._bf(n, acts[i].shape[1])
+            dx = out if (i == 0 and out is not None) else self._bf(n, acts[i].shape[1])
             self._bwd_linear(acts[i], dm, 'dec.' + self.dec.fcn_keys[i], dx=dx,
                              residual=de_contra_bf16 if i == 0 else None)
             d = dx
@@ -417,37 +422,46 @@ class KeypointTrainCore:
         L, st, D = lib(), self._st(), self.D
         n = batch['pose1'].shape[0]
         names = [k for k in ('pose1', 'pose2', 'pose_neg') if k in batch]
-        embs, ctxs = {}, {}
-        for j, k in enumerate(names):
-            if train:
-                m = None if masks is None else masks[j]
-                embs[k], ctxs[k] = self.encoder_forward(batch[k], m)
-            else:                      # evaluation: running statistics, no dropout
-                embs[k] = self.enc.eval().forward(batch[k])
+        G = len(names)
+        # the weight-sharing passes are stacked along the rows: one launch per layer for all
+        pose = batch[names[0]] if G == 1 else torch.cat([batch[k] for k in names])
+        if train:
+            m = None
+            if masks is not None:      # [pass][layer] -> [layer] stacked like the poses
+                m = [torch.cat([masks[g][l] for g in range(G)]).contiguous()
+                     for l in range(2 * self.enc.num_blocks)]
+            emb, ctx = self.encoder_forward(pose, G, m)
+        else:                          # evaluation: running statistics, no dropout
+            emb = self.enc.eval().forward(pose)
+        rows = {k: slice(i * n, (i + 1) * n) for i, k in enumerate(names)}
         has3d = 'kp_features' in batch
-        preds, dctx = {}, {}
+        nd = (1 + ('pose2' in rows)) if has3d else 0            # decoder: pose1 (+ pose2) rows
+        pred = dctx = None
         if has3d:
-            for k in ('pose1', 'pose2'):
-                if k in embs:
-                    preds[k], dctx[k] = self.decoder_forward(embs[k], target)
-        f32 = lambda: torch.empty((n, D), device=self.dev, dtype=torch.float32)
-        de = {k: f32() for k in names}
-        dpred = {k: torch.empty_like(v) for k, v in preds.items()}
+            pred, dctx = self.decoder_forward(emb[:nd * n], target)
+        de = torch.empty((G * n, D), device=self.dev, dtype=torch.float32)
+        dpred = torch.empty_like(pred) if has3d else None
         true3d = batch['kp_features'].reshape(n, -1).contiguous() if has3d else None
         T = true3d.shape[1] if has3d else 0
-        tpad = preds['pose1'].shape[1] if has3d else 0
-        L.call('vpd_vipe_loss', embs['pose1'], embs.get('pose2'), embs.get('pose_neg'),
-               batch.get('pose_neg_is_valid'), preds.get('pose1'), preds.get('pose2'), true3d,
-               de['pose1'], de.get('pose2'), de.get('pose_neg'), dpred.get('pose1'),
-               dpred.get('pose2'), self.loss_sums, n, D, T, tpad, float(weight_3d), float(gscale), st)
+        tpad = pred.shape[1] if has3d else 0
+        part = lambda t, k: t[rows[k]] if (t is not None and k in rows) else None
+        two = has3d and nd == 2
+        L.call('vpd_vipe_loss', emb[rows['pose1']], part(emb, 'pose2'), part(emb, 'pose_neg'),
+               batch.get('pose_neg_is_valid'), pred[:n] if has3d else None,
+               pred[n:2 * n] if two else None, true3d, de[rows['pose1']], part(de, 'pose2'),
+               part(de, 'pose_neg'), dpred[:n] if has3d else None, dpred[n:2 * n] if two else None,
+               self.loss_sums, n, D, T, tpad, float(weight_3d), float(gscale), st)
         if not train:
             return n
-        for k in names:
-            db = self._bf(n, 64)
-            L.call('vpd_rows_to_bf16', de[k], db, n, D, 64, st)
-            if k in dctx:
-                db = self.decoder_backward(dctx[k], dpred[k], db)
-            self.encoder_backward(ctxs[k], db)
+        db = self._bf(G * n, 64)
+        L.call('vpd_rows_to_bf16', de, db, G * n, D, 64, st)
+        if has3d:
+            tot = self._bf(G * n, 64)
+            self.decoder_backward(dctx, dpred, db[:nd * n], out=tot[:nd * n])
+            if nd < G:
+                tot[nd * n:].copy_(db[nd * n:])
+            db = tot
+        self.encoder_backward(ctx, db)
         return n
 
 
