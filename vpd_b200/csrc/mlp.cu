@@ -74,24 +74,28 @@ bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
 // CTA = 32 rows x 256 threads; thread (r = tid / 8, q = tid % 8) owns outputs d = q, q+8, ...
 constexpr int kLinRows = 32;
 constexpr int kLinK = 64;
+constexpr int kLinStride = kLinK + 4;   // rows stay 16-byte aligned; float4 reads conflict-free
 __global__ void __launch_bounds__(256)
 linear_rows_f32_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                        const float* __restrict__ bias, float* __restrict__ out, long long M,
                        int K, int D) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float s_w[64][kLinK + 1];
-  __shared__ float s_x[kLinRows][kLinK + 1];
+  __shared__ __align__(16) float s_w[64][kLinStride];
+  __shared__ __align__(16) float s_x[kLinRows][kLinStride];
   const int tid = threadIdx.x;
   const int r = tid >> 3, q = tid & 7;
   const long long row0 = (long long)blockIdx.x * kLinRows;
+  const int nj = (D + 7) >> 3;
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
   for (int k0 = 0; k0 < K; k0 += kLinK) {
-    for (int i = tid; i < D * kLinK; i += 256) {
-      const int d = i / kLinK, k = i - d * kLinK;
-      s_w[d][k] = __ldg(w + (size_t)d * K + k0 + k);
+    for (int i = tid; i < 64 * (kLinK / 4); i += 256) {
+      const int d = i / (kLinK / 4), k4 = i - d * (kLinK / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (d < D) v = __ldg(reinterpret_cast<const float4*>(w + (size_t)d * K + k0) + k4);
+      *reinterpret_cast<float4*>(&s_w[d][k4 * 4]) = v;
     }
     for (int i = tid; i < kLinRows * (kLinK / 8); i += 256) {
       const int rr = i / (kLinK / 8), g = i - rr * (kLinK / 8);
@@ -101,15 +105,20 @@ linear_rows_f32_kernel(const __nv_bfloat16* __restrict__ x, const float* __restr
         v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
         v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s_x[rr][g * 8 + j] = v[j];
+      *reinterpret_cast<float4*>(&s_x[rr][g * 8]) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(&s_x[rr][g * 8 + 4]) = make_float4(v[4], v[5], v[6], v[7]);
     }
     __syncthreads();
-    for (int k = 0; k < kLinK; ++k) {
-      const float xv = s_x[r][k];
+#pragma unroll 4
+    for (int k = 0; k < kLinK; k += 4) {
+      const float4 xv = *reinterpret_cast<const float4*>(&s_x[r][k]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (q + 8 * j < D) acc[j] = fmaf(xv, s_w[q + 8 * j][k], acc[j]);
+      for (int j = 0; j < 8; ++j) {
+        if (j < nj) {   // uniform: rows >= D of s_w are zero padding
+          const float4 wv = *reinterpret_cast<const float4*>(&s_w[q + 8 * j][k]);
+          acc[j] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, acc[j]))));
+        }
+      }
     }
     __syncthreads();
   }
@@ -343,20 +352,101 @@ bn1d_bwd_kernel(const Bn1dBwdParams p) {
   }
 }
 
-// stats[g][0][c] += sum_r x, stats[g][1][c] += sum_r x^2 over the rows of group g = blockIdx.y
+// Column reductions share one mapping: a CTA owns `ccta` (<= 256) adjacent columns of one row
+// group (blockIdx.z = column chunk, blockIdx.y = row group) and 256 / (ccta / 8) row lanes, so
+// even a 1024-wide tensor keeps >= 8 rows per CTA in flight; the row lanes are combined in
+// shared memory and each column ends in ONE atomic per CTA.
+struct RedMap {
+  int cg, rstep, gl, rl, gg;
+};
+VPD_DEVINL RedMap red_map(int ccta) {
+  RedMap m;
+  m.cg = ccta >> 3;
+  m.rstep = 256 / m.cg;
+  m.gl = threadIdx.x % m.cg;
+  m.rl = threadIdx.x / m.cg;
+  m.gg = blockIdx.z * m.cg + m.gl;
+  return m;
+}
+// combine the row lanes' partials (a[8], b[8] per thread) and hand column c's totals to f(c, sa, sb)
+template <typename F>
+VPD_DEVINL void red_finish(const RedMap& m, int ccta, const float* a, const float* b, bool two, F f) {
+  __shared__ float s_a[2048], s_b[2048];
+  if (m.rl < m.rstep) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s_a[m.rl * ccta + m.gl * 8 + j] = a[j];
+      if (two) s_b[m.rl * ccta + m.gl * 8 + j] = b[j];
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < ccta) {
+    float sa = 0.f, sb = 0.f;
+    for (int l = 0; l < m.rstep; ++l) {
+      sa += s_a[l * ccta + threadIdx.x];
+      if (two) sb += s_b[l * ccta + threadIdx.x];
+    }
+    f(blockIdx.z * ccta + threadIdx.x, sa, sb);
+  }
+}
+
 __global__ void __launch_bounds__(256)
-colstats_bf16_kernel(const __nv_bfloat16* __restrict__ x, double* stats, long long M, int C) {
+bn1d_bwd_reduce_kernel(const Bn1dBwdParams p, int ccta) {
   pdl_trigger();
   pdl_wait();
-  const int groups = C >> 3;
-  const int rstep = 256 / groups;
-  const int gg = threadIdx.x % groups, rl = threadIdx.x / groups;
+  const RedMap m = red_map(ccta);
   const int grp = blockIdx.y;
-  if (rl < rstep) {
-    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const long long r0 = (long long)blockIdx.x * rstep + rl;
-    for (long long r = r0; r < M; r += (long long)gridDim.x * rstep) {
-      const uint4 v = ldg_nc_v4(x + ((size_t)grp * M + r) * C + gg * 8);
+  double* sums = p.sums + (size_t)grp * 2 * p.C;
+  const size_t base = (size_t)grp * p.M * p.C;
+  float sg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sgx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (m.rl < m.rstep) {
+    float mean[8], rstd[8], ga[8], be[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = m.gg * 8 + j;
+      mean[j] = p.save_mean[(size_t)grp * p.C + c];
+      rstd[j] = p.save_rstd[(size_t)grp * p.C + c];
+      ga[j] = p.gamma[c];
+      be[j] = p.beta[c];
+    }
+    for (long long r = (long long)blockIdx.x * m.rstep + m.rl; r < p.M; r += (long long)gridDim.x * m.rstep) {
+      const size_t off = base + (size_t)r * p.C + m.gg * 8;
+      const uint4 vd = ldg_nc_v4(p.dz + off), va = ldg_nc_v4(p.a + off);
+      const float d[8] = {bf16_lo(vd.x), bf16_hi(vd.x), bf16_lo(vd.y), bf16_hi(vd.y),
+                          bf16_lo(vd.z), bf16_hi(vd.z), bf16_lo(vd.w), bf16_hi(vd.w)};
+      const float av[8] = {bf16_lo(va.x), bf16_hi(va.x), bf16_lo(va.y), bf16_hi(va.y),
+                           bf16_lo(va.z), bf16_hi(va.z), bf16_lo(va.w), bf16_hi(va.w)};
+      unsigned long long kp = 0x0101010101010101ull;
+      if (p.keep) kp = *reinterpret_cast<const unsigned long long*>(p.keep + off);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float sc = ga[j] * rstd[j];
+        const float pre = fmaf(av[j], sc, be[j] - mean[j] * sc);   // same expression as forward
+        const float xh = (av[j] - mean[j]) * rstd[j];
+        const float gr = (pre > 0.f && ((kp >> (8 * j)) & 0xff)) ? d[j] * p.keep_scale : 0.f;
+        sg[j] += gr;
+        sgx[j] = fmaf(gr, xh, sgx[j]);
+      }
+    }
+  }
+  const int C = p.C;
+  red_finish(m, ccta, sg, sgx, true, [sums, C](int c, float a, float b) {
+    atomicAdd(&sums[c], static_cast<double>(a));
+    atomicAdd(&sums[C + c], static_cast<double>(b));
+  });
+}
+
+// stats[g][0][c] += sum_r x, stats[g][1][c] += sum_r x^2 over the rows of group g = blockIdx.y
+__global__ void __launch_bounds__(256)
+colstats_bf16_kernel(const __nv_bfloat16* __restrict__ x, double* stats, long long M, int C, int ccta) {
+  pdl_trigger();
+  pdl_wait();
+  const RedMap m = red_map(ccta);
+  const int grp = blockIdx.y;
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, q[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (m.rl < m.rstep) {
+    for (long long r = (long long)blockIdx.x * m.rstep + m.rl; r < M; r += (long long)gridDim.x * m.rstep) {
+      const uint4 v = ldg_nc_v4(x + ((size_t)grp * M + r) * C + m.gg * 8);
       const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
                           bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
 #pragma unroll
@@ -365,13 +455,12 @@ colstats_bf16_kernel(const __nv_bfloat16* __restrict__ x, double* stats, long lo
         q[j] = fmaf(f[j], f[j], q[j]);
       }
     }
-    double* st = stats + (size_t)grp * 2 * C;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&st[gg * 8 + j], static_cast<double>(s[j]));
-      atomicAdd(&st[C + gg * 8 + j], static_cast<double>(q[j]));
-    }
   }
+  double* st = stats + (size_t)grp * 2 * C;
+  red_finish(m, ccta, s, q, true, [st, C](int c, float a, float b) {
+    atomicAdd(&st[c], static_cast<double>(a));
+    atomicAdd(&st[C + c], static_cast<double>(b));
+  });
 }
 
 // out = d * 1[z > 0]
@@ -390,23 +479,19 @@ relu_mask_kernel(const __nv_bfloat16* __restrict__ d, const __nv_bfloat16* __res
 
 // out[c] += sum over rows of x[r][c]   (x bf16 [M][C], C % 8 == 0)
 __global__ void __launch_bounds__(256)
-colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* out, long long M, int C) {
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, float* out, long long M, int C, int ccta) {
   pdl_trigger();
   pdl_wait();
-  const int groups = C >> 3;
-  const int rstep = 256 / groups;
-  const int gg = threadIdx.x % groups, rl = threadIdx.x / groups;
-  if (rl < rstep) {
-    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const long long r0 = (long long)blockIdx.x * rstep + rl;
-    for (long long r = r0; r < M; r += (long long)gridDim.x * rstep) {
-      const uint4 v = ldg_nc_v4(x + (size_t)r * C + gg * 8);
+  const RedMap m = red_map(ccta);
+  float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (m.rl < m.rstep) {
+    for (long long r = (long long)blockIdx.x * m.rstep + m.rl; r < M; r += (long long)gridDim.x * m.rstep) {
+      const uint4 v = ldg_nc_v4(x + (size_t)r * C + m.gg * 8);
       s[0] += bf16_lo(v.x); s[1] += bf16_hi(v.x); s[2] += bf16_lo(v.y); s[3] += bf16_hi(v.y);
       s[4] += bf16_lo(v.z); s[5] += bf16_hi(v.z); s[6] += bf16_lo(v.w); s[7] += bf16_hi(v.w);
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(out + gg * 8 + j, s[j]);
   }
+  red_finish(m, ccta, s, s, false, [out](int c, float a, float) { atomicAdd(out + c, a); });
 }
 
 // Loss head of Keypoint_EmbeddingModel.epoch (models/keypoint.py:58-104), one warp per sample:
@@ -568,8 +653,21 @@ static unsigned rows_grid(long long M, int C, long long cap = 148 * 4) {
   if (blocks < 1) blocks = 1;
   return (unsigned)blocks;
 }
-// reductions end in one atomic per thread and column: fewer, longer-running CTAs
-constexpr long long kReduceCtas = 74;
+// column-reduction launches: columns per CTA (<= 256, divides C) and the (x, y, z) grid
+static int red_ccta(int C) {
+  if (C <= 256) return C;
+  for (int c = 256; c >= 8; c -= 8)
+    if (C % c == 0) return c;
+  return 8;
+}
+static dim3 red_grid(long long M, int C, int groups) {
+  const int ccta = red_ccta(C), nz = C / ccta, rstep = 256 / (ccta / 8);
+  long long nx = 296 / ((long long)groups * nz);
+  const long long need = (M + rstep - 1) / rstep;
+  if (nx > need) nx = need;
+  if (nx < 1) nx = 1;
+  return dim3((unsigned)nx, (unsigned)groups, (unsigned)nz);
+}
 #define VPD_ROWS_OK(C) VPD_REQUIRE((C) >= 8 && (C) % 8 == 0 && (C) <= 2048, "row kernels: C %% 8 == 0, C <= 2048 (got %d)", (C))
 
 int dropout_mask(uint8_t* keep, long long n, float p_drop, unsigned long long seed,
@@ -614,7 +712,7 @@ int bn1d_bwd(const __nv_bfloat16* dz, const __nv_bfloat16* a, const uint8_t* kee
   p.sums = sums; p.da = da; p.dgamma = dgamma; p.dbeta = dbeta; p.M = M; p.C = C;
   // a kernel, not a memset node: the step is captured into a CUDA graph with programmatic edges
   VPD_CHECK_CUDA(launch_kernel(zero_f64_kernel, dim3((2 * C * groups + 255) / 256), dim3(256), 0, stream, sums, 2 * C * groups));
-  VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<false>, dim3(rows_grid(M, C, kReduceCtas / groups + 1), groups), dim3(256), 0, stream, p));
+  VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_reduce_kernel, red_grid(M, C, groups), dim3(256), 0, stream, p, red_ccta(C)));
   VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<true>, dim3(rows_grid(M, C, 148 * 4 / groups + 1), groups), dim3(256), 0, stream, p));
   VPD_LAUNCHED(3);
   return 0;
@@ -625,7 +723,7 @@ int colstats_bf16(const __nv_bfloat16* x, double* stats, long long M, int C, int
   VPD_ROWS_OK(C);
   VPD_REQUIRE(M >= 1 && groups >= 1 && groups <= 64, "colstats: empty batch / bad group count");
   VPD_CHECK_CUDA(launch_kernel(zero_f64_kernel, dim3((2 * C * groups + 255) / 256), dim3(256), 0, stream, stats, 2 * C * groups));
-  VPD_CHECK_CUDA(launch_kernel(colstats_bf16_kernel, dim3(rows_grid(M, C, kReduceCtas / groups + 1), groups), dim3(256), 0, stream, x, stats, M, C));
+  VPD_CHECK_CUDA(launch_kernel(colstats_bf16_kernel, red_grid(M, C, groups), dim3(256), 0, stream, x, stats, M, C, red_ccta(C)));
   VPD_LAUNCHED(2);
   return 0;
 }
@@ -643,7 +741,7 @@ int relu_mask_bf16(const __nv_bfloat16* d, const __nv_bfloat16* z, __nv_bfloat16
 int colsum_bf16(const __nv_bfloat16* x, float* out, long long M, int C, cudaStream_t stream) {
   VPD_ROWS_OK(C);
   if (M <= 0) return 0;
-  VPD_CHECK_CUDA(launch_kernel(colsum_bf16_kernel, dim3(rows_grid(M, C, kReduceCtas)), dim3(256), 0, stream, x, out, M, C));
+  VPD_CHECK_CUDA(launch_kernel(colsum_bf16_kernel, red_grid(M, C, 1), dim3(256), 0, stream, x, out, M, C, red_ccta(C)));
   VPD_LAUNCHED(1);
   return 0;
 }
