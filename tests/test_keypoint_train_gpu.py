@@ -189,6 +189,7 @@ def test_vipe_loss_against_torch_autograd(full):
             torch.norm(a - c, dim=1), -torch.ones(n, device=dev()), reduction='none') * valid)
         loss = contra + w3d * (F.mse_loss(q1, true3d, reduction='sum') + F.mse_loss(q2, true3d, reduction='sum'))
     (loss * gs).backward()
+    contra, loss = contra.detach(), loss.detach()
     assert abs(float(sums[0]) - float(contra)) <= 1e-5 * abs(float(contra))
     assert abs(float(sums[1]) - float(loss)) <= 1e-4 * abs(float(loss))
     torch.testing.assert_close(de1, a.grad, rtol=1e-4, atol=1e-7)
