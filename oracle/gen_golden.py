@@ -318,6 +318,19 @@ def gen_keypoint(ref):
             embs.append((frame, torch.randn(32, generator=g).numpy(),
                          {'kp_score': float(torch.rand(1, generator=g)), 'is_mean': False,
                           'is_flip': fl}))
+    # normalize_2d_skeleton on synthetic COCO detections (pixel coordinates), all four variants
+    from vipe_dataset.dataset_base import normalize_2d_skeleton
+    g2 = torch.Generator().manual_seed(10)
+    kp = torch.rand((6, 17, 3), generator=g2)
+    kp[:, :, :2] = kp[:, :, :2] * 300 + 50
+    kp[5, [5, 6, 11, 12], :2] = 77.0                     # degenerate torso: zero extent
+    kp = kp.numpy()
+    out['skel_in'] = kp
+    for fl in (False, True):
+        for bones in (False, True):
+            out['skel_f{}_b{}'.format(int(fl), int(bones))] = np.stack([
+                normalize_2d_skeleton(kp[i], fl, include_bone_features=bones).numpy()
+                for i in range(6)])
     res = apply_vipe_model.mean_embs_by_frame(embs, True)
     out['mean_frames'] = np.array([r[0] for r in res])
     out['mean_embs'] = np.stack([r[1] for r in res])

@@ -85,3 +85,60 @@ def test_no_cpu_fallback():
     with pytest.raises(NotImplementedError):
         keypoint.FCResNet(39, None, 2, 128)
     assert list(enc.state_dict())[:2] == ['layers.0.weight', 'layers.0.bias']
+
+
+def test_normalize_2d_skeletons_bit_exact_vs_reference():
+    from vpd_b200 import keypoint_apply as KA
+    gold = np.load(GOLD)
+    kp = gold['skel_in']
+    for fl in (False, True):
+        for bones in (False, True):
+            got = KA.normalize_2d_skeletons(kp, fl, include_bone_features=bones)
+            want = gold['skel_f{}_b{}'.format(int(fl), int(bones))]
+            assert got.dtype == np.float32 and got.shape == want.shape
+            assert np.array_equal(got, want), (fl, bones, float(np.abs(got - want).max()))
+    mixed = KA.normalize_2d_skeletons(kp, np.array([0, 1, 0, 1, 1, 0], bool))
+    assert np.array_equal(mixed[1], gold['skel_f1_b0'][1]) and np.array_equal(mixed[2], gold['skel_f0_b0'][2])
+    assert len(KA.COCO_BONES) == keypoint.NUM_COCO_BONES == 12
+
+
+def test_apply_pose_dir_host_pipeline(tmp_path):
+    """pose files (flat and nested layout) -> per-video pickles, with a stand-in model"""
+    import gzip
+    import json
+    import pickle
+    from vpd_b200 import keypoint_apply as KA
+    gold = np.load(GOLD)
+    kp = gold['skel_in']
+    pose_dir, model_dir, out_dir = (os.path.join(str(tmp_path), d) for d in ('poses', 'model', 'out'))
+    os.makedirs(os.path.join(pose_dir, 'nested'))
+    os.makedirs(model_dir)
+    with open(os.path.join(model_dir, 'config.json'), 'w') as fp:
+        json.dump({'embed_bones': False, 'embedding_dim': 8, 'encoder_arch': [2, 128]}, fp)
+    dets = [[3, [[0.9, [0, 0, 1, 1], kp[0].tolist()], [0.2, [0, 0, 1, 1], kp[1].tolist()]]],
+            [1, [[0.8, [0, 0, 1, 1], kp[2].tolist()]]], [2, []]]
+    for path in (os.path.join(pose_dir, 'flat.json.gz'),
+                 os.path.join(pose_dir, 'nested', 'coco_keypoints.json.gz')):
+        with gzip.open(path, 'wt', encoding='ascii') as fp:
+            json.dump(dets, fp)
+
+    class FakeModel:
+        def embed(self, pose):
+            return np.asarray(pose, dtype=np.float32).reshape(len(pose), -1)[:, :8].copy()
+    v = KA.load_video_poses(os.path.join(pose_dir, 'flat.json.gz'), min_score=0.5)
+    assert v['frame'].tolist() == [3, 3, 1, 1] and v['is_flip'].tolist() == [False, True] * 2
+    assert np.array_equal(v['pose'][0], gold['skel_f0_b0'][0]) and np.array_equal(v['pose'][3], gold['skel_f1_b0'][2])
+    assert abs(v['score'][0] - kp[0][:, 2].mean()) < 1e-7
+    done = KA.apply_pose_dir(pose_dir, model_dir, out_dir, min_score=0.5, model=FakeModel(),
+                             log=lambda *_: None)
+    assert done == [('flat', 2), ('nested', 2)]
+    with open(os.path.join(out_dir, 'nested.emb.pkl'), 'rb') as fp:
+        embs = pickle.load(fp)
+    assert [e[0] for e in embs] == [1, 3] and embs[0][1].shape == (2, 8) and embs[0][2]['is_mean'] is False
+    assert np.array_equal(embs[1][1][1], gold['skel_f1_b0'][0].reshape(-1)[:8])
+    # every detection kept, no flip
+    done = KA.apply_pose_dir(pose_dir, model_dir, os.path.join(out_dir, 'all'), no_flip=True,
+                             allow_many_per_frame=True, model=FakeModel(), log=lambda *_: None)
+    assert done[0] == ('flat', 3)
+    data, emb_dim = targets.load_teacher_targets(out_dir, embed_time=False, min_pose_score=0)
+    assert emb_dim == 8 and len(data) == 4

@@ -121,3 +121,33 @@ def test_row_ops_against_torch():
     torch.testing.assert_close(y, h.float() @ w.t() + bb, rtol=1e-4, atol=1e-4)
     with pytest.raises(Exception):
         L.call('vpd_linear_rows_f32', h, w, bb, y, 77, 100, 32, st)
+
+
+def test_apply_pose_dir_end_to_end(tmp_path):
+    """apply_vipe_model.main on the device: coco_keypoints.json.gz -> <video>.emb.pkl"""
+    import gzip
+    import pickle
+    from vpd_b200 import keypoint_apply as KA
+    torch.manual_seed(41)
+    sd = K.perturb_bn(init.fcresnet_state(39, 32, 2, 128), 42)
+    model_dir, pose_dir, out_dir = (os.path.join(str(tmp_path), d) for d in ('m', 'p', 'o'))
+    os.makedirs(model_dir)
+    os.makedirs(pose_dir)
+    torch.save(sd, os.path.join(model_dir, 'best_epoch.encoder.pt'))
+    with open(os.path.join(model_dir, 'config.json'), 'w') as fp:
+        json.dump({'embedding_dim': 32, 'encoder_arch': [2, 128], 'embed_bones': False}, fp)
+    g = torch.Generator().manual_seed(43)
+    kp = torch.rand((30, 17, 3), generator=g)
+    kp[:, :, :2] = kp[:, :, :2] * 200 + 20
+    dets = [[f, [[0.9, [0, 0, 1, 1], kp[f].tolist()]]] for f in range(30)]
+    with gzip.open(os.path.join(pose_dir, 'clip.json.gz'), 'wt', encoding='ascii') as fp:
+        json.dump(dets, fp)
+    done = KA.apply_pose_dir(pose_dir, model_dir, out_dir, log=lambda *_: None)
+    assert done == [('clip', 30)]
+    with open(os.path.join(out_dir, 'clip.emb.pkl'), 'rb') as fp:
+        embs = pickle.load(fp)
+    assert [e[0] for e in embs] == list(range(30)) and embs[0][1].shape == (2, 32)
+    got = np.stack([e[1] for e in embs])                                  # [30, 2, 32]
+    for row, fl in ((0, False), (1, True)):
+        want = K.embed(sd, KA.normalize_2d_skeletons(kp.numpy(), fl), 2)
+        assert _cos(got[:, row], want).min() >= 0.999
