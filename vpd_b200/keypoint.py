@@ -179,39 +179,37 @@ class FCResNet:
 
 
 def batch_mulitplexer(data_loaders):
-    """models/util.py:5-23 - drain all loaders in a weighted way (evaluation)"""
+    """models/util.py:5-23 (evaluation order): yields (name, batch) until every loader is drained;
+    the next loader is drawn with `random.choices` weighted by the batches it has left, so the
+    draws consumed from Python's generator equal the reference's."""
     import random
-    its = [{'name': a, 'n': len(b), 'it': iter(b)} for a, b in data_loaders]
-    while len(its) > 0:
-        i = random.choices(list(range(len(its))), k=1, weights=[x['n'] for x in its])[0]
-        sel = its[i]
+    live = [[name, len(loader), iter(loader)] for name, loader in data_loaders]
+    while live:
+        pick = random.choices(list(range(len(live))), k=1, weights=[e[1] for e in live])[0]
+        entry = live[pick]
         try:
-            yield sel['name'], next(sel['it'])
+            batch = next(entry[2])
         except StopIteration:
-            raise Exception('Uh oh... something went horribly wrong! :(')
-        sel['n'] -= 1
-        if sel['n'] == 0:
-            its.pop(i)
+            raise Exception('loader {} ended before its announced length'.format(entry[0]))
+        yield entry[0], batch
+        entry[1] -= 1
+        if entry[1] == 0:
+            del live[pick]
 
 
 def batch_zipper(data_loaders):
-    """models/util.py:26-47 - drain all loaders simultaneously (training); loaders with fewer
-    batches skip randomly chosen rounds (numpy's global generator, like the reference)"""
-    its = [(a, len(b), iter(b)) for a, b in data_loaders]
-    num_batches = max(len(b) for a, b in data_loaders)
-    skip_idxs = {}
-    for a, b in data_loaders:
-        deficit = num_batches - len(b)
+    """models/util.py:26-47 (training order): round i yields one batch from every loader, except
+    that a loader with fewer batches than the longest sits out `deficit` rounds drawn without
+    replacement from numpy's global generator (same call, same order as the reference)."""
+    rounds = max(len(loader) for _, loader in data_loaders)
+    sits_out = {}
+    for name, loader in data_loaders:
+        deficit = rounds - len(loader)
         if deficit > 0:
-            skip_idxs[a] = set(np.random.choice(np.arange(num_batches), deficit,
-                                                replace=False).tolist())
-    for i in range(num_batches):
-        batch = []
-        for a, b, c in its:
-            if a in skip_idxs and i in skip_idxs[a]:
-                continue
-            batch.append((a, next(c)))
-        yield batch
+            sits_out[name] = set(np.random.choice(np.arange(rounds), deficit, replace=False).tolist())
+    iters = [(name, iter(loader)) for name, loader in data_loaders]
+    for i in range(rounds):
+        yield [(name, next(it)) for name, it in iters if i not in sits_out.get(name, ())]
 
 
 class Keypoint_EmbeddingModel:
@@ -340,33 +338,36 @@ def load_embedding_model(model_dir, model_epoch=None, device='cuda'):
 
 
 def mean_embs_by_frame(pred_embs, flip):
-    """apply_vipe_model.py:37-69: one entry per frame; with flip, rows [unflipped, flipped]"""
-    grouped = defaultdict(list)
+    """apply_vipe_model.py:37-69: one entry per frame, sorted by frame number. Several
+    detections in a frame are averaged (meta = lowest score, is_mean); with `flip` the entry is
+    the [2, D] stack (unflipped, flipped) and carries the unflipped side's meta."""
+    if not pred_embs:
+        return []
+    shape = pred_embs[-1][1].shape
+    per_frame = {}
     for frame_num, emb, meta in pred_embs:
-        grouped[frame_num].append((emb, meta))
-    expected_shape = emb.shape
+        per_frame.setdefault(frame_num, []).append((emb, meta))
 
-    def get_mean(emb_and_metas):
-        embs, metas = zip(*emb_and_metas)
-        if len(embs) == 1:
-            e, meta = embs[0], metas[0]
+    def reduce(items):
+        if len(items) == 1:
+            e, meta = items[0]
         else:
-            e = np.mean(embs, axis=0)
-            meta = {'kp_score': min(m['kp_score'] for m in metas), 'is_mean': True}
-        assert e.shape == expected_shape
+            e = np.mean([it[0] for it in items], axis=0)
+            meta = {'kp_score': min(it[1]['kp_score'] for it in items), 'is_mean': True}
+        assert e.shape == shape
         return e, meta
 
-    result = []
-    for frame_num, emb_and_metas in grouped.items():
+    out = []
+    for frame_num, items in per_frame.items():
         if flip:
-            e, mean_meta = get_mean([x for x in emb_and_metas if not x[1]['is_flip']])
-            e_flip, _ = get_mean([x for x in emb_and_metas if x[1]['is_flip']])
-            mean_emb = np.stack((e, e_flip))
+            e, meta = reduce([it for it in items if not it[1]['is_flip']])
+            e_flip, _ = reduce([it for it in items if it[1]['is_flip']])
+            out.append((frame_num, np.stack((e, e_flip)), meta))
         else:
-            mean_emb, mean_meta = get_mean(emb_and_metas)
-        result.append((frame_num, mean_emb, mean_meta))
-    result.sort(key=lambda x: x[0])
-    return result
+            e, meta = reduce(items)
+            out.append((frame_num, e, meta))
+    out.sort(key=lambda x: x[0])
+    return out
 
 
 def embed_video(model, frames, scores, is_flip, poses, flip=True, allow_many_per_frame=False):
