@@ -7,6 +7,10 @@ Drop-in mirrors of the reference's Python API for this path:
     vpd_b200.assemble              <- vpd_dataset/{common,single_frame}.py deterministic part
     vpd_b200.targets               <- GenericDataset.load_default's teacher-target construction
     vpd_b200.train                 <- train_vpd_model.main's epoch loop (+ GPU-assembling loader)
+    vpd_b200.augment               <- the reference's augment=True random draws (device kernel K1a)
+    vpd_b200.keypoint              <- models/module.py FCResNet, models/keypoint.py (teacher apply)
+    vpd_b200.keypoint_train        <- models/keypoint.py epoch, FCPoseDecoder, train_vipe_model loop
+    vpd_b200.keypoint_apply        <- apply_vipe_model.py (pose files -> teacher .emb.pkl)
 All compute runs in libvpd_b200.so (hand-written CUDA behind the C ABI of
 include/vpd_b200.h); importing the model classes without that library raises.
 """
