@@ -219,6 +219,21 @@ def write_teacher_pickles(root):
         fp.write('not a pickle')
 
 
+def write_tennis_pickles(root):
+    """`<player>__<video>_<start>_<end>.emb.pkl` as the tennis teacher run writes them"""
+    import pickle
+    rng = np.random.RandomState(22)
+    for stem, frames in (('front__match_a_100_140', [0, 1, 2, 3, 4, 6, 7]),
+                         ('back__match_a_100_140', [0, 1, 2, 5, 6]),
+                         ('front__match_b_set_2_7_30', [3, 4, 5, 6])):
+        embs = []
+        for j, f in enumerate(frames):
+            meta = {'kp_score': 0.3 if j == 2 else 0.9}
+            embs.append((f, rng.randn(2, 8).astype(np.float32), meta))
+        with open(os.path.join(root, stem + '.emb.pkl'), 'wb') as fp:
+            pickle.dump(embs, fp)
+
+
 def gen_targets(ref):
     """A13: GenericDataset.load_default on synthetic teacher pickles."""
     tmp = tempfile.mkdtemp()
@@ -238,6 +253,19 @@ def gen_targets(ref):
             for part, ds in (('train', tr), ('val', va)):
                 meta['{}_{}_keys'.format(name, part)] = [[d[0], int(d[1])] for d in ds.data]
                 arrays['{}_{}'.format(name, part)] = np.stack([d[2] for d in ds.data])
+            meta[name + '_emb_dim'] = int(D)
+        # TennisDataset.load_default: per player-and-clip pickles, frame = clip start + index
+        tmp2 = os.path.join(tmp, 'tennis')
+        os.makedirs(tmp2)
+        write_tennis_pickles(tmp2)
+        for name, kw in (('tennis_motion', dict(embed_time=True)),
+                         ('tennis_plain', dict(embed_time=False, min_pose_score=0.2))):
+            np.random.seed(6)
+            tr, va, D = ref.single_frame.TennisDataset.load_default(
+                tmp2, tmp2, 128, kw.pop('embed_time'), 100, ([0.5] * 3, [0.2] * 3), **kw)
+            for part, ds in (('train', tr), ('val', va)):
+                meta['{}_{}_keys'.format(name, part)] = [[d[0], d[1], int(d[2])] for d in ds.data]
+                arrays['{}_{}'.format(name, part)] = np.stack([d[3] for d in ds.data])
             meta[name + '_emb_dim'] = int(D)
     finally:
         os.listdir = real_listdir

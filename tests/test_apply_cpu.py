@@ -102,3 +102,32 @@ def test_downstream_reference_loader_reads_our_pickles(tmp_path):
     assert np.allclose(dense[2], 0.5 * dense[1] + 0.5 * dense[3])   # its gap interpolation
     normed = load_embs(str(tmp_path), norm=True)['clipB'][0]
     assert np.allclose(np.linalg.norm(normed, axis=2), 1.0)
+
+
+def test_tennis_crop_layout(tmp_path):
+    """apply_vpd_model.get_tennis_dataset's layout: <crop_dir>/<src_video>/<player>/<abs frame>.png,
+    one output video per player and clip, frame numbers relative to the clip start"""
+    import cv2
+    import torch
+    crop_dir = str(tmp_path)
+    g = torch.Generator().manual_seed(3)
+    imgs = {}
+    for player, frames in (('front', [100, 101, 103]), ('back', [])):
+        d = os.path.join(crop_dir, 'match_a', player)
+        os.makedirs(d)
+        for f in frames:
+            rgb = torch.randint(0, 256, (16, 16, 3), generator=g, dtype=torch.uint8).numpy()
+            flow = torch.randint(0, 256, (16, 16, 3), generator=g, dtype=torch.uint8).numpy()
+            cv2.imwrite(os.path.join(d, '{}.png'.format(f)), cv2.cvtColor(rgb, cv2.COLOR_RGB2BGR))
+            cv2.imwrite(os.path.join(d, '{}.flow.png'.format(f)), flow)
+            imgs[f] = (rgb, flow)
+    videos = vapply.read_tennis_crops(crop_dir, ['match_a_100_104'], flow_img='flow', img_dim=16)
+    assert [v[0] for v in videos] == ['front__match_a_100_104', 'back__match_a_100_104']
+    name, frames, rgb, flow = videos[0]
+    assert frames == [0, 1, 3] and rgb.shape == (3, 16, 16, 3) and flow.shape == (3, 16, 16, 3)
+    assert np.array_equal(rgb[2].numpy(), imgs[103][0]) and np.array_equal(flow[0].numpy(), imgs[100][1])
+    assert videos[1][1] == [] and videos[1][2].shape[0] == 0
+    # the generic reader sees the same files under their directory name
+    gen = vapply.read_crop_dir(os.path.join(crop_dir, 'match_a'), flow_img='flow', img_dim=16)
+    assert [v[0] for v in gen] == ['back', 'front'] and gen[1][1] == [100, 101, 103]
+    assert np.array_equal(gen[1][2].numpy(), rgb.numpy())

@@ -64,3 +64,23 @@ def test_targets_edge_cases(tmp_path):
         with open(tmp_path / 'w.emb.pkl', 'wb') as fp:
             pickle.dump([(0, np.ones((2, 5), np.float32), {'dp_score': 1.0})], fp)
         targets.load_teacher_targets(str(tmp_path), False)
+
+
+@pytest.mark.parametrize('name,kw', [('tennis_motion', dict(embed_time=True)),
+                                     ('tennis_plain', dict(embed_time=False, min_pose_score=0.2))])
+def test_tennis_targets_match_reference_golden(name, kw, tmp_path, golden_dir, sorted_listdir):
+    """TennisDataset.load_default: per player-and-clip pickles, (video, player, frame) keys"""
+    from oracle.gen_golden import write_tennis_pickles
+    gold = np.load(os.path.join(golden_dir, 'targets.npz'))
+    with open(os.path.join(golden_dir, 'targets.json')) as fp:
+        meta = json.load(fp)
+    write_tennis_pickles(str(tmp_path))
+    data, D = targets.load_teacher_targets_tennis(str(tmp_path), **kw)
+    assert D == meta[name + '_emb_dim'] == 8
+    np.random.seed(6)
+    train, val = targets.split_train_val(data, key_len=3)
+    for part, got in (('train', train), ('val', val)):
+        assert [[d[0], d[1], int(d[2])] for d in got] == meta['{}_{}_keys'.format(name, part)]
+        arr = targets.targets_array(got)
+        assert np.array_equal(arr, gold['{}_{}'.format(name, part)])
+    assert targets._tennis_key('front__match_b_set_2_7_30') == ('match_b_set_2', 'front', 7)

@@ -102,7 +102,6 @@ def load_model_dir(model_dir, model_epoch=None, device='cuda'):
 def read_crop_dir(crop_dir, flow_img=None, img_dim=128):
     """`<crop_dir>/<video>/<n>.png` (+ `<n>.<flow_img>.png`) -> videos list for
     extract_corpus (apply_vpd_model.py:69-89). Host-side PNG decode with cv2."""
-    import cv2
     img_re = re.compile(r'^\d+\.png$')
     videos = []
     for video_name in sorted(os.listdir(crop_dir)):
@@ -110,20 +109,46 @@ def read_crop_dir(crop_dir, flow_img=None, img_dim=128):
         if not os.path.isdir(vdir):
             continue
         frames = sorted(int(os.path.splitext(f)[0]) for f in os.listdir(vdir) if img_re.match(f))
-        rgb = np.empty((len(frames), img_dim, img_dim, 3), np.uint8)
-        flow = np.empty((len(frames), img_dim, img_dim, 3), np.uint8) if flow_img else None
-        for i, f in enumerate(frames):
-            im = cv2.cvtColor(cv2.imread(os.path.join(vdir, '{}.png'.format(f))), cv2.COLOR_BGR2RGB)
-            if im.shape[:2] != (img_dim, img_dim):
-                im = cv2.resize(im, (img_dim, img_dim))
-            rgb[i] = im
-            if flow_img:
-                fl = cv2.imread(os.path.join(vdir, '{}.{}.png'.format(f, flow_img)))
-                if fl.shape[:2] != (img_dim, img_dim):
-                    fl = cv2.resize(fl, (img_dim, img_dim))
-                flow[i] = fl
-        videos.append((video_name, frames, torch.from_numpy(rgb),
-                       None if flow is None else torch.from_numpy(flow)))
+        rgb, flow = _read_frames(vdir, frames, flow_img, img_dim)
+        videos.append((video_name, frames, rgb, flow))
+    return videos
+
+
+def _read_frames(vdir, frames, flow_img, img_dim):
+    import cv2
+    rgb = np.empty((len(frames), img_dim, img_dim, 3), np.uint8)
+    flow = np.empty((len(frames), img_dim, img_dim, 3), np.uint8) if flow_img else None
+    for i, f in enumerate(frames):
+        im = cv2.cvtColor(cv2.imread(os.path.join(vdir, '{}.png'.format(f))), cv2.COLOR_BGR2RGB)
+        if im.shape[:2] != (img_dim, img_dim):
+            im = cv2.resize(im, (img_dim, img_dim))
+        rgb[i] = im
+        if flow_img:
+            fl = cv2.imread(os.path.join(vdir, '{}.{}.png'.format(f, flow_img)))
+            if fl.shape[:2] != (img_dim, img_dim):
+                fl = cv2.resize(fl, (img_dim, img_dim))
+            flow[i] = fl
+    return torch.from_numpy(rgb), None if flow is None else torch.from_numpy(flow)
+
+
+def read_tennis_crops(crop_dir, clip_names, flow_img=None, img_dim=128, players=('front', 'back')):
+    """The tennis layout of apply_vpd_model.get_tennis_dataset (:36-66): clips are named
+    `<src_video>_<start>_<end>`, crops live in `<crop_dir>/<src_video>/<player>/<frame>.png` with
+    ABSOLUTE frame numbers; every clip yields one output "video" per player,
+    `<player>__<clip>`, whose frame numbers are relative to the clip start. Frames without a
+    crop are skipped; a player without any crop in the clip still gets an (empty) entry, like
+    the reference's video list."""
+    videos = []
+    for clip in clip_names:
+        src_video_name, start_frame, end_frame = clip.rsplit('_', 2)
+        start_frame, end_frame = int(start_frame), int(end_frame)
+        for player in players:
+            vdir = os.path.join(crop_dir, src_video_name, player)
+            present = [f for f in range(start_frame, end_frame + 1)
+                       if os.path.isfile(os.path.join(vdir, '{}.png'.format(f)))]
+            rgb, flow = _read_frames(vdir, present, flow_img, img_dim)
+            videos.append(('{}__{}'.format(player, clip), [f - start_frame for f in present],
+                           rgb, flow))
     return videos
 
 

@@ -76,19 +76,68 @@ def load_teacher_targets(emb_dir, embed_time, min_pose_score=None, normalize_tar
     return all_data, emb_dim
 
 
-def split_train_val(all_data, test_size=0.2):
+def _tennis_key(file_stem):
+    """`<player>__<video>_<start>_<end>` (one pickle per player and clip) -> (video, player, start)"""
+    player, rest = file_stem.split('__', 1)
+    video_name, start_frame, _ = rest.rsplit('_', 2)
+    return video_name, player, int(start_frame)
+
+
+def load_teacher_targets_tennis(emb_dir, embed_time, min_pose_score=None, normalize_target=False,
+                                exclude_prefixes=None):
+    """`TennisDataset.load_default` (single_frame.py:90-163): same filtering / motion targets as
+    `load_teacher_targets`, but the pickles are per player and clip and the entries become
+    (video, player, start_frame + frame_num, target, meta) - the crop of that frame lives in
+    `<img_dir>/<video>/<player>/<frame>.png` (:51-57). The reference loads every pickle first
+    and takes emb_dim from each file's first entry; the order of the result is the same."""
+    all_data = []
+    emb_dim = None
+    for emb_file in os.listdir(emb_dir):
+        if not emb_file.endswith(EMB_FILE_SUFFIX):
+            continue
+        stem = emb_file.split(EMB_FILE_SUFFIX)[0]
+        if exclude_prefixes is not None and stem.startswith(exclude_prefixes):
+            continue
+        with open(os.path.join(emb_dir, emb_file), 'rb') as fp:
+            video_embs = pickle.load(fp)
+        if emb_dim is None:
+            emb_dim = video_embs[0][1].shape[-1]
+        else:
+            assert emb_dim == video_embs[0][1].shape[-1]
+        video_name, player, start_frame = _tennis_key(stem)
+        thresh = DEFAULT_MIN_POSE_SCORE if min_pose_score is None else min_pose_score
+        for i, (frame_num, emb_target, emb_meta) in enumerate(video_embs):
+            if _get_pose_score(emb_meta) < thresh:
+                continue
+            if normalize_target:
+                emb_target = _normalize_rows(emb_target)
+            if embed_time:
+                if i == 0 or video_embs[i - 1][0] != frame_num - 1:
+                    continue
+                emb_prev = video_embs[i - 1][1]
+                if normalize_target:
+                    emb_prev = _normalize_rows(emb_prev)
+                emb_target = np.concatenate(
+                    [emb_target, emb_target - emb_prev],
+                    axis=0 if len(emb_target.shape) == 1 else 1)
+            all_data.append((video_name, player, start_frame + frame_num, emb_target, emb_meta))
+    return all_data, emb_dim
+
+
+def split_train_val(all_data, test_size=0.2, key_len=2):
     """80/20 split like the reference (`train_test_split` on the numpy global RNG, then
     sort). Sorting tuples that contain ndarrays only works while (video, frame) pairs are
     unique - the reference has the same precondition."""
     from sklearn.model_selection import train_test_split
     train_data, val_data = train_test_split(all_data, test_size=test_size)
-    train_data.sort(key=lambda x: x[:2])
-    val_data.sort(key=lambda x: x[:2])
+    train_data.sort(key=lambda x: x[:key_len])         # Tennis entries sort on x[:3] (:150)
+    val_data.sort(key=lambda x: x[:key_len])
     return train_data, val_data
 
 
 def targets_array(data):
     """Stack the targets of a data list into one fp32 array [n, 2, Dt] (or [n, Dt]) - the
     `teacher` operand of vpd_b200.assemble (row 0: unflipped crop, row 1: flipped)."""
-    return np.stack([np.asarray(d[2], dtype=np.float32) for d in data]) if data else \
+    col = 3 if data and isinstance(data[0][1], str) else 2      # Tennis tuples carry the player
+    return np.stack([np.asarray(d[col], dtype=np.float32) for d in data]) if data else \
         np.zeros((0,), np.float32)
