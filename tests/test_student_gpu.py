@@ -426,3 +426,35 @@ def test_train_driver_targets_to_checkpoint_roundtrip(tmp_path):
     batch = next(iter(mk(5, 4)))
     e = model.embed(batch['img'].cpu().numpy())
     assert e.shape == (4, D) and e.dtype == np.float32 and np.isfinite(e).all()
+
+
+def test_train_main_from_shard_and_teacher_pickles(tmp_path):
+    """train.main = train_vpd_model.main in one call: crop directory -> packed shard, teacher
+    pickles -> targets, augmenting PoolLoaders, model, AdamW, fit, run directory."""
+    import pickle
+    import cv2
+    from vpd_b200 import ingest, train
+    D, n = 8, 20
+    rng = np.random.RandomState(5)
+    crop_dir, emb_dir = str(tmp_path / 'crops'), str(tmp_path / 'embs')
+    os.makedirs(os.path.join(crop_dir, 'clip'))
+    os.makedirs(emb_dir)
+    rgb, flow = synth.crops(n, seed=91)
+    for f in range(n):
+        cv2.imwrite(os.path.join(crop_dir, 'clip', '{}.png'.format(f)),
+                    cv2.cvtColor(rgb[f].numpy(), cv2.COLOR_RGB2BGR))
+        cv2.imwrite(os.path.join(crop_dir, 'clip', '{}.flow.png'.format(f)), flow[f].numpy())
+    with open(os.path.join(emb_dir, 'clip.emb.pkl'), 'wb') as fp:
+        pickle.dump([(f, (0.3 * rng.randn(2, D)).astype(np.float32), {'dp_score': 0.9})
+                     for f in range(n)], fp)
+    prefix = str(tmp_path / 'shard')
+    ingest.pack_crop_dir(crop_dir, prefix, flow_img='flow')
+    np.random.seed(1)
+    torch.manual_seed(6)
+    hist = train.main(emb_dir, prefix, str(tmp_path / 'run'), synth.FS_MEAN_STD, num_epochs=2,
+                      batch_size=8, motion=True, target_len=16, checkpoint_frequency=None,
+                      model_select_window=1, log=lambda *a: None)
+    assert len(hist) == 2 and all(np.isfinite(h['train']) and np.isfinite(h['val']) for h in hist)
+    for f in ('config.json', 'loss.json', 'best_epoch.encoder.pt', 'best_epoch.decoder.pt',
+              'epoch0002.encoder.pt'):
+        assert os.path.exists(os.path.join(str(tmp_path / 'run'), f)), f

@@ -55,3 +55,58 @@ def test_fit_without_validation_and_bad_config(tmp_path):
     del bad['emb_dim']
     with pytest.raises(AssertionError):
         train.fit(tr, [1], None, str(tmp_path / 'r2'), bad, 1, optimizer=object())
+
+
+@pytest.mark.parametrize('dataset', ['generic', 'tennis'])
+def test_main_wires_targets_shard_rows_and_loaders(tmp_path, dataset):
+    """train.main's data plumbing with the GPU-side constructors replaced: teacher pickles ->
+    targets -> split -> shard rows -> pools aligned with their targets; loader lengths; files."""
+    import pickle
+    import cv2
+    import numpy as np
+    from vpd_b200 import ingest
+    rng = np.random.RandomState(1)
+    crop_dir, emb_dir = os.path.join(str(tmp_path), 'crops'), os.path.join(str(tmp_path), 'embs')
+    os.makedirs(emb_dir)
+    if dataset == 'tennis':
+        vdirs = {'match_a/front': ('front__match_a_100_140', 100), 'match_a/back': ('back__match_a_100_140', 100)}
+    else:
+        vdirs = {'clipA': ('clipA', 0), 'clipB': ('clipB', 0)}
+    for vi, (vdir, (stem, start)) in enumerate(vdirs.items()):
+        os.makedirs(os.path.join(crop_dir, vdir))
+        embs = []
+        for f in range(12):
+            img = np.full((8, 8, 3), 10 * vi + f, np.uint8)         # pixel value identifies the frame
+            cv2.imwrite(os.path.join(crop_dir, vdir, '{}.png'.format(start + f)), img)
+            cv2.imwrite(os.path.join(crop_dir, vdir, '{}.flow.png'.format(start + f)), img)
+            embs.append((f, np.full((2, 4), 10 * vi + f, np.float32), {'dp_score': 0.9}))
+        with open(os.path.join(emb_dir, stem + '.emb.pkl'), 'wb') as fp:
+            pickle.dump(embs, fp)
+    prefix = os.path.join(str(tmp_path), 'shard')
+    ingest.pack_crop_dir(crop_dir, prefix, flow_img='flow', img_dim=8, nested=dataset == 'tennis')
+    seen = {}
+
+    def fake_pools(shard, rows):
+        return np.asarray(shard.rgb)[rows], np.asarray(shard.flow)[rows], None
+
+    def fake_loader(rgb, flow, mask, teach, length):
+        # every pool frame sits next to ITS teacher target
+        assert rgb.shape[0] == teach.shape[0] and teach.shape[1:] == (2, 4)
+        assert np.array_equal(rgb[:, 0, 0, 0].astype(np.float32), teach[:, 0, 0])
+        seen.setdefault('lengths', []).append(length)
+        seen.setdefault('sizes', []).append(rgb.shape[0])
+        return ['loader', length]
+
+    tr = FakeTrainer([3.0, 2.0], [3.0, 2.5])
+    np.random.seed(0)
+    hist = train.main(emb_dir, prefix, os.path.join(str(tmp_path), 'run'), CFG['rgb_mean_std'],
+                      dataset=dataset, num_epochs=2, batch_size=4, motion=False, target_len=100,
+                      checkpoint_frequency=None, model_select_window=1, log=lambda *a: None,
+                      _factories={'pools': fake_pools, 'loader': fake_loader,
+                                  'trainer': lambda D, flow: (tr, object(), None)})
+    assert [h['epoch'] for h in hist] == [1, 2] and seen['lengths'] == [100, 20]
+    assert sorted(seen['sizes']) == [5, 19]                          # 24 frames, 80 / 20 split
+    with open(os.path.join(str(tmp_path), 'run', 'config.json')) as fp:
+        cfg = json.load(fp)
+    assert cfg['emb_dim'] == 4 and cfg['use_flow'] is True and cfg['motion'] is False
+    assert tr.saved == ['best_epoch', 'best_epoch', 'epoch0002']

@@ -99,15 +99,25 @@ def load_model_dir(model_dir, model_epoch=None, device='cuda'):
     return model, cfg
 
 
-def read_crop_dir(crop_dir, flow_img=None, img_dim=128):
+def read_crop_dir(crop_dir, flow_img=None, img_dim=128, nested=False):
     """`<crop_dir>/<video>/<n>.png` (+ `<n>.<flow_img>.png`) -> videos list for
-    extract_corpus (apply_vpd_model.py:69-89). Host-side PNG decode with cv2."""
+    extract_corpus (apply_vpd_model.py:69-89). Host-side PNG decode with cv2.
+    nested: the tennis layout `<crop_dir>/<video>/<player>/<n>.png` (single_frame.py:51-57);
+    the entries are then named `<video>/<player>`."""
     img_re = re.compile(r'^\d+\.png$')
-    videos = []
+    names = []
     for video_name in sorted(os.listdir(crop_dir)):
         vdir = os.path.join(crop_dir, video_name)
         if not os.path.isdir(vdir):
             continue
+        if nested:
+            names.extend('{}/{}'.format(video_name, p) for p in sorted(os.listdir(vdir))
+                         if os.path.isdir(os.path.join(vdir, p)))
+        else:
+            names.append(video_name)
+    videos = []
+    for video_name in names:
+        vdir = os.path.join(crop_dir, video_name)
         frames = sorted(int(os.path.splitext(f)[0]) for f in os.listdir(vdir) if img_re.match(f))
         rgb, flow = _read_frames(vdir, frames, flow_img, img_dim)
         videos.append((video_name, frames, rgb, flow))

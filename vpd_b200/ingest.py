@@ -77,9 +77,10 @@ def _read_masks(crop_dir, videos, img_dim):
     return out
 
 
-def pack_crop_dir(crop_dir, out_prefix, flow_img=None, img_dim=128, with_mask=False):
-    """Decode every `<video>/<n>.png` (and flow / mask PNG) once and write the shard files."""
-    videos = read_crop_dir(crop_dir, flow_img, img_dim)
+def pack_crop_dir(crop_dir, out_prefix, flow_img=None, img_dim=128, with_mask=False, nested=False):
+    """Decode every `<video>/<n>.png` (and flow / mask PNG) once and write the shard files.
+    nested: the tennis layout `<video>/<player>/<n>.png`; shard videos are `<video>/<player>`."""
+    videos = read_crop_dir(crop_dir, flow_img, img_dim, nested=nested)
     n = sum(len(v[1]) for v in videos)
     rgb = np.lib.format.open_memmap(out_prefix + '.rgb.npy', mode='w+', dtype=np.uint8,
                                     shape=(n, img_dim, img_dim, 3))

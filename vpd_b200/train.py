@@ -125,3 +125,73 @@ class PoolLoader:
                           seed=int(torch.randint(0, 2 ** 62, (1,), generator=self.gen).item()))
             yield assemble_batch(self.rgb, self.flow, self.rgb_mean_std, flip=flip,
                                  teacher=self.teacher, index=idx, **kw)
+
+
+def main(emb_dir, shard_prefix, save_dir, rgb_mean_std, dataset='generic', num_epochs=50,
+         batch_size=256, learning_rate=5e-4, img_dim=128, motion=False, encoder_arch='resnet34',
+         model_select_window=5, checkpoint_frequency=25, min_pose_score=None,
+         exclude_prefixes=None, augment=True, target_len=20000, device='cuda', log=print,
+         _factories=None):
+    """`train_vpd_model.main` (:171-283) on this package, from the packed crop shard
+    (`vpd_b200.ingest.pack_crop_dir`) and the teacher pickles: targets (A13; `dataset='tennis'`
+    selects the per player-and-clip variant, :119-128) -> 80/20 split -> device-resident pools ->
+    `PoolLoader`s of `target_len` / 20 % of it draws per epoch (:183, single_frame.py:268-272;
+    the reference augments the validation set too, common.py:86) -> model, trainer, AdamW ->
+    `fit`. Returns the loss history. `_factories` (tests) replaces the GPU-side constructors:
+    {'pools': fn(shard, rows) -> (rgb, flow, mask), 'loader': fn(...), 'trainer': fn(emb_dim,
+    use_flow) -> (trainer, optimizer, scaler)}."""
+    import torch
+    from . import targets
+    from .ingest import load_shard
+    f = _factories or {}
+    if dataset == 'tennis':
+        data, emb_dim = targets.load_teacher_targets_tennis(
+            emb_dir, motion, min_pose_score=min_pose_score, exclude_prefixes=exclude_prefixes)
+        train_data, val_data = targets.split_train_val(data, key_len=3)
+        key = lambda d: ('{}/{}'.format(d[0], d[1]), d[2])        # shard video = <video>/<player>
+    else:
+        data, emb_dim = targets.load_teacher_targets(
+            emb_dir, motion, min_pose_score=min_pose_score, exclude_prefixes=exclude_prefixes)
+        train_data, val_data = targets.split_train_val(data)
+        key = lambda d: (d[0], d[1])
+    shard = load_shard(shard_prefix)
+    use_flow = shard.flow is not None
+    log('Train images: {}  Val images: {}  Embedding dim: {}'.format(
+        len(train_data), len(val_data), emb_dim))
+
+    def pools(part):
+        rows = shard.rows_of([key(d) for d in part])
+        if 'pools' in f:
+            return f['pools'](shard, rows)
+        idx = torch.from_numpy(rows)
+        rgb = torch.from_numpy(np.asarray(shard.rgb))[idx].to(device)
+        flow = torch.from_numpy(np.asarray(shard.flow))[idx].to(device) if use_flow else None
+        mask = None
+        if shard.mask is not None:
+            mask = torch.from_numpy(np.asarray(shard.mask))[idx].to(device)
+        return rgb, flow, mask
+
+    def loader(part, length):
+        rgb, flow, mask = pools(part)
+        teach = targets.targets_array(part)
+        if 'loader' in f:
+            return f['loader'](rgb, flow, mask, teach, length)
+        return PoolLoader(rgb, flow, torch.from_numpy(teach).to(device), rgb_mean_std, batch_size,
+                          length, mask_u8=mask, augment=augment)
+
+    train_loader = loader(train_data, target_len)
+    val_loader = loader(val_data, int(target_len * 0.2)) if val_data else None
+    if 'trainer' in f:
+        trainer, optimizer, scaler = f['trainer'](emb_dim, use_flow)
+    else:
+        from .rgb import RGBF_EmbeddingModel
+        from .trainer import ModelTrainer
+        trainer = ModelTrainer(RGBF_EmbeddingModel(encoder_arch, emb_dim, use_flow, device), motion)
+        optimizer, scaler = trainer.get_optimizer(learning_rate)
+    config = {'num_epochs': num_epochs, 'batch_size': batch_size, 'learning_rate': learning_rate,
+              'img_dim': img_dim, 'use_flow': use_flow, 'motion': motion, 'emb_dim': emb_dim,
+              'encoder_arch': encoder_arch,
+              'rgb_mean_std': [list(map(float, rgb_mean_std[0])), list(map(float, rgb_mean_std[1]))]}
+    return fit(trainer, train_loader, val_loader, save_dir, config, num_epochs, optimizer,
+               scaler=scaler, model_select_window=model_select_window,
+               checkpoint_frequency=checkpoint_frequency, dataset=dataset, log=log)
