@@ -73,7 +73,8 @@ def assemble_batch_aug(rgb, flow, rgb_mean_std, params, teacher=None, mask=None,
     from .augment import check_params
     mean, std = _mean_std(rgb_mean_std)
     P, H, W, _ = rgb.shape
-    check_params(params, H, W)
+    if not params.crop.is_cuda:      # device-resident draws were validated when drawn (no sync)
+        check_params(params, H, W)
     B = params.index.numel()
     C = 5 if flow is not None else 3
     img = torch.empty((B, C, H, W), device=rgb.device, dtype=torch.float32)

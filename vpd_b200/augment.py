@@ -108,6 +108,7 @@ def draw_batch(B, pool_size, H, W, two_rows=True, has_mask=None, host_noise=Fals
             p.crop[b] = torch.tensor([i, j, h, w], dtype=torch.int32)
         else:
             p.crop[b] = torch.tensor([0, 0, H, W], dtype=torch.int32)
+    check_params(p, H, W)
     return p
 
 
