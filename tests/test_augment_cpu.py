@@ -133,3 +133,46 @@ def test_oracle_and_sampler_reproduce_the_reference_dataset(tag, n, dim, items):
         exact += _same(got, want)
     assert exact >= items // 3                   # the mean usually rounds the same way
     assert int(p.noise_on.sum()) > 0 or dim > 32
+
+
+def test_fast_sampler_same_distributions_and_layout():
+    import time
+    g = torch.Generator().manual_seed(11)
+    has_mask = torch.tensor([True, False] * 8)
+    B = 20000
+    p = augment.draw_batch_fast(B, 16, 128, 128, has_mask=has_mask, generator=g)
+    augment.check_params(p, 128, 128)
+    c = p.crop.numpy().astype(np.float64)
+    area = c[:, 2] * c[:, 3] / (128. * 128.)
+    ratio = c[:, 3] / c[:, 2]
+    # reference distribution (torchvision get_params), same moments
+    random.seed(0)
+    torch.manual_seed(0)
+    q = augment.draw_batch(1500, 16, 128, 128, has_mask=has_mask)
+    cq = q.crop.numpy().astype(np.float64)
+    assert abs(area.mean() - (cq[:, 2] * cq[:, 3] / 16384.).mean()) < 0.02
+    assert abs(ratio.mean() - (cq[:, 3] / cq[:, 2]).mean()) < 0.01
+    assert area.min() > 0.45 and area.max() <= 1.0 and ratio.min() > 0.85 and ratio.max() < 1.17
+    assert abs(c[:, 0].mean() - cq[:, 0].mean()) < 1.0 and abs(c[:, 1].mean() - cq[:, 1].mean()) < 1.0
+    # jitter: uniform permutations, factor ranges, packed complements
+    order = p.jitter_order.numpy()
+    assert (np.sort(order, axis=1) == np.arange(4)).all()
+    first = np.bincount(order[:, 0], minlength=4) / B
+    assert np.abs(first - 0.25).max() < 0.02
+    jf = p.jitter_factor.numpy()
+    assert jf[:, 0].min() >= 0.8 and jf[:, 0].max() <= 1.2 and abs(jf[:, 0].mean() - 1.0) < 0.005
+    assert jf[:, 3].min() >= 0.95 and jf[:, 3].max() <= 1.05
+    assert np.abs(jf[:, 5]).max() <= 0.05 + 1e-7 and abs(jf[:, 5].mean()) < 0.002
+    assert np.allclose(jf[:, 2], 1.0 - jf[:, 1].astype(np.float64), atol=1e-7)
+    assert abs(p.flip.float().mean() - 0.5) < 0.02
+    on = p.noise_on.numpy().astype(bool)
+    assert abs(on.mean() - 0.25) < 0.02 and has_mask.numpy()[p.index.numpy()][on].all()
+    assert p.index.min() >= 0 and p.index.max() < 16 and p.jitter is None and p.noise is None
+    # switches and speed
+    z = augment.draw_batch_fast(5, 16, 32, 32, jitter=None, crop=False, generator=g)
+    assert (z.jitter_order == 255).all() and z.crop.tolist() == [[0, 0, 32, 32]] * 5
+    t0 = time.perf_counter()
+    for _ in range(10):
+        augment.draw_batch_fast(256, 4096, 128, 128, has_mask=torch.ones(4096, dtype=torch.bool),
+                                generator=g)
+    assert (time.perf_counter() - t0) / 10 < 0.01

@@ -86,7 +86,10 @@ def assemble_batch_aug(rgb, flow, rgb_mean_std, params, teacher=None, mask=None,
         tdim = teacher.shape[-1]
         emb = torch.empty((B, tdim), device=rgb.device, dtype=torch.float32)
     jo, jf = params.jitter_order, params.jitter_factor
-    if jo is not None and bool((jo > 3).all()):
+    has_jitter = getattr(params, 'has_jitter', None)       # set where the draws are made (host)
+    if has_jitter is None:
+        has_jitter = jo is not None and not bool((jo > 3).all())
+    if not has_jitter:
         jo = jf = None
     nz = (None, None, None, 0.0, 0)
     if mask is not None:

@@ -53,6 +53,7 @@ class AugmentParams:
         self.crop = torch.zeros((B, 4), dtype=torch.int32)
         self.noise_on = torch.zeros(B, dtype=torch.uint8)
         self.noise = None                    # fp32 [B,3,H,W] when the host draws the noise
+        self.has_jitter = None               # any ColorJitter op active (None: look at the orders)
 
     def set_jitter(self, b, fn_idx, bf, cf, sf, hf):
         """pack one ColorJitter draw the way the kernel wants it (factors rounded from the
@@ -108,6 +109,7 @@ def draw_batch(B, pool_size, H, W, two_rows=True, has_mask=None, host_noise=Fals
             p.crop[b] = torch.tensor([i, j, h, w], dtype=torch.int32)
         else:
             p.crop[b] = torch.tensor([0, 0, H, W], dtype=torch.int32)
+    p.has_jitter = bool(use_jitter)
     check_params(p, H, W)
     return p
 
@@ -118,3 +120,76 @@ def check_params(p, H, W):
     ok = ((c[:, 2] >= 1) & (c[:, 3] >= 1) & (c[:, 0] >= 0) & (c[:, 1] >= 0)
           & (c[:, 0] + c[:, 2] <= H) & (c[:, 1] + c[:, 3] <= W))
     assert bool(ok.all()), 'crop box outside the frame'
+
+
+def draw_batch_fast(B, pool_size, H, W, two_rows=True, has_mask=None, generator=None,
+                    jitter=JITTER_KWARGS, crop=True):
+    """Vectorised draws with the SAME distributions as `draw_batch` (ColorJitter.get_params,
+    RandomResizedCrop.get_params incl. its 10-try rejection loop and central fallback, flip and
+    noise coins, sampling with replacement) but from one torch.Generator in batched calls: about
+    0.3 ms per 256 frames instead of 22 ms, so the augmenting loader keeps up with the training
+    step. Not stream-identical with the reference (use `draw_batch` for that); the noise always
+    comes from the device generator."""
+    import math
+    g = generator
+    p = AugmentParams(B)
+    p.jitter = None
+    p.index = torch.randint(0, pool_size, (B,), generator=g).to(torch.int32)
+    if two_rows:
+        p.flip = torch.randint(0, 2, (B,), generator=g).to(torch.uint8)
+    ranges = _jitter_ranges(jitter or {})
+    if any(v is not None for v in ranges.values()):
+        order = torch.rand((B, 4), generator=g).argsort(dim=1)             # uniform permutations
+        fac = torch.zeros((B, 4), dtype=torch.float64)
+        present = torch.zeros(4, dtype=torch.bool)
+        for k, name in enumerate(('brightness', 'contrast', 'saturation', 'hue')):
+            r = ranges[name]
+            if r is not None:
+                present[k] = True
+                fac[:, k] = (torch.rand(B, generator=g, dtype=torch.float32).double()
+                             * (r[1] - r[0]) + r[0])
+            elif k < 3:
+                fac[:, k] = 1.0
+        p.jitter_order = torch.where(present[order], order, torch.full_like(order, 255)).to(torch.uint8)
+        jf = torch.zeros((B, 8), dtype=torch.float64)
+        jf[:, 0], jf[:, 1], jf[:, 2] = fac[:, 0], fac[:, 1], 1.0 - fac[:, 1]
+        jf[:, 3], jf[:, 4], jf[:, 5] = fac[:, 2], 1.0 - fac[:, 2], fac[:, 3]
+        p.jitter_factor = jf.to(torch.float32)
+    coin = torch.rand(B, generator=g) <= RANDOM_MASK_PROB
+    if has_mask is not None:
+        p.noise_on = (coin & torch.as_tensor(has_mask, dtype=torch.bool)[p.index.long()]).to(torch.uint8)
+    if crop:
+        tries = 10
+        area = float(H * W)
+        ta = area * (torch.rand((B, tries), generator=g, dtype=torch.float32).double()
+                     * (CROP_SCALE[1] - CROP_SCALE[0]) + CROP_SCALE[0])
+        lr0, lr1 = math.log(CROP_RATIO[0]), math.log(CROP_RATIO[1])
+        ar = torch.exp(torch.rand((B, tries), generator=g, dtype=torch.float32).double() * (lr1 - lr0) + lr0)
+        w = torch.round(torch.sqrt(ta * ar)).long()
+        h = torch.round(torch.sqrt(ta / ar)).long()
+        ok = (w > 0) & (w <= W) & (h > 0) & (h <= H)
+        first = ok.int().argmax(dim=1)
+        any_ok = ok.any(dim=1)
+        w = w.gather(1, first[:, None])[:, 0]
+        h = h.gather(1, first[:, None])[:, 0]
+        # central fallback (transforms.py:951-963)
+        in_ratio = float(W) / float(H)
+        if in_ratio < min(CROP_RATIO):
+            fw, fh = W, int(round(W / min(CROP_RATIO)))
+        elif in_ratio > max(CROP_RATIO):
+            fh = H
+            fw = int(round(fh * max(CROP_RATIO)))
+        else:
+            fw, fh = W, H
+        w = torch.where(any_ok, w, torch.full_like(w, fw))
+        h = torch.where(any_ok, h, torch.full_like(h, fh))
+        i = (torch.rand(B, generator=g, dtype=torch.float64) * (H - h + 1).double()).floor().long()
+        j = (torch.rand(B, generator=g, dtype=torch.float64) * (W - w + 1).double()).floor().long()
+        i = torch.where(any_ok, torch.minimum(i, H - h), (H - h) // 2)
+        j = torch.where(any_ok, torch.minimum(j, W - w), (W - w) // 2)
+        p.crop = torch.stack([i, j, h, w], dim=1).to(torch.int32)
+    else:
+        p.crop = torch.tensor([[0, 0, H, W]], dtype=torch.int32).repeat(B, 1)
+    p.has_jitter = any(v is not None for v in ranges.values())
+    check_params(p, H, W)
+    return p
