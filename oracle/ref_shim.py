@@ -1,8 +1,10 @@
-"""Import the UNMODIFIED reference (jhong93/vpd) from /root/reference.
+"""Import the UNMODIFIED reference (jhong93/vpd): from /root/reference where it exists
+(the build container), else from the verbatim copy `oracle/_ref/` that
+`oracle/build_ref.py` makes (git-ignored; it travels to the GPU box with the snapshot).
 
-TEST INFRASTRUCTURE ONLY. Only usable in the build container (the GPU box has
-no /root/reference); used by oracle/gen_golden.py to create tests/golden/* and
-by tests that are skipped when the reference is absent.
+TEST / MEASUREMENT INFRASTRUCTURE ONLY: used by oracle/gen_golden.py to create
+tests/golden/*, by tests that are skipped when no reference is importable, and by
+bench.py's CPU arm (`--impl reference`, `cpu_baseline`).
 
 models/rgb.py:3 imports `efficientnet_pytorch` unconditionally; it is not
 installed and the resnet path never touches it, so a stub module is inserted
@@ -14,10 +16,19 @@ import types
 import warnings
 
 REFERENCE_DIR = os.environ.get('VPD_REFERENCE_DIR', '/root/reference')
+if not os.path.isfile(os.path.join(REFERENCE_DIR, 'models', 'rgb.py')):
+    REFERENCE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')
 
 
 def available():
     return os.path.isfile(os.path.join(REFERENCE_DIR, 'models', 'rgb.py'))
+
+
+def source():
+    """'reference' (the tree under /root/reference), 'copy' (oracle/_ref) or None"""
+    if not available():
+        return None
+    return 'copy' if REFERENCE_DIR.endswith('_ref') else 'reference'
 
 
 def load():
