@@ -36,6 +36,16 @@ extern "C" {
 VPD_API const char* vpd_last_error(void);
 VPD_API int vpd_abi_version(void);
 
+/* Per-channel statistics accumulator (BatchNorm batch sums, BN-backward sums): two 64-bit
+ * INTEGER limbs, value = hi * 2^-4 + lo * 2^-52. Kernels add to it with integer atomics,
+ * which are associative: the totals - and every activation / gradient downstream of the
+ * batch statistics - are bit-reproducible from run to run (fp64 atomics are not).
+ * Buffers are arrays of these, zeroed by the caller where a function accumulates (+=);
+ * vpd_b200/_lib.py has acc_zeros / acc_from_f64 / acc_to_f64 for the Python side. */
+typedef struct vpd_stat_acc {
+  int64_t hi, lo;
+} vpd_stat_acc;
+
 /* ---- K1: frame-batch assembly ------------------------------------------------
  * Replaces vpd_dataset/common.py:52-69 (_load_image/_load_flow arithmetic),
  * vpd_dataset/single_frame.py:168-206 (GenericDataset.__getitem__, deterministic
@@ -125,13 +135,13 @@ VPD_API int vpd_pack_conv_weight(const float* w_oihw, void* w_tap_bf16, void* wT
                          int Cin, int k, void* stream);
 VPD_API int vpd_pack_stem_weight(const float* w_oihw, void* w_stem_bf16, int Cimg, void* stream);
 /* y = conv(x); optional epilogue: y*scale[c]+shift[c], + residual, ReLU; optional
- * fp64 per-channel (sum, sumsq) accumulation into stats[2][Cout] (training BN). */
+ * per-channel (sum, sumsq) accumulation into stats[2][Cout] (training BN). */
 VPD_API int vpd_conv2d_fwd(const void* x, const void* w_tap, void* y, int N, int H, int W, int Cin,
                    int Cout, int k, int stride, int pad, const float* scale, const float* shift,
-                   const void* residual, int relu, double* stats, void* stream);
+                   const void* residual, int relu, vpd_stat_acc* stats, void* stream);
 /* 7x7/2 pad-3 stem on the padded input layout written by vpd_assemble_stem */
 VPD_API int vpd_stem_conv_fwd(const void* x_stem, const void* w_stem, void* y, int N, int H, int W,
-                      const float* scale, const float* shift, int relu, double* stats,
+                      const float* scale, const float* shift, int relu, vpd_stat_acc* stats,
                       void* stream);
 /* dx = conv_transpose(dy) (+ residual); for stride 2 the optional 1x1/2
  * downsample branch (dy_ds, wT_ds) is accumulated in the same pass. */
@@ -142,11 +152,11 @@ VPD_API int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N
 /* Same as vpd_conv2d_dgrad (stride 1 or 2, no downsample branch) with the BatchNorm-
  * backward reduction of the consuming ReLU->BN stage folded into the epilogue: dx is
  * stored already masked, g = dx * 1[z > 0], and sums[0..Cin) += sum g,
- * sums[Cin..2Cin) += sum g * (y - mean) * rstd  (fp64, accumulated). */
+ * sums[Cin..2Cin) += sum g * (y - mean) * rstd  (accumulated). */
 VPD_API int vpd_conv2d_dgrad_bnfused(const void* dy, const void* wT_tap, void* dx, int N, int H, int W,
                              int Cin, int Cout, int k, int stride, int pad, const void* residual,
                              const void* z, const void* y, const float* mean, const float* rstd,
-                             double* sums, void* stream);
+                             vpd_stat_acc* sums, void* stream);
 /* dw[k*k][Cout][Cin] (fp32, tap-major: the gradient arena's native conv layout)
  * += sum over pixels dy (x) x. ACCUMULATES into dw (zero it first). */
 VPD_API int vpd_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
@@ -160,34 +170,34 @@ VPD_API int vpd_stem_conv_wgrad(const void* x_stem, const void* dy, float* dw, i
  * head, FCNet and F.mse_loss(sum) with their autograd (models/rgb.py:68-70,
  * models/module.py:133-156, train_vpd_model.py:87). Exposed for tests and reuse. */
 /* train-mode BN (+ optional residual, itself optionally batch-normalised) + ReLU.
- * stats/res_stats: fp64 [2][C] per-channel (sum, sumsq) of y / res as produced by
+ * stats/res_stats: [2][C] per-channel (sum, sumsq) of y / res as produced by
  * vpd_conv2d_fwd; running buffers are updated (momentum .1), save_* receive batch
  * mean and 1/sqrt(var+eps). res_stats == NULL: residual added as is. */
 VPD_API int vpd_bn_act_fwd(const void* y, const void* res, void* z, int64_t M, int C, int relu,
-                   const double* stats, const float* gamma, const float* beta,
+                   const vpd_stat_acc* stats, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, int64_t* num_batches,
-                   float* save_mean, float* save_rstd, const double* res_stats,
+                   float* save_mean, float* save_rstd, const vpd_stat_acc* res_stats,
                    const float* res_gamma, const float* res_beta, float* res_running_mean,
                    float* res_running_var, int64_t* res_num_batches, float* res_save_mean,
                    float* res_save_rstd, void* stream);
 /* gradient of the stage above: g = dz * 1[z > 0] (z may be NULL: no mask); dy = BN
  * backward of g through (y, save_mean, save_rstd, gamma); optional second branch
- * (y2...) fed by the same g; dmask (may alias dz) receives g; sums = fp64 [2][C]
+ * (y2...) fed by the same g; dmask (may alias dz) receives g; sums = [2][C]
  * scratch per branch, zeroed by the caller. */
 VPD_API int vpd_bn_act_bwd(const void* dz, const void* z, void* dmask, int64_t M, int C,
                    const void* y, void* dy, const float* gamma, const float* save_mean,
-                   const float* save_rstd, double* sums, float* dgamma, float* dbeta,
+                   const float* save_rstd, vpd_stat_acc* sums, float* dgamma, float* dbeta,
                    const void* y2, void* dy2, const float* gamma2, const float* save_mean2,
-                   const float* save_rstd2, double* sums2, float* dgamma2, float* dbeta2,
+                   const float* save_rstd2, vpd_stat_acc* sums2, float* dgamma2, float* dbeta2,
                    void* stream);
 /* stem: train-mode BN + ReLU + maxpool 3x3/2 pad 1 (argmax: uint8 window index) */
 VPD_API int vpd_stem_bn_pool_fwd(const void* y, void* z, uint8_t* argmax, int N, int H, int W, int C,
-                         const double* stats, const float* gamma, const float* beta,
+                         const vpd_stat_acc* stats, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, int64_t* num_batches,
                          float* save_mean, float* save_rstd, void* stream);
 VPD_API int vpd_stem_bn_pool_bwd(const void* dpool, const uint8_t* argmax, const void* y, void* dy,
                          int N, int H, int W, int C, const float* gamma, const float* beta,
-                         const float* save_mean, const float* save_rstd, double* sums,
+                         const float* save_mean, const float* save_rstd, vpd_stat_acc* sums,
                          float* dgamma, float* dbeta, void* stream);
 /* K4: avgpool -> fc -> [FCNet] -> sum-squared-error loss and backward. params/grads:
  * fp32 arrays laid out [fc_w D*F][fc_b D][w0 Hd*D][b0 Hd][w2 Hd*Hd][b2 Hd][w5 T*Hd][b5 T]
@@ -226,18 +236,18 @@ VPD_API int vpd_linear_rows_f32(const void* x_bf16, const float* w, const float*
  *                      n % 4 == 0
  *   vpd_bn1d_fwd       out = keep * relu(BatchNorm1d_train(a)) / (1 - p_drop) [- res].
  *                      `a` is the Linear output WITHOUT its bias (a bias in front of a batch-
- *                      statistics BN cancels; lin_bias only enters running_mean); stats = fp64
+ *                      statistics BN cancels; lin_bias only enters running_mean); stats =
  *                      [2][C] column sums / sums of squares of `a` as vpd_conv2d_fwd
  *                      accumulates them; running stats (momentum .1, unbiased variance) and
  *                      num_batches are updated; save_mean / save_rstd for the backward
  *   vpd_bn1d_bwd       da = BN backward of g = dz * keep / (1-p) * 1[bn(a) > 0];
  *                      dgamma += sum g*xhat, dbeta += sum g (ACCUMULATED: the three encoder
- *                      passes of a step share weights); sums = fp64 [2][C] scratch
+ *                      passes of a step share weights); sums = [2][C] accumulator scratch
  *                      `groups`: the weight-sharing encoder passes of a step are stacked along
  *                      the rows - `groups` consecutive blocks of M rows, each its own BatchNorm
  *                      batch (stats / save_mean / save_rstd / sums are [groups][...]); running
  *                      statistics are updated group after group like consecutive calls
- *   vpd_colstats_bf16  stats[g] = column sums and sums of squares (fp64) of row group g
+ *   vpd_colstats_bf16  stats[g] = column sums and sums of squares of row group g
  *   vpd_relu_mask_bf16 out = d * 1[z > 0]
  *   vpd_colsum_bf16    out[c] += sum_r x[r][c]   (Linear bias gradients)
  *   vpd_vipe_loss      the loss head: contra = ||e1-e2|| + valid * max(0, 1 - ||e1-en||)
@@ -248,16 +258,16 @@ VPD_API int vpd_linear_rows_f32(const void* x_bf16, const float* w, const float*
  *                      pred2 may be NULL (datasets without those entries). */
 VPD_API int vpd_dropout_mask(uint8_t* keep, int64_t n, float p_drop, uint64_t seed,
                      const uint64_t* seed_add, int stream_id, void* stream);
-VPD_API int vpd_bn1d_fwd(const void* a, const double* stats, const float* gamma, const float* beta,
+VPD_API int vpd_bn1d_fwd(const void* a, const vpd_stat_acc* stats, const float* gamma, const float* beta,
                  const float* lin_bias, float* running_mean, float* running_var,
                  int64_t* num_batches, float* save_mean, float* save_rstd, const uint8_t* keep,
                  float p_drop, const void* res, void* out, int64_t M, int C, int groups,
                  void* stream);
 VPD_API int vpd_bn1d_bwd(const void* dz, const void* a, const uint8_t* keep, float p_drop,
                  const float* gamma, const float* beta, const float* save_mean,
-                 const float* save_rstd, double* sums, void* da, float* dgamma, float* dbeta,
+                 const float* save_rstd, vpd_stat_acc* sums, void* da, float* dgamma, float* dbeta,
                  int64_t M, int C, int groups, void* stream);
-VPD_API int vpd_colstats_bf16(const void* x, double* stats, int64_t M, int C, int groups, void* stream);
+VPD_API int vpd_colstats_bf16(const void* x, vpd_stat_acc* stats, int64_t M, int C, int groups, void* stream);
 VPD_API int vpd_relu_mask_bf16(const void* d, const void* z, void* out, int64_t n, void* stream);
 VPD_API int vpd_colsum_bf16(const void* x, float* out, int64_t M, int C, void* stream);
 VPD_API int vpd_vipe_loss(const float* e1, const float* e2, const float* en, const float* valid,

@@ -30,13 +30,13 @@ def main():
         wT = torch.empty((9, Cin, Cout), device=dev, dtype=torch.bfloat16)
         lib().call('vpd_pack_conv_weight', w, w_tap, wT, Cout, Cin, 3, s)
         y = torch.empty((N, H, W, Cout), device=dev, dtype=torch.bfloat16)
-        st = torch.zeros((2, Cout), device=dev, dtype=torch.float64)
+        st = torch.zeros((2, Cout, 2), device=dev, dtype=torch.int64)
 
         z = torch.randn((N, H, W, Cin), device=dev).to(torch.bfloat16)
         yf = torch.randn((N, H, W, Cin), device=dev).to(torch.bfloat16)
         mean = torch.zeros(Cin, device=dev)
         rstd = torch.ones(Cin, device=dev)
-        bs = torch.zeros((2, Cin), device=dev, dtype=torch.float64)
+        bs = torch.zeros((2, Cin, 2), device=dev, dtype=torch.int64)
         dgrad = os.environ.get('DIAG_MODE', 'fwd') == 'dgrad'
         alias = os.environ.get('DIAG_ALIAS', '0')
         if alias == '1':      # z and y share one tensor (half the unique bytes)

@@ -4,14 +4,15 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from vpd_b200._lib import lib, stream_ptr
+from vpd_b200._lib import lib, stream_ptr, acc_zeros, acc_from_f64
 from gpu_util import dev, nhwc_bf16, nchw_f32, rel_err
 
 pytestmark = pytest.mark.gpu
 
 
 def _stats(y_nchw):
-    return torch.stack([y_nchw.double().sum((0, 2, 3)), (y_nchw.double() ** 2).sum((0, 2, 3))]).contiguous()
+    return acc_from_f64(torch.stack([y_nchw.double().sum((0, 2, 3)),
+                                     (y_nchw.double() ** 2).sum((0, 2, 3))]))
 
 
 def _bn_ref(y, gamma, beta):
@@ -67,7 +68,7 @@ def test_bn_act_forward_and_backward(N, H, W, C, mode):
     dz = nhwc_bf16(mk(N, C, H, W)).to(dev())
     ref.backward(nchw_f32(dz))
     dy = torch.empty_like(y)
-    sums = torch.zeros((2, C), device=dev(), dtype=torch.float64)
+    sums = acc_zeros((2, C), dev())
     dgamma = torch.empty(C, device=dev()); dbeta = torch.empty(C, device=dev())
     dmask = torch.empty_like(dz)
     b2args = [None] * 8
@@ -106,7 +107,7 @@ def test_stem_bn_pool_forward_and_backward(N, H, W):
     dpool = nhwc_bf16(torch.randn((N, C, H // 2, W // 2), generator=g)).to(dev())
     ref.backward(nchw_f32(dpool))
     dy = torch.empty_like(y)
-    sums = torch.zeros((2, C), device=dev(), dtype=torch.float64)
+    sums = acc_zeros((2, C), dev())
     dgamma = torch.empty(C, device=dev()); dbeta = torch.empty(C, device=dev())
     lib().call('vpd_stem_bn_pool_bwd', dpool, am, y, dy, N, H, W, C, gamma, beta, sm, sr, sums, dgamma,
                dbeta, stream_ptr())

@@ -14,7 +14,7 @@ import torch
 
 from oracle import keypoint_train_ref as T
 from vpd_b200 import keypoint
-from vpd_b200._lib import lib, stream_ptr
+from vpd_b200._lib import lib, stream_ptr, acc_zeros, acc_from_f64, acc_to_f64
 from vpd_b200.keypoint_train import FCPoseDecoder
 from gpu_util import dev, OUT
 from test_keypoint_train_cpu import GOLD, H, BLOCKS, N1, N2, P, unpack_masks
@@ -52,7 +52,7 @@ def test_bn1d_fwd_bwd_against_torch(M, C, drop, res):
     r = _bf(torch.randn((M, C), generator=g)) if res else None
     dz = _bf(torch.randn((M, C), generator=g))
     af = a.float()
-    stats = torch.cat([af.double().sum(0), (af.double() ** 2).sum(0)]).contiguous()
+    stats = acc_from_f64(torch.cat([af.double().sum(0), (af.double() ** 2).sum(0)]))
     rm, rv = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
     nbt = torch.zeros((), device=dev(), dtype=torch.int64)
     sm, sr = torch.empty(C, device=dev()), torch.empty(C, device=dev())
@@ -76,7 +76,7 @@ def test_bn1d_fwd_bwd_against_torch(M, C, drop, res):
     y.backward(dz.float())
     da = torch.empty_like(a)
     dg, db = torch.ones(C, device=dev()), torch.ones(C, device=dev())     # += semantics
-    sums = torch.empty(2 * C, device=dev(), dtype=torch.float64)
+    sums = acc_zeros(2 * C, dev())
     L.call('vpd_bn1d_bwd', dz, a, keep, P if drop else 0.0, gamma, beta, sm, sr, sums, da, dg, db,
            M, C, 1, st)
     msg = 'bn1d M={} C={}: da cos {:.5f}, dgamma cos {:.5f}, dbeta cos {:.5f}'.format(
@@ -99,11 +99,12 @@ def test_bn1d_row_groups_are_separate_batches():
     beta = (torch.randn(C, generator=g) * 0.3).to(dev())
     keep = (torch.rand((G * M, C), generator=g) < 0.8).to(torch.uint8).to(dev())
     dz = _bf(torch.randn((G * M, C), generator=g))
-    stats = torch.empty(G * 2 * C, device=dev(), dtype=torch.float64)
+    stats = acc_zeros(G * 2 * C, dev()) + 7          # the call zeroes it
     L.call('vpd_colstats_bf16', a, stats, M, C, G, st)
     af = a.float().view(G, M, C)
-    torch.testing.assert_close(stats.view(G, 2, C)[:, 0].float(), af.sum(1), rtol=1e-4, atol=1e-2)
-    torch.testing.assert_close(stats.view(G, 2, C)[:, 1].float(), (af ** 2).sum(1), rtol=1e-4, atol=1e-2)
+    stf = acc_to_f64(stats).view(G, 2, C)
+    torch.testing.assert_close(stf[:, 0].float(), af.sum(1), rtol=1e-4, atol=1e-2)
+    torch.testing.assert_close(stf[:, 1].float(), (af ** 2).sum(1), rtol=1e-4, atol=1e-2)
     rm, rv = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
     nbt = torch.zeros((), device=dev(), dtype=torch.int64)
     sm, sr = torch.empty(G * C, device=dev()), torch.empty(G * C, device=dev())
@@ -126,7 +127,7 @@ def test_bn1d_row_groups_are_separate_batches():
     y.backward(dz.float())
     da = torch.empty_like(a)
     dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
-    sums = torch.empty(G * 2 * C, device=dev(), dtype=torch.float64)
+    sums = acc_zeros(G * 2 * C, dev())
     L.call('vpd_bn1d_bwd', dz, a, keep, P, gamma, beta, sm, sr, sums, da, dg, db, M, C, G, st)
     assert _cos(da.float(), x.grad) > 0.995
     torch.testing.assert_close(dg, gp.grad, rtol=2e-2, atol=2e-2 * float(gp.grad.abs().max()))
@@ -212,12 +213,12 @@ def test_linear_backward_as_1x1_convolution():
     wt, wtt = (torch.empty(cout * cin, device=dev(), dtype=torch.bfloat16) for _ in range(2))
     L.call('vpd_pack_conv_weight', w, wt, wtt, cout, cin, 1, st)
     y = torch.empty((n, cout), device=dev(), dtype=torch.bfloat16)
-    stats = torch.zeros(2 * cout, device=dev(), dtype=torch.float64)
+    stats = acc_zeros(2 * cout, dev())
     L.call('vpd_conv2d_fwd', x, wt, y, n, 1, 1, cin, cout, 1, 1, 0, None, None, None, 0, stats, st)
     wb = w.to(torch.bfloat16).float()
     ref = x.float() @ wb.t()
     assert _cos(y.float(), ref) > 0.9999
-    torch.testing.assert_close(stats[:cout].float(), y.float().sum(0), rtol=1e-3, atol=1e-2)
+    torch.testing.assert_close(acc_to_f64(stats)[:cout].float(), y.float().sum(0), rtol=1e-3, atol=1e-2)
     dw = torch.zeros((cout, cin), device=dev())
     L.call('vpd_conv2d_wgrad', x, dy, dw, n, 1, 1, cin, cout, 1, 1, 0, st)
     torch.testing.assert_close(dw, dy.float().t() @ x.float(), rtol=1e-3, atol=1e-2)

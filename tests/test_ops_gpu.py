@@ -7,7 +7,7 @@ import torch.nn.functional as F
 
 from oracle import assemble_ref, student_ref
 from vpd_b200 import synth
-from vpd_b200._lib import lib, stream_ptr
+from vpd_b200._lib import lib, stream_ptr, acc_zeros, acc_from_f64, acc_to_f64
 from gpu_util import dev, nhwc_bf16, nchw_f32, rel_err, report
 
 pytestmark = pytest.mark.gpu
@@ -189,7 +189,7 @@ def _conv_case(N, H, W, Cin, Cout, k, stride, pad, seed, affine=False, residual=
     if residual:
         res = nhwc_bf16(torch.randn((N, Cout, Ho, Wo), generator=g)).to(dev())
     if stats:
-        st = torch.zeros((2, Cout), device=dev(), dtype=torch.float64)
+        st = acc_zeros((2, Cout), dev())
     lib().call('vpd_conv2d_fwd', xb, w_tap, y, N, H, W, Cin, Cout, k, stride, pad, scale, shift,
                res, int(relu), st, stream_ptr())
     torch.cuda.synchronize()
@@ -234,13 +234,13 @@ def test_conv2d_fwd_epilogue_and_stats():
     assert rel_err(got, ref) < 6e-3, report('conv_stats', got, ref)
     s = got.double().sum((0, 2, 3))
     s2 = (got.double() ** 2).sum((0, 2, 3))
-    assert torch.allclose(st[0], s, rtol=1e-5, atol=1e-3)
-    assert torch.allclose(st[1], s2, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(acc_to_f64(st)[0], s, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(acc_to_f64(st)[1], s2, rtol=1e-5, atol=1e-3)
     got, ref, st, _ = _conv_case(3, 8, 8, 256, 512, 3, 1, 1, seed=4, stats=True)
     s = got.double().sum((0, 2, 3))
     s2 = (got.double() ** 2).sum((0, 2, 3))
-    assert torch.allclose(st[0], s, rtol=1e-5, atol=1e-3)
-    assert torch.allclose(st[1], s2, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(acc_to_f64(st)[0], s, rtol=1e-5, atol=1e-3)
+    assert torch.allclose(acc_to_f64(st)[1], s2, rtol=1e-5, atol=1e-3)
 
 
 @pytest.mark.parametrize('N,H,W,Cimg', [(2, 128, 128, 5), (3, 64, 64, 3), (9, 32, 32, 5)])
@@ -253,7 +253,7 @@ def test_stem_conv_fwd(N, H, W, Cimg):
     ws = torch.empty((7, 64, 64), device=dev(), dtype=torch.bfloat16)
     lib().call('vpd_pack_stem_weight', w.to(dev()), ws, Cimg, stream_ptr())
     y = torch.full((N, H // 2, W // 2, 64), float('nan'), device=dev(), dtype=torch.bfloat16)
-    st = torch.zeros((2, 64), device=dev(), dtype=torch.float64)
+    st = acc_zeros((2, 64), dev())
     lib().call('vpd_stem_conv_fwd', xs, ws, y, N, H, W, None, None, 0, st, stream_ptr())
     ref = F.conv2d(x.to(torch.bfloat16).float().to(dev()), w.to(torch.bfloat16).float().to(dev()),
                    stride=2, padding=3)
@@ -261,7 +261,7 @@ def test_stem_conv_fwd(N, H, W, Cimg):
     msg = report('stem{}'.format((N, H, W, Cimg)), got, ref)
     assert torch.isfinite(got).all(), msg
     assert rel_err(got, ref) < 6e-3, msg
-    assert torch.allclose(st[0], got.double().sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
+    assert torch.allclose(acc_to_f64(st)[0], got.double().sum((0, 2, 3)), rtol=1e-5, atol=1e-3)
 
 
 DGRAD_CASES = [
@@ -382,7 +382,7 @@ def test_conv2d_dgrad_with_fused_bn_backward_reduction(case):
     y = nhwc_bf16(torch.randn((N, Cin, H, W), generator=g) * 2 + 0.5).to(dev())
     mean = (torch.randn(Cin, generator=g) * 0.3).to(dev())
     rstd = (torch.rand(Cin, generator=g) + 0.5).to(dev())
-    sums = torch.zeros((2, Cin), device=dev(), dtype=torch.float64)
+    sums = acc_zeros((2, Cin), dev())
     dx = torch.full((N, H, W, Cin), float('nan'), device=dev(), dtype=torch.bfloat16)
     lib().call('vpd_conv2d_dgrad_bnfused', dy, wT_tap, dx, N, H, W, Cin, Cout, k, stride, pad, res,
                z, y, mean, rstd, sums, stream_ptr())
@@ -395,8 +395,8 @@ def test_conv2d_dgrad_with_fused_bn_backward_reduction(case):
     xhat = (nchw_f32(y) - mean.view(1, -1, 1, 1)) * rstd.view(1, -1, 1, 1)
     s0 = got.double().sum((0, 2, 3))
     s1 = (got.double() * xhat.double()).sum((0, 2, 3))
-    assert torch.allclose(sums[0], s0, rtol=1e-4, atol=1e-2)
-    assert torch.allclose(sums[1], s1, rtol=1e-4, atol=1e-2)
+    assert torch.allclose(acc_to_f64(sums)[0], s0, rtol=1e-4, atol=1e-2)
+    assert torch.allclose(acc_to_f64(sums)[1], s1, rtol=1e-4, atol=1e-2)
 
 
 # --------------------------------------------------- K1 masked-noise augmentation

@@ -1,0 +1,239 @@
+"""Parity at the sizes BASELINE.json names, through the Python mirror -> C ABI:
+
+  config 2  one distillation training step at batch 256 (train_vpd_model.py:67-98,
+            models/util.py:50-58) vs the fp32 oracle on the SAME 256 synthetic frames
+            (seeds of §8d: crops 1, flips 2, teacher 3; init under torch.manual_seed(0)):
+            loss, every gradient tensor, BN running statistics, then AdamW and `embed`
+            of the 256 frames on the updated weights;
+  config 1  `embed` forward at batch 32 (models/rgb.py:72-86), seed-0 crops, reference init.
+
+The oracle costs ~6 s of host time per batch-256 step. Everything measured is also written to
+gpurun_out/parity_b256.txt so the bars below can be checked against what the hardware gave.
+
+On the gradient bars. The loss agrees to 4e-5 and the gradient NORMS of all weight tensors to
+< 2 %, but the per-tensor COSINE against the fp32 oracle is 0.75-0.80 in layers 1-3 at batch 256
+exactly as at batch 8: it is not sampling noise, it is what 8-bit-mantissa storage does to this
+network. A freshly initialised ResNet-34 with batch-statistic BN amplifies a 2^-9 relative
+perturbation of weights / activations into an O(1) change of the gradient DIRECTION of the early
+layers. The fp32 oracle itself, with bf16 rounding applied at the CUDA path's storage points
+(oracle.student_ref.encoder_forward_rounded), lands on the same cosines (conv1: 0.748 modelled,
+0.745 measured); fp16 or TF32 (11-bit mantissa, the reference's own autocast precision) reach
+only 0.95-0.96, and >= 0.99 needs ~14 bits (tests/diag_precision.py prints the table). So the
+test asserts what can be asserted: our gradients are never further from fp32 than the storage
+model of the same arithmetic predicts, the head (no amplification) is tight, and every kernel
+is checked tightly on its own at this batch size in test_ops_b256_gpu.py.
+
+Also here: the run-to-run determinism the integer BatchNorm-statistics accumulators give
+(same step twice from the same state -> bit-identical activations, loss and data gradients).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import assemble_ref, student_ref
+from vpd_b200 import synth
+from vpd_b200._lib import lib
+from gpu_util import dev, OUT
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a = a.double().flatten(); b = b.double().flatten()
+    return (a @ b / (a.norm() * b.norm() + 1e-300)).item()
+
+
+def _model(seed=0):
+    from vpd_b200 import RGBF_EmbeddingModel
+    torch.manual_seed(seed)
+    return RGBF_EmbeddingModel('resnet34', 32, True, 'cuda')
+
+
+def _grads_as_state(m):
+    """the gradient arena read through the parameter views -> reference layout (OIHW ...)"""
+    params, m._params = m._params, m._grads
+    try:
+        return m._read_state(lambda k: True)
+    finally:
+        m._params = params
+
+
+def _config2_batch(B=256):
+    rgb, flow = synth.crops(B, seed=1)
+    fl = synth.flips(B, seed=2)
+    teach = synth.teacher(B, seed=3, emb_dim=32, motion=True)
+    img, tgt = assemble_ref.train_batch(rgb.numpy(), flow.numpy(), teach.numpy(), fl.numpy(),
+                                        *synth.FS_MEAN_STD)
+    return rgb, flow, fl, teach, img, tgt
+
+
+def _log(lines):
+    os.makedirs(OUT, exist_ok=True)
+    with open(os.path.join(OUT, 'parity_b256.txt'), 'a') as fp:
+        fp.write('\n'.join(lines) + '\n')
+    print('\n'.join(lines))
+
+
+def test_config2_train_step_batch256_vs_oracle():
+    from vpd_b200 import ModelTrainer
+    from vpd_b200.assemble import assemble_batch
+    B = 256
+    rgb, flow, fl, teach, img, tgt = _config2_batch(B)
+    # K1 at the benchmarked size: bit-exact against the oracle's assembly
+    batch = assemble_batch(rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD, flip=fl.to(dev()),
+                           teacher=teach.to(dev()))
+    assert torch.equal(batch['img'].cpu(), img) and torch.equal(batch['emb'].cpu(), tgt)
+
+    m = _model(0)
+    tr = ModelTrainer(m, True)
+    opt, _ = tr.get_optimizer(5e-4)
+    m._ensure_grads()
+    m.train()
+    tr._loss.zero_()
+    tr._run(batch['img'], batch['emb'], B, True)
+    torch.cuda.synchronize()
+    loss = tr._loss.item()
+    gsd = {k: v.cpu() for k, v in _grads_as_state(m).items()}
+
+    torch.manual_seed(0)
+    osd = student_ref.init_encoder_state('resnet34', 32, True)
+    odsd = student_ref.init_decoder_state(32)
+    otr = student_ref.OracleTrainer(osd, odsd)
+    ref_loss, ograds, _ = otr.loss_and_grads(img, tgt, train=True)
+    names = otr.enc_names + ['decoder.' + n for n in student_ref.DECODER_PARAM_NAMES]
+    assert len(names) == len(ograds)
+
+    # what bf16 STORAGE alone does to a correct fp32 implementation (oracle arithmetic with the
+    # CUDA path's rounding points laid over it): the yardstick for the cosines below
+    _, egrads = otr.loss_and_grads_rounded(img, tgt)
+    rows, bad = [], []
+    worst = {'ours': (2.0, ''), 'model': (2.0, '')}
+    for name, og, eg in zip(names, ograds, egrads):
+        g = gsd[name]
+        c, ce = _cos(g, og), _cos(eg, og)
+        nrel = abs(g.norm().item() - og.norm().item()) / (og.norm().item() + 1e-30)
+        mabs = (g - og).abs().max().item()
+        rows.append('{:44s} cos {:.5f} (bf16-storage model {:.5f})  |g| rel {:.4f}  max-abs '
+                    '{:.3e} (ref max {:.3e})'.format(name, c, ce, nrel, mabs, og.abs().max().item()))
+        worst['ours'] = min(worst['ours'], (c, name))
+        worst['model'] = min(worst['model'], (ce, name))
+        head = name.startswith(('decoder', 'resnet.fc'))
+        # (1) never worse than the storage model says bf16 must be (margin: the two are
+        #     different noise realisations); (2) the head, which sees no amplification, tight;
+        # (3) gradient norms: weights within 3 %, 1-D tensors within 25 %
+        if c < ce - 0.08 or (head and c < 0.99) or nrel > (0.03 if og.dim() > 1 else 0.25):
+            bad.append((name, round(c, 4), round(ce, 4), round(nrel, 4)))
+    _log(['== config 2: train step, batch 256 (bf16 operands / activations vs fp32 oracle) ==',
+          'loss {:.4f}  oracle {:.4f}  rel {:.2e}'.format(loss, ref_loss, abs(loss - ref_loss) / ref_loss),
+          'worst cosine: ours {:.5f} ({}), bf16-storage model of the oracle {:.5f} ({})'.format(
+              *worst['ours'], *worst['model'])] + rows)
+    assert abs(loss - ref_loss) <= 1e-3 * ref_loss, (loss, ref_loss)
+    assert not bad, bad
+    assert worst['ours'][0] >= 0.55, worst
+
+    # BN running statistics after the train-mode forward (momentum .1, unbiased variance)
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    with torch.no_grad():
+        student_ref.encoder_forward(otr.sd, img, 'resnet34', train=True)   # updates otr.sd buffers
+    for k in ('resnet.bn1', 'resnet.layer2.0.downsample.1', 'resnet.layer4.2.bn2'):
+        np.testing.assert_allclose(sd[k + '.running_mean'].numpy(),
+                                   otr.sd[k + '.running_mean'].detach().numpy(), rtol=2e-2, atol=2e-3)
+        np.testing.assert_allclose(sd[k + '.running_var'].numpy(),
+                                   otr.sd[k + '.running_var'].detach().numpy(), rtol=2e-2)
+        assert int(sd[k + '.num_batches_tracked']) == 1
+
+    # AdamW on these gradients, then `embed` of the 256 frames on the UPDATED weights vs the
+    # oracle forward on the same weights
+    opt.step()
+    torch.cuda.synchronize()
+    sd = {k: v.cpu() for k, v in m.state_dict().items()}
+    got = m.embed(img.numpy())
+    ref = student_ref.embed(sd, img)
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    _log(['embed(256 frames) after the step: cosine min {:.6f} mean {:.6f}, max-abs {:.4f} at '
+          'max |ref| {:.2f}'.format(cos.min(), cos.mean(), np.abs(got - ref).max(), np.abs(ref).max())])
+    assert got.shape == (B, 32) and got.dtype == np.float32
+    assert cos.min() >= 0.999, cos.min()
+
+
+def test_config1_embed_batch32_vs_oracle():
+    B = 32
+    rgb, flow = synth.crops(B, seed=0)
+    x = assemble_ref.train_batch(rgb.numpy(), flow.numpy(), np.zeros((B, 2, 64), np.float32),
+                                 np.zeros(B, np.uint8), *synth.FS_MEAN_STD)[0]
+    m = _model(0)
+    torch.manual_seed(0)
+    sd = student_ref.init_encoder_state('resnet34', 32, True)
+    got = m.embed(x.numpy())
+    ref = student_ref.embed(sd, x)
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    _log(['== config 1: embed forward, batch 32, reference init ==',
+          'cosine min {:.6f} mean {:.6f}; max-abs {:.4f} at max |ref| {:.2f}'.format(
+              cos.min(), cos.mean(), np.abs(got - ref).max(), np.abs(ref).max())])
+    assert cos.min() >= 0.999
+    assert np.abs(got - ref).max() <= 0.03 * np.abs(ref).max()
+    # trained-like statistics (randomised BN buffers) at the same size
+    sd2 = student_ref.randomize_bn_state(sd, 7)
+    m.load_state_dict(sd2)
+    got = m.embed(x.numpy())
+    ref = student_ref.embed(sd2, x)
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    _log(['randomised BN buffers: cosine min {:.6f}; max-abs {:.4f} at max |ref| {:.2f}'.format(
+        cos.min(), np.abs(got - ref).max(), np.abs(ref).max())])
+    assert cos.min() >= 0.999
+
+
+def _activation(m, net, block, which, B):
+    ptr, numel = ctypes.c_void_p(), ctypes.c_int64()
+    lib().call('vpd_net_activation', net.handle, block, which, B, ctypes.byref(ptr),
+               ctypes.byref(numel))
+    out = torch.empty(numel.value, device=dev(), dtype=torch.bfloat16)
+    lib().call('vpd_copy_d2d', out, ptr.value, numel.value * 2,
+               torch.cuda.current_stream().cuda_stream)
+    return out
+
+
+@pytest.mark.parametrize('B', [24, 256])
+def test_train_step_is_bit_reproducible(B):
+    """Two runs of the same step from the same state: the integer statistics accumulators make
+    every activation, the loss and every gradient that does not go through the weight-gradient
+    kernels' fp32 atomics bit-identical (those agree to fp32 rounding)."""
+    from vpd_b200 import ModelTrainer
+    rgb, flow, fl, teach, img, tgt = _config2_batch(B)
+    img, tgt = img.to(dev()), tgt.to(dev())
+    runs = []
+    for _ in range(2):
+        m = _model(0)
+        tr = ModelTrainer(m, True)
+        m._ensure_grads()
+        m.train()
+        for rep in range(3):               # eager, eager, captured graph: all must agree
+            tr._loss.zero_()
+            m._buffers.zero_()             # same BN running state every repetition
+            tr._run(img, tgt, B, True)
+            torch.cuda.synchronize()
+            net = m._native(128, 128, B)
+            runs.append({'loss': tr._loss.item(), 'grads': m._grads.clone(),
+                         'z_last': _activation(m, net, 15, 4, B).clone(),
+                         'z_first': _activation(m, net, 0, 4, B).clone(),
+                         'n_conv': lib().call('vpd_net_conv_param_count', net.handle)})
+    a = runs[0]
+    table = m._table
+    for b in runs[1:]:
+        assert b['loss'] == a['loss']
+        assert torch.equal(a['z_first'], b['z_first']) and torch.equal(a['z_last'], b['z_last'])
+        for name, arena, off, layout, shape in table:
+            if arena != 0:
+                continue
+            numel = int(np.prod(shape)) if shape else 1
+            if layout == 2:
+                numel = 7 * 64 * 64
+            ga, gb = a['grads'][off:off + numel], b['grads'][off:off + numel]
+            if layout == 0 and not name.startswith(('decoder', 'resnet.fc')):
+                assert torch.equal(ga, gb), name           # BN gamma / beta gradients
+            else:
+                err = (ga - gb).abs().max().item()
+                assert err <= 2e-5 * ga.abs().max().item() + 1e-12, (name, err)

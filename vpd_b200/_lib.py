@@ -114,3 +114,25 @@ def lib():
 def stream_ptr(device=None):
     import torch
     return torch.cuda.current_stream(device).cuda_stream
+
+
+# ---- vpd_stat_acc buffers (include/vpd_b200.h): int64 [..., 2] = (hi, lo), value = hi/16 + lo/2^52
+def acc_zeros(shape, device):
+    """A zeroed statistics-accumulator buffer of `shape` elements (torch int64 [*shape, 2])."""
+    import torch
+    shape = (shape,) if isinstance(shape, int) else tuple(shape)
+    return torch.zeros(shape + (2,), device=device, dtype=torch.int64)
+
+
+def acc_from_f64(t):
+    """float64 tensor -> accumulator buffer holding the same values (to 2^-52 absolute)."""
+    import torch
+    t = t.double()
+    hi = torch.round(t * 16.0)
+    lo = torch.round((t - hi / 16.0) * float(1 << 52))
+    return torch.stack([hi.to(torch.int64), lo.to(torch.int64)], dim=-1).contiguous()
+
+
+def acc_to_f64(a):
+    """accumulator buffer [..., 2] -> float64 values"""
+    return a[..., 0].double() / 16.0 + a[..., 1].double() / float(1 << 52)

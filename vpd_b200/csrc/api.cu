@@ -15,7 +15,7 @@ typedef __nv_bfloat16 bf16;
 extern "C" {
 
 const char* vpd_last_error(void) { return get_error(); }
-int vpd_abi_version(void) { return 1; }
+int vpd_abi_version(void) { return 2; }
 
 int vpd_assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
                       const int32_t* index, const uint8_t* flip, const float* teacher,
@@ -108,24 +108,24 @@ int vpd_dropout_mask(uint8_t* keep, int64_t n, float p_drop, uint64_t seed,
   return dropout_mask(keep, n, p_drop, seed, (const unsigned long long*)seed_add,
                       (unsigned int)stream_id, (cudaStream_t)stream);
 }
-int vpd_bn1d_fwd(const void* a, const double* stats, const float* gamma, const float* beta,
+int vpd_bn1d_fwd(const void* a, const vpd_stat_acc* stats, const float* gamma, const float* beta,
                  const float* lin_bias, float* running_mean, float* running_var,
                  int64_t* num_batches, float* save_mean, float* save_rstd, const uint8_t* keep,
                  float p_drop, const void* res, void* out, int64_t M, int C, int groups,
                  void* stream) {
-  return bn1d_fwd((const bf16*)a, stats, gamma, beta, lin_bias, running_mean, running_var,
+  return bn1d_fwd((const bf16*)a, (const StatAcc*)stats, gamma, beta, lin_bias, running_mean, running_var,
                   (long long*)num_batches, save_mean, save_rstd, keep, p_drop, (const bf16*)res,
                   (bf16*)out, M, C, groups, (cudaStream_t)stream);
 }
 int vpd_bn1d_bwd(const void* dz, const void* a, const uint8_t* keep, float p_drop,
                  const float* gamma, const float* beta, const float* save_mean,
-                 const float* save_rstd, double* sums, void* da, float* dgamma, float* dbeta,
+                 const float* save_rstd, vpd_stat_acc* sums, void* da, float* dgamma, float* dbeta,
                  int64_t M, int C, int groups, void* stream) {
   return bn1d_bwd((const bf16*)dz, (const bf16*)a, keep, p_drop, gamma, beta, save_mean, save_rstd,
-                  sums, (bf16*)da, dgamma, dbeta, M, C, groups, (cudaStream_t)stream);
+                  (StatAcc*)sums, (bf16*)da, dgamma, dbeta, M, C, groups, (cudaStream_t)stream);
 }
-int vpd_colstats_bf16(const void* x, double* stats, int64_t M, int C, int groups, void* stream) {
-  return colstats_bf16((const bf16*)x, stats, M, C, groups, (cudaStream_t)stream);
+int vpd_colstats_bf16(const void* x, vpd_stat_acc* stats, int64_t M, int C, int groups, void* stream) {
+  return colstats_bf16((const bf16*)x, (StatAcc*)stats, M, C, groups, (cudaStream_t)stream);
 }
 int vpd_relu_mask_bf16(const void* d, const void* z, void* out, int64_t n, void* stream) {
   return relu_mask_bf16((const bf16*)d, (const bf16*)z, (bf16*)out, n, (cudaStream_t)stream);
@@ -173,27 +173,27 @@ int vpd_pack_stem_weight(const float* w_oihw, void* w_stem_bf16, int Cimg, void*
 
 int vpd_conv2d_fwd(const void* x, const void* w_tap, void* y, int N, int H, int W, int Cin,
                    int Cout, int k, int stride, int pad, const float* scale, const float* shift,
-                   const void* residual, int relu, double* stats, void* stream) {
+                   const void* residual, int relu, vpd_stat_acc* stats, void* stream) {
   ConvGeom g{N, H, W, Cin, Cout, k, stride, pad};
   ConvEpilogue e;
   e.scale = scale;
   e.shift = shift;
   e.residual = (const bf16*)residual;
   e.relu = relu;
-  e.stats = stats;
+  e.stats = (StatAcc*)stats;
   ConvLaunch L;
   if (plan_conv_fwd(&L, g, (const bf16*)x, (const bf16*)w_tap, (bf16*)y, e)) return -1;
   return launch_conv(L, (cudaStream_t)stream);
 }
 
 int vpd_stem_conv_fwd(const void* x_stem, const void* w_stem, void* y, int N, int H, int W,
-                      const float* scale, const float* shift, int relu, double* stats,
+                      const float* scale, const float* shift, int relu, vpd_stat_acc* stats,
                       void* stream) {
   ConvEpilogue e;
   e.scale = scale;
   e.shift = shift;
   e.relu = relu;
-  e.stats = stats;
+  e.stats = (StatAcc*)stats;
   ConvLaunch L;
   if (plan_stem_fwd(&L, N, H, W, (const bf16*)x_stem, (const bf16*)w_stem, (bf16*)y, e)) return -1;
   return launch_conv(L, (cudaStream_t)stream);
@@ -216,7 +216,7 @@ int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N, int H,
 int vpd_conv2d_dgrad_bnfused(const void* dy, const void* wT_tap, void* dx, int N, int H, int W,
                              int Cin, int Cout, int k, int stride, int pad, const void* residual,
                              const void* z, const void* y, const float* mean, const float* rstd,
-                             double* sums, void* stream) {
+                             vpd_stat_acc* sums, void* stream) {
   ConvGeom g{N, H, W, Cin, Cout, k, stride, pad};
   ConvBwdFuse f;
   f.nb = 1;
@@ -224,7 +224,7 @@ int vpd_conv2d_dgrad_bnfused(const void* dy, const void* wT_tap, void* dx, int N
   f.y[0] = (const bf16*)y;
   f.mean[0] = mean;
   f.rstd[0] = rstd;
-  f.sums[0] = sums;
+  f.sums[0] = (StatAcc*)sums;
   ConvLaunch L[4];
   int count = 0;
   if (plan_conv_dgrad(L, &count, g, (const bf16*)dy, (const bf16*)wT_tap, (bf16*)dx,
@@ -250,10 +250,10 @@ int vpd_stem_conv_wgrad(const void* x_stem, const void* dy, float* dw, int N, in
   return launch_wgrad(L, (cudaStream_t)stream);
 }
 
-static BnLayer make_bn(const double* stats, const float* gamma, const float* beta, float* rm,
+static BnLayer make_bn(const vpd_stat_acc* stats, const float* gamma, const float* beta, float* rm,
                        float* rv, int64_t* nbt, float* sm, float* sr, long long count) {
   BnLayer L;
-  L.stats = stats;
+  L.stats = (const StatAcc*)stats;
   L.gamma = gamma;
   L.beta = beta;
   L.running_mean = rm;
@@ -270,9 +270,9 @@ static BnLayer make_bn(const double* stats, const float* gamma, const float* bet
 }
 
 int vpd_bn_act_fwd(const void* y, const void* res, void* z, int64_t M, int C, int relu,
-                   const double* stats, const float* gamma, const float* beta,
+                   const vpd_stat_acc* stats, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, int64_t* num_batches,
-                   float* save_mean, float* save_rstd, const double* res_stats,
+                   float* save_mean, float* save_rstd, const vpd_stat_acc* res_stats,
                    const float* res_gamma, const float* res_beta, float* res_running_mean,
                    float* res_running_var, int64_t* res_num_batches, float* res_save_mean,
                    float* res_save_rstd, void* stream) {
@@ -295,9 +295,9 @@ int vpd_bn_act_fwd(const void* y, const void* res, void* z, int64_t M, int C, in
 
 int vpd_bn_act_bwd(const void* dz, const void* z, void* dmask, int64_t M, int C,
                    const void* y, void* dy, const float* gamma, const float* save_mean,
-                   const float* save_rstd, double* sums, float* dgamma, float* dbeta,
+                   const float* save_rstd, vpd_stat_acc* sums, float* dgamma, float* dbeta,
                    const void* y2, void* dy2, const float* gamma2, const float* save_mean2,
-                   const float* save_rstd2, double* sums2, float* dgamma2, float* dbeta2,
+                   const float* save_rstd2, vpd_stat_acc* sums2, float* dgamma2, float* dbeta2,
                    void* stream) {
   BnBwdParams q;
   memset(&q, 0, sizeof(q));
@@ -308,14 +308,14 @@ int vpd_bn_act_bwd(const void* dz, const void* z, void* dmask, int64_t M, int C,
   q.C = C;
   q.nbranch = y2 != nullptr ? 2 : 1;
   q.y[0] = (const bf16*)y; q.dy[0] = (bf16*)dy; q.gamma[0] = gamma; q.save_mean[0] = save_mean;
-  q.save_rstd[0] = save_rstd; q.sums[0] = sums; q.dgamma[0] = dgamma; q.dbeta[0] = dbeta;
+  q.save_rstd[0] = save_rstd; q.sums[0] = (StatAcc*)sums; q.dgamma[0] = dgamma; q.dbeta[0] = dbeta;
   q.y[1] = (const bf16*)y2; q.dy[1] = (bf16*)dy2; q.gamma[1] = gamma2; q.save_mean[1] = save_mean2;
-  q.save_rstd[1] = save_rstd2; q.sums[1] = sums2; q.dgamma[1] = dgamma2; q.dbeta[1] = dbeta2;
+  q.save_rstd[1] = save_rstd2; q.sums[1] = (StatAcc*)sums2; q.dgamma[1] = dgamma2; q.dbeta[1] = dbeta2;
   return launch_bn_bwd(q, (cudaStream_t)stream);
 }
 
 int vpd_stem_bn_pool_fwd(const void* y, void* z, uint8_t* argmax, int N, int H, int W, int C,
-                         const double* stats, const float* gamma, const float* beta,
+                         const vpd_stat_acc* stats, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, int64_t* num_batches,
                          float* save_mean, float* save_rstd, void* stream) {
   PoolParams pp;
@@ -331,7 +331,7 @@ int vpd_stem_bn_pool_fwd(const void* y, void* z, uint8_t* argmax, int N, int H, 
 
 int vpd_stem_bn_pool_bwd(const void* dpool, const uint8_t* argmax, const void* y, void* dy,
                          int N, int H, int W, int C, const float* gamma, const float* beta,
-                         const float* save_mean, const float* save_rstd, double* sums,
+                         const float* save_mean, const float* save_rstd, vpd_stat_acc* sums,
                          float* dgamma, float* dbeta, void* stream) {
   StemBwdParams sp;
   memset(&sp, 0, sizeof(sp));
@@ -341,7 +341,7 @@ int vpd_stem_bn_pool_bwd(const void* dpool, const uint8_t* argmax, const void* y
   sp.dy = (bf16*)dy;
   sp.N = N; sp.H = H; sp.W = W; sp.C = C;
   sp.gamma = gamma; sp.beta = beta; sp.save_mean = save_mean; sp.save_rstd = save_rstd;
-  sp.sums = sums; sp.dgamma = dgamma; sp.dbeta = dbeta;
+  sp.sums = (StatAcc*)sums; sp.dgamma = dgamma; sp.dbeta = dbeta;
   return launch_stem_bwd(sp, (cudaStream_t)stream);
 }
 

@@ -20,6 +20,38 @@ namespace vpd {
 VPD_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 VPD_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// --------------------------------------------- order-independent statistics accumulators
+// Per-channel sums that many CTAs add to (BatchNorm batch statistics, BN-backward sums) are
+// kept as TWO 64-bit INTEGER limbs: value = hi * 2^-4 + lo * 2^-52. Integer atomic adds are
+// associative, so the total does not depend on the order in which the CTAs arrive: with the
+// fixed tile -> CTA assignment of the kernels the statistics, and everything downstream of
+// them, are bit-reproducible from run to run (fp64 atomics are not: a last-bit change of a
+// mean flips bf16 roundings that the quantised network then amplifies to its noise floor).
+// A contribution x (an fp32 partial sum widened to fp64) is split exactly: hi = rint(16 x),
+// the remainder (< 2^-5, exact in fp64) is quantised to 2^-52. Range per contribution
+// |x| < 2^58; resolution 2.2e-16 absolute, i.e. an fp32 partial >= 4e-9 keeps all its bits.
+struct __align__(16) StatAcc {
+  long long hi, lo;
+};
+VPD_DEVINL void stat_add(StatAcc* a, double x) {
+  const long long hi = __double2ll_rn(x * 16.0);
+  const double rem = x - static_cast<double>(hi) * 0.0625;
+  const long long lo = __double2ll_rn(rem * 4503599627370496.0);
+  atomicAdd(reinterpret_cast<unsigned long long*>(&a->hi), static_cast<unsigned long long>(hi));
+  atomicAdd(reinterpret_cast<unsigned long long*>(&a->lo), static_cast<unsigned long long>(lo));
+}
+VPD_DEVINL double stat_value(longlong2 v) {
+  return fma(static_cast<double>(v.y), 2.220446049250313e-16, static_cast<double>(v.x) * 0.0625);
+}
+// read-only path (sums produced by an EARLIER kernel)
+VPD_DEVINL double stat_read(const StatAcc* a) {
+  return stat_value(__ldg(reinterpret_cast<const longlong2*>(a)));
+}
+// through L2 (sums produced earlier in THIS kernel by other CTAs, behind a grid barrier)
+VPD_DEVINL double stat_read_cg(const StatAcc* a) {
+  return stat_value(__ldcg(reinterpret_cast<const longlong2*>(a)));
+}
+
 // ---------------------------------------------------------------- addresses
 VPD_DEVINL uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

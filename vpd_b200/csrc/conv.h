@@ -35,7 +35,7 @@ struct ConvEpilogue {
   const float* shift = nullptr;
   const __nv_bfloat16* residual = nullptr;
   int relu = 0;
-  double* stats = nullptr;
+  StatAcc* stats = nullptr;
   // optional: apply the training-mode BatchNorm of this conv in the same launch (grid
   // barrier; only taken when every CTA gets at most one tile): z = relu?(bn(y) (+ fuse_res))
   bool fuse_bn = false;
@@ -53,7 +53,7 @@ struct ConvBwdFuse {
   const __nv_bfloat16* y[2] = {nullptr, nullptr};
   const float* mean[2] = {nullptr, nullptr};
   const float* rstd[2] = {nullptr, nullptr};
-  double* sums[2] = {nullptr, nullptr};
+  StatAcc* sums[2] = {nullptr, nullptr};
 };
 
 int device_sm_count();

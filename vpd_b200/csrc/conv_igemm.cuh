@@ -19,7 +19,7 @@
 //   * epilogue warps read TMEM (tcgen05.ld), optionally apply a per-channel
 //     affine (folded eval-mode BN) + residual + ReLU, write bf16 NHWC, and in
 //     training mode accumulate the per-channel sum / sum-of-squares that
-//     BatchNorm needs (warp transpose-reduce -> smem -> fp64 global atomics).
+//     BatchNorm needs (warp transpose-reduce -> smem -> order-independent integer global atomics, see StatAcc).
 #pragma once
 #include "common.cuh"
 #include "elementwise.cuh"
@@ -78,7 +78,7 @@ struct ConvParams {
   const float* scale;                 // [cout] or null
   const float* shift;                 // [cout] or null
   int relu;
-  double* stats;                      // [2][cout] (sum, sumsq) or null
+  StatAcc* stats;                     // [2][cout] (sum, sumsq) or null
   // pre-tiled bf16 weights (see wtile_offset) for tap.src 0 / 1: element offset of the
   // [BLOCK_N x 64] tile (tap t, chunk kc, rows n0..) = ((t*w_kc + kc)*w_rb + n0/64) * 4096
   const __nv_bfloat16* w[2];
@@ -92,7 +92,7 @@ struct ConvParams {
   const __nv_bfloat16* by[2];         // its pre-BN conv outputs
   const float* bmean[2];              // [cout] saved batch mean
   const float* brstd[2];              // [cout] saved 1/sqrt(var+eps)
-  double* bsums[2];                   // [2][cout]: sum g, sum g*xhat
+  StatAcc* bsums[2];                  // [2][cout]: sum g, sum g*xhat
   // debug (vpd_conv_trace): 8 int64 per CTA - globaltimer at entry, then clock64 at
   // entry / after the dependency wait / first operands landed / last MMA issued /
   // first accumulator ready / epilogue done / exit
@@ -414,17 +414,17 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
     for (int i = st; i < BLOCK_N; i += kStatThreads) {
       const int c = ntile * BLOCK_N + i;
       if (fwd_stats) {
-        atomicAdd(&p.stats[c], static_cast<double>(s_sum[i]));
-        atomicAdd(&p.stats[p.cout + c], static_cast<double>(s_sq[i]));
+        stat_add(&p.stats[c], static_cast<double>(s_sum[i]));
+        stat_add(&p.stats[p.cout + c], static_cast<double>(s_sq[i]));
       } else {
         // sum g * xhat = rstd * sum g * (y - mean)
-        atomicAdd(&p.bsums[0][c], static_cast<double>(s_sum[i]));
-        atomicAdd(&p.bsums[0][p.cout + c],
-                  static_cast<double>(s_sq[i]) * static_cast<double>(__ldg(p.brstd[0] + c)));
+        stat_add(&p.bsums[0][c], static_cast<double>(s_sum[i]));
+        stat_add(&p.bsums[0][p.cout + c],
+                 static_cast<double>(s_sq[i]) * static_cast<double>(__ldg(p.brstd[0] + c)));
         if (nbr > 1) {
-          atomicAdd(&p.bsums[1][c], static_cast<double>(s_sum[i]));
-          atomicAdd(&p.bsums[1][p.cout + c],
-                    static_cast<double>(s_x2[i]) * static_cast<double>(__ldg(p.brstd[1] + c)));
+          stat_add(&p.bsums[1][c], static_cast<double>(s_sum[i]));
+          stat_add(&p.bsums[1][p.cout + c],
+                   static_cast<double>(s_x2[i]) * static_cast<double>(__ldg(p.brstd[1] + c)));
         }
       }
       s_sum[i] = 0.f;

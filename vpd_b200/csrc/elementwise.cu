@@ -6,6 +6,23 @@ namespace vpd {
 
 constexpr int kEwThreads = 256;
 
+// Deterministic block-level combine of per-thread column partials. Thread t = r0 * groups + g
+// holds eight partial sums for channels g*8 .. g*8+7 of its row lane r0; they go to
+// scr[r0][C] and channel c is then added up over the row lanes IN LANE ORDER by one thread.
+// (Shared-memory float atomics would add them in arrival order, so the rounding - and through
+// the BatchNorm statistics every activation downstream - would change from run to run.)
+constexpr int kColScratch = kEwThreads * 8;   // floats per quantity
+VPD_DEVINL void colsum_put(const float* acc, float* scr, int C, int g, int r0) {
+  float4* d = reinterpret_cast<float4*>(scr + r0 * C + g * 8);
+  d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+VPD_DEVINL float colsum_get(const float* scr, int C, int lanes, int c) {
+  float s = 0.f;
+  for (int r = 0; r < lanes; ++r) s += scr[r * C + c];
+  return s;
+}
+
 VPD_DEVINL void unpack8(const uint4& v, float (&f)[8]) {
   f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
   f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
@@ -29,6 +46,27 @@ VPD_DEVINL void bn_side_effects(const BnLayer& bn, int C) {
   if (bn.update_running && threadIdx.x == 0 && bn.num_batches) *bn.num_batches += 1;
 }
 
+// The BatchNorm affine of channel c is derived ONCE per CTA (by thread c, through the fp64
+// mean / variance path on the integer statistics accumulators) and shared through shared
+// memory, instead of by every thread that owns the channel: these kernels are latency-bound
+// and the fp64 prologue was a measurable part of every launch.
+constexpr int kMaxEwC = 2048;
+VPD_DEVINL void bn_stage_affine(const BnLayer& bn, int C, float* s_sc, float* s_sh) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, rstd, var, sc, sh;
+    bn_mean_rstd(bn, c, C, mean, rstd, var);
+    bn_affine(bn.gamma[c], bn.beta[c], mean, rstd, sc, sh);
+    s_sc[c] = sc;
+    s_sh[c] = sh;
+  }
+}
+VPD_DEVINL void load8(const float* s, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(s);
+  const float4 b = *reinterpret_cast<const float4*>(s + 4);
+  f[0] = a.x, f[1] = a.y, f[2] = a.z, f[3] = a.w;
+  f[4] = b.x, f[5] = b.y, f[6] = b.z, f[7] = b.w;
+}
+
 // ------------------------------------------------------------------ BN apply
 template <int RES>  // 0: no residual, 1: plain residual, 2: residual through its own BN
 __global__ void __launch_bounds__(kEwThreads, RES == 0 ? 4 : 3) bn_apply_kernel(const BnApplyParams p) {
@@ -38,19 +76,19 @@ __global__ void __launch_bounds__(kEwThreads, RES == 0 ? 4 : 3) bn_apply_kernel(
   const int g = threadIdx.x % groups;
   const int r0 = threadIdx.x / groups;
   const int rstep = kEwThreads / groups;
+  __shared__ __align__(16) float s_co[(RES == 2 ? 4 : 2) * kMaxEwC];
+  bn_stage_affine(p.bn, p.C, s_co, s_co + kMaxEwC);
+  if (RES == 2) bn_stage_affine(p.res_bn, p.C, s_co + 2 * kMaxEwC, s_co + 3 * kMaxEwC);
+  __syncthreads();
   float sc[8], sh[8], rsc[8], rsh[8];
+  load8(s_co + g * 8, sc);
+  load8(s_co + kMaxEwC + g * 8, sh);
+  if (RES == 2) {
+    load8(s_co + 2 * kMaxEwC + g * 8, rsc);
+    load8(s_co + 3 * kMaxEwC + g * 8, rsh);
+  } else {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = g * 8 + j;
-    float mean, rstd, var;
-    bn_mean_rstd(p.bn, c, p.C, mean, rstd, var);
-    bn_affine(p.bn.gamma[c], p.bn.beta[c], mean, rstd, sc[j], sh[j]);
-    rsc[j] = 1.f;
-    rsh[j] = 0.f;
-    if (RES == 2) {
-      bn_mean_rstd(p.res_bn, c, p.C, mean, rstd, var);
-      bn_affine(p.res_bn.gamma[c], p.res_bn.beta[c], mean, rstd, rsc[j], rsh[j]);
-    }
+    for (int j = 0; j < 8; ++j) rsc[j] = 1.f, rsh[j] = 0.f;
   }
   const long long chunk = (p.M + gridDim.x - 1) / gridDim.x;
   const long long beg = (long long)blockIdx.x * chunk;
@@ -134,14 +172,12 @@ __global__ void __launch_bounds__(kEwThreads) bn_pool_kernel(const PoolParams p)
   // channel group is fixed per thread when the grid stride is a multiple of `groups`
   const long long stride = (long long)gridDim.x * kEwThreads;
   const int g = threadIdx.x % groups;
+  __shared__ __align__(16) float s_co[2 * 512];
+  bn_stage_affine(p.bn, p.C, s_co, s_co + 512);
+  __syncthreads();
   float sc[8], sh[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = g * 8 + j;
-    float mean, rstd, var;
-    bn_mean_rstd(p.bn, c, p.C, mean, rstd, var);
-    bn_affine(p.bn.gamma[c], p.bn.beta[c], mean, rstd, sc[j], sh[j]);
-  }
+  load8(s_co + g * 8, sc);
+  load8(s_co + 512 + g * 8, sh);
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += stride) {
     long long pix = i / groups;
     const int wo = (int)(pix % Wo);
@@ -196,7 +232,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_pool_kernel(const PoolParams p)
 }
 
 int launch_bn_pool(const PoolParams& p, cudaStream_t s) {
-  VPD_REQUIRE(p.C % 64 == 0 && kEwThreads % (p.C / 8) == 0, "bn_pool: unsupported C=%d", p.C);
+  VPD_REQUIRE(p.C % 64 == 0 && p.C <= 512 && kEwThreads % (p.C / 8) == 0, "bn_pool: unsupported C=%d", p.C);
   VPD_REQUIRE(p.H % 2 == 0 && p.W % 2 == 0, "bn_pool: odd spatial dims");
   if (p.N == 0) return 0;
   const long long total = (long long)p.N * (p.H / 2) * (p.W / 2) * (p.C / 8);
@@ -278,11 +314,11 @@ int launch_bn_fold(const float* gamma, const float* beta, const float* rm, const
 // Used for the 64-channel layers, whose conv epilogue is the bottleneck: moving the
 // reduction out of it is cheaper than the extra (L2-resident) read.
 __global__ void __launch_bounds__(kEwThreads, 4)
-channel_stats_kernel(const __nv_bfloat16* __restrict__ y, long long M, int C, double* __restrict__ stats) {
+channel_stats_kernel(const __nv_bfloat16* __restrict__ y, long long M, int C, StatAcc* __restrict__ stats) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float s_a[512];
-  __shared__ float s_b[512];
+  __shared__ __align__(16) float s_a[kColScratch];
+  __shared__ __align__(16) float s_b[kColScratch];
   const int groups = C >> 3;
   const int g = threadIdx.x % groups;
   const int r0 = threadIdx.x / groups;
@@ -314,21 +350,16 @@ channel_stats_kernel(const __nv_bfloat16* __restrict__ y, long long M, int C, do
       }
     }
   }
-  for (int c = threadIdx.x; c < C; c += kEwThreads) s_a[c] = s_b[c] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&s_a[g * 8 + j], a[j]);
-    atomicAdd(&s_b[g * 8 + j], b[j]);
-  }
+  colsum_put(a, s_a, C, g, r0);
+  colsum_put(b, s_b, C, g, r0);
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += kEwThreads) {
-    atomicAdd(&stats[c], static_cast<double>(s_a[c]));
-    atomicAdd(&stats[C + c], static_cast<double>(s_b[c]));
+    stat_add(&stats[c], static_cast<double>(colsum_get(s_a, C, rstep, c)));
+    stat_add(&stats[C + c], static_cast<double>(colsum_get(s_b, C, rstep, c)));
   }
 }
 
-int launch_channel_stats(const __nv_bfloat16* y, long long M, int C, double* stats, cudaStream_t s) {
+int launch_channel_stats(const __nv_bfloat16* y, long long M, int C, StatAcc* stats, cudaStream_t s) {
   VPD_REQUIRE(C % 64 == 0 && C <= 512 && kEwThreads % (C / 8) == 0, "channel_stats: C=%d", C);
   if (M == 0) return 0;
   VPD_CHECK_CUDA(launch_kernel(channel_stats_kernel, dim3(ew_grid(M * (C / 8), 4, 4)),
@@ -347,31 +378,43 @@ template <bool kApply, int NB>
 __global__ void __launch_bounds__(kEwThreads, NB == 1 ? 3 : 2) bn_bwd_kernel(const BnBwdParams p) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float s_g[512];
-  __shared__ float s_gx[NB][512];
+  __shared__ __align__(16) float s_g[kApply ? 4 : kColScratch];
+  __shared__ __align__(16) float s_gx[NB][kApply ? 4 : kColScratch];
   const int groups = p.C >> 3;
   const int g = threadIdx.x % groups;
   const int r0 = threadIdx.x / groups;
   const int rstep = kEwThreads / groups;
-  // reduce: c0 = mean, c1 = rstd.  apply: dy = c0*g + c1*y + c2
+  // reduce: c0 = mean, c1 = rstd.  apply: dy = c0*g + c1*y + c2 (derived once per CTA and
+  // channel from the integer sums, then shared: see bn_stage_affine)
   float c0[NB][8], c1[NB][8], c2[NB][8];
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
+  if (kApply) {
+    __shared__ __align__(16) float s_co[kApply ? NB * 3 * 512 : 4];
+    for (int i = threadIdx.x; i < NB * p.C; i += kEwThreads) {
+      const int b = i / p.C, c = i - b * p.C;
       const float mean = __ldg(p.save_mean[b] + c), rstd = __ldg(p.save_rstd[b] + c);
-      if (kApply) {
-        const float invM = 1.0f / static_cast<float>(p.M);
-        const float k0 = __ldg(p.gamma[b] + c) * rstd;
-        const float k1 = static_cast<float>(p.sums[b][c]) * invM;
-        const float k2 = static_cast<float>(p.sums[b][p.C + c]) * invM;
-        c0[b][j] = k0;
-        c1[b][j] = -k0 * k2 * rstd;
-        c2[b][j] = -k0 * k1 + k0 * k2 * rstd * mean;
-      } else {
-        c0[b][j] = mean;
-        c1[b][j] = rstd;
+      const float invM = 1.0f / static_cast<float>(p.M);
+      const float k0 = __ldg(p.gamma[b] + c) * rstd;
+      const float k1 = static_cast<float>(stat_read(p.sums[b] + c)) * invM;
+      const float k2 = static_cast<float>(stat_read(p.sums[b] + p.C + c)) * invM;
+      s_co[(b * 3 + 0) * 512 + c] = k0;
+      s_co[(b * 3 + 1) * 512 + c] = -k0 * k2 * rstd;
+      s_co[(b * 3 + 2) * 512 + c] = -k0 * k1 + k0 * k2 * rstd * mean;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      load8(s_co + (b * 3 + 0) * 512 + g * 8, c0[b]);
+      load8(s_co + (b * 3 + 1) * 512 + g * 8, c1[b]);
+      load8(s_co + (b * 3 + 2) * 512 + g * 8, c2[b]);
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        c0[b][j] = __ldg(p.save_mean[b] + c);
+        c1[b][j] = __ldg(p.save_rstd[b] + c);
         c2[b][j] = 0.f;
       }
     }
@@ -441,28 +484,22 @@ __global__ void __launch_bounds__(kEwThreads, NB == 1 ? 3 : 2) bn_bwd_kernel(con
     if (blockIdx.x == 0) {
       for (int c = threadIdx.x; c < p.C; c += kEwThreads)
         for (int b = 0; b < NB; ++b) {
-          p.dbeta[b][c] = static_cast<float>(p.sums[b][c]);
-          p.dgamma[b][c] = static_cast<float>(p.sums[b][p.C + c]);
+          p.dbeta[b][c] = static_cast<float>(stat_read(p.sums[b] + c));
+          p.dgamma[b][c] = static_cast<float>(stat_read(p.sums[b] + p.C + c));
         }
     }
   } else {
+    colsum_put(acc_g, s_g, p.C, g, r0);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) colsum_put(acc_gx[b], s_gx[b], p.C, g, r0);
+    __syncthreads();
     for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
-      s_g[c] = 0.f;
-      for (int b = 0; b < NB; ++b) s_gx[b][c] = 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_g[g * 8 + j], acc_g[j]);
-#pragma unroll
-      for (int b = 0; b < NB; ++b) atomicAdd(&s_gx[b][g * 8 + j], acc_gx[b][j]);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < p.C; c += kEwThreads)
+      const double sg = static_cast<double>(colsum_get(s_g, p.C, rstep, c));
       for (int b = 0; b < NB; ++b) {
-        atomicAdd(&p.sums[b][c], static_cast<double>(s_g[c]));
-        atomicAdd(&p.sums[b][p.C + c], static_cast<double>(s_gx[b][c]));
+        stat_add(&p.sums[b][c], sg);
+        stat_add(&p.sums[b][p.C + c], static_cast<double>(colsum_get(s_gx[b], p.C, rstep, c)));
       }
+    }
   }
 }
 
@@ -495,8 +532,8 @@ int launch_bn_bwd(const BnBwdParams& p, cudaStream_t s) {
 __global__ void __launch_bounds__(kEwThreads) stem_bwd_reduce_kernel(const StemBwdParams p) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float s_g[512];
-  __shared__ float s_gx[512];
+  __shared__ __align__(16) float s_g[kColScratch];
+  __shared__ __align__(16) float s_gx[kColScratch];
   const int groups = p.C >> 3;
   const int g = threadIdx.x % groups;
   const int Ho = p.H / 2, Wo = p.W / 2;
@@ -557,17 +594,12 @@ __global__ void __launch_bounds__(kEwThreads) stem_bwd_reduce_kernel(const StemB
       acc_gx[j] = fmaf(gq, (ysel[j] - mean[j]) * rstd[j], acc_gx[j]);
     }
   }
-  for (int c = threadIdx.x; c < p.C; c += kEwThreads) s_g[c] = s_gx[c] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&s_g[g * 8 + j], acc_g[j]);
-    atomicAdd(&s_gx[g * 8 + j], acc_gx[j]);
-  }
+  colsum_put(acc_g, s_g, p.C, g, threadIdx.x / groups);
+  colsum_put(acc_gx, s_gx, p.C, g, threadIdx.x / groups);
   __syncthreads();
   for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
-    atomicAdd(&p.sums[c], static_cast<double>(s_g[c]));
-    atomicAdd(&p.sums[p.C + c], static_cast<double>(s_gx[c]));
+    stat_add(&p.sums[c], static_cast<double>(colsum_get(s_g, p.C, kEwThreads / groups, c)));
+    stat_add(&p.sums[p.C + c], static_cast<double>(colsum_get(s_gx, p.C, kEwThreads / groups, c)));
   }
 }
 
@@ -583,20 +615,28 @@ __global__ void __launch_bounds__(kEwThreads, 2) stem_bwd_apply_kernel(const Ste
   const int Ho = p.H / 2, Wo = p.W / 2;
   const long long M = (long long)p.N * p.H * p.W;
   float sc[8], sh[8], a0[8], a1[8], a2[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = g * 8 + j;
+  __shared__ __align__(16) float s_co[5 * 512];
+  for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
     const float mean = __ldg(p.save_mean + c), rstd = __ldg(p.save_rstd + c);
     const float gamma = __ldg(p.gamma + c);
-    bn_affine(gamma, __ldg(p.beta + c), mean, rstd, sc[j], sh[j]);
+    float scc, shc;
+    bn_affine(gamma, __ldg(p.beta + c), mean, rstd, scc, shc);
     const float invM = 1.0f / static_cast<float>(M);
     const float k0 = gamma * rstd;
-    const float k1 = static_cast<float>(p.sums[c]) * invM;
-    const float k2 = static_cast<float>(p.sums[p.C + c]) * invM;
-    a0[j] = k0;
-    a1[j] = -k0 * k2 * rstd;
-    a2[j] = -k0 * k1 + k0 * k2 * rstd * mean;
+    const float k1 = static_cast<float>(stat_read(p.sums + c)) * invM;
+    const float k2 = static_cast<float>(stat_read(p.sums + p.C + c)) * invM;
+    s_co[c] = scc;
+    s_co[512 + c] = shc;
+    s_co[2 * 512 + c] = k0;
+    s_co[3 * 512 + c] = -k0 * k2 * rstd;
+    s_co[4 * 512 + c] = -k0 * k1 + k0 * k2 * rstd * mean;
   }
+  __syncthreads();
+  load8(s_co + g * 8, sc);
+  load8(s_co + 512 + g * 8, sh);
+  load8(s_co + 2 * 512 + g * 8, a0);
+  load8(s_co + 3 * 512 + g * 8, a1);
+  load8(s_co + 4 * 512 + g * 8, a2);
   const long long total = (long long)p.N * Ho * Wo * groups;   // quads x channel groups
   const long long stride = (long long)gridDim.x * kEwThreads;
   for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += stride) {
@@ -671,8 +711,8 @@ __global__ void __launch_bounds__(kEwThreads, 2) stem_bwd_apply_kernel(const Ste
   }
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
-      p.dbeta[c] = static_cast<float>(p.sums[c]);
-      p.dgamma[c] = static_cast<float>(p.sums[p.C + c]);
+      p.dbeta[c] = static_cast<float>(stat_read(p.sums + c));
+      p.dgamma[c] = static_cast<float>(stat_read(p.sums + p.C + c));
     }
 }
 

@@ -9,11 +9,11 @@
 
 namespace vpd {
 
-// Per-BatchNorm-layer pointers. Training: `stats` holds the fp64 sum / sumsq
-// produced by the conv epilogue; evaluation: stats == nullptr and the running
-// buffers are used.
+// Per-BatchNorm-layer pointers. Training: `stats` holds the sum / sumsq produced by
+// the conv epilogue (order-independent integer accumulators, see StatAcc);
+// evaluation: stats == nullptr and the running buffers are used.
 struct BnLayer {
-  const double* stats;     // [2][C] or null (eval)
+  const StatAcc* stats;    // [2][C] or null (eval)
   const float* gamma;      // [C]
   const float* beta;       // [C]
   float* running_mean;     // [C]
@@ -38,8 +38,8 @@ VPD_DEVINL void bn_mean_rstd(const BnLayer& bn, int c, int C, float& mean, float
                              float& var_biased) {
   if (bn.stats != nullptr) {
     const double inv = bn.inv_count;
-    const double s0 = kCoherent ? __ldcg(bn.stats + c) : __ldg(bn.stats + c);
-    const double s1 = kCoherent ? __ldcg(bn.stats + C + c) : __ldg(bn.stats + C + c);
+    const double s0 = kCoherent ? stat_read_cg(bn.stats + c) : stat_read(bn.stats + c);
+    const double s1 = kCoherent ? stat_read_cg(bn.stats + C + c) : stat_read(bn.stats + C + c);
     const double m = s0 * inv;
     double v = fma(s1, inv, -m * m);
     if (v < 0.0) v = 0.0;
@@ -104,7 +104,7 @@ struct BnBwdParams {
   const float* gamma[2];
   const float* save_mean[2];
   const float* save_rstd[2];
-  double* sums[2];           // [2][C] scratch: sum g, sum g*xhat (zeroed by caller)
+  StatAcc* sums[2];          // [2][C] scratch: sum g, sum g*xhat (zeroed by caller)
   float* dgamma[2];          // [C] out
   float* dbeta[2];           // [C] out
 };
@@ -119,13 +119,13 @@ struct StemBwdParams {       // maxpool + ReLU + BN backward of the stem
   const float* save_mean;
   const float* save_rstd;
   const float* beta;
-  double* sums;                // [2][C]
+  StatAcc* sums;               // [2][C]
   float* dgamma;
   float* dbeta;
 };
 
 int launch_bn_apply(const BnApplyParams& p, cudaStream_t s);
-int launch_channel_stats(const __nv_bfloat16* y, long long M, int C, double* stats, cudaStream_t s);
+int launch_channel_stats(const __nv_bfloat16* y, long long M, int C, StatAcc* stats, cudaStream_t s);
 int launch_bn_pool(const PoolParams& p, cudaStream_t s);
 int launch_bn_bwd(const BnBwdParams& p, cudaStream_t s);    // reduce + apply
 int launch_stem_bwd(const StemBwdParams& p, cudaStream_t s);

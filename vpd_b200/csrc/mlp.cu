@@ -175,7 +175,7 @@ dropout_mask_kernel(uint8_t* __restrict__ keep, long long n4, float p_drop,
 
 struct Bn1dParams {
   const __nv_bfloat16* a;      // [M][C] pre-BN Linear output WITHOUT its bias
-  const double* stats;         // [2][C] sum, sum of squares of `a` over the M rows
+  const StatAcc* stats;        // [2][C] sum, sum of squares of `a` over the M rows
   const float* gamma;
   const float* beta;
   const float* lin_bias;       // the Linear's bias: only shifts the batch mean (running_mean)
@@ -205,15 +205,15 @@ bn1d_fwd_kernel(const Bn1dParams p) {
   const int rstep = 256 / groups;                 // rows per CTA pass; threads beyond are idle
   const int gg = threadIdx.x % groups, rl = threadIdx.x / groups;
   const int grp = blockIdx.y;
-  const double* stats = p.stats + (size_t)grp * 2 * p.C;
+  const StatAcc* stats = p.stats + (size_t)grp * 2 * p.C;
   const size_t base = (size_t)grp * p.M * p.C;
   if (rl < rstep) {
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = gg * 8 + j;
-      const double mean = stats[c] / static_cast<double>(p.M);
-      double var = stats[p.C + c] / static_cast<double>(p.M) - mean * mean;
+      const double mean = stat_read(stats + c) / static_cast<double>(p.M);
+      double var = stat_read(stats + p.C + c) / static_cast<double>(p.M) - mean * mean;
       if (var < 0.0) var = 0.0;
       const float rstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
       sc[j] = p.gamma[c] * rstd;
@@ -225,8 +225,8 @@ bn1d_fwd_kernel(const Bn1dParams p) {
           const float bias = p.lin_bias ? p.lin_bias[c] : 0.f;
           float rm = p.running_mean[c], rv = p.running_var[c];
           for (int q = 0; q < (int)gridDim.y; ++q) {
-            const double m = p.stats[(size_t)q * 2 * p.C + c] / static_cast<double>(p.M);
-            double v = p.stats[(size_t)q * 2 * p.C + p.C + c] / static_cast<double>(p.M) - m * m;
+            const double m = stat_read(p.stats + (size_t)q * 2 * p.C + c) / static_cast<double>(p.M);
+            double v = stat_read(p.stats + (size_t)q * 2 * p.C + p.C + c) / static_cast<double>(p.M) - m * m;
             if (v < 0.0) v = 0.0;
             const double unbiased = p.M > 1 ? v * static_cast<double>(p.M) / static_cast<double>(p.M - 1) : v;
             rm = (1.f - p.momentum) * rm + p.momentum * (static_cast<float>(m) + bias);
@@ -274,7 +274,7 @@ struct Bn1dBwdParams {
   const float* beta;
   const float* save_mean;
   const float* save_rstd;
-  double* sums;                // [2][C] scratch: sum g, sum g * xhat (zeroed by the caller)
+  StatAcc* sums;               // [2][C] scratch: sum g, sum g * xhat (zeroed by the caller)
   __nv_bfloat16* da;           // [M][C]
   float* dgamma;               // += (weights are shared by the three encoder passes)
   float* dbeta;                // +=
@@ -292,7 +292,7 @@ bn1d_bwd_kernel(const Bn1dBwdParams p) {
   const int rstep = 256 / groups;
   const int gg = threadIdx.x % groups, rl = threadIdx.x / groups;
   const int grp = blockIdx.y;
-  double* sums = p.sums + (size_t)grp * 2 * p.C;
+  StatAcc* sums = p.sums + (size_t)grp * 2 * p.C;
   const size_t base = (size_t)grp * p.M * p.C;
   if (rl < rstep) {
     float mean[8], rstd[8], ga[8], be[8], k1[8], k2[8];
@@ -303,8 +303,8 @@ bn1d_bwd_kernel(const Bn1dBwdParams p) {
       rstd[j] = p.save_rstd[(size_t)grp * p.C + c];
       ga[j] = p.gamma[c];
       be[j] = p.beta[c];
-      k1[j] = kApply ? static_cast<float>(sums[c] / static_cast<double>(p.M)) : 0.f;
-      k2[j] = kApply ? static_cast<float>(sums[p.C + c] / static_cast<double>(p.M)) : 0.f;
+      k1[j] = kApply ? static_cast<float>(stat_read(sums + c) / static_cast<double>(p.M)) : 0.f;
+      k2[j] = kApply ? static_cast<float>(stat_read(sums + p.C + c) / static_cast<double>(p.M)) : 0.f;
     }
     float sg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sgx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const long long r0 = (long long)blockIdx.x * rstep + rl;
@@ -338,15 +338,15 @@ bn1d_bwd_kernel(const Bn1dBwdParams p) {
     if (!kApply) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sums[gg * 8 + j], static_cast<double>(sg[j]));
-        atomicAdd(&sums[p.C + gg * 8 + j], static_cast<double>(sgx[j]));
+        stat_add(&sums[gg * 8 + j], static_cast<double>(sg[j]));
+        stat_add(&sums[p.C + gg * 8 + j], static_cast<double>(sgx[j]));
       }
     } else if (blockIdx.x == 0 && rl == 0) {
       // the groups (and earlier launches of the step) accumulate into the same dgamma / dbeta
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&p.dbeta[gg * 8 + j], static_cast<float>(sums[gg * 8 + j]));
-        atomicAdd(&p.dgamma[gg * 8 + j], static_cast<float>(sums[p.C + gg * 8 + j]));
+        atomicAdd(&p.dbeta[gg * 8 + j], static_cast<float>(stat_read(sums + gg * 8 + j)));
+        atomicAdd(&p.dgamma[gg * 8 + j], static_cast<float>(stat_read(sums + p.C + gg * 8 + j)));
       }
     }
   }
@@ -396,7 +396,7 @@ bn1d_bwd_reduce_kernel(const Bn1dBwdParams p, int ccta) {
   pdl_wait();
   const RedMap m = red_map(ccta);
   const int grp = blockIdx.y;
-  double* sums = p.sums + (size_t)grp * 2 * p.C;
+  StatAcc* sums = p.sums + (size_t)grp * 2 * p.C;
   const size_t base = (size_t)grp * p.M * p.C;
   float sg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, sgx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (m.rl < m.rstep) {
@@ -431,14 +431,14 @@ bn1d_bwd_reduce_kernel(const Bn1dBwdParams p, int ccta) {
   }
   const int C = p.C;
   red_finish(m, ccta, sg, sgx, true, [sums, C](int c, float a, float b) {
-    atomicAdd(&sums[c], static_cast<double>(a));
-    atomicAdd(&sums[C + c], static_cast<double>(b));
+    stat_add(&sums[c], static_cast<double>(a));
+    stat_add(&sums[C + c], static_cast<double>(b));
   });
 }
 
 // stats[g][0][c] += sum_r x, stats[g][1][c] += sum_r x^2 over the rows of group g = blockIdx.y
 __global__ void __launch_bounds__(256)
-colstats_bf16_kernel(const __nv_bfloat16* __restrict__ x, double* stats, long long M, int C, int ccta) {
+colstats_bf16_kernel(const __nv_bfloat16* __restrict__ x, StatAcc* stats, long long M, int C, int ccta) {
   pdl_trigger();
   pdl_wait();
   const RedMap m = red_map(ccta);
@@ -456,10 +456,10 @@ colstats_bf16_kernel(const __nv_bfloat16* __restrict__ x, double* stats, long lo
       }
     }
   }
-  double* st = stats + (size_t)grp * 2 * C;
+  StatAcc* st = stats + (size_t)grp * 2 * C;
   red_finish(m, ccta, s, q, true, [st, C](int c, float a, float b) {
-    atomicAdd(&st[c], static_cast<double>(a));
-    atomicAdd(&st[C + c], static_cast<double>(b));
+    stat_add(&st[c], static_cast<double>(a));
+    stat_add(&st[C + c], static_cast<double>(b));
   });
 }
 
@@ -639,11 +639,11 @@ int linear_rows_f32(const __nv_bfloat16* x, const float* w, const float* bias, f
   return 0;
 }
 
-__global__ void __launch_bounds__(256) zero_f64_kernel(double* p, int n) {
+__global__ void __launch_bounds__(256) zero_acc_kernel(StatAcc* p, int n) {
   pdl_trigger();
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = 0.0;
+  if (i < n) p[i] = StatAcc{0, 0};
 }
 
 static unsigned rows_grid(long long M, int C, long long cap = 148 * 4) {
@@ -681,7 +681,7 @@ int dropout_mask(uint8_t* keep, long long n, float p_drop, unsigned long long se
   return 0;
 }
 
-int bn1d_fwd(const __nv_bfloat16* a, const double* stats, const float* gamma, const float* beta,
+int bn1d_fwd(const __nv_bfloat16* a, const StatAcc* stats, const float* gamma, const float* beta,
              const float* lin_bias, float* running_mean, float* running_var, long long* num_batches,
              float* save_mean, float* save_rstd, const uint8_t* keep, float p_drop,
              const __nv_bfloat16* res, __nv_bfloat16* out, long long M, int C, int groups,
@@ -702,7 +702,7 @@ int bn1d_fwd(const __nv_bfloat16* a, const double* stats, const float* gamma, co
 
 int bn1d_bwd(const __nv_bfloat16* dz, const __nv_bfloat16* a, const uint8_t* keep, float p_drop,
              const float* gamma, const float* beta, const float* save_mean, const float* save_rstd,
-             double* sums, __nv_bfloat16* da, float* dgamma, float* dbeta, long long M, int C,
+             StatAcc* sums, __nv_bfloat16* da, float* dgamma, float* dbeta, long long M, int C,
              int groups, cudaStream_t stream) {
   VPD_ROWS_OK(C);
   VPD_REQUIRE(M >= 1 && groups >= 1 && groups <= 64, "bn1d_bwd: empty batch / bad group count");
@@ -711,18 +711,18 @@ int bn1d_bwd(const __nv_bfloat16* dz, const __nv_bfloat16* a, const uint8_t* kee
   p.gamma = gamma; p.beta = beta; p.save_mean = save_mean; p.save_rstd = save_rstd;
   p.sums = sums; p.da = da; p.dgamma = dgamma; p.dbeta = dbeta; p.M = M; p.C = C;
   // a kernel, not a memset node: the step is captured into a CUDA graph with programmatic edges
-  VPD_CHECK_CUDA(launch_kernel(zero_f64_kernel, dim3((2 * C * groups + 255) / 256), dim3(256), 0, stream, sums, 2 * C * groups));
+  VPD_CHECK_CUDA(launch_kernel(zero_acc_kernel, dim3((2 * C * groups + 255) / 256), dim3(256), 0, stream, sums, 2 * C * groups));
   VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_reduce_kernel, red_grid(M, C, groups), dim3(256), 0, stream, p, red_ccta(C)));
   VPD_CHECK_CUDA(launch_kernel(bn1d_bwd_kernel<true>, dim3(rows_grid(M, C, 148 * 4 / groups + 1), groups), dim3(256), 0, stream, p));
   VPD_LAUNCHED(3);
   return 0;
 }
 
-int colstats_bf16(const __nv_bfloat16* x, double* stats, long long M, int C, int groups,
+int colstats_bf16(const __nv_bfloat16* x, StatAcc* stats, long long M, int C, int groups,
                   cudaStream_t stream) {
   VPD_ROWS_OK(C);
   VPD_REQUIRE(M >= 1 && groups >= 1 && groups <= 64, "colstats: empty batch / bad group count");
-  VPD_CHECK_CUDA(launch_kernel(zero_f64_kernel, dim3((2 * C * groups + 255) / 256), dim3(256), 0, stream, stats, 2 * C * groups));
+  VPD_CHECK_CUDA(launch_kernel(zero_acc_kernel, dim3((2 * C * groups + 255) / 256), dim3(256), 0, stream, stats, 2 * C * groups));
   VPD_CHECK_CUDA(launch_kernel(colstats_bf16_kernel, red_grid(M, C, groups), dim3(256), 0, stream, x, stats, M, C, red_ccta(C)));
   VPD_LAUNCHED(2);
   return 0;

@@ -212,8 +212,8 @@ struct Net {
   // workspace carve
   long long ws_need = 0;
   bf16 *w_tap, *wT_tap;            // bf16 mirrors of section [A]
-  double* stats;                   // [2][total_ch] forward sum/sumsq   (zeroed per step)
-  double* bwd_sums;                // [2][total_ch] backward sums        (zeroed per step)
+  StatAcc* stats;                  // [2][total_ch] forward sum/sumsq   (zeroed per step)
+  StatAcc* bwd_sums;               // [2][total_ch] backward sums        (zeroed per step)
   unsigned int* bn_bar;            // one grid-barrier counter per BN layer (fused BN apply)
   double* loss_dev;                // scalar
   float *save_mean, *save_rstd;    // [total_ch]
@@ -463,8 +463,8 @@ static long long carve(Net* n, uint8_t* base) {
   const long long B = n->maxB;
   n->w_tap = c.take<bf16>(n->secA_len);
   n->wT_tap = c.take<bf16>(n->secA_len);
-  n->stats = c.take<double>(2 * n->total_ch);
-  n->bwd_sums = c.take<double>(2 * n->total_ch);
+  n->stats = c.take<StatAcc>(2 * n->total_ch);
+  n->bwd_sums = c.take<StatAcc>(2 * n->total_ch);
   n->bn_bar = c.take<unsigned int>(n->num_bn + 8);   // grid-barrier counters (zeroed per step)
   n->loss_dev = c.take<double>(8);
   n->save_mean = c.take<float>(n->total_ch);

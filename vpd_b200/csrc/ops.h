@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "common.cuh"
+
 namespace vpd {
 
 // optional masked-noise augmentation of the assembled training batch (see assemble.cu)
@@ -51,16 +53,16 @@ int linear_rows_f32(const __nv_bfloat16* x, const float* w, const float* bias, f
 
 int dropout_mask(uint8_t* keep, long long n, float p_drop, unsigned long long seed,
                  const unsigned long long* seed_add, unsigned int stream_id, cudaStream_t stream);
-int bn1d_fwd(const __nv_bfloat16* a, const double* stats, const float* gamma, const float* beta,
+int bn1d_fwd(const __nv_bfloat16* a, const StatAcc* stats, const float* gamma, const float* beta,
              const float* lin_bias, float* running_mean, float* running_var, long long* num_batches,
              float* save_mean, float* save_rstd, const uint8_t* keep, float p_drop,
              const __nv_bfloat16* res, __nv_bfloat16* out, long long M, int C, int groups,
              cudaStream_t stream);
 int bn1d_bwd(const __nv_bfloat16* dz, const __nv_bfloat16* a, const uint8_t* keep, float p_drop,
              const float* gamma, const float* beta, const float* save_mean, const float* save_rstd,
-             double* sums, __nv_bfloat16* da, float* dgamma, float* dbeta, long long M, int C,
+             StatAcc* sums, __nv_bfloat16* da, float* dgamma, float* dbeta, long long M, int C,
              int groups, cudaStream_t stream);
-int colstats_bf16(const __nv_bfloat16* x, double* stats, long long M, int C, int groups,
+int colstats_bf16(const __nv_bfloat16* x, StatAcc* stats, long long M, int C, int groups,
                   cudaStream_t stream);
 int relu_mask_bf16(const __nv_bfloat16* d, const __nv_bfloat16* z, __nv_bfloat16* out, long long n,
                    cudaStream_t stream);

@@ -52,3 +52,47 @@ def epoch_loss(loss_sum, frames):
     dist.all_reduce(total, op=dist.ReduceOp.SUM)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     return total.item() / cnt.item()
+
+
+def rank():
+    dist = active()
+    return 0 if dist is None else dist.get_rank()
+
+
+def barrier():
+    dist = active()
+    if dist is not None:
+        dist.barrier()
+
+
+def broadcast_state(tensors, src=0):
+    """Replicas must START identical: copy rank `src`'s parameters / BN buffers / counters (and
+    optimizer moments when resuming) to every rank. The reference has no DP; DDP does the same
+    broadcast at construction. No-op without an initialised process group."""
+    dist = active()
+    if dist is None:
+        return
+    for t in tensors:
+        if t is not None:
+            dist.broadcast(t, src=src)
+
+
+def check_bucket_sums(got, expect, buckets, rtol=1e-4):
+    """Per bucket: is `got` (the arena after the trainer's bucketed all-reduce) the SUM over ranks
+    `expect` (all-reduce of every rank's local gradients of the same step)? A bucket that was
+    never exchanged still holds one rank's local gradient, i.e. a relative error of order 1, so
+    every bucket is judged on its own norm, not the arena's.
+    -> {'ok', 'max_rel', 'per_bucket': [(offset, count, rel)]}; buckets must tile the arena."""
+    covered = sorted((int(o), int(c)) for o, c in buckets)
+    pos = 0
+    for o, c in covered:
+        assert o == pos, 'buckets must partition the gradient arena (gap/overlap at {})'.format(o)
+        pos = o + c
+    assert pos == got.numel() == expect.numel(), 'buckets cover {} of {}'.format(pos, got.numel())
+    per = []
+    for o, c in covered:
+        e = expect[o:o + c].double()
+        rel = ((got[o:o + c].double() - e).norm() / (e.norm() + 1e-300)).item()
+        per.append((o, c, rel))
+    max_rel = max(r for _, _, r in per)
+    return {'ok': bool(max_rel <= rtol), 'max_rel': max_rel, 'per_bucket': per}

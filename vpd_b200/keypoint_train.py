@@ -244,7 +244,7 @@ class KeypointTrainCore:
         self.weights_dirty = False
 
     def _fwd(self, x, name, y, relu, bias=True, stats=None):
-        """y = [relu](x . W^T [+ b]) as a 1x1 convolution; stats: fp64 [2][Cout] (+=, no bias)"""
+        """y = [relu](x . W^T [+ b]) as a 1x1 convolution; stats: vpd_stat_acc [2][Cout] (+=, no bias)"""
         cout, cin = self.arena.entries[name + '.weight'][1]
         n = x.shape[0]
         scale = shift = None
@@ -298,7 +298,7 @@ class KeypointTrainCore:
             for j, (lin, bn) in enumerate(((0, 1), (4, 5))):
                 a = self._bf(N, H)
                 self._fwd(z, 'enc.{}.{}'.format(p, lin), a, relu=False, bias=False)
-                stats = torch.empty(groups * 2 * H, device=self.dev, dtype=torch.float64)
+                stats = torch.empty((groups * 2 * H, 2), device=self.dev, dtype=torch.int64)
                 L.call('vpd_colstats_bf16', a, stats, n, H, groups, st)
                 keep = self._mask(N, None if masks is None else masks[2 * i + j])
                 out = self._bf(N, H)
@@ -326,7 +326,7 @@ class KeypointTrainCore:
         L, st, H, n, N, G = lib(), self._st(), self.H, ctx['n'], ctx['N'], ctx['groups']
         dh = self._bf(N, H)
         self._bwd_linear(ctx['h_last'], de_bf16, self.last, dx=dh)
-        sums = torch.empty(G * 2 * H, device=self.dev, dtype=torch.float64)
+        sums = torch.empty((G * 2 * H, 2), device=self.dev, dtype=torch.int64)
         for blk in reversed(ctx['blocks']):
             s2, s1 = blk['stage'][1], blk['stage'][0]
             da2 = self._bf(N, H)

@@ -28,11 +28,20 @@ def get_moving_avg_loss(losses, n, key):      # train_vpd_model.py:114-115
 def fit(trainer, train_loader, val_loader, save_dir, config, num_epochs, optimizer, scaler=None,
         model_select_window=5, checkpoint_frequency=None, dataset='synthetic', log=print):
     """Runs `num_epochs` epochs; returns the loss history (the content of loss.json)."""
+    from . import dp
     missing = [k for k in CONFIG_KEYS if k not in config]
     assert not missing, 'config lacks {}'.format(missing)
-    os.makedirs(save_dir)                      # like the reference: refuses to overwrite a run
-    with open(os.path.join(save_dir, 'config.json'), 'w') as fp:
-        json.dump({k: config[k] for k in CONFIG_KEYS}, fp, indent=2)
+    # data parallel: rank 0 owns the run directory (config, loss history, checkpoints - the BN
+    # running statistics saved are rank 0's); the epoch losses are reduced over all ranks, so
+    # every rank takes the same branches below
+    main_rank = dp.rank() == 0
+    if main_rank:
+        os.makedirs(save_dir)                  # like the reference: refuses to overwrite a run
+        with open(os.path.join(save_dir, 'config.json'), 'w') as fp:
+            json.dump({k: config[k] for k in CONFIG_KEYS}, fp, indent=2)
+    else:
+        log = lambda *a, **k: None             # noqa: E731
+    dp.barrier()
     loss_file = os.path.join(save_dir, 'loss.json')
     losses = []
     best_val_loss = float('inf')
@@ -49,18 +58,23 @@ def fit(trainer, train_loader, val_loader, save_dir, config, num_epochs, optimiz
         log('Epoch {} - train loss: {:0.4f} [avg: {:0.4f}] val loss: {:0.4f} [avg: {:0.4f}]'.format(
             epoch, train_loss, get_moving_avg_loss(losses, model_select_window, 'train'),
             val_loss, moving_avg_val_loss))
-        with open(loss_file, 'w') as fp:
-            json.dump(losses, fp, indent=2)
+        if main_rank:
+            with open(loss_file, 'w') as fp:
+                json.dump(losses, fp, indent=2)
         if moving_avg_val_loss < best_val_loss:
             log('New best epoch!')
-            trainer.save_model(save_dir, 'best_epoch')
+            if main_rank:
+                trainer.save_model(save_dir, 'best_epoch')
         if checkpoint_frequency is not None and epoch % checkpoint_frequency == 0:
             log('Saving checkpoint: {}'.format(epoch))
-            trainer.save_model(save_dir, 'epoch{:04d}'.format(epoch))
+            if main_rank:
+                trainer.save_model(save_dir, 'epoch{:04d}'.format(epoch))
         best_val_loss = min(moving_avg_val_loss, best_val_loss)
     if epoch > 0:
         log('Saving last epoch: {}'.format(epoch))
-        trainer.save_model(save_dir, 'epoch{:04d}'.format(epoch))
+        if main_rank:
+            trainer.save_model(save_dir, 'epoch{:04d}'.format(epoch))
+    dp.barrier()
     return losses
 
 
@@ -82,15 +96,21 @@ class PoolLoader:
     (exact, but 3*H*W floats per noisy frame over PCIe) instead of the device generator.
     `fast_draws=True` draws the same distributions in batched calls from the loader's own
     generator (`seed`): 0.3 ms instead of 22 ms of host time per 256 frames, not
-    stream-identical with the reference."""
+    stream-identical with the reference.
+    Flips follow the reference (single_frame.py:171-174): a frame is flipped only when the
+    dataset augments AND its teacher entry has the two rows [as is, flipped]; with
+    `augment=False` no frame is flipped unless `random_flip=True` asks for the flip alone
+    (still only with two-row teachers - a one-row target has no flipped counterpart)."""
 
     def __init__(self, rgb_u8, flow_u8, teacher, rgb_mean_std, batch_size, target_len, seed=0,
-                 mask_u8=None, augment=False, has_mask=None, host_noise=False, fast_draws=False):
+                 mask_u8=None, augment=False, has_mask=None, host_noise=False, fast_draws=False,
+                 random_flip=False):
         import torch
         self.rgb, self.flow, self.teacher = rgb_u8, flow_u8, teacher
         self.mask = mask_u8
         self.augment, self.has_mask, self.host_noise = augment, has_mask, host_noise
         self.fast_draws = fast_draws
+        self.random_flip = random_flip
         if augment and mask_u8 is not None and has_mask is None:
             self.has_mask = torch.ones(rgb_u8.shape[0], dtype=torch.bool)
         self.rgb_mean_std = rgb_mean_std
@@ -126,7 +146,9 @@ class PoolLoader:
                                          teacher=self.teacher, mask=self.mask)
                 continue
             idx = torch.randint(0, n, (b,), generator=self.gen).int().to(dev)
-            flip = torch.randint(0, 2, (b,), generator=self.gen).to(torch.uint8).to(dev)
+            flip = None
+            if self.random_flip and self.teacher is not None and self.teacher.dim() == 3:
+                flip = torch.randint(0, 2, (b,), generator=self.gen).to(torch.uint8).to(dev)
             kw = {}
             if self.mask is not None:
                 from .assemble import RANDOM_MASK_PROB

@@ -117,13 +117,19 @@ class ModelTrainer:
         self._bucket_cb = _BUCKET_FN(self._on_bucket)
         self._hooked = None
         self._pending = []
+        self._buckets_seen = []          # (offset, count) handed out by the last train step
         self.overlap_allreduce = os.environ.get('VPD_DP_OVERLAP', '1') != '0'
+        # data parallel: every replica starts from rank 0's parameters, BN running statistics
+        # and counters (identical seeds are NOT assumed - an augmenting loader draws from the
+        # same global generators the constructor does, and those must differ per rank)
+        dp.broadcast_state([encoder._params, encoder._buffers, encoder._nbt])
 
     def _on_bucket(self, user, offset, count):
         """Called by the native step when grads[offset:offset+count] are enqueued."""
         dist = _dist()
         if dist is None or count <= 0:
             return
+        self._buckets_seen.append((int(offset), int(count)))
         enc = self.encoder
         cur = torch.cuda.current_stream(enc._dev)
         ev = torch.cuda.Event()
@@ -150,6 +156,7 @@ class ModelTrainer:
         with torch.cuda.device(enc._dev):
             if train:
                 enc._ensure_grads()
+                self._buckets_seen = []
             net = enc._native(H, W, n)
             self._overlapped = self._hook(net) if train else False
             fn = 'vpd_net_train_step' if train else 'vpd_net_eval_loss'
@@ -164,12 +171,53 @@ class ModelTrainer:
         enc = self.encoder
         with torch.cuda.device(enc._dev):
             enc._ensure_grads()
+            self._buckets_seen = []
             net = enc._native(height, width, n)
             self._overlapped = self._hook(net)
             lib().call('vpd_net_train_step', net.handle, None, stem, tgt, n, self._loss,
                        stream_ptr(enc._dev))
             self._sync_grads()
             optimizer.step()
+
+    def dp_self_check(self, img, tgt, n, rtol=1e-4):
+        """Data-parallel correctness of ONE step, judged bucket by bucket: the
+        gradient arena the trainer's path leaves behind (bucketed all-reduce overlapped with the
+        backward pass, or the single call) must equal the SUM over ranks of the gradients every
+        rank computes on its own for the same batch. Runs the step twice on `img`/`tgt` (fp32
+        NCHW batch + targets on the device): once without any exchange, then through the
+        trainer; the two runs agree bit for bit in everything but the weight-gradient kernels'
+        fp32 atomics (integer BatchNorm statistics), so the bar is fp32 rounding, and a bucket
+        that was never reduced misses it by four orders of magnitude. Does not touch the
+        parameters or the BN running statistics. -> dp.check_bucket_sums(...) + {'buckets', 'overlapped'}; every rank must
+        call it (collectives inside)."""
+        dist = _dist()
+        enc = self.encoder
+        H, W = img.shape[-2:]
+        loss_keep = self._loss.clone()
+        with torch.cuda.device(enc._dev):
+            enc._ensure_grads()
+            net = enc._native(H, W, n)
+            keep = (enc._buffers.clone(), enc._nbt.clone())     # BN running state is restored
+            lib().call('vpd_net_set_bucket_callback', net.handle, None, None)
+            self._hooked = None
+            lib().call('vpd_net_train_step', net.handle, img, None, tgt, n, self._loss,
+                       stream_ptr(enc._dev))
+            expect = enc._grads.clone()
+            if dist is not None:
+                dist.all_reduce(expect, op=dist.ReduceOp.SUM)
+            self._run(img, tgt, n, True)
+            self._sync_grads()
+            torch.cuda.synchronize(enc._dev)
+            buckets = list(self._buckets_seen) if self._overlapped else []
+            if not buckets:
+                buckets = [(0, enc._grads.numel())]
+            res = dp.check_bucket_sums(enc._grads, expect, buckets, rtol=rtol)
+            enc._buffers.copy_(keep[0])
+            enc._nbt.copy_(keep[1])
+        self._loss.copy_(loss_keep)
+        res['buckets'] = len(buckets)
+        res['overlapped'] = bool(self._overlapped)
+        return res
 
     def stem_buffer(self, n, height, width):
         """Raw device pointer of the bound net's own input buffer (so assembly can
@@ -209,6 +257,7 @@ class ModelTrainer:
         with torch.cuda.device(enc._dev):
             if train:
                 enc._ensure_grads()
+                self._buckets_seen = []
             net = enc._native(H, W, n)
             stem = lib().call('vpd_net_stem_input', net.handle)
             if teacher is not None:
@@ -329,9 +378,9 @@ class ModelTrainer:
                 progress_cb(n)
         if epoch_n == 0:
             return float('nan')
-        if train:
-            return dp.epoch_loss(self._loss, epoch_n)
-        return self._loss.item() / epoch_n
+        # data parallel: the loss over the GLOBAL batch, the same number on every rank (so every
+        # rank takes the same model-selection decisions in fit())
+        return dp.epoch_loss(self._loss, epoch_n)
 
     def get_optimizer(self, learning_rate):
         return FusedAdamW(self.encoder, learning_rate), None
