@@ -24,6 +24,39 @@ def test_shard_videos_partitions_and_balances():
     assert vapply.shard_videos([], 4, 1) == []
 
 
+def test_plan_chunks_tiles_the_frames_in_order():
+    for counts, bs in (([5, 0, 12, 3], 8), ([2695] * 3, 500), ([1], 500), ([], 4), ([4, 4], 4)):
+        chunks = vapply.plan_chunks(counts, bs)
+        assert all(sum(hi - lo for _, lo, hi, _ in c) == bs for c in chunks[:-1])
+        seen = [[] for _ in counts]
+        for c in chunks:
+            fill = 0
+            for v, lo, hi, off in c:
+                assert off == fill and 0 <= lo < hi <= counts[v]
+                fill += hi - lo
+                seen[v].extend(range(lo, hi))
+            assert 0 < fill <= bs
+        assert seen == [list(range(n)) for n in counts]
+
+
+def test_pickle_writer_processes(tmp_path):
+    w = vapply._PickleWriters(2)
+    embs = np.random.RandomState(0).randn(6, 2, 4).astype(np.float32)
+    for i in range(5):
+        w.submit(os.path.join(str(tmp_path), 'v{}.emb.pkl'.format(i)), [3, 1, 2], embs[i:i + 3] if i < 4 else embs[:3], True)
+    w.close()
+    with open(os.path.join(str(tmp_path), 'v1.emb.pkl'), 'rb') as fp:
+        back = pickle.load(fp)
+    assert [t[0] for t in back] == [1, 2, 3] and np.array_equal(back[0][1], embs[2])
+    bad = vapply._PickleWriters(1)
+    bad.submit(os.path.join(str(tmp_path), 'missing_dir', 'x.pkl'), [0], embs[:1], True)
+    try:
+        bad.close()
+        raise AssertionError('a failed write must surface')
+    except FileNotFoundError:
+        pass
+
+
 def test_pickle_format_matches_reference(tmp_path):
     embs = np.arange(3 * 2 * 4, dtype=np.float32).reshape(3, 2, 4)
     out = vapply.format_video_embs([7, 2, 5], embs, flip=True)

@@ -44,6 +44,33 @@ try:
 except AssertionError:
     pass
 
+# the per-bucket checker the GPU test and bench.py use: passes on the real sum, and a bucket
+# whose exchange was skipped (it still holds the local gradient) is caught - on its own norm,
+# even when it is a tiny part of the arena
+chk = dp.check_bucket_sums(b, expect, buckets)
+assert chk['ok'] and chk['max_rel'] <= 1e-6 and len(chk['per_bucket']) == 3
+skipped = b.clone()
+skipped[0:256] = local[0:256]                   # bucket (0, 256) never all-reduced
+chk = dp.check_bucket_sums(skipped, expect, buckets)
+assert not chk['ok'] and chk['max_rel'] > 0.1
+assert [r > 0.1 for _, _, r in chk['per_bucket']] == [True, False, False]
+tiny = [(0, 4), (4, 996)]
+skipped = b.clone()
+skipped[0:4] = local[0:4]
+assert not dp.check_bucket_sums(skipped, expect, tiny)['ok']
+try:
+    dp.check_bucket_sums(b, expect, [(0, 500), (600, 400)])
+    raise SystemExit('buckets with a gap must be rejected')
+except AssertionError:
+    pass
+
+# replicas start from rank 0's state whatever their own initialisation was
+state = [torch.full((5,), float(rank + 1)), None, torch.arange(3) + 10 * rank]
+dp.broadcast_state(state)
+assert torch.equal(state[0], torch.ones(5)) and torch.equal(state[2], torch.arange(3))
+assert dp.rank() == rank
+dp.barrier()
+
 # identical parameters + summed gradients -> identical parameters after the step
 p = torch.ones(n)
 p -= 0.1 * a

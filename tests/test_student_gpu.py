@@ -342,6 +342,26 @@ def test_apply_corpus_extraction_pickles(tmp_path):
     for f, e, _ in embs:
         for k in range(2):
             assert _cos(torch.from_numpy(e[k]), torch.from_numpy(by_frame[f][k])) >= 0.999
+    # the second video's frames arrived in the tail of a chunk shared with the first one
+    with open(os.path.join(str(tmp_path), 'vid2.emb.pkl'), 'rb') as fp:
+        embs2 = pickle.load(fp)
+    x2 = assemble_ref.apply_batch(videos[2][2].numpy(), videos[2][3].numpy(), *synth.FS_MEAN_STD)
+    ref2 = student_ref.embed(sd, x2.view(-1, 5, 128, 128)).reshape(3, 2, 32)
+    by_frame2 = {f: ref2[i] for i, f in enumerate(videos[2][1])}
+    assert [e[0] for e in embs2] == sorted(videos[2][1])
+    for f, e, _ in embs2:
+        assert _cos(torch.from_numpy(e[0]), torch.from_numpy(by_frame2[f][0])) >= 0.999
+    # in-thread writer, one chunk per launch group, no flip: same embeddings, [D] entries
+    out2 = tmp_path / 'inline'
+    timing = {}
+    names2 = vapply.extract_corpus(m, videos, str(out2), synth.FS_MEAN_STD, flip=False,
+                                   batch_size=500, writers=0, timing=timing)
+    assert names2 == names and timing['frames'] == 8 and timing['chunks'] == 1
+    with open(os.path.join(str(out2), 'vid0.emb.pkl'), 'rb') as fp:
+        single = pickle.load(fp)
+    assert all(e[1].shape == (32,) for e in single)
+    for (f, e, _), (f1, e1, _) in zip(single, embs):
+        assert f == f1 and _cos(torch.from_numpy(e), torch.from_numpy(e1[0])) >= 0.99999
     # two-rank sharding writes disjoint files
     a = vapply.shard_videos([5, 0, 3], 2, 0)
     b = vapply.shard_videos([5, 0, 3], 2, 1)

@@ -6,7 +6,9 @@ and horizontally flipped variant, flow-x negated on the flip) -> eval-mode encod
 pickled to `<out_dir>/<video>.emb.pkl` (util/io.py:35-37, README.md:185-194).
 
 Multi-GPU: videos are partitioned across ranks (greedy longest-first), every rank
-writes its own files, there is no collective.
+writes its own files, there is no collective. `extract_corpus` overlaps the host->device
+copy of the next chunk, the forward pass and the per-video pickling (reader thread, CUDA
+events, writer processes).
 """
 import json
 import os
@@ -65,23 +67,214 @@ def embed_frames(model, rgb_u8, flow_u8, rgb_mean_std, flip=True, batch_size=BAT
     return out.cpu().numpy()
 
 
+def plan_chunks(frame_counts, batch_size):
+    """Cut the concatenation of the videos (in the given order) into chunks of exactly
+    `batch_size` frames (the last one may be shorter). A chunk may span video boundaries, so
+    every launch but the last runs the same full batch.
+    -> [[(video_pos, lo, hi, offset_in_chunk), ...], ...] with lo/hi frame ranges inside the video."""
+    chunks, cur, fill = [], [], 0
+    for v, n in enumerate(frame_counts):
+        lo = 0
+        while lo < n:
+            take = min(n - lo, batch_size - fill)
+            cur.append((v, lo, lo + take, fill))
+            fill += take
+            lo += take
+            if fill == batch_size:
+                chunks.append(cur)
+                cur, fill = [], 0
+    if cur:
+        chunks.append(cur)
+    return chunks
+
+
+def _write_video_pickle(path, frame_nums, embs, flip):
+    """Body of a writer process: build the reference's tuples and pickle them."""
+    store_pickle(path, format_video_embs(frame_nums, embs, flip))
+    return path
+
+
+class _PickleWriters:
+    """Per-video pickling off the critical path. Formatting + pickling a 2,700-frame video is
+    ~15 ms of pure Python (5.6 us per (frame, ndarray, {}) tuple), i.e. one core writes about as
+    many frames per second as one B200 embeds; it runs in worker PROCESSES so that it neither
+    caps the rate nor competes with the launching thread for the interpreter lock.
+    workers = 0: write in the calling thread (tests, tiny corpora)."""
+
+    def __init__(self, workers):
+        self.pool, self.futures = None, []
+        if workers > 0:
+            import multiprocessing
+            from concurrent.futures import ProcessPoolExecutor
+            # fork: the children never touch CUDA (numpy + pickle only) and start in ~1 ms
+            self.pool = ProcessPoolExecutor(workers, mp_context=multiprocessing.get_context('fork'))
+            self.pool.submit(int).result()  # start the workers now, before any thread of ours runs
+
+    def submit(self, path, frame_nums, embs, flip):
+        if self.pool is None:
+            _write_video_pickle(path, frame_nums, embs, flip)
+        else:
+            self.futures.append(self.pool.submit(_write_video_pickle, path, list(frame_nums),
+                                                 np.ascontiguousarray(embs), flip))
+
+    def close(self):
+        try:
+            for f in self.futures:
+                f.result()                  # re-raises a worker's exception
+        finally:
+            if self.pool is not None:
+                self.pool.shutdown()
+
+
 def extract_corpus(model, videos, out_dir, rgb_mean_std, flip=True, rank=0, world_size=1,
-                   batch_size=BATCH_SIZE):
-    """videos: list of (name, frame_nums, rgb_u8 [n,H,W,3], flow_u8 or None) with host or
-    device uint8 tensors. Writes this rank's `<name>.emb.pkl`; returns the names written."""
-    counts = [len(v[1]) for v in videos]
-    written = []
+                   batch_size=BATCH_SIZE, writers=2, timing=None):
+    """videos: list of (name, frame_nums, rgb_u8 [n,H,W,3], flow_u8 or None) with host (ideally
+    pinned or memory-mapped) or device uint8 tensors. Writes this rank's `<name>.emb.pkl`;
+    returns the names written (apply_vpd_model.py:152-178).
+
+    A three-stage pipeline over fixed-size chunks of the rank's frames (`plan_chunks`):
+      reader thread   host frames -> pinned staging slot -> H2D copy on a copy stream into one
+                      of the device input slots (98 KB per frame: 15 GB/s at 158 k frames/s);
+      this thread     K1 assembly [orig, flipped] -> eval-mode encoder (one CUDA-graph replay
+                      per chunk) -> D2H of the chunk's [n, k, D] embeddings into a pinned array;
+      writer procs    per finished video: tuples + pickle.
+    The stages meet only through CUDA events and two queues, so the copy of chunk i+1 and the
+    pickling of earlier videos overlap the forward pass of chunk i. `timing` (dict) receives
+    frames / seconds / chunks of this rank."""
+    import queue
+    import threading
+    import time
+    from ._lib import lib
+    from .assemble import assemble_stem
+    t_start = time.perf_counter()
+    dev = model._dev
     os.makedirs(out_dir, exist_ok=True)
-    for i in shard_videos(counts, world_size, rank):
-        name, frame_nums, rgb, flow = videos[i]
-        if len(frame_nums) == 0:
-            continue
-        rgb = rgb.to(model._dev, non_blocking=True)
-        flow = None if flow is None else flow.to(model._dev, non_blocking=True)
-        embs = embed_frames(model, rgb, flow, rgb_mean_std, flip, batch_size)
-        store_pickle(os.path.join(out_dir, '{}.emb.pkl'.format(name)),
-                     format_video_embs(frame_nums, embs, flip))
-        written.append(name)
+    mine = [i for i in shard_videos([len(v[1]) for v in videos], world_size, rank)
+            if len(videos[i][1]) > 0]
+    if not mine:
+        return []
+    counts = [len(videos[i][1]) for i in mine]
+    chunks = plan_chunks(counts, batch_size)
+    total = sum(counts)
+    k = 2 if flip else 1
+    first = videos[mine[0]]
+    H, W = first[2].shape[1:3]
+    has_flow = first[3] is not None
+    fch = first[3].shape[-1] if has_flow else 0
+    D = model.emb_dim
+    model.eval()
+    n_in, n_pin = 2, 3
+    with torch.cuda.device(dev):
+        pin_rgb = [torch.empty((batch_size, H, W, 3), dtype=torch.uint8).pin_memory()
+                   for _ in range(n_pin)]
+        pin_flow = [torch.empty((batch_size, H, W, fch), dtype=torch.uint8).pin_memory()
+                    for _ in range(n_pin)] if has_flow else None
+        dev_rgb = [torch.empty((batch_size, H, W, 3), device=dev, dtype=torch.uint8)
+                   for _ in range(n_in)]
+        dev_flow = [torch.empty((batch_size, H, W, fch), device=dev, dtype=torch.uint8)
+                    for _ in range(n_in)] if has_flow else None
+        dev_out = [torch.empty((batch_size * k, D), device=dev, dtype=torch.float32)
+                   for _ in range(2)]
+        host_out = torch.empty((total, k, D), dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream(device=dev)
+        main_stream = torch.cuda.current_stream(dev)
+    ready = queue.Queue()                    # (chunk index, H2D-done event) or an exception
+    consumed = [None] * len(chunks)          # event: the compute that read device slot is done
+    consumed_cv = threading.Condition()
+
+    def reader():
+        try:
+            torch.cuda.set_device(dev)
+            pin_free = [None] * n_pin        # event of the H2D that last read the staging slot
+            for ci, parts in enumerate(chunks):
+                ps, ds = ci % n_pin, ci % n_in
+                if pin_free[ps] is not None:
+                    pin_free[ps].synchronize()
+                for v, lo, hi, off in parts:
+                    _, _, rgb, flow = videos[mine[v]]
+                    pin_rgb[ps][off:off + hi - lo].copy_(rgb[lo:hi])
+                    if has_flow:
+                        pin_flow[ps][off:off + hi - lo].copy_(flow[lo:hi])
+                if ci >= n_in:               # the device slot's previous chunk must be consumed
+                    with consumed_cv:
+                        consumed_cv.wait_for(lambda: consumed[ci - n_in] is not None)
+                    copy_stream.wait_event(consumed[ci - n_in])
+                n = sum(hi - lo for _, lo, hi, _ in parts)
+                with torch.cuda.stream(copy_stream):
+                    dev_rgb[ds][:n].copy_(pin_rgb[ps][:n], non_blocking=True)
+                    if has_flow:
+                        dev_flow[ds][:n].copy_(pin_flow[ps][:n], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                pin_free[ps] = ev
+                ready.put((ci, ev))
+        except BaseException as exc:         # surface in the consuming thread
+            ready.put(exc)
+
+    th = threading.Thread(target=reader, name='vpd-corpus-reader', daemon=True)
+    th.start()
+    writer = _PickleWriters(writers)
+    done_ev = [None] * len(chunks)
+    last_chunk_of = {}
+    for ci, parts in enumerate(chunks):
+        for v, _, _, _ in parts:
+            last_chunk_of[v] = ci
+    first_row = np.concatenate([[0], np.cumsum(counts)])
+    next_video = 0
+    written = []
+
+    def flush(upto_chunk, block):
+        """hand every video whose last chunk is <= upto_chunk and finished to the writers"""
+        nonlocal next_video
+        while next_video < len(mine) and last_chunk_of[next_video] <= upto_chunk:
+            ev = done_ev[last_chunk_of[next_video]]
+            if block:
+                ev.synchronize()
+            elif not ev.query():
+                return
+            name, frame_nums = videos[mine[next_video]][0], videos[mine[next_video]][1]
+            lo, hi = first_row[next_video], first_row[next_video + 1]
+            writer.submit(os.path.join(out_dir, '{}.emb.pkl'.format(name)), frame_nums,
+                          host_out[lo:hi].numpy(), flip)
+            written.append(name)
+            next_video += 1
+
+    try:
+        with torch.cuda.device(dev):
+            row = 0
+            for _ in range(len(chunks)):
+                item = ready.get()
+                if isinstance(item, BaseException):
+                    raise item
+                ci, ev = item
+                parts = chunks[ci]
+                n = sum(hi - lo for _, lo, hi, _ in parts)
+                ds, os_ = ci % n_in, ci % 2
+                main_stream.wait_event(ev)
+                net = model._native(H, W, batch_size * k)
+                stem = lib().call('vpd_net_stem_input', net.handle)
+                assemble_stem(stem, dev_rgb[ds][:n], dev_flow[ds][:n] if has_flow else None,
+                              rgb_mean_std, k=k)
+                lib().call('vpd_net_forward', net.handle, None, stem, n * k, dev_out[os_],
+                           main_stream.cuda_stream)
+                cev = torch.cuda.Event()
+                cev.record(main_stream)
+                with consumed_cv:
+                    consumed[ci] = cev
+                    consumed_cv.notify_all()
+                host_out[row:row + n].copy_(dev_out[os_][:n * k].view(n, k, D), non_blocking=True)
+                dev_ev = torch.cuda.Event()
+                dev_ev.record(main_stream)
+                done_ev[ci] = dev_ev
+                row += n
+                flush(ci - 1, block=False)
+            flush(len(chunks) - 1, block=True)
+    finally:
+        th.join(timeout=60)
+        writer.close()
+    if timing is not None:
+        timing.update(frames=total, chunks=len(chunks), videos=len(written),
+                      seconds=time.perf_counter() - t_start)
     return written
 
 

@@ -44,16 +44,21 @@ class Shard:
             torch.from_numpy(np.array(self.flow)).to(device)
         return rgb, flow
 
-    def videos(self):
-        """-> the `videos` list vpd_b200.apply.extract_corpus takes."""
+    def videos(self, materialize=False):
+        """-> the `videos` list vpd_b200.apply.extract_corpus takes. The tensors are views of
+        the memory-mapped shard (nothing is read until the extraction pipeline copies a chunk
+        into its pinned staging buffer), so a corpus larger than RAM streams through;
+        materialize=True reads every video into memory now."""
+        import warnings
         import torch
         out = []
-        for v in self.index['videos']:
-            lo, hi = v['first_row'], v['first_row'] + len(v['frames'])
-            out.append((v['name'], list(v['frames']),
-                        torch.from_numpy(np.array(self.rgb[lo:hi])),
-                        None if self.flow is None else
-                        torch.from_numpy(np.array(self.flow[lo:hi]))))
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')         # read-only memmap -> tensor: never written
+            for v in self.index['videos']:
+                lo, hi = v['first_row'], v['first_row'] + len(v['frames'])
+                take = (lambda a: np.array(a[lo:hi])) if materialize else (lambda a: a[lo:hi])
+                out.append((v['name'], list(v['frames']), torch.from_numpy(take(self.rgb)),
+                            None if self.flow is None else torch.from_numpy(take(self.flow))))
         return out
 
 

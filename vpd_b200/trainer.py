@@ -235,7 +235,8 @@ class ModelTrainer:
         if getattr(self, '_overlapped', False):
             # buckets were launched from the callback; make the compute stream wait for them
             for work in self._pending:
-                work.wait()
+                if work is not None:
+                    work.wait()
             self._pending = []
             torch.cuda.current_stream(self.encoder._dev).wait_stream(self._comm_stream)
         else:
