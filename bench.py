@@ -16,11 +16,12 @@ backward -> [NCCL all-reduce SUM of the gradient arena when N > 1] -> fused Adam
             (H2D copies and the loss read-back inside the timed region); `e2e.u8_batches` is
             the same with raw uint8 crop batches (4x fewer bytes, K1 on the device);
   roofline  the implicit-GEMM conv family (forward + data-gradient launches): algorithmic FLOPs
-            / kernel time. Kernel times are hardware start/end timestamps of every launch of a
-            few extra steps run exactly like the timed ones (CUDA-graph replay, side stream),
-            collected through CUPTI activity records (torch.profiler); CUDA events around every
-            launch of an eager single-stream pass are kept beside them (`achieved_events` -
-            they include launch gaps). `frac` is against the measured bf16 peak that matches
+            / kernel time. Kernel times are hardware start/end timestamps of every launch (CUPTI
+            activity records through torch.profiler) of a few extra steps run SERIALISED after
+            the timed region (eager, one stream - as replayed in the timed region every kernel
+            starts early under programmatic dependent launch and waits for its predecessor, so
+            as-run durations overlap); the CUDA-event intervals around the same launches are
+            kept beside them (`achieved_events` - they include the gaps between launches). `frac` is against the measured bf16 peak that matches
             the clocks seen during the timed region (burst at full clocks, else sustained);
             both fractions are printed. `kernels` has the other families with their own
             rooflines (K1 assembly and AdamW against measured HBM bandwidth);
@@ -333,14 +334,15 @@ def cupti_kernel_times(step_fn, nsteps):
     """Run `nsteps` steps under CUPTI activity tracing (torch.profiler, CUDA activities only)
     -> {family: {'us': total, 'n': launches, 'by_kernel': {name: [n, us]}}} per nsteps, or None
     when the profiler is not usable. Durations are the hardware start/end timestamps of each
-    launch; kernels that ran concurrently (side stream) each keep their own full duration."""
+    launch. The caller runs the steps SERIALISED (one stream, an event record between
+    launches): as replayed in the timed region every kernel starts early under programmatic
+    dependent launch and spins in griddepcontrol.wait until its predecessor drains, and the
+    weight gradients share the SMs with the main chain, so as-run durations overlap."""
     try:
         from torch.profiler import profile, ProfilerActivity
-        step_fn(0)
-        torch.cuda.synchronize()
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
             for i in range(nsteps):
-                step_fn(1 + i)
+                step_fn(i)
             torch.cuda.synchronize()
         fam = {}
         for e in prof.events():
@@ -643,17 +645,14 @@ def run_native(args, rank, world, local_rank):
                    torch.cuda.current_stream().cuda_stream)
             opt.step()
 
-        if dist is not None:
-            for i in range(3):       # the hook-free step graph is a different one: capture it first
-                local_step(i)
-        cupti = cupti_kernel_times(local_step, nprof)
+        # one serialised pass (eager, single stream, an event pair around every launch) read
+        # two ways: CUPTI kernel durations (kernel only) and the event intervals (kernel + gap)
         L.call('vpd_net_profile_enable', net.handle, 1)
-        for i in range(nprof):
-            j = i % NIDX
-            assemble_stem(stem, rgb, flow, synth.FS_MEAN_STD, flip=flip_all[j], teacher=teach,
-                          index=idx_all[j], tgt=tgt)
-            L.call('vpd_net_train_step', net.handle, None, stem, tgt, B, trainer._loss,
-                   torch.cuda.current_stream().cuda_stream)
+        local_step(0)
+        torch.cuda.synchronize()
+        L.call('vpd_net_profile_read', net.handle, (ctypes.c_float * 64)(), (ctypes.c_int * 64)())
+        L.call('vpd_net_profile_enable', net.handle, 1)
+        cupti = cupti_kernel_times(local_step, nprof)
         torch.cuda.synchronize()
         msbuf = (ctypes.c_float * 64)()
         cntbuf = (ctypes.c_int * 64)()
@@ -664,7 +663,49 @@ def run_native(args, rank, world, local_rank):
         f_fwd, f_dgrad, f_wgrad = conv_flops(B)
         flops = {'conv_fwd': f_fwd, 'conv_dgrad': f_dgrad, 'conv_wgrad': f_wgrad}
         n_params = enc._params.numel()
-        fam_bytes = {'assemble': K1_BYTES_PER_FRAME * B, 'adamw': ADAMW_BYTES_PER_PARAM * n_params}
+        fam_bytes = {}
+        # the HBM-bound kernels north_star names, each timed alone (CUDA events around 20
+        # back-to-back launches; inputs larger than L2 / the 600 MB optimizer state)
+        def loop_ms(fn, reps=20):
+            for _ in range(3):
+                fn(0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for r in range(reps):
+                fn(r)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        def hbm_entry(ms_, nbytes, what):
+            gbs = nbytes / (ms_ * 1e-3) / 1e9
+            return {'ms_per_launch': round(ms_, 4), 'what': what,
+                    'roofline': {'bound': 'hbm', 'achieved': round(gbs, 1), 'peak': pk['hbm_gbs'],
+                                 'unit': 'GB/s', 'frac': round(gbs / pk['hbm_gbs'], 4),
+                                 'algorithmic_bytes_per_launch': int(nbytes)},
+                    'frac': round(gbs / pk['hbm_gbs'], 4)}
+
+        img_f32 = torch.empty((B, 1, 5, IMG, IMG), device=dev, dtype=torch.float32)
+        alone = {
+            'assemble_stem': hbm_entry(
+                loop_ms(lambda r: assemble_stem(stem, rgb, flow, synth.FS_MEAN_STD,
+                                                flip=flip_all[r % NIDX], teacher=teach,
+                                                index=idx_all[r % NIDX], tgt=tgt)),
+                K1_BYTES_PER_FRAME * B,
+                'K1, training batch: 256 random frames of the uint8 pools -> bf16 network layout '
+                '(81,920 B read + 291,584 B written per frame)'),
+            'assemble_nchw': hbm_entry(
+                loop_ms(lambda r: assemble_batch(rgb, flow, synth.FS_MEAN_STD,
+                                                 flip=flip_all[r % NIDX], teacher=teach,
+                                                 index=idx_all[r % NIDX])),
+                409600 * B,
+                'K1, reference layout: the same frames -> fp32 [B,5,128,128] (409,600 B per frame; '
+                'includes the output allocation)'),
+            'adamw': hbm_entry(loop_ms(lambda r: opt.step()), ADAMW_BYTES_PER_PARAM * n_params,
+                               'K5 over the flat arena of {} parameters (28 B each)'.format(n_params)),
+        }
+        del img_f32
         breakdown = {}
         if cupti is not None:
             for name, d in sorted(cupti.items()):
@@ -683,9 +724,11 @@ def run_native(args, rank, world, local_rank):
                                          'algorithmic_bytes_per_launch': fam_bytes[name]}
                     entry['frac'] = entry['roofline']['frac']
                 breakdown[name] = entry
-            breakdown['_how'] = ('CUPTI activity records (hardware start/end timestamps per launch) '
-                                 'of {} steps replayed like the timed ones; concurrent side-stream '
-                                 'kernels each keep their full duration'.format(nprof))
+            breakdown['_how'] = ('CUPTI activity records (hardware start/end timestamps per launch) of '
+                                 '{} steps run serialised after the timed region (eager, one stream: '
+                                 'no programmatic early start, no side-stream overlap), caches in '
+                                 'their in-step state'.format(nprof))
+        breakdown['_alone'] = alone
         events = {}
         for k, name in enumerate(KINDS):
             if ev_n[k]:

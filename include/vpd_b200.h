@@ -309,6 +309,14 @@ VPD_API int vpd_net_tensor_info(vpd_net* net, int i, char* name, int name_cap, i
                         int64_t* offset, int* layout, int* ndim, int64_t* shape4);
 VPD_API int vpd_net_bind(vpd_net* net, float* params, float* grads, float* buffers, int64_t* nbt,
                  void* workspace, int64_t workspace_bytes);
+/* vpd_adamw over the arenas bound to `net` (same arithmetic, bit-identical parameters and
+ * moments) that also writes the bf16 tensor-core mirrors of the updated conv weights, so the
+ * next vpd_net_train_step / vpd_net_forward starts without a weight-packing pass
+ * (train_vpd_model.py:100-105, models/util.py:50-58). exp_avg / exp_avg_sq: fp32 arenas of
+ * vpd_net_param_count elements. */
+VPD_API int vpd_net_adamw(vpd_net* net, float* exp_avg, float* exp_avg_sq, double lr, double beta1,
+                  double beta2, double eps, double weight_decay, int step, float grad_scale,
+                  void* stream);
 /* call after writing the parameter arena from outside (load_state_dict, optimizer) */
 VPD_API int vpd_net_params_changed(vpd_net* net);
 VPD_API void* vpd_net_stem_input(vpd_net* net);

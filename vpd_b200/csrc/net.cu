@@ -226,6 +226,10 @@ struct Net {
   int tr_blocks;
   bool tr_uploaded = false;
   std::vector<int> tr_table_host;
+  int* mt_table_dev;               // 32 x 64 tiles of every (conv, tap) matrix: AdamW + mirrors
+  int mt_blocks;
+  bool mt_uploaded = false;
+  std::vector<int> mt_table_host;
   std::map<int, Plan*> plans;
 };
 
@@ -410,6 +414,27 @@ Net* net_create(const char* arch, int emb_dim, int in_channels, int H, int W, in
     }
   }
   n->tr_blocks = (int)(n->tr_table_host.size() / 5);
+  // the same matrices cut into 32 (cout) x 64 (cin) tiles for the mirror-writing optimizer
+  auto add_tiles = [&](long long off, int rows, int cols) {
+    for (int r = 0; r < rows / 32; ++r)
+      for (int q = 0; q < cols / 64; ++q) {
+        n->mt_table_host.push_back((int)off);
+        n->mt_table_host.push_back(rows);
+        n->mt_table_host.push_back(cols);
+        n->mt_table_host.push_back(r);
+        n->mt_table_host.push_back(q);
+      }
+  };
+  for (int t = 0; t < 7; ++t) add_tiles(n->stem.w_off + (long long)t * 64 * 64, 64, 64);
+  for (auto& bd : n->blocks) {
+    const ConvDesc* cs[3] = {&bd.c1, &bd.c2, bd.has_ds ? &bd.ds : nullptr};
+    for (const ConvDesc* c : cs) {
+      if (!c) continue;
+      for (int t = 0; t < c->k * c->k; ++t)
+        add_tiles(c->w_off + (long long)t * c->Cout * c->Cin, c->Cout, c->Cin);
+    }
+  }
+  n->mt_blocks = (int)(n->mt_table_host.size() / 5);
   return n;
 }
 
@@ -472,6 +497,7 @@ static long long carve(Net* n, uint8_t* base) {
   n->ev_scale = c.take<float>(n->total_ch);
   n->ev_shift = c.take<float>(n->total_ch);
   n->tr_table_dev = c.take<int>((long long)n->tr_table_host.size());
+  n->mt_table_dev = c.take<int>((long long)n->mt_table_host.size());
   n->x_stem = c.take<bf16>(B * (n->H + 6) * (n->W + 8) * 8);
   const long long stem_out = B * (n->H / 2) * (n->W / 2) * 64;
   n->y_stem = c.take<bf16>(stem_out);
@@ -524,6 +550,7 @@ int net_bind(Net* n, float* params, float* grads, float* buffers, long long* nbt
   drop_graphs(n);   // they hold the old pointers
   n->params_dirty = true;
   n->tr_uploaded = false;
+  n->mt_uploaded = false;
   return 0;
 }
 
@@ -940,7 +967,6 @@ static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, 
   n->prof.begin(kPack, 5, s);
   VPD_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, (size_t)((uint8_t*)n->loss_dev - (uint8_t*)n->stats), s));
   VPD_CHECK_CUDA(cudaMemsetAsync(n->grads + n->secA, 0, (size_t)n->secA_len * sizeof(float), s));
-  if (pack_weights(n, s)) return -1;
   n->prof.end(s);
 
   // ------------------------------------------------------------------ forward
@@ -1139,6 +1165,9 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
                    double* loss_sum, cudaStream_t s) {
   VPD_REQUIRE(n->grads != nullptr, "net: gradient arena not bound");
   VPD_REQUIRE(target != nullptr && loss_sum != nullptr, "net_train_step: null target/loss");
+  // bf16 operand mirrors: refreshed here (never inside a captured graph) only when the fp32
+  // masters changed behind our back - net_adamw writes them itself as part of the update
+  if (n->params_dirty && pack_weights(n, s)) return -1;
   static const bool graphs_on = getenv("VPD_GRAPH") == nullptr || getenv("VPD_GRAPH")[0] != '0';
   if (!graphs_on || n->prof.on)
     return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
@@ -1222,6 +1251,24 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
       n->bucket_fn(n->bucket_user, g->buckets[k].first, g->buckets[k].second);
   }
   n->params_dirty = true;
+  return 0;
+}
+
+// AdamW over the bound arenas (K5) that leaves the bf16 mirrors of the updated conv weights
+// behind, so the next step starts without a weight-packing pass.
+int net_adamw(Net* n, float* exp_avg, float* exp_avg_sq, double lr, double b1, double b2,
+              double eps, double wd, int step, float grad_scale, cudaStream_t s) {
+  VPD_REQUIRE(n->params != nullptr && n->grads != nullptr, "net_adamw: arenas not bound");
+  if (!n->mt_uploaded) {
+    VPD_CHECK_CUDA(cudaMemcpyAsync(n->mt_table_dev, n->mt_table_host.data(),
+                                   n->mt_table_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    n->mt_uploaded = true;
+  }
+  if (adamw_step_mirrored(n->params, n->grads, exp_avg, exp_avg_sq, n->n_params, n->secA,
+                          n->secA_len, n->w_tap, n->wT_tap, n->mt_table_dev, n->mt_blocks, lr, b1,
+                          b2, eps, wd, step, grad_scale, s))
+    return -1;
+  n->params_dirty = false;
   return 0;
 }
 

@@ -37,6 +37,14 @@ int adamw_step(float* p, const float* g, float* m, float* v, long long n, double
                double b2, double eps, double wd, int step, float grad_scale,
                cudaStream_t stream);
 
+// AdamW whose conv-weight section also refreshes the bf16 operand mirrors (adamw.cu);
+// `table` = one (matrix offset, rows, cols, 32-row tile, 64-column tile) entry per CTA
+int adamw_step_mirrored(float* p, const float* g, float* m, float* v, long long n,
+                        long long conv_off, long long conv_len, __nv_bfloat16* w_tap,
+                        __nv_bfloat16* wT, const int* table, int tiles, double lr, double b1,
+                        double b2, double eps, double wd, int step, float grad_scale,
+                        cudaStream_t stream);
+
 int sgd_step(float* p, const float* g, float* buf, long long n, double lr, double momentum,
              double dampening, double wd, int nesterov, int first_step, float grad_scale,
              cudaStream_t stream);

@@ -42,11 +42,19 @@ class FusedAdamW:
         m, v = self._state()
         self.step_count += 1
         with torch.cuda.device(enc._dev):
-            lib().call('vpd_adamw', enc._params, enc._grads, m, v, enc._params.numel(), self.lr,
-                       self.betas[0], self.betas[1], self.eps, self.weight_decay,
-                       self.step_count, 1.0, stream_ptr(enc._dev))
-            if enc._net is not None:
-                lib().call('vpd_net_params_changed', enc._net.handle)
+            net = enc._net
+            if net is not None and getattr(net, 'has_grads', False):
+                # the bound net's variant also leaves the bf16 operand mirrors of the updated
+                # conv weights behind (no weight-packing pass at the start of the next step)
+                lib().call('vpd_net_adamw', net.handle, m, v, self.lr, self.betas[0],
+                           self.betas[1], self.eps, self.weight_decay, self.step_count, 1.0,
+                           stream_ptr(enc._dev))
+            else:
+                lib().call('vpd_adamw', enc._params, enc._grads, m, v, enc._params.numel(),
+                           self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay,
+                           self.step_count, 1.0, stream_ptr(enc._dev))
+                if net is not None:
+                    lib().call('vpd_net_params_changed', net.handle)
 
     def zero_grad(self, set_to_none=False):
         pass    # every train step overwrites the whole gradient arena
