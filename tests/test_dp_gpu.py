@@ -33,7 +33,7 @@ def test_two_rank_nccl_gradient_sum(overlap):
     kv = dict(item.split('=') for item in m.group(1).split())
     assert kv['ok'] == 'True' and float(kv['max_rel']) <= 1e-4, kv
     assert kv['overlapped'] == ('True' if overlap == '1' else 'False')
-    assert int(kv['buckets']) == (3 if overlap == '1' else 1)
+    assert int(kv['buckets']) == (4 if overlap == '1' else 1)
     assert kv['dropped_ok'] == 'False' and float(kv['dropped_max_rel']) > 1e-2, kv
     assert kv['start_identical'] == 'True' and kv['params_identical'] == 'True'
     assert kv['eval_identical'] == 'True'

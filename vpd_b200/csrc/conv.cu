@@ -575,8 +575,68 @@ static void copy_geometry(WgradParams* w, const ConvParams& c) {
   for (int i = 0; i < kMaxTaps; ++i) w->taps[i] = c.taps[i];
 }
 
+// Halo-reuse plan for the weight gradient of a stride-1 3x3 'same' convolution (see
+// conv_wgrad_halo_kernel): images of 8k x 16m pixels use 8 x 16 tiles, 8 x 8 images two per tile.
+static bool try_wgrad_halo(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
+                           const __nv_bfloat16* dy, float* dw) {
+  static const int enable = env_int("VPD_WGRAD_HALO", 1);
+  if (!enable || g.k != 3 || g.stride != 1 || g.pad != 1) return false;
+  if (g.Cin % 64 != 0 || g.Cout % 64 != 0 || g.W % 8 != 0) return false;
+  WgradHaloParams& p = L->hp;
+  if (g.H % 16 == 0) {
+    p.th = 16;
+    p.tn = 1;
+  } else if (g.H == 8) {
+    p.th = 8;
+    p.tn = 2;
+  } else {
+    return false;
+  }
+  p.tiles_w = g.W / 8;
+  p.tiles_h = g.H / p.th;
+  p.tiles_b = (g.N + p.tn - 1) / p.tn;
+  p.kchunks = g.Cin / 64;
+  p.n_tiles = g.Cout / 64;
+  p.cin = g.Cin;
+  p.cout = g.Cout;
+  p.dw = dw;
+  const int img_rows = (p.th + 2) * 10;                 // patch rows per image
+  p.patch_bytes = img_rows * p.tn * 128;
+  if (p.patch_bytes > WgradHaloCfg::kPatchSlot) return false;
+  for (int k = 0; k < 8; ++k) {
+    // pixels 16k .. 16k+15 of the tile = image k / (th/2), rows 2 (k % (th/2)) and the next
+    const int per_img = p.th / 2;
+    const int row = (k / per_img) * img_rows + 2 * (k % per_img) * 10;
+    p.kstep16[k] = row * 128 / 16;
+  }
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int combos = p.kchunks * p.n_tiles;
+  int splits = device_sm_count() / combos;
+  if (splits < 1) splits = 1;
+  if (splits > pix_tiles) splits = pix_tiles;
+  while (splits > 1 && (splits - 1) * ((pix_tiles + splits - 1) / splits) >= pix_tiles) --splits;
+  p.splits = splits;
+  const int items = combos * splits;
+  L->grid = items < device_sm_count() ? items : device_sm_count();
+  uint64_t dims[5] = {(uint64_t)g.Cin, (uint64_t)g.W, 1, (uint64_t)g.H, (uint64_t)g.N};
+  uint64_t str[5] = {2, (uint64_t)g.Cin * 2, (uint64_t)g.W * g.Cin * 2, (uint64_t)g.W * g.Cin * 2,
+                     (uint64_t)g.H * g.W * g.Cin * 2};
+  uint32_t box[5] = {64, 10, 1, (uint32_t)(p.th + 2), (uint32_t)p.tn};
+  if (encode_tmap_bf16(&L->x, x, 5, dims, str, box, true)) return false;
+  uint64_t ddims[5] = {(uint64_t)g.Cout, (uint64_t)g.W, 1, (uint64_t)g.H, (uint64_t)g.N};
+  uint64_t dstr[5] = {2, (uint64_t)g.Cout * 2, (uint64_t)g.W * g.Cout * 2,
+                      (uint64_t)g.W * g.Cout * 2, (uint64_t)g.H * g.W * g.Cout * 2};
+  uint32_t dbox[5] = {64, 8, 1, (uint32_t)p.th, (uint32_t)p.tn};
+  if (encode_tmap_bf16(&L->dy, dy, 5, ddims, dstr, dbox, true)) return false;
+  L->halo = 1;
+  L->block_n = 64;
+  return true;
+}
+
 int plan_conv_wgrad(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
                     const __nv_bfloat16* dy, float* dw) {
+  memset(L, 0, sizeof(*L));
+  if (try_wgrad_halo(L, g, x, dy, dw)) return 0;
   memset(L, 0, sizeof(*L));
   // reuse the forward plan for tile geometry, taps and the X tensor-map view
   ConvLaunch f;
@@ -622,10 +682,25 @@ static int launch_wgrad_bn(const WgradLaunch& L, cudaStream_t stream) {
   return 0;
 }
 
+static int launch_wgrad_halo(const WgradLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_halo_kernel<64>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        WgradHaloCfg::kSmemBytes));
+    attr_set = true;
+  }
+  VPD_CHECK_CUDA(launch_kernel(conv_wgrad_halo_kernel<64>, dim3(L.grid), dim3(kWgradThreads),
+                               WgradHaloCfg::kSmemBytes, stream, L.x, L.dy, L.hp));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
 int launch_wgrad(const WgradLaunch& L, cudaStream_t stream) {
   if (L.grid <= 0) return 0;
   static const int skip = env_int("VPD_DBG_SKIP_WGRAD", 0);  // timing experiments only
   if (skip) return 0;
+  if (L.halo) return launch_wgrad_halo(L, stream);
   if (L.block_n == 64) return launch_wgrad_bn<64>(L, stream);
   return launch_wgrad_bn<128>(L, stream);
 }

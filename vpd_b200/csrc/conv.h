@@ -88,6 +88,8 @@ struct WgradLaunch {
   WgradParams p;
   int block_n;
   int grid;
+  int halo;              // 1: conv_wgrad_halo_kernel (stride-1 3x3 on 8-pixel-wide tiles), hp valid
+  WgradHaloParams hp;
 };
 // dw[k*k][Cout][Cin] (fp32, tap-major) += sum over pixels dy * x  (accumulates!)
 int plan_conv_wgrad(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,

@@ -1445,4 +1445,194 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
 }
 
+// ===========================================================================
+// K2c-h: weight gradient of a stride-1 3x3 convolution with HALO REUSE.
+//
+// conv_wgrad_kernel above re-fetches the activation box for every (tap, chunk) unit and the
+// dY box for every unit pair: per 128-pixel tile 9 x 16 KB + 5 x 16 KB of L2 -> SM traffic for
+// 1280 MMA cycles at N = 64, four times what the ~50 B/cycle/SM delivery path sustains (the
+// six 64 -> 64 layers ran at 460 TFLOP/s). Here, as in the forward halo kernel, ONE TMA
+// patch {64 ch, 10, th+2 rows, tn images} brings the tile and its 1-pixel halo, and every tap
+// is a shifted operand descriptor into it. Both operands stay MN-major (the reduction runs
+// over pixels): A = patch rows, M = 2 taps x 64 input channels - the second tap is simply
+// LBO = (its first patch row - the first tap's) x 128 B away; an MMA's K = 16 pixels are two
+// 8-pixel row groups SBO = 10 patch rows (1280 B) apart; B = the dY tile [128 pixels][64 co].
+// All nine taps of a (64-channel chunk, 64-cout block) accumulate side by side in TMEM
+// (5 tap pairs x 64 columns) over the work item's pixel range and leave through coalesced
+// red.global.add.f32 into the tap-major gradient arena. Per tile: 39 KB loaded for 40 MMAs.
+// ===========================================================================
+struct WgradHaloParams {
+  int th, tn;                 // tile = 8 wide x th high x tn images, th * tn == 16
+  int tiles_w, tiles_h, tiles_b;
+  int kchunks, n_tiles;       // Cin / 64, Cout / 64
+  int splits;                 // pixel-range splits per (chunk, cout block)
+  int cin, cout;
+  int patch_bytes;            // (th + 2) * 10 * tn * 128
+  int kstep16[8];             // K step k (16 pixels): patch offset of its first row, in 16-byte units
+  float* dw;                  // [9][cout][cin] fp32, accumulated
+};
+
+struct WgradHaloCfg {
+  static constexpr int kPatchSlot = 25600;      // 200 rows (8x8 images, two per tile): max
+  static constexpr int kDyBytes = kBlockM * 128;
+  static constexpr int kStageBytes = kPatchSlot + kDyBytes;
+  static constexpr int kStages = 4;
+  static constexpr int kTmemCols = 512;         // 5 tap pairs x 64 columns, power of two
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
+};
+
+template <int NCO>   // couts per work item (accumulator columns per tap pair)
+__global__ void __launch_bounds__(kWgradThreads, 1)
+conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                       const __grid_constant__ WgradHaloParams p) {
+  using Cfg = WgradHaloCfg;
+  pdl_trigger();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(tempty_bar, 4);
+    fence_mbar_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+
+  const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int per_split = (pix_tiles + p.splits - 1) / p.splits;
+  const int total_items = p.kchunks * p.n_tiles * p.splits;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int n_tile = (item / p.splits) % p.n_tiles;
+        const int kc = item / (p.splits * p.n_tiles);
+        const int pt_end = min(pix_tiles, (split + 1) * per_split);
+        for (int pt = split * per_split; pt < pt_end; ++pt) {
+          int mt = pt;
+          const int w0 = (mt % p.tiles_w) * 8;
+          mt /= p.tiles_w;
+          const int h0 = (mt % p.tiles_h) * p.th;
+          const int b0 = (mt / p.tiles_h) * p.tn;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sp = smem + stage * Cfg::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], p.patch_bytes + Cfg::kDyBytes);
+          tma_load_5d(sp, &tmX, &full_bar[stage], kc * 64, w0 - 1, 0, h0 - 1, b0);
+          tma_load_5d(sp + Cfg::kPatchSlot, &tmDY, &full_bar[stage], n_tile * 64, w0, 0, h0, b0);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      static_assert(NCO == 64, "5 tap pairs x NCO accumulator columns must fit 512 TMEM columns");
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, NCO, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tphase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int pt_beg = split * per_split;
+        const int pt_end = min(pix_tiles, (split + 1) * per_split);
+        mbar_wait(tempty_bar, tphase ^ 1);   // the previous item's accumulators have been drained
+        tc_fence_after();
+        for (int pt = pt_beg; pt < pt_end; ++pt) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t patch = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint64_t bdesc = make_smem_desc(patch + Cfg::kPatchSlot, kBlockM * 128, 1024);
+#pragma unroll 1
+          for (int j = 0; j < 5; ++j) {
+            // taps 2j, 2j+1 (row-major over (dy, dx)): first patch row kh*10 + kw; the pair with
+            // tap 9 (absent) reads one row further - its half of the accumulator is discarded
+            const int ta = 2 * j, tb = 2 * j + 1;
+            const int row_a = (ta / 3) * 10 + ta % 3;
+            const int row_b = tb < 9 ? (tb / 3) * 10 + tb % 3 : row_a + 1;
+            const uint64_t adesc =
+                make_smem_desc(patch + row_a * 128, (row_b - row_a) * 128, 1280);
+            const uint32_t d_tmem = tmem_base + j * 64;
+#pragma unroll
+            for (int k = 0; k < kBlockM / kUmmaK; ++k)
+              umma_bf16(d_tmem, adesc + static_cast<uint64_t>(p.kstep16[k]), bdesc + 128 * k, idesc,
+                        (pt != pt_beg || k != 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull_bar);
+        tphase ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;       // TMEM lane: rows 0-63 first tap of a pair, 64-127 second
+    uint32_t tphase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int split = item % p.splits;
+      const int n_tile = (item / p.splits) % p.n_tiles;
+      const int kc = item / (p.splits * p.n_tiles);
+      const bool has_work = split * per_split < pix_tiles;
+      mbar_wait(tfull_bar, tphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < 5; ++j) {
+        const int tap = 2 * j + (r >> 6);
+        const bool valid = has_work && tap < 9;
+        float* dst = p.dw + ((size_t)(valid ? tap : 0) * p.cout + n_tile * 64) * p.cin + kc * 64 +
+                     (r & 63);
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + j * 64 + c * 32, v);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              atomicAdd(dst + (size_t)(c * 32 + i) * p.cin, __uint_as_float(v[i]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar);
+      tphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+
 }  // namespace vpd
