@@ -310,7 +310,7 @@ def classify_kernel(name):
         return 'other', name
     base, targs = m.group(1), [a.strip() for a in (m.group(2) or '').split(',')]
     short = base + ('<' + ','.join(targs) + '>' if m.group(2) else '')
-    if base == 'conv_wgrad_kernel':
+    if base in ('conv_wgrad_kernel', 'conv_wgrad_halo_kernel'):
         return 'conv_wgrad', short
     if base in ('conv_igemm_kernel', 'conv3x3_halo_kernel', 'conv3x3_halo_stream_kernel'):
         mode = targs[-1]

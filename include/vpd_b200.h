@@ -190,13 +190,15 @@ VPD_API int vpd_bn_act_bwd(const void* dz, const void* z, void* dmask, int64_t M
                    const void* y2, void* dy2, const float* gamma2, const float* save_mean2,
                    const float* save_rstd2, vpd_stat_acc* sums2, float* dgamma2, float* dbeta2,
                    void* stream);
-/* stem: train-mode BN + ReLU + maxpool 3x3/2 pad 1 (argmax: uint8 window index) */
-VPD_API int vpd_stem_bn_pool_fwd(const void* y, void* z, uint8_t* argmax, int N, int H, int W, int C,
-                         const vpd_stat_acc* stats, const float* gamma, const float* beta,
+/* stem: train-mode BN + ReLU + maxpool 3x3/2 pad 1 (argmax: uint8 window index; ysel, may be
+ * NULL: bf16 [N][H/2][W/2][C], the pre-BN value at the argmax - handing it to the backward
+ * call lets its reduction read two pooled tensors instead of gathering from y again) */
+VPD_API int vpd_stem_bn_pool_fwd(const void* y, void* z, uint8_t* argmax, void* ysel, int N, int H, int W,
+                         int C, const vpd_stat_acc* stats, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, int64_t* num_batches,
                          float* save_mean, float* save_rstd, void* stream);
-VPD_API int vpd_stem_bn_pool_bwd(const void* dpool, const uint8_t* argmax, const void* y, void* dy,
-                         int N, int H, int W, int C, const float* gamma, const float* beta,
+VPD_API int vpd_stem_bn_pool_bwd(const void* dpool, const uint8_t* argmax, const void* y,
+                         const void* ysel, void* dy, int N, int H, int W, int C, const float* gamma, const float* beta,
                          const float* save_mean, const float* save_rstd, vpd_stat_acc* sums,
                          float* dgamma, float* dbeta, void* stream);
 /* K4: avgpool -> fc -> [FCNet] -> sum-squared-error loss and backward. params/grads:

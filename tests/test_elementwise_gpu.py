@@ -97,8 +97,13 @@ def test_stem_bn_pool_forward_and_backward(N, H, W):
     sm = torch.empty(C, device=dev()); sr = torch.empty(C, device=dev())
     z = torch.empty((N, H // 2, W // 2, C), device=dev(), dtype=torch.bfloat16)
     am = torch.empty((N, H // 2, W // 2, C), device=dev(), dtype=torch.uint8)
-    lib().call('vpd_stem_bn_pool_fwd', y, z, am, N, H, W, C, _stats(nchw_f32(y)), gamma, beta, rm, rv,
-               nbt, sm, sr, stream_ptr())
+    ysel = torch.empty_like(z)
+    lib().call('vpd_stem_bn_pool_fwd', y, z, am, ysel, N, H, W, C, _stats(nchw_f32(y)), gamma, beta,
+               rm, rv, nbt, sm, sr, stream_ptr())
+    # ysel = the pre-BN value the pooled output came from: bn+relu of it reproduces z
+    sc = gamma * sr
+    zz = torch.relu(ysel.float() * sc + (beta - sm * sc))
+    assert rel_err(zz, z.float()) < 5e-3
     yf = nchw_f32(y).requires_grad_(True)
     gr = gamma.clone().requires_grad_(True); br = beta.clone().requires_grad_(True)
     ref = F.max_pool2d(_bn_ref(yf, gr, br).relu(), 3, 2, 1)
@@ -109,10 +114,18 @@ def test_stem_bn_pool_forward_and_backward(N, H, W):
     dy = torch.empty_like(y)
     sums = acc_zeros((2, C), dev())
     dgamma = torch.empty(C, device=dev()); dbeta = torch.empty(C, device=dev())
-    lib().call('vpd_stem_bn_pool_bwd', dpool, am, y, dy, N, H, W, C, gamma, beta, sm, sr, sums, dgamma,
-               dbeta, stream_ptr())
+    lib().call('vpd_stem_bn_pool_bwd', dpool, am, y, ysel, dy, N, H, W, C, gamma, beta, sm, sr, sums,
+               dgamma, dbeta, stream_ptr())
     assert rel_err(nchw_f32(dy), yf.grad) < 2e-2
     assert rel_err(dgamma, gr.grad) < 1e-2 and rel_err(dbeta, br.grad) < 1e-2
+    # without ysel the reduction gathers the windows from y: bit-identical sums and outputs
+    dy2 = torch.empty_like(y)
+    sums2 = acc_zeros((2, C), dev())
+    dg2 = torch.empty(C, device=dev()); db2 = torch.empty(C, device=dev())
+    lib().call('vpd_stem_bn_pool_bwd', dpool, am, y, None, dy2, N, H, W, C, gamma, beta, sm, sr, sums2,
+               dg2, db2, stream_ptr())
+    assert rel_err(dg2, dgamma) < 1e-5 and rel_err(db2, dbeta) < 1e-5
+    assert rel_err(nchw_f32(dy2), nchw_f32(dy)) < 1e-3
 
 
 @pytest.mark.parametrize('motion,D', [(1, 32), (0, 26)])

@@ -69,3 +69,18 @@ def test_conv2d_wgrad_b256(case):
 def test_stem_b256():
     small.test_stem_conv_fwd(B, 128, 128, 5)
     small.test_stem_conv_wgrad(B, 128, 128, 5)
+
+
+def test_optin_halo_wgrad_kernel_parity():
+    """conv_wgrad_halo_kernel (VPD_WGRAD_HALO=1; opt-in, see conv.cu::try_wgrad_halo) against the
+    same references, small shapes and batch 256 (the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, VPD_WGRAD_HALO='1')
+    res = subprocess.run([sys.executable, '-m', 'pytest', '-q', '-x',
+                          os.path.join(here, 'test_ops_gpu.py'), os.path.join(here, 'test_ops_b256_gpu.py'),
+                          '-k', 'wgrad and not optin'], env=env, capture_output=True, text=True,
+                         timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:]

@@ -1,4 +1,5 @@
 import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
-k=d['kernels']
-print('value {:.0f} ms {:.3f} e2e {:.0f} | fwd {} dgrad {} wgrad {} ewf {} ewb {}'.format(d['value'], d['ms_per_step'], d['e2e']['value'] if d['e2e'] else 0, k['conv_fwd']['by_stage_ms'], k['conv_dgrad']['by_stage_ms'], k['conv_wgrad']['ms_per_step'], k['bn_relu_pool_fwd']['ms_per_step'], k['bn_relu_pool_bwd']['ms_per_step']))
+k=d.get('kernels') or {}
+fam={n:(v['ms_per_step'], v.get('tflops')) for n,v in k.items() if isinstance(v,dict) and 'ms_per_step' in v}
+print('value {:.0f} ms {:.3f} mhz {} e2e {:.0f} frac {} | {}'.format(d['value'], d['ms_per_step'], (d.get('clocks') or {}).get('sm_mhz'), d['e2e']['value'] if d.get('e2e') else 0, (d.get('roofline') or {}).get('frac'), fam))

@@ -314,8 +314,8 @@ int vpd_bn_act_bwd(const void* dz, const void* z, void* dmask, int64_t M, int C,
   return launch_bn_bwd(q, (cudaStream_t)stream);
 }
 
-int vpd_stem_bn_pool_fwd(const void* y, void* z, uint8_t* argmax, int N, int H, int W, int C,
-                         const vpd_stat_acc* stats, const float* gamma, const float* beta,
+int vpd_stem_bn_pool_fwd(const void* y, void* z, uint8_t* argmax, void* ysel, int N, int H, int W,
+                         int C, const vpd_stat_acc* stats, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, int64_t* num_batches,
                          float* save_mean, float* save_rstd, void* stream) {
   PoolParams pp;
@@ -323,14 +323,15 @@ int vpd_stem_bn_pool_fwd(const void* y, void* z, uint8_t* argmax, int N, int H, 
   pp.y = (const bf16*)y;
   pp.z = (bf16*)z;
   pp.argmax = argmax;
+  pp.ysel = (bf16*)ysel;
   pp.N = N; pp.H = H; pp.W = W; pp.C = C;
   pp.bn = make_bn(stats, gamma, beta, running_mean, running_var, num_batches, save_mean, save_rstd,
                   (long long)N * H * W);
   return launch_bn_pool(pp, (cudaStream_t)stream);
 }
 
-int vpd_stem_bn_pool_bwd(const void* dpool, const uint8_t* argmax, const void* y, void* dy,
-                         int N, int H, int W, int C, const float* gamma, const float* beta,
+int vpd_stem_bn_pool_bwd(const void* dpool, const uint8_t* argmax, const void* y,
+                         const void* ysel, void* dy, int N, int H, int W, int C, const float* gamma, const float* beta,
                          const float* save_mean, const float* save_rstd, vpd_stat_acc* sums,
                          float* dgamma, float* dbeta, void* stream) {
   StemBwdParams sp;
@@ -338,6 +339,7 @@ int vpd_stem_bn_pool_bwd(const void* dpool, const uint8_t* argmax, const void* y
   sp.dpool = (const bf16*)dpool;
   sp.argmax = argmax;
   sp.y = (const bf16*)y;
+  sp.ysel = (const bf16*)ysel;
   sp.dy = (bf16*)dy;
   sp.N = N; sp.H = H; sp.W = W; sp.C = C;
   sp.gamma = gamma; sp.beta = beta; sp.save_mean = save_mean; sp.save_rstd = save_rstd;

@@ -579,7 +579,14 @@ static void copy_geometry(WgradParams* w, const ConvParams& c) {
 // conv_wgrad_halo_kernel): images of 8k x 16m pixels use 8 x 16 tiles, 8 x 8 images two per tile.
 static bool try_wgrad_halo(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
                            const __nv_bfloat16* dy, float* dw) {
-  static const int enable = env_int("VPD_WGRAD_HALO", 1);
+  // Opt-in (VPD_WGRAD_HALO=1): parity-tested, but measured no faster than conv_wgrad_kernel at
+  // batch 256 (tests/diag_wgrad.py: 64->64 29.3 vs 29.0 us, 128->128 26.5 vs 19.0, 256->256
+  // 26.2 vs 18.0). The L2 -> SM traffic does fall 6x, but with N = 64 accumulator columns per
+  // tap pair (5 pairs must share the 512 TMEM columns) every MMA reads 6 KB of operands for 32
+  // cycles of math - the shared-memory bandwidth bound (22 us without the atomics) - and a work
+  // item now covers all nine taps of 1/148 of the pixels, so 5x as many fp32 atomics leave
+  // through L2 (4-7 us, nothing to overlap them with).
+  static const int enable = env_int("VPD_WGRAD_HALO", 0);
   if (!enable || g.k != 3 || g.stride != 1 || g.pad != 1) return false;
   if (g.Cin % 64 != 0 || g.Cout % 64 != 0 || g.W % 8 != 0) return false;
   WgradHaloParams& p = L->hp;
@@ -600,6 +607,7 @@ static bool try_wgrad_halo(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat1
   p.cin = g.Cin;
   p.cout = g.Cout;
   p.dw = dw;
+  p.dbg = env_int("VPD_WGRAD_DBG", 0);
   const int img_rows = (p.th + 2) * 10;                 // patch rows per image
   p.patch_bytes = img_rows * p.tn * 128;
   if (p.patch_bytes > WgradHaloCfg::kPatchSlot) return false;
@@ -612,6 +620,8 @@ static bool try_wgrad_halo(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat1
   const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   const int combos = p.kchunks * p.n_tiles;
   int splits = device_sm_count() / combos;
+  const int cap = env_int("VPD_WGRAD_SPLITS", 0);      // experiments: fewer, longer work items
+  if (cap > 0 && splits > cap) splits = cap;
   if (splits < 1) splits = 1;
   if (splits > pix_tiles) splits = pix_tiles;
   while (splits > 1 && (splits - 1) * ((pix_tiles + splits - 1) / splits) >= pix_tiles) --splits;

@@ -1470,6 +1470,7 @@ struct WgradHaloParams {
   int patch_bytes;            // (th + 2) * 10 * tn * 128
   int kstep16[8];             // K step k (16 pixels): patch offset of its first row, in 16-byte units
   float* dw;                  // [9][cout][cin] fp32, accumulated
+  int dbg;                    // diagnostics (VPD_WGRAD_DBG): 1 skip the atomics, 2 skip the MMAs, 4 skip the dY loads
 };
 
 struct WgradHaloCfg {
@@ -1540,9 +1541,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           const int b0 = (mt / p.tiles_h) * p.tn;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sp = smem + stage * Cfg::kStageBytes;
-          mbar_expect_tx(&full_bar[stage], p.patch_bytes + Cfg::kDyBytes);
+          mbar_expect_tx(&full_bar[stage], p.patch_bytes + ((p.dbg & 4) ? 0 : Cfg::kDyBytes));
           tma_load_5d(sp, &tmX, &full_bar[stage], kc * 64, w0 - 1, 0, h0 - 1, b0);
-          tma_load_5d(sp + Cfg::kPatchSlot, &tmDY, &full_bar[stage], n_tile * 64, w0, 0, h0, b0);
+          if (!(p.dbg & 4))
+            tma_load_5d(sp + Cfg::kPatchSlot, &tmDY, &full_bar[stage], n_tile * 64, w0, 0, h0, b0);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -1569,7 +1571,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           const uint32_t patch = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t bdesc = make_smem_desc(patch + Cfg::kPatchSlot, kBlockM * 128, 1024);
 #pragma unroll 1
-          for (int j = 0; j < 5; ++j) {
+          for (int j = 0; j < ((p.dbg & 2) ? 0 : 5); ++j) {
             // taps 2j, 2j+1 (row-major over (dy, dx)): first patch row kh*10 + kw; the pair with
             // tap 9 (absent) reads one row further - its half of the accumulator is discarded
             const int ta = 2 * j, tb = 2 * j + 1;
@@ -1607,7 +1609,7 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
 #pragma unroll 1
       for (int j = 0; j < 5; ++j) {
         const int tap = 2 * j + (r >> 6);
-        const bool valid = has_work && tap < 9;
+        const bool valid = has_work && tap < 9 && !(p.dbg & 1);
         float* dst = p.dw + ((size_t)(valid ? tap : 0) * p.cout + n_tile * 64) * p.cin + kc * 64 +
                      (r & 63);
 #pragma unroll 1

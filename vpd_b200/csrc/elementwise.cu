@@ -184,11 +184,12 @@ __global__ void __launch_bounds__(kEwThreads) bn_pool_kernel(const PoolParams p)
     pix /= Wo;
     const int ho = (int)(pix % Ho);
     const int n = (int)(pix / Ho);
-    float best[8];
+    float best[8], ysel[8];
     int idx[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       best[j] = -INFINITY;
+      ysel[j] = 0.f;
       idx[j] = 0;
     }
     uint4 win[9];
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_pool_kernel(const PoolParams p)
         const float v = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
         if (v > best[j]) {
           best[j] = v;
+          ysel[j] = f[j];
           idx[j] = k;
         }
       }
@@ -227,6 +229,7 @@ __global__ void __launch_bounds__(kEwThreads) bn_pool_kernel(const PoolParams p)
       a.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
       *reinterpret_cast<uint2*>(p.argmax + o) = a;
     }
+    if (p.ysel != nullptr) stg_v4(p.ysel + o, pack8(ysel));   // bf16 in, bf16 out: exact
   }
   if (blockIdx.x == 0) bn_side_effects(p.bn, p.C);
 }
@@ -603,6 +606,63 @@ __global__ void __launch_bounds__(kEwThreads) stem_bwd_reduce_kernel(const StemB
   }
 }
 
+// pass 1 when the forward kept the pre-BN value at every window's argmax (PoolParams::ysel):
+// two pooled tensors (dpool, ysel: 2 x 33 MB at batch 256) instead of gathering the 3x3
+// window of every pooled element from y again (134 MB + argmax).
+__global__ void __launch_bounds__(kEwThreads, 3) stem_bwd_reduce_sel_kernel(const StemBwdParams p) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ __align__(16) float s_g[kColScratch];
+  __shared__ __align__(16) float s_gx[kColScratch];
+  const int groups = p.C >> 3;
+  const int g = threadIdx.x % groups;
+  float mean[8], rstd[8], sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = g * 8 + j;
+    mean[j] = __ldg(p.save_mean + c);
+    rstd[j] = __ldg(p.save_rstd + c);
+    bn_affine(__ldg(p.gamma + c), __ldg(p.beta + c), mean[j], rstd[j], sc[j], sh[j]);
+  }
+  float acc_g[8], acc_gx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc_g[j] = acc_gx[j] = 0.f;
+  const long long total = (long long)p.N * (p.H / 2) * (p.W / 2) * groups;   // 16-byte vectors
+  const long long stride = (long long)gridDim.x * kEwThreads;                // multiple of groups
+  constexpr int U = 2;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += stride * U) {
+    uint4 vd[U], vs[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long k = i + u * stride;
+      if (k < total) {
+        vd[u] = ldg_nc_v4(p.dpool + k * 8);
+        vs[u] = ldg_nc_v4(p.ysel + k * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (i + u * stride >= total) break;
+      float dp[8], ys[8];
+      unpack8(vd[u], dp);
+      unpack8(vs[u], ys);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gq = fmaf(ys[j], sc[j], sh[j]) > 0.f ? dp[j] : 0.f;
+        acc_g[j] += gq;
+        acc_gx[j] = fmaf(gq, (ys[j] - mean[j]) * rstd[j], acc_gx[j]);
+      }
+    }
+  }
+  colsum_put(acc_g, s_g, p.C, g, threadIdx.x / groups);
+  colsum_put(acc_gx, s_gx, p.C, g, threadIdx.x / groups);
+  __syncthreads();
+  for (int c = threadIdx.x; c < p.C; c += kEwThreads) {
+    stat_add(&p.sums[c], static_cast<double>(colsum_get(s_g, p.C, kEwThreads / groups, c)));
+    stat_add(&p.sums[p.C + c], static_cast<double>(colsum_get(s_gx, p.C, kEwThreads / groups, c)));
+  }
+}
+
 // pass 2 at input resolution. A thread owns a 2x2 pixel quad (rows 2a, 2a+1; columns 2b,
 // 2b+1) of one 8-channel group: the only pooling windows that contain any of its pixels are
 // (a | a+1, b | b+1), so four dpool / argmax vectors serve four outputs (a per-pixel
@@ -720,7 +780,10 @@ int launch_stem_bwd(const StemBwdParams& p, cudaStream_t s) {
   VPD_REQUIRE(p.C % 64 == 0 && p.C <= 512 && kEwThreads % (p.C / 8) == 0, "stem_bwd: C=%d", p.C);
   if (p.N == 0) return 0;
   const long long pooled = (long long)p.N * (p.H / 2) * (p.W / 2) * (p.C / 8);
-  VPD_CHECK_CUDA(launch_kernel(stem_bwd_reduce_kernel, dim3(ew_grid(pooled, 2, 2)), dim3(kEwThreads), 0, s, p));
+  if (p.ysel != nullptr)
+    VPD_CHECK_CUDA(launch_kernel(stem_bwd_reduce_sel_kernel, dim3(ew_grid(pooled, 2, 3)), dim3(kEwThreads), 0, s, p));
+  else
+    VPD_CHECK_CUDA(launch_kernel(stem_bwd_reduce_kernel, dim3(ew_grid(pooled, 2, 2)), dim3(kEwThreads), 0, s, p));
   VPD_CHECK_CUDA(launch_kernel(stem_bwd_apply_kernel, dim3(ew_grid(pooled, 2, 2)), dim3(kEwThreads), 0, s, p));
   VPD_LAUNCHED(2);
   return 0;

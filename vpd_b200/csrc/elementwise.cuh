@@ -86,6 +86,7 @@ struct PoolParams {          // stem: BN + ReLU + maxpool 3x3/2 pad 1
   const __nv_bfloat16* y;    // [N][H][W][C]
   __nv_bfloat16* z;          // [N][H/2][W/2][C]
   uint8_t* argmax;           // [N][H/2][W/2][C] window index 0..8, or null
+  __nv_bfloat16* ysel;       // [N][H/2][W/2][C] out: the PRE-BN value at the argmax, or null
   int N, H, W, C;
   BnLayer bn;
 };
@@ -113,6 +114,9 @@ struct StemBwdParams {       // maxpool + ReLU + BN backward of the stem
   const __nv_bfloat16* dpool;  // [N][H/2][W/2][C]
   const uint8_t* argmax;       // [N][H/2][W/2][C]
   const __nv_bfloat16* y;      // [N][H][W][C]
+  const __nv_bfloat16* ysel;   // [N][H/2][W/2][C] from the forward pool kernel, or null: the
+                               // reduction then reads two pooled tensors instead of gathering
+                               // every window from y again
   __nv_bfloat16* dy;           // [N][H][W][C]
   int N, H, W, C;
   const float* gamma;

@@ -218,7 +218,7 @@ struct Net {
   double* loss_dev;                // scalar
   float *save_mean, *save_rstd;    // [total_ch]
   float *ev_scale, *ev_shift;      // [total_ch]
-  bf16 *x_stem, *y_stem, *z_pool;
+  bf16 *x_stem, *y_stem, *z_pool, *y_sel;
   uint8_t* argmax;
   bf16 *gA, *gA2, *gStem;
   float* head_ws;
@@ -504,6 +504,7 @@ static long long carve(Net* n, uint8_t* base) {
   const long long l1 = B * (n->H / 4) * (n->W / 4) * 64;
   n->z_pool = c.take<bf16>(l1);
   n->argmax = c.take<uint8_t>(l1);
+  n->y_sel = c.take<bf16>(l1);
   for (auto& bd : n->blocks) {
     const long long sz = B * (bd.c2.Hin) * (bd.c2.Win) * bd.c2.Cout;
     bd.y1 = c.take<bf16>(sz);
@@ -979,6 +980,7 @@ static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, 
     pp.y = n->y_stem;
     pp.z = n->z_pool;
     pp.argmax = n->argmax;
+    pp.ysel = n->y_sel;
     pp.N = B;
     pp.H = n->H / 2;
     pp.W = n->W / 2;
@@ -1136,6 +1138,7 @@ static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, 
     sp.dpool = cur;
     sp.argmax = n->argmax;
     sp.y = n->y_stem;
+    sp.ysel = n->y_sel;
     sp.dy = n->gStem;
     sp.N = B;
     sp.H = n->H / 2;

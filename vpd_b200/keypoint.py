@@ -98,6 +98,7 @@ class FCResNet:
                 # in place: during training the entries are views into the flat arena
                 self._sd[k].copy_(v.detach().to(device=self._sd[k].device, dtype=self._sd[k].dtype))
         self._prepared = None
+        self._version = getattr(self, '_version', 0) + 1    # KeypointTrainCore re-packs its mirrors
 
     def parameters(self):
         return [v for k, v in self._sd.items()

@@ -108,6 +108,7 @@ class FCPoseDecoder:
         for k in self._sd:
             if k in sd:
                 self._sd[k].copy_(sd[k].detach().to(self._sd[k].device))      # keeps arena views
+        self._version = getattr(self, '_version', 0) + 1    # KeypointTrainCore re-packs its mirrors
 
     def parameters(self):
         return list(self._sd.values())
@@ -230,6 +231,12 @@ class KeypointTrainCore:
 
     def _refresh_mirrors(self):
         """bf16 tiled copies of every Linear weight (forward and transposed), once per step"""
+        # a load_state_dict on either module (it copies into the arena views in place) bumps
+        # the module's version: the mirrors then no longer match the masters
+        versions = tuple(getattr(m, '_version', 0) for m in (self.enc, self.dec) if m is not None)
+        if versions != getattr(self, '_seen_versions', None):
+            self._seen_versions = versions
+            self.weights_dirty = True
         if not self.weights_dirty:
             return
         L, st = lib(), self._st()
