@@ -317,7 +317,8 @@ def classify_kernel(name):
         return ('conv_fwd' if mode == '1' else 'conv_dgrad'), short      # train step: MODE 1 = forward
     if base in ('bn_apply_kernel', 'bn_pool_kernel', 'channel_stats_kernel'):
         return 'bn_relu_pool_fwd', short
-    if base in ('bn_bwd_kernel', 'stem_bwd_reduce_kernel', 'stem_bwd_apply_kernel'):
+    if base in ('bn_bwd_kernel', 'stem_bwd_reduce_kernel', 'stem_bwd_reduce_sel_kernel',
+                'stem_bwd_apply_kernel'):
         return 'bn_relu_pool_bwd', short
     if base in ('head_kernel', 'head_wgrad_kernel'):
         return 'head_loss', short

@@ -292,11 +292,10 @@ def load_model_dir(model_dir, model_epoch=None, device='cuda'):
     return model, cfg
 
 
-def read_crop_dir(crop_dir, flow_img=None, img_dim=128, nested=False):
-    """`<crop_dir>/<video>/<n>.png` (+ `<n>.<flow_img>.png`) -> videos list for
-    extract_corpus (apply_vpd_model.py:69-89). Host-side PNG decode with cv2.
-    nested: the tennis layout `<crop_dir>/<video>/<player>/<n>.png` (single_frame.py:51-57);
-    the entries are then named `<video>/<player>`."""
+def scan_crop_dir(crop_dir, nested=False):
+    """[(video name, sorted frame numbers)] of `<crop_dir>/<video>/<n>.png` without decoding
+    anything. nested: the tennis layout `<crop_dir>/<video>/<player>/<n>.png`
+    (single_frame.py:51-57); the entries are then named `<video>/<player>`."""
     img_re = re.compile(r'^\d+\.png$')
     names = []
     for video_name in sorted(os.listdir(crop_dir)):
@@ -308,11 +307,22 @@ def read_crop_dir(crop_dir, flow_img=None, img_dim=128, nested=False):
                          if os.path.isdir(os.path.join(vdir, p)))
         else:
             names.append(video_name)
-    videos = []
+    out = []
     for video_name in names:
         vdir = os.path.join(crop_dir, video_name)
-        frames = sorted(int(os.path.splitext(f)[0]) for f in os.listdir(vdir) if img_re.match(f))
-        rgb, flow = _read_frames(vdir, frames, flow_img, img_dim)
+        out.append((video_name, sorted(int(os.path.splitext(f)[0]) for f in os.listdir(vdir)
+                                       if img_re.match(f))))
+    return out
+
+
+def read_crop_dir(crop_dir, flow_img=None, img_dim=128, nested=False):
+    """`<crop_dir>/<video>/<n>.png` (+ `<n>.<flow_img>.png`) -> videos list for
+    extract_corpus (apply_vpd_model.py:69-89), every frame decoded into host memory (cv2).
+    For corpora that do not fit in RAM pack them once with vpd_b200.ingest.pack_crop_dir
+    (parallel, streaming) and hand `load_shard(...).videos()` to extract_corpus instead."""
+    videos = []
+    for video_name, frames in scan_crop_dir(crop_dir, nested):
+        rgb, flow = _read_frames(os.path.join(crop_dir, video_name), frames, flow_img, img_dim)
         videos.append((video_name, frames, rgb, flow))
     return videos
 

@@ -18,7 +18,6 @@ import os
 
 import numpy as np
 
-from .apply import read_crop_dir
 
 
 class Shard:
@@ -62,51 +61,75 @@ class Shard:
         return out
 
 
-def _read_masks(crop_dir, videos, img_dim):
-    """First channel of `<n>.mask.png` per frame ([n, H, W] uint8); frames without a mask file
-    get zeros, which the noise augmentation treats as "nothing to perturb" - the reference
-    skips the augmentation for them (single_frame.py:182)."""
+def _decode_chunk(task):
+    """Worker: decode frames[lo:hi] of one video straight into rows [row0, row0 + k) of the
+    shard files (opened memory-mapped here: nothing but the row count travels back)."""
     import cv2
-    n = sum(len(v[1]) for v in videos)
-    out = np.zeros((n, img_dim, img_dim), np.uint8)
-    row = 0
-    for name, frames, _, _ in videos:
-        for f in frames:
-            path = os.path.join(crop_dir, name, '{}.mask.png'.format(f))
-            if os.path.exists(path):
-                m = cv2.imread(path)
-                if m.shape[:2] != (img_dim, img_dim):
-                    m = cv2.resize(m, (img_dim, img_dim))
-                out[row] = m[:, :, 0]
-            row += 1
-    return out
+    (crop_dir, prefix, name, frames, row0, flow_img, img_dim, with_mask) = task
+    cv2.setNumThreads(1)
+    vdir = os.path.join(crop_dir, name)
+    rgb = np.load(prefix + '.rgb.npy', mmap_mode='r+')
+    flow = np.load(prefix + '.flow.npy', mmap_mode='r+') if flow_img else None
+    mask = np.load(prefix + '.mask.npy', mmap_mode='r+') if with_mask else None
 
-
-def pack_crop_dir(crop_dir, out_prefix, flow_img=None, img_dim=128, with_mask=False, nested=False):
-    """Decode every `<video>/<n>.png` (and flow / mask PNG) once and write the shard files.
-    nested: the tennis layout `<video>/<player>/<n>.png`; shard videos are `<video>/<player>`."""
-    videos = read_crop_dir(crop_dir, flow_img, img_dim, nested=nested)
-    n = sum(len(v[1]) for v in videos)
-    rgb = np.lib.format.open_memmap(out_prefix + '.rgb.npy', mode='w+', dtype=np.uint8,
-                                    shape=(n, img_dim, img_dim, 3))
-    flow = None
-    if flow_img:
-        flow = np.lib.format.open_memmap(out_prefix + '.flow.npy', mode='w+', dtype=np.uint8,
-                                         shape=(n, img_dim, img_dim, 3))
-    index = {'img_dim': img_dim, 'flow_img': flow_img, 'with_mask': bool(with_mask), 'videos': []}
-    if with_mask:
-        np.save(out_prefix + '.mask.npy', _read_masks(crop_dir, videos, img_dim))
-    row = 0
-    for name, frames, vrgb, vflow in videos:
-        k = len(frames)
-        rgb[row:row + k] = vrgb.numpy()
+    def fit(im):
+        return im if im.shape[:2] == (img_dim, img_dim) else cv2.resize(im, (img_dim, img_dim))
+    for j, f in enumerate(frames):
+        im = cv2.imread(os.path.join(vdir, '{}.png'.format(f)))
+        rgb[row0 + j] = fit(cv2.cvtColor(im, cv2.COLOR_BGR2RGB))
         if flow is not None:
-            flow[row:row + k] = vflow.numpy()
+            flow[row0 + j] = fit(cv2.imread(os.path.join(vdir, '{}.{}.png'.format(f, flow_img))))
+        if mask is not None:
+            # first channel of `<n>.mask.png`; frames without one keep zeros, which the noise
+            # augmentation treats as "nothing to perturb" - the reference skips it for them
+            # (single_frame.py:182)
+            path = os.path.join(vdir, '{}.mask.png'.format(f))
+            if os.path.exists(path):
+                mask[row0 + j] = fit(cv2.imread(path))[:, :, 0]
+    for a in (rgb, flow, mask):
+        if a is not None:
+            a.flush()
+    return len(frames)
+
+
+def pack_crop_dir(crop_dir, out_prefix, flow_img=None, img_dim=128, with_mask=False, nested=False,
+                  workers=None, chunk_frames=256):
+    """Decode every `<video>/<n>.png` (and flow / mask PNG) once and write the shard files.
+    nested: the tennis layout `<video>/<player>/<n>.png`; shard videos are `<video>/<player>`.
+
+    Streaming and parallel: the directory is scanned for names only, the shard files are
+    created at their final size as memory maps, and `workers` processes (default: all cores)
+    each decode chunks of `chunk_frames` frames straight into their rows - the corpus is never
+    held in RAM (the page cache writes rows back as they fill) and PNG decoding, the whole
+    cost (~0.3 ms per 128x128 PNG and core), scales with the core count."""
+    from .apply import scan_crop_dir
+    listing = scan_crop_dir(crop_dir, nested)
+    n = sum(len(frames) for _, frames in listing)
+    shape = (n, img_dim, img_dim)
+    np.lib.format.open_memmap(out_prefix + '.rgb.npy', mode='w+', dtype=np.uint8, shape=shape + (3,)).flush()
+    if flow_img:
+        np.lib.format.open_memmap(out_prefix + '.flow.npy', mode='w+', dtype=np.uint8,
+                                  shape=shape + (3,)).flush()
+    if with_mask:
+        np.lib.format.open_memmap(out_prefix + '.mask.npy', mode='w+', dtype=np.uint8, shape=shape).flush()
+    index = {'img_dim': img_dim, 'flow_img': flow_img, 'with_mask': bool(with_mask), 'videos': []}
+    tasks, row = [], 0
+    for name, frames in listing:
         index['videos'].append({'name': name, 'frames': [int(f) for f in frames], 'first_row': row})
-        row += k
-    rgb.flush()
-    if flow is not None:
-        flow.flush()
+        for lo in range(0, len(frames), chunk_frames):
+            part = frames[lo:lo + chunk_frames]
+            tasks.append((crop_dir, out_prefix, name, part, row + lo, flow_img, img_dim, with_mask))
+        row += len(frames)
+    workers = (os.cpu_count() or 1) if workers is None else workers
+    if workers <= 1 or len(tasks) <= 1:
+        done = sum(_decode_chunk(t) for t in tasks)
+    else:
+        import multiprocessing
+        from concurrent.futures import ProcessPoolExecutor
+        with ProcessPoolExecutor(min(workers, len(tasks)),
+                                 mp_context=multiprocessing.get_context('fork')) as pool:
+            done = sum(pool.map(_decode_chunk, tasks))
+    assert done == n, (done, n)
     with open(out_prefix + '.json', 'w') as fp:
         json.dump(index, fp)
     return index
