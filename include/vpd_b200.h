@@ -60,7 +60,10 @@ typedef struct vpd_stat_acc {
  *   k        1: one image per frame (flipped iff flip[b]); 2: [orig, flipped]
  * vpd_assemble_nchw writes the reference layout fp32 [B][k][C][H][W] (bit-exact);
  * vpd_assemble_stem writes the network's own input layout, bf16
- * [B*k][H+6][W+8][8], for the fused device-resident pipeline.
+ * [B*k][(H+7)/2][(W+9)/4][64]: the image zero-padded by 3 rows / columns on the top / left,
+ * 8 channel slots per pixel, stored space-to-depth 2 x 4 (cell (i, j), element (a*4+q)*8+c =
+ * padded pixel (2i+a, 4j+q), channel c; the same bytes per frame as a padded [H+6][W+8][8]
+ * image - see DESIGN.md), for the fused device-resident pipeline.
  */
 VPD_API int vpd_assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
                       const int32_t* index, const uint8_t* flip, const float* teacher,
@@ -133,6 +136,9 @@ VPD_API int vpd_sgd(float* params, const float* grads, float* momentum_buf, int6
  * weights into bf16 [k*k][Cout][Cin] (forward) and [k*k][Cin][Cout] (dgrad). */
 VPD_API int vpd_pack_conv_weight(const float* w_oihw, void* w_tap_bf16, void* wT_tap_bf16, int Cout,
                          int Cin, int k, void* stream);
+/* stem (7x7/2, Cimg <= 8 input channels): fp32 [64][Cimg][7][7] -> the operand mirrors of the
+ * space-to-depth stem kernel, 20 x 64 x 64 bf16 (8 + 12 tap tiles of the two output-column
+ * classes; opaque) */
 VPD_API int vpd_pack_stem_weight(const float* w_oihw, void* w_stem_bf16, int Cimg, void* stream);
 /* y = conv(x); optional epilogue: y*scale[c]+shift[c], + residual, ReLU; optional
  * per-channel (sum, sumsq) accumulation into stats[2][Cout] (training BN). */

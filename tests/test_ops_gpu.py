@@ -93,12 +93,26 @@ def test_assemble_empty_batch_and_bad_width():
                    None, 1, 8, 6, 1, stream_ptr())
 
 
+def _stem_cells(H, W):
+    return (H + 7) // 2, (W + 9) // 4
+
+
 def _stem_layout_ref(x_nchw):
-    """fp32 [B,C,H,W] -> bf16 [B,H+6,W+8,8] like the kernels write it."""
+    """fp32 [B,C,H,W] -> the network input layout like the kernels write it: the image padded by
+    3 rows / columns on the top / left with 8 channel slots per pixel, stored space-to-depth
+    2 x 4 (common.cuh::stem_pixel_offset): bf16 [B, Hs, Ws, 64], element (a*4 + q)*8 + c of cell
+    (i, j) = padded pixel (2i + a, 4j + q), channel c."""
     B, C, H, W = x_nchw.shape
-    out = torch.zeros((B, H + 6, W + 8, 8), dtype=torch.bfloat16)
-    out[:, 3:3 + H, 3:3 + W, :C] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
-    return out
+    Hs, Ws = _stem_cells(H, W)
+    pad = torch.zeros((B, 2 * Hs, 4 * Ws, 8), dtype=torch.bfloat16)
+    pad[:, 3:3 + H, 3:3 + W, :C] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return pad.view(B, Hs, 2, Ws, 4, 8).permute(0, 1, 3, 2, 4, 5).reshape(B, Hs, Ws, 64).contiguous()
+
+
+def _stem_layout_unpack(cells, H, W):
+    """inverse of the cell packing: [B, Hs, Ws, 64] -> padded [B, 2 Hs, 4 Ws, 8]"""
+    B, Hs, Ws, _ = cells.shape
+    return cells.view(B, Hs, Ws, 2, 4, 8).permute(0, 1, 3, 2, 4, 5).reshape(B, 2 * Hs, 4 * Ws, 8)
 
 
 def test_assemble_stem_layout_bit_exact():
@@ -108,7 +122,7 @@ def test_assemble_stem_layout_bit_exact():
     teach = synth.teacher(B, seed=39)
     ref_img, ref_emb = assemble_ref.train_batch(rgb.numpy(), flow.numpy(), teach.numpy(),
                                                 flips.numpy(), *synth.FS_MEAN_STD)
-    out = torch.full((B, 134, 136, 8), 7.0, device=dev(), dtype=torch.bfloat16)
+    out = torch.full((B, 67, 34, 64), 7.0, device=dev(), dtype=torch.bfloat16)
     tgt = torch.empty((B, 64), device=dev())
     lib().call('vpd_assemble_stem', rgb.to(dev()), flow.to(dev()), 3, None, flips.to(dev()),
                teach.to(dev()), 2, 64, MEAN, STD, out, tgt, B, 128, 128, 1, stream_ptr())
@@ -116,7 +130,7 @@ def test_assemble_stem_layout_bit_exact():
     assert torch.equal(tgt.cpu(), ref_emb)
     # k = 2 apply variant and the fp32 NCHW -> stem converter
     ref2 = assemble_ref.apply_batch(rgb.numpy(), flow.numpy(), *synth.FS_MEAN_STD, flip=True)
-    out2 = torch.empty((B * 2, 134, 136, 8), device=dev(), dtype=torch.bfloat16)
+    out2 = torch.empty((B * 2, 67, 34, 64), device=dev(), dtype=torch.bfloat16)
     lib().call('vpd_assemble_stem', rgb.to(dev()), flow.to(dev()), 3, None, None, None, 0, 0,
                MEAN, STD, out2, None, B, 128, 128, 2, stream_ptr())
     assert torch.equal(out2.cpu(), _stem_layout_ref(ref2.view(-1, 5, 128, 128)))
@@ -248,9 +262,9 @@ def test_stem_conv_fwd(N, H, W, Cimg):
     g = torch.Generator().manual_seed(7)
     x = torch.randn((N, Cimg, H, W), generator=g)
     w = torch.randn((64, Cimg, 7, 7), generator=g) * 0.1
-    xs = torch.empty((N, H + 6, W + 8, 8), device=dev(), dtype=torch.bfloat16)
+    xs = torch.empty((N,) + _stem_cells(H, W) + (64,), device=dev(), dtype=torch.bfloat16)
     lib().call('vpd_nchw_to_stem', x.to(dev()), xs, N, Cimg, H, W, stream_ptr())
-    ws = torch.empty((7, 64, 64), device=dev(), dtype=torch.bfloat16)
+    ws = torch.empty((20, 64, 64), device=dev(), dtype=torch.bfloat16)   # 8 + 12 class taps
     lib().call('vpd_pack_stem_weight', w.to(dev()), ws, Cimg, stream_ptr())
     y = torch.full((N, H // 2, W // 2, 64), float('nan'), device=dev(), dtype=torch.bfloat16)
     st = acc_zeros((2, 64), dev())
@@ -349,7 +363,7 @@ def test_conv2d_wgrad_matches_autograd(case):
 def test_stem_conv_wgrad(N, H, W, Cimg):
     g = torch.Generator().manual_seed(17)
     x = torch.randn((N, Cimg, H, W), generator=g)
-    xs = torch.empty((N, H + 6, W + 8, 8), device=dev(), dtype=torch.bfloat16)
+    xs = torch.empty((N,) + _stem_cells(H, W) + (64,), device=dev(), dtype=torch.bfloat16)
     lib().call('vpd_nchw_to_stem', x.to(dev()), xs, N, Cimg, H, W, stream_ptr())
     dy = nhwc_bf16(torch.randn((N, 64, H // 2, W // 2), generator=g)).to(dev())
     dw = torch.zeros((7, 64, 64), device=dev(), dtype=torch.float32)
@@ -448,9 +462,10 @@ def test_assemble_masked_noise_device_rng_statistics():
     assert abs(nz.mean().item()) < 4e-3 and abs(nz.std().item() - 0.05 ** 0.5) < 4e-3
     assert abs((nz ** 4).mean().item() / nz.var().item() ** 2 - 3.0) < 0.15   # Gaussian kurtosis
     # the network-layout kernel draws the same noise (then rounds to bf16)
-    stem = torch.zeros((B, H + 6, W + 8, 8), device=dev(), dtype=torch.bfloat16)
+    Hs, Ws = _stem_cells(H, W)
+    stem = torch.zeros((B, Hs, Ws, 64), device=dev(), dtype=torch.bfloat16)
     assemble_stem(stem, rgb.to(dev()), flow.to(dev()), synth.FS_MEAN_STD, seed=5, **args)
-    got = stem[:, 3:3 + H, 3:3 + W, :5].permute(0, 3, 1, 2).float()
+    got = _stem_layout_unpack(stem, H, W)[:, 3:3 + H, 3:3 + W, :5].permute(0, 3, 1, 2).float()
     assert torch.equal(got, a.to(torch.bfloat16).float())
 
 

@@ -188,25 +188,36 @@ def extract_corpus(model, videos, out_dir, rgb_mean_std, flip=True, rank=0, worl
             pin_free = [None] * n_pin        # event of the H2D that last read the staging slot
             for ci, parts in enumerate(chunks):
                 ps, ds = ci % n_pin, ci % n_in
-                if pin_free[ps] is not None:
-                    pin_free[ps].synchronize()
-                for v, lo, hi, off in parts:
-                    _, _, rgb, flow = videos[mine[v]]
-                    pin_rgb[ps][off:off + hi - lo].copy_(rgb[lo:hi])
-                    if has_flow:
-                        pin_flow[ps][off:off + hi - lo].copy_(flow[lo:hi])
+                # frames that already sit in pinned memory go to the device straight from
+                # there; pageable / memory-mapped ones pass through a pinned staging slot first
+                staged = [not videos[mine[v]][2].is_pinned() for v, _, _, _ in parts]
+                if any(staged):
+                    if pin_free[ps] is not None:
+                        pin_free[ps].synchronize()
+                    for (v, lo, hi, off), st in zip(parts, staged):
+                        if not st:
+                            continue
+                        _, _, rgb, flow = videos[mine[v]]
+                        pin_rgb[ps][off:off + hi - lo].copy_(rgb[lo:hi])
+                        if has_flow:
+                            pin_flow[ps][off:off + hi - lo].copy_(flow[lo:hi])
                 if ci >= n_in:               # the device slot's previous chunk must be consumed
                     with consumed_cv:
                         consumed_cv.wait_for(lambda: consumed[ci - n_in] is not None)
                     copy_stream.wait_event(consumed[ci - n_in])
-                n = sum(hi - lo for _, lo, hi, _ in parts)
                 with torch.cuda.stream(copy_stream):
-                    dev_rgb[ds][:n].copy_(pin_rgb[ps][:n], non_blocking=True)
-                    if has_flow:
-                        dev_flow[ds][:n].copy_(pin_flow[ps][:n], non_blocking=True)
+                    for (v, lo, hi, off), st in zip(parts, staged):
+                        _, _, rgb, flow = videos[mine[v]]
+                        k_ = hi - lo
+                        src_r = pin_rgb[ps][off:off + k_] if st else rgb[lo:hi]
+                        dev_rgb[ds][off:off + k_].copy_(src_r, non_blocking=True)
+                        if has_flow:
+                            src_f = pin_flow[ps][off:off + k_] if st else flow[lo:hi]
+                            dev_flow[ds][off:off + k_].copy_(src_f, non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(copy_stream)
-                pin_free[ps] = ev
+                if any(staged):
+                    pin_free[ps] = ev
                 ready.put((ci, ev))
         except BaseException as exc:         # surface in the consuming thread
             ready.put(exc)

@@ -9,6 +9,54 @@ import torch
 from ._lib import lib, stream_ptr
 
 
+def _check(t, name, dtype, device, ndim=None):
+    """The C ABI takes raw pointers: a wrong dtype / device / stride is silently misread there,
+    so it is rejected here. None passes (optional arguments)."""
+    if t is None or not isinstance(t, torch.Tensor):
+        return t
+    if t.dtype != dtype:
+        raise TypeError('{} must be {} (got {})'.format(name, dtype, t.dtype))
+    if t.device != device:
+        raise ValueError('{} must live on {} (got {})'.format(name, device, t.device))
+    if not t.is_contiguous():
+        raise ValueError('{} must be contiguous'.format(name))
+    if ndim is not None and t.dim() not in ndim:
+        raise ValueError('{} must have {} dimensions (got shape {})'.format(name, ndim, tuple(t.shape)))
+    return t
+
+
+def _check_batch_args(rgb, flow, flip, teacher, index, mask=None, noise_on=None, noise=None):
+    dev = rgb.device
+    if dev.type != 'cuda':
+        raise ValueError('K1 assembles on the GPU: rgb must be a CUDA tensor')
+    _check(rgb, 'rgb', torch.uint8, dev, (4,))
+    _check(flow, 'flow', torch.uint8, dev, (4,))
+    _check(flip, 'flip', torch.uint8, dev, (1,))
+    _check(teacher, 'teacher', torch.float32, dev, (2, 3))
+    _check(index, 'index', torch.int32, dev, (1,))
+    _check(mask, 'mask', torch.uint8, dev, (3,))
+    _check(noise_on, 'noise_on', torch.uint8, dev, (1,))
+    _check(noise, 'noise', torch.float32, dev, (4,))
+    if flow is not None and flow.shape[:3] != rgb.shape[:3]:
+        raise ValueError('flow {} does not match rgb {}'.format(tuple(flow.shape), tuple(rgb.shape)))
+    B = rgb.shape[0] if index is None else index.numel()
+    if flip is not None and flip.numel() != B:
+        raise ValueError('flip has {} entries for {} frames'.format(flip.numel(), B))
+    if teacher is not None and teacher.shape[0] != rgb.shape[0]:
+        raise ValueError('teacher has {} rows for a pool of {} frames'.format(
+            teacher.shape[0], rgb.shape[0]))
+
+
+def check_index(index, pool):
+    """Host-side range check of pool indices where they are drawn (the kernels trust them):
+    raises for any index outside [0, pool). Accepts a CPU tensor / array; device tensors are
+    checked only on request because it costs a synchronisation."""
+    idx = torch.as_tensor(index)
+    if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= pool):
+        raise IndexError('pool index outside [0, {})'.format(pool))
+    return index
+
+
 def _mean_std(rgb_mean_std):
     mean = torch.tensor([float(v) for v in rgb_mean_std[0]], dtype=torch.float32)
     std = torch.tensor([float(v) for v in rgb_mean_std[1]], dtype=torch.float32)
@@ -36,6 +84,7 @@ def assemble_batch(rgb, flow, rgb_mean_std, flip=None, teacher=None, index=None,
     augmentation (single_frame.py:179-191) for the frames with noise_on[b] != 0: Gaussian
     noise of sd `noise_sd` on the normalised RGB planes where the mask byte is not 0;
     `noise` fp32 [B,3,H,W] supplies the noise explicitly (else device Philox from `seed`)."""
+    _check_batch_args(rgb, flow, flip, teacher, index, mask, noise_on, noise)
     mean, std = _mean_std(rgb_mean_std)
     P, H, W, _ = rgb.shape
     B = P if index is None else index.numel()
@@ -106,6 +155,7 @@ def assemble_batch_aug(rgb, flow, rgb_mean_std, params, teacher=None, mask=None,
 
 def assemble_apply(rgb, flow, rgb_mean_std, flip=True):
     """FrameDataset batch: fp32 [B,k,C,H,W], k = 2 ([orig, flipped]) or 1."""
+    _check_batch_args(rgb, flow, None, None, None)
     mean, std = _mean_std(rgb_mean_std)
     B, H, W, _ = rgb.shape
     k = 2 if flip else 1
@@ -120,7 +170,10 @@ def assemble_stem(out, rgb, flow, rgb_mean_std, flip=None, teacher=None, index=N
                   tgt=None, mask=None, noise_on=None, noise=None, noise_sd=RANDOM_NOISE_SD,
                   seed=None):
     """Fused device pipeline: write the network's own bf16 input layout
-    [B*k, H+6, W+8, 8] straight into `out` (tensor or raw pointer)."""
+    [B*k, (H+7)//2, (W+9)//4, 64] (the padded image, 8 channel slots per pixel, space-to-depth
+    2 x 4 - include/vpd_b200.h) straight into `out` (tensor or raw pointer)."""
+    _check_batch_args(rgb, flow, flip, teacher, index, mask, noise_on, noise)
+    _check(tgt, 'tgt', torch.float32, rgb.device, (2,))
     mean, std = _mean_std(rgb_mean_std)
     P, H, W, _ = rgb.shape
     B = P if index is None else index.numel()
@@ -128,6 +181,8 @@ def assemble_stem(out, rgb, flow, rgb_mean_std, flip=None, teacher=None, index=N
     if teacher is not None:
         rows = teacher.shape[1] if teacher.dim() == 3 else 1
         tdim = teacher.shape[-1]
+        if tgt is not None and tuple(tgt.shape) != (B, tdim):
+            raise ValueError('tgt must be [{}, {}] (got {})'.format(B, tdim, tuple(tgt.shape)))
     if mask is not None:
         assert k == 1, 'the noise augmentation is a training-batch option'
         lib().call('vpd_assemble_stem_noise', rgb, flow, 0 if flow is None else flow.shape[-1],

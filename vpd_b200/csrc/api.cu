@@ -194,9 +194,10 @@ int vpd_stem_conv_fwd(const void* x_stem, const void* w_stem, void* y, int N, in
   e.shift = shift;
   e.relu = relu;
   e.stats = (StatAcc*)stats;
-  ConvLaunch L;
-  if (plan_stem_fwd(&L, N, H, W, (const bf16*)x_stem, (const bf16*)w_stem, (bf16*)y, e)) return -1;
-  return launch_conv(L, (cudaStream_t)stream);
+  ConvLaunch L[2];
+  if (plan_stem_fwd(L, N, H, W, (const bf16*)x_stem, (const bf16*)w_stem, (bf16*)y, e)) return -1;
+  if (launch_conv(L[0], (cudaStream_t)stream)) return -1;
+  return launch_conv(L[1], (cudaStream_t)stream);
 }
 
 int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N, int H, int W, int Cin,
@@ -245,9 +246,10 @@ int vpd_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int
 
 int vpd_stem_conv_wgrad(const void* x_stem, const void* dy, float* dw, int N, int H, int W,
                         void* stream) {
-  WgradLaunch L;
-  if (plan_stem_wgrad(&L, N, H, W, (const bf16*)x_stem, (const bf16*)dy, dw)) return -1;
-  return launch_wgrad(L, (cudaStream_t)stream);
+  WgradLaunch L[2];
+  if (plan_stem_wgrad(L, N, H, W, (const bf16*)x_stem, (const bf16*)dy, dw)) return -1;
+  if (launch_wgrad(L[0], (cudaStream_t)stream)) return -1;
+  return launch_wgrad(L[1], (cudaStream_t)stream);
 }
 
 static BnLayer make_bn(const vpd_stat_acc* stats, const float* gamma, const float* beta, float* rm,

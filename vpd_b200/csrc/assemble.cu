@@ -69,7 +69,7 @@ struct AsmParams {
   unsigned long long seed;
   float* out_img;         // [B][k][C][H][W] fp32, C = 3 or 5
   float* out_tgt;         // [B][tdim]
-  __nv_bfloat16* out_pad; // [B*k][H+6][W+8][8] bf16 (stem layout), or null
+  __nv_bfloat16* out_pad; // [B*k][Hs][Ws][64] bf16 (stem layout, common.cuh), or null
 };
 
 // noise added to RGB channel c of SOURCE pixel (h, ws) of output frame b (0 where masked out)
@@ -143,9 +143,9 @@ assemble_nchw_kernel(const AsmParams p) {
   }
 }
 
-// Stem layout: bf16 [frame][H+6][W+8][8] (3 zero rows/cols of conv padding on
-// the top/left, channels 5..7 zero). One 16-byte store per pixel. The border
-// is written here too, so the buffer needs no separate clearing.
+// Stem layout (common.cuh::stem_pixel_offset): the padded image, 8 channel slots per pixel
+// (5..7 zero), space-to-depth 2 x 4 cells. One 16-byte store per pixel. The border is
+// written here too, so the buffer needs no separate clearing.
 __global__ void __launch_bounds__(kAsmThreads)
 assemble_pad8_kernel(const AsmParams p) {
   pdl_trigger();
@@ -155,7 +155,10 @@ assemble_pad8_kernel(const AsmParams p) {
   uint8_t* s_rgb = sm + 5 * 256 * 4;
   const int R = p.rows_per_cta;
   uint8_t* s_flow = s_rgb + ((R * p.W * 3 + 15) & ~15);
-  const int Hp = p.H + 6, Wp = p.W + 8;
+  // padded pixel grid covered by the cells: 2 * Hs rows x 4 * Ws columns (134 x 136 for 128^2)
+  const int Hs = stem_cells_h(p.H), Ws = stem_cells_w(p.W);
+  const int Hp = 2 * Hs, Wp = 4 * Ws;
+  const long long frame_elems = (long long)Hs * Ws * 64;
   const int chunks = (Hp + R - 1) / R;
   const int b = blockIdx.x / chunks;
   const int hp0 = (blockIdx.x % chunks) * R;  // padded row range [hp0, hp0+rows)
@@ -185,13 +188,12 @@ assemble_pad8_kernel(const AsmParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int v = 0; v < p.k; ++v) {
     const bool fl = (p.k == 2) ? (v == 1) : (p.flip && p.flip[b]);
-    __nv_bfloat16* obase = p.out_pad + ((size_t)b * p.k + v) * Hp * Wp * 8;
+    __nv_bfloat16* obase = p.out_pad + ((size_t)b * p.k + v) * frame_elems;
     for (int rr = warp; rr < rows; rr += kAsmThreads / 32) {
       const int hp = hp0 + rr;
       const int h = hp - 3;
       const bool row_in = h >= 0 && h < p.H;
       const int r = h - h_lo;
-      uint4* orow = reinterpret_cast<uint4*>(obase + (size_t)hp * Wp * 8);
       const uint8_t* srow = s_rgb + r * p.W * 3;
       const uint8_t* frow = s_flow + r * p.W * p.fc;
       for (int wp = lane; wp < Wp; wp += 32) {
@@ -217,7 +219,7 @@ assemble_pad8_kernel(const AsmParams p) {
           o.y = pack_bf16x2(c2, c3);
           o.z = pack_bf16x2(c4, 0.f);
         }
-        stg_v4(orow + wp, o);
+        stg_v4(reinterpret_cast<uint4*>(obase + stem_pixel_offset(hp, wp, Ws)), o);
       }
     }
   }
@@ -229,7 +231,8 @@ nchw_to_pad8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out
                     int H, int W) {
   pdl_trigger();
   pdl_wait();
-  const int Hp = H + 6, Wp = W + 8;
+  const int Hs = stem_cells_h(H), Ws = stem_cells_w(W);
+  const int Hp = 2 * Hs, Wp = 4 * Ws;
   const long long total = (long long)B * Hp * Wp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -242,7 +245,7 @@ nchw_to_pad8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out
       const float* px = x + ((size_t)b * C * H + h) * W + w;
       for (int k = 0; k < C; ++k) c[k] = __ldg(px + (size_t)k * H * W);
     }
-    stg_v4(reinterpret_cast<uint4*>(out + i * 8),
+    stg_v4(reinterpret_cast<uint4*>(out + (long long)b * Hs * Ws * 64 + stem_pixel_offset(hp, wp, Ws)),
            make_uint4(pack_bf16x2(c[0], c[1]), pack_bf16x2(c[2], c[3]), pack_bf16x2(c[4], c[5]),
                       pack_bf16x2(c[6], c[7])));
   }
@@ -345,7 +348,7 @@ int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
   if (smem > 48 * 1024)
     VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const int chunks = (H + 6 + p.rows_per_cta - 1) / p.rows_per_cta;
+  const int chunks = (2 * stem_cells_h(H) + p.rows_per_cta - 1) / p.rows_per_cta;
   VPD_CHECK_CUDA(launch_kernel(assemble_pad8_kernel, dim3(B * chunks), dim3(kAsmThreads), smem, stream, p));
   VPD_LAUNCHED(1);
   return 0;
@@ -355,7 +358,7 @@ int nchw_to_pad8(const float* x, __nv_bfloat16* out, int B, int C, int H, int W,
                  cudaStream_t stream) {
   VPD_REQUIRE(C >= 1 && C <= 8, "nchw_to_pad8: C=%d unsupported", C);
   if (B == 0) return 0;
-  const long long total = (long long)B * (H + 6) * (W + 8);
+  const long long total = (long long)B * 2 * stem_cells_h(H) * 4 * stem_cells_w(W);
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   VPD_CHECK_CUDA(launch_kernel(nchw_to_pad8_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, x, out, B, C, H, W));

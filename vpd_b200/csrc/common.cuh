@@ -334,6 +334,22 @@ __host__ __device__ inline long long wtile_offset(int row, int col, int rows) {
   return ((long long)(kc * (rows >> 6) + rb) * 64 + rr) * 64 + chunk * 8 + (cc & 7);
 }
 
+// Network input ("stem") layout: the zero-padded image (3 rows / columns of conv padding on
+// the top / left, 8 channel slots per pixel) stored SPACE-TO-DEPTH 2 x 4: cell (i, j) holds
+// padded rows 2i, 2i+1 x padded columns 4j .. 4j+3 as 64 contiguous bf16 (128 bytes),
+// element (a*4 + q)*8 + c. [frame][Hs = (H+6+1)/2][Ws = (W+6+3)/4][64]; for 128 x 128 crops
+// 67 x 34 cells = the same 291,584 bytes per frame as a plain padded [H+6][W+8][8] image.
+// Why: the 7x7 / stride-2 stem then is two STRIDE-1 convolutions over cells (even / odd
+// output columns, 4 x 2 and 4 x 3 taps of K = 64), i.e. exactly what the halo-reuse kernels
+// do - one aligned TMA patch per tile instead of seven 128-row tiles of 32-byte-misaligned,
+// overlapping windows (which ran at a quarter of the kernel's own bound).
+__host__ __device__ inline int stem_cells_h(int H) { return (H + 6 + 1) / 2; }
+__host__ __device__ inline int stem_cells_w(int W) { return (W + 6 + 3) / 4; }
+// element offset of channel slot 0 of padded pixel (ph, pw) inside one frame
+__host__ __device__ inline long long stem_pixel_offset(int ph, int pw, int Ws) {
+  return ((long long)(ph >> 1) * Ws + (pw >> 2)) * 64 + ((ph & 1) * 4 + (pw & 3)) * 8;
+}
+
 // ------------------------------------------------------------- small helpers
 VPD_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

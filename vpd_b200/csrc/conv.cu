@@ -160,6 +160,9 @@ static bool try_halo(ConvLaunch* L, const __nv_bfloat16* x, const __nv_bfloat16*
   p.n_tiles = cout_k / L->block_n;
   p.cout = cout_k;
   for (int t = 0; t < 9; ++t) p.taps[t].kchunks = chunks;
+  p.patch_dx = -1;
+  p.patch_dy = -1;
+  p.patch_bytes = 18 * 10 * 128;
   const int total = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
   int grid = device_sm_count();
   if (grid > total) grid = total;
@@ -253,44 +256,85 @@ int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
   return 0;
 }
 
-int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
-                  const __nv_bfloat16* w_stem, __nv_bfloat16* y, const ConvEpilogue& e) {
-  memset(L, 0, sizeof(*L));
-  L->w_ptr = w_stem;
-  L->w_bytes = 7LL * 64 * 64 * 2;
-  VPD_REQUIRE(H % 2 == 0 && W % 8 == 0, "stem: H must be even and W a multiple of 8 (%d,%d)", H, W);
-  const int Ho = H / 2, Wo = W / 2, Hp = H + 6, Wp = W + 8;
-  ConvParams& p = L->p;
-  tile_geometry(Ho, Wo, N, &p);
-  p.num_taps = 7;
-  for (int kh = 0; kh < 7; ++kh) {
-    ConvTap& t = p.taps[kh];
-    t.c0 = 0;
-    t.d1 = 0;
-    t.d2 = kh % 2;
-    t.d3 = kh / 2;
-    t.src = 0;
-    t.btap = kh;
-    t.kchunks = 1;
+// The 7x7 / stride-2 / pad-3 stem on the space-to-depth input layout (common.cuh::
+// stem_pixel_offset): output pixel (ho, wo = 2m + cls) reads padded rows 2ho + kh = cell rows
+// ho + (kh >> 1) and padded columns 2wo + kw = 4m + 2 cls + kw = cell columns m + ((kw + 2 cls)
+// >> 2), so each column-parity class `cls` is a STRIDE-1 convolution over cells with 4 x (2 +
+// cls) taps of K = 64 (cell elements (a*4 + q)*8 + c <-> kh = 2 dy + a, kw = 4 dxb + q - 2 cls;
+// combinations that fall outside the 7x7 kernel carry zero weights). Two launches of the
+// resident-weight halo kernel (one aligned 19 x 10-cell patch per 16 x 8-pixel tile, every tap
+// a shifted descriptor into it), writing the class's columns through a (2C, W/2) view of y.
+// w_s2d: bf16 [8 taps of class 0][12 taps of class 1] 64 x 64 tiles (pack_stem_weight).
+int stem_taps(int cls) { return 4 * (2 + cls); }
+
+int plan_stem_fwd(ConvLaunch* L2, int N, int H, int W, const __nv_bfloat16* x_s2d,
+                  const __nv_bfloat16* w_s2d, __nv_bfloat16* y, const ConvEpilogue& e) {
+  VPD_REQUIRE(H % 32 == 0 && W % 32 == 0, "stem: H and W must be multiples of 32 (%d,%d)", H, W);
+  const int Ho = H / 2, Wo = W / 2, Hs = stem_cells_h(H), Ws = stem_cells_w(W);
+  for (int cls = 0; cls < 2; ++cls) {
+    ConvLaunch* L = L2 + cls;
+    memset(L, 0, sizeof(*L));
+    const __nv_bfloat16* wc = w_s2d + (cls == 0 ? 0 : stem_taps(0) * 4096);
+    L->w_ptr = wc;
+    L->w_bytes = (long long)stem_taps(cls) * 4096 * 2;
+    ConvParams& p = L->p;
+    p.tw = 8;
+    p.th = 16;
+    p.tn = 1;
+    p.tiles_w = (Wo / 2) / 8;
+    p.tiles_h = Ho / 16;
+    p.tiles_b = N;
+    p.batch = N;
+    p.out_h = Ho;
+    p.out_w = Wo / 2;
+    const int ntx = 2 + cls;
+    p.num_taps = stem_taps(cls);
+    for (int t = 0; t < p.num_taps; ++t) {
+      ConvTap& tp = p.taps[t];
+      tp.c0 = 0;
+      tp.d3 = t / ntx - 1;   // the kernel reads patch row (1 + d3) * 10 + (1 + d1) = dy * 10 + dxb
+      tp.d1 = t % ntx - 1;
+      tp.d2 = 0;
+      tp.src = 0;
+      tp.btap = t;
+      tp.kchunks = 1;
+    }
+    p.patch_dx = 0;
+    p.patch_dy = 0;
+    p.patch_bytes = 19 * 10 * 128;
+    p.out = y;
+    p.out_sn = (long long)Ho * Wo * 64;
+    p.out_sh = (long long)Wo * 64;
+    p.out_sw = 128;                       // consecutive pixels of a class are two columns apart
+    set_epilogue(&p, e);
+    L->block_n = 64;
+    L->cluster = 1;
+    L->halo = 4;                          // resident-weight halo kernel, 12-tap configuration
+    p.n_tiles = 1;
+    p.cout = 64;
+    p.num_classes = 1;
+    p.cls[0].tap0 = 0;
+    p.cls[0].ntaps = p.num_taps;
+    p.cls[0].out_c0 = cls * 64;
+    p.cls[0].out_d2 = 0;
+    p.cls[0].base = cls * 64;
+    const int total = p.tiles_w * p.tiles_h * p.tiles_b;
+    L->grid = device_sm_count() < total ? device_sm_count() : total;
+    uint64_t dims[5] = {64, (uint64_t)Ws, 1, (uint64_t)Hs, (uint64_t)N};
+    uint64_t str[5] = {2, 128, (uint64_t)Ws * 128, (uint64_t)Ws * 128, (uint64_t)Hs * Ws * 128};
+    uint32_t box[5] = {64, 10, 1, 19, 1};
+    if (encode_tmap_bf16(&L->a0, x_s2d, 5, dims, str, box, true)) return -1;
+    L->a1 = L->a0;
+    set_weights(&p, 0, wc, 64, 64);
+    set_weights(&p, 1, wc, 64, 64);
+    // y [N][Ho][Wo][64] seen as [N][Ho][Wo/2][2 x 64]: channel coordinate cls * 64 + c
+    uint64_t odims[5] = {128, (uint64_t)Wo / 2, 1, (uint64_t)Ho, (uint64_t)N};
+    uint64_t ostr[5] = {2, 256, (uint64_t)Wo * 128, (uint64_t)Wo * 128, (uint64_t)Ho * Wo * 128};
+    uint32_t obox[5] = {64, 8, 1, 16, 1};
+    if (encode_tmap_bf16(&L->o, y, 5, odims, ostr, obox, true)) return -1;
+    L->o2 = L->o;
   }
-  p.out = y;
-  p.out_sn = (long long)Ho * Wo * 64;
-  p.out_sh = (long long)Wo * 64;
-  p.out_sw = 64;
-  set_epilogue(&p, e);
-  finish_launch(L, 64, e.stats != nullptr);
-  // overlapping 8-pixel windows: output column wo reads padded columns
-  // 2wo .. 2wo+7 (64 contiguous bf16), output row ho / tap kh reads padded
-  // row 2ho+kh = 2*(ho + kh/2) + kh%2
-  const uint64_t pitch = (uint64_t)Wp * 8 * 2;
-  uint64_t dims[5] = {64, (uint64_t)Wo, 2, (uint64_t)Hp / 2, (uint64_t)N};
-  uint64_t str[5] = {2, 2 * 8 * 2, pitch, 2 * pitch, (uint64_t)Hp * pitch};
-  uint32_t box[5] = {64, (uint32_t)p.tw, 1, (uint32_t)p.th, (uint32_t)p.tn};
-  if (encode_tmap_bf16(&L->a0, x_pad, 5, dims, str, box, true)) return -1;
-  set_weights(&p, 0, w_stem, 64, 64);
-  set_weights(&p, 1, w_stem, 64, 64);
-  L->a1 = L->a0;
-  return out_map(L, y, N, Ho, Wo, 64, 1, 0, 0);
+  return 0;
 }
 
 int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bfloat16* dy,
@@ -460,27 +504,31 @@ static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
   }
 }
 
-template <int CHUNKS, int MODE>
+template <int CHUNKS, int MODE, int NTAPS>
 static int launch_halo_impl(const ConvLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<CHUNKS, MODE>,
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv3x3_halo_kernel<CHUNKS, MODE, NTAPS>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        HaloCfg<CHUNKS>::kSmemBytes));
+                                        HaloCfg<CHUNKS, NTAPS>::kSmemBytes));
     attr_set = true;
   }
-  VPD_CHECK_CUDA(launch_kernel(conv3x3_halo_kernel<CHUNKS, MODE>, dim3(L.grid), dim3(kConvThreads),
-                               HaloCfg<CHUNKS>::kSmemBytes, stream, L.a0, L.o, L.p));
+  VPD_CHECK_CUDA(launch_kernel(conv3x3_halo_kernel<CHUNKS, MODE, NTAPS>, dim3(L.grid),
+                               dim3(kConvThreads), HaloCfg<CHUNKS, NTAPS>::kSmemBytes, stream, L.a0,
+                               L.o, L.p));
   VPD_LAUNCHED(1);
   return 0;
 }
-template <int CHUNKS>
+template <int CHUNKS, int NTAPS = 9>
 static int launch_halo(const ConvLaunch& L, cudaStream_t stream) {
+  if (NTAPS > 9)   // the stem: forward only (statistics in training, folded BN + ReLU in eval)
+    return conv_mode(L) == 1 ? launch_halo_impl<CHUNKS, 1, NTAPS>(L, stream)
+                             : launch_halo_impl<CHUNKS, 0, NTAPS>(L, stream);
   switch (conv_mode(L)) {
-    case 1: return launch_halo_impl<CHUNKS, 1>(L, stream);
-    case 2: return launch_halo_impl<CHUNKS, 2>(L, stream);
-    case 3: return launch_halo_impl<CHUNKS, 3>(L, stream);
-    default: return launch_halo_impl<CHUNKS, 0>(L, stream);
+    case 1: return launch_halo_impl<CHUNKS, 1, 9>(L, stream);
+    case 2: return launch_halo_impl<CHUNKS, 2, 9>(L, stream);
+    case 3: return launch_halo_impl<CHUNKS, 3, 9>(L, stream);
+    default: return launch_halo_impl<CHUNKS, 0, 9>(L, stream);
   }
 }
 template <int MODE>
@@ -516,6 +564,7 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t stream) {
   }
   const ConvLaunch& L = (g_conv_trace != nullptr || dbg_skip != 0) ? traced : L0;
   if (L.halo == 1) return launch_halo<1>(L, stream);
+  if (L.halo == 4) return launch_halo<1, 12>(L, stream);
   if (L.halo == 3) {
     switch (conv_mode(L)) {
       case 1: return launch_halo_stream_impl<1>(L, stream);
@@ -608,6 +657,14 @@ static bool try_wgrad_halo(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat1
   p.cout = g.Cout;
   p.dw = dw;
   p.dbg = env_int("VPD_WGRAD_DBG", 0);
+  p.num_taps = 9;
+  p.num_pairs = 5;
+  for (int t = 0; t < 9; ++t) p.tap_row[t] = (t / 3) * 10 + t % 3;
+  p.patch_dx = -1;
+  p.patch_dy = -1;
+  p.dy_c0 = 0;
+  p.stem_ntx = 0;
+  p.stem_cls = 0;
   const int img_rows = (p.th + 2) * 10;                 // patch rows per image
   p.patch_bytes = img_rows * p.tn * 128;
   if (p.patch_bytes > WgradHaloCfg::kPatchSlot) return false;
@@ -663,18 +720,56 @@ int plan_conv_wgrad(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
   return 0;
 }
 
-int plan_stem_wgrad(WgradLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
+// Stem weight gradient on the space-to-depth input: per column class the halo-reuse wgrad
+// kernel (one aligned cell patch per 16 x 8-pixel tile feeds all 8 / 12 taps; accumulator rows
+// are cell elements, mapped back to (kh, kw, c) when they leave for the arena).
+int plan_stem_wgrad(WgradLaunch* L2, int N, int H, int W, const __nv_bfloat16* x_s2d,
                     const __nv_bfloat16* dy, float* dw) {
-  memset(L, 0, sizeof(*L));
-  ConvLaunch f;
-  ConvEpilogue e;
-  if (plan_stem_fwd(&f, N, H, W, x_pad, reinterpret_cast<const __nv_bfloat16*>(dw),
-                    const_cast<__nv_bfloat16*>(dy), e))
-    return -1;
-  copy_geometry(&L->p, f.p);
-  L->x = f.a0;
-  if (act_map(&L->dy, dy, N, H / 2, W / 2, 64, 1, f.p)) return -1;
-  finish_wgrad(L, 64, 64, 7, 1, 56, dw);
+  VPD_REQUIRE(H % 32 == 0 && W % 32 == 0, "stem: H and W must be multiples of 32 (%d,%d)", H, W);
+  const int Ho = H / 2, Wo = W / 2, Hs = stem_cells_h(H), Ws = stem_cells_w(W);
+  for (int cls = 0; cls < 2; ++cls) {
+    WgradLaunch* L = L2 + cls;
+    memset(L, 0, sizeof(*L));
+    WgradHaloParams& p = L->hp;
+    p.th = 16;
+    p.tn = 1;
+    p.tiles_w = (Wo / 2) / 8;
+    p.tiles_h = Ho / 16;
+    p.tiles_b = N;
+    p.kchunks = 1;
+    p.n_tiles = 1;
+    p.cin = 64;
+    p.cout = 64;
+    p.dw = dw;
+    p.dbg = 0;
+    p.patch_bytes = 19 * 10 * 128;
+    for (int k = 0; k < 8; ++k) p.kstep16[k] = 2 * k * 10 * 128 / 16;
+    const int ntx = 2 + cls;
+    p.num_taps = stem_taps(cls);
+    p.num_pairs = (p.num_taps + 1) / 2;
+    for (int t = 0; t < p.num_taps; ++t) p.tap_row[t] = (t / ntx) * 10 + t % ntx;
+    p.patch_dx = 0;
+    p.patch_dy = 0;
+    p.dy_c0 = cls * 64;
+    p.stem_ntx = ntx;
+    p.stem_cls = cls;
+    const int pix_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+    int splits = device_sm_count();
+    if (splits > pix_tiles) splits = pix_tiles;
+    while (splits > 1 && (splits - 1) * ((pix_tiles + splits - 1) / splits) >= pix_tiles) --splits;
+    p.splits = splits;
+    L->grid = splits;
+    uint64_t dims[5] = {64, (uint64_t)Ws, 1, (uint64_t)Hs, (uint64_t)N};
+    uint64_t str[5] = {2, 128, (uint64_t)Ws * 128, (uint64_t)Ws * 128, (uint64_t)Hs * Ws * 128};
+    uint32_t box[5] = {64, 10, 1, 19, 1};
+    if (encode_tmap_bf16(&L->x, x_s2d, 5, dims, str, box, true)) return -1;
+    uint64_t ddims[5] = {128, (uint64_t)Wo / 2, 1, (uint64_t)Ho, (uint64_t)N};
+    uint64_t dstr[5] = {2, 256, (uint64_t)Wo * 128, (uint64_t)Wo * 128, (uint64_t)Ho * Wo * 128};
+    uint32_t dbox[5] = {64, 8, 1, 16, 1};
+    if (encode_tmap_bf16(&L->dy, dy, 5, ddims, dstr, dbox, true)) return -1;
+    L->halo = 1;
+    L->block_n = 64;
+  }
   return 0;
 }
 
@@ -742,23 +837,40 @@ int pack_conv_weight(const float* w_oihw, __nv_bfloat16* w_tap, __nv_bfloat16* w
   return 0;
 }
 
-__global__ void pack_stem_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws,
-                                        int Cimg) {
+// Stem operand mirrors for the space-to-depth kernel (see plan_stem_fwd): per column-parity
+// class and tap (dy, dxb) a 64 (cout) x 64 (cell element e = (a*4 + q)*8 + c) tile in the
+// pre-tiled operand layout; the entry is weight (kh = 2 dy + a, kw = 4 dxb + q - 2 cls, c) or
+// zero where that falls outside the 7 x 7 x Cimg kernel. kArena: the source is the parameter
+// arena's packed stem block [kh][co][kw*8 + c] (fp32), else the reference's OIHW tensor.
+template <bool kArena>
+__global__ void pack_stem_s2d_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ ws,
+                                     int Cimg) {
   pdl_trigger();
   pdl_wait();
-  // ws[kh][co][kw*8 + c], zero for kw == 7 or c >= Cimg
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 7 * 64 * 64) return;
-  const int e = i % 64, co = (i / 64) % 64, kh = i / 4096;
-  const int kw = e / 8, c = e % 8;
+  if (i >= 20 * 4096) return;
+  const int e = i % 64, co = (i / 64) % 64, tg = i / 4096;       // tg: 0..7 class 0, 8..19 class 1
+  const int cls = tg >= 8 ? 1 : 0, t = tg - 8 * cls, ntx = 2 + cls;
+  const int dy = t / ntx, dxb = t % ntx;
+  const int a = e >> 5, q = (e >> 3) & 3, c = e & 7;
+  const int kh = 2 * dy + a, kw = 4 * dxb + q - 2 * cls;
   float v = 0.f;
-  if (kw < 7 && c < Cimg) v = w[((co * Cimg + c) * 7 + kh) * 7 + kw];
-  ws[(long long)kh * 4096 + wtile_offset(co, e, 64)] = __float2bfloat16_rn(v);
+  if (kh < 7 && kw >= 0 && kw < 7 && c < Cimg)
+    v = kArena ? w[kh * 4096 + co * 64 + kw * 8 + c] : w[((co * Cimg + c) * 7 + kh) * 7 + kw];
+  ws[(long long)tg * 4096 + wtile_offset(co, e, 64)] = __float2bfloat16_rn(v);
 }
 
 int pack_stem_weight(const float* w_oihw, __nv_bfloat16* w_stem, int Cimg, cudaStream_t stream) {
   VPD_REQUIRE(Cimg >= 1 && Cimg <= 8, "stem: %d input channels unsupported", Cimg);
-  VPD_CHECK_CUDA(launch_kernel(pack_stem_weight_kernel, dim3((7 * 64 * 64 + 255) / 256), dim3(256), 0, stream, w_oihw, w_stem, Cimg));
+  VPD_CHECK_CUDA(launch_kernel(pack_stem_s2d_kernel<false>, dim3((20 * 4096 + 255) / 256), dim3(256),
+                               0, stream, w_oihw, w_stem, Cimg));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
+int pack_stem_weight_arena(const float* w_arena, __nv_bfloat16* w_stem, cudaStream_t stream) {
+  VPD_CHECK_CUDA(launch_kernel(pack_stem_s2d_kernel<true>, dim3((20 * 4096 + 255) / 256), dim3(256),
+                               0, stream, w_arena, w_stem, 8));
   VPD_LAUNCHED(1);
   return 0;
 }

@@ -62,10 +62,11 @@ int device_sm_count();
 int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
                   const __nv_bfloat16* w_tap, __nv_bfloat16* y, const ConvEpilogue& e);
 
-// 7x7/2 pad 3 stem on the padded NHWC8 input [N][H+6][W+8][8];
-// w_stem = bf16 [7][64][64] (kw*8+c, zero padded)
-int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
-                  const __nv_bfloat16* w_stem, __nv_bfloat16* y, const ConvEpilogue& e);
+// 7x7/2 pad 3 stem on the space-to-depth input (common.cuh::stem_pixel_offset): TWO launches
+// (even / odd output columns) into L[0], L[1]; w_s2d = kStemMirrorElems bf16 (pack_stem_weight)
+constexpr int kStemMirrorElems = 20 * 4096;
+int plan_stem_fwd(ConvLaunch* L, int N, int H, int W, const __nv_bfloat16* x_s2d,
+                  const __nv_bfloat16* w_s2d, __nv_bfloat16* y, const ConvEpilogue& e);
 
 // dx[N,H,W,Cin] = conv_transpose(dy[N,Ho,Wo,Cout], w) (+ residual)
 // wT_tap = bf16 [k*k][Cin][Cout]. For stride 2 this produces 4 launches (one
@@ -94,8 +95,9 @@ struct WgradLaunch {
 // dw[k*k][Cout][Cin] (fp32, tap-major) += sum over pixels dy * x  (accumulates!)
 int plan_conv_wgrad(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
                     const __nv_bfloat16* dy, float* dw);
-// stem: dw[7][64][64] (kw*8+c, entries with kw == 7 are left untouched)
-int plan_stem_wgrad(WgradLaunch* L, int N, int H, int W, const __nv_bfloat16* x_pad,
+// stem: dw[7][64][64] (kh, cout, kw*8+c; entries with kw == 7 are left untouched); TWO launches
+// (even / odd output columns) into L[0], L[1]
+int plan_stem_wgrad(WgradLaunch* L, int N, int H, int W, const __nv_bfloat16* x_s2d,
                     const __nv_bfloat16* dy, float* dw);
 int launch_wgrad(const WgradLaunch& L, cudaStream_t stream);
 
@@ -103,5 +105,7 @@ int launch_wgrad(const WgradLaunch& L, cudaStream_t stream);
 int pack_conv_weight(const float* w_oihw, __nv_bfloat16* w_tap, __nv_bfloat16* wT_tap, int Cout,
                      int Cin, int k, cudaStream_t stream);
 int pack_stem_weight(const float* w_oihw, __nv_bfloat16* w_stem, int Cimg, cudaStream_t stream);
+// same mirrors from the parameter arena's packed stem block [kh][co][kw*8+c] (fp32)
+int pack_stem_weight_arena(const float* w_arena, __nv_bfloat16* w_stem, cudaStream_t stream);
 
 }  // namespace vpd

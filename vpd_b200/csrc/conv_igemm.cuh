@@ -112,6 +112,9 @@ struct ConvParams {
   // this kernel runs (they come from HBM once per step and nothing else would hide that)
   const __nv_bfloat16* pf_ptr;
   long long pf_bytes;
+  // halo-reuse kernels: the patch box (tile + halo) starts at tile origin + (patch_dx, patch_dy)
+  // and is patch_bytes long; tap t reads it from patch row (1 + d3) * 10 + (1 + d1)
+  int patch_dx, patch_dy, patch_bytes;
   int dbg;  // diagnostics (VPD_DBG_SKIP): bit0 skip the A loads, bit1 skip the B loads, bit2 skip the epilogue body
 };
 struct TileCoord {
@@ -893,14 +896,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 // loaded once and stay resident. L2->SM traffic per tile drops from
 // 9*CHUNKS*(16+8) KB to CHUNKS*22.5 KB.
 // ===========================================================================
-template <int CHUNKS>
+// NTAPS: taps with resident weights. 9 = the 3x3 layers (18-row patches); 12 = the stem on its
+// space-to-depth input (4 x 2 / 4 x 3 taps over cells, 19-row patches, see plan_stem_fwd).
+template <int CHUNKS, int NTAPS = 9>
 struct HaloCfg {
   static constexpr int kBlockN = 64;
-  static constexpr int kPatchRows = 18 * 10;
-  static constexpr int kPatchBytes = kPatchRows * 128;               // 23040
-  static constexpr int kPatchSlot = (kPatchBytes + 1023) & ~1023;    // 23552
-  static constexpr int kWBytes = 9 * CHUNKS * kBlockN * 128;         // resident weights
-  static constexpr int kSlots = CHUNKS == 1 ? 4 : 3;                 // patch ring (per chunk)
+  static constexpr int kPatchRows = (NTAPS > 9 ? 19 : 18) * 10;
+  static constexpr int kPatchSlot = (kPatchRows * 128 + 1023) & ~1023;   // 23552 / 24576
+  static constexpr int kWBytes = NTAPS * CHUNKS * kBlockN * 128;     // resident weights
+  static constexpr int kSlots = (CHUNKS == 1 && NTAPS <= 9) ? 4 : 3; // patch ring (per chunk)
   static constexpr int kTmemCols = 2 * kBlockN;
   static constexpr int kBarBytes = 1024;
   static constexpr int kSmemBytes =
@@ -908,11 +912,11 @@ struct HaloCfg {
       kStatScratchBytes + 1024;
 };
 
-template <int CHUNKS, int MODE>
+template <int CHUNKS, int MODE, int NTAPS = 9>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmOut,
                     const __grid_constant__ ConvParams p) {
-  using Cfg = HaloCfg<CHUNKS>;
+  using Cfg = HaloCfg<CHUNKS, NTAPS>;
   constexpr int BLOCK_N = Cfg::kBlockN;
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
@@ -982,10 +986,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
    if (warp == 0) {
     if (elect_one()) {
       // resident weights of this CTA's channel block: CHUNKS x 9 boxes {64 cin, 64 cout, 1}
-      mbar_expect_tx(w_bar, Cfg::kWBytes);
+      mbar_expect_tx(w_bar, p.num_taps * CHUNKS * (BLOCK_N * 128));
       for (int kc = 0; kc < CHUNKS; ++kc)
-        for (int t = 0; t < 9; ++t)
-          bulk_load(s_w + (kc * 9 + t) * (BLOCK_N * 128),
+        for (int t = 0; t < p.num_taps; ++t)
+          bulk_load(s_w + (kc * NTAPS + t) * (BLOCK_N * 128),
                     p.w[0] + ((size_t)(p.taps[t].btap * p.w_kc[0] + kc) * p.w_rb[0] + my_ntile) * 4096,
                     BLOCK_N * 128, w_bar);
       int slot = 0;
@@ -998,9 +1002,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int b0 = mt / p.tiles_h;
         for (int kc = 0; kc < CHUNKS; ++kc) {
           mbar_wait(&empty_bar[slot], phase ^ 1);
-          mbar_expect_tx(&full_bar[slot], Cfg::kPatchBytes);
-          tma_load_5d(s_patch + slot * Cfg::kPatchSlot, &tmA, &full_bar[slot], kc * 64, w0 - 1, 0,
-                      h0 - 1, b0);
+          mbar_expect_tx(&full_bar[slot], p.patch_bytes);
+          tma_load_5d(s_patch + slot * Cfg::kPatchSlot, &tmA, &full_bar[slot], kc * 64,
+                      w0 + p.patch_dx, 0, h0 + p.patch_dy, b0);
           if (++slot == Cfg::kSlots) {
             slot = 0;
             phase ^= 1;
@@ -1025,12 +1029,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint32_t patch = smem_u32(s_patch + slot * Cfg::kPatchSlot);
 #pragma unroll 1
-          for (int t = 0; t < 9; ++t) {
+          for (int t = 0; t < p.num_taps; ++t) {
             // tap (dy, dx): patch rows start at (1+dy)*10 + (1+dx); tile row h -> +10 rows
             const int start_row = (1 + p.taps[t].d3) * 10 + (1 + p.taps[t].d1);
             const uint64_t adesc = make_smem_desc(patch + start_row * 128, 16, 1280);
             const uint64_t bdesc =
-                make_smem_desc(smem_u32(s_w + (kc * 9 + t) * (BLOCK_N * 128)), 16, 1024);
+                make_smem_desc(smem_u32(s_w + (kc * NTAPS + t) * (BLOCK_N * 128)), 16, 1024);
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
               umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | t | k) != 0);
@@ -1163,8 +1167,8 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int kc = 0; kc < chunks; ++kc) {
           mbar_wait(&pempty[slot], pphase ^ 1);
           mbar_expect_tx(&pfull[slot], Cfg::kPatchBytes);
-          tma_load_5d(s_patch + slot * Cfg::kPatchSlot, &tmA, &pfull[slot], kc * 64, w0 - 1, 0,
-                      h0 - 1, b0);
+          tma_load_5d(s_patch + slot * Cfg::kPatchSlot, &tmA, &pfull[slot], kc * 64,
+                      w0 + p.patch_dx, 0, h0 + p.patch_dy, b0);
           if (++slot == Cfg::kSlots) {
             slot = 0;
             pphase ^= 1;
@@ -1471,6 +1475,16 @@ struct WgradHaloParams {
   int kstep16[8];             // K step k (16 pixels): patch offset of its first row, in 16-byte units
   float* dw;                  // [9][cout][cin] fp32, accumulated
   int dbg;                    // diagnostics (VPD_WGRAD_DBG): 1 skip the atomics, 2 skip the MMAs, 4 skip the dY loads
+  // taps: first patch row of tap t (3x3: kh * 10 + kw); processed two at a time
+  int num_taps, num_pairs;
+  int tap_row[12];
+  int patch_dx, patch_dy;     // patch origin relative to the tile origin (-1, -1 for 3x3 'same')
+  int dy_c0;                  // channel-coordinate offset of the dY view (stem: column class * 64)
+  // stem (space-to-depth input, see plan_stem_fwd): stem_ntx = horizontal taps of the class
+  // (2 or 3), else 0. Accumulator row e = (a*4 + q)*8 + c of tap (dy, dxb) is the gradient of
+  // weight (kh = 2 dy + a, kw = 4 dxb + q - 2 cls, c): written to dw[kh][co][kw*8 + c], skipped
+  // where that lies outside the 7 x 7 kernel
+  int stem_ntx, stem_cls;
 };
 
 struct WgradHaloCfg {
@@ -1478,7 +1492,7 @@ struct WgradHaloCfg {
   static constexpr int kDyBytes = kBlockM * 128;
   static constexpr int kStageBytes = kPatchSlot + kDyBytes;
   static constexpr int kStages = 4;
-  static constexpr int kTmemCols = 512;         // 5 tap pairs x 64 columns, power of two
+  static constexpr int kTmemCols = 512;         // <= 6 tap pairs x 64 columns, power of two
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 1024;
 };
 
@@ -1542,9 +1556,10 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sp = smem + stage * Cfg::kStageBytes;
           mbar_expect_tx(&full_bar[stage], p.patch_bytes + ((p.dbg & 4) ? 0 : Cfg::kDyBytes));
-          tma_load_5d(sp, &tmX, &full_bar[stage], kc * 64, w0 - 1, 0, h0 - 1, b0);
+          tma_load_5d(sp, &tmX, &full_bar[stage], kc * 64, w0 + p.patch_dx, 0, h0 + p.patch_dy, b0);
           if (!(p.dbg & 4))
-            tma_load_5d(sp + Cfg::kPatchSlot, &tmDY, &full_bar[stage], n_tile * 64, w0, 0, h0, b0);
+            tma_load_5d(sp + Cfg::kPatchSlot, &tmDY, &full_bar[stage], p.dy_c0 + n_tile * 64, w0, 0,
+                        h0, b0);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -1571,12 +1586,11 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
           const uint32_t patch = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t bdesc = make_smem_desc(patch + Cfg::kPatchSlot, kBlockM * 128, 1024);
 #pragma unroll 1
-          for (int j = 0; j < ((p.dbg & 2) ? 0 : 5); ++j) {
-            // taps 2j, 2j+1 (row-major over (dy, dx)): first patch row kh*10 + kw; the pair with
-            // tap 9 (absent) reads one row further - its half of the accumulator is discarded
-            const int ta = 2 * j, tb = 2 * j + 1;
-            const int row_a = (ta / 3) * 10 + ta % 3;
-            const int row_b = tb < 9 ? (tb / 3) * 10 + tb % 3 : row_a + 1;
+          for (int j = 0; j < ((p.dbg & 2) ? 0 : p.num_pairs); ++j) {
+            // taps 2j, 2j+1 in patch-row order; an odd tap count pairs the last one with the
+            // row after it - that half of the accumulator is discarded
+            const int row_a = p.tap_row[2 * j];
+            const int row_b = 2 * j + 1 < p.num_taps ? p.tap_row[2 * j + 1] : row_a + 1;
             const uint64_t adesc =
                 make_smem_desc(patch + row_a * 128, (row_b - row_a) * 128, 1280);
             const uint32_t d_tmem = tmem_base + j * 64;
@@ -1607,11 +1621,18 @@ conv_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_con
       mbar_wait(tfull_bar, tphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int j = 0; j < 5; ++j) {
+      for (int j = 0; j < p.num_pairs; ++j) {
         const int tap = 2 * j + (r >> 6);
-        const bool valid = has_work && tap < 9 && !(p.dbg & 1);
+        bool valid = has_work && tap < p.num_taps && !(p.dbg & 1);
         float* dst = p.dw + ((size_t)(valid ? tap : 0) * p.cout + n_tile * 64) * p.cin + kc * 64 +
                      (r & 63);
+        if (p.stem_ntx > 0) {
+          const int e = r & 63;
+          const int kh = 2 * (tap / p.stem_ntx) + (e >> 5);
+          const int kw = 4 * (tap % p.stem_ntx) + ((e >> 3) & 3) - 2 * p.stem_cls;
+          valid = valid && kh < 7 && kw >= 0 && kw < 7;
+          dst = p.dw + (valid ? kh * 4096 + kw * 8 + (e & 7) : 0);
+        }
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t v[32];

@@ -66,12 +66,12 @@ struct TensorInfo {
 
 struct Plan {  // everything that depends on the batch size
   int B;
-  ConvLaunch stem_train, stem_eval;
+  ConvLaunch stem_train[2], stem_eval[2];   // even / odd output columns (plan_stem_fwd)
   std::vector<ConvLaunch> c1_train, c2_train, ds_train, c1_eval, c2_eval, ds_eval;
   std::vector<ConvLaunch> dgrad2;                // conv2 data grad per block
   std::vector<std::vector<ConvLaunch>> dgrad1;   // conv1 (+ds) data grad per block
   std::vector<WgradLaunch> wg1, wg2, wgds;
-  WgradLaunch wg_stem;
+  WgradLaunch wg_stem[2];
   bool fused = false;  // BN-backward reductions folded into the dgrad epilogues
   bool split_stats = false;  // 64-channel layers: BN statistics by a separate kernel
 };
@@ -212,6 +212,7 @@ struct Net {
   // workspace carve
   long long ws_need = 0;
   bf16 *w_tap, *wT_tap;            // bf16 mirrors of section [A]
+  bf16* w_stem_s2d;                // stem operand mirrors for the space-to-depth kernel
   StatAcc* stats;                  // [2][total_ch] forward sum/sumsq   (zeroed per step)
   StatAcc* bwd_sums;               // [2][total_ch] backward sums        (zeroed per step)
   unsigned int* bn_bar;            // one grid-barrier counter per BN layer (fused BN apply)
@@ -488,6 +489,7 @@ static long long carve(Net* n, uint8_t* base) {
   const long long B = n->maxB;
   n->w_tap = c.take<bf16>(n->secA_len);
   n->wT_tap = c.take<bf16>(n->secA_len);
+  n->w_stem_s2d = c.take<bf16>(kStemMirrorElems);
   n->stats = c.take<StatAcc>(2 * n->total_ch);
   n->bwd_sums = c.take<StatAcc>(2 * n->total_ch);
   n->bn_bar = c.take<unsigned int>(n->num_bn + 8);   // grid-barrier counters (zeroed per step)
@@ -498,7 +500,7 @@ static long long carve(Net* n, uint8_t* base) {
   n->ev_shift = c.take<float>(n->total_ch);
   n->tr_table_dev = c.take<int>((long long)n->tr_table_host.size());
   n->mt_table_dev = c.take<int>((long long)n->mt_table_host.size());
-  n->x_stem = c.take<bf16>(B * (n->H + 6) * (n->W + 8) * 8);
+  n->x_stem = c.take<bf16>(B * stem_cells_h(n->H) * stem_cells_w(n->W) * 64);
   const long long stem_out = B * (n->H / 2) * (n->W / 2) * 64;
   n->y_stem = c.take<bf16>(stem_out);
   const long long l1 = B * (n->H / 4) * (n->W / 4) * 64;
@@ -604,6 +606,7 @@ static int pack_weights(Net* n, cudaStream_t s) {
   VPD_CHECK_CUDA(launch_kernel(mirror_weights_kernel, dim3(n->tr_blocks), dim3(256), 0, s,
                                n->params + n->secA, n->w_tap, n->wT_tap, n->tr_table_dev));
   VPD_LAUNCHED(1);
+  if (pack_stem_weight_arena(n->params + n->secA + n->stem.w_off, n->w_stem_s2d, s)) return -1;
   n->params_dirty = false;
   return 0;
 }
@@ -663,12 +666,12 @@ static Plan* get_plan(Net* n, int B) {
   };
   const bf16* wt = n->w_tap;
   const bf16* wT = n->wT_tap;
-  ok &= !plan_stem_fwd(&P->stem_train, B, n->H, n->W, n->x_stem, wt + n->stem.w_off, n->y_stem,
+  ok &= !plan_stem_fwd(P->stem_train, B, n->H, n->W, n->x_stem, n->w_stem_s2d, n->y_stem,
                        tr(n->stem_bn));
-  ok &= !plan_stem_fwd(&P->stem_eval, B, n->H, n->W, n->x_stem, wt + n->stem.w_off, n->y_stem,
+  ok &= !plan_stem_fwd(P->stem_eval, B, n->H, n->W, n->x_stem, n->w_stem_s2d, n->y_stem,
                        ev(n->stem_bn, nullptr, 1));
   if (n->grads)
-    ok &= !plan_stem_wgrad(&P->wg_stem, B, n->H, n->W, n->x_stem, n->gStem,
+    ok &= !plan_stem_wgrad(P->wg_stem, B, n->H, n->W, n->x_stem, n->gStem,
                            n->grads + n->secA + n->stem.w_off);
   const bf16* zin = n->z_pool;
   bf16* gcur = n->gA;   // buffer holding dz_out of the block being processed (backward order!)
@@ -782,7 +785,8 @@ static Plan* get_plan(Net* n, int B) {
     static const bool pf_on = getenv("VPD_WEIGHT_PREFETCH") == nullptr ||
                               getenv("VPD_WEIGHT_PREFETCH")[0] != '0';
     std::vector<ConvLaunch*> order;
-    order.push_back(&P->stem_train);
+    order.push_back(&P->stem_train[0]);
+    order.push_back(&P->stem_train[1]);
     for (size_t i = 0; i < nb; ++i) {
       order.push_back(&P->c1_train[i]);
       order.push_back(&P->c2_train[i]);
@@ -797,7 +801,8 @@ static Plan* get_plan(Net* n, int B) {
       for (size_t k = 0; k + 1 < order.size(); ++k) chain_weight_prefetch(order[k], *order[k + 1]);
     // evaluation chain (apply path)
     std::vector<ConvLaunch*> ev_order;
-    ev_order.push_back(&P->stem_eval);
+    ev_order.push_back(&P->stem_eval[0]);
+    ev_order.push_back(&P->stem_eval[1]);
     for (size_t i = 0; i < nb; ++i) {
       ev_order.push_back(&P->c1_eval[i]);
       if (n->blocks[i].has_ds) ev_order.push_back(&P->ds_eval[i]);
@@ -819,7 +824,7 @@ static int prepare_input(Net* n, const float* x_nchw, const void* x_stem, int B,
   VPD_REQUIRE(x_stem != nullptr, "net: no input given");
   if (x_stem != n->x_stem) {
     VPD_CHECK_CUDA(cudaMemcpyAsync(n->x_stem, x_stem,
-                                   (size_t)B * (n->H + 6) * (n->W + 8) * 8 * sizeof(bf16),
+                                   (size_t)B * stem_cells_h(n->H) * stem_cells_w(n->W) * 64 * sizeof(bf16),
                                    cudaMemcpyDeviceToDevice, s));
   }
   return 0;
@@ -854,7 +859,7 @@ static int forward_eval_body(Net* n, Plan* P, int B, cudaStream_t s) {
   if (launch_bn_fold(n->params + n->gamma_off, n->params + n->beta_off, n->buffers,
                      n->buffers + n->total_ch, 1e-5f, n->ev_scale, n->ev_shift, (int)n->total_ch, s))
     return -1;
-  if (launch_conv(P->stem_eval, s)) return -1;
+  if (launch_conv(P->stem_eval[0], s) || launch_conv(P->stem_eval[1], s)) return -1;
   if (launch_maxpool(n->y_stem, n->z_pool, B, n->H / 2, n->W / 2, 64, s)) return -1;
   for (size_t i = 0; i < n->blocks.size(); ++i) {
     if (launch_conv(P->c1_eval[i], s)) return -1;
@@ -971,7 +976,8 @@ static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, 
   n->prof.end(s);
 
   // ------------------------------------------------------------------ forward
-  PROF(kConvFwd, 0, launch_conv(P->stem_train, s));
+  PROF(kConvFwd, 0, launch_conv(P->stem_train[0], s));
+  PROF(kConvFwd, 0, launch_conv(P->stem_train[1], s));
   if (P->split_stats)
     PROF(kEwFwd, 0, launch_channel_stats(n->y_stem, (long long)B * (n->H / 2) * (n->W / 2), 64,
                                          n->stats + 2 * n->stem_bn.ch_off, s));
@@ -1153,7 +1159,8 @@ static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, 
     sp.dbeta = n->grads + n->beta_off + n->stem_bn.ch_off;
     PROF(kEwBwd, 0, launch_stem_bwd(sp, s));
     if (use_side && n->side.order(s, ws)) return -1;
-    PROF(kConvWgrad, 0, launch_wgrad(P->wg_stem, ws));
+    PROF(kConvWgrad, 0, launch_wgrad(P->wg_stem[0], ws));
+    PROF(kConvWgrad, 0, launch_wgrad(P->wg_stem[1], ws));
     if (use_side && n->side.order(ws, s)) return -1;   // join: every gradient is final
   }
   if (bucket_boundary(n, s, 0, bucket_hi, true)) return -1;
@@ -1164,8 +1171,9 @@ static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, 
 // The step is ~190 launches with static arguments per (batch size, input / target / loss
 // pointers): after two eager runs it is captured into a CUDA graph (the side stream and the
 // programmatic-dependent-launch edges are captured with it) and replayed, which takes the
-// per-launch driver work off the critical path. Eager when profiling, when an all-reduce
-// bucket callback is installed (host code inside the step) or with VPD_GRAPH=0.
+// per-launch driver work off the critical path. With an all-reduce bucket callback installed
+// (data parallel: host code between parts of the step) the capture is cut into one graph per
+// segment and the callback runs between the replays. Eager when profiling or with VPD_GRAPH=0.
 int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float* target, int B,
                    double* loss_sum, cudaStream_t s) {
   VPD_REQUIRE(n->grads != nullptr, "net: gradient arena not bound");
@@ -1273,6 +1281,7 @@ int net_adamw(Net* n, float* exp_avg, float* exp_avg_sq, double lr, double b1, d
                           n->secA_len, n->w_tap, n->wT_tap, n->mt_table_dev, n->mt_blocks, lr, b1,
                           b2, eps, wd, step, grad_scale, s))
     return -1;
+  if (pack_stem_weight_arena(n->params + n->secA + n->stem.w_off, n->w_stem_s2d, s)) return -1;
   n->params_dirty = false;
   return 0;
 }

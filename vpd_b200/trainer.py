@@ -158,20 +158,41 @@ class ModelTrainer:
         return want
 
     # ------------------------------------------------------------- one batch
+    def _tgt_buffer(self, n, dim):
+        """Persistent target buffer: the captured step graphs are keyed by their input / target
+        pointers, so batches are copied into fixed buffers instead of handing the loader's
+        freshly allocated tensors (a new graph key per batch) to the native step."""
+        key = (n, dim)
+        bufs = self.__dict__.setdefault('_tgt_bufs', {})
+        if key not in bufs:
+            if len(bufs) >= 4:
+                bufs.clear()
+            bufs[key] = torch.empty((n, dim), device=self.encoder._dev, dtype=torch.float32)
+        return bufs[key]
+
     def _run(self, img, tgt, n, train):
+        """One batch in the reference loader's format: fp32 NCHW `img`, fp32 `tgt` on the device.
+        The layout conversion into the bound net's own input buffer is a launch of its own, so
+        the step itself always sees the same pointers (one captured graph per batch size)."""
         enc = self.encoder
-        H, W = img.shape[-2:]
+        C, H, W = img.shape[-3:]
+        if img.dtype != torch.float32 or tgt.dtype != torch.float32:
+            raise TypeError('img / emb must be float32')
         with torch.cuda.device(enc._dev):
             if train:
                 enc._ensure_grads()
                 self._buckets_seen = []
             net = enc._native(H, W, n)
             self._overlapped = self._hook(net) if train else False
-            fn = 'vpd_net_train_step' if train else 'vpd_net_eval_loss'
-            args = [net.handle, img, None, tgt, n, self._loss]
-            if not train:
-                args.append(None)
-            lib().call(fn, *args, stream_ptr(enc._dev))
+            stem = lib().call('vpd_net_stem_input', net.handle)
+            st = stream_ptr(enc._dev)
+            lib().call('vpd_nchw_to_stem', img.contiguous(), stem, n, C, H, W, st)
+            buf = self._tgt_buffer(n, tgt.shape[1])
+            buf.copy_(tgt, non_blocking=True)
+            if train:
+                lib().call('vpd_net_train_step', net.handle, None, stem, buf, n, self._loss, st)
+            else:
+                lib().call('vpd_net_eval_loss', net.handle, None, stem, buf, n, self._loss, None, st)
 
     def train_step_stem(self, stem, tgt, n, height, width, optimizer):
         """Device-resident fast path: input already in the network layout (K1
@@ -272,12 +293,14 @@ class ModelTrainer:
             if teacher is not None:
                 if teacher.shape[-1] != expect:
                     raise ValueError('target dim {} != {}'.format(teacher.shape[-1], expect))
-                if tgt is None or tuple(tgt.shape) != (n, expect):
-                    tgt = torch.empty((n, expect), device=enc._dev, dtype=torch.float32)
+                tgt = self._tgt_buffer(n, expect)
                 assemble_stem(stem, rgb, flow, ms, flip=flip, teacher=teacher, tgt=tgt)
             else:
                 if tgt.shape[1] != expect:
                     raise ValueError('target dim {} != {}'.format(tgt.shape[1], expect))
+                buf = self._tgt_buffer(n, expect)
+                buf.copy_(tgt, non_blocking=True)
+                tgt = buf
                 assemble_stem(stem, rgb, flow, ms, flip=flip)
             self._overlapped = self._hook(net) if train else False
             if train:
@@ -296,26 +319,30 @@ class ModelTrainer:
         PCIe than the fp32 batch; normalisation / stacking / flip run in the K1 kernel."""
         dev = self.encoder._dev
         names = [k for k in ('rgb_u8', 'flow_u8', 'flip', 'emb', 'teacher') if batch.get(k) is not None]
-        key = ('u8',) + tuple((k, tuple(batch[k].shape)) for k in names)
-        ring = getattr(self, '_ring', None)
-        if ring is None or ring['key'] != key:
-            ring = {'key': key, 'free': [None, None],
-                    'buf': [{k: torch.empty(batch[k].shape, device=dev, dtype=batch[k].dtype)
-                             for k in names} for _ in range(2)]}
-            self._ring = ring
         extra = {k: batch[k] for k in ('rgb_mean_std',) if k in batch}
-        if all(batch[k].device == dev for k in names):
+        if all(batch[k].device == dev for k in names):     # already resident: no staging ring
             raw = {k: batch[k] for k in names}
             raw.update(extra)
             return raw, raw.get('emb'), None, None
+        # two device slots sized for the largest batch seen; shorter batches use slices
+        n = batch['rgb_u8'].shape[0]
+        key = ('u8',) + tuple((k, tuple(batch[k].shape[1:]), batch[k].dtype) for k in names)
+        ring = getattr(self, '_ring', None)
+        if ring is None or ring.get('key') != key or ring['cap'] < n:
+            cap = n if ring is None or ring.get('key') != key else max(ring['cap'], n)
+            ring = {'key': key, 'cap': cap, 'free': [None, None],
+                    'buf': [{k: torch.empty((cap,) + tuple(batch[k].shape[1:]), device=dev,
+                                            dtype=batch[k].dtype) for k in names}
+                            for _ in range(2)]}
+            self._ring = ring
         with torch.cuda.stream(self._copy_stream):
             if ring['free'][slot] is not None:
                 self._copy_stream.wait_event(ring['free'][slot])
             for k in names:
-                ring['buf'][slot][k].copy_(batch[k], non_blocking=True)
+                ring['buf'][slot][k][:n].copy_(batch[k], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        raw = dict(ring['buf'][slot])
+        raw = {k: ring['buf'][slot][k][:n] for k in names}
         raw.update(extra)
         return raw, raw.get('emb'), ev, slot
 
@@ -328,24 +355,29 @@ class ModelTrainer:
             return self._stage_u8(batch, slot)
         dev = self.encoder._dev
         img_h, emb_h = batch['img'], batch['emb']
-        key = (tuple(img_h.shape), tuple(emb_h.shape))
-        ring = getattr(self, '_ring', None)
-        if ring is None or ring['key'] != key:
-            ring = {'key': key,
-                    'img': [torch.empty(img_h.shape, device=dev, dtype=torch.float32) for _ in range(2)],
-                    'emb': [torch.empty(emb_h.shape, device=dev, dtype=torch.float32) for _ in range(2)],
-                    'free': [None, None]}
-            self._ring = ring
         if img_h.device == dev and emb_h.device == dev and img_h.dtype == torch.float32:
-            return img_h, emb_h, None, None            # already resident
+            return img_h, emb_h, None, None            # already resident: no staging ring
+        # ring sized for the largest batch seen (a shorter last batch of an epoch uses a slice)
+        ring = getattr(self, '_ring', None)
+        need = (tuple(img_h.shape[1:]), tuple(emb_h.shape[1:]))
+        if (ring is None or ring.get('key') != need or ring['cap'] < img_h.shape[0]):
+            cap = img_h.shape[0] if ring is None or ring.get('key') != need else \
+                max(ring['cap'], img_h.shape[0])
+            ring = {'key': need, 'cap': cap, 'free': [None, None],
+                    'img': [torch.empty((cap,) + need[0], device=dev, dtype=torch.float32)
+                            for _ in range(2)],
+                    'emb': [torch.empty((cap,) + need[1], device=dev, dtype=torch.float32)
+                            for _ in range(2)]}
+            self._ring = ring
+        n = img_h.shape[0]
         with torch.cuda.stream(self._copy_stream):
             if ring['free'][slot] is not None:         # previous consumer of this slot done?
                 self._copy_stream.wait_event(ring['free'][slot])
-            ring['img'][slot].copy_(img_h, non_blocking=True)
-            ring['emb'][slot].copy_(emb_h, non_blocking=True)
+            ring['img'][slot][:n].copy_(img_h, non_blocking=True)
+            ring['emb'][slot][:n].copy_(emb_h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        return ring['img'][slot], ring['emb'][slot], ev, slot
+        return ring['img'][slot][:n], ring['emb'][slot][:n], ev, slot
 
     def epoch(self, data_loader, optimizer=None, scaler=None, progress_cb=None):
         enc = self.encoder
