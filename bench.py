@@ -313,8 +313,10 @@ def classify_kernel(name):
     if base in ('conv_wgrad_kernel', 'conv_wgrad_halo_kernel'):
         return 'conv_wgrad', short
     if base in ('conv_igemm_kernel', 'conv3x3_halo_kernel', 'conv3x3_halo_stream_kernel'):
-        mode = targs[-1]
-        return ('conv_fwd' if mode == '1' else 'conv_dgrad'), short      # train step: MODE 1 = forward
+        # MODE (1 = training forward, 0 / 2 / 3 = data gradients in the train step) is the last
+        # template argument, except for conv3x3_halo_kernel<CHUNKS, MODE, NTAPS>
+        mode = targs[1] if base == 'conv3x3_halo_kernel' else targs[-1]
+        return ('conv_fwd' if mode == '1' else 'conv_dgrad'), short
     if base in ('bn_apply_kernel', 'bn_pool_kernel', 'channel_stats_kernel'):
         return 'bn_relu_pool_fwd', short
     if base in ('bn_bwd_kernel', 'stem_bwd_reduce_kernel', 'stem_bwd_reduce_sel_kernel',

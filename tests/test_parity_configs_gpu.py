@@ -121,10 +121,13 @@ def test_config2_train_step_batch256_vs_oracle():
         worst['ours'] = min(worst['ours'], (c, name))
         worst['model'] = min(worst['model'], (ce, name))
         head = name.startswith(('decoder', 'resnet.fc'))
-        # (1) never worse than the storage model says bf16 must be (margin: the two are
-        #     different noise realisations); (2) the head, which sees no amplification, tight;
+        # (1) never worse than the storage model says bf16 must be; (2) the head, which sees no
+        #     amplification, tight;
         # (3) gradient norms: weights within 3 %, 1-D tensors within 25 %
-        if c < ce - 0.08 or (head and c < 0.99) or nrel > (0.03 if og.dim() > 1 else 0.25):
+        # margins: two noise realisations of the same storage model differ by a few 1e-3 on
+        # the big weight tensors and by up to ~0.1 on 64..512-element BN vectors
+        if (c < ce - (0.05 if og.dim() > 1 else 0.15) or (head and c < 0.99)
+                or nrel > (0.03 if og.dim() > 1 else 0.25)):
             bad.append((name, round(c, 4), round(ce, 4), round(nrel, 4)))
     _log(['== config 2: train step, batch 256 (bf16 operands / activations vs fp32 oracle) ==',
           'loss {:.4f}  oracle {:.4f}  rel {:.2e}'.format(loss, ref_loss, abs(loss - ref_loss) / ref_loss),
