@@ -74,6 +74,8 @@ static void finish_launch(ConvLaunch* L, int cout, bool stats) {
   // keep the channel block fixed per CTA so BN statistics stay in shared memory
   if (stats && clusters >= L->p.n_tiles) clusters -= clusters % L->p.n_tiles;
   L->grid = clusters * cs;
+  static const int direct_on = env_int("VPD_DIRECT_SLABS", 1);
+  L->p.single_tile = (direct_on && clusters >= items) ? 1 : 0;
 }
 
 // weights [taps][rows][kdim] bf16 -> 3-D map, box {64, block_n, 1}

@@ -115,6 +115,11 @@ struct ConvParams {
   // halo-reuse kernels: the patch box (tile + halo) starts at tile origin + (patch_dx, patch_dy)
   // and is patch_bytes long; tap t reads it from patch row (1 + d3) * 10 + (1 + d1)
   int patch_dx, patch_dy, patch_bytes;
+  // generic kernel, every CTA has at most ONE tile: once its accumulator is complete the operand
+  // ring is dead, so every output slab gets its own 16 KB of it - the epilogue warps drain TMEM
+  // without waiting for slab slots and the statistics warps follow one slab behind (with the
+  // one- or two-slot ring TMEM drain, statistics and store of a slab ran back to back)
+  int single_tile;
   int dbg;  // diagnostics (VPD_DBG_SKIP): bit0 skip the A loads, bit1 skip the B loads, bit2 skip the epilogue body
 };
 struct TileCoord {
@@ -190,8 +195,9 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
   using SC = StageCfg<BLOCK_N>;
   constexpr int passes = FUSE ? 2 : 1;
   // fused-BN launches have one tile per CTA: once its accumulator is complete the operand
-  // ring is dead, so every slab of both passes gets its own 16 KB of it (no slot hand-shake)
-  constexpr bool direct = FUSE;
+  // ring is dead, so every slab of both passes gets its own 16 KB of it (no slot hand-shake);
+  // the same holds for any launch whose CTAs have a single tile (ConvParams::single_tile)
+  const bool direct = FUSE || (ring != nullptr && p.single_tile != 0);
   // pair mode (CS == 2): the leader's MMA thread owns the accumulator hand-shake, so the
   // peer's epilogue warps release the TMEM stage on the LEADER's barrier
   const uint32_t tempty_remote0 =
@@ -509,7 +515,7 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       if (cur_ntile >= 0) global_flush(cur_ntile);
       cur_ntile = n_tile;
     }
-    constexpr bool direct = FUSE;   // one tile per CTA: slab j lives in the dead operand ring
+    const bool direct = FUSE || (ring != nullptr && p.single_tile != 0);   // slab j lives in the dead operand ring
     if (direct) mbar_wait(&zfull[j], 0);
     else mbar_wait(&sfull[slot], sphase);
     const uint8_t* slab_ptr = direct ? ring + j * kSlabBytes : slabs + slot * kSlabBytes;
@@ -585,9 +591,17 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       if (!(p.dbg & (4 | 8)))
         tma_store_5d(tm_out, slabs + slot * kSlabBytes, st_c, st_w, st_d2, st_h, st_b);
       bulk_commit_group();
-      if (SC::kSlots > 1) {
-        // release the slot of the PREVIOUS slab: its store has finished reading shared memory
-        // once at most one group (the one just committed) is still pending
+      if (SC::kSlots > 1 && !(p.dbg & 64)) {
+        // Release THIS slab's slot as soon as its store has finished reading shared memory.
+        // (Releasing the previous slab's slot here instead - one group still pending - costs
+        // this thread nothing, but the slot then stays busy for the whole processing time of
+        // the next slab: with two slots the epilogue warps could refill it only after the
+        // statistics warps had finished the slab in between, i.e. TMEM drain and statistics
+        // ran back to back instead of overlapped - the ncu PC samples of the data-gradient
+        // kernels sat in exactly that wait.)
+        bulk_wait_read0();
+        mbar_arrive(&sempty[slot]);
+      } else if (SC::kSlots > 1) {
         bulk_wait_read1();
         if (prev_slot >= 0) mbar_arrive(&sempty[prev_slot]);
         prev_slot = slot;
