@@ -21,21 +21,47 @@ namespace vpd {
 
 constexpr int kAsmThreads = 256;
 
-__device__ __forceinline__ void build_lut(float* lut, const float* mean, const float* stdv,
-                                          int cimg) {
-  // lut[c*256 + u]; c < 3 rgb (or fewer), c = 3,4 flow
-  for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) {
-    const int c = i >> 8, u = i & 255;
-    float v;
-    if (c < 3) {
-      const float x = __fdiv_rn(static_cast<float>(u), 255.f);
-      v = __fdiv_rn(__fsub_rn(x, mean[c]), stdv[c]);
-    } else {
-      v = static_cast<float>(__dsub_rn(__ddiv_rn(static_cast<double>(u), 255.0), 0.5));
-    }
-    lut[i] = v;
+// The five 256-entry tables are computed ONCE per launch on the host with the reference's
+// IEEE operations (fp32 / fp64 division and subtraction are correctly rounded on the CPU and
+// in the _rn device intrinsics alike, so the entries are bit-identical to the device-built
+// tables of the first version) and travel as a kernel argument; every CTA copies them to
+// shared memory. Building them per CTA cost 768 fp32 double-divisions and 512 fp64
+// divisions in each of the 1280 CTAs of a launch.
+struct AsmLut {
+  float v[5 * 256];   // [c*256 + u]; c < 3 rgb, c = 3, 4 flow
+};
+static void host_lut(AsmLut* lut, const float* mean, const float* stdv) {
+  // a loader calls with the same normalisation constants every batch: keep the last table
+  static thread_local AsmLut cached;
+  static thread_local float key[6] = {-1.f, -1.f, -1.f, -1.f, -1.f, -1.f};
+  bool hit = true;
+  for (int i = 0; i < 3; ++i) hit = hit && key[i] == mean[i] && key[3 + i] == stdv[i];
+  if (hit) {
+    *lut = cached;
+    return;
   }
-  (void)cimg;
+  for (int c = 0; c < 5; ++c)
+    for (int u = 0; u < 256; ++u) {
+      float v;
+      if (c < 3) {
+        volatile float x = static_cast<float>(u) / 255.f;      // one rounding per operation
+        volatile float d = x - mean[c];
+        v = d / stdv[c];
+      } else {
+        volatile double q = static_cast<double>(u) / 255.0;
+        volatile double d = q - 0.5;
+        v = static_cast<float>(d);
+      }
+      lut->v[c * 256 + u] = v;
+    }
+  cached = *lut;
+  for (int i = 0; i < 3; ++i) {
+    key[i] = mean[i];
+    key[3 + i] = stdv[i];
+  }
+}
+__device__ __forceinline__ void build_lut(float* lut, const AsmLut& src) {
+  for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) lut[i] = src.v[i];
 }
 
 // Stage `rows` image rows of packed uint8 pixels (pc bytes per pixel) into smem.
@@ -84,7 +110,7 @@ __device__ __forceinline__ float pixel_noise(const AsmParams& p, int b, int src,
 
 // Reference layout: fp32 NCHW planes.
 __global__ void __launch_bounds__(kAsmThreads)
-assemble_nchw_kernel(const AsmParams p) {
+assemble_nchw_kernel(const __grid_constant__ AsmParams p, const __grid_constant__ AsmLut tables) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) uint8_t sm[];
@@ -99,7 +125,7 @@ assemble_nchw_kernel(const AsmParams p) {
   const int src = p.index ? p.index[b] : b;
   const int C = p.flow ? 5 : 3;
 
-  build_lut(lut, p.mean, p.stdv, 3);
+  build_lut(lut, tables);
   stage_rows(s_rgb, p.rgb + ((size_t)src * p.H + h0) * p.W * 3, rows * p.W * 3);
   if (p.flow) stage_rows(s_flow, p.flow + ((size_t)src * p.H + h0) * p.W * p.fc, rows * p.W * p.fc);
   __syncthreads();
@@ -147,7 +173,7 @@ assemble_nchw_kernel(const AsmParams p) {
 // (5..7 zero), space-to-depth 2 x 4 cells. One 16-byte store per pixel. The border is
 // written here too, so the buffer needs no separate clearing.
 __global__ void __launch_bounds__(kAsmThreads)
-assemble_pad8_kernel(const AsmParams p) {
+assemble_pad8_kernel(const __grid_constant__ AsmParams p, const __grid_constant__ AsmLut tables) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) uint8_t sm[];
@@ -168,7 +194,7 @@ assemble_pad8_kernel(const AsmParams p) {
   const int h_lo = max(hp0 - 3, 0), h_hi = min(hp0 + rows - 3, p.H);
   const int nimg = max(h_hi - h_lo, 0);
 
-  build_lut(lut, p.mean, p.stdv, 3);
+  build_lut(lut, tables);
   if (nimg > 0) {
     stage_rows(s_rgb, p.rgb + ((size_t)src * p.H + h_lo) * p.W * 3, nimg * p.W * 3);
     if (p.flow)
@@ -323,7 +349,9 @@ int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
     VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_nchw_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int chunks = (H + p.rows_per_cta - 1) / p.rows_per_cta;
-  VPD_CHECK_CUDA(launch_kernel(assemble_nchw_kernel, dim3(B * chunks), dim3(kAsmThreads), smem, stream, p));
+  AsmLut tables;
+  host_lut(&tables, p.mean, p.stdv);
+  VPD_CHECK_CUDA(launch_kernel(assemble_nchw_kernel, dim3(B * chunks), dim3(kAsmThreads), smem, stream, p, tables));
   VPD_LAUNCHED(1);
   return 0;
 }
@@ -349,7 +377,9 @@ int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
     VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int chunks = (2 * stem_cells_h(H) + p.rows_per_cta - 1) / p.rows_per_cta;
-  VPD_CHECK_CUDA(launch_kernel(assemble_pad8_kernel, dim3(B * chunks), dim3(kAsmThreads), smem, stream, p));
+  AsmLut tables;
+  host_lut(&tables, p.mean, p.stdv);
+  VPD_CHECK_CUDA(launch_kernel(assemble_pad8_kernel, dim3(B * chunks), dim3(kAsmThreads), smem, stream, p, tables));
   VPD_LAUNCHED(1);
   return 0;
 }
