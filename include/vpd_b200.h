@@ -338,6 +338,11 @@ VPD_API int vpd_net_set_bucket_callback(vpd_net* net, vpd_bucket_fn fn, void* us
 /* eval-mode encoder: emb_out fp32 [B][emb_dim] */
 VPD_API int vpd_net_forward(vpd_net* net, const float* x_nchw, const void* x_stem, int B,
                     float* emb_out, void* stream);
+/* training-mode encoder forward only (models/rgb.py:68-70 on a module in train() mode):
+ * BatchNorm uses the batch statistics and updates its running buffers / counters;
+ * emb_out fp32 [B][emb_dim]. No loss, no gradients (those come from vpd_net_train_step). */
+VPD_API int vpd_net_forward_train(vpd_net* net, const float* x_nchw, const void* x_stem, int B,
+                          float* emb_out, void* stream);
 /* eval-mode forward + decoder + sum-squared-error; *loss_sum (device fp64) += loss;
  * out (optional) fp32 [B][target_dim] */
 VPD_API int vpd_net_eval_loss(vpd_net* net, const float* x_nchw, const void* x_stem,

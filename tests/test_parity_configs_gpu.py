@@ -288,3 +288,29 @@ def test_net_adamw_equals_plain_adamw_and_leaves_fresh_mirrors():
             pass
     assert outs[0][0] == outs[1][0]
     assert torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][2], outs[1][2])
+
+
+def test_train_mode_forward_matches_oracle_and_updates_bn_buffers():
+    """`encoder(x)` on a model in train() mode (models/rgb.py:68-70): batch-statistics BN,
+    running buffers and counters updated - against the oracle's train-mode forward."""
+    B = 32
+    rgb, flow, fl, teach, img, tgt = _config2_batch(B)
+    m = _model(0)
+    torch.manual_seed(0)
+    sd = student_ref.init_encoder_state('resnet34', 32, True)
+    assert m.training
+    got = m(img.to(dev())).cpu().numpy()
+    with torch.no_grad():
+        ref = student_ref.encoder_forward(sd, img, 'resnet34', train=True).numpy()   # updates sd
+    cos = (got * ref).sum(1) / (np.linalg.norm(got, axis=1) * np.linalg.norm(ref, axis=1))
+    assert got.shape == (B, 32) and cos.min() >= 0.999, cos.min()
+    ours = {k: v.cpu() for k, v in m.state_dict().items()}
+    for k in ('resnet.bn1', 'resnet.layer3.2.bn1'):
+        assert int(ours[k + '.num_batches_tracked']) == 1
+        for buf in ('.running_mean', '.running_var'):
+            a, b = ours[k + buf].double(), sd[k + buf].double()
+            assert ((a - b).norm() / b.norm()).item() <= 0.05, k + buf
+    # eval mode afterwards uses those buffers
+    m.eval()
+    e = m(img.to(dev()))
+    assert e.shape == (B, 32) and torch.isfinite(e).all()

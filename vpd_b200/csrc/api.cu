@@ -413,6 +413,10 @@ int vpd_net_forward(vpd_net* net, const float* x_nchw, const void* x_stem, int B
                     float* emb_out, void* stream) {
   return net_forward((Net*)net, x_nchw, x_stem, B, emb_out, (cudaStream_t)stream);
 }
+int vpd_net_forward_train(vpd_net* net, const float* x_nchw, const void* x_stem, int B,
+                          float* emb_out, void* stream) {
+  return net_forward_train((Net*)net, x_nchw, x_stem, B, emb_out, (cudaStream_t)stream);
+}
 int vpd_net_eval_loss(vpd_net* net, const float* x_nchw, const void* x_stem,
                       const float* target, int B, double* loss_sum, float* out, void* stream) {
   return net_eval_loss((Net*)net, x_nchw, x_stem, target, B, loss_sum, out, (cudaStream_t)stream);

@@ -943,6 +943,26 @@ int net_forward(Net* n, const float* x_nchw, const void* x_stem, int B, float* e
   return 0;
 }
 
+static int train_forward_body(Net* n, Plan* P, int B, cudaStream_t s);
+
+// Forward in TRAINING mode without loss / backward (what `encoder(x)` does on a module in
+// train() mode, models/rgb.py:68-70): BatchNorm normalises with the batch statistics and
+// updates its running buffers and counters; returns the embeddings only.
+int net_forward_train(Net* n, const float* x_nchw, const void* x_stem, int B, float* emb_out,
+                      cudaStream_t s) {
+  if (prepare_input(n, x_nchw, x_stem, B, s)) return -1;
+  Plan* P = get_plan(n, B);
+  if (!P) return -1;
+  if (n->params_dirty && pack_weights(n, s)) return -1;
+  VPD_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, (size_t)((uint8_t*)n->loss_dev - (uint8_t*)n->stats), s));
+  if (train_forward_body(n, P, B, s)) return -1;
+  HeadParams h = head_params(n, n->blocks.back().zout, B);
+  h.emb_out = emb_out;
+  h.motion = 0;
+  h.T = h.D;
+  return launch_head(h, nullptr, s);
+}
+
 int net_eval_loss(Net* n, const float* x_nchw, const void* x_stem, const float* target, int B,
                   double* loss_sum, float* out, cudaStream_t s) {
   if (prepare_input(n, x_nchw, x_stem, B, s)) return -1;
@@ -964,18 +984,8 @@ int net_eval_loss(Net* n, const float* x_nchw, const void* x_stem, const float* 
     if (_rc) return -1;                \
   } while (0)
 
-static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, const float* target,
-                               int B, double* loss_sum, cudaStream_t s) {
-  PROF(kPack, 0, prepare_input(n, x_nchw, x_stem, B, s));
-  Plan* P = get_plan(n, B);
-  if (!P) return -1;
-  // zero: BN statistics (fwd + bwd, contiguous) and the conv-weight gradients
-  n->prof.begin(kPack, 5, s);
-  VPD_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, (size_t)((uint8_t*)n->loss_dev - (uint8_t*)n->stats), s));
-  VPD_CHECK_CUDA(cudaMemsetAsync(n->grads + n->secA, 0, (size_t)n->secA_len * sizeof(float), s));
-  n->prof.end(s);
-
-  // ------------------------------------------------------------------ forward
+// train-mode forward: batch-statistics BatchNorm (running buffers updated), activations kept
+static int train_forward_body(Net* n, Plan* P, int B, cudaStream_t s) {
   PROF(kConvFwd, 0, launch_conv(P->stem_train[0], s));
   PROF(kConvFwd, 0, launch_conv(P->stem_train[1], s));
   if (P->split_stats)
@@ -1032,6 +1042,22 @@ static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, 
     if (!P->c2_train[i].fused_bn) PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
     zin = bd.zout;
   }
+  return 0;
+}
+
+static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, const float* target,
+                               int B, double* loss_sum, cudaStream_t s) {
+  PROF(kPack, 0, prepare_input(n, x_nchw, x_stem, B, s));
+  Plan* P = get_plan(n, B);
+  if (!P) return -1;
+  // zero: BN statistics (fwd + bwd, contiguous) and the conv-weight gradients
+  n->prof.begin(kPack, 5, s);
+  VPD_CHECK_CUDA(cudaMemsetAsync(n->stats, 0, (size_t)((uint8_t*)n->loss_dev - (uint8_t*)n->stats), s));
+  VPD_CHECK_CUDA(cudaMemsetAsync(n->grads + n->secA, 0, (size_t)n->secA_len * sizeof(float), s));
+  n->prof.end(s);
+
+  // ------------------------------------------------------------------ forward
+  if (train_forward_body(n, P, B, s)) return -1;
 
   // ------------------------------------------------------- head: loss + gradient
   const size_t nb = n->blocks.size();

@@ -14,6 +14,8 @@ int net_bind(Net* n, float* params, float* grads, float* buffers, long long* nbt
              long long ws_bytes);
 int net_forward(Net* n, const float* x_nchw, const void* x_stem, int B, float* emb_out,
                 cudaStream_t s);
+int net_forward_train(Net* n, const float* x_nchw, const void* x_stem, int B, float* emb_out,
+                      cudaStream_t s);
 int net_eval_loss(Net* n, const float* x_nchw, const void* x_stem, const float* target, int B,
                   double* loss_sum, float* out, cudaStream_t s);
 int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float* target, int B,

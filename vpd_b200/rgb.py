@@ -261,17 +261,22 @@ class RGBF_EmbeddingModel:
             assert x.shape[1] == 3, 'Wrong number of channels for RGB'
 
     def forward(self, x):
-        """Eval-mode encoder output [B, emb_dim] as a device tensor (no autograd
-        graph: training goes through ModelTrainer.epoch, which runs the native
-        forward+backward)."""
-        if self.training:
-            raise NotImplementedError(
-                'train-mode forward is only available through ModelTrainer.epoch()')
+        """Encoder output [B, emb_dim] as a device tensor (models/rgb.py:68-70). In eval mode
+        BatchNorm uses the running statistics; in train mode (the nn.Module default) the batch
+        statistics, and the running buffers / counters are updated, like the reference module
+        does - the whole batch in one launch group, because the statistics are per batch. There
+        is no autograd graph either way: gradients come from ModelTrainer.epoch, which runs the
+        native forward + backward."""
         x = x.to(self._dev, dtype=torch.float32).contiguous()
         self._check_channels(x)
         B, _, H, W = x.shape
         out = torch.empty((B, self.emb_dim), device=self._dev, dtype=torch.float32)
         with torch.cuda.device(self._dev):
+            if self.training:
+                net = self._native(H, W, B)
+                lib().call('vpd_net_forward_train', net.handle, x, None, B, out,
+                           stream_ptr(self._dev))
+                return out
             for i in range(0, B, _MAX_CHUNK):
                 n = min(_MAX_CHUNK, B - i)
                 net = self._native(H, W, n)

@@ -195,12 +195,13 @@ def main(emb_dir, shard_prefix, save_dir, rgb_mean_std, dataset='generic', num_e
         rows = shard.rows_of([key(d) for d in part])
         if 'pools' in f:
             return f['pools'](shard, rows)
-        idx = torch.from_numpy(rows)
-        rgb = torch.from_numpy(np.asarray(shard.rgb))[idx].to(device)
-        flow = torch.from_numpy(np.asarray(shard.flow))[idx].to(device) if use_flow else None
+        # numpy fancy indexing on the memory-mapped shard reads just these rows into a fresh
+        # (writable) array
+        rgb = torch.from_numpy(np.asarray(shard.rgb)[rows]).to(device)
+        flow = torch.from_numpy(np.asarray(shard.flow)[rows]).to(device) if use_flow else None
         mask = None
         if shard.mask is not None:
-            mask = torch.from_numpy(np.asarray(shard.mask))[idx].to(device)
+            mask = torch.from_numpy(np.asarray(shard.mask)[rows]).to(device)
         return rgb, flow, mask
 
     def loader(part, length):
