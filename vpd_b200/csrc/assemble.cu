@@ -172,7 +172,7 @@ assemble_nchw_kernel(const __grid_constant__ AsmParams p, const __grid_constant_
 // Stem layout (common.cuh::stem_pixel_offset): the padded image, 8 channel slots per pixel
 // (5..7 zero), space-to-depth 2 x 4 cells. One 16-byte store per pixel. The border is
 // written here too, so the buffer needs no separate clearing.
-__global__ void __launch_bounds__(kAsmThreads)
+__global__ void __launch_bounds__(kAsmThreads, 6)
 assemble_pad8_kernel(const __grid_constant__ AsmParams p, const __grid_constant__ AsmLut tables) {
   pdl_trigger();
   pdl_wait();
