@@ -325,6 +325,14 @@ VPD_API int vpd_net_bind(vpd_net* net, float* params, float* grads, float* buffe
 VPD_API int vpd_net_adamw(vpd_net* net, float* exp_avg, float* exp_avg_sq, double lr, double beta1,
                   double beta2, double eps, double weight_decay, int step, float grad_scale,
                   void* stream);
+/* The same update for the arena range [offset, offset + count) only - one gradient bucket as
+ * handed out by the vpd_net_set_bucket_callback hook - so the optimizer can run bucket by
+ * bucket on another stream (after that bucket's all-reduce when data-parallel) while the
+ * backward pass of the earlier layers is still running. The ranges of a step must tile the
+ * arena; finish != 0 on the last one. */
+VPD_API int vpd_net_adamw_range(vpd_net* net, float* exp_avg, float* exp_avg_sq, double lr, double beta1,
+                        double beta2, double eps, double weight_decay, int step, float grad_scale,
+                        int64_t offset, int64_t count, int finish, void* stream);
 /* call after writing the parameter arena from outside (load_state_dict, optimizer) */
 VPD_API int vpd_net_params_changed(vpd_net* net);
 VPD_API void* vpd_net_stem_input(vpd_net* net);

@@ -314,3 +314,30 @@ def test_train_mode_forward_matches_oracle_and_updates_bn_buffers():
     m.eval()
     e = m(img.to(dev()))
     assert e.shape == (B, 32) and torch.isfinite(e).all()
+
+
+def test_bucketwise_adamw_equals_whole_arena_adamw():
+    """ModelTrainer applies FusedAdamW bucket by bucket from the gradient-bucket hook (on the
+    communication stream, under the rest of the backward pass): parameters, moments and BN
+    buffers after a few steps must be bit-identical to one whole-arena update per step."""
+    from vpd_b200 import ModelTrainer
+    B = 32
+    rgb, flow, fl, teach, img, tgt = _config2_batch(B)
+    batch = {'img': img.to(dev()), 'emb': tgt.to(dev())}
+    out = []
+    for bucketed in (True, False):
+        m = _model(0)
+        tr = ModelTrainer(m, True)
+        tr.bucket_adamw = bucketed
+        opt, _ = tr.get_optimizer(5e-4)
+        losses = [tr.epoch([batch, batch], optimizer=opt) for _ in range(3)]   # eager, eager, graphs
+        torch.cuda.synchronize()
+        if bucketed:
+            assert len(tr._buckets_seen) == 4 and tr._buckets_seen[-1][0] == 0
+        mm, vv = opt._state()
+        out.append((losses, m._params.clone(), mm.clone(), vv.clone(), m._buffers.clone(),
+                    opt.step_count))
+    a, b = out
+    assert a[0] == b[0] and a[5] == b[5] == 6
+    for i in (1, 2, 3, 4):
+        assert torch.equal(a[i], b[i]), i

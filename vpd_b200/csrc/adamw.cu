@@ -166,6 +166,20 @@ static AdamScalars adam_scalars(double lr, double b1, double b2, double eps, dou
   return s;
 }
 
+// the mirror-writing kernel over `tiles` table entries (pointers at the start of the conv section)
+int adamw_tiles(float* p_conv, const float* g_conv, float* m_conv, float* v_conv,
+                __nv_bfloat16* w_tap, __nv_bfloat16* wT, const int* table, int tiles, double lr,
+                double b1, double b2, double eps, double wd, int step, float grad_scale,
+                cudaStream_t stream) {
+  VPD_REQUIRE(step >= 1, "adamw: step must be >= 1");
+  if (tiles <= 0) return 0;
+  const AdamScalars s = adam_scalars(lr, b1, b2, eps, wd, step, grad_scale);
+  VPD_CHECK_CUDA(launch_kernel(adamw_mirror_kernel, dim3((unsigned)tiles), dim3(256), 0, stream,
+                               p_conv, g_conv, m_conv, v_conv, w_tap, wT, table, s));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
 // conv section [conv_off, conv_off + conv_len) of the arenas: tile kernel + mirrors; the rest
 // (BN affine, fc, decoder: a few 10^4 parameters) through the flat kernel.
 int adamw_step_mirrored(float* p, const float* g, float* m, float* v, long long n,

@@ -433,6 +433,13 @@ int vpd_net_adamw(vpd_net* net, float* exp_avg, float* exp_avg_sq, double lr, do
                    grad_scale, (cudaStream_t)stream);
 }
 
+int vpd_net_adamw_range(vpd_net* net, float* exp_avg, float* exp_avg_sq, double lr, double beta1,
+                        double beta2, double eps, double weight_decay, int step, float grad_scale,
+                        int64_t offset, int64_t count, int finish, void* stream) {
+  return net_adamw_range((Net*)net, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step,
+                         grad_scale, offset, count, finish, (cudaStream_t)stream);
+}
+
 int vpd_net_activation(vpd_net* net, int block, int which, int B, void** ptr, int64_t* numel) {
   return net_activation((Net*)net, block, which, B, ptr, (long long*)numel);
 }

@@ -1190,7 +1190,6 @@ static int net_train_step_body(Net* n, const float* x_nchw, const void* x_stem, 
     if (use_side && n->side.order(ws, s)) return -1;   // join: every gradient is final
   }
   if (bucket_boundary(n, s, 0, bucket_hi, true)) return -1;
-  n->params_dirty = true;  // the caller is about to update the parameters
   return 0;
 }
 
@@ -1207,6 +1206,9 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
   // bf16 operand mirrors: refreshed here (never inside a captured graph) only when the fp32
   // masters changed behind our back - net_adamw writes them itself as part of the update
   if (n->params_dirty && pack_weights(n, s)) return -1;
+  // the caller is about to update the parameters; set BEFORE the step runs because a bucket
+  // callback may already apply the optimizer (net_adamw_range), whose last range clears it
+  n->params_dirty = true;
   static const bool graphs_on = getenv("VPD_GRAPH") == nullptr || getenv("VPD_GRAPH")[0] != '0';
   if (!graphs_on || n->prof.on)
     return net_train_step_body(n, x_nchw, x_stem, target, B, loss_sum, s);
@@ -1228,7 +1230,6 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
         n->bucket_fn(n->bucket_user, g->buckets[k].first, g->buckets[k].second);
     }
     count_launches(g->launches);
-    n->params_dirty = true;
     return 0;
   }
   if (g->seen < 2) {   // warm-up: plans, function attributes, side stream, uploads
@@ -1289,7 +1290,6 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
     if (k < g->buckets.size() && n->bucket_fn != nullptr)
       n->bucket_fn(n->bucket_user, g->buckets[k].first, g->buckets[k].second);
   }
-  n->params_dirty = true;
   return 0;
 }
 
@@ -1309,6 +1309,57 @@ int net_adamw(Net* n, float* exp_avg, float* exp_avg_sq, double lr, double b1, d
     return -1;
   if (pack_stem_weight_arena(n->params + n->secA + n->stem.w_off, n->w_stem_s2d, s)) return -1;
   n->params_dirty = false;
+  return 0;
+}
+
+// The same update restricted to the arena range [offset, offset + count) - one all-reduce
+// bucket (vpd_net_set_bucket_callback): the optimizer can then run bucket by bucket, on
+// another stream, while the backward pass of the earlier layers is still going (AdamW is
+// HBM-bound, the backward kernels tensor-bound). Ranges must start and end on tensor
+// boundaries of the arena (the buckets do). `finish` != 0 on the last range of a step.
+int net_adamw_range(Net* n, float* exp_avg, float* exp_avg_sq, double lr, double b1, double b2,
+                    double eps, double wd, int step, float grad_scale, long long offset,
+                    long long count, int finish, cudaStream_t s) {
+  VPD_REQUIRE(n->params != nullptr && n->grads != nullptr, "net_adamw_range: arenas not bound");
+  VPD_REQUIRE(offset >= 0 && count >= 0 && offset + count <= n->n_params && offset % 4 == 0 &&
+                  (count % 4 == 0 || offset + count == n->n_params),
+              "net_adamw_range: bad range [%lld, +%lld)", offset, count);
+  if (!n->mt_uploaded) {
+    VPD_CHECK_CUDA(cudaMemcpyAsync(n->mt_table_dev, n->mt_table_host.data(),
+                                   n->mt_table_host.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    n->mt_uploaded = true;
+  }
+  const long long hi = offset + count;
+  // tiles of the conv matrices inside the range (the table is in arena order)
+  int t0 = n->mt_blocks, t1 = n->mt_blocks;
+  for (int i = 0; i < n->mt_blocks; ++i) {
+    const long long a = n->secA + n->mt_table_host[5 * i];
+    if (a >= offset && t0 == n->mt_blocks) t0 = i;
+    if (a >= hi) {
+      t1 = i;
+      break;
+    }
+  }
+  if (t0 > t1) t0 = t1;
+  if (adamw_tiles(n->params + n->secA, n->grads + n->secA, exp_avg + n->secA,
+                  exp_avg_sq + n->secA, n->w_tap, n->wT_tap, n->mt_table_dev + 5 * t0, t1 - t0, lr,
+                  b1, b2, eps, wd, step, grad_scale, s))
+    return -1;
+  // the parts of the range outside the conv section (BN affine in front, fc + decoder behind)
+  const long long seg[2][2] = {{0, n->secA}, {n->secA + n->secA_len, n->n_params}};
+  for (int k = 0; k < 2; ++k) {
+    const long long lo = offset > seg[k][0] ? offset : seg[k][0];
+    const long long up = hi < seg[k][1] ? hi : seg[k][1];
+    if (up > lo &&
+        adamw_step(n->params + lo, n->grads + lo, exp_avg + lo, exp_avg_sq + lo, up - lo, lr, b1, b2,
+                   eps, wd, step, grad_scale, s))
+      return -1;
+  }
+  const long long stem_at = n->secA + n->stem.w_off;
+  if (stem_at >= offset && stem_at < hi &&
+      pack_stem_weight_arena(n->params + stem_at, n->w_stem_s2d, s))
+    return -1;
+  if (finish) n->params_dirty = false;
   return 0;
 }
 

@@ -24,6 +24,10 @@ int net_train_step(Net* n, const float* x_nchw, const void* x_stem, const float*
 int net_adamw(Net* n, float* exp_avg, float* exp_avg_sq, double lr, double b1, double b2,
               double eps, double wd, int step, float grad_scale, cudaStream_t s);
 
+int net_adamw_range(Net* n, float* exp_avg, float* exp_avg_sq, double lr, double b1, double b2,
+                    double eps, double wd, int step, float grad_scale, long long offset,
+                    long long count, int finish, cudaStream_t s);
+
 // introspection (implemented in net.cu)
 long long net_param_count(Net* n);
 long long net_buffer_count(Net* n);

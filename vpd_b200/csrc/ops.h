@@ -45,6 +45,11 @@ int adamw_step_mirrored(float* p, const float* g, float* m, float* v, long long 
                         double b2, double eps, double wd, int step, float grad_scale,
                         cudaStream_t stream);
 
+int adamw_tiles(float* p_conv, const float* g_conv, float* m_conv, float* v_conv,
+                __nv_bfloat16* w_tap, __nv_bfloat16* wT, const int* table, int tiles, double lr,
+                double b1, double b2, double eps, double wd, int step, float grad_scale,
+                cudaStream_t stream);
+
 int sgd_step(float* p, const float* g, float* buf, long long n, double lr, double momentum,
              double dampening, double wd, int nesterov, int first_step, float grad_scale,
              cudaStream_t stream);

@@ -40,7 +40,11 @@ class FusedAdamW:
     def step(self):
         enc = self.encoder
         m, v = self._state()
-        self.step_count += 1
+        state, self._bucketed = getattr(self, '_bucketed', None), None
+        if state == 'done':
+            return          # every bucket of this step went through step_range already
+        if state != 'open':
+            self.step_count += 1     # ('open': begin_bucketed counted the step, no bucket came)
         with torch.cuda.device(enc._dev):
             net = enc._net
             if net is not None and getattr(net, 'has_grads', False):
@@ -55,6 +59,23 @@ class FusedAdamW:
                            self.step_count, 1.0, stream_ptr(enc._dev))
                 if net is not None:
                     lib().call('vpd_net_params_changed', net.handle)
+
+    # ---- bucket-wise application (ModelTrainer's gradient-bucket hook) -------------------
+    def begin_bucketed(self):
+        """A train step is about to run whose gradient buckets will be handed to
+        `step_range` as they become final."""
+        self._state()
+        self.step_count += 1
+        self._bucketed = 'open'
+
+    def step_range(self, net, offset, count, finish, stream):
+        """AdamW for parameters [offset, offset + count) (one gradient bucket) on `stream`."""
+        m, v = self._state()
+        lib().call('vpd_net_adamw_range', net.handle, m, v, self.lr, self.betas[0], self.betas[1],
+                   self.eps, self.weight_decay, self.step_count, 1.0, offset, count, int(finish),
+                   stream.cuda_stream)
+        if finish:
+            self._bucketed = 'done'
 
     def zero_grad(self, set_to_none=False):
         pass    # every train step overwrites the whole gradient arena
@@ -127,6 +148,10 @@ class ModelTrainer:
         self._pending = []
         self._buckets_seen = []          # (offset, count) handed out by the last train step
         self.overlap_allreduce = os.environ.get('VPD_DP_OVERLAP', '1') != '0'
+        # AdamW bucket by bucket on the communication stream while the backward pass of the
+        # earlier layers still runs (HBM-bound optimizer under tensor-bound kernels)
+        self.bucket_adamw = os.environ.get('VPD_BUCKET_ADAMW', '1') != '0'
+        self._step_opt = None
         # data parallel: every replica starts from rank 0's parameters, BN running statistics
         # and counters (identical seeds are NOT assumed - an augmenting loader draws from the
         # same global generators the constructor does, and those must differ per rank)
@@ -134,8 +159,9 @@ class ModelTrainer:
 
     def _on_bucket(self, user, offset, count):
         """Called by the native step when grads[offset:offset+count] are enqueued."""
-        dist = _dist()
-        if dist is None or count <= 0:
+        dist = _dist() if self.overlap_allreduce else None
+        opt = self._step_opt
+        if count <= 0 or (dist is None and opt is None):
             return
         self._buckets_seen.append((int(offset), int(count)))
         enc = self.encoder
@@ -144,12 +170,19 @@ class ModelTrainer:
         ev.record(cur)
         self._comm_stream.wait_event(ev)
         with torch.cuda.stream(self._comm_stream):
-            work = dp.sum_bucket(enc._grads, offset, count, async_op=True)
-        self._pending.append(work)
+            if dist is not None:
+                work = dp.sum_bucket(enc._grads, offset, count, async_op=True)
+                if opt is not None and work is not None:
+                    work.wait()          # stream-side: the optimizer below follows the reduce
+                else:
+                    self._pending.append(work)
+            if opt is not None:
+                opt.step_range(enc._net, offset, count, finish=(offset == 0),
+                               stream=self._comm_stream)
 
     def _hook(self, net):
         """(Un)install the bucket callback on the bound native net."""
-        want = _dist() is not None and self.overlap_allreduce
+        want = (_dist() is not None and self.overlap_allreduce) or self._step_opt is not None
         key = (net.handle, want)
         if self._hooked != key:
             lib().call('vpd_net_set_bucket_callback', net.handle,
@@ -202,11 +235,13 @@ class ModelTrainer:
             enc._ensure_grads()
             self._buckets_seen = []
             net = enc._native(height, width, n)
+            self._arm_optimizer(optimizer, True)
             self._overlapped = self._hook(net)
             lib().call('vpd_net_train_step', net.handle, None, stem, tgt, n, self._loss,
                        stream_ptr(enc._dev))
             self._sync_grads()
             optimizer.step()
+            self._step_opt = None
 
     def dp_self_check(self, img, tgt, n, rtol=1e-4):
         """Data-parallel correctness of ONE step, judged bucket by bucket: the
@@ -222,6 +257,7 @@ class ModelTrainer:
         dist = _dist()
         enc = self.encoder
         H, W = img.shape[-2:]
+        self._step_opt = None                # gradients only: the optimizer must not run here
         loss_keep = self._loss.clone()
         with torch.cuda.device(enc._dev):
             enc._ensure_grads()
@@ -259,17 +295,26 @@ class ModelTrainer:
 
     def _sync_grads(self):
         dist = _dist()
-        if dist is None:
-            return
         if getattr(self, '_overlapped', False):
-            # buckets were launched from the callback; make the compute stream wait for them
+            # buckets (all-reduce and / or optimizer ranges) were launched from the callback on
+            # the communication stream: make the compute stream wait for them
             for work in self._pending:
                 if work is not None:
                     work.wait()
             self._pending = []
             torch.cuda.current_stream(self.encoder._dev).wait_stream(self._comm_stream)
-        else:
+        elif dist is not None:
             dp.sum_gradients(self.encoder._grads)
+
+    def _arm_optimizer(self, optimizer, train):
+        """Bucket-wise AdamW for this step? Only with the package's own optimizer; a data-
+        parallel run without the overlapped exchange reduces the whole arena after the step,
+        so the optimizer has to wait for that."""
+        ok = (train and self.bucket_adamw and isinstance(optimizer, FusedAdamW)
+              and (_dist() is None or self.overlap_allreduce))
+        self._step_opt = optimizer if ok else None
+        if ok:
+            optimizer.begin_bucketed()
 
     def _run_u8(self, raw, tgt, train):
         """One batch of raw uint8 crops (see `_stage`): K1 assembly straight into the bound
@@ -395,6 +440,7 @@ class ModelTrainer:
             nxt = self._stage(next(it, None), step_i % 2)   # overlap next copy with this step
             if ev is not None:
                 cur_stream.wait_event(ev)
+            self._arm_optimizer(optimizer, train)
             if isinstance(img, dict):                       # raw uint8 crops: K1 on the device
                 n = self._run_u8(img, emb, train)
             else:
@@ -414,6 +460,7 @@ class ModelTrainer:
                 self._sync_grads()
                 optimizer.step()
                 optimizer.zero_grad()
+                self._step_opt = None
             epoch_n += n
             if progress_cb is not None:
                 progress_cb(n)
