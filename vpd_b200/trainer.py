@@ -149,8 +149,12 @@ class ModelTrainer:
         self._buckets_seen = []          # (offset, count) handed out by the last train step
         self.overlap_allreduce = os.environ.get('VPD_DP_OVERLAP', '1') != '0'
         # AdamW bucket by bucket on the communication stream while the backward pass of the
-        # earlier layers still runs (HBM-bound optimizer under tensor-bound kernels)
-        self.bucket_adamw = os.environ.get('VPD_BUCKET_ADAMW', '1') != '0'
+        # earlier layers still runs (HBM-bound optimizer under tensor-bound kernels). Opt-in
+        # (VPD_BUCKET_ADAMW=1): parity-tested, but measured neutral - the step is SM- and
+        # power-bound, so the overlapped optimizer only displaces backward kernels (1 GPU: 3.375
+        # vs 3.405 ms at 2.5 % higher clocks; 2 GPUs: 3.502 vs 3.490 ms, e2e 140 k vs 145 k
+        # frames/s because of the extra host work per bucket)
+        self.bucket_adamw = os.environ.get('VPD_BUCKET_ADAMW', '0') != '0'
         self._step_opt = None
         # data parallel: every replica starts from rank 0's parameters, BN running statistics
         # and counters (identical seeds are NOT assumed - an augmenting loader draws from the
