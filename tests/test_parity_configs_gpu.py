@@ -356,22 +356,29 @@ def test_bucketwise_adamw_equals_whole_arena_adamw():
     torch.cuda.synchronize()
     for a, b in zip(whole, (m._params, mm, vv)):
         assert torch.equal(a, b)
-    # (2) through the trainer, both modes
-    out = []
-    for bucketed in (True, False):
+    # (2) through the trainer: ONE step from the same state in three runs - whole-arena twice
+    # (calibrates the run-to-run noise of the weight-gradient atomics, which AdamW's normalised
+    # first step turns into a +-lr flip wherever |g| is at the noise level) and bucket-wise once
+    def one_step(bucketed):
         m = _model(0)
         tr = ModelTrainer(m, True)
         tr.bucket_adamw = bucketed
         opt, _ = tr.get_optimizer(5e-4)
-        losses = [tr.epoch([batch, batch], optimizer=opt) for _ in range(3)]   # eager, eager, graphs
+        loss = tr.epoch([batch], optimizer=opt)
         torch.cuda.synchronize()
         if bucketed:
             assert len(tr._buckets_seen) == 4 and tr._buckets_seen[-1][0] == 0
-        out.append((losses, m._params.clone(), opt.step_count))
-    a, b = out
-    assert a[2] == b[2] == 6
-    # same trajectory: the first epoch agrees to the atomics' noise, which the quantised
-    # network then amplifies step by step (two runs of ONE mode drift apart the same way)
-    assert abs(a[0][0] - b[0][0]) <= 1e-5 * abs(b[0][0]), (a[0], b[0])
-    assert np.allclose(a[0], b[0], rtol=5e-3), (a[0], b[0])
-    assert ((a[1] - b[1]).norm() / b[1].norm()).item() <= 1e-3
+        mm, vv = opt._state()
+        return loss, m._params.clone(), mm.clone(), opt.step_count
+
+    la, pa, ma, sa = one_step(False)
+    lb, pb, mb, sb = one_step(False)
+    lc, pc, mc, sc = one_step(True)
+    assert la == lb == lc and sa == sb == sc == 1
+    frac = lambda x, y: ((x - y).abs() > 1e-6).float().mean().item()      # noqa: E731
+    noise, got = frac(pa, pb), frac(pa, pc)
+    _log(['bucket-wise AdamW: parameters differing by > 1e-6 after one step: {:.2e} '
+          '(two whole-arena runs: {:.2e})'.format(got, noise)])
+    assert got <= max(5 * noise, 1e-3), (got, noise)
+    # first moments = (1 - beta1) * g: the gradients the ranges consumed are the final ones
+    assert ((ma - mc).norm() / ma.norm()).item() <= 1e-4
