@@ -128,9 +128,10 @@ def test_stem_bn_pool_forward_and_backward(N, H, W):
     assert rel_err(nchw_f32(dy2), nchw_f32(dy)) < 1e-3
 
 
-@pytest.mark.parametrize('motion,D', [(1, 32), (0, 26)])
-def test_head_loss_forward_and_backward(motion, D):
-    B, HW, Fd, Hd = 7, 16, 512, 128
+@pytest.mark.parametrize('motion,D,B', [(1, 32, 7), (0, 26, 7), (1, 32, 300)])
+def test_head_loss_forward_and_backward(motion, D, B):
+    # B = 300: the weight-gradient kernel walks the frames in chunks of 128 (two full, one partial)
+    HW, Fd, Hd = 16, 512, 128
     T = 2 * D if motion else D
     g = torch.Generator().manual_seed(D)
     z = torch.randn((B, HW, Fd), generator=g).relu().to(torch.bfloat16).to(dev())

@@ -385,6 +385,17 @@ VPD_DEVINL void stg_v4(void* p, uint4 v) {
                "r"(v.w)
                : "memory");
 }
+VPD_DEVINL uint2 ldg_nc_v2(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
+}
+VPD_DEVINL void stg_v2(void* p, uint2 v) {
+  asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+VPD_DEVINL void stg_cs_v2(void* p, uint2 v) {  // streaming store (evict-first)
+  asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
 VPD_DEVINL void stg_cs_v4(void* p, uint4 v) {  // streaming store (evict-first)
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
                "r"(v.z), "r"(v.w)

@@ -163,73 +163,97 @@ int launch_bn_apply(const BnApplyParams& p, cudaStream_t s) {
 }
 
 // ---------------------------------------------- stem: BN + ReLU + maxpool 3x3/2
-__global__ void __launch_bounds__(kEwThreads) bn_pool_kernel(const PoolParams p) {
+// The kernel is bound by instruction issue (ncu: 64 % issue-active at 24 % of DRAM
+// throughput, 960 instructions per thread in the first version), so the inner loop is pared
+// down: 32-bit index arithmetic, the maximum is taken over the BN outputs BEFORE the ReLU
+// (max relu(a) = relu(max a): nine fmax fewer per channel), and the running maximum carries
+// its payload - the pre-BN bf16 value in the upper half, the window index in the lower - in ONE
+// register, so a new maximum costs two selects instead of three. The window index follows
+// torch's max_pool2d on the ReLU output: the first position that attains the maximum, which is
+// the first valid position when nothing in the window is positive.
+template <bool kInterior>
+VPD_DEVINL void pool_window(const __nv_bfloat16* __restrict__ y0, int rs, int C, int ho, int wo,
+                            const float (&sc)[8], const float (&sh)[8], float (&best)[8],
+                            uint32_t (&pay)[8]) {
+  // y0 -> window position (0, 0); rs = row stride in elements
+  uint4 win[9];
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const bool ok = kInterior || ((kh > 0 || ho > 0) && (kw > 0 || wo > 0));
+      win[kh * 3 + kw] = ok ? __ldg(reinterpret_cast<const uint4*>(y0 + kh * rs + kw * C))
+                            : make_uint4(0, 0, 0, 0);
+    }
+  const int kf = kInterior ? 0 : (ho == 0 ? 3 : 0) + (wo == 0 ? 1 : 0);   // first valid position
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    best[j] = -INFINITY;
+    pay[j] = 0u;
+  }
+  uint32_t first[8];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const bool ok = kInterior || ((k >= 3 || ho > 0) && (k % 3 > 0 || wo > 0));
+    const uint32_t w4[4] = {win[k].x, win[k].y, win[k].z, win[k].w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t fb = (j & 1) ? (w4[j >> 1] & 0xFFFF0000u) : (w4[j >> 1] << 16);
+      const float a = fmaf(__uint_as_float(fb), sc[j], sh[j]);
+      const bool up = ok && a > best[j];
+      best[j] = up ? a : best[j];
+      pay[j] = up ? (fb | static_cast<uint32_t>(k)) : pay[j];
+      if (kInterior ? k == 0 : k == kf) first[j] = fb | static_cast<uint32_t>(k);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (!(best[j] > 0.f)) {   // nothing positive: ReLU output 0 everywhere, first position wins
+      best[j] = 0.f;
+      pay[j] = first[j];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kEwThreads, 2) bn_pool_kernel(const PoolParams p) {
   pdl_trigger();
   pdl_wait();
   const int groups = p.C >> 3;
   const int Ho = p.H / 2, Wo = p.W / 2;
-  const long long total = (long long)p.N * Ho * Wo * groups;
-  // channel group is fixed per thread when the grid stride is a multiple of `groups`
-  const long long stride = (long long)gridDim.x * kEwThreads;
+  const unsigned npix = (unsigned)p.N * Ho * Wo;
   const int g = threadIdx.x % groups;
+  const unsigned ppc = kEwThreads / groups;      // pooled pixels per CTA and pass
   __shared__ __align__(16) float s_co[2 * 512];
   bn_stage_affine(p.bn, p.C, s_co, s_co + 512);
   __syncthreads();
   float sc[8], sh[8];
   load8(s_co + g * 8, sc);
   load8(s_co + 512 + g * 8, sh);
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < total; i += stride) {
-    long long pix = i / groups;
-    const int wo = (int)(pix % Wo);
-    pix /= Wo;
-    const int ho = (int)(pix % Ho);
-    const int n = (int)(pix / Ho);
-    float best[8], ysel[8];
-    int idx[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      best[j] = -INFINITY;
-      ysel[j] = 0.f;
-      idx[j] = 0;
-    }
-    uint4 win[9];
-    bool ok[9];
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int h = 2 * ho - 1 + kh;
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int w = 2 * wo - 1 + kw;
-        ok[kh * 3 + kw] = h >= 0 && h < p.H && w >= 0 && w < p.W;
-        if (ok[kh * 3 + kw])
-          win[kh * 3 + kw] = __ldg(reinterpret_cast<const uint4*>(
-              p.y + (((size_t)n * p.H + h) * p.W + w) * p.C + g * 8));
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      if (!ok[k]) continue;
-      float f[8];
-      unpack8(win[k], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float v = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
-        if (v > best[j]) {
-          best[j] = v;
-          ysel[j] = f[j];
-          idx[j] = k;
-        }
-      }
-    }
-    const size_t o = (((size_t)n * Ho + ho) * Wo + wo) * p.C + g * 8;
+  const int rs = p.W * p.C;
+  for (unsigned pix = blockIdx.x * ppc + threadIdx.x / groups; pix < npix; pix += gridDim.x * ppc) {
+    const unsigned t = pix / Wo;
+    const int wo = (int)(pix - t * Wo);
+    const unsigned n = t / Ho;
+    const int ho = (int)(t - n * Ho);
+    const __nv_bfloat16* y0 =
+        p.y + (((long long)n * p.H + 2 * ho - 1) * p.W + 2 * wo - 1) * p.C + g * 8;
+    float best[8];
+    uint32_t pay[8];
+    if (ho > 0 && wo > 0) pool_window<true>(y0, rs, p.C, ho, wo, sc, sh, best, pay);
+    else pool_window<false>(y0, rs, p.C, ho, wo, sc, sh, best, pay);
+    const size_t o = (size_t)pix * p.C + g * 8;
     stg_v4(p.z + o, pack8(best));
     if (p.argmax != nullptr) {
       uint2 a;
-      a.x = idx[0] | (idx[1] << 8) | (idx[2] << 16) | (idx[3] << 24);
-      a.y = idx[4] | (idx[5] << 8) | (idx[6] << 16) | (idx[7] << 24);
+      a.x = (pay[0] & 0xFFu) | ((pay[1] & 0xFFu) << 8) | ((pay[2] & 0xFFu) << 16) | (pay[3] << 24);
+      a.y = (pay[4] & 0xFFu) | ((pay[5] & 0xFFu) << 8) | ((pay[6] & 0xFFu) << 16) | (pay[7] << 24);
       *reinterpret_cast<uint2*>(p.argmax + o) = a;
     }
-    if (p.ysel != nullptr) stg_v4(p.ysel + o, pack8(ysel));   // bf16 in, bf16 out: exact
+    if (p.ysel != nullptr)   // bf16 in, bf16 out: exact
+      stg_v4(p.ysel + o, make_uint4((pay[0] >> 16) | (pay[1] & 0xFFFF0000u),
+                                    (pay[2] >> 16) | (pay[3] & 0xFFFF0000u),
+                                    (pay[4] >> 16) | (pay[5] & 0xFFFF0000u),
+                                    (pay[6] >> 16) | (pay[7] & 0xFFFF0000u)));
   }
   if (blockIdx.x == 0) bn_side_effects(p.bn, p.C);
 }
@@ -239,8 +263,9 @@ int launch_bn_pool(const PoolParams& p, cudaStream_t s) {
   VPD_REQUIRE(p.H % 2 == 0 && p.W % 2 == 0, "bn_pool: odd spatial dims");
   if (p.N == 0) return 0;
   const long long total = (long long)p.N * (p.H / 2) * (p.W / 2) * (p.C / 8);
+  VPD_REQUIRE(total < (1LL << 31), "bn_pool: tensor too large for 32-bit indexing");
   long long blocks = (total + kEwThreads - 1) / kEwThreads;
-  if (blocks > 148 * 2) blocks = 148 * 2;  // one resident wave (97 registers/thread)
+  if (blocks > 148 * 2) blocks = 148 * 2;  // one resident wave
   VPD_CHECK_CUDA(launch_kernel(bn_pool_kernel, dim3((int)blocks), dim3(kEwThreads), 0, s, p));
   VPD_LAUNCHED(1);
   return 0;

@@ -162,40 +162,57 @@ struct OuterParams {
   int stride;  // floats between consecutive frames in the workspace
 };
 
-// 8 lanes per weight element, each summing every 8th frame, then a 3-step shuffle
+// One CTA per 16 x 32 tile of one weight matrix: the two operand tiles of a chunk of frames
+// (dout[b][16], in[b][32]) are staged in shared memory with coalesced loads and every thread
+// accumulates two weight elements over the frames in frame order (a fixed, run-to-run
+// identical reduction). The first version gave 8 lanes to every weight element, each walking
+// every 8th frame straight from global memory: a warp instruction touched eight 16-byte
+// pieces of eight different rows, 57 us per step at batch 256 for 23 MFLOP.
+constexpr int kOwTileO = 16, kOwTileI = 32, kOwChunk = 128;
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const OuterParams p) {
   pdl_trigger();
   pdl_wait();
-  int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-  const int sub = threadIdx.x & 7;
-  int seg = -1, o = 0, i = 0;
-  for (int s = 0; s < p.nseg; ++s) {
-    const int n = p.seg[s].O * (p.seg[s].I + 1);  // +1 column for the bias
-    if (idx < n) {
-      seg = s;
-      o = idx / (p.seg[s].I + 1);
-      i = idx % (p.seg[s].I + 1);
-      break;
-    }
-    idx -= n;
+  __shared__ float s_do[kOwChunk][kOwTileO];
+  __shared__ float s_in[kOwChunk][kOwTileI];
+  int tile = blockIdx.x, seg = 0, tiles_i = 1;
+  for (; seg < p.nseg; ++seg) {
+    tiles_i = (p.seg[seg].I + kOwTileI - 1) / kOwTileI;
+    const int n = ((p.seg[seg].O + kOwTileO - 1) / kOwTileO) * tiles_i;
+    if (tile < n) break;
+    tile -= n;
   }
-  float acc = 0.f;
-  if (seg >= 0) {
-    const OuterSeg& g = p.seg[seg];
-    if (i < g.I) {
-      for (int b = sub; b < p.B; b += 8)
-        acc = fmaf(g.dout[(size_t)b * p.stride + o], g.in[(size_t)b * p.stride + i], acc);
-    } else {
-      for (int b = sub; b < p.B; b += 8) acc += g.dout[(size_t)b * p.stride + o];
+  if (seg >= p.nseg) return;
+  const OuterSeg g = p.seg[seg];
+  const int o0 = (tile / tiles_i) * kOwTileO, i0 = (tile % tiles_i) * kOwTileI;
+  const int to = threadIdx.x >> 4, ti = (threadIdx.x & 15) * 2;
+  float acc0 = 0.f, acc1 = 0.f, accb = 0.f;
+  for (int b0 = 0; b0 < p.B; b0 += kOwChunk) {
+    const int nb = min(kOwChunk, p.B - b0);
+    // dout tile: 16 columns x nb rows, in tile: 32 columns x nb rows (zero outside the matrix)
+    for (int e = threadIdx.x; e < kOwChunk * kOwTileO; e += 256) {
+      const int r = e / kOwTileO, c = e % kOwTileO;
+      s_do[r][c] = (r < nb && o0 + c < g.O) ? g.dout[(size_t)(b0 + r) * p.stride + o0 + c] : 0.f;
     }
+    for (int e = threadIdx.x; e < kOwChunk * kOwTileI; e += 256) {
+      const int r = e / kOwTileI, c = e % kOwTileI;
+      s_in[r][c] = (r < nb && i0 + c < g.I) ? g.in[(size_t)(b0 + r) * p.stride + i0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < kOwChunk; ++r) {
+      const float d = s_do[r][to];
+      const float2 x = *reinterpret_cast<const float2*>(&s_in[r][ti]);
+      acc0 = fmaf(d, x.x, acc0);
+      acc1 = fmaf(d, x.y, acc1);
+      accb += d;
+    }
+    __syncthreads();
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);  // all 32 lanes take part
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-  if (seg >= 0 && sub == 0) {
-    const OuterSeg& g = p.seg[seg];
-    if (i < g.I) g.dW[(size_t)o * g.I + i] = acc;
-    else g.db[o] = acc;
+  const int o = o0 + to;
+  if (o < g.O) {
+    if (i0 + ti < g.I) g.dW[(size_t)o * g.I + i0 + ti] = acc0;
+    if (i0 + ti + 1 < g.I) g.dW[(size_t)o * g.I + i0 + ti + 1] = acc1;
+    if (i0 == 0 && ti == 0) g.db[o] = accb;
   }
 }
 
@@ -228,8 +245,9 @@ int launch_head(const HeadParams& p, const HeadGrads* grads, cudaStream_t stream
     op.seg[n++] = OuterSeg{dO, h2, grads->w5, grads->b5, p.T, p.Hd};
   }
   op.nseg = n;
-  for (int i = 0; i < n; ++i) total += op.seg[i].O * (op.seg[i].I + 1);
-  VPD_CHECK_CUDA(launch_kernel(head_wgrad_kernel, dim3((total * 8 + 255) / 256), dim3(256), 0, stream, op));
+  for (int i = 0; i < n; ++i)
+    total += ((op.seg[i].O + kOwTileO - 1) / kOwTileO) * ((op.seg[i].I + kOwTileI - 1) / kOwTileI);
+  VPD_CHECK_CUDA(launch_kernel(head_wgrad_kernel, dim3(total), dim3(256), 0, stream, op));
   VPD_LAUNCHED(1);
   return 0;
 }
