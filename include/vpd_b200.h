@@ -158,11 +158,13 @@ VPD_API int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N
 /* Same as vpd_conv2d_dgrad (stride 1 or 2, no downsample branch) with the BatchNorm-
  * backward reduction of the consuming ReLU->BN stage folded into the epilogue: dx is
  * stored already masked, g = dx * 1[z > 0], and sums[0..Cin) += sum g,
- * sums[Cin..2Cin) += sum g * (y - mean) * rstd  (accumulated). */
+ * sums[Cin..2Cin) += sum g * (y - mean) * rstd  (accumulated). relu_mask = 1[z > 0] as one
+ * bit per element, uint8 [N][H][W][Cin/8], bit j of byte g = channel 8g + j (written by
+ * vpd_bn_act_fwd, or by vpd_relu_mask from a tensor z): the kernel reads 1/16 of z's bytes. */
 VPD_API int vpd_conv2d_dgrad_bnfused(const void* dy, const void* wT_tap, void* dx, int N, int H, int W,
                              int Cin, int Cout, int k, int stride, int pad, const void* residual,
-                             const void* z, const void* y, const float* mean, const float* rstd,
-                             vpd_stat_acc* sums, void* stream);
+                             const uint8_t* relu_mask, const void* y, const float* mean,
+                             const float* rstd, vpd_stat_acc* sums, void* stream);
 /* dw[k*k][Cout][Cin] (fp32, tap-major: the gradient arena's native conv layout)
  * += sum over pixels dy (x) x. ACCUMULATES into dw (zero it first). */
 VPD_API int vpd_conv2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Cin,
@@ -178,14 +180,18 @@ VPD_API int vpd_stem_conv_wgrad(const void* x_stem, const void* dy, float* dw, i
 /* train-mode BN (+ optional residual, itself optionally batch-normalised) + ReLU.
  * stats/res_stats: [2][C] per-channel (sum, sumsq) of y / res as produced by
  * vpd_conv2d_fwd; running buffers are updated (momentum .1), save_* receive batch
- * mean and 1/sqrt(var+eps). res_stats == NULL: residual added as is. */
+ * mean and 1/sqrt(var+eps). res_stats == NULL: residual added as is. relu_mask (may be
+ * NULL): uint8 [M][C/8] out, bit j of byte (row, g) = 1[z[row][8g + j] > 0] - what
+ * vpd_conv2d_dgrad_bnfused reads in the backward pass instead of z. */
 VPD_API int vpd_bn_act_fwd(const void* y, const void* res, void* z, int64_t M, int C, int relu,
                    const vpd_stat_acc* stats, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, int64_t* num_batches,
                    float* save_mean, float* save_rstd, const vpd_stat_acc* res_stats,
                    const float* res_gamma, const float* res_beta, float* res_running_mean,
                    float* res_running_var, int64_t* res_num_batches, float* res_save_mean,
-                   float* res_save_rstd, void* stream);
+                   float* res_save_rstd, uint8_t* relu_mask, void* stream);
+/* relu_mask of an existing bf16 tensor z [M][C] (same bit layout) */
+VPD_API int vpd_relu_mask(const void* z, uint8_t* mask, int64_t M, int C, void* stream);
 /* gradient of the stage above: g = dz * 1[z > 0] (z may be NULL: no mask); dy = BN
  * backward of g through (y, save_mean, save_rstd, gamma); optional second branch
  * (y2...) fed by the same g; dmask (may alias dz) receives g; sums = [2][C]
@@ -362,7 +368,9 @@ VPD_API int vpd_net_train_step(vpd_net* net, const float* x_nchw, const void* x_
 
 /* Test/debug access to the bf16 NHWC activation buffers left by the last step:
  * block -1 = stem (which 0: conv1 output, 4: pooled), block >= 0 = BasicBlock index
- * (which 0 conv1 out, 1 post-bn1-relu, 2 conv2 out, 3 downsample conv out, 4 block out) */
+ * (which 0 conv1 out, 1 post-bn1-relu, 2 conv2 out, 3 downsample conv out, 4 block out;
+ * 5 / 6: the ReLU bit masks of 1 / 4 left by a TRAINING step - uint8, numel = bytes, one bit
+ * per element as in vpd_bn_act_fwd) */
 VPD_API int vpd_net_activation(vpd_net* net, int block, int which, int B, void** ptr,
                        int64_t* numel);
 /* device-to-device copy on `stream` (lets tests snapshot the buffers above) */

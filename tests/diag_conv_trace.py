@@ -44,10 +44,13 @@ def main():
         elif alias == '2':    # both alias the conv input (already streamed by TMA)
             z = yf = x
 
+        zmask = torch.zeros((N, H, W, Cin // 8), device=dev, dtype=torch.uint8)
+        lib().call('vpd_relu_mask', z, zmask, N * H * W, Cin, s)
+
         def run():
             if dgrad:   # Cin == Cout in every case: x doubles as dy, y as dx
                 lib().call('vpd_conv2d_dgrad_bnfused', x, wT, y, N, H, W, Cin, Cout, 3, 1, 1, None,
-                           z, yf, mean, rstd, bs, s)
+                           zmask, yf, mean, rstd, bs, s)
             else:
                 lib().call('vpd_conv2d_fwd', x, w_tap, y, N, H, W, Cin, Cout, 3, 1, 1, None, None,
                            None, 0, st if use_stats else None, s)

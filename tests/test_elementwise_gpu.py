@@ -53,10 +53,18 @@ def test_bn_act_forward_and_backward(N, H, W, C, mode):
         extra = [_stats(nchw_f32(res)), g2.detach(), b2.detach(), rm2, rv2, nbt2, sm2, sr2]
     ref = ref.relu()
     z = torch.empty_like(y)
+    mask = torch.zeros((M, C // 8), device=dev(), dtype=torch.uint8)
     lib().call('vpd_bn_act_fwd', y, res, z, M, C, 1, _stats(nchw_f32(y)), gamma, beta, rm, rv, nbt,
-               sm, sr, *extra, stream_ptr())
+               sm, sr, *extra, mask, stream_ptr())
     got = nchw_f32(z)
     assert rel_err(got, ref.detach()) < 5e-3
+    # the ReLU mask the data-gradient kernels read instead of z: bit j of byte (row, g) is
+    # channel 8g + j of the STORED tensor; the stand-alone kernel gives the same bytes
+    bits = ((z.view(M, C // 8, 8).float() > 0).to(torch.int32) << torch.arange(8, device=dev())).sum(-1)
+    assert torch.equal(mask.to(torch.int32), bits)
+    mask2 = torch.zeros_like(mask)
+    lib().call('vpd_relu_mask', z, mask2, M, C, stream_ptr())
+    assert torch.equal(mask2, mask)
     # running statistics like nn.BatchNorm2d (momentum 0.1, unbiased variance)
     yv = nchw_f32(y)
     assert torch.allclose(rm, 0.9 * rm0 + 0.1 * yv.mean((0, 2, 3)), atol=1e-4)

@@ -398,8 +398,10 @@ def test_conv2d_dgrad_with_fused_bn_backward_reduction(case):
     rstd = (torch.rand(Cin, generator=g) + 0.5).to(dev())
     sums = acc_zeros((2, Cin), dev())
     dx = torch.full((N, H, W, Cin), float('nan'), device=dev(), dtype=torch.bfloat16)
+    zmask = torch.zeros((N, H, W, Cin // 8), device=dev(), dtype=torch.uint8)
+    lib().call('vpd_relu_mask', z, zmask, N * H * W, Cin, stream_ptr())
     lib().call('vpd_conv2d_dgrad_bnfused', dy, wT_tap, dx, N, H, W, Cin, Cout, k, stride, pad, res,
-               z, y, mean, rstd, sums, stream_ptr())
+               zmask, y, mean, rstd, sums, stream_ptr())
     ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w.to(torch.bfloat16).float().to(dev()),
                                      nchw_f32(dy), stride=stride, padding=pad) + nchw_f32(res)
     ref = ref * (nchw_f32(z) > 0)

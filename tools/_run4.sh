@@ -1,10 +1,12 @@
-timeout 600 python -m pytest tests/test_elementwise_gpu.py tests/test_student_gpu.py -x -q -m gpu 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_elementwise_gpu.py tests/test_ops_gpu.py tests/test_student_gpu.py tests/test_ops_b256_gpu.py -x -q -m gpu 2>&1 | tail -4
+echo "=== dgrad diag"; DIAG_MODE=dgrad timeout 120 python tests/diag_conv_trace.py 2>&1 | grep -E "^case"
+echo "=== fwd diag"; DIAG_MODE=fwd timeout 120 python tests/diag_conv_trace.py 2>&1 | grep -E "^case"
 B="timeout 300 python bench.py --steps 30 --warmup 5 --no-configs --no-e2e --no-cpu-baseline"
 $B > gpurun_out/r02w.json 2> gpurun_out/r02w.err
 timeout 20 python tools/benchsum.py < gpurun_out/r02w.json
 python - <<'PY'
 import json
 d=json.loads(open('gpurun_out/r02w.json').read().strip().splitlines()[-1])
-for fam in ['bn_relu_pool_fwd','bn_relu_pool_bwd','head_loss']:
+for fam in ['conv_fwd','conv_dgrad','bn_relu_pool_fwd','head_loss']:
     print(fam, d['kernels'][fam]['by_kernel_us_per_step'])
 PY

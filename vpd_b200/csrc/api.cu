@@ -216,12 +216,13 @@ int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N, int H,
 
 int vpd_conv2d_dgrad_bnfused(const void* dy, const void* wT_tap, void* dx, int N, int H, int W,
                              int Cin, int Cout, int k, int stride, int pad, const void* residual,
-                             const void* z, const void* y, const float* mean, const float* rstd,
-                             vpd_stat_acc* sums, void* stream) {
+                             const uint8_t* relu_mask, const void* y, const float* mean,
+                             const float* rstd, vpd_stat_acc* sums, void* stream) {
   ConvGeom g{N, H, W, Cin, Cout, k, stride, pad};
+  VPD_REQUIRE(relu_mask != nullptr && y != nullptr, "dgrad_bnfused: relu_mask and y are required");
   ConvBwdFuse f;
   f.nb = 1;
-  f.z = (const bf16*)z;
+  f.mask = relu_mask;
   f.y[0] = (const bf16*)y;
   f.mean[0] = mean;
   f.rstd[0] = rstd;
@@ -277,12 +278,13 @@ int vpd_bn_act_fwd(const void* y, const void* res, void* z, int64_t M, int C, in
                    float* save_mean, float* save_rstd, const vpd_stat_acc* res_stats,
                    const float* res_gamma, const float* res_beta, float* res_running_mean,
                    float* res_running_var, int64_t* res_num_batches, float* res_save_mean,
-                   float* res_save_rstd, void* stream) {
+                   float* res_save_rstd, uint8_t* relu_mask, void* stream) {
   BnApplyParams a;
   memset(&a, 0, sizeof(a));
   a.y = (const bf16*)y;
   a.res = (const bf16*)res;
   a.z = (bf16*)z;
+  a.mask = relu_mask;
   a.M = M;
   a.C = C;
   a.relu = relu;
@@ -293,6 +295,10 @@ int vpd_bn_act_fwd(const void* y, const void* res, void* z, int64_t M, int C, in
                        res_num_batches, res_save_mean, res_save_rstd, M);
   }
   return launch_bn_apply(a, (cudaStream_t)stream);
+}
+
+int vpd_relu_mask(const void* z, uint8_t* mask, int64_t M, int C, void* stream) {
+  return launch_relu_mask((const bf16*)z, mask, M, C, (cudaStream_t)stream);
 }
 
 int vpd_bn_act_bwd(const void* dz, const void* z, void* dmask, int64_t M, int C,

@@ -364,6 +364,18 @@ VPD_DEVINL uint32_t bf16x2_gt0_mask(uint32_t v) {
 }
 VPD_DEVINL float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
+// PTX prmt (default mode): selector nibble bits 0-2 pick a byte of {b, a}, bit 3 replicates
+// that byte's sign bit over the whole output byte (__byte_perm documents only the low 3 bits)
+VPD_DEVINL uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+VPD_DEVINL uint32_t ldg_nc_u8(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
 VPD_DEVINL uint4 ldg_nc_v4(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

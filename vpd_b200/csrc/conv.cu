@@ -239,22 +239,6 @@ int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
   L->a1 = L->a0;
   if (out_map(L, y, g.N, Ho, Wo, g.Cout, 1, 0, 0)) return -1;
   L->o2 = L->o;
-  // BatchNorm apply behind a grid barrier: every CTA must hold its only tile's accumulator
-  // in TMEM across the barrier, and all CTAs must be co-resident (grid <= SMs, 1 CTA/SM)
-  const int items = p.tiles_w * p.tiles_h * p.tiles_b * p.n_tiles;
-  // correct, measured neutral (3.87-3.93 vs 3.89 ms/step): opt-in; read at every planning so
-  // that a test can build one net with and one without it
-  const int fuse_on = env_int("VPD_FUSE_BNFWD", 0);
-  if (fuse_on && e.fuse_bn && e.stats != nullptr && L->cluster == 1 && items == L->grid &&
-      L->grid <= device_sm_count()) {
-    p.fuse_bn = 1;
-    p.fbn = e.bn;
-    p.fres = e.fuse_res;
-    p.frelu = e.fuse_relu;
-    p.fbar = e.fuse_bar;
-    L->fused_bn = 1;
-    if (act_map(&L->o2, e.fuse_z, g.N, Ho, Wo, g.Cout, 1, p)) return -1;
-  }
   return 0;
 }
 
@@ -350,7 +334,7 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
     p->bnb = 0;
     if (fuse == nullptr || fuse->nb == 0) return;
     p->bnb = fuse->nb;
-    p->bz = fuse->z + base;
+    p->bmask = fuse->mask + base / 8;
     for (int b = 0; b < fuse->nb; ++b) {
       p->by[b] = fuse->y[b] + base;
       p->bmean[b] = fuse->mean[b];
@@ -360,6 +344,9 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
   };
   const int Ho = g.Ho(), Wo = g.Wo();
   *count = 0;
+  VPD_REQUIRE(fuse == nullptr || fuse->nb == 0 || (long long)g.N * g.H * g.W * g.Cin < (1LL << 31),
+              "dgrad: the fused BN-backward reduction indexes with 32 bits (%lld elements)",
+              (long long)g.N * g.H * g.W * g.Cin);
   if (g.stride == 1) {
     VPD_REQUIRE(g.k == 2 * g.pad + 1, "dgrad: stride-1 conv must be 'same' padded");
     ConvLaunch* L = &Ls[0];
@@ -492,11 +479,8 @@ static int launch_bn_impl(const ConvLaunch& L, cudaStream_t stream) {
   return 0;
 }
 
-// the fused-BatchNorm variant is its own kernel (single-CTA mode only): keeping both epilogue
-// flavours in one kernel doubled its code and slowed every launch (instruction cache)
 template <int BN, int CS>
 static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
-  if (CS == 1 && L.fused_bn) return launch_bn_impl<BN, 1, true, 1>(L, stream);
   if (CS != 1) return launch_bn_impl<BN, CS, false, -1>(L, stream);   // opt-in pair mode: generic
   switch (conv_mode(L)) {
     case 1: return launch_bn_impl<BN, 1, false, 1>(L, stream);
@@ -554,17 +538,20 @@ void set_conv_trace(long long* dev_buf) { g_conv_trace = dev_buf; }
 
 int launch_conv(const ConvLaunch& L0, cudaStream_t stream) {
   if (L0.grid <= 0) return 0;
-  ConvLaunch traced;
-  if (g_conv_trace != nullptr) {
-    traced = L0;
-    traced.p.trace = g_conv_trace;
-  }
+  ConvLaunch traced = L0;
+  if (g_conv_trace != nullptr) traced.p.trace = g_conv_trace;
   static const int dbg_skip = env_int("VPD_DBG_SKIP", 0);
-  if (dbg_skip != 0) {
-    if (g_conv_trace == nullptr) traced = L0;
-    traced.p.dbg = dbg_skip;
+  if (dbg_skip != 0) traced.p.dbg = dbg_skip;
+  {   // divisors of the tile decode (decode_tile)
+    ConvParams& q = traced.p;
+    const int cs = L0.cluster > 1 ? L0.cluster : 1;
+    const int m_tiles = q.tiles_w * q.tiles_h * q.tiles_b;
+    q.fd_class = fd_make((uint32_t)(((m_tiles + cs - 1) / cs) * q.n_tiles));
+    q.fd_ntiles = fd_make((uint32_t)q.n_tiles);
+    q.fd_tw = fd_make((uint32_t)q.tiles_w);
+    q.fd_th = fd_make((uint32_t)q.tiles_h);
   }
-  const ConvLaunch& L = (g_conv_trace != nullptr || dbg_skip != 0) ? traced : L0;
+  const ConvLaunch& L = traced;
   if (L.halo == 1) return launch_halo<1>(L, stream);
   if (L.halo == 4) return launch_halo<1, 12>(L, stream);
   if (L.halo == 3) {

@@ -49,7 +49,7 @@ struct ConvEpilogue {
 // Fused BN-backward reduction for a dgrad launch (see ConvParams::bnb)
 struct ConvBwdFuse {
   int nb = 0;
-  const __nv_bfloat16* z = nullptr;
+  const uint8_t* mask = nullptr;   // 1[z > 0], one bit per element (BnApplyParams::mask)
   const __nv_bfloat16* y[2] = {nullptr, nullptr};
   const float* mean[2] = {nullptr, nullptr};
   const float* rstd[2] = {nullptr, nullptr};

@@ -45,6 +45,29 @@ constexpr int kConvThreads = kStatThread0 + kStatThreads;
 constexpr int kRegsCtl = 64, kRegsEpi = 152, kRegsStat = 232;
 constexpr int kWgradThreads = 192;
 
+// Division by a launch constant without the ~30-instruction signed-division sequence
+// (Granlund-Montgomery, unsigned n < 2^32): q = (t + ((n - t) >> s1)) >> s2, t = umulhi(m, n).
+// The per-tile coordinate decode sits on the critical path of the statistics warps: with four
+// runtime divisions it was 120 of their ~880 instructions per tile.
+struct FastDiv {
+  uint32_t d, m, s1, s2;
+};
+inline FastDiv fd_make(uint32_t d) {
+  FastDiv f;
+  if (d == 0) d = 1;
+  uint32_t l = 0;
+  while ((1ull << l) < d) ++l;
+  f.d = d;
+  f.m = static_cast<uint32_t>(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+  f.s1 = l < 1 ? l : 1;
+  f.s2 = l > 0 ? l - 1 : 0;
+  return f;
+}
+VPD_DEVINL uint32_t fd_div(const FastDiv& f, uint32_t n) {
+  const uint32_t t = __umulhi(f.m, n);
+  return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+
 struct ConvTap {
   int c0;       // offset added to the innermost (channel) coordinate
   int d1, d2, d3;  // offsets for the w, parity and h coordinates
@@ -88,7 +111,11 @@ struct ConvParams {
   // dz of a ReLU->BN stage; mask it with 1[z > 0] before it is stored (so `out`
   // holds g) and accumulate sum(g), sum(g * xhat_b) for up to two BN branches.
   int bnb;                            // 0 = off, else number of branches (1 or 2)
-  const __nv_bfloat16* bz;            // post-ReLU output of that stage (same addressing as out)
+  // 1[z > 0] of that stage's post-ReLU output as ONE BIT per element, written by the forward
+  // BatchNorm kernel: byte (pixel, g) covers channels 8g .. 8g+7 (element offset / 8 in out's
+  // addressing). Reading z itself cost as many bytes as the gradient tile: the stage-1 data
+  // gradients were bound by HBM traffic (dy + z + y in, g out)
+  const uint8_t* bmask;
   const __nv_bfloat16* by[2];         // its pre-BN conv outputs
   const float* bmean[2];              // [cout] saved batch mean
   const float* brstd[2];              // [cout] saved 1/sqrt(var+eps)
@@ -120,6 +147,9 @@ struct ConvParams {
   // without waiting for slab slots and the statistics warps follow one slab behind (with the
   // one- or two-slot ring TMEM drain, statistics and store of a slab ran back to back)
   int single_tile;
+  // decode_tile's divisors (launch_conv fills them): work items per output class, channel
+  // blocks, pixel tiles per row / column
+  FastDiv fd_class, fd_ntiles, fd_tw, fd_th;
   int dbg;  // diagnostics (VPD_DBG_SKIP): bit0 skip the A loads, bit1 skip the B loads, bit2 skip the epilogue body
 };
 struct TileCoord {
@@ -129,16 +159,18 @@ struct TileCoord {
 template <int CS>
 VPD_DEVINL TileCoord decode_tile(const ConvParams& p, int tile, int rank) {
   TileCoord t;
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
-  const int per_class = ((m_tiles + CS - 1) / CS) * p.n_tiles;
-  t.cls = p.num_classes > 1 ? tile / per_class : 0;
-  const int inner = tile - t.cls * per_class;
-  t.n_tile = inner % p.n_tiles;
-  int mt = (inner / p.n_tiles) * CS + rank;
-  t.w0 = (mt % p.tiles_w) * p.tw;
-  mt /= p.tiles_w;
-  t.h0 = (mt % p.tiles_h) * p.th;
-  t.b0 = (mt / p.tiles_h) * p.tn;
+  const uint32_t u = static_cast<uint32_t>(tile);
+  const uint32_t c = p.num_classes > 1 ? fd_div(p.fd_class, u) : 0u;
+  const uint32_t inner = u - c * p.fd_class.d;
+  const uint32_t q = fd_div(p.fd_ntiles, inner);
+  const uint32_t mt = q * CS + rank;
+  const uint32_t r1 = fd_div(p.fd_tw, mt);
+  const uint32_t r2 = fd_div(p.fd_th, r1);
+  t.cls = static_cast<int>(c);
+  t.n_tile = static_cast<int>(inner - q * p.fd_ntiles.d);
+  t.w0 = static_cast<int>(mt - r1 * p.fd_tw.d) * p.tw;
+  t.h0 = static_cast<int>(r1 - r2 * p.fd_th.d) * p.th;
+  t.b0 = static_cast<int>(r2) * p.tn;
   return t;
 }
 // one thread per CTA: this CTA's slice of the next convolution's weights -> L2
@@ -206,6 +238,10 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
   const int r = q * 32 + lane;  // row of the 128-row tile
   const uint32_t row_addr = smem_u32(slabs) + r * 128;
   const uint32_t rsw = static_cast<uint32_t>(r & 7);
+  // position of this row inside a tile (tile extents are powers of two)
+  const int ltw = __ffs(p.tw) - 1, lth = __ffs(p.th) - 1;
+  const int r_w = r & (p.tw - 1), r_h = (r >> ltw) & (p.th - 1), r_n = r >> (ltw + lth);
+  const long long r_off = r_n * p.out_sn + r_h * p.out_sh + r_w * p.out_sw;
   int as = 0;
   uint32_t aphase = 0;
   int slot = 0;
@@ -213,12 +249,9 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
   for (int tile = first_item; tile < total_tiles; tile += item_stride) {
     const TileCoord tc = decode_tile<CS>(p, tile, rank);
     const int n_tile = tc.n_tile;
-    const int w = tc.w0 + r % p.tw;
-    const int h = tc.h0 + (r / p.tw) % p.th;
-    const int n = tc.b0 + r / (p.tw * p.th);
-    const bool valid = (n < p.batch) && (h < p.out_h) && (w < p.out_w);
-    const long long off =
-        p.cls[tc.cls].base + n * p.out_sn + h * p.out_sh + w * p.out_sw + n_tile * BLOCK_N;
+    const bool valid = (tc.b0 + r_n < p.batch) && (tc.h0 + r_h < p.out_h) && (tc.w0 + r_w < p.out_w);
+    const long long off = p.cls[tc.cls].base + tc.b0 * p.out_sn + tc.h0 * p.out_sh +
+                          tc.w0 * p.out_sw + r_off + n_tile * BLOCK_N;
 
     mbar_wait(&tfull_bar[as], aphase);
     if (tile == first_item && threadIdx.x == kEpiThread0) trace_mark(p, 5);
@@ -334,7 +367,8 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 // Statistics / store warps (warps 6..9, threads 192..319). For every staged slab:
 //   forward train (p.stats):  sum y, sum y^2 per channel  -> BatchNorm batch statistics
 //   dgrad (p.bnb):  the slab holds dz of a ReLU->BN stage; mask it in place with 1[z > 0]
-//                   (so the stored tensor is g) and accumulate sum g and sum g*(y - mean)
+//                   (one bit per element, ConvParams::bmask; so the stored tensor is g) and
+//                   accumulate sum g and sum g*(y - mean)
 //                   for up to two BN branches               -> fused BN-backward reduction
 // always on the stored (bf16-rounded) values; then ONE thread issues the slab's TMA tile
 // store. A lane owns eight consecutive channels and the four row groups of a warp
@@ -426,14 +460,17 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
         stat_add(&p.stats[c], static_cast<double>(s_sum[i]));
         stat_add(&p.stats[p.cout + c], static_cast<double>(s_sq[i]));
       } else {
-        // sum g * xhat = rstd * sum g * (y - mean)
-        stat_add(&p.bsums[0][c], static_cast<double>(s_sum[i]));
+        // sum g * xhat = rstd * (sum g * y - mean * sum g)
+        const double sg = static_cast<double>(s_sum[i]);
+        stat_add(&p.bsums[0][c], sg);
         stat_add(&p.bsums[0][p.cout + c],
-                 static_cast<double>(s_sq[i]) * static_cast<double>(__ldg(p.brstd[0] + c)));
+                 (static_cast<double>(s_sq[i]) - static_cast<double>(__ldg(p.bmean[0] + c)) * sg) *
+                     static_cast<double>(__ldg(p.brstd[0] + c)));
         if (nbr > 1) {
-          stat_add(&p.bsums[1][c], static_cast<double>(s_sum[i]));
+          stat_add(&p.bsums[1][c], sg);
           stat_add(&p.bsums[1][p.cout + c],
-                   static_cast<double>(s_x2[i]) * static_cast<double>(__ldg(p.brstd[1] + c)));
+                   (static_cast<double>(s_x2[i]) - static_cast<double>(__ldg(p.bmean[1] + c)) * sg) *
+                       static_cast<double>(__ldg(p.brstd[1] + c)));
         }
       }
       s_sum[i] = 0.f;
@@ -443,21 +480,22 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
     asm volatile("bar.sync 2, %0;" ::"n"(kStatThreads) : "memory");
   };
 
-  // ---- prefetched operands of the fused BN backward: this warp's 32 rows of z, y0 (, y1)
-  // element offset of row i of this lane inside a tile (tile-invariant)
-  int rel[8];
+  // ---- prefetched operands of the fused BN backward: this warp's 32 rows of the mask, y0 (, y1).
+  // All offsets are 32-bit element counts (the planner rejects tensors of 2^31 elements or more)
+  const int sn = static_cast<int>(p.out_sn), sh = static_cast<int>(p.out_sh),
+            sw_ = static_cast<int>(p.out_sw);
+  int rel[8];   // element offset of row i of this lane inside a tile (tile-invariant)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int r = sw * 32 + i * 4 + rsub;
-    rel[i] = static_cast<int>((r >> (ltw + lth)) * p.out_sn + ((r >> ltw) & (p.th - 1)) * p.out_sh +
-                              (r & (p.tw - 1)) * p.out_sw);
+    rel[i] = (r >> (ltw + lth)) * sn + ((r >> ltw) & (p.th - 1)) * sh + (r & (p.tw - 1)) * sw_ + cg * 8;
   }
-  uint4 zz[8], y0[8], y1[8];
-  float m0[8], m1[8];
+  uint32_t mb[8];        // mask bytes of this lane's eight rows
+  uint4 y0[8], y1[8];
   int cls = 0;  // output class of the tile the cursor is on
   auto issue_loads = [&](int n_tile, int w0, int h0, int b0, int j) {
-    const int ch = n_tile * BLOCK_N + j * 64 + cg * 8;
-    const long long base = p.cls[cls].base + b0 * p.out_sn + h0 * p.out_sh + w0 * p.out_sw + ch;
+    const int cbase = static_cast<int>(p.cls[cls].base) + n_tile * BLOCK_N + j * 64;
+    const int base = cbase + b0 * sn + h0 * sh + w0 * sw_;
     const bool full = (b0 + p.tn <= p.batch) && (h0 + p.th <= p.out_h) && (w0 + p.tw <= p.out_w);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -468,20 +506,10 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
              (w0 + (r & (p.tw - 1)) < p.out_w);
       }
       // rows outside the tensor hold g = 0 in the slab: any finite operand will do
-      const long long off = ok ? base + rel[i] : p.cls[cls].base + ch;
-      zz[i] = ldg_nc_v4(p.bz + off);
+      const uint32_t off = static_cast<uint32_t>(ok ? base + rel[i] : cbase + cg * 8);
+      mb[i] = ldg_nc_u8(p.bmask + (off >> 3));
       y0[i] = ldg_nc_v4(p.by[0] + off);
       if (nbr > 1) y1[i] = ldg_nc_v4(p.by[1] + off);
-    }
-    const float4 ma = __ldg(reinterpret_cast<const float4*>(p.bmean[0] + ch));
-    const float4 mb = __ldg(reinterpret_cast<const float4*>(p.bmean[0] + ch + 4));
-    m0[0] = ma.x, m0[1] = ma.y, m0[2] = ma.z, m0[3] = ma.w;
-    m0[4] = mb.x, m0[5] = mb.y, m0[6] = mb.z, m0[7] = mb.w;
-    if (nbr > 1) {
-      const float4 mc = __ldg(reinterpret_cast<const float4*>(p.bmean[1] + ch));
-      const float4 md = __ldg(reinterpret_cast<const float4*>(p.bmean[1] + ch + 4));
-      m1[0] = mc.x, m1[1] = mc.y, m1[2] = mc.z, m1[3] = mc.w;
-      m1[4] = md.x, m1[5] = md.y, m1[6] = md.z, m1[7] = md.w;
     }
   };
   auto tile_coords = [&](int tile, int& n_tile, int& w0, int& h0, int& b0) {
@@ -543,20 +571,26 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         uint32_t gw[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
-        const uint32_t zw[4] = {zz[i].x, zz[i].y, zz[i].z, zz[i].w};
+        // bits 0-3 / 4-7 of the mask byte -> the sign bits of four bytes (no carries: the
+        // partial products of the multiplier do not overlap), then byte-wise sign replication
+        const uint32_t s03 = ((mb[i] & 0xFu) * 0x10204080u) & 0x80808080u;
+        const uint32_t s47 = ((mb[i] >> 4) * 0x10204080u) & 0x80808080u;
+        const uint32_t zw[4] = {prmt(s03, 0u, 0x9988u), prmt(s03, 0u, 0xBBAAu),
+                                prmt(s47, 0u, 0x9988u), prmt(s47, 0u, 0xBBAAu)};
         const uint32_t yw[4] = {y0[i].x, y0[i].y, y0[i].z, y0[i].w};
         const uint32_t y1w[4] = {y1[i].x, y1[i].y, y1[i].z, y1[i].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          gw[k] &= bf16x2_gt0_mask(zw[k]);  // g = dz * 1[z > 0]
+          gw[k] &= zw[k];  // g = dz * 1[z > 0]
           const float lo = bf16_lo(gw[k]), hi = bf16_hi(gw[k]);
           a0[2 * k] += lo;
           a0[2 * k + 1] += hi;
-          a1[2 * k] = fmaf(lo, bf16_lo(yw[k]) - m0[2 * k], a1[2 * k]);
-          a1[2 * k + 1] = fmaf(hi, bf16_hi(yw[k]) - m0[2 * k + 1], a1[2 * k + 1]);
+          // sum g*y here, sum g*(y - mean) = sum g*y - mean * sum g when the CTA's sums leave
+          a1[2 * k] = fmaf(lo, bf16_lo(yw[k]), a1[2 * k]);
+          a1[2 * k + 1] = fmaf(hi, bf16_hi(yw[k]), a1[2 * k + 1]);
           if (nbr > 1) {
-            a2[2 * k] = fmaf(lo, bf16_lo(y1w[k]) - m1[2 * k], a2[2 * k]);
-            a2[2 * k + 1] = fmaf(hi, bf16_hi(y1w[k]) - m1[2 * k + 1], a2[2 * k + 1]);
+            a2[2 * k] = fmaf(lo, bf16_lo(y1w[k]), a2[2 * k]);
+            a2[2 * k + 1] = fmaf(hi, bf16_hi(y1w[k]), a2[2 * k + 1]);
           }
         }
         g[i] = make_uint4(gw[0], gw[1], gw[2], gw[3]);

@@ -33,6 +33,17 @@ VPD_DEVINL uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
                     pack_bf16x2(f[6], f[7]));
 }
+// bit j = 1[element j of the packed bf16 vector > 0] (the stored, rounded values decide)
+VPD_DEVINL uint32_t gt0_bits(const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  uint32_t b = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t m = bf16x2_gt0_mask(w[k]);
+    b |= ((m & 1u) << (2 * k)) | ((m >> 31) << (2 * k + 1));
+  }
+  return b;
+}
 
 // Block 0: persist batch statistics and update the running buffers like
 // nn.BatchNorm2d (momentum 0.1, unbiased variance for the running estimate).
@@ -124,7 +135,9 @@ __global__ void __launch_bounds__(kEwThreads, RES == 0 ? 4 : 3) bn_apply_kernel(
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
-      stg_v4(p.z + off, pack8(f));
+      const uint4 zv = pack8(f);
+      stg_v4(p.z + off, zv);
+      if (p.mask != nullptr) p.mask[(size_t)r * groups + g] = static_cast<uint8_t>(gt0_bits(zv));
     }
   }
   // every block has consumed the statistics above before block 0 may touch
@@ -158,6 +171,23 @@ int launch_bn_apply(const BnApplyParams& p, cudaStream_t s) {
     VPD_CHECK_CUDA(launch_kernel(bn_apply_kernel<1>, dim3(ew_grid(vectors, 4, 3)), dim3(kEwThreads), 0, s, p));
   else
     VPD_CHECK_CUDA(launch_kernel(bn_apply_kernel<2>, dim3(ew_grid(vectors, 4, 3)), dim3(kEwThreads), 0, s, p));
+  VPD_LAUNCHED(1);
+  return 0;
+}
+
+__global__ void __launch_bounds__(kEwThreads) relu_mask_kernel(const __nv_bfloat16* __restrict__ z,
+                                                               uint8_t* __restrict__ mask, long long vectors) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < vectors;
+       i += (long long)gridDim.x * kEwThreads)
+    mask[i] = static_cast<uint8_t>(gt0_bits(ldg_nc_v4(z + i * 8)));
+}
+int launch_relu_mask(const __nv_bfloat16* z, uint8_t* mask, long long M, int C, cudaStream_t s) {
+  VPD_REQUIRE(C % 8 == 0, "relu_mask: C=%d must be a multiple of 8", C);
+  const long long vectors = M * (C / 8);
+  if (vectors == 0) return 0;
+  VPD_CHECK_CUDA(launch_kernel(relu_mask_kernel, dim3(ew_grid(vectors, 4, 8)), dim3(kEwThreads), 0, s, z, mask, vectors));
   VPD_LAUNCHED(1);
   return 0;
 }

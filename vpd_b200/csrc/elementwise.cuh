@@ -75,6 +75,9 @@ struct BnApplyParams {
   const __nv_bfloat16* y;    // [M][C] conv output (pre-BN)
   const __nv_bfloat16* res;  // [M][C] residual input or null
   __nv_bfloat16* z;          // [M][C] out
+  uint8_t* mask;             // [M][C/8] out or null: bit j of byte (row, g) = 1[z[row][8g + j] > 0],
+                             // what the fused BN-backward reduction of the data-gradient kernels
+                             // reads instead of z (1/16 of its bytes)
   long long M;
   int C;
   int relu;
@@ -129,6 +132,8 @@ struct StemBwdParams {       // maxpool + ReLU + BN backward of the stem
 };
 
 int launch_bn_apply(const BnApplyParams& p, cudaStream_t s);
+// mask[row][g] bit j = 1[z[row][8g + j] > 0] for a bf16 tensor produced elsewhere
+int launch_relu_mask(const __nv_bfloat16* z, uint8_t* mask, long long M, int C, cudaStream_t s);
 int launch_channel_stats(const __nv_bfloat16* y, long long M, int C, StatAcc* stats, cudaStream_t s);
 int launch_bn_pool(const PoolParams& p, cudaStream_t s);
 int launch_bn_bwd(const BnBwdParams& p, cudaStream_t s);    // reduce + apply

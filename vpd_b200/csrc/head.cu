@@ -162,13 +162,14 @@ struct OuterParams {
   int stride;  // floats between consecutive frames in the workspace
 };
 
-// One CTA per 16 x 32 tile of one weight matrix: the two operand tiles of a chunk of frames
-// (dout[b][16], in[b][32]) are staged in shared memory with coalesced loads and every thread
-// accumulates two weight elements over the frames in frame order (a fixed, run-to-run
-// identical reduction). The first version gave 8 lanes to every weight element, each walking
-// every 8th frame straight from global memory: a warp instruction touched eight 16-byte
-// pieces of eight different rows, 57 us per step at batch 256 for 23 MFLOP.
-constexpr int kOwTileO = 16, kOwTileI = 32, kOwChunk = 128;
+// One CTA per 8 x 32 tile of one weight matrix (176 CTAs for the default head): the two
+// operand tiles of up to 256 frames (dout[b][8], in[b][32]) are staged in shared memory with
+// coalesced loads, all in flight at once, and every thread accumulates ONE weight element
+// over the frames in frame order (a fixed, run-to-run identical reduction). The first version
+// gave 8 lanes to every weight element, each walking every 8th frame straight from global
+// memory: a warp instruction touched eight 16-byte pieces of eight different rows, 57 us per
+// step at batch 256 for 23 MFLOP.
+constexpr int kOwTileO = 8, kOwTileI = 32, kOwChunk = 256;
 __global__ void __launch_bounds__(256) head_wgrad_kernel(const OuterParams p) {
   pdl_trigger();
   pdl_wait();
@@ -184,34 +185,33 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const OuterParams p) {
   if (seg >= p.nseg) return;
   const OuterSeg g = p.seg[seg];
   const int o0 = (tile / tiles_i) * kOwTileO, i0 = (tile % tiles_i) * kOwTileI;
-  const int to = threadIdx.x >> 4, ti = (threadIdx.x & 15) * 2;
-  float acc0 = 0.f, acc1 = 0.f, accb = 0.f;
+  const int to = threadIdx.x >> 5, ti = threadIdx.x & 31;
+  float acc = 0.f, accb = 0.f;
   for (int b0 = 0; b0 < p.B; b0 += kOwChunk) {
     const int nb = min(kOwChunk, p.B - b0);
-    // dout tile: 16 columns x nb rows, in tile: 32 columns x nb rows (zero outside the matrix)
+    // dout tile: 8 columns x nb rows, in tile: 32 columns x nb rows (zero outside the matrix)
+#pragma unroll
     for (int e = threadIdx.x; e < kOwChunk * kOwTileO; e += 256) {
       const int r = e / kOwTileO, c = e % kOwTileO;
-      s_do[r][c] = (r < nb && o0 + c < g.O) ? g.dout[(size_t)(b0 + r) * p.stride + o0 + c] : 0.f;
+      s_do[r][c] = (r < nb && o0 + c < g.O) ? __ldg(g.dout + (size_t)(b0 + r) * p.stride + o0 + c) : 0.f;
     }
+#pragma unroll 8
     for (int e = threadIdx.x; e < kOwChunk * kOwTileI; e += 256) {
       const int r = e / kOwTileI, c = e % kOwTileI;
-      s_in[r][c] = (r < nb && i0 + c < g.I) ? g.in[(size_t)(b0 + r) * p.stride + i0 + c] : 0.f;
+      s_in[r][c] = (r < nb && i0 + c < g.I) ? __ldg(g.in + (size_t)(b0 + r) * p.stride + i0 + c) : 0.f;
     }
     __syncthreads();
 #pragma unroll 8
     for (int r = 0; r < kOwChunk; ++r) {
       const float d = s_do[r][to];
-      const float2 x = *reinterpret_cast<const float2*>(&s_in[r][ti]);
-      acc0 = fmaf(d, x.x, acc0);
-      acc1 = fmaf(d, x.y, acc1);
+      acc = fmaf(d, s_in[r][ti], acc);
       accb += d;
     }
     __syncthreads();
   }
   const int o = o0 + to;
   if (o < g.O) {
-    if (i0 + ti < g.I) g.dW[(size_t)o * g.I + i0 + ti] = acc0;
-    if (i0 + ti + 1 < g.I) g.dW[(size_t)o * g.I + i0 + ti + 1] = acc1;
+    if (i0 + ti < g.I) g.dW[(size_t)o * g.I + i0 + ti] = acc;
     if (i0 == 0 && ti == 0) g.db[o] = accb;
   }
 }

@@ -50,6 +50,7 @@ struct BlockDesc {
   bool has_ds;
   // workspace activations (bf16 NHWC)
   bf16 *y1, *z1, *y2, *yds, *zout;
+  uint8_t *m1, *mout;   // ReLU masks of z1 / zout, one bit per element (training)
   // per-block gradients wrt the conv outputs (dy2, dy1, dy_ds): not shared between blocks, so
   // the weight-gradient kernels may read them long after the backward chain has moved on
   bf16 *gB, *gC, *gD;
@@ -514,6 +515,8 @@ static long long carve(Net* n, uint8_t* base) {
     bd.y2 = c.take<bf16>(sz);
     bd.yds = bd.has_ds ? c.take<bf16>(sz) : nullptr;
     bd.zout = c.take<bf16>(sz);
+    bd.m1 = c.take<uint8_t>(sz / 8);
+    bd.mout = c.take<uint8_t>(sz / 8);
     bd.gB = c.take<bf16>(sz);
     bd.gC = c.take<bf16>(sz);
     bd.gD = bd.has_ds ? c.take<bf16>(sz) : nullptr;
@@ -694,25 +697,7 @@ static Plan* get_plan(Net* n, int B) {
   for (size_t i = 0; i < nb && ok; ++i) {
     BlockDesc& bd = n->blocks[i];
     const ConvGeom g1 = geom(bd.c1, B), g2 = geom(bd.c2, B);
-    // training convs: where every CTA gets a single tile (the deep, small layers) the
-    // BatchNorm apply rides in the same launch (ConvEpilogue::fuse_bn)
-    const long long Mout = (long long)B * bd.c2.Hin * bd.c2.Win;
     ConvEpilogue e1 = tr(bd.b1), e2 = tr(bd.b2);
-    if (e1.stats != nullptr) {
-      e1.fuse_bn = true;
-      e1.bn = bn_layer(n, bd.b1, true, Mout);
-      e1.fuse_z = bd.z1;
-      e1.fuse_relu = 1;
-      e1.fuse_bar = n->bn_bar + bd.b1.idx;
-    }
-    if (e2.stats != nullptr && !bd.has_ds) {
-      e2.fuse_bn = true;
-      e2.bn = bn_layer(n, bd.b2, true, Mout);
-      e2.fuse_z = bd.zout;
-      e2.fuse_res = zin;
-      e2.fuse_relu = 1;
-      e2.fuse_bar = n->bn_bar + bd.b2.idx;
-    }
     ok &= !plan_conv_fwd(&P->c1_train[i], g1, zin, wt + bd.c1.w_off, bd.y1, e1);
     ok &= !plan_conv_fwd(&P->c2_train[i], g2, bd.z1, wt + bd.c2.w_off, bd.y2, e2);
     ok &= !plan_conv_fwd(&P->c1_eval[i], g1, zin, wt + bd.c1.w_off, bd.z1, ev(bd.b1, nullptr, 1));
@@ -740,7 +725,7 @@ static Plan* get_plan(Net* n, int B) {
       ConvBwdFuse f2;
       if (fuse_on) {
         f2.nb = 1;
-        f2.z = bd.z1;
+        f2.mask = bd.m1;
         bn_fuse(&f2, 0, bd.b1, bd.y1);
       }
       ok &= !plan_conv_dgrad(tmp, &cnt, g2, bd.gB, wT + bd.c2.w_off, bd.gC, nullptr, nullptr,
@@ -754,7 +739,7 @@ static Plan* get_plan(Net* n, int B) {
       if (fuse_on && i > 0) {
         BlockDesc& pb = n->blocks[i - 1];
         f1.nb = pb.has_ds ? 2 : 1;
-        f1.z = pb.zout;
+        f1.mask = pb.mout;
         bn_fuse(&f1, 0, pb.b2, pb.y2);
         if (pb.has_ds) bn_fuse(&f1, 1, pb.bds, pb.yds);
       }
@@ -1016,11 +1001,12 @@ static int train_forward_body(Net* n, Plan* P, int B, cudaStream_t s) {
     memset(&a, 0, sizeof(a));
     a.y = bd.y1;
     a.z = bd.z1;
+    a.mask = n->grads ? bd.m1 : nullptr;
     a.M = M;
     a.C = bd.c1.Cout;
     a.relu = 1;
     a.bn = bn_layer(n, bd.b1, true, M);
-    if (!P->c1_train[i].fused_bn) PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
+    PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
     PROF(kConvFwd, bd.stage, launch_conv(P->c2_train[i], s));
     if (split)
       PROF(kEwFwd, bd.stage, launch_channel_stats(bd.y2, M, 64, n->stats + 2 * bd.b2.ch_off, s));
@@ -1028,6 +1014,7 @@ static int train_forward_body(Net* n, Plan* P, int B, cudaStream_t s) {
     memset(&a, 0, sizeof(a));
     a.y = bd.y2;
     a.z = bd.zout;
+    a.mask = n->grads ? bd.mout : nullptr;
     a.M = M;
     a.C = bd.c2.Cout;
     a.relu = 1;
@@ -1039,7 +1026,7 @@ static int train_forward_body(Net* n, Plan* P, int B, cudaStream_t s) {
     } else {
       a.res = zin;
     }
-    if (!P->c2_train[i].fused_bn) PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
+    PROF(kEwFwd, bd.stage, launch_bn_apply(a, s));
     zin = bd.zout;
   }
   return 0;
@@ -1365,7 +1352,8 @@ int net_adamw_range(Net* n, float* exp_avg, float* exp_avg_sq, double lr, double
 
 // Debug/test access to the activation buffers of the last step.
 // block = -1: stem (which 0 = conv output y, 4 = pooled z); block >= 0: which
-// 0 y1, 1 z1, 2 y2, 3 y_ds, 4 z_out.
+// 0 y1, 1 z1, 2 y2, 3 y_ds, 4 z_out (bf16, numel elements); 5 / 6: the ReLU bit masks of z1 /
+// z_out (uint8, numel bytes = elements / 8; training steps only).
 int net_activation(Net* n, int block, int which, int B, void** ptr, long long* numel) {
   VPD_REQUIRE(n->ws != nullptr, "net_activation: not bound");
   if (block < 0) {
@@ -1374,11 +1362,16 @@ int net_activation(Net* n, int block, int which, int B, void** ptr, long long* n
                         : (long long)B * (n->H / 4) * (n->W / 4) * 64;
     return 0;
   }
-  VPD_REQUIRE(block < (int)n->blocks.size() && which >= 0 && which <= 4, "net_activation: range");
+  VPD_REQUIRE(block < (int)n->blocks.size() && which >= 0 && which <= 6, "net_activation: range");
   BlockDesc& bd = n->blocks[block];
+  *numel = (long long)B * bd.c2.Hin * bd.c2.Win * bd.c2.Cout;
+  if (which >= 5) {
+    *ptr = which == 5 ? bd.m1 : bd.mout;
+    *numel /= 8;
+    return 0;
+  }
   bf16* ps[5] = {bd.y1, bd.z1, bd.y2, bd.yds, bd.zout};
   *ptr = ps[which];
-  *numel = (long long)B * bd.c2.Hin * bd.c2.Win * bd.c2.Cout;
   return 0;
 }
 
