@@ -17,6 +17,10 @@
 #include "rng.cuh"
 #include "tma_host.h"
 
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
 namespace vpd {
 
 constexpr int kAsmThreads = 256;
@@ -29,7 +33,18 @@ constexpr int kAsmThreads = 256;
 // divisions in each of the 1280 CTAs of a launch.
 struct AsmLut {
   float v[5 * 256];   // [c*256 + u]; c < 3 rgb, c = 3, 4 flow
+  // bf16 outputs only (the network's input layout): fmaf(float(u), sc[c], sh[c]) rounds to the
+  // same bf16 as v[c*256 + u] for ALL 256 bytes of every channel when arith_ok is set (checked
+  // entry by entry whenever the tables are built) - the kernel may then compute instead of look up
+  float sc[5], sh[5];
+  int arith_ok;
 };
+// round-to-nearest-even fp32 -> bf16 bits (finite inputs), what cvt.rn.bf16.f32 does
+static unsigned bf16_bits_rn(float f) {
+  unsigned u;
+  memcpy(&u, &f, 4);
+  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+}
 static void host_lut(AsmLut* lut, const float* mean, const float* stdv) {
   // a loader calls with the same normalisation constants every batch: keep the last table
   static thread_local AsmLut cached;
@@ -54,6 +69,42 @@ static void host_lut(AsmLut* lut, const float* mean, const float* stdv) {
       }
       lut->v[c * 256 + u] = v;
     }
+  lut->arith_ok = 1;
+  for (int c = 0; c < 5; ++c) {
+    if (c < 3) {
+      lut->sc[c] = static_cast<float>(1.0 / (255.0 * static_cast<double>(stdv[c])));
+      lut->sh[c] = static_cast<float>(-static_cast<double>(mean[c]) / static_cast<double>(stdv[c]));
+    } else {
+      lut->sc[c] = static_cast<float>(1.0 / 255.0);
+      lut->sh[c] = -0.5f;
+    }
+    // the correctly rounded constants miss an occasional entry by one fp32 ulp right at a bf16
+    // rounding boundary; a pair a few ulps away that reproduces all 256 entries almost always
+    // exists (search order: nearest first)
+    const float sc0 = lut->sc[c], sh0 = lut->sh[c];
+    bool found = false;
+    static const int kNudge[7] = {0, 1, -1, 2, -2, 3, -3};
+    for (int ia = 0; ia < 7 && !found; ++ia)
+      for (int ib = 0; ib < 7 && !found; ++ib) {
+        unsigned ua, ub;
+        memcpy(&ua, &sc0, 4);
+        memcpy(&ub, &sh0, 4);
+        ua += static_cast<unsigned>(kNudge[ia]);
+        ub += static_cast<unsigned>(kNudge[ib]);
+        float sc, sh;
+        memcpy(&sc, &ua, 4);
+        memcpy(&sh, &ub, 4);
+        bool all = true;
+        for (int u = 0; u < 256 && all; ++u)
+          all = bf16_bits_rn(fmaf(static_cast<float>(u), sc, sh)) == bf16_bits_rn(lut->v[c * 256 + u]);
+        if (all) {
+          lut->sc[c] = sc;
+          lut->sh[c] = sh;
+          found = true;
+        }
+      }
+    if (!found) lut->arith_ok = 0;
+  }
   cached = *lut;
   for (int i = 0; i < 3; ++i) {
     key[i] = mean[i];
@@ -251,6 +302,158 @@ assemble_pad8_kernel(const __grid_constant__ AsmParams p, const __grid_constant_
   }
 }
 
+// Stem layout, persistent version (the training / apply fast path: no noise, 16-byte aligned
+// rows). One CTA per SM slot walks (frame, 32-row chunk) units; the packed uint8 rows of the
+// NEXT unit arrive through 1-D bulk copies (cp.async.bulk -> mbarrier, no LSU traffic, no
+// registers) while the current one is converted, the tables are built once per CTA instead of
+// once per unit, and they hold the bf16 bit patterns already placed in the half of the 32-bit
+// word their channel occupies, so a pixel is five shared-memory lookups and three ORs. A warp
+// iteration covers 4 cells x (2 rows x 4 columns) = 32 pixels = 512 contiguous output bytes.
+// The first version (one CTA per unit: load, __syncthreads, convert) ran at 0.35 of the
+// measured HBM bandwidth with its output staying in L2: latency-bound, not bandwidth-bound.
+constexpr int kAsmRows = 32;       // padded rows per unit (even: whole cell rows)
+constexpr int kLutRep = 2;         // table replicas: lane l reads replica l & 1
+template <bool kArith>   // true: AsmLut::arith_ok - compute the values, no tables
+__global__ void __launch_bounds__(kAsmThreads, 4)
+assemble_pad8_stream_kernel(const __grid_constant__ AsmParams p, const __grid_constant__ AsmLut tables) {
+  pdl_trigger();
+  extern __shared__ __align__(128) uint8_t sm[];
+  uint32_t* lut = reinterpret_cast<uint32_t*>(sm);              // [5][256][kLutRep] packed halves
+  constexpr int kLutBytes = 5 * 256 * kLutRep * 4;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + kLutBytes);  // [2]
+  // shared-memory rows are 64 bytes longer than the image rows: the two rows a warp reads in
+  // one instruction then sit 16 banks apart instead of on the same banks
+  const int rpitch = p.W * 3 + 64, fpitch = p.W * p.fc + 64;
+  const int rgb_bytes = kAsmRows * rpitch, flow_bytes = p.flow ? kAsmRows * fpitch : 0;
+  const int stage_bytes = (rgb_bytes + flow_bytes + 127) & ~127;
+  uint8_t* stage0 = sm + kLutBytes + 128;
+  const int Hs = stem_cells_h(p.H), Ws = stem_cells_w(p.W);
+  const int Hp = 2 * Hs;
+  const long long frame_elems = (long long)Hs * Ws * 64;
+  const int chunks = (Hp + kAsmRows - 1) / kAsmRows;
+  const int units = p.B * chunks;
+
+  // tables: bf16 bits of channel c's value in the low (c even) or high (c odd) half
+  // (the table is a kernel parameter = constant memory: read with a WARP-UNIFORM index - a
+  // per-lane index is replayed once per distinct address, which made this loop 15 % of the
+  // kernel's stall samples - and let lanes 0..1 store the replicas)
+  for (int i0 = (threadIdx.x >> 5) * 4; !kArith && i0 < 5 * 256; i0 += (kAsmThreads / 32) * 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k;
+      const uint32_t b = pack_bf16x2(tables.v[i], 0.f) & 0xFFFFu;
+      const uint32_t e = ((i >> 8) & 1) ? (b << 16) : b;
+      if ((threadIdx.x & 31) < kLutRep) lut[i * kLutRep + (threadIdx.x & 31)] = e;
+    }
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+
+  // unit u -> frame b, padded rows [hp0, hp0 + rows), image rows [h_lo, h_hi)
+  // (called by warp 0: lane r copies image row r of the unit)
+  auto issue = [&](int u, int st) {
+    const int b = u / chunks, hp0 = (u - b * chunks) * kAsmRows;
+    const int rows = min(kAsmRows, Hp - hp0);
+    const int h_lo = max(hp0 - 3, 0), h_hi = min(hp0 + rows - 3, p.H);
+    const int nimg = max(h_hi - h_lo, 0);
+    const int src = p.index ? p.index[b] : b;
+    uint8_t* dst = stage0 + st * stage_bytes;
+    const uint32_t nr = p.W * 3, nf = p.flow ? p.W * p.fc : 0;
+    const int r = threadIdx.x & 31;
+    if (r == 0) mbar_expect_tx(&bar[st], nimg * (nr + nf));
+    __syncwarp();
+    if (r < nimg) {
+      bulk_load(dst + r * rpitch, p.rgb + ((size_t)src * p.H + h_lo + r) * nr, nr, &bar[st]);
+      if (nf) bulk_load(dst + rgb_bytes + r * fpitch, p.flow + ((size_t)src * p.H + h_lo + r) * nf, nf, &bar[st]);
+    }
+  };
+  int u = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && u < units) issue(u, 0);
+  const int a = (lane >> 2) & 1, q = lane & 3, cl = lane >> 3;   // row of the pair, column, cell
+  const uint32_t* lutl = lut + (lane & (kLutRep - 1));
+  const int cgroups = (Ws + 3) >> 2;                             // groups of 4 cells per row
+  uint32_t phases = 0;   // bit st = parity the next wait on stage st expects
+  for (int it = 0; u < units; u += gridDim.x, ++it) {
+    const int st = it & 1;
+    if (warp == 0 && u + (int)gridDim.x < units) issue(u + gridDim.x, st ^ 1);
+    const int b = u / chunks, hp0 = (u - b * chunks) * kAsmRows;
+    const int rows = min(kAsmRows, Hp - hp0);
+    const int h_lo = max(hp0 - 3, 0);
+    if (hp0 == 0 && p.teacher && p.out_tgt) {
+      const int src = p.index ? p.index[b] : b;
+      const int row = (p.teacher_rows > 1 && p.flip && p.flip[b]) ? 1 : 0;
+      const float* t = p.teacher + ((size_t)src * p.teacher_rows + row) * p.tdim;
+      for (int i = threadIdx.x; i < p.tdim; i += kAsmThreads) p.out_tgt[(size_t)b * p.tdim + i] = t[i];
+    }
+    const uint8_t* s_rgb = stage0 + st * stage_bytes;
+    const uint8_t* s_flow = s_rgb + rgb_bytes;
+    mbar_wait(&bar[st], (phases >> st) & 1u);
+    phases ^= 1u << st;
+    const int pairs = rows >> 1;
+    for (int v = 0; v < p.k; ++v) {
+      const bool fl = (p.k == 2) ? (v == 1) : (p.flip && p.flip[b]);
+      const uint32_t sgn = fl ? 0x80000000u : 0u;
+      uint4* obase = reinterpret_cast<uint4*>(p.out_pad + ((size_t)b * p.k + v) * frame_elems);
+      // a warp owns row pairs warp, warp + 8, ...; per pair it walks the cell groups two at a
+      // time (two independent pixels per lane in flight: the lookups are a dependent chain)
+      for (int pr = warp; pr < pairs; pr += kAsmThreads / 32) {
+        const int hp = hp0 + 2 * pr + a, h = hp - 3;
+        const bool row_in = h >= 0 && h < p.H;
+        const uint8_t* rrow = s_rgb + (h - h_lo) * rpitch;
+        const uint8_t* frow = s_flow + (h - h_lo) * fpitch;
+        uint4* orow = obase + (size_t)(hp >> 1) * Ws * 8 + a * 4 + q;
+        for (int cg0 = 0; cg0 < cgroups; cg0 += 2) {
+          uint4 o[2];
+          int cell[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            cell[e] = (cg0 + e) * 4 + cl;
+            const int w = cell[e] * 4 + q - 3;
+            o[e] = make_uint4(0, 0, 0, 0);
+            if (row_in && w >= 0 && w < p.W) {
+              const int ws = fl ? (p.W - 1 - w) : w;
+              const uint8_t* px = rrow + ws * 3;
+              if (kArith) {
+                const float c0 = fmaf(static_cast<float>(px[0]), tables.sc[0], tables.sh[0]);
+                const float c1 = fmaf(static_cast<float>(px[1]), tables.sc[1], tables.sh[1]);
+                const float c2 = fmaf(static_cast<float>(px[2]), tables.sc[2], tables.sh[2]);
+                float c3 = 0.f, c4 = 0.f;
+                if (p.flow) {
+                  const uint8_t* pf = frow + ws * p.fc;
+                  c3 = fmaf(static_cast<float>(pf[0]), tables.sc[3], tables.sh[3]);
+                  c4 = fmaf(static_cast<float>(pf[1]), tables.sc[4], tables.sh[4]);
+                }
+                o[e].x = pack_bf16x2(c0, c1);
+                o[e].y = pack_bf16x2(c2, c3) ^ (p.flow ? sgn : 0u);
+                o[e].z = pack_bf16x2(c4, 0.f);
+              } else {
+                o[e].x = lutl[px[0] * kLutRep] | lutl[(256 + px[1]) * kLutRep];
+                o[e].y = lutl[(512 + px[2]) * kLutRep];
+                if (p.flow) {
+                  const uint8_t* pf = frow + ws * p.fc;
+                  o[e].y |= lutl[(768 + pf[0]) * kLutRep] ^ sgn;
+                  o[e].z = lutl[(1024 + pf[1]) * kLutRep];
+                }
+              }
+            }
+          }
+          // cell (hp >> 1, cell): 64 elements = 8 uint4, this lane's pixel is slot a * 4 + q
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (cell[e] < Ws) stg_v4(orow + (size_t)cell[e] * 8, o[e]);
+        }
+      }
+    }
+    __syncthreads();   // the stage may be refilled (next iteration's issue targets it)
+  }
+}
+
 // fp32 NCHW (the reference's batch['img']) -> stem layout
 __global__ void __launch_bounds__(256)
 nchw_to_pad8_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C,
@@ -371,14 +574,42 @@ int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
   p.out_tgt = out_tgt;
   if (set_noise(&p, nz)) return -1;
   p.rows_per_cta = 32;
+  AsmLut tables;
+  host_lut(&tables, p.mean, p.stdv);
+  // persistent bulk-copy version: no noise, every row range a multiple of 16 bytes at a
+  // 16-byte aligned address (true for the 128 x 128 crops of the reference and any W % 16 == 0)
+  static const bool stream_on = getenv("VPD_K1_STREAM") == nullptr || getenv("VPD_K1_STREAM")[0] != '0';
+  const bool aligned = (W * 3) % 16 == 0 && ((uintptr_t)rgb % 16) == 0 && ((size_t)H * W * 3) % 16 == 0 &&
+                       (flow == nullptr || ((W * flow_channels) % 16 == 0 && ((uintptr_t)flow % 16) == 0));
+  if (stream_on && aligned && p.mask == nullptr) {
+    const int rgb_b = kAsmRows * (W * 3 + 64), flow_b = flow ? kAsmRows * (W * flow_channels + 64) : 0;
+    const int smem2 = 5 * 256 * kLutRep * 4 + 128 + 2 * ((rgb_b + flow_b + 127) & ~127) + 128;
+    if (smem2 <= 72 * 1024) {
+      static bool attr = false;
+      if (!attr) {
+        VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_stream_kernel<true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_stream_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        attr = true;
+      }
+      const int units = B * ((2 * stem_cells_h(H) + kAsmRows - 1) / kAsmRows);
+      const int grid = units < 148 * 3 ? units : 148 * 3;   // 68 KB each: three per SM
+      static const bool arith_on = getenv("VPD_K1_ARITH") == nullptr || getenv("VPD_K1_ARITH")[0] != '0';
+      if (tables.arith_ok && arith_on)
+        VPD_CHECK_CUDA(launch_kernel(assemble_pad8_stream_kernel<true>, dim3(grid), dim3(kAsmThreads), smem2, stream, p, tables));
+      else
+        VPD_CHECK_CUDA(launch_kernel(assemble_pad8_stream_kernel<false>, dim3(grid), dim3(kAsmThreads), smem2, stream, p, tables));
+      VPD_LAUNCHED(1);
+      return 0;
+    }
+  }
   const int smem = smem_for(p, p.rows_per_cta);
   VPD_REQUIRE(smem <= 200 * 1024, "assemble: image too wide (W=%d)", W);
   if (smem > 48 * 1024)
     VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int chunks = (2 * stem_cells_h(H) + p.rows_per_cta - 1) / p.rows_per_cta;
-  AsmLut tables;
-  host_lut(&tables, p.mean, p.stdv);
   VPD_CHECK_CUDA(launch_kernel(assemble_pad8_kernel, dim3(B * chunks), dim3(kAsmThreads), smem, stream, p, tables));
   VPD_LAUNCHED(1);
   return 0;

@@ -130,6 +130,10 @@ VPD_DEVINL void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 
 // ... have completed (writes performed)
 VPD_DEVINL void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// one cache line -> L2
+VPD_DEVINL void prefetch_l2(const void* g) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
+}
 // asynchronous L2 prefetch of a contiguous global range (bytes % 16 == 0)
 VPD_DEVINL void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gsrc)),

@@ -537,6 +537,23 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
   if (have) {
     tile_coords(tile, n_tile, w0, h0, b0);
     if (nbr > 0 && live && !(p.dbg & 32)) issue_loads(n_tile, w0, h0, b0, 0);
+    if (nbr > 0 && live && SC::kSlabs > 1 && p.single_tile != 0 && !(p.dbg & 128)) {
+      // One tile per CTA: the operands of slabs 1.. are requested only when the slab before
+      // them has been reduced, i.e. after the main loop, and they were written a whole
+      // forward pass ago. Pull them into L2 now, under the main loop (thread st = tile row st).
+      const int pn = b0 + (st >> (ltw + lth)), ph = h0 + ((st >> ltw) & (p.th - 1)),
+                pw = w0 + (st & (p.tw - 1));
+      if (pn < p.batch && ph < p.out_h && pw < p.out_w) {
+        const uint32_t off = static_cast<uint32_t>(static_cast<int>(p.cls[cls].base) +
+                                                   n_tile * BLOCK_N + pn * sn + ph * sh + pw * sw_);
+        prefetch_l2(p.bmask + (off >> 3));
+#pragma unroll
+        for (int jj = 1; jj < SC::kSlabs; ++jj) {
+          prefetch_l2(p.by[0] + off + jj * 64);
+          if (nbr > 1) prefetch_l2(p.by[1] + off + jj * 64);
+        }
+      }
+    }
   }
   while (have) {
     if (sums && cur_ntile != n_tile) {
