@@ -118,7 +118,6 @@ static int out_map(ConvLaunch* L, const __nv_bfloat16* out, int N, int H, int W,
     L->p.cls[0].base = 0;
   }
   if (act_map(&L->o, out, N, H, W, C, stride, L->p)) return -1;
-  L->o2 = L->o;
   return 0;
 }
 
@@ -238,7 +237,6 @@ int plan_conv_fwd(ConvLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
   set_weights(&p, 1, w_tap, g.Cout, g.Cin);
   L->a1 = L->a0;
   if (out_map(L, y, g.N, Ho, Wo, g.Cout, 1, 0, 0)) return -1;
-  L->o2 = L->o;
   return 0;
 }
 
@@ -318,8 +316,7 @@ int plan_stem_fwd(ConvLaunch* L2, int N, int H, int W, const __nv_bfloat16* x_s2
     uint64_t ostr[5] = {2, 256, (uint64_t)Wo * 128, (uint64_t)Wo * 128, (uint64_t)Ho * Wo * 128};
     uint32_t obox[5] = {64, 8, 1, 16, 1};
     if (encode_tmap_bf16(&L->o, y, 5, odims, ostr, obox, true)) return -1;
-    L->o2 = L->o;
-  }
+    }
   return 0;
 }
 
@@ -454,7 +451,6 @@ int plan_conv_dgrad(ConvLaunch* Ls, int* count, const ConvGeom& g, const __nv_bf
     L->a1 = L->a0;
   }
   if (out_map(L, dx, g.N, g.H, g.W, g.Cin, 2, 0, 0)) return -1;
-  L->o2 = L->o;
   *count = 1;
   return 0;
 }
@@ -463,30 +459,30 @@ static int conv_mode(const ConvLaunch& L) {
   return L.p.stats != nullptr ? 1 : (L.p.bnb == 1 ? 2 : (L.p.bnb == 2 ? 3 : 0));
 }
 
-template <int BN, int CS, bool FUSE, int MODE>
+template <int BN, int CS, int MODE>
 static int launch_bn_impl(const ConvLaunch& L, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, CS, FUSE, MODE>,
+    VPD_CHECK_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, CS, MODE>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         ConvCfg<BN>::kSmemBytes));
     attr_set = true;
   }
-  VPD_CHECK_CUDA(launch_kernel_cluster(CS, conv_igemm_kernel<BN, CS, FUSE, MODE>, dim3(L.grid),
+  VPD_CHECK_CUDA(launch_kernel_cluster(CS, conv_igemm_kernel<BN, CS, MODE>, dim3(L.grid),
                                        dim3(kConvThreads), ConvCfg<BN>::kSmemBytes, stream, L.a0,
-                                       L.a1, L.o, L.o2, L.p));
+                                       L.a1, L.o, L.p));
   VPD_LAUNCHED(1);
   return 0;
 }
 
 template <int BN, int CS>
 static int launch_bn(const ConvLaunch& L, cudaStream_t stream) {
-  if (CS != 1) return launch_bn_impl<BN, CS, false, -1>(L, stream);   // opt-in pair mode: generic
+  if (CS != 1) return launch_bn_impl<BN, CS, -1>(L, stream);   // opt-in pair mode: generic
   switch (conv_mode(L)) {
-    case 1: return launch_bn_impl<BN, 1, false, 1>(L, stream);
-    case 2: return launch_bn_impl<BN, 1, false, 2>(L, stream);
-    case 3: return launch_bn_impl<BN, 1, false, 3>(L, stream);
-    default: return launch_bn_impl<BN, 1, false, 0>(L, stream);
+    case 1: return launch_bn_impl<BN, 1, 1>(L, stream);
+    case 2: return launch_bn_impl<BN, 1, 2>(L, stream);
+    case 3: return launch_bn_impl<BN, 1, 3>(L, stream);
+    default: return launch_bn_impl<BN, 1, 0>(L, stream);
   }
 }
 

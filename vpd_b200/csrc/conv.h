@@ -8,8 +8,6 @@ namespace vpd {
 struct ConvLaunch {
   CUtensorMap a0, a1;  // activation views read by the taps (tap.src 0 / 1)
   CUtensorMap o;       // output view written by the TMA tile stores
-  CUtensorMap o2;      // second output (z) of a conv with the BatchNorm apply fused in
-  int fused_bn;        // 1: this launch also applies its BatchNorm (no bn_apply kernel needed)
   const void* w_ptr;   // this launch's (main) weight block, for the previous launch's L2 prefetch
   long long w_bytes;
   ConvParams p;
@@ -36,14 +34,6 @@ struct ConvEpilogue {
   const __nv_bfloat16* residual = nullptr;
   int relu = 0;
   StatAcc* stats = nullptr;
-  // optional: apply the training-mode BatchNorm of this conv in the same launch (grid
-  // barrier; only taken when every CTA gets at most one tile): z = relu?(bn(y) (+ fuse_res))
-  bool fuse_bn = false;
-  BnLayer bn;                               // bn.stats must equal `stats`
-  __nv_bfloat16* fuse_z = nullptr;
-  const __nv_bfloat16* fuse_res = nullptr;
-  int fuse_relu = 0;
-  unsigned int* fuse_bar = nullptr;         // zeroed by the caller before every launch
 };
 
 // Fused BN-backward reduction for a dgrad launch (see ConvParams::bnb)

@@ -124,17 +124,6 @@ struct ConvParams {
   // entry / after the dependency wait / first operands landed / last MMA issued /
   // first accumulator ready / epilogue done / exit
   long long* trace;
-  // Training-mode BatchNorm apply fused behind a GRID BARRIER (CTAs with exactly one tile,
-  // i.e. the small deep layers, where a separate elementwise kernel costs ~10 us of pipeline
-  // drain/fill for ~4 us of work): pass 1 stores y and accumulates the statistics as usual,
-  // all CTAs meet at `fbar`, every CTA derives scale/shift of its channel block and pass 2
-  // re-reads the accumulator still sitting in TMEM, rounds it exactly like the stored y and
-  // writes z = relu(y*scale + shift (+ residual)) through the second output map.
-  int fuse_bn;
-  BnLayer fbn;                   // fbn.stats == stats
-  const __nv_bfloat16* fres;     // residual (same addressing as out) or null
-  int frelu;
-  unsigned int* fbar;            // zeroed every step
   // weights of the NEXT convolution in the stream: every CTA pulls one slice into L2 while
   // this kernel runs (they come from HBM once per step and nothing else would hide that)
   const __nv_bfloat16* pf_ptr;
@@ -217,19 +206,16 @@ struct ConvCfg {
 // Epilogue, warps 2..5 (threads 64..191): drains the TMEM accumulator stages tile by tile -
 // optional folded-BN affine, residual, ReLU - and writes bf16 slabs to the staging ring.
 // It performs no reductions and no global stores.
-template <int BLOCK_N, int CS, bool FUSE, int MODE>
+template <int BLOCK_N, int CS, int MODE>
 VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                               uint64_t* tempty_bar, uint8_t* slabs, uint64_t* sfull,
-                              uint64_t* sempty, const float* s_scale, const float* s_shift,
-                              uint64_t* bnready, uint8_t* ring, uint64_t* zfull, int rank,
+                              uint64_t* sempty, uint8_t* ring, uint64_t* zfull, int rank,
                               int first_item, int item_stride, int total_tiles, int warp,
                               int lane) {
   using SC = StageCfg<BLOCK_N>;
-  constexpr int passes = FUSE ? 2 : 1;
-  // fused-BN launches have one tile per CTA: once its accumulator is complete the operand
-  // ring is dead, so every slab of both passes gets its own 16 KB of it (no slot hand-shake);
-  // the same holds for any launch whose CTAs have a single tile (ConvParams::single_tile)
-  const bool direct = FUSE || (ring != nullptr && p.single_tile != 0);
+  // launches whose CTAs have a single tile (ConvParams::single_tile): once the accumulator is
+  // complete the operand ring is dead, so every slab gets its own 16 KB of it (no slot hand-shake)
+  const bool direct = ring != nullptr && p.single_tile != 0;
   // pair mode (CS == 2): the leader's MMA thread owns the accumulator hand-shake, so the
   // peer's epilogue warps release the TMEM stage on the LEADER's barrier
   const uint32_t tempty_remote0 =
@@ -257,21 +243,17 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
     if (tile == first_item && threadIdx.x == kEpiThread0) trace_mark(p, 5);
     tc_fence_after();
 #pragma unroll 1
-    for (int pass = 0; pass < passes; ++pass) {
-    if (FUSE && pass == 1) mbar_wait(bnready, 0);  // scale / shift of this channel block are in smem
-#pragma unroll 1
     for (int j = 0; j < SC::kSlabs; ++j) {
       if (!direct) mbar_wait(&sempty[slot], sphase ^ 1);  // the slab's previous contents have been stored
-      const uint32_t dst = direct ? smem_u32(ring) + (pass * SC::kSlabs + j) * kSlabBytes + r * 128
+      const uint32_t dst = direct ? smem_u32(ring) + j * kSlabBytes + r * 128
                                   : row_addr + slot * kSlabBytes;
 #pragma unroll 1
       for (int cc = 0; cc < ((p.dbg & 4) ? 0 : 2); ++cc) {
         const int c = 2 * j + cc;
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
-        // training-forward kernels (MODE 1): the first pass is a plain conversion
-        const __nv_bfloat16* resp =
-            (FUSE && pass == 1) ? p.fres : (MODE == 1 ? nullptr : p.residual);
+        // training-forward kernels (MODE 1): a plain conversion
+        const __nv_bfloat16* resp = MODE == 1 ? nullptr : p.residual;
         const bool do_res = resp != nullptr && valid;
         uint4 rres[4];
         if (do_res) {
@@ -284,19 +266,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 #pragma unroll
         for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
         const int ch0 = n_tile * BLOCK_N + c * 32;
-        if (FUSE && pass == 1) {
-          // exactly what bn_apply_kernel does with the stored bf16 y
-          const uint32_t sc_a = smem_u32(s_scale + c * 32), sh_a = smem_u32(s_shift + c * 32);
-#pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            const float4 sc = __uint4_as_float4(lds_v4(sc_a + k * 4));
-            const float4 sh = __uint4_as_float4(lds_v4(sh_a + k * 4));
-            f[k + 0] = fmaf(bf16_round(f[k + 0]), sc.x, sh.x);
-            f[k + 1] = fmaf(bf16_round(f[k + 1]), sc.y, sh.y);
-            f[k + 2] = fmaf(bf16_round(f[k + 2]), sc.z, sh.z);
-            f[k + 3] = fmaf(bf16_round(f[k + 3]), sc.w, sh.w);
-          }
-        } else if (MODE != 1 && p.scale != nullptr) {
+        if (MODE != 1 && p.scale != nullptr) {
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
             const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + k));
@@ -320,7 +290,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
             f[8 * k + 7] += bf16_hi(rres[k].w);
           }
         }
-        if ((FUSE && pass == 1) ? p.frelu : (MODE != 1 && p.relu)) {
+        if (MODE != 1 && p.relu) {
 #pragma unroll
           for (int k = 0; k < 32; ++k) f[k] = fmaxf(f[k], 0.f);
         }
@@ -336,7 +306,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
                             pack_bf16x2(f[8 * k + 4], f[8 * k + 5]),
                             pack_bf16x2(f[8 * k + 6], f[8 * k + 7])));
       }
-      if (j == SC::kSlabs - 1 && pass == passes - 1) {
+      if (j == SC::kSlabs - 1) {
         // accumulator fully read: hand the TMEM stage back to the MMA warp
         tc_fence_before();
         __syncwarp();
@@ -347,7 +317,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
       }
       fence_proxy_async();  // generic-proxy writes -> visible to the TMA store
       if (direct) {
-        mbar_arrive(&zfull[pass * SC::kSlabs + j]);
+        mbar_arrive(&zfull[j]);
       } else {
         mbar_arrive(&sfull[slot]);
         if (++slot == SC::kSlots) {
@@ -355,7 +325,6 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
           sphase ^= 1;
         }
       }
-    }
     }
     if (++as == 2) {
       as = 0;
@@ -382,9 +351,9 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 // 2 / 3 fused BN-backward reduction with one / two BN branches (dgrad), -1 decided at run time. The specialised kernels
 // carry only their own reduction code: these kernels are large enough for instruction-cache
 // misses to show (keeping two epilogue flavours in one kernel cost ~10 % on the deep layers).
-template <int BLOCK_N, int CS, bool FUSE, int MODE>
+template <int BLOCK_N, int CS, int MODE>
 VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
-                           const CUtensorMap* tm_out2, uint64_t* bnready, uint8_t* ring,
+                           uint8_t* ring,
                            uint64_t* zfull, uint8_t* slabs,
                            uint64_t* sfull, uint64_t* sempty, float* s_sum, float* s_sq,
                            float* s_x2, float* s_scr, int rank, int first_item, int item_stride,
@@ -560,7 +529,7 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       if (cur_ntile >= 0) global_flush(cur_ntile);
       cur_ntile = n_tile;
     }
-    const bool direct = FUSE || (ring != nullptr && p.single_tile != 0);   // slab j lives in the dead operand ring
+    const bool direct = ring != nullptr && p.single_tile != 0;   // slab j lives in the dead operand ring
     if (direct) mbar_wait(&zfull[j], 0);
     else mbar_wait(&sfull[slot], sphase);
     const uint8_t* slab_ptr = direct ? ring + j * kSlabBytes : slabs + slot * kSlabBytes;
@@ -667,52 +636,6 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
     }
   }
   if (sums && cur_ntile >= 0) global_flush(cur_ntile);
-  if (FUSE && cur_ntile >= 0) {
-    // ---- grid barrier: every CTA's sums are in the global accumulators after this
-    if (st == 0) {
-      __threadfence();
-      atomicAdd(p.fbar, 1u);
-      unsigned int seen = 0, spins = 0;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(p.fbar) : "memory");
-        if (seen >= gridDim.x) break;
-        __nanosleep(64);
-        if (++spins > (1u << 24)) __trap();  // a CTA of the grid never arrived: fail loudly
-      } while (true);
-      __threadfence();
-    }
-    asm volatile("bar.sync 2, %0;" ::"n"(kStatThreads) : "memory");
-    // scale / shift of this CTA's channel block (same arithmetic as the elementwise kernels);
-    // the CTA holding the first pixel tile of the block also persists the batch statistics
-    const bool owner = (first_item / p.n_tiles) == 0 && rank == 0;
-    for (int i = st; i < BLOCK_N; i += kStatThreads) {
-      const int c = cur_ntile * BLOCK_N + i;
-      float mean, rstd, var, sc, sh;
-      bn_mean_rstd<true>(p.fbn, c, p.cout, mean, rstd, var);
-      bn_affine(__ldg(p.fbn.gamma + c), __ldg(p.fbn.beta + c), mean, rstd, sc, sh);
-      s_sum[i] = sc;
-      s_sq[i] = sh;
-      if (owner) bn_channel_side_effects(p.fbn, c, mean, rstd, var);
-    }
-    if (first_item == 0 && rank == 0 && st == 0 && p.fbn.update_running && p.fbn.num_batches)
-      *p.fbn.num_batches += 1;
-    mbar_arrive(bnready);  // release: the epilogue warps may read scale / shift
-    // ---- pass 2: the epilogue warps stage z slabs; only the store thread has work
-    if (st == 0) {
-      const int n_tile0 = first_item % p.n_tiles;
-      int mt = (first_item / p.n_tiles) * CS + rank;
-      const int zw0 = (mt % p.tiles_w) * p.tw;
-      mt /= p.tiles_w;
-      const int zh0 = (mt % p.tiles_h) * p.th;
-      const int zb0 = (mt / p.tiles_h) * p.tn;
-      for (int jz = 0; jz < SC::kSlabs; ++jz) {
-        mbar_wait(&zfull[SC::kSlabs + jz], 0);
-        tma_store_5d(tm_out2, ring + (SC::kSlabs + jz) * kSlabBytes,
-                     p.cls[0].out_c0 + n_tile0 * BLOCK_N + jz * 64, zw0, p.cls[0].out_d2, zh0, zb0);
-        bulk_commit_group();
-      }
-    }
-  }
   // the last stores only need to have READ their slabs before the CTA (and its shared memory)
   // goes away; grid completion makes the writes visible to the dependent kernel
   if (st == 0) bulk_wait_read0();
@@ -726,10 +649,10 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
 // plus as much TMA write traffic - twice the 128 B/cycle the shared memory can move -
 // which is what pins the single-CTA kernel near half of the tensor peak; in pair mode a
 // CTA reads/writes 3/4 (N=128) or 1/2 (N=256) as many bytes per MAC.
-template <int BLOCK_N, int CS, bool FUSE, int MODE>
+template <int BLOCK_N, int CS, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+                  const __grid_constant__ CUtensorMap tmOut,
                   const __grid_constant__ ConvParams p) {
   using Cfg = ConvCfg<BLOCK_N>;
   pdl_trigger();
@@ -744,8 +667,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* pfull_bar = tempty_bar + 2;  // leader only: "the peer's stage has landed"
   uint64_t* sfull_bar = pfull_bar + Cfg::kStages;  // epilogue -> statistics warps: slab staged
   uint64_t* sempty_bar = sfull_bar + 2;            // slab stored, slot free
-  uint64_t* bnready_bar = sempty_bar + 2;          // fused BN: scale / shift ready
-  uint64_t* zfull_bar = bnready_bar + 1;           // fused BN: slab (pass, j) staged in the ring
+  uint64_t* zfull_bar = sempty_bar + 2;            // single-tile launches: slab j staged in the ring
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(zfull_bar + 8);
   float* s_sum = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + Cfg::kBarBytes);
   float* s_sq = s_sum + BLOCK_N;
@@ -767,7 +689,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       mbar_init(&sfull_bar[s], kEpiThreads);
       mbar_init(&sempty_bar[s], 1);
     }
-    mbar_init(bnready_bar, kStatThreads);
     for (int s = 0; s < 8; ++s) mbar_init(&zfull_bar[s], kEpiThreads);
     fence_mbar_init();
     tma_prefetch_desc(&tmA0);
@@ -808,13 +729,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, CS, FUSE, MODE>(p, &tmOut, &tmOut2, bnready_bar, smem, zfull_bar, slabs, sfull_bar,
+    conv_stats<BLOCK_N, CS, MODE>(p, &tmOut, smem, zfull_bar, slabs, sfull_bar,
                                   sempty_bar, s_sum, s_sq, s_x2, s_scr, rank, first_item,
                                   item_stride, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, CS, FUSE, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar,
-                                     sempty_bar, s_sum, s_sq, bnready_bar, smem, zfull_bar, rank,
+    conv_epilogue<BLOCK_N, CS, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar,
+                                     sempty_bar, smem, zfull_bar, rank,
                                      first_item, item_stride, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
@@ -1040,12 +961,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, 1, false, MODE>(p, &tmOut, &tmOut, nullptr, nullptr, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
+    conv_stats<BLOCK_N, 1, MODE>(p, &tmOut, nullptr, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
                            blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, 1, false, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
-                              s_sum, s_sq, nullptr, nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
+    conv_epilogue<BLOCK_N, 1, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
+                              nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
    if (warp == 0) {
@@ -1210,12 +1131,12 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
 
   if (warp >= kStatWarp0) {
     setmaxnreg_inc<kRegsStat>();
-    conv_stats<BLOCK_N, 1, false, MODE>(p, &tmOut, &tmOut, nullptr, nullptr, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
+    conv_stats<BLOCK_N, 1, MODE>(p, &tmOut, nullptr, nullptr, slabs, sfull_bar, sempty_bar, s_sum, s_sq, s_x2, s_scr, 0,
                            blockIdx.x, gridDim.x, total_tiles, warp - kStatWarp0, lane);
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
-    conv_epilogue<BLOCK_N, 1, false, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
-                              s_sum, s_sq, nullptr, nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
+    conv_epilogue<BLOCK_N, 1, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
+                              nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
    if (warp == 0) {

@@ -216,7 +216,6 @@ struct Net {
   bf16* w_stem_s2d;                // stem operand mirrors for the space-to-depth kernel
   StatAcc* stats;                  // [2][total_ch] forward sum/sumsq   (zeroed per step)
   StatAcc* bwd_sums;               // [2][total_ch] backward sums        (zeroed per step)
-  unsigned int* bn_bar;            // one grid-barrier counter per BN layer (fused BN apply)
   double* loss_dev;                // scalar
   float *save_mean, *save_rstd;    // [total_ch]
   float *ev_scale, *ev_shift;      // [total_ch]
@@ -493,7 +492,6 @@ static long long carve(Net* n, uint8_t* base) {
   n->w_stem_s2d = c.take<bf16>(kStemMirrorElems);
   n->stats = c.take<StatAcc>(2 * n->total_ch);
   n->bwd_sums = c.take<StatAcc>(2 * n->total_ch);
-  n->bn_bar = c.take<unsigned int>(n->num_bn + 8);   // grid-barrier counters (zeroed per step)
   n->loss_dev = c.take<double>(8);
   n->save_mean = c.take<float>(n->total_ch);
   n->save_rstd = c.take<float>(n->total_ch);
