@@ -34,6 +34,15 @@ VPD_DEVINL uint4 pack8(const float (&f)[8]) {
                     pack_bf16x2(f[6], f[7]));
 }
 // bit j = 1[element j of the packed bf16 vector > 0] (the stored, rounded values decide)
+// The vector holds ReLU outputs: no negative values and no -0 (fmaxf(x, 0.f) returns +0), so
+// "> 0" is "bit pattern != 0" and min(half, 1) is the flag of a half (one SIMD instruction per
+// packed pair); NaNs (never produced by a finite network) would count as positive.
+VPD_DEVINL uint32_t gt0_bits_relu(const uint4& v) {
+  const uint32_t x = __vminu2(v.x, 0x00010001u) + (__vminu2(v.y, 0x00010001u) << 2) +
+                     (__vminu2(v.z, 0x00010001u) << 4) + (__vminu2(v.w, 0x00010001u) << 6);
+  return (x & 0x55u) | ((x >> 15) & 0xAAu);   // even channels sit at bits 0,2,4,6, odd at 16,18,..
+}
+// any bf16 vector (negative values, -0, NaN -> 0)
 VPD_DEVINL uint32_t gt0_bits(const uint4& v) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
   uint32_t b = 0;
@@ -137,7 +146,8 @@ __global__ void __launch_bounds__(kEwThreads, RES == 0 ? 4 : 3) bn_apply_kernel(
       }
       const uint4 zv = pack8(f);
       stg_v4(p.z + off, zv);
-      if (p.mask != nullptr) p.mask[(size_t)r * groups + g] = static_cast<uint8_t>(gt0_bits(zv));
+      if (p.mask != nullptr)
+        p.mask[(size_t)r * groups + g] = static_cast<uint8_t>(p.relu ? gt0_bits_relu(zv) : gt0_bits(zv));
     }
   }
   // every block has consumed the statistics above before block 0 may touch
