@@ -282,6 +282,20 @@ int plan_stem_fwd(ConvLaunch* L2, int N, int H, int W, const __nv_bfloat16* x_s2
       tp.src = 0;
       tp.btap = t;
       tp.kchunks = 1;
+      // K step ks of a cell = row a = ks >> 1, column pair q = 2 (ks & 1), + 1: weight
+      // (kh = 2 dy + a, kw = 4 dxb + q - 2 cls) lies outside the 7 x 7 kernel for BOTH columns
+      // (or for the row) -> all-zero slice, not issued: 28 of 32 / 28 of 48 MMAs remain
+      const int dy = t / ntx, dxb = t % ntx;
+      tp.kskip = 0;
+      for (int ks = 0; ks < 4; ++ks) {
+        const int kh = 2 * dy + (ks >> 1);
+        bool any = false;
+        for (int q = 2 * (ks & 1); q < 2 * (ks & 1) + 2; ++q) {
+          const int kw = 4 * dxb + q - 2 * cls;
+          any = any || (kh < 7 && kw >= 0 && kw < 7);
+        }
+        if (!any) tp.kskip |= 1 << ks;
+      }
     }
     p.patch_dx = 0;
     p.patch_dy = 0;

@@ -74,7 +74,8 @@ struct ConvTap {
   int src;      // which (A,B) tensor-map pair (0/1)
   int btap;     // index on the tap axis of the weight tensor
   int kchunks;  // number of 64-wide K chunks for this tap
-  int pad_;
+  int kskip;    // halo kernels: bit k set = K step k (16 channels) of this tap has all-zero weights
+                // and is not issued (the stem's taps cover 8 x 8 positions of a 7 x 7 kernel)
 };
 
 struct ConvParams {
@@ -1010,6 +1011,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        uint32_t accum = 0u;   // the tile's first MMA overwrites the accumulator
         for (int kc = 0; kc < CHUNKS; ++kc) {
           mbar_wait(&full_bar[slot], phase);
           tc_fence_after();
@@ -1021,9 +1023,13 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint64_t adesc = make_smem_desc(patch + start_row * 128, 16, 1280);
             const uint64_t bdesc =
                 make_smem_desc(smem_u32(s_w + (kc * NTAPS + t) * (BLOCK_N * 128)), 16, 1024);
+            const int kskip = NTAPS > 9 ? p.taps[t].kskip : 0;
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kc | t | k) != 0);
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              if (NTAPS > 9 && ((kskip >> k) & 1)) continue;
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+              accum = 1u;
+            }
           }
           umma_commit(&empty_bar[slot]);
           if (++slot == Cfg::kSlots) {
