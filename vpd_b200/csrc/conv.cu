@@ -592,12 +592,14 @@ int launch_conv(const ConvLaunch& L0, cudaStream_t stream) {
 static void finish_wgrad(WgradLaunch* L, int cin, int cout, int num_taps, int kchunks,
                          int row_limit, float* dw) {
   WgradParams& p = L->p;
-  L->block_n = cout % 128 == 0 ? 128 : 64;
+  if (L->block_n != 256) L->block_n = cout % 128 == 0 ? 128 : 64;
   p.n_tiles = cout / L->block_n;
   p.kchunks = kchunks;
   p.num_taps = num_taps;
   p.num_units = num_taps * kchunks;
-  p.num_pairs = (p.num_units + 1) / 2;
+  const int group = 2;                           // WgradCfg::kUnits
+  p.dbg = env_int("VPD_WGRAD_DBG", 0);
+  p.num_pairs = (p.num_units + group - 1) / group;
   p.cin = cin;
   p.cout = cout;
   p.row_limit = row_limit;
@@ -712,6 +714,20 @@ int plan_conv_wgrad(WgradLaunch* L, const ConvGeom& g, const __nv_bfloat16* x,
                                const_cast<__nv_bfloat16*>(dy), e);
   g_plan_no_halo = false;
   if (rc) return -1;
+  // 256-wide output blocks (conv_wgrad_kernel<256>) work on 64-pixel tiles: halve the tile
+  // along the image (or row) axis and rebuild the X view with the smaller box
+  static const int wide_on = env_int("VPD_WGRAD256", 1);
+  if (wide_on && g.Cout % 256 == 0 && (f.p.tn % 2 == 0 || f.p.th % 2 == 0)) {
+    if (f.p.tn % 2 == 0) {
+      f.p.tn /= 2;
+      f.p.tiles_b = (g.N + f.p.tn - 1) / f.p.tn;
+    } else {
+      f.p.th /= 2;
+      f.p.tiles_h = (g.Ho() + f.p.th - 1) / f.p.th;
+    }
+    if (act_map(&f.a0, x, g.N, g.H, g.W, g.Cin, g.stride, f.p)) return -1;
+    L->block_n = 256;
+  }
   copy_geometry(&L->p, f.p);
   L->x = f.a0;
   if (act_map(&L->dy, dy, g.N, g.Ho(), g.Wo(), g.Cout, 1, f.p)) return -1;
@@ -806,6 +822,7 @@ int launch_wgrad(const WgradLaunch& L, cudaStream_t stream) {
   if (skip) return 0;
   if (L.halo) return launch_wgrad_halo(L, stream);
   if (L.block_n == 64) return launch_wgrad_bn<64>(L, stream);
+  if (L.block_n == 256) return launch_wgrad_bn<256>(L, stream);
   return launch_wgrad_bn<128>(L, stream);
 }
 

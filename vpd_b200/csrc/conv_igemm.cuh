@@ -1250,23 +1250,37 @@ struct WgradParams {
   int tiles_w, tiles_h, tiles_b;
   int n_tiles;          // Cout / BLOCK_N
   int num_units;        // taps * (Cin / 64)
-  int num_pairs;        // ceil(num_units / 2)
-  int splits;           // pixel-range splits per (pair, n_tile)
+  int num_pairs;        // unit groups: ceil(num_units / 2), or / 4 for the 256-wide kernel
+  int splits;           // pixel-range splits per (unit group, n_tile)
   int kchunks;          // Cin / 64
   int num_taps;
   ConvTap taps[kMaxTaps];
   int cin, cout;
   int row_limit;        // rows (ci within unit) >= row_limit are not written (stem pad)
   float* dw;            // [taps][cout][cin] fp32, accumulated
+  int dbg;              // diagnostics (VPD_WGRAD_DBG): bit 0 skip the atomics
 };
 
+// BLOCK_N = 256 (256 / 512 output channels): per unit pair the dY tile is read once for 256
+// output channels instead of once per 128 (48 KB instead of 64 KB of operands per 64 pixels x
+// 256 channels). Its pipeline stages hold 64 pixels (K = 64) instead of 128: 48 KB x 4 stages.
+// kUnits = 4 (two M = 128 accumulators filling all 512 TMEM columns, 64 KB per 8 MMAs) is
+// implemented by the loops below and measured SLOWER (21.2 vs 17.4 us per 256 -> 256 layer): a
+// CTA has one work item, so the fp32 red.global epilogue - 148 x the accumulator size per
+// launch, whatever the split - is exposed, and it doubles with the accumulator.
 template <int BLOCK_N>
 struct WgradCfg {
-  static constexpr int kABytes = 2 * kBlockM * 64 * 2;        // two unit boxes
-  static constexpr int kBBytes = (BLOCK_N / 64) * kBlockM * 64 * 2;
+  static constexpr int kUnits = 2;                            // (tap, chunk) units per work item
+  static constexpr int kPix = BLOCK_N == 256 ? 64 : kBlockM;  // pixels (K) per pipeline stage
+  static constexpr int kBoxBytes = kPix * 64 * 2;             // one {64 ch, kPix pixels} TMA box
+  static constexpr int kABytes = kUnits * kBoxBytes;
+  static constexpr int kBBytes = (BLOCK_N / 64) * kBoxBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BLOCK_N == 64 ? 4 : 3;
-  static constexpr int kTmemCols = 2 * BLOCK_N;
+  static constexpr int kStages = BLOCK_N == 128 ? 3 : 4;
+  // accumulator stages: two (the epilogue of an item overlaps the next item's MMAs) when they fit
+  static constexpr int kAccCols = (kUnits / 2) * BLOCK_N;
+  static constexpr int kAccStages = 2 * kAccCols <= 512 ? 2 : 1;
+  static constexpr int kTmemCols = kAccStages * kAccCols;
   static constexpr int kBarBytes = 1024;
   static constexpr int kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;
 };
@@ -1323,8 +1337,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int split = item % p.splits;
         const int n_tile = (item / p.splits) % p.n_tiles;
         const int pair = item / (p.splits * p.n_tiles);
-        int u[2] = {2 * pair, 2 * pair + 1};
-        if (u[1] >= p.num_units) u[1] = u[0];  // dummy second unit (result discarded)
+        int u[Cfg::kUnits];
+#pragma unroll
+        for (int j = 0; j < Cfg::kUnits; ++j) {
+          u[j] = Cfg::kUnits * pair + j;
+          if (u[j] >= p.num_units) u[j] = Cfg::kUnits * pair;  // dummy unit (result discarded)
+        }
         const int pt_end = min(pix_tiles, (split + 1) * per_split);
         for (int pt = split * per_split; pt < pt_end; ++pt) {
           int mt = pt;
@@ -1337,15 +1355,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
+          for (int j = 0; j < Cfg::kUnits; ++j) {
             const ConvTap tap = p.taps[u[j] / p.kchunks];
             const int kc = u[j] % p.kchunks;
-            tma_load_5d(sa + j * (kBlockM * 128), &tmX, &full_bar[stage], tap.c0 + kc * 64,
+            tma_load_5d(sa + j * Cfg::kBoxBytes, &tmX, &full_bar[stage], tap.c0 + kc * 64,
                         w0 + tap.d1, tap.d2, h0 + tap.d3, b0);
           }
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_5d(sb + j * (kBlockM * 128), &tmDY, &full_bar[stage],
+            tma_load_5d(sb + j * Cfg::kBoxBytes, &tmDY, &full_bar[stage],
                         n_tile * BLOCK_N + j * 64, w0, 0, h0, b0);
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -1367,7 +1385,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int pt_end = min(pix_tiles, (split + 1) * per_split);
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + as * Cfg::kAccCols;
         for (int pt = pt_beg; pt < pt_end; ++pt) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -1375,13 +1393,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const uint32_t sb = sa + Cfg::kABytes;
           // MN-major: LBO = bytes between 64-wide M/N blocks (one TMA box),
           // SBO = bytes between 8-pixel groups along K
-          const uint64_t adesc = make_smem_desc(sa, kBlockM * 128, 1024);
-          const uint64_t bdesc = make_smem_desc(sb, kBlockM * 128, 1024);
+          const uint64_t bdesc = make_smem_desc(sb, Cfg::kBoxBytes, 1024);
 #pragma unroll
-          for (int k = 0; k < kBlockM / kUmmaK; ++k) {
-            // 16 pixels (rows of 128 B) per MMA -> 2048 B -> +128 in the address field
-            umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, idesc,
-                      (pt != pt_beg || k != 0) ? 1u : 0u);
+          for (int h = 0; h < Cfg::kUnits / 2; ++h) {   // unit pairs = M = 128 accumulators
+            const uint64_t adesc = make_smem_desc(sa + h * 2 * Cfg::kBoxBytes, Cfg::kBoxBytes, 1024);
+#pragma unroll
+            for (int k = 0; k < Cfg::kPix / kUmmaK; ++k) {
+              // 16 pixels (rows of 128 B) per MMA -> 2048 B -> +128 in the address field
+              umma_bf16(d_tmem + h * BLOCK_N, adesc + 128 * k, bdesc + 128 * k, idesc,
+                        (pt != pt_beg || k != 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == Cfg::kStages) {
@@ -1390,7 +1411,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           }
         }
         umma_commit(&tfull_bar[as]);
-        if (++as == 2) {
+        if (++as == Cfg::kAccStages) {
           as = 0;
           aphase ^= 1;
         }
@@ -1405,31 +1426,35 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       const int split = item % p.splits;
       const int n_tile = (item / p.splits) % p.n_tiles;
       const int pair = item / (p.splits * p.n_tiles);
-      const int unit = 2 * pair + (r >> 6);
       const int rl = r & 63;
       const bool has_work = split * per_split < pix_tiles;
-      const bool valid = has_work && unit < p.num_units && rl < p.row_limit;
-      const int tap_i = valid ? unit / p.kchunks : 0;
-      const int kc = valid ? unit % p.kchunks : 0;
-      float* dst = p.dw + ((size_t)p.taps[tap_i].btap * p.cout + n_tile * BLOCK_N) * p.cin +
-                   kc * 64 + rl;
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
-        tmem_ld_wait();
-        if (valid) {
+      for (int h = 0; h < Cfg::kUnits / 2; ++h) {
+        const int unit = Cfg::kUnits * pair + 2 * h + (r >> 6);
+        const bool valid = has_work && unit < p.num_units && rl < p.row_limit && !(p.dbg & 1);
+        const int tap_i = valid ? unit / p.kchunks : 0;
+        const int kc = valid ? unit % p.kchunks : 0;
+        float* dst = p.dw + ((size_t)p.taps[tap_i].btap * p.cout + n_tile * BLOCK_N) * p.cin +
+                     kc * 64 + rl;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * Cfg::kAccCols +
+                        h * BLOCK_N + c * 32, v);
+          tmem_ld_wait();
+          if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            atomicAdd(dst + (size_t)(c * 32 + j) * p.cin, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; ++j)
+              atomicAdd(dst + (size_t)(c * 32 + j) * p.cin, __uint_as_float(v[j]));
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (++as == 2) {
+      if (++as == Cfg::kAccStages) {
         as = 0;
         aphase ^= 1;
       }
