@@ -536,8 +536,12 @@ def run_native(args, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     torch.cuda.set_device(dev)
     dist = None
+    numa_cpus = None
     if world > 1:
         import torch.distributed as dist
+        from vpd_b200 import dp
+        if os.environ.get('VPD_NUMA_BIND', '1') != '0':
+            numa_cpus = dp.bind_host_to_device(local_rank)   # before any pinned allocation
         dist.init_process_group('nccl', device_id=dev)
     B = args.batch
 
@@ -900,6 +904,9 @@ def run_native(args, rank, world, local_rank):
             'step_tflops_per_gpu': round(step_tflops, 2),
             'step_frac_of_bf16_burst_peak': round(step_tflops / pk['tflops_burst'], 4),
             'loss_per_frame_timed_region': final_loss,
+            'host_numa_bind': ({'rank0_cpus': len(numa_cpus), 'how': 'vpd_b200.dp.bind_host_to_device: every '
+                                'rank pinned to the CPUs of its GPU\'s NUMA node before allocating pinned batches'}
+                               if numa_cpus else None),
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -95,3 +95,12 @@ def test_two_rank_gloo_gradient_sum_and_epoch_loss(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, (res.stdout[-1500:], res.stderr[-2500:])
     assert res.stdout.count('OK') == 2, res.stdout      # the two ranks' lines may interleave
+
+
+def test_bind_host_to_device_is_best_effort():
+    """No GPU / no readable topology: the NUMA binding returns None and leaves the affinity alone."""
+    import os
+    from vpd_b200 import dp
+    before = os.sched_getaffinity(0)
+    assert dp.bind_host_to_device(0) is None
+    assert os.sched_getaffinity(0) == before
