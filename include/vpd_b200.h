@@ -160,7 +160,7 @@ VPD_API int vpd_conv2d_dgrad(const void* dy, const void* wT_tap, void* dx, int N
  * stored already masked, g = dx * 1[z > 0], and sums[0..Cin) += sum g,
  * sums[Cin..2Cin) += sum g * (y - mean) * rstd  (accumulated). relu_mask = 1[z > 0] as one
  * bit per element, uint8 [N][H][W][Cin/8], bit j of byte g = channel 8g + j (written by
- * vpd_bn_act_fwd, or by vpd_relu_mask from a tensor z): the kernel reads 1/16 of z's bytes. */
+ * vpd_bn_act_fwd, or by vpd_relu_bitmask from a tensor z): the kernel reads 1/16 of z's bytes. */
 VPD_API int vpd_conv2d_dgrad_bnfused(const void* dy, const void* wT_tap, void* dx, int N, int H, int W,
                              int Cin, int Cout, int k, int stride, int pad, const void* residual,
                              const uint8_t* relu_mask, const void* y, const float* mean,
@@ -191,7 +191,7 @@ VPD_API int vpd_bn_act_fwd(const void* y, const void* res, void* z, int64_t M, i
                    float* res_running_var, int64_t* res_num_batches, float* res_save_mean,
                    float* res_save_rstd, uint8_t* relu_mask, void* stream);
 /* relu_mask of an existing bf16 tensor z [M][C] (same bit layout) */
-VPD_API int vpd_relu_mask(const void* z, uint8_t* mask, int64_t M, int C, void* stream);
+VPD_API int vpd_relu_bitmask(const void* z, uint8_t* mask, int64_t M, int C, void* stream);
 /* gradient of the stage above: g = dz * 1[z > 0] (z may be NULL: no mask); dy = BN
  * backward of g through (y, save_mean, save_rstd, gamma); optional second branch
  * (y2...) fed by the same g; dmask (may alias dz) receives g; sums = [2][C]

@@ -45,7 +45,7 @@ def main():
             z = yf = x
 
         zmask = torch.zeros((N, H, W, Cin // 8), device=dev, dtype=torch.uint8)
-        lib().call('vpd_relu_mask', z, zmask, N * H * W, Cin, s)
+        lib().call('vpd_relu_bitmask', z, zmask, N * H * W, Cin, s)
 
         def run():
             if dgrad:   # Cin == Cout in every case: x doubles as dy, y as dx

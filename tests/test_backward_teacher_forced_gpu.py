@@ -130,7 +130,7 @@ def test_every_backward_kernel_on_the_oracles_tensors_batch256():
         m1, r1 = _batch_stats(y1)
         z1d = nhwc_bf16(z1).to(dev())
         zmask = torch.zeros((N, Ho, Wo, cout // 8), device=dev(), dtype=torch.uint8)
-        lib().call('vpd_relu_mask', z1d, zmask, M, cout, s)
+        lib().call('vpd_relu_bitmask', z1d, zmask, M, cout, s)
         g1 = torch.empty_like(dy2)
         s1 = acc_zeros((2, cout), dev())
         lib().call('vpd_conv2d_dgrad_bnfused', nhwc_bf16(g_y2).to(dev()), wT2, g1, N, Ho, Wo, cout, cout, 3, 1, 1,

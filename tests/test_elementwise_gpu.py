@@ -63,7 +63,7 @@ def test_bn_act_forward_and_backward(N, H, W, C, mode):
     bits = ((z.view(M, C // 8, 8).float() > 0).to(torch.int32) << torch.arange(8, device=dev())).sum(-1)
     assert torch.equal(mask.to(torch.int32), bits)
     mask2 = torch.zeros_like(mask)
-    lib().call('vpd_relu_mask', z, mask2, M, C, stream_ptr())
+    lib().call('vpd_relu_bitmask', z, mask2, M, C, stream_ptr())
     assert torch.equal(mask2, mask)
     # running statistics like nn.BatchNorm2d (momentum 0.1, unbiased variance)
     yv = nchw_f32(y)

@@ -399,7 +399,7 @@ def test_conv2d_dgrad_with_fused_bn_backward_reduction(case):
     sums = acc_zeros((2, Cin), dev())
     dx = torch.full((N, H, W, Cin), float('nan'), device=dev(), dtype=torch.bfloat16)
     zmask = torch.zeros((N, H, W, Cin // 8), device=dev(), dtype=torch.uint8)
-    lib().call('vpd_relu_mask', z, zmask, N * H * W, Cin, stream_ptr())
+    lib().call('vpd_relu_bitmask', z, zmask, N * H * W, Cin, stream_ptr())
     lib().call('vpd_conv2d_dgrad_bnfused', dy, wT_tap, dx, N, H, W, Cin, Cout, k, stride, pad, res,
                zmask, y, mean, rstd, sums, stream_ptr())
     ref = torch.nn.grad.conv2d_input((N, Cin, H, W), w.to(torch.bfloat16).float().to(dev()),

@@ -297,7 +297,7 @@ int vpd_bn_act_fwd(const void* y, const void* res, void* z, int64_t M, int C, in
   return launch_bn_apply(a, (cudaStream_t)stream);
 }
 
-int vpd_relu_mask(const void* z, uint8_t* mask, int64_t M, int C, void* stream) {
+int vpd_relu_bitmask(const void* z, uint8_t* mask, int64_t M, int C, void* stream) {
   return launch_relu_mask((const bf16*)z, mask, M, C, (cudaStream_t)stream);
 }
 
