@@ -136,6 +136,7 @@ struct AsmParams {
   int B, H, W, fc, rows_per_cta;
   int teacher_rows, tdim;
   int k;                  // apply variants: 1 = as is (flip bit per frame), 2 = [orig, flipped]
+  int row_pad;            // stream kernel: extra bytes per shared-memory row (0: rows contiguous)
   // masked Gaussian noise on the normalised RGB planes (single_frame.py:179-191): applied to
   // the frames with noise_on[b] != 0, at the pixels whose mask byte is NOT 0 (the reference
   // zeroes the noise where `mask_png[:,:,0] == 0`), before the flip; k == 1 only
@@ -313,17 +314,17 @@ assemble_pad8_kernel(const __grid_constant__ AsmParams p, const __grid_constant_
 // measured HBM bandwidth with its output staying in L2: latency-bound, not bandwidth-bound.
 constexpr int kAsmRows = 32;       // padded rows per unit (even: whole cell rows)
 constexpr int kLutRep = 2;         // table replicas: lane l reads replica l & 1
-template <bool kArith>   // true: AsmLut::arith_ok - compute the values, no tables
+template <bool kArith, bool kFlow>   // kArith: AsmLut::arith_ok - compute the values, no tables
 __global__ void __launch_bounds__(kAsmThreads, 4)
 assemble_pad8_stream_kernel(const __grid_constant__ AsmParams p, const __grid_constant__ AsmLut tables) {
   pdl_trigger();
   extern __shared__ __align__(128) uint8_t sm[];
   uint32_t* lut = reinterpret_cast<uint32_t*>(sm);              // [5][256][kLutRep] packed halves
-  constexpr int kLutBytes = 5 * 256 * kLutRep * 4;
+  constexpr int kLutBytes = kArith ? 0 : 5 * 256 * kLutRep * 4;   // no tables on the arithmetic path
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + kLutBytes);  // [2]
   // shared-memory rows are 64 bytes longer than the image rows: the two rows a warp reads in
   // one instruction then sit 16 banks apart instead of on the same banks
-  const int rpitch = p.W * 3 + 64, fpitch = p.W * p.fc + 64;
+  const int rpitch = p.W * 3 + p.row_pad, fpitch = p.W * p.fc + p.row_pad;
   const int rgb_bytes = kAsmRows * rpitch, flow_bytes = p.flow ? kAsmRows * fpitch : 0;
   const int stage_bytes = (rgb_bytes + flow_bytes + 127) & ~127;
   uint8_t* stage0 = sm + kLutBytes + 128;
@@ -367,7 +368,12 @@ assemble_pad8_stream_kernel(const __grid_constant__ AsmParams p, const __grid_co
     const int r = threadIdx.x & 31;
     if (r == 0) mbar_expect_tx(&bar[st], nimg * (nr + nf));
     __syncwarp();
-    if (r < nimg) {
+    if (p.row_pad == 0) {          // contiguous rows: one copy per tensor
+      if (r == 0 && nimg > 0) {
+        bulk_load(dst, p.rgb + ((size_t)src * p.H + h_lo) * nr, nimg * nr, &bar[st]);
+        if (nf) bulk_load(dst + rgb_bytes, p.flow + ((size_t)src * p.H + h_lo) * nf, nimg * nf, &bar[st]);
+      }
+    } else if (r < nimg) {
       bulk_load(dst + r * rpitch, p.rgb + ((size_t)src * p.H + h_lo + r) * nr, nr, &bar[st]);
       if (nf) bulk_load(dst + rgb_bytes + r * fpitch, p.flow + ((size_t)src * p.H + h_lo + r) * nf, nf, &bar[st]);
     }
@@ -401,52 +407,60 @@ assemble_pad8_stream_kernel(const __grid_constant__ AsmParams p, const __grid_co
       const uint32_t sgn = fl ? 0x80000000u : 0u;
       uint4* obase = reinterpret_cast<uint4*>(p.out_pad + ((size_t)b * p.k + v) * frame_elems);
       // a warp owns row pairs warp, warp + 8, ...; per pair it walks the cell groups two at a
-      // time (two independent pixels per lane in flight: the lookups are a dependent chain)
+      // time (two independent pixels per lane in flight). The body is branch-free: a pixel outside
+      // the image reads some in-bounds shared-memory bytes and is zeroed by a select.
+      const int wl = cl * 4 + q - 3;                      // this lane's column inside a cell group
+      float sc[5], sh[5];
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        sc[c] = tables.sc[c];
+        sh[c] = tables.sh[c];
+      }
       for (int pr = warp; pr < pairs; pr += kAsmThreads / 32) {
         const int hp = hp0 + 2 * pr + a, h = hp - 3;
         const bool row_in = h >= 0 && h < p.H;
-        const uint8_t* rrow = s_rgb + (h - h_lo) * rpitch;
-        const uint8_t* frow = s_flow + (h - h_lo) * fpitch;
+        const int hr = row_in ? h - h_lo : 0;
+        const uint8_t* rrow = s_rgb + hr * rpitch;
+        const uint8_t* frow = s_flow + hr * fpitch;
         uint4* orow = obase + (size_t)(hp >> 1) * Ws * 8 + a * 4 + q;
         for (int cg0 = 0; cg0 < cgroups; cg0 += 2) {
           uint4 o[2];
-          int cell[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            cell[e] = (cg0 + e) * 4 + cl;
-            const int w = cell[e] * 4 + q - 3;
-            o[e] = make_uint4(0, 0, 0, 0);
-            if (row_in && w >= 0 && w < p.W) {
-              const int ws = fl ? (p.W - 1 - w) : w;
-              const uint8_t* px = rrow + ws * 3;
-              if (kArith) {
-                const float c0 = fmaf(static_cast<float>(px[0]), tables.sc[0], tables.sh[0]);
-                const float c1 = fmaf(static_cast<float>(px[1]), tables.sc[1], tables.sh[1]);
-                const float c2 = fmaf(static_cast<float>(px[2]), tables.sc[2], tables.sh[2]);
-                float c3 = 0.f, c4 = 0.f;
-                if (p.flow) {
-                  const uint8_t* pf = frow + ws * p.fc;
-                  c3 = fmaf(static_cast<float>(pf[0]), tables.sc[3], tables.sh[3]);
-                  c4 = fmaf(static_cast<float>(pf[1]), tables.sc[4], tables.sh[4]);
-                }
-                o[e].x = pack_bf16x2(c0, c1);
-                o[e].y = pack_bf16x2(c2, c3) ^ (p.flow ? sgn : 0u);
-                o[e].z = pack_bf16x2(c4, 0.f);
-              } else {
-                o[e].x = lutl[px[0] * kLutRep] | lutl[(256 + px[1]) * kLutRep];
-                o[e].y = lutl[(512 + px[2]) * kLutRep];
-                if (p.flow) {
-                  const uint8_t* pf = frow + ws * p.fc;
-                  o[e].y |= lutl[(768 + pf[0]) * kLutRep] ^ sgn;
-                  o[e].z = lutl[(1024 + pf[1]) * kLutRep];
-                }
+            const int w = (cg0 + e) * 16 + wl;
+            const bool in = row_in && static_cast<unsigned>(w) < static_cast<unsigned>(p.W);
+            const int ws = in ? (fl ? (p.W - 1 - w) : w) : 0;
+            const uint8_t* px = rrow + ws * 3;
+            const uint8_t* pf = frow + ws * p.fc;
+            uint32_t x, y, z = 0u;
+            if (kArith) {
+              const float c0 = fmaf(static_cast<float>(px[0]), sc[0], sh[0]);
+              const float c1 = fmaf(static_cast<float>(px[1]), sc[1], sh[1]);
+              const float c2 = fmaf(static_cast<float>(px[2]), sc[2], sh[2]);
+              float c3 = 0.f, c4 = 0.f;
+              if (kFlow) {
+                c3 = fmaf(static_cast<float>(pf[0]), sc[3], sh[3]);
+                c4 = fmaf(static_cast<float>(pf[1]), sc[4], sh[4]);
+              }
+              x = pack_bf16x2(c0, c1);
+              y = pack_bf16x2(c2, c3) ^ (kFlow ? sgn : 0u);
+              if (kFlow) z = pack_bf16x2(c4, 0.f);
+            } else {
+              x = lutl[px[0] * kLutRep] | lutl[(256 + px[1]) * kLutRep];
+              y = lutl[(512 + px[2]) * kLutRep];
+              if (kFlow) {
+                y |= lutl[(768 + pf[0]) * kLutRep] ^ sgn;
+                z = lutl[(1024 + pf[1]) * kLutRep];
               }
             }
+            o[e] = make_uint4(in ? x : 0u, in ? y : 0u, in ? z : 0u, 0u);
           }
           // cell (hp >> 1, cell): 64 elements = 8 uint4, this lane's pixel is slot a * 4 + q
 #pragma unroll
-          for (int e = 0; e < 2; ++e)
-            if (cell[e] < Ws) stg_v4(orow + (size_t)cell[e] * 8, o[e]);
+          for (int e = 0; e < 2; ++e) {
+            const int cell = (cg0 + e) * 4 + cl;
+            if (cell < Ws) stg_v4(orow + (size_t)cell * 8, o[e]);
+          }
         }
       }
     }
@@ -504,6 +518,7 @@ static int fill_params(AsmParams* p, const uint8_t* rgb, const uint8_t* flow, in
   p->teacher_rows = teacher_rows;
   p->tdim = tdim;
   p->k = k;
+  p->row_pad = 0;
   p->out_img = nullptr;
   p->out_tgt = nullptr;
   p->out_pad = nullptr;
@@ -582,24 +597,40 @@ int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
   const bool aligned = (W * 3) % 16 == 0 && ((uintptr_t)rgb % 16) == 0 && ((size_t)H * W * 3) % 16 == 0 &&
                        (flow == nullptr || ((W * flow_channels) % 16 == 0 && ((uintptr_t)flow % 16) == 0));
   if (stream_on && aligned && p.mask == nullptr) {
-    const int rgb_b = kAsmRows * (W * 3 + 64), flow_b = flow ? kAsmRows * (W * flow_channels + 64) : 0;
-    const int smem2 = 5 * 256 * kLutRep * 4 + 128 + 2 * ((rgb_b + flow_b + 127) & ~127) + 128;
+    // row_pad: 64 puts the two image rows a warp reads 16 banks apart but needs one bulk copy
+    // per row (64 small copies per unit); measured slower than contiguous rows with one copy
+    // per tensor and 2-way conflicts on the byte loads (20.2 vs 18.3 us per launch)
+    static const int row_pad = getenv("VPD_K1_PAD") ? atoi(getenv("VPD_K1_PAD")) : 0;
+    p.row_pad = row_pad;
+    static const bool arith_on = getenv("VPD_K1_ARITH") == nullptr || getenv("VPD_K1_ARITH")[0] != '0';
+    const bool ar = tables.arith_ok && arith_on;
+    const int rgb_b = kAsmRows * (W * 3 + row_pad), flow_b = flow ? kAsmRows * (W * flow_channels + row_pad) : 0;
+    const int smem2 = (ar ? 0 : 5 * 256 * kLutRep * 4) + 128 + 2 * ((rgb_b + flow_b + 127) & ~127) + 128;
     if (smem2 <= 72 * 1024) {
       static bool attr = false;
       if (!attr) {
-        VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_stream_kernel<true>,
+        VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_stream_kernel<true, true>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
-        VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_stream_kernel<false>,
+        VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_stream_kernel<true, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_stream_kernel<false, true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_pad8_stream_kernel<false, false>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
         attr = true;
       }
       const int units = B * ((2 * stem_cells_h(H) + kAsmRows - 1) / kAsmRows);
-      const int grid = units < 148 * 3 ? units : 148 * 3;   // 68 KB each: three per SM
-      static const bool arith_on = getenv("VPD_K1_ARITH") == nullptr || getenv("VPD_K1_ARITH")[0] != '0';
-      if (tables.arith_ok && arith_on)
-        VPD_CHECK_CUDA(launch_kernel(assemble_pad8_stream_kernel<true>, dim3(grid), dim3(kAsmThreads), smem2, stream, p, tables));
+      static const int per_sm = getenv("VPD_K1_CTAS") ? atoi(getenv("VPD_K1_CTAS")) : 3;   // 3 and 4 measure the same
+      const int resident = 220 * 1024 / (smem2 + 1024) < per_sm ? 220 * 1024 / (smem2 + 1024) : per_sm;
+      const int grid = units < 148 * resident ? units : 148 * resident;
+      if (ar && flow)
+        VPD_CHECK_CUDA(launch_kernel(assemble_pad8_stream_kernel<true, true>, dim3(grid), dim3(kAsmThreads), smem2, stream, p, tables));
+      else if (ar)
+        VPD_CHECK_CUDA(launch_kernel(assemble_pad8_stream_kernel<true, false>, dim3(grid), dim3(kAsmThreads), smem2, stream, p, tables));
+      else if (flow)
+        VPD_CHECK_CUDA(launch_kernel(assemble_pad8_stream_kernel<false, true>, dim3(grid), dim3(kAsmThreads), smem2, stream, p, tables));
       else
-        VPD_CHECK_CUDA(launch_kernel(assemble_pad8_stream_kernel<false>, dim3(grid), dim3(kAsmThreads), smem2, stream, p, tables));
+        VPD_CHECK_CUDA(launch_kernel(assemble_pad8_stream_kernel<false, false>, dim3(grid), dim3(kAsmThreads), smem2, stream, p, tables));
       VPD_LAUNCHED(1);
       return 0;
     }
