@@ -375,6 +375,11 @@ VPD_DEVINL uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
   return r;
 }
+VPD_DEVINL uint32_t ldg_nc_u32(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
 VPD_DEVINL uint32_t ldg_nc_u8(const void* p) {
   uint32_t r;
   asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(r) : "l"(p));

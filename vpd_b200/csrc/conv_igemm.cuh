@@ -240,6 +240,14 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
     const long long off = p.cls[tc.cls].base + tc.b0 * p.out_sn + tc.h0 * p.out_sh +
                           tc.w0 * p.out_sw + r_off + n_tile * BLOCK_N;
 
+    // fused BN backward (MODE 2 / 3): this row's ReLU mask bits, 32 channels per word, requested
+    // before the wait for the accumulator (a whole main loop hides the latency)
+    uint32_t mw[2 * SC::kSlabs];
+    if (MODE == 2 || MODE == 3 || (MODE < 0 && p.bnb > 0)) {
+#pragma unroll
+      for (int c = 0; c < 2 * SC::kSlabs; ++c)
+        mw[c] = valid ? ldg_nc_u32(p.bmask + ((off + c * 32) >> 3)) : 0u;
+    }
     mbar_wait(&tfull_bar[as], aphase);
     if (tile == first_item && threadIdx.x == kEpiThread0) trace_mark(p, 5);
     tc_fence_after();
@@ -299,13 +307,33 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 #pragma unroll
           for (int k = 0; k < 32; ++k) f[k] = 0.f;
         }
+        const bool masked = MODE == 2 || MODE == 3 || (MODE < 0 && p.bnb > 0);
+        // chunks come in order: take the head of the queue and shift it (static register indices)
+        const uint32_t mword = masked ? mw[0] : 0u;
+        if (masked) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          sts_v4(dst + (((static_cast<uint32_t>(cc * 4 + k)) ^ rsw) << 4),
-                 make_uint4(pack_bf16x2(f[8 * k + 0], f[8 * k + 1]),
-                            pack_bf16x2(f[8 * k + 2], f[8 * k + 3]),
-                            pack_bf16x2(f[8 * k + 4], f[8 * k + 5]),
-                            pack_bf16x2(f[8 * k + 6], f[8 * k + 7])));
+          for (int i = 0; i + 1 < 2 * SC::kSlabs; ++i) mw[i] = mw[i + 1];
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint4 o = make_uint4(pack_bf16x2(f[8 * k + 0], f[8 * k + 1]),
+                               pack_bf16x2(f[8 * k + 2], f[8 * k + 3]),
+                               pack_bf16x2(f[8 * k + 4], f[8 * k + 5]),
+                               pack_bf16x2(f[8 * k + 6], f[8 * k + 7]));
+          if (masked) {
+            // g = dz * 1[z > 0]. Bits 0-3 / 4-7 of the byte -> the sign bits of four bytes (no
+            // carries: the partial products of the multiplier do not overlap), then byte-wise
+            // sign replication gives 0xFFFF per selected bf16
+            const uint32_t b = (mword >> (8 * k)) & 0xFFu;
+            const uint32_t s03 = ((b & 0xFu) * 0x10204080u) & 0x80808080u;
+            const uint32_t s47 = ((b >> 4) * 0x10204080u) & 0x80808080u;
+            o.x &= prmt(s03, 0u, 0x9988u);
+            o.y &= prmt(s03, 0u, 0xBBAAu);
+            o.z &= prmt(s47, 0u, 0x9988u);
+            o.w &= prmt(s47, 0u, 0xBBAAu);
+          }
+          sts_v4(dst + (((static_cast<uint32_t>(cc * 4 + k)) ^ rsw) << 4), o);
+        }
       }
       if (j == SC::kSlabs - 1) {
         // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -336,9 +364,8 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
 
 // Statistics / store warps (warps 6..9, threads 192..319). For every staged slab:
 //   forward train (p.stats):  sum y, sum y^2 per channel  -> BatchNorm batch statistics
-//   dgrad (p.bnb):  the slab holds dz of a ReLU->BN stage; mask it in place with 1[z > 0]
-//                   (one bit per element, ConvParams::bmask; so the stored tensor is g) and
-//                   accumulate sum g and sum g*(y - mean)
+//   dgrad (p.bnb):  the slab holds g = dz * 1[z > 0] of a ReLU->BN stage (the epilogue warps
+//                   applied the bit mask ConvParams::bmask): accumulate sum g and sum g*(y - mean)
 //                   for up to two BN branches               -> fused BN-backward reduction
 // always on the stored (bf16-rounded) values; then ONE thread issues the slab's TMA tile
 // store. A lane owns eight consecutive channels and the four row groups of a warp
@@ -460,7 +487,6 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
     const int r = sw * 32 + i * 4 + rsub;
     rel[i] = (r >> (ltw + lth)) * sn + ((r >> ltw) & (p.th - 1)) * sh + (r & (p.tw - 1)) * sw_ + cg * 8;
   }
-  uint32_t mb[8];        // mask bytes of this lane's eight rows
   uint4 y0[8], y1[8];
   int cls = 0;  // output class of the tile the cursor is on
   auto issue_loads = [&](int n_tile, int w0, int h0, int b0, int j) {
@@ -477,7 +503,6 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       }
       // rows outside the tensor hold g = 0 in the slab: any finite operand will do
       const uint32_t off = static_cast<uint32_t>(ok ? base + rel[i] : cbase + cg * 8);
-      mb[i] = ldg_nc_u8(p.bmask + (off >> 3));
       y0[i] = ldg_nc_v4(p.by[0] + off);
       if (nbr > 1) y1[i] = ldg_nc_v4(p.by[1] + off);
     }
@@ -516,7 +541,6 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       if (pn < p.batch && ph < p.out_h && pw < p.out_w) {
         const uint32_t off = static_cast<uint32_t>(static_cast<int>(p.cls[cls].base) +
                                                    n_tile * BLOCK_N + pn * sn + ph * sh + pw * sw_);
-        prefetch_l2(p.bmask + (off >> 3));
 #pragma unroll
         for (int jj = 1; jj < SC::kSlabs; ++jj) {
           prefetch_l2(p.by[0] + off + jj * 64);
@@ -557,18 +581,12 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
       for (int i = 0; i < 8; ++i) g[i] = lds_v4(slab + srow[i]);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        uint32_t gw[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
-        // bits 0-3 / 4-7 of the mask byte -> the sign bits of four bytes (no carries: the
-        // partial products of the multiplier do not overlap), then byte-wise sign replication
-        const uint32_t s03 = ((mb[i] & 0xFu) * 0x10204080u) & 0x80808080u;
-        const uint32_t s47 = ((mb[i] >> 4) * 0x10204080u) & 0x80808080u;
-        const uint32_t zw[4] = {prmt(s03, 0u, 0x9988u), prmt(s03, 0u, 0xBBAAu),
-                                prmt(s47, 0u, 0x9988u), prmt(s47, 0u, 0xBBAAu)};
+        // the slab already holds g = dz * 1[z > 0]: the epilogue warps applied the mask
+        const uint32_t gw[4] = {g[i].x, g[i].y, g[i].z, g[i].w};
         const uint32_t yw[4] = {y0[i].x, y0[i].y, y0[i].z, y0[i].w};
         const uint32_t y1w[4] = {y1[i].x, y1[i].y, y1[i].z, y1[i].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          gw[k] &= zw[k];  // g = dz * 1[z > 0]
           const float lo = bf16_lo(gw[k]), hi = bf16_hi(gw[k]);
           a0[2 * k] += lo;
           a0[2 * k + 1] += hi;
@@ -580,11 +598,7 @@ VPD_DEVINL void conv_stats(const ConvParams& p, const CUtensorMap* tm_out,
             a2[2 * k + 1] = fmaf(hi, bf16_hi(y1w[k]), a2[2 * k + 1]);
           }
         }
-        g[i] = make_uint4(gw[0], gw[1], gw[2], gw[3]);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sts_v4(slab + srow[i], g[i]);
-      fence_proxy_async();
     }
     // store coordinates of the slab just processed
     const int st_c = p.cls[cls].out_c0 + n_tile * BLOCK_N + j * 64, st_w = w0, st_h = h0, st_b = b0;
