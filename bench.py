@@ -673,15 +673,29 @@ def run_native(args, rank, world, local_rank):
         fam_bytes = {}
         # the HBM-bound kernels north_star names, each timed alone (CUDA events around 20
         # back-to-back launches; inputs larger than L2 / the 600 MB optimizer state)
+        # (replayed from a CUDA graph: the Python wrappers cost more host time per call than the
+        # ~20 us kernels run, so an eager loop would time the launch rate, not the kernels)
         def loop_ms(fn, reps=20):
             for _ in range(3):
                 fn(0)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for r in range(reps):
-                fn(r)
-            e1.record()
+            try:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    for r in range(reps):
+                        fn(r)
+                graph.replay()
+                torch.cuda.synchronize()
+                e0.record()
+                graph.replay()
+                e1.record()
+            except Exception:
+                torch.cuda.synchronize()
+                e0.record()
+                for r in range(reps):
+                    fn(r)
+                e1.record()
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / reps
 
