@@ -482,3 +482,42 @@ def test_train_main_from_shard_and_teacher_pickles(tmp_path):
     for f in ('config.json', 'loss.json', 'best_epoch.encoder.pt', 'best_epoch.decoder.pt',
               'epoch0002.encoder.pt'):
         assert os.path.exists(os.path.join(str(tmp_path / 'run'), f)), f
+
+
+@pytest.mark.parametrize('arch,H,W,B', [('resnet18', 64, 64, 6), ('resnet34', 96, 160, 5)])
+def test_train_step_other_sizes_vs_oracle(arch, H, W, B):
+    """One training step away from the benchmarked shape (other image sizes, odd batches, the
+    other BasicBlock depth): raw uint8 batches through K1's stem-layout kernel, loss and updated
+    BN running statistics against the fp32 oracle, then `embed` on the oracle's updated weights. Exercises
+    the ReLU bit masks, the 256-wide weight-gradient blocks and the partial tiles of every
+    kernel on geometries the batch-256 tests do not have."""
+    from vpd_b200 import ModelTrainer
+    rgb, flow = synth.crops(B, seed=61, height=H, width=W)
+    teach = synth.teacher(B, seed=62, emb_dim=32, motion=True)
+    fl = synth.flips(B, seed=63)
+    img, tgt = assemble_ref.train_batch(rgb.numpy(), flow.numpy(), teach.numpy(), fl.numpy(),
+                                        *synth.FS_MEAN_STD)
+    m = _model(7, arch=arch)
+    tr = ModelTrainer(m, True)
+    opt, _ = tr.get_optimizer(5e-4)
+    torch.manual_seed(7)
+    otr = student_ref.OracleTrainer(student_ref.init_encoder_state(arch, 32, True),
+                                    student_ref.init_decoder_state(32), arch=arch)
+    batch = {'rgb_u8': rgb.to(dev()), 'flow_u8': flow.to(dev()), 'flip': fl.to(dev()),
+             'teacher': teach.to(dev()), 'rgb_mean_std': synth.FS_MEAN_STD}
+    loss = tr.epoch([batch], optimizer=opt)
+    ref = otr.step(img, tgt) / B
+    assert abs(loss - ref) <= 0.01 * abs(ref), (loss, ref)
+    sd = {k: v.float().cpu() for k, v in m.state_dict().items()}
+    for k in ('resnet.bn1.running_mean', 'resnet.layer2.0.bn1.running_var',
+              'resnet.layer4.0.downsample.1.running_mean'):
+        r = otr.sd[k].detach()
+        assert (sd[k] - r).norm() <= 0.05 * r.norm() + 1e-3, k
+    # forward at this geometry on identical weights: the oracle's updated state in our model
+    # (the two AdamW steps differ by the sign flips of a tiny batch's bf16 gradients)
+    osd = {k: v.detach().clone() for k, v in otr.sd.items()}
+    m.load_state_dict(osd)
+    got = m.embed(img.numpy())
+    want = student_ref.embed(osd, img, arch=arch)
+    cos = [_cos(torch.from_numpy(got[i]), torch.from_numpy(want[i])) for i in range(B)]
+    assert min(cos) >= 0.999, cos
