@@ -521,3 +521,30 @@ def test_train_step_other_sizes_vs_oracle(arch, H, W, B):
     want = student_ref.embed(osd, img, arch=arch)
     cos = [_cos(torch.from_numpy(got[i]), torch.from_numpy(want[i])) for i in range(B)]
     assert min(cos) >= 0.999, cos
+
+
+def test_pool_loader_raw_batches_equal_reference_format_batches():
+    """PoolLoader(raw=True) hands the draw itself to ModelTrainer.epoch (K1 straight into the
+    network layout); the same seed through the reference-format fp32 batches must give the
+    same training: an identical first loss (the two input paths round to the same bf16) and the
+    same curve after it."""
+    from vpd_b200 import ModelTrainer
+    from vpd_b200.train import PoolLoader
+    P, B = 96, 24
+    rgb, flow = synth.crops(P, seed=71)
+    teach = synth.teacher(P, seed=72, emb_dim=32, motion=True)
+    losses = []
+    for raw in (False, True):
+        m = _model(9)
+        tr = ModelTrainer(m, True)
+        opt, _ = tr.get_optimizer(5e-4)
+        ld = PoolLoader(rgb.to(dev()), flow.to(dev()), teach.to(dev()), synth.FS_MEAN_STD, B, 3 * B,
+                        seed=5, random_flip=True, raw=raw)
+        batches = list(ld)
+        assert ('index' in batches[0]) == raw
+        losses.append([tr.epoch([b], optimizer=opt) for b in batches])
+    # the first step sees bit-identical inputs and weights; afterwards the weights differ by the
+    # fp32 atomics of the weight-gradient kernels (order-dependent last bits)
+    assert losses[0][0] == losses[1][0], losses
+    for a, b in zip(losses[0][1:], losses[1][1:]):
+        assert abs(a - b) <= 1e-3 * abs(a), losses

@@ -326,7 +326,12 @@ class ModelTrainer:
         from .assemble import assemble_stem
         enc = self.encoder
         rgb, flow, flip, teacher = raw['rgb_u8'], raw.get('flow_u8'), raw.get('flip'), raw.get('teacher')
+        index = raw.get('index')          # frames = rows `index` of device-resident pools
         n, H, W, _ = rgb.shape
+        if index is not None:
+            if index.device != rgb.device or index.dtype != torch.int32:
+                raise ValueError("'index' must be an int32 tensor on the pools' device")
+            n = int(index.shape[0])
         if (flow is not None) != bool(enc.use_flow):
             raise AssertionError('Wrong number of channels for RGB' + (' + flow' if enc.use_flow else ''))
         ms = raw.get('rgb_mean_std', getattr(self, 'rgb_mean_std', None))
@@ -343,14 +348,14 @@ class ModelTrainer:
                 if teacher.shape[-1] != expect:
                     raise ValueError('target dim {} != {}'.format(teacher.shape[-1], expect))
                 tgt = self._tgt_buffer(n, expect)
-                assemble_stem(stem, rgb, flow, ms, flip=flip, teacher=teacher, tgt=tgt)
+                assemble_stem(stem, rgb, flow, ms, flip=flip, teacher=teacher, tgt=tgt, index=index)
             else:
                 if tgt.shape[1] != expect:
                     raise ValueError('target dim {} != {}'.format(tgt.shape[1], expect))
                 buf = self._tgt_buffer(n, expect)
                 buf.copy_(tgt, non_blocking=True)
                 tgt = buf
-                assemble_stem(stem, rgb, flow, ms, flip=flip)
+                assemble_stem(stem, rgb, flow, ms, flip=flip, index=index)
             self._overlapped = self._hook(net) if train else False
             if train:
                 lib().call('vpd_net_train_step', net.handle, None, stem, tgt, n, self._loss,
@@ -367,8 +372,10 @@ class ModelTrainer:
         'rgb_mean_std': ((m,m,m),(s,s,s)) (or set `trainer.rgb_mean_std`)}: 4x fewer bytes over
         PCIe than the fp32 batch; normalisation / stacking / flip run in the K1 kernel."""
         dev = self.encoder._dev
-        names = [k for k in ('rgb_u8', 'flow_u8', 'flip', 'emb', 'teacher') if batch.get(k) is not None]
+        names = [k for k in ('rgb_u8', 'flow_u8', 'flip', 'emb', 'teacher', 'index') if batch.get(k) is not None]
         extra = {k: batch[k] for k in ('rgb_mean_std',) if k in batch}
+        if batch.get('index') is not None and batch['rgb_u8'].device != dev:
+            raise ValueError("'index' batches gather from device-resident pools")
         if all(batch[k].device == dev for k in names):     # already resident: no staging ring
             raw = {k: batch[k] for k in names}
             raw.update(extra)
