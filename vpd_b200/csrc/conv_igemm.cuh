@@ -210,7 +210,8 @@ struct ConvCfg {
 template <int BLOCK_N, int CS, int MODE>
 VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t* tfull_bar,
                               uint64_t* tempty_bar, uint8_t* slabs, uint64_t* sfull,
-                              uint64_t* sempty, uint8_t* ring, uint64_t* zfull, int rank,
+                              uint64_t* sempty, float* s_scale, float* s_shift, uint8_t* ring,
+                              uint64_t* zfull, int rank,
                               int first_item, int item_stride, int total_tiles, int warp,
                               int lane) {
   using SC = StageCfg<BLOCK_N>;
@@ -233,6 +234,7 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
   uint32_t aphase = 0;
   int slot = 0;
   uint32_t sphase = 0;
+  int cached_ntile = -1;
   for (int tile = first_item; tile < total_tiles; tile += item_stride) {
     const TileCoord tc = decode_tile<CS>(p, tile, rank);
     const int n_tile = tc.n_tile;
@@ -248,6 +250,31 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
       for (int c = 0; c < 2 * SC::kSlabs; ++c)
         mw[c] = valid ? ldg_nc_u32(p.bmask + ((off + c * 32) >> 3)) : 0u;
     }
+    // the residual rows of the FIRST slab likewise (a row's residual may alias its output, but
+    // that is written by this tile's own store, after this read); later slabs load in place
+    const __nv_bfloat16* resp = MODE == 1 ? nullptr : p.residual;
+    const bool do_res = resp != nullptr && valid;
+    uint4 rpre[2][4];
+    if (do_res) {
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        const uint4* rp = reinterpret_cast<const uint4*>(resp + off + cc * 32);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rpre[cc][k] = rp[k];
+      }
+    }
+    // folded BatchNorm (eval): this channel block's scale / shift through shared memory (every
+    // thread of a warp reads the same 16 bytes: one broadcast instead of 16 global loads per
+    // chunk and thread)
+    if (MODE != 1 && p.scale != nullptr && n_tile != cached_ntile) {
+      asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");   // the old block is no longer read
+      for (int i = threadIdx.x - kEpiThread0; i < BLOCK_N; i += kEpiThreads) {
+        s_scale[i] = __ldg(p.scale + n_tile * BLOCK_N + i);
+        s_shift[i] = __ldg(p.shift + n_tile * BLOCK_N + i);
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(kEpiThreads) : "memory");
+      cached_ntile = n_tile;
+    }
     mbar_wait(&tfull_bar[as], aphase);
     if (tile == first_item && threadIdx.x == kEpiThread0) trace_mark(p, 5);
     tc_fence_after();
@@ -262,13 +289,16 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
         uint32_t v[32];
         tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c * 32, v);
         // training-forward kernels (MODE 1): a plain conversion
-        const __nv_bfloat16* resp = MODE == 1 ? nullptr : p.residual;
-        const bool do_res = resp != nullptr && valid;
         uint4 rres[4];
         if (do_res) {
-          const uint4* rp = reinterpret_cast<const uint4*>(resp + off + c * 32);
+          if (j == 0) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) rres[k] = rp[k];  // plain load: residual may alias out
+            for (int k = 0; k < 4; ++k) rres[k] = cc == 0 ? rpre[0][k] : rpre[1][k];
+          } else {
+            const uint4* rp = reinterpret_cast<const uint4*>(resp + off + c * 32);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rres[k] = rp[k];  // plain load: residual may alias out
+          }
         }
         tmem_ld_wait();
         float f[32];
@@ -276,10 +306,11 @@ VPD_DEVINL void conv_epilogue(const ConvParams& p, uint32_t tmem_base, uint64_t*
         for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
         const int ch0 = n_tile * BLOCK_N + c * 32;
         if (MODE != 1 && p.scale != nullptr) {
+          const uint32_t sc_a = smem_u32(s_scale + c * 32), sh_a = smem_u32(s_shift + c * 32);
 #pragma unroll
           for (int k = 0; k < 32; k += 4) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + ch0 + k));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + ch0 + k));
+            const float4 sc = __uint4_as_float4(lds_v4(sc_a + k * 4));
+            const float4 sh = __uint4_as_float4(lds_v4(sh_a + k * 4));
             f[k + 0] = fmaf(f[k + 0], sc.x, sh.x);
             f[k + 1] = fmaf(f[k + 1], sc.y, sh.y);
             f[k + 2] = fmaf(f[k + 2], sc.z, sh.z);
@@ -750,7 +781,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
     conv_epilogue<BLOCK_N, CS, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar,
-                                     sempty_bar, smem, zfull_bar, rank,
+                                     sempty_bar, s_sum, s_sq, smem, zfull_bar, rank,
                                      first_item, item_stride, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
@@ -981,7 +1012,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
     conv_epilogue<BLOCK_N, 1, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
-                              nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
+                              s_sum, s_sq, nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
    if (warp == 0) {
@@ -1156,7 +1187,7 @@ conv3x3_halo_stream_kernel(const __grid_constant__ CUtensorMap tmA,
   } else if (warp >= kEpiWarp0) {
     setmaxnreg_dec<kRegsEpi>();
     conv_epilogue<BLOCK_N, 1, MODE>(p, tmem_base, tfull_bar, tempty_bar, slabs, sfull_bar, sempty_bar,
-                              nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
+                              s_sum, s_sq, nullptr, nullptr, 0, blockIdx.x, gridDim.x, total_tiles, warp, lane);
   } else {
    setmaxnreg_dec<kRegsCtl>();
    if (warp == 0) {
