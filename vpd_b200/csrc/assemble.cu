@@ -221,6 +221,136 @@ assemble_nchw_kernel(const __grid_constant__ AsmParams p, const __grid_constant_
   }
 }
 
+// Reference layout, persistent version (no noise, 16-byte aligned rows, flow with 2 or 3 bytes
+// per pixel): the same bulk-copy pipeline as assemble_pad8_stream_kernel. A lane owns four
+// consecutive pixels: their 12 + 12 packed bytes are three + three aligned 32-bit shared-memory
+// loads, the RGB values are COMPUTED with the reference's own three correctly rounded fp32
+// operations (__fdiv_rn / __fsub_rn are IEEE, as on the CPU: bit-identical to the table), the
+// flow values (fp64 in the reference) come from two 256-entry tables, and a warp writes one
+// 512-byte row piece per plane. The one-CTA-per-unit kernel above did two shared-memory
+// loads per OUTPUT FLOAT and rebuilt five tables in each of its 1024 CTAs (0.29 of HBM).
+template <bool kFlow>
+__global__ void __launch_bounds__(kAsmThreads, 3)
+assemble_nchw_stream_kernel(const __grid_constant__ AsmParams p, const __grid_constant__ AsmLut tables) {
+  pdl_trigger();
+  extern __shared__ __align__(128) uint8_t sm[];
+  float* flut = reinterpret_cast<float*>(sm);                    // [2][256] flow tables
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + 2 * 256 * 4);
+  const int R = p.rows_per_cta;
+  const int rgb_bytes = R * p.W * 3, flow_bytes = kFlow ? R * p.W * p.fc : 0;
+  const int stage_bytes = (rgb_bytes + flow_bytes + 127) & ~127;
+  uint8_t* stage0 = sm + 2 * 256 * 4 + 128;
+  const int chunks = (p.H + R - 1) / R;
+  const int units = p.B * chunks;
+  const int C = kFlow ? 5 : 3;
+  // flow tables: a warp-uniform index into the constant-memory parameter (see the stem kernel)
+  for (int i0 = (threadIdx.x >> 5) * 4; kFlow && i0 < 2 * 256; i0 += (kAsmThreads / 32) * 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if ((threadIdx.x & 31) == 0) flut[i0 + k] = tables.v[3 * 256 + i0 + k];
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  auto issue = [&](int u, int st) {    // thread 0
+    const int b = u / chunks, h0 = (u - b * chunks) * R;
+    const int rows = min(R, p.H - h0);
+    const int src = p.index ? p.index[b] : b;
+    uint8_t* dst = stage0 + st * stage_bytes;
+    const uint32_t nr = rows * p.W * 3, nf = kFlow ? rows * p.W * p.fc : 0;
+    mbar_expect_tx(&bar[st], nr + nf);
+    bulk_load(dst, p.rgb + ((size_t)src * p.H + h0) * p.W * 3, nr, &bar[st]);
+    if (nf) bulk_load(dst + rgb_bytes, p.flow + ((size_t)src * p.H + h0) * p.W * p.fc, nf, &bar[st]);
+  };
+  int u = blockIdx.x;
+  if (threadIdx.x == 0 && u < units) issue(u, 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int groups = p.W >> 2;
+  const float m0 = p.mean[0], m1 = p.mean[1], m2 = p.mean[2];
+  const float d0 = p.stdv[0], d1 = p.stdv[1], d2 = p.stdv[2];
+  uint32_t phases = 0;
+  for (int it = 0; u < units; u += gridDim.x, ++it) {
+    const int st = it & 1;
+    if (threadIdx.x == 0 && u + (int)gridDim.x < units) issue(u + gridDim.x, st ^ 1);
+    const int b = u / chunks, h0 = (u - b * chunks) * R;
+    const int rows = min(R, p.H - h0);
+    if (h0 == 0 && p.teacher && p.out_tgt) {
+      const int src = p.index ? p.index[b] : b;
+      const int row = (p.teacher_rows > 1 && p.flip && p.flip[b]) ? 1 : 0;
+      const float* t = p.teacher + ((size_t)src * p.teacher_rows + row) * p.tdim;
+      for (int i = threadIdx.x; i < p.tdim; i += kAsmThreads) p.out_tgt[(size_t)b * p.tdim + i] = t[i];
+    }
+    const uint8_t* s_rgb = stage0 + st * stage_bytes;
+    const uint8_t* s_flow = s_rgb + rgb_bytes;
+    mbar_wait(&bar[st], (phases >> st) & 1u);
+    phases ^= 1u << st;
+    for (int v = 0; v < p.k; ++v) {
+      const bool fl = (p.k == 2) ? (v == 1) : (p.flip && p.flip[b]);
+      float* obase = p.out_img + ((size_t)b * p.k + v) * C * p.H * p.W;
+      for (int rr = warp; rr < rows; rr += kAsmThreads / 32) {
+        float* orow = obase + (size_t)(h0 + rr) * p.W;
+        for (int g = lane; g < groups; g += 32) {
+          const int sg = fl ? groups - 1 - g : g;      // source group (mirrored when flipped)
+          const uint32_t* pr = reinterpret_cast<const uint32_t*>(s_rgb + (rr * p.W + sg * 4) * 3);
+          const uint32_t w0 = pr[0], w1 = pr[1], w2 = pr[2];
+          // bytes of pixel i, channel c = byte 3 i + c of the 12
+          const uint32_t by[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
+                                   w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
+                                   w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+          float o[3][4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            o[0][i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(by[3 * i + 0]), 255.f), m0), d0);
+            o[1][i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(by[3 * i + 1]), 255.f), m1), d1);
+            o[2][i] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(by[3 * i + 2]), 255.f), m2), d2);
+          }
+          // (a flipped row also reverses the four pixels of the group)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            __stcs(reinterpret_cast<float4*>(orow + (size_t)c * p.H * p.W) + g,
+                   fl ? make_float4(o[c][3], o[c][2], o[c][1], o[c][0])
+                      : make_float4(o[c][0], o[c][1], o[c][2], o[c][3]));
+          if (kFlow) {
+            float fx[4], fy[4];
+            if (p.fc == 3) {
+              const uint32_t* pf = reinterpret_cast<const uint32_t*>(s_flow + (rr * p.W + sg * 4) * 3);
+              const uint32_t f0 = pf[0], f1 = pf[1], f2 = pf[2];
+              const uint32_t bx[4] = {f0 & 255u, f0 >> 24, (f1 >> 16) & 255u, (f2 >> 8) & 255u};
+              const uint32_t bz[4] = {(f0 >> 8) & 255u, f1 & 255u, f1 >> 24, (f2 >> 16) & 255u};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                fx[i] = flut[bx[i]];
+                fy[i] = flut[256 + bz[i]];
+              }
+            } else {   // fc == 2
+              const uint32_t* pf = reinterpret_cast<const uint32_t*>(s_flow + (rr * p.W + sg * 4) * 2);
+              const uint32_t f0 = pf[0], f1 = pf[1];
+              const uint32_t bx[4] = {f0 & 255u, (f0 >> 16) & 255u, f1 & 255u, (f1 >> 16) & 255u};
+              const uint32_t bz[4] = {(f0 >> 8) & 255u, f0 >> 24, (f1 >> 8) & 255u, f1 >> 24};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                fx[i] = flut[bx[i]];
+                fy[i] = flut[256 + bz[i]];
+              }
+            }
+            __stcs(reinterpret_cast<float4*>(orow + (size_t)3 * p.H * p.W) + g,
+                   fl ? make_float4(-fx[3], -fx[2], -fx[1], -fx[0])
+                      : make_float4(fx[0], fx[1], fx[2], fx[3]));
+            __stcs(reinterpret_cast<float4*>(orow + (size_t)4 * p.H * p.W) + g,
+                   fl ? make_float4(fy[3], fy[2], fy[1], fy[0])
+                      : make_float4(fy[0], fy[1], fy[2], fy[3]));
+          }
+        }
+      }
+    }
+    __syncthreads();   // the stage may be refilled
+  }
+}
+
 // Stem layout (common.cuh::stem_pixel_offset): the padded image, 8 channel slots per pixel
 // (5..7 zero), space-to-depth 2 x 4 cells. One 16-byte store per pixel. The border is
 // written here too, so the buffer needs no separate clearing.
@@ -561,14 +691,42 @@ int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
   p.out_tgt = out_tgt;
   if (set_noise(&p, nz)) return -1;
   p.rows_per_cta = H < 32 ? H : 32;
+  AsmLut tables;
+  host_lut(&tables, p.mean, p.stdv);
+  {   // persistent bulk-copy version (see assemble_nchw_stream_kernel for the conditions)
+    static const bool stream_on = getenv("VPD_K1_STREAM") == nullptr || getenv("VPD_K1_STREAM")[0] != '0';
+    const bool aligned = (W * 3) % 16 == 0 && ((uintptr_t)rgb % 16) == 0 && ((size_t)H * W * 3) % 16 == 0 &&
+                         (flow == nullptr || ((flow_channels == 2 || flow_channels == 3) &&
+                                              (W * flow_channels) % 16 == 0 && ((uintptr_t)flow % 16) == 0)) &&
+                         ((uintptr_t)out_img % 16) == 0;
+    const int R = p.rows_per_cta;
+    const int stage = (R * W * 3 + (flow ? R * W * flow_channels : 0) + 127) & ~127;
+    const int smem2 = 2 * 256 * 4 + 128 + 2 * stage + 128;
+    if (stream_on && aligned && p.mask == nullptr && smem2 <= 72 * 1024) {
+      static bool attr = false;
+      if (!attr) {
+        VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_nchw_stream_kernel<true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_nchw_stream_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+        attr = true;
+      }
+      const int units = B * ((H + R - 1) / R);
+      const int grid = units < 148 * 3 ? units : 148 * 3;
+      if (flow)
+        VPD_CHECK_CUDA(launch_kernel(assemble_nchw_stream_kernel<true>, dim3(grid), dim3(kAsmThreads), smem2, stream, p, tables));
+      else
+        VPD_CHECK_CUDA(launch_kernel(assemble_nchw_stream_kernel<false>, dim3(grid), dim3(kAsmThreads), smem2, stream, p, tables));
+      VPD_LAUNCHED(1);
+      return 0;
+    }
+  }
   const int smem = smem_for(p, p.rows_per_cta);
   VPD_REQUIRE(smem <= 200 * 1024, "assemble: image too wide (W=%d)", W);
   if (smem > 48 * 1024)
     VPD_CHECK_CUDA(cudaFuncSetAttribute(assemble_nchw_kernel,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int chunks = (H + p.rows_per_cta - 1) / p.rows_per_cta;
-  AsmLut tables;
-  host_lut(&tables, p.mean, p.stdv);
   VPD_CHECK_CUDA(launch_kernel(assemble_nchw_kernel, dim3(B * chunks), dim3(kAsmThreads), smem, stream, p, tables));
   VPD_LAUNCHED(1);
   return 0;
