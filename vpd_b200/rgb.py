@@ -289,7 +289,9 @@ class RGBF_EmbeddingModel:
     def embed(self, x):
         """models/rgb.py:72-86: ndarray/Tensor [C,H,W] or [N,C,H,W] -> np.float32 [N, emb_dim]."""
         if not isinstance(x, torch.Tensor):
-            x = torch.Tensor(x)
+            # the reference's torch.Tensor(x): float32 values; as_tensor shares a float32
+            # ndarray's memory instead of copying it first (10 MB at batch 32)
+            x = torch.as_tensor(x, dtype=torch.float32)
         x = x.to(self._dev)
         if len(x.shape) == 3:
             x = x.unsqueeze(0)
