@@ -63,8 +63,12 @@ inline FastDiv fd_make(uint32_t d) {
   f.s2 = l > 0 ? l - 1 : 0;
   return f;
 }
-VPD_DEVINL uint32_t fd_div(const FastDiv& f, uint32_t n) {
+__host__ __device__ __forceinline__ uint32_t fd_div(const FastDiv& f, uint32_t n) {
+#ifdef __CUDA_ARCH__
   const uint32_t t = __umulhi(f.m, n);
+#else
+  const uint32_t t = static_cast<uint32_t>((static_cast<uint64_t>(f.m) * n) >> 32);   // host: tests
+#endif
   return (t + ((n - t) >> f.s1)) >> f.s2;
 }
 
