@@ -69,6 +69,14 @@ VPD_API int vpd_assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_
                       const int32_t* index, const uint8_t* flip, const float* teacher,
                       int teacher_rows, int tdim, const float* mean, const float* std,
                       float* out_img, float* out_tgt, int B, int H, int W, int k, void* stream);
+/* Host only (no GPU, no stream): K1's lookup tables, lut[c*256 + u] = the reference's fp32
+ * value of byte u in channel c (c < 3: ((u/255) - mean[c]) / std[c] with three fp32 roundings,
+ * vpd_dataset/common.py:52-58; c = 3, 4: float32(u/255.0 - 0.5), common.py:61-69), and the
+ * constants of the stem-layout kernel's arithmetic path. Returns 1 when
+ * bf16(fmaf(u, scale[c], shift[c])) == bf16(lut[c*256 + u]) for all 5 x 256 entries (the kernel
+ * then computes instead of looking up), 0 when it keeps the tables. Value-returning, never fails. */
+VPD_API int vpd_assemble_tables(const float* mean, const float* std, float* lut, float* scale,
+                        float* shift);
 VPD_API int vpd_assemble_stem(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
                       const int32_t* index, const uint8_t* flip, const float* teacher,
                       int teacher_rows, int tdim, const float* mean, const float* std,

@@ -49,7 +49,7 @@ def parse_header(path=HEADER):
 
 
 # int-returning entry points whose result is a value, not a status code
-_VALUE_INT = {'vpd_abi_version', 'vpd_net_num_bn', 'vpd_net_num_tensors'}
+_VALUE_INT = {'vpd_abi_version', 'vpd_net_num_bn', 'vpd_net_num_tensors', 'vpd_assemble_tables'}
 
 
 class VpdError(RuntimeError):

@@ -25,6 +25,10 @@ int vpd_assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels
                        std, out_img, out_tgt, B, H, W, k, (cudaStream_t)stream);
 }
 
+int vpd_assemble_tables(const float* mean, const float* std, float* lut, float* scale, float* shift) {
+  return assemble_tables(mean, std, lut, scale, shift);
+}
+
 int vpd_assemble_stem(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
                       const int32_t* index, const uint8_t* flip, const float* teacher,
                       int teacher_rows, int tdim, const float* mean, const float* std,

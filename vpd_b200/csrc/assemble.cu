@@ -111,6 +111,17 @@ static void host_lut(AsmLut* lut, const float* mean, const float* stdv) {
     key[3 + i] = stdv[i];
   }
 }
+// Host-only view of the tables for tests (no GPU needed): the 5 x 256 fp32 entries and the
+// constants / verdict of the arithmetic path.
+int assemble_tables(const float* mean, const float* stdv, float* lut_out, float* sc_out,
+                    float* sh_out) {
+  AsmLut t;
+  host_lut(&t, mean, stdv);
+  if (lut_out) memcpy(lut_out, t.v, sizeof(t.v));
+  if (sc_out) memcpy(sc_out, t.sc, sizeof(t.sc));
+  if (sh_out) memcpy(sh_out, t.sh, sizeof(t.sh));
+  return t.arith_ok;
+}
 __device__ __forceinline__ void build_lut(float* lut, const AsmLut& src) {
   for (int i = threadIdx.x; i < 5 * 256; i += blockDim.x) lut[i] = src.v[i];
 }

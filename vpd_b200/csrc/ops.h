@@ -21,6 +21,10 @@ int assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels, co
                   const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
                   const float* mean, const float* stdv, float* out_img, float* out_tgt, int B,
                   int H, int W, int k, cudaStream_t stream, const AsmNoise* nz = nullptr);
+// host only: K1's 5 x 256 lookup tables and the verified constants of its arithmetic path
+// (returns 1 when fmaf(u, sc[c], sh[c]) reproduces every table entry in bf16)
+int assemble_tables(const float* mean, const float* stdv, float* lut_out, float* sc_out,
+                    float* sh_out);
 int assemble_pad8(const uint8_t* rgb, const uint8_t* flow, int flow_channels, const int* index,
                   const uint8_t* flip, const float* teacher, int teacher_rows, int tdim,
                   const float* mean, const float* stdv, __nv_bfloat16* out_pad, float* out_tgt,
