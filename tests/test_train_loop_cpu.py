@@ -110,3 +110,35 @@ def test_main_wires_targets_shard_rows_and_loaders(tmp_path, dataset):
         cfg = json.load(fp)
     assert cfg['emb_dim'] == 4 and cfg['use_flow'] is True and cfg['motion'] is False
     assert tr.saved == ['best_epoch', 'best_epoch', 'epoch0002']
+
+
+def test_pool_loader_raw_yields_the_draw_itself():
+    """PoolLoader(raw=True): index batches over the pools (no kernel call, so it runs anywhere);
+    flips only with two-row teachers and random_flip, the epoch length of the reference's
+    `_TrainDataset`, and the fallback to assembled batches when augmentation / mask noise is on."""
+    import torch
+    from vpd_b200.train import PoolLoader
+    P, B = 10, 4
+    rgb = torch.zeros((P, 8, 8, 3), dtype=torch.uint8)
+    flow = torch.zeros((P, 8, 8, 3), dtype=torch.uint8)
+    teach2 = torch.zeros((P, 2, 6))
+    ms = ((0.5, 0.5, 0.5), (0.2, 0.2, 0.2))
+    ld = PoolLoader(rgb, flow, teach2, ms, B, 10, seed=1, random_flip=True, raw=True)
+    batches = list(ld)
+    assert len(batches) == len(ld) == 3 and [b['index'].numel() for b in batches] == [4, 4, 2]
+    for b in batches:
+        assert b['index'].dtype == torch.int32 and int(b['index'].min()) >= 0 and int(b['index'].max()) < P
+        assert b['flip'].dtype == torch.uint8 and b['flip'].shape == b['index'].shape
+        assert b['rgb_u8'] is rgb and b['flow_u8'] is flow and b['teacher'] is teach2
+        assert b['rgb_mean_std'] == ms
+    # one-row teachers have no flipped counterpart; without random_flip nothing is flipped
+    assert all(b['flip'] is None for b in PoolLoader(rgb, flow, torch.zeros((P, 6)), ms, B, 8,
+                                                     random_flip=True, raw=True))
+    assert all(b['flip'] is None for b in PoolLoader(rgb, flow, teach2, ms, B, 8, raw=True))
+    # same seed, same draws as the reference-format loader would make
+    a = [b['index'].tolist() for b in PoolLoader(rgb, flow, teach2, ms, B, 10, seed=7, raw=True)]
+    c = [b['index'].tolist() for b in PoolLoader(rgb, flow, teach2, ms, B, 10, seed=7, raw=True)]
+    assert a == c
+    assert PoolLoader(rgb, flow, teach2, ms, B, 8, raw=True, augment=True).raw is False
+    assert PoolLoader(rgb, flow, teach2, ms, B, 8, raw=True,
+                      mask_u8=torch.zeros((P, 8, 8), dtype=torch.uint8)).raw is False
