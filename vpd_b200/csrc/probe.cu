@@ -46,9 +46,11 @@ umma_probe_kernel(const __nv_bfloat16* __restrict__ src, int rows, int row_start
   if (tid == 0) {
     const uint32_t a_addr = smem_u32(sA) + row_start * 128;
     uint64_t adesc = make_smem_desc(a_addr, 16, sbo_bytes);
-    if (base_offset_mode) adesc |= static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
+    if (base_offset_mode & 1) adesc |= static_cast<uint64_t>((a_addr >> 7) & 7) << 49;
     const uint64_t bdesc = make_smem_desc(smem_u32(sB), 16, 1024);
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+    // base_offset_mode bit 1: the A rows hold fp16 (a_format field = 0) while B stays bf16 - does
+    // kind::f16 take a different 16-bit format per operand?
+    const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0) & ~((base_offset_mode & 2) ? (1u << 7) : 0u);
     for (int k = 0; k < 4; ++k) umma_bf16(tmem, adesc + 2 * k, bdesc + 2 * k, idesc, k != 0);
     umma_commit(&bar);
   }
