@@ -15,7 +15,7 @@ typedef __nv_bfloat16 bf16;
 extern "C" {
 
 const char* vpd_last_error(void) { return get_error(); }
-int vpd_abi_version(void) { return 2; }
+int vpd_abi_version(void) { return 3; }   // 3: ReLU bit masks (vpd_bn_act_fwd, vpd_conv2d_dgrad_bnfused), vpd_relu_bitmask, vpd_assemble_tables
 
 int vpd_assemble_nchw(const uint8_t* rgb, const uint8_t* flow, int flow_channels,
                       const int32_t* index, const uint8_t* flip, const float* teacher,
